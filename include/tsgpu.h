@@ -1,0 +1,112 @@
+/* tsgpu.h - C ABI of the B200 (sm_100a) prover backend for the Twist & Shout hot path.
+ *
+ * This is the drop-in boundary: the entry points are what a Rust `cuda-sys` crate placed next to the
+ * reference crate (`twist-and-shout`, /root/reference) would bind with `extern "C"` (see INTEGRATION.md
+ * for the binding and for which reference function each call replaces).  Plain pointers and sizes
+ * only; no C++ or torch types.
+ *
+ * Data layout (reference types, unchanged - no conversion at the boundary):
+ *   tsgpu_fr  = ark_bn254::Fr  = [u64; 4] little-endian limbs holding a * 2^256 mod r   (src/utils.rs:14)
+ *   tsgpu_g1  = G1Projective   = Jacobian {x, y, z} over Fq, Montgomery limbs, identity z = 0 (src/utils.rs:17)
+ *   tsgpu_g1a = affine (x, y), Montgomery limbs, identity = all-zero
+ * Host buffers passed in are caller-owned and only read for the duration of the call; results are
+ * written before the call returns (calls are synchronous with respect to the host).
+ *
+ * Errors: every call returns 0 on success or one of the TSGPU_E_* codes, which map 1:1 onto the
+ * reference's TwistAndShoutError variants (src/lib.rs:59-78); tsgpu_last_error() returns the message
+ * (the reference's own strings where one exists).  Nothing unwinds across the boundary.
+ * There is no CPU fallback: without a CUDA device tsgpu_init fails with TSGPU_E_PROOF_GENERATION.
+ */
+#ifndef TSGPU_H
+#define TSGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSGPU_ABI_VERSION 1
+
+/* TwistAndShoutError variants, src/lib.rs:59-78 */
+#define TSGPU_OK 0
+#define TSGPU_E_INVALID_PARAMETERS 1
+#define TSGPU_E_PROOF_GENERATION 2
+#define TSGPU_E_PROOF_VERIFICATION 3
+#define TSGPU_E_COMMITMENT 4
+#define TSGPU_E_POLYNOMIAL 5
+#define TSGPU_E_SUMCHECK 6
+
+typedef struct { uint64_t l[4]; } tsgpu_fr;
+typedef struct { uint64_t x[4], y[4], z[4]; } tsgpu_g1;
+typedef struct { uint64_t x[4], y[4]; } tsgpu_g1a;
+
+typedef struct tsgpu_ctx tsgpu_ctx;       /* one GPU, one stream, scratch memory; not re-entrant */
+typedef struct tsgpu_table tsgpu_table;   /* an MLE evaluation table resident in HBM */
+typedef struct tsgpu_sc tsgpu_sc;         /* a sum-check prover instance (tables being folded) */
+typedef struct tsgpu_srs tsgpu_srs;       /* CommitmentParams.g1_powers resident in HBM (affine) */
+typedef struct tsgpu_poly tsgpu_poly;     /* a coefficient vector resident in HBM */
+
+int tsgpu_abi_version(void);
+
+/* ---- context ------------------------------------------------------------------------------------ */
+/* `stream` is a cudaStream_t the caller owns (e.g. torch's current stream) or NULL to create one. */
+int tsgpu_init(int device, void* stream, tsgpu_ctx** out);
+void tsgpu_destroy(tsgpu_ctx* ctx);
+const char* tsgpu_last_error(const tsgpu_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's `gpu_launches`) */
+uint64_t tsgpu_launch_count(const tsgpu_ctx* ctx);
+int tsgpu_synchronize(tsgpu_ctx* ctx);
+int tsgpu_sm_count(const tsgpu_ctx* ctx);
+
+/* ---- MLE tables: MultilinearExtension { num_vars, evaluations }  (src/polynomials.rs:18-82) ------ */
+/* from_evaluations / from_evaluations_vec: `n` host entries, zero-padded or truncated to 2^num_vars
+ * (polynomials.rs:40-50).  Uploaded once; lives in HBM until freed. */
+int tsgpu_table_upload(tsgpu_ctx* ctx, const tsgpu_fr* evals, size_t n, unsigned num_vars, tsgpu_table** out);
+/* evaluations back to the host in reference index order (2^num_vars entries) */
+int tsgpu_table_download(tsgpu_ctx* ctx, const tsgpu_table* t, tsgpu_fr* out);
+int tsgpu_table_clone(tsgpu_ctx* ctx, const tsgpu_table* t, tsgpu_table** out);
+unsigned tsgpu_table_num_vars(const tsgpu_table* t);
+void tsgpu_table_free(tsgpu_ctx* ctx, tsgpu_table* t);
+/* device-side generators for the tables the protocols are built from:
+ *   eq(w, .)[i] = prod_j (bit_j(i) ? w_j : 1 - w_j)      - the basis polynomial of polynomials.rs:108-122
+ *   one-hot matrix: entry [row * 2^log_k + idx[row]] = 1  - MultilinearExtension::one_hot (polynomials.rs:71-82) per row
+ *   from_u64: entry i = Fr::from(v[i])                    - twist.rs:119 / shout.rs:112 */
+int tsgpu_table_eq(tsgpu_ctx* ctx, const tsgpu_fr* w, unsigned num_vars, tsgpu_table** out);
+int tsgpu_table_one_hot_rows(tsgpu_ctx* ctx, const uint64_t* idx, size_t rows, unsigned log_k, unsigned num_vars, tsgpu_table** out);
+int tsgpu_table_from_u64(tsgpu_ctx* ctx, const uint64_t* v, size_t n, unsigned num_vars, tsgpu_table** out);
+
+/* ---- MultilinearExtension::evaluate / partial_evaluate  (src/polynomials.rs:85-161) -------------- */
+/* host-buffer forms (copy in, compute, copy out) */
+int tsgpu_mle_evaluate(tsgpu_ctx* ctx, const tsgpu_fr* evals, unsigned num_vars, const tsgpu_fr* point, tsgpu_fr* out);
+int tsgpu_mle_partial_evaluate(tsgpu_ctx* ctx, const tsgpu_fr* evals, unsigned num_vars, const tsgpu_fr* fixed, unsigned k, tsgpu_fr* out);
+/* HBM-resident forms */
+int tsgpu_table_evaluate(tsgpu_ctx* ctx, const tsgpu_table* t, const tsgpu_fr* point, tsgpu_fr* out);
+int tsgpu_table_partial_evaluate(tsgpu_ctx* ctx, const tsgpu_table* t, const tsgpu_fr* fixed, unsigned k, tsgpu_table** out);
+/* one fold: T'[i] = T[2i] + r (T[2i+1] - T[2i]) in place (num_vars decreases by one) */
+int tsgpu_table_bind(tsgpu_ctx* ctx, tsgpu_table* t, const tsgpu_fr* r);
+
+/* ---- sum-check prover round  (SumCheck::prove / compute_round_polynomial, src/sumcheck.rs:56-110,156-207)
+ * Structured sibling of the closure-typed SumCheck::prove for f(v) = prod_{t<d} mle_t.evaluate(v), d in 1..3.
+ * Round-stepped so the Fiat-Shamir transcript stays with the caller:
+ *     begin -> round_eval -> [transcript] -> bind_eval(r_0) -> [transcript] -> ... -> bind_eval(r_{n-2})
+ *           -> [transcript] -> final(r_{n-1})
+ * The tables are consumed (folded in place). */
+int tsgpu_sc_begin(tsgpu_ctx* ctx, tsgpu_table* const* tables, int d, tsgpu_sc** out);
+unsigned tsgpu_sc_num_vars(const tsgpu_sc* sc);   /* variables still unbound */
+/* g(0), g(1), g(2), g(3) of the current round (sumcheck.rs:175-198) */
+int tsgpu_sc_round_eval(tsgpu_sc* sc, tsgpu_fr evals[4]);
+/* bind the current variable to r (sumcheck.rs:99) */
+int tsgpu_sc_bind(tsgpu_sc* sc, const tsgpu_fr* r);
+/* fused: bind to r, then evaluate the next round's g(0..3) in the same pass */
+int tsgpu_sc_bind_eval(tsgpu_sc* sc, const tsgpu_fr* r, tsgpu_fr evals[4]);
+/* after all variables are bound: the d table values mle_t(r_0..r_{n-1}); their product is
+ * SumCheckProof.final_evaluation (sumcheck.rs:104) */
+int tsgpu_sc_final(tsgpu_sc* sc, tsgpu_fr* finals);
+void tsgpu_sc_end(tsgpu_sc* sc);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSGPU_H */

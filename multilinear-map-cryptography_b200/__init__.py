@@ -1,0 +1,10 @@
+"""B200 (sm_100a) prover backend for the Twist & Shout hot path.
+
+The directory name carries a hyphen, so import it with
+    importlib.import_module("multilinear-map-cryptography_b200")
+(tests/conftest.py and bench.py do exactly that).  Contents:
+    csrc/       CUDA kernels + the C ABI (include/tsgpu.h)  -> libtsgpu.so
+    host/       C++ host mirror of the reference API (Transcript, SumCheck, KZG, Twist, Shout)
+    binding.py  ctypes binding of libtsgpu.so - no CPU fallback
+"""
+from .binding import Context, Table, SumCheckRounds, TwistAndShoutError, LIB_PATH, lib  # noqa: F401

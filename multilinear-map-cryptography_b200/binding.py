@@ -1,0 +1,252 @@
+"""ctypes binding of libtsgpu.so (include/tsgpu.h) - the only way Python code reaches the CUDA path.
+
+There is deliberately no fallback: if the shared library is missing, or no CUDA device is present,
+the calls raise.  Numpy arrays carry the reference layouts unchanged:
+    Fr  : uint64[..., 4]   Montgomery limbs (ark_bn254::Fr)
+    G1  : uint64[..., 12]  Jacobian {x, y, z}
+    G1a : uint64[..., 8]   affine {x, y}
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtsgpu.so")
+
+# TwistAndShoutError variants (reference src/lib.rs:59-78)
+ERROR_NAMES = {1: "InvalidParameters", 2: "ProofGeneration", 3: "ProofVerification", 4: "Commitment",
+               5: "Polynomial", 6: "SumCheck"}
+
+
+class TwistAndShoutError(Exception):
+    """Mirror of the reference error enum: `.variant` is the Rust variant name, str() the message."""
+
+    def __init__(self, code: int, message: str):
+        self.code = code
+        self.variant = ERROR_NAMES.get(code, f"Unknown({code})")
+        super().__init__(f"{self.variant}: {message}")
+        self.message = message
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.tsgpu_last_error.restype = C.c_char_p
+        L.tsgpu_last_error.argtypes = [C.c_void_p]
+        L.tsgpu_launch_count.restype = C.c_uint64
+        L.tsgpu_launch_count.argtypes = [C.c_void_p]
+        L.tsgpu_table_num_vars.restype = C.c_uint
+        L.tsgpu_table_num_vars.argtypes = [C.c_void_p]
+        L.tsgpu_sc_num_vars.restype = C.c_uint
+        L.tsgpu_sc_num_vars.argtypes = [C.c_void_p]
+        L.tsgpu_destroy.argtypes = [C.c_void_p]
+        L.tsgpu_table_free.argtypes = [C.c_void_p, C.c_void_p]
+        L.tsgpu_sc_end.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _p(a: np.ndarray) -> C.c_void_p:
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _fr(a, n: Optional[int] = None) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
+    if n is not None and a.shape[0] != n:
+        raise ValueError(f"expected {n} field elements, got {a.shape[0]}")
+    return a
+
+
+class Context:
+    """tsgpu_ctx: one GPU + one stream.  `stream` may be a raw cudaStream_t (int) such as
+    torch.cuda.current_stream().cuda_stream so that torch events time the library's kernels."""
+
+    def __init__(self, device: int = 0, stream: Optional[int] = None):
+        self._h = C.c_void_p()
+        rc = lib().tsgpu_init(C.c_int(device), C.c_void_p(stream or 0), C.byref(self._h))
+        if rc:
+            raise TwistAndShoutError(rc, "tsgpu_init failed: no usable CUDA device (there is no CPU fallback)")
+        self.device = device
+
+    def close(self):
+        if self._h:
+            lib().tsgpu_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc: int):
+        if rc:
+            raise TwistAndShoutError(rc, lib().tsgpu_last_error(self._h).decode())
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().tsgpu_launch_count(self._h))
+
+    @property
+    def sm_count(self) -> int:
+        return int(lib().tsgpu_sm_count(self._h))
+
+    def synchronize(self):
+        self.check(lib().tsgpu_synchronize(self._h))
+
+    # ---- tables
+    def table_upload(self, evals, num_vars: Optional[int] = None) -> "Table":
+        evals = _fr(evals)
+        n = evals.shape[0]
+        if num_vars is None:
+            num_vars = max(n.bit_length() - 1, 0)
+            if n == 0 or (1 << num_vars) != n:
+                raise ValueError("Evaluation vector length must be a power of 2")   # polynomials.rs:30
+        h = C.c_void_p()
+        self.check(lib().tsgpu_table_upload(self._h, _p(evals), C.c_size_t(n), C.c_uint(num_vars), C.byref(h)))
+        return Table(self, h)
+
+    def table_eq(self, w) -> "Table":
+        w = _fr(w)
+        h = C.c_void_p()
+        self.check(lib().tsgpu_table_eq(self._h, _p(w), C.c_uint(w.shape[0]), C.byref(h)))
+        return Table(self, h)
+
+    def table_one_hot_rows(self, idx, log_k: int, num_vars: int) -> "Table":
+        idx = np.ascontiguousarray(idx, dtype=np.uint64).reshape(-1)
+        h = C.c_void_p()
+        self.check(lib().tsgpu_table_one_hot_rows(self._h, _p(idx), C.c_size_t(idx.shape[0]), C.c_uint(log_k),
+                                                  C.c_uint(num_vars), C.byref(h)))
+        return Table(self, h)
+
+    def table_from_u64(self, v, num_vars: int) -> "Table":
+        v = np.ascontiguousarray(v, dtype=np.uint64).reshape(-1)
+        h = C.c_void_p()
+        self.check(lib().tsgpu_table_from_u64(self._h, _p(v), C.c_size_t(v.shape[0]), C.c_uint(num_vars), C.byref(h)))
+        return Table(self, h)
+
+    # ---- host-buffer MLE calls
+    def mle_evaluate(self, evals, point) -> np.ndarray:
+        evals = _fr(evals); nv = evals.shape[0].bit_length() - 1
+        point = _fr(point, nv)
+        out = np.empty(4, dtype=np.uint64)
+        self.check(lib().tsgpu_mle_evaluate(self._h, _p(evals), C.c_uint(nv), _p(point), _p(out)))
+        return out
+
+    def mle_partial_evaluate(self, evals, fixed) -> np.ndarray:
+        evals = _fr(evals); nv = evals.shape[0].bit_length() - 1
+        fixed = _fr(fixed); k = fixed.shape[0]
+        out = np.empty((1 << max(nv - k, 0), 4), dtype=np.uint64)
+        self.check(lib().tsgpu_mle_partial_evaluate(self._h, _p(evals), C.c_uint(nv), _p(fixed), C.c_uint(k), _p(out)))
+        return out
+
+    def sumcheck(self, tables: Sequence["Table"]) -> "SumCheckRounds":
+        return SumCheckRounds(self, tables)
+
+
+class Table:
+    """tsgpu_table: MultilinearExtension.evaluations resident in HBM."""
+
+    def __init__(self, ctx: Context, handle: C.c_void_p):
+        self.ctx = ctx
+        self._h = handle
+
+    @property
+    def num_vars(self) -> int:
+        return int(lib().tsgpu_table_num_vars(self._h))
+
+    def download(self) -> np.ndarray:
+        out = np.empty((1 << self.num_vars, 4), dtype=np.uint64)
+        self.ctx.check(lib().tsgpu_table_download(self.ctx._h, self._h, _p(out)))
+        return out
+
+    def clone(self) -> "Table":
+        h = C.c_void_p()
+        self.ctx.check(lib().tsgpu_table_clone(self.ctx._h, self._h, C.byref(h)))
+        return Table(self.ctx, h)
+
+    def evaluate(self, point) -> np.ndarray:
+        point = _fr(point, self.num_vars)
+        out = np.empty(4, dtype=np.uint64)
+        self.ctx.check(lib().tsgpu_table_evaluate(self.ctx._h, self._h, _p(point), _p(out)))
+        return out
+
+    def partial_evaluate(self, fixed) -> "Table":
+        fixed = _fr(fixed)
+        h = C.c_void_p()
+        self.ctx.check(lib().tsgpu_table_partial_evaluate(self.ctx._h, self._h, _p(fixed), C.c_uint(fixed.shape[0]), C.byref(h)))
+        return Table(self.ctx, h)
+
+    def bind(self, r):
+        r = _fr(r, 1)
+        self.ctx.check(lib().tsgpu_table_bind(self.ctx._h, self._h, _p(r)))
+
+    def free(self):
+        if self._h:
+            lib().tsgpu_table_free(self.ctx._h, self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            if self.ctx._h:
+                self.free()
+        except Exception:
+            pass
+
+
+class SumCheckRounds:
+    """tsgpu_sc: round-stepped sum-check prover over a product of 1..3 tables (consumed)."""
+
+    def __init__(self, ctx: Context, tables: Sequence[Table]):
+        self.ctx = ctx
+        self.tables = list(tables)
+        arr = (C.c_void_p * len(self.tables))(*[t._h for t in self.tables])
+        self._h = C.c_void_p()
+        ctx.check(lib().tsgpu_sc_begin(ctx._h, arr, C.c_int(len(self.tables)), C.byref(self._h)))
+
+    @property
+    def vars_left(self) -> int:
+        return int(lib().tsgpu_sc_num_vars(self._h))
+
+    def round_eval(self) -> np.ndarray:
+        out = np.empty((4, 4), dtype=np.uint64)
+        self.ctx.check(lib().tsgpu_sc_round_eval(self._h, _p(out)))
+        return out
+
+    def bind(self, r):
+        r = _fr(r, 1)
+        self.ctx.check(lib().tsgpu_sc_bind(self._h, _p(r)))
+
+    def bind_eval(self, r) -> np.ndarray:
+        r = _fr(r, 1)
+        out = np.empty((4, 4), dtype=np.uint64)
+        self.ctx.check(lib().tsgpu_sc_bind_eval(self._h, _p(r), _p(out)))
+        return out
+
+    def final(self) -> np.ndarray:
+        out = np.empty((len(self.tables), 4), dtype=np.uint64)
+        self.ctx.check(lib().tsgpu_sc_final(self._h, _p(out)))
+        return out
+
+    def end(self):
+        if self._h:
+            lib().tsgpu_sc_end(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.end()
+        except Exception:
+            pass

@@ -1,0 +1,362 @@
+// api_core.cu - C ABI (include/tsgpu.h): context, MLE tables, evaluate / partial evaluate, sum-check rounds.
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include "context.cuh"
+#include "mle.cuh"
+#include "sumcheck.cuh"
+
+using namespace tsg;
+
+namespace tsg {
+
+int fail(tsgpu_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+int cuda_fail(tsgpu_ctx* ctx, cudaError_t e, const char* what) {
+    // CUDA failures surface as TwistAndShoutError::ProofGeneration
+    std::string m = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+    cudaGetLastError();
+    return fail(ctx, TSGPU_E_PROOF_GENERATION, m);
+}
+
+int table_alloc(tsgpu_ctx* ctx, unsigned num_vars, tsgpu_table** out) {
+    if (num_vars > 34) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "num_vars too large");
+    tsgpu_table* t = new (std::nothrow) tsgpu_table;
+    if (!t) return fail(ctx, TSGPU_E_PROOF_GENERATION, "out of host memory");
+    t->num_vars = num_vars;
+    t->capacity = (size_t)1 << num_vars;
+    cudaError_t e = cudaMallocAsync((void**)&t->d, t->capacity * sizeof(fr_t), ctx->stream);
+    if (e != cudaSuccess) { delete t; return cuda_fail(ctx, e, "cudaMallocAsync(table)"); }
+    *out = t;
+    return TSGPU_OK;
+}
+
+}  // namespace tsg
+
+static_assert(sizeof(fr_t) == 32 && sizeof(tsgpu_fr) == 32, "Fr element must be 32 bytes");
+
+static inline fr_t to_fr(const tsgpu_fr* p) { fr_t r; memcpy(r.l, p->l, 32); return r; }
+
+extern "C" {
+
+int tsgpu_abi_version(void) { return TSGPU_ABI_VERSION; }
+
+int tsgpu_init(int device, void* stream, tsgpu_ctx** out) {
+    if (!out) return TSGPU_E_INVALID_PARAMETERS;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0 || device < 0 || device >= count) {
+        cudaGetLastError();
+        return TSGPU_E_PROOF_GENERATION;   // no CUDA device: there is no CPU fallback
+    }
+    tsgpu_ctx* ctx = new (std::nothrow) tsgpu_ctx;
+    if (!ctx) return TSGPU_E_PROOF_GENERATION;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return TSGPU_E_PROOF_GENERATION; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return TSGPU_E_PROOF_GENERATION; }
+    ctx->sm_count = prop.multiProcessorCount;
+    if (stream) { ctx->stream = (cudaStream_t)stream; ctx->own_stream = false; }
+    else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return TSGPU_E_PROOF_GENERATION; }
+        ctx->own_stream = true;
+    }
+    // keep freed stream-ordered allocations cached in the pool instead of returning them to the OS
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thresh = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
+    }
+    size_t np = (size_t)sc_max_grid(ctx->sm_count) * 4 + 64;
+    bool ok = cudaMalloc((void**)&ctx->partials, np * sizeof(fr_t)) == cudaSuccess &&
+              cudaMalloc((void**)&ctx->ticket, 64) == cudaSuccess &&
+              cudaMalloc((void**)&ctx->dev_out, 8 * sizeof(fr_t)) == cudaSuccess &&
+              cudaMallocHost((void**)&ctx->host_out, 8 * sizeof(fr_t)) == cudaSuccess &&
+              cudaMemset(ctx->ticket, 0, 64) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); tsgpu_destroy(ctx); return TSGPU_E_PROOF_GENERATION; }
+    *out = ctx;
+    return TSGPU_OK;
+}
+
+void tsgpu_destroy(tsgpu_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->partials) cudaFree(ctx->partials);
+    if (ctx->ticket) cudaFree(ctx->ticket);
+    if (ctx->dev_out) cudaFree(ctx->dev_out);
+    if (ctx->host_out) cudaFreeHost(ctx->host_out);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* tsgpu_last_error(const tsgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+uint64_t tsgpu_launch_count(const tsgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int tsgpu_sm_count(const tsgpu_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+int tsgpu_synchronize(tsgpu_ctx* ctx) {
+    TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return TSGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------- tables
+int tsgpu_table_upload(tsgpu_ctx* ctx, const tsgpu_fr* evals, size_t n, unsigned num_vars, tsgpu_table** out) {
+    if (!ctx || !out || (!evals && n)) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    tsgpu_table* t = nullptr;
+    int rc = table_alloc(ctx, num_vars, &t);
+    if (rc) return rc;
+    size_t size = (size_t)1 << num_vars;
+    size_t take = n < size ? n : size;   // from_evaluations_vec pads with zeros or truncates (polynomials.rs:40-50)
+    TempBuf tmp;
+    TSG_CUDA(ctx, tmp.alloc(size * sizeof(fr_t), ctx->stream));
+    if (take < size) TSG_CUDA(ctx, cudaMemsetAsync(tmp.as<fr_t>() + take, 0, (size - take) * sizeof(fr_t), ctx->stream));
+    if (take) TSG_CUDA(ctx, cudaMemcpyAsync(tmp.p, evals, take * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+    TSG_CUDA(ctx, launch_bitrev_permute(tmp.as<fr_t>(), t->d, num_vars, ctx->sm_count, ctx->stream));
+    ctx->launches += 1;
+    TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // host buffer is only borrowed for the call
+    *out = t;
+    return TSGPU_OK;
+}
+
+int tsgpu_table_download(tsgpu_ctx* ctx, const tsgpu_table* t, tsgpu_fr* outp) {
+    if (!ctx || !t || !outp) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    size_t size = (size_t)1 << t->num_vars;
+    TempBuf tmp;
+    TSG_CUDA(ctx, tmp.alloc(size * sizeof(fr_t), ctx->stream));
+    TSG_CUDA(ctx, launch_bitrev_permute(t->d, tmp.as<fr_t>(), t->num_vars, ctx->sm_count, ctx->stream));
+    ctx->launches += 1;
+    TSG_CUDA(ctx, cudaMemcpyAsync(outp, tmp.p, size * sizeof(fr_t), cudaMemcpyDeviceToHost, ctx->stream));
+    TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return TSGPU_OK;
+}
+
+int tsgpu_table_clone(tsgpu_ctx* ctx, const tsgpu_table* t, tsgpu_table** out) {
+    if (!ctx || !t || !out) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    tsgpu_table* c = nullptr;
+    int rc = table_alloc(ctx, t->num_vars, &c);
+    if (rc) return rc;
+    TSG_CUDA(ctx, cudaMemcpyAsync(c->d, t->d, ((size_t)1 << t->num_vars) * sizeof(fr_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    *out = c;
+    return TSGPU_OK;
+}
+
+unsigned tsgpu_table_num_vars(const tsgpu_table* t) { return t ? t->num_vars : 0; }
+
+void tsgpu_table_free(tsgpu_ctx* ctx, tsgpu_table* t) {
+    if (!t) return;
+    if (t->d) cudaFreeAsync(t->d, ctx ? ctx->stream : nullptr);
+    delete t;
+}
+
+int tsgpu_table_eq(tsgpu_ctx* ctx, const tsgpu_fr* w, unsigned num_vars, tsgpu_table** out) {
+    if (!ctx || !out || (!w && num_vars)) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    tsgpu_table* t = nullptr;
+    int rc = table_alloc(ctx, num_vars, &t);
+    if (rc) return rc;
+    TempBuf wd;
+    TSG_CUDA(ctx, wd.alloc((num_vars + 1) * sizeof(fr_t), ctx->stream));
+    if (num_vars) TSG_CUDA(ctx, cudaMemcpyAsync(wd.p, w, num_vars * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+    TSG_CUDA(ctx, launch_eq_table_bitrev(wd.as<fr_t>(), num_vars, t->d, ctx->sm_count, ctx->stream));
+    ctx->launches += 1;
+    TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = t;
+    return TSGPU_OK;
+}
+
+int tsgpu_table_one_hot_rows(tsgpu_ctx* ctx, const uint64_t* idx, size_t rows, unsigned log_k, unsigned num_vars, tsgpu_table** out) {
+    if (!ctx || !out || (!idx && rows)) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    if (log_k > num_vars || rows > ((size_t)1 << (num_vars - log_k)))
+        return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "one-hot rows exceed table size");
+    tsgpu_table* t = nullptr;
+    int rc = table_alloc(ctx, num_vars, &t);
+    if (rc) return rc;
+    TSG_CUDA(ctx, cudaMemsetAsync(t->d, 0, ((size_t)1 << num_vars) * sizeof(fr_t), ctx->stream));
+    TempBuf id;
+    TSG_CUDA(ctx, id.alloc(rows * 8, ctx->stream));
+    if (rows) {
+        TSG_CUDA(ctx, cudaMemcpyAsync(id.p, idx, rows * 8, cudaMemcpyHostToDevice, ctx->stream));
+        TSG_CUDA(ctx, launch_one_hot_scatter(id.as<unsigned long long>(), rows, log_k, num_vars, t->d, ctx->sm_count, ctx->stream));
+        ctx->launches += 1;
+    }
+    TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = t;
+    return TSGPU_OK;
+}
+
+int tsgpu_table_from_u64(tsgpu_ctx* ctx, const uint64_t* v, size_t n, unsigned num_vars, tsgpu_table** out) {
+    if (!ctx || !out || (!v && n)) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    tsgpu_table* t = nullptr;
+    int rc = table_alloc(ctx, num_vars, &t);
+    if (rc) return rc;
+    size_t size = (size_t)1 << num_vars;
+    size_t take = n < size ? n : size;
+    TSG_CUDA(ctx, cudaMemsetAsync(t->d, 0, size * sizeof(fr_t), ctx->stream));
+    TempBuf src;
+    TSG_CUDA(ctx, src.alloc(take * 8, ctx->stream));
+    if (take) {
+        TSG_CUDA(ctx, cudaMemcpyAsync(src.p, v, take * 8, cudaMemcpyHostToDevice, ctx->stream));
+        TSG_CUDA(ctx, launch_fr_from_u64(src.as<unsigned long long>(), take, t->d, num_vars, 1, ctx->sm_count, ctx->stream));
+        ctx->launches += 1;
+    }
+    TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = t;
+    return TSGPU_OK;
+}
+
+// ------------------------------------------------------------------------------- evaluate / partial
+static int read_result(tsgpu_ctx* ctx, int count, tsgpu_fr* out) {
+    TSG_CUDA(ctx, cudaMemcpyAsync(ctx->host_out, ctx->dev_out, count * sizeof(fr_t), cudaMemcpyDeviceToHost, ctx->stream));
+    TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(out, ctx->host_out, count * sizeof(fr_t));
+    return TSGPU_OK;
+}
+
+int tsgpu_table_partial_evaluate(tsgpu_ctx* ctx, const tsgpu_table* t, const tsgpu_fr* fixed, unsigned k, tsgpu_table** out) {
+    if (!ctx || !t || !out || (!fixed && k)) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    if (k > t->num_vars) return fail(ctx, TSGPU_E_POLYNOMIAL, "Cannot fix more variables than available");   // polynomials.rs:128
+    if (k == 0) return tsgpu_table_clone(ctx, t, out);   // polynomials.rs:130-132
+    tsgpu_table* o = nullptr;
+    int rc = table_alloc(ctx, t->num_vars - k, &o);
+    if (rc) return rc;
+    size_t rows = (size_t)1 << k, cols = (size_t)1 << (t->num_vars - k);
+    TempBuf fx, W, part;
+    TSG_CUDA(ctx, fx.alloc(k * sizeof(fr_t), ctx->stream));
+    TSG_CUDA(ctx, W.alloc(rows * sizeof(fr_t), ctx->stream));
+    TSG_CUDA(ctx, cudaMemcpyAsync(fx.p, fixed, k * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+    TSG_CUDA(ctx, launch_eq_table_bitrev(fx.as<fr_t>(), k, W.as<fr_t>(), ctx->sm_count, ctx->stream));
+    size_t nsplit = colsum_splits(rows, cols, ctx->sm_count);
+    TSG_CUDA(ctx, part.alloc(nsplit > 1 ? nsplit * cols * sizeof(fr_t) : 32, ctx->stream));
+    TSG_CUDA(ctx, launch_colsum(t->d, W.as<fr_t>(), rows, cols, nsplit, part.as<fr_t>(), o->d, ctx->stream));
+    ctx->launches += 2 + (nsplit > 1 ? 1 : 0);
+    TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // `fixed` is borrowed
+    *out = o;
+    return TSGPU_OK;
+}
+
+int tsgpu_table_evaluate(tsgpu_ctx* ctx, const tsgpu_table* t, const tsgpu_fr* point, tsgpu_fr* out) {
+    if (!ctx || !t || !out || (!point && t->num_vars)) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    const unsigned nv = t->num_vars;
+    const unsigned l = nv < 16 ? nv : 16, h = nv - l;
+    size_t rows = (size_t)1 << h, cols = (size_t)1 << l;
+    TempBuf pt, Whi, Wlo, colv, part;
+    TSG_CUDA(ctx, pt.alloc((nv + 1) * sizeof(fr_t), ctx->stream));
+    if (nv) TSG_CUDA(ctx, cudaMemcpyAsync(pt.p, point, nv * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+    TSG_CUDA(ctx, Wlo.alloc(cols * sizeof(fr_t), ctx->stream));
+    TSG_CUDA(ctx, launch_eq_table_bitrev(pt.as<fr_t>() + h, l, Wlo.as<fr_t>(), ctx->sm_count, ctx->stream));
+    ctx->launches += 1;
+    const fr_t* vec = t->d;
+    if (h) {
+        TSG_CUDA(ctx, Whi.alloc(rows * sizeof(fr_t), ctx->stream));
+        TSG_CUDA(ctx, colv.alloc(cols * sizeof(fr_t), ctx->stream));
+        TSG_CUDA(ctx, launch_eq_table_bitrev(pt.as<fr_t>(), h, Whi.as<fr_t>(), ctx->sm_count, ctx->stream));
+        size_t nsplit = colsum_splits(rows, cols, ctx->sm_count);
+        TSG_CUDA(ctx, part.alloc(nsplit > 1 ? nsplit * cols * sizeof(fr_t) : 32, ctx->stream));
+        TSG_CUDA(ctx, launch_colsum(t->d, Whi.as<fr_t>(), rows, cols, nsplit, part.as<fr_t>(), colv.as<fr_t>(), ctx->stream));
+        ctx->launches += 2 + (nsplit > 1 ? 1 : 0);
+        vec = colv.as<fr_t>();
+    }
+    TSG_CUDA(ctx, launch_dot(vec, Wlo.as<fr_t>(), cols, ctx->partials, ctx->ticket, ctx->dev_out, ctx->sm_count, ctx->stream));
+    ctx->launches += 1;
+    return read_result(ctx, 1, out);
+}
+
+int tsgpu_table_bind(tsgpu_ctx* ctx, tsgpu_table* t, const tsgpu_fr* r) {
+    if (!ctx || !t || !r) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    if (t->num_vars == 0) return fail(ctx, TSGPU_E_POLYNOMIAL, "Cannot fix more variables than available");
+    TSG_CUDA(ctx, launch_bind(t->d, (size_t)1 << t->num_vars, to_fr(r), ctx->sm_count, ctx->stream));
+    ctx->launches += 1;
+    t->num_vars -= 1;
+    return TSGPU_OK;
+}
+
+int tsgpu_mle_evaluate(tsgpu_ctx* ctx, const tsgpu_fr* evals, unsigned num_vars, const tsgpu_fr* point, tsgpu_fr* out) {
+    tsgpu_table* t = nullptr;
+    int rc = tsgpu_table_upload(ctx, evals, (size_t)1 << num_vars, num_vars, &t);
+    if (rc) return rc;
+    rc = tsgpu_table_evaluate(ctx, t, point, out);
+    tsgpu_table_free(ctx, t);
+    return rc;
+}
+
+int tsgpu_mle_partial_evaluate(tsgpu_ctx* ctx, const tsgpu_fr* evals, unsigned num_vars, const tsgpu_fr* fixed, unsigned k, tsgpu_fr* out) {
+    if (k > num_vars) return fail(ctx, TSGPU_E_POLYNOMIAL, "Cannot fix more variables than available");
+    tsgpu_table *t = nullptr, *o = nullptr;
+    int rc = tsgpu_table_upload(ctx, evals, (size_t)1 << num_vars, num_vars, &t);
+    if (rc) return rc;
+    rc = tsgpu_table_partial_evaluate(ctx, t, fixed, k, &o);
+    if (!rc) rc = tsgpu_table_download(ctx, o, out);
+    tsgpu_table_free(ctx, t);
+    tsgpu_table_free(ctx, o);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------- sum-check
+int tsgpu_sc_begin(tsgpu_ctx* ctx, tsgpu_table* const* tables, int d, tsgpu_sc** out) {
+    if (!ctx || !tables || !out) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    if (d < 1 || d > SC_MAX_TABLES) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "sum-check supports products of 1..3 tables");
+    for (int i = 0; i < d; ++i) {
+        if (!tables[i]) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null table");
+        if (tables[i]->num_vars != tables[0]->num_vars) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "Number of variables must match");
+    }
+    tsgpu_sc* sc = new (std::nothrow) tsgpu_sc;
+    if (!sc) return fail(ctx, TSGPU_E_PROOF_GENERATION, "out of host memory");
+    sc->ctx = ctx; sc->d = d; sc->vars_left = tables[0]->num_vars;
+    for (int i = 0; i < d; ++i) sc->tables[i] = tables[i];
+    *out = sc;
+    return TSGPU_OK;
+}
+
+unsigned tsgpu_sc_num_vars(const tsgpu_sc* sc) { return sc ? sc->vars_left : 0; }
+
+static ScTables sc_tabs(const tsgpu_sc* sc) {
+    ScTables t; for (int i = 0; i < SC_MAX_TABLES; ++i) t.t[i] = i < sc->d ? sc->tables[i]->d : nullptr;
+    return t;
+}
+
+int tsgpu_sc_round_eval(tsgpu_sc* sc, tsgpu_fr evals[4]) {
+    if (!sc || !evals) return TSGPU_E_INVALID_PARAMETERS;
+    tsgpu_ctx* ctx = sc->ctx;
+    if (sc->vars_left == 0) return fail(ctx, TSGPU_E_SUMCHECK, "no variables left to evaluate");
+    TSG_CUDA(ctx, launch_round_eval(sc->d, sc_tabs(sc), (size_t)1 << sc->vars_left, ctx->partials, ctx->ticket, ctx->dev_out, ctx->sm_count, ctx->stream));
+    ctx->launches += 1;
+    return read_result(ctx, 4, evals);
+}
+
+int tsgpu_sc_bind(tsgpu_sc* sc, const tsgpu_fr* r) {
+    if (!sc || !r) return TSGPU_E_INVALID_PARAMETERS;
+    tsgpu_ctx* ctx = sc->ctx;
+    if (sc->vars_left == 0) return fail(ctx, TSGPU_E_SUMCHECK, "no variables left to bind");
+    for (int i = 0; i < sc->d; ++i) {
+        TSG_CUDA(ctx, launch_bind(sc->tables[i]->d, (size_t)1 << sc->vars_left, to_fr(r), ctx->sm_count, ctx->stream));
+        ctx->launches += 1;
+        sc->tables[i]->num_vars -= 1;
+    }
+    sc->vars_left -= 1;
+    return TSGPU_OK;
+}
+
+int tsgpu_sc_bind_eval(tsgpu_sc* sc, const tsgpu_fr* r, tsgpu_fr evals[4]) {
+    if (!sc || !r || !evals) return TSGPU_E_INVALID_PARAMETERS;
+    tsgpu_ctx* ctx = sc->ctx;
+    if (sc->vars_left < 2) return fail(ctx, TSGPU_E_SUMCHECK, "bind_eval needs at least two unbound variables");
+    TSG_CUDA(ctx, launch_bind_eval(sc->d, sc_tabs(sc), (size_t)1 << sc->vars_left, to_fr(r), ctx->partials, ctx->ticket, ctx->dev_out, ctx->sm_count, ctx->stream));
+    ctx->launches += 1;
+    for (int i = 0; i < sc->d; ++i) sc->tables[i]->num_vars -= 1;
+    sc->vars_left -= 1;
+    return read_result(ctx, 4, evals);
+}
+
+int tsgpu_sc_final(tsgpu_sc* sc, tsgpu_fr* finals) {
+    if (!sc || !finals) return TSGPU_E_INVALID_PARAMETERS;
+    tsgpu_ctx* ctx = sc->ctx;
+    if (sc->vars_left != 0) return fail(ctx, TSGPU_E_SUMCHECK, "variables remain unbound");
+    for (int i = 0; i < sc->d; ++i)
+        TSG_CUDA(ctx, cudaMemcpyAsync(ctx->dev_out + i, sc->tables[i]->d, sizeof(fr_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    return read_result(ctx, sc->d, finals);
+}
+
+void tsgpu_sc_end(tsgpu_sc* sc) { delete sc; }
+
+}  // extern "C"

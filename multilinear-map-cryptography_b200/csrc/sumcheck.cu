@@ -1,0 +1,196 @@
+// sumcheck.cu - sum-check prover round kernels over BN254 Fr tables resident in HBM.
+//
+// Replaces the reference's closure-driven round (SumCheck::compute_round_polynomial,
+// src/sumcheck.rs:156-207, which re-evaluates whole MLEs via src/polynomials.rs:85-122 for each of
+// 4 * 2^remaining points) by the table form: round k pairs the entries that differ in variable k,
+// g(X) = sum_pairs prod_t (lo_t + X (hi_t - lo_t)) at X = 0..3, then binds
+// T'[.] = lo + r (hi - lo) (what MultilinearExtension::partial_evaluate computes, polynomials.rs:126-161).
+// The values are exact field elements, so they equal the reference's.
+//
+// HBM layout: a table of 2^n entries is stored in BIT-REVERSED index order (entry with reference
+// index i lives at position bitrev_n(i)); 32 bytes per entry, reference Montgomery limbs.  Variable k
+// (bit k of the reference index, polynomials.rs:111-118) is then the TOP bit of the position in round
+// k, so a round streams two (bind) or four (fused bind + next-round evaluation) perfectly contiguous
+// ranges with one 256-bit load per entry per thread, and the bound table is written in place to the
+// low half - again contiguous.  Algorithmic bytes: evaluation 32 d N_k, bind 48 d N_k.
+#include "fr_device.cuh"
+#include "sumcheck.cuh"
+
+namespace tsg {
+
+// ---------------------------------------------------------------- per-pair evaluation contributions
+template <int D> struct EvalAcc;
+
+// d = 1: g is linear; only g(0), g(1) are accumulated, g(2), g(3) follow by extrapolation.
+template <> struct EvalAcc<1> {
+    static constexpr int NV = 2;
+    fr_t e0, e1;
+    __device__ __forceinline__ void clear() { e0 = fr_t::zero(); e1 = fr_t::zero(); }
+    __device__ __forceinline__ void pair(const fr_t* lo, const fr_t* hi) { e0 = e0 + lo[0]; e1 = e1 + hi[0]; }
+    __device__ __forceinline__ void finish(fr_t (&v)[NV]) { v[0] = e0; v[1] = e1; }
+    __device__ static void expand(const fr_t (&v)[NV], fr_t* out4) {
+        out4[0] = v[0]; out4[1] = v[1];
+        fr_t d = v[1] - v[0];
+        out4[2] = v[1] + d; out4[3] = out4[2] + d;
+    }
+};
+
+// d = 2: g is quadratic; g(0), g(1), g(2) as lazily reduced 512-bit dot products, g(3) = g0 - 3 g1 + 3 g2.
+template <> struct EvalAcc<2> {
+    static constexpr int NV = 3;
+    wide_acc<FrP> a0, a1, a2;
+    __device__ __forceinline__ void clear() { a0.clear(); a1.clear(); a2.clear(); }
+    __device__ __forceinline__ void pair(const fr_t* lo, const fr_t* hi) {
+        a0.add_product(lo[0], lo[1]);
+        a1.add_product(hi[0], hi[1]);
+        fr_t x = hi[0] + (hi[0] - lo[0]);
+        fr_t y = hi[1] + (hi[1] - lo[1]);
+        a2.add_product(x, y);
+    }
+    __device__ __forceinline__ void finish(fr_t (&v)[NV]) { v[0] = a0.reduce(); v[1] = a1.reduce(); v[2] = a2.reduce(); }
+    __device__ static void expand(const fr_t (&v)[NV], fr_t* out4) {
+        out4[0] = v[0]; out4[1] = v[1]; out4[2] = v[2];
+        fr_t d = v[2] - v[1];
+        out4[3] = v[0] + d + d + d;
+    }
+};
+
+// d = 3: cubic; all four points, one Montgomery product + one lazy product per point.
+template <> struct EvalAcc<3> {
+    static constexpr int NV = 4;
+    wide_acc<FrP> a[4];
+    __device__ __forceinline__ void clear() { for (int i = 0; i < 4; ++i) a[i].clear(); }
+    __device__ __forceinline__ void pair(const fr_t* lo, const fr_t* hi) {
+        fr_t v0 = lo[0], v1 = lo[1], v2 = lo[2];
+        fr_t d0 = hi[0] - lo[0], d1 = hi[1] - lo[1], d2 = hi[2] - lo[2];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            a[x].add_product(v0 * v1, v2);
+            v0 = v0 + d0; v1 = v1 + d1; v2 = v2 + d2;
+        }
+    }
+    __device__ __forceinline__ void finish(fr_t (&v)[NV]) { for (int i = 0; i < 4; ++i) v[i] = a[i].reduce(); }
+    __device__ static void expand(const fr_t (&v)[NV], fr_t* out4) { for (int i = 0; i < 4; ++i) out4[i] = v[i]; }
+};
+
+template <int D>
+struct EvalEpilogue {
+    fr_t* out4;
+    __device__ void operator()(fr_t (&v)[EvalAcc<D>::NV]) const {
+        fr_t o[4];
+        EvalAcc<D>::expand(v, o);
+        for (int i = 0; i < 4; ++i) out4[i] = o[i];
+    }
+};
+
+// ---------------------------------------------------------------- K2: round evaluation
+template <int D>
+__global__ void __launch_bounds__(SC_THREADS, (D <= 2 ? 2 : 1)) k_round_eval(ScTables tabs, size_t half, fr_t* partials, unsigned int* ticket, fr_t* out4) {
+    __shared__ fr_t smem[EvalAcc<D>::NV * 32];
+    EvalAcc<D> acc; acc.clear();
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < half; p += stride) {
+        fr_t lo[D], hi[D];
+#pragma unroll
+        for (int t = 0; t < D; ++t) { lo[t] = ld256_stream(tabs.t[t] + p); hi[t] = ld256_stream(tabs.t[t] + p + half); }
+        acc.pair(lo, hi);
+    }
+    fr_t v[EvalAcc<D>::NV];
+    acc.finish(v);
+    grid_finish_sum<fr_t, EvalAcc<D>::NV>(v, partials, ticket, smem, EvalEpilogue<D>{out4});
+}
+
+// ---------------------------------------------------------------- K1: bind (fold) one table in place
+__global__ void __launch_bounds__(SC_THREADS) k_bind(fr_t* t, size_t half, const fr_t r) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < half; p += stride) {
+        fr_t lo = ld256_stream(t + p), hi = ld256_stream(t + p + half);
+        st256(t + p, lo + r * (hi - lo));
+    }
+}
+// out-of-place variant (keeps the source table intact; used by partial_evaluate on borrowed tables)
+__global__ void __launch_bounds__(SC_THREADS) k_bind_to(const fr_t* t, fr_t* out, size_t half, const fr_t r) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < half; p += stride) {
+        fr_t lo = ld256_nc(t + p), hi = ld256_nc(t + p + half);
+        st256(out + p, lo + r * (hi - lo));
+    }
+}
+
+// ---------------------------------------------------------------- K3: fused bind(r_k) + evaluate(round k+1)
+// Thread p < quarter owns positions p, p+q, p+2q, p+3q of each table: top position bit = variable k
+// (bound now), next bit = variable k+1 (evaluated now).  Writes the bound table to positions [0, 2q).
+template <int D>
+__global__ void __launch_bounds__(SC_THREADS, (D <= 2 ? 2 : 1)) k_bind_eval(ScTables tabs, size_t quarter, const fr_t r, fr_t* partials,
+                                                          unsigned int* ticket, fr_t* out4) {
+    __shared__ fr_t smem[EvalAcc<D>::NV * 32];
+    EvalAcc<D> acc; acc.clear();
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < quarter; p += stride) {
+        fr_t lo[D], hi[D];
+#pragma unroll
+        for (int t = 0; t < D; ++t) {
+            fr_t* base = tabs.t[t];
+            fr_t a0 = ld256_stream(base + p), a1 = ld256_stream(base + p + quarter);
+            fr_t b0 = ld256_stream(base + p + 2 * quarter), b1 = ld256_stream(base + p + 3 * quarter);
+            lo[t] = a0 + r * (b0 - a0);
+            hi[t] = a1 + r * (b1 - a1);
+            st256(base + p, lo[t]);
+            st256(base + p + quarter, hi[t]);
+        }
+        acc.pair(lo, hi);
+    }
+    fr_t v[EvalAcc<D>::NV];
+    acc.finish(v);
+    grid_finish_sum<fr_t, EvalAcc<D>::NV>(v, partials, ticket, smem, EvalEpilogue<D>{out4});
+}
+
+// ---------------------------------------------------------------- launch helpers
+static inline int sc_grid(size_t work, int sm_count, int blocks_per_sm) {
+    size_t need = (work + SC_THREADS - 1) / SC_THREADS;
+    size_t cap = (size_t)sm_count * blocks_per_sm;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+cudaError_t launch_round_eval(int d, const ScTables& tabs, size_t n, fr_t* partials, unsigned int* ticket, fr_t* out4,
+                              int sm_count, cudaStream_t s) {
+    size_t half = n / 2;
+    int grid = sc_grid(half, sm_count, SC_BLOCKS_PER_SM);
+    switch (d) {
+        case 1: k_round_eval<1><<<grid, SC_THREADS, 0, s>>>(tabs, half, partials, ticket, out4); break;
+        case 2: k_round_eval<2><<<grid, SC_THREADS, 0, s>>>(tabs, half, partials, ticket, out4); break;
+        case 3: k_round_eval<3><<<grid, SC_THREADS, 0, s>>>(tabs, half, partials, ticket, out4); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bind(fr_t* t, size_t n, const fr_t& r, int sm_count, cudaStream_t s) {
+    size_t half = n / 2;
+    int grid = sc_grid(half, sm_count, SC_BLOCKS_PER_SM_BIND);
+    k_bind<<<grid, SC_THREADS, 0, s>>>(t, half, r);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bind_to(const fr_t* t, fr_t* out, size_t n, const fr_t& r, int sm_count, cudaStream_t s) {
+    size_t half = n / 2;
+    int grid = sc_grid(half, sm_count, SC_BLOCKS_PER_SM_BIND);
+    k_bind_to<<<grid, SC_THREADS, 0, s>>>(t, out, half, r);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bind_eval(int d, const ScTables& tabs, size_t n, const fr_t& r, fr_t* partials, unsigned int* ticket,
+                             fr_t* out4, int sm_count, cudaStream_t s) {
+    size_t quarter = n / 4;
+    int grid = sc_grid(quarter, sm_count, SC_BLOCKS_PER_SM);
+    switch (d) {
+        case 1: k_bind_eval<1><<<grid, SC_THREADS, 0, s>>>(tabs, quarter, r, partials, ticket, out4); break;
+        case 2: k_bind_eval<2><<<grid, SC_THREADS, 0, s>>>(tabs, quarter, r, partials, ticket, out4); break;
+        case 3: k_bind_eval<3><<<grid, SC_THREADS, 0, s>>>(tabs, quarter, r, partials, ticket, out4); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace tsg

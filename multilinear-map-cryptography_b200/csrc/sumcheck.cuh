@@ -1,0 +1,25 @@
+// sumcheck.cuh - launch interface of the sum-check round kernels (sumcheck.cu)
+#pragma once
+#include <cuda_runtime.h>
+#include "fp.cuh"
+
+namespace tsg {
+
+constexpr int SC_THREADS = 256;
+constexpr int SC_BLOCKS_PER_SM = 2;        // evaluation kernels: ~100+ registers per thread
+constexpr int SC_BLOCKS_PER_SM_BIND = 4;   // bind-only kernel: light
+constexpr int SC_MAX_TABLES = 3;
+
+struct ScTables { fr_t* t[SC_MAX_TABLES]; };
+
+// number of blocks the evaluation kernels may launch (sizes the partial-sum scratch)
+inline int sc_max_grid(int sm_count) { return sm_count * SC_BLOCKS_PER_SM_BIND; }
+
+cudaError_t launch_round_eval(int d, const ScTables& tabs, size_t n, fr_t* partials, unsigned int* ticket, fr_t* out4,
+                              int sm_count, cudaStream_t s);
+cudaError_t launch_bind(fr_t* t, size_t n, const fr_t& r, int sm_count, cudaStream_t s);
+cudaError_t launch_bind_to(const fr_t* t, fr_t* out, size_t n, const fr_t& r, int sm_count, cudaStream_t s);
+cudaError_t launch_bind_eval(int d, const ScTables& tabs, size_t n, const fr_t& r, fr_t* partials, unsigned int* ticket,
+                             fr_t* out4, int sm_count, cudaStream_t s);
+
+}  // namespace tsg

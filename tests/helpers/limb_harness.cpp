@@ -1,0 +1,43 @@
+// Host-emulation harness for the limb algorithms in csrc/fp.cuh (carry flag emulated in ptx.cuh).
+// Built by tests/test_limb_arith_host.py with g++; lets the exact device algorithms be checked
+// against the oracle without a GPU.  Not part of the product.
+#include <cstddef>
+#include <cstring>
+#include "fp.cuh"
+using namespace tsg;
+
+template <class P>
+static void binop(int op, const uint32_t* a, const uint32_t* b, size_t n, uint32_t* out) {
+    for (size_t i = 0; i < n; ++i) {
+        fp<P> x, y, r;
+        memcpy(x.l, a + 8 * i, 32); memcpy(y.l, b + 8 * i, 32);
+        switch (op) {
+            case 0: r = x + y; break;
+            case 1: r = x - y; break;
+            case 2: r = x * y; break;
+            case 3: { uint32_t t[16]; limb::mul_wide(t, x.l, y.l); limb::wide_normalize<P>(t); limb::mont_reduce<P>(r.l, t); break; }
+            case 4: r = x.from_mont(); break;
+            case 5: r = x.to_mont(); break;
+            case 6: r = x.inverse(); break;
+            case 7: r = x.neg(); break;
+            default: r = fp<P>::zero();
+        }
+        memcpy(out + 8 * i, r.l, 32);
+    }
+}
+extern "C" void limb_binop(int field, int op, const uint32_t* a, const uint32_t* b, size_t n, uint32_t* out) {
+    if (field == 0) binop<FrP>(op, a, b, n, out); else binop<FqP>(op, a, b, n, out);
+}
+// sum_i a_i * b_i through the lazy 512-bit accumulator
+extern "C" void limb_dot(int field, const uint32_t* a, const uint32_t* b, size_t n, uint32_t* out) {
+    if (field == 0) {
+        wide_acc<FrP> acc; acc.clear();
+        for (size_t i = 0; i < n; ++i) { fr_t x, y; memcpy(x.l, a + 8 * i, 32); memcpy(y.l, b + 8 * i, 32); acc.add_product(x, y); }
+        fr_t r = acc.reduce(); memcpy(out, r.l, 32);
+    } else {
+        wide_acc<FqP> acc; acc.clear();
+        for (size_t i = 0; i < n; ++i) { fq_t x, y; memcpy(x.l, a + 8 * i, 32); memcpy(y.l, b + 8 * i, 32); acc.add_product(x, y); }
+        fq_t r = acc.reduce(); memcpy(out, r.l, 32);
+    }
+}
+extern "C" void limb_mul_wide(const uint32_t* a, const uint32_t* b, uint32_t* out16) { limb::mul_wide(out16, a, b); }

@@ -1,0 +1,93 @@
+"""GPU parity: sum-check round kernels (through the C ABI) vs the CPU oracle, bit-exact.
+
+Reference: SumCheck::prove / compute_round_polynomial (src/sumcheck.rs:56-110,156-207) called with
+f(v) = prod_t mle_t.evaluate(v)."""
+import numpy as np
+import pytest
+
+from conftest import seed_bytes
+
+pytestmark = pytest.mark.gpu
+
+
+def drive_rounds(ctx, oracle, host_tables, fused=True):
+    """Run the device sum-check with the oracle's transcript supplying challenges.
+    Returns (round evals list, challenges, finals)."""
+    tabs = [ctx.table_upload(t) for t in host_tables]
+    nv = tabs[0].num_vars
+    sc = ctx.sumcheck(tabs)
+    tr = oracle.Transcript()
+    xs = oracle.fr_from_ints([0, 1, 2, 3])
+    evals_all, chals, coeffs_all = [], [], []
+    ev = sc.round_eval() if nv else None
+    for rnd in range(nv):
+        evals_all.append(ev.copy())
+        coeffs = oracle.lagrange_interpolate(xs, ev)
+        coeffs_all.append(coeffs)
+        tr.append_field_elements(f"sumcheck_round_{rnd}".encode(), coeffs)
+        r = tr.challenge_field_element(f"sumcheck_challenge_{rnd}".encode())
+        chals.append(r)
+        if rnd + 1 < nv:
+            if fused:
+                ev = sc.bind_eval(r)
+            else:
+                sc.bind(r)
+                ev = sc.round_eval()
+        else:
+            sc.bind(r)
+    finals = sc.final()
+    sc.end()
+    return np.array(coeffs_all).reshape(nv, 4, 4), np.array(chals).reshape(nv, 4), finals
+
+
+@pytest.mark.parametrize("d", [1, 2, 3])
+@pytest.mark.parametrize("nv", [1, 2, 3, 5, 8, 11])
+@pytest.mark.parametrize("fused", [True, False])
+def test_sumcheck_product_matches_oracle(ctx, oracle, d, nv, fused):
+    n = 1 << nv
+    tables = [oracle.chacha_fr_rand(seed_bytes(10 * d + t + nv), n) for t in range(d)]
+    ref_closure_ok = nv <= 5
+    ints = [oracle.fr_to_ints(t) for t in tables]
+    claimed = 0
+    for i in range(n):
+        p = 1
+        for t in range(d):
+            p = p * ints[t][i] % oracle.R_MOD
+        claimed = (claimed + p) % oracle.R_MOD
+    claimed_m = oracle.fr_from_ints([claimed])[0]
+    ref = oracle.sumcheck_prove_product(tables, claimed_m, mode="closure" if ref_closure_ok else "tables")
+    coeffs, chals, finals = drive_rounds(ctx, oracle, tables, fused=fused)
+    assert (coeffs == ref["round_polynomials"]).all()
+    assert (chals == ref["challenges"]).all()
+    fe = oracle.fr_from_ints([1])[0]
+    for t in range(d):
+        fe = oracle.field_binop("fr", "mul", fe, finals[t])[0]
+    assert (fe == ref["final_evaluation"]).all()
+    tab_ref = oracle.sumcheck_prove_product(tables, claimed_m, mode="tables")
+    assert (finals == tab_ref["finals"]).all()
+
+
+def test_appendix_c3_vector(ctx, oracle):
+    """A=[1..8], B=[3,1,4,1,5,9,2,6], claimed sum 162."""
+    A = oracle.fr_from_ints(list(range(1, 9)))
+    B = oracle.fr_from_ints([3, 1, 4, 1, 5, 9, 2, 6])
+    coeffs, chals, finals = drive_rounds(ctx, oracle, [A, B])
+    assert oracle.fr_to_ints(coeffs[0]) == [54, 51, 3, 0]
+    assert oracle.fr_to_ints(chals)[0] == 21125437990100363807064869691380599404649938677815818472735327310510785473320
+    fe = oracle.fr_to_ints(oracle.field_binop("fr", "mul", finals[0], finals[1]))[0]
+    assert fe == 359745214182377975469500176028792295272184875172441352787133304826151130394
+
+
+def test_large_round_linearity(ctx, oracle):
+    """2^20 entries, d=2: g(0)+g(1) of round k must equal g_{k-1}(r_{k-1}) - the size-independent
+    sum-check invariant - and the final product must equal the last round polynomial at the last challenge."""
+    nv = 20
+    n = 1 << nv
+    A = oracle.chacha_fr_rand(seed_bytes(91), n)
+    B = oracle.chacha_fr_rand(seed_bytes(92), n)
+    coeffs, chals, finals = drive_rounds(ctx, oracle, [A, B])
+    zero, one = oracle.fr_from_ints([0, 1])
+    claimed = oracle.field_binop("fr", "add", oracle.horner(coeffs[0], zero), oracle.horner(coeffs[0], one))[0]
+    ref = oracle.sumcheck_prove_product([A, B], claimed, mode="tables")
+    assert (coeffs == ref["round_polynomials"]).all()
+    assert (finals == ref["finals"]).all()
