@@ -59,6 +59,9 @@ const char* tsgpu_last_error(const tsgpu_ctx* ctx);
 uint64_t tsgpu_launch_count(const tsgpu_ctx* ctx);
 int tsgpu_synchronize(tsgpu_ctx* ctx);
 int tsgpu_sm_count(const tsgpu_ctx* ctx);
+/* tuning knobs (process-wide): "tma_min_log2" = log2 of the per-stream size from which the sum-check rounds use
+ * the TMA bulk-copy pipelined kernels instead of the plain streaming kernels (negative: never; default never) */
+int tsgpu_set_tuning(tsgpu_ctx* ctx, const char* key, long value);
 
 /* ---- MLE tables: MultilinearExtension { num_vars, evaluations }  (src/polynomials.rs:18-82) ------ */
 /* from_evaluations / from_evaluations_vec: `n` host entries, zero-padded or truncated to 2^num_vars
@@ -105,6 +108,27 @@ int tsgpu_sc_bind_eval(tsgpu_sc* sc, const tsgpu_fr* r, tsgpu_fr evals[4]);
  * SumCheckProof.final_evaluation (sumcheck.rs:104) */
 int tsgpu_sc_final(tsgpu_sc* sc, tsgpu_fr* finals);
 void tsgpu_sc_end(tsgpu_sc* sc);
+
+/* ---- host side of the path: Transcript and the SumCheck::prove / verify loops --------------------------
+ * These run on the CPU (the Fiat-Shamir transcript stays on the host) and drive the round kernels above.
+ * A Rust host would keep its own Transcript (src/utils.rs:134-204) and call the tsgpu_sc_* entry points;
+ * these C entry points exist so that non-Rust callers (the parity tests, bench.py) use the same logic. */
+typedef struct tsgpu_transcript tsgpu_transcript;
+tsgpu_transcript* tsgpu_transcript_new(const uint8_t* seed32);   /* Transcript::new - the seed has no effect (utils.rs:190) */
+void tsgpu_transcript_free(tsgpu_transcript* t);
+void tsgpu_transcript_append(tsgpu_transcript* t, const char* label, size_t label_len, const tsgpu_fr* elems, size_t n);
+void tsgpu_transcript_challenge(tsgpu_transcript* t, const char* label, size_t label_len, tsgpu_fr* out);
+size_t tsgpu_transcript_state_len(const tsgpu_transcript* t);
+
+/* SumCheck::new(num_vars, claimed_sum).prove(|v| prod_t mle_t.evaluate(v), transcript)   (sumcheck.rs:56-110)
+ * round_polys: num_vars x 4 coefficients (low -> high); challenges / table_finals may be NULL.
+ * Returns TSGPU_E_SUMCHECK with "Round {k} consistency check failed" when claimed_sum is wrong. */
+int tsgpu_sumcheck_prove_product(tsgpu_ctx* ctx, tsgpu_table* const* tables, int d, const tsgpu_fr* claimed_sum,
+                                 tsgpu_transcript* transcript, tsgpu_fr* round_polys, tsgpu_fr* final_evaluation,
+                                 tsgpu_fr* challenges, tsgpu_fr* table_finals);
+/* SumCheck::verify (sumcheck.rs:113-153): *valid = 1/0; TSGPU_E_SUMCHECK for a wrong number of rounds */
+int tsgpu_sumcheck_verify(unsigned num_vars, const tsgpu_fr* claimed_sum, const tsgpu_fr* round_polys, size_t num_rounds,
+                          const tsgpu_fr* final_evaluation, tsgpu_transcript* transcript, int* valid, tsgpu_fr* challenges);
 
 #ifdef __cplusplus
 }

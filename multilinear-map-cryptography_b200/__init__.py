@@ -7,4 +7,5 @@ The directory name carries a hyphen, so import it with
     host/       C++ host mirror of the reference API (Transcript, SumCheck, KZG, Twist, Shout)
     binding.py  ctypes binding of libtsgpu.so - no CPU fallback
 """
-from .binding import Context, Table, SumCheckRounds, TwistAndShoutError, LIB_PATH, lib  # noqa: F401
+from .binding import (Context, Table, SumCheckRounds, SumCheck, SumCheckProof, Transcript,  # noqa: F401
+                      TwistAndShoutError, LIB_PATH, lib)

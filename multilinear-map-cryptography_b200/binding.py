@@ -15,7 +15,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtsgpu.so")
+LIB_PATH = os.environ.get("TSGPU_LIB") or os.path.join(_HERE, "libtsgpu.so")   # TSGPU_LIB: tuning builds only
 
 # TwistAndShoutError variants (reference src/lib.rs:59-78)
 ERROR_NAMES = {1: "InvalidParameters", 2: "ProofGeneration", 3: "ProofVerification", 4: "Commitment",
@@ -54,6 +54,13 @@ def lib() -> C.CDLL:
         L.tsgpu_destroy.argtypes = [C.c_void_p]
         L.tsgpu_table_free.argtypes = [C.c_void_p, C.c_void_p]
         L.tsgpu_sc_end.argtypes = [C.c_void_p]
+        L.tsgpu_transcript_new.restype = C.c_void_p
+        L.tsgpu_transcript_new.argtypes = [C.c_void_p]
+        L.tsgpu_transcript_free.argtypes = [C.c_void_p]
+        L.tsgpu_transcript_append.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        L.tsgpu_transcript_challenge.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_void_p]
+        L.tsgpu_transcript_state_len.restype = C.c_size_t
+        L.tsgpu_transcript_state_len.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -102,6 +109,9 @@ class Context:
     @property
     def sm_count(self) -> int:
         return int(lib().tsgpu_sm_count(self._h))
+
+    def set_tuning(self, key: str, value: int):
+        self.check(lib().tsgpu_set_tuning(self._h, key.encode(), C.c_long(value)))
 
     def synchronize(self):
         self.check(lib().tsgpu_synchronize(self._h))
@@ -250,3 +260,84 @@ class SumCheckRounds:
             self.end()
         except Exception:
             pass
+
+
+class Transcript:
+    """Host-side Fiat-Shamir transcript of the reference (src/utils.rs:134-204); no GPU needed."""
+
+    def __init__(self, seed: bytes = b"\0" * 32):
+        buf = C.create_string_buffer(bytes(seed), 32)
+        self._h = C.c_void_p(lib().tsgpu_transcript_new(buf))
+
+    def append_field_element(self, label: bytes, x):
+        self.append_field_elements(label, _fr(x, 1))
+
+    def append_field_elements(self, label: bytes, xs):
+        xs = _fr(xs)
+        lib().tsgpu_transcript_append(self._h, label, len(label), _p(xs), xs.shape[0])
+
+    def challenge_field_element(self, label: bytes) -> np.ndarray:
+        out = np.empty(4, dtype=np.uint64)
+        lib().tsgpu_transcript_challenge(self._h, label, len(label), _p(out))
+        return out
+
+    def challenge_field_elements(self, label: bytes, count: int) -> np.ndarray:
+        """labels "{label}_{i}" (utils.rs:195-203)"""
+        if count == 0:
+            return np.empty((0, 4), dtype=np.uint64)
+        return np.stack([self.challenge_field_element(label + b"_" + str(i).encode()) for i in range(count)])
+
+    @property
+    def state_len(self) -> int:
+        return int(lib().tsgpu_transcript_state_len(self._h))
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().tsgpu_transcript_free(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+
+class SumCheckProof:
+    """src/sumcheck.rs:25-31"""
+
+    def __init__(self, round_polynomials: np.ndarray, final_evaluation: np.ndarray):
+        self.round_polynomials = round_polynomials     # (num_vars, 4, 4) coefficients low -> high
+        self.final_evaluation = final_evaluation       # (4,)
+
+
+class SumCheck:
+    """Mirror of the reference's SumCheck { num_vars, claimed_sum } (src/sumcheck.rs:15-53) with the structured
+    prover: `prove_product(tables, transcript)` equals `prove(|v| prod_t mle_t.evaluate(v), transcript)`."""
+
+    def __init__(self, num_vars: int, claimed_sum):
+        self.num_vars = num_vars
+        self.claimed_sum = _fr(claimed_sum, 1).reshape(4)
+
+    def prove_product(self, ctx: Context, tables: Sequence[Table], transcript: Transcript, return_aux: bool = False):
+        tables = list(tables)
+        if any(t.num_vars != self.num_vars for t in tables):
+            raise TwistAndShoutError(1, "Number of variables must match")
+        nv, d = self.num_vars, len(tables)
+        arr = (C.c_void_p * d)(*[t._h for t in tables])
+        rp = np.zeros((max(nv, 1), 4, 4), dtype=np.uint64)
+        fe = np.zeros(4, dtype=np.uint64)
+        ch = np.zeros((max(nv, 1), 4), dtype=np.uint64)
+        fin = np.zeros((d, 4), dtype=np.uint64)
+        ctx.check(lib().tsgpu_sumcheck_prove_product(ctx._h, arr, C.c_int(d), _p(self.claimed_sum), transcript._h,
+                                                     _p(rp), _p(fe), _p(ch), _p(fin)))
+        proof = SumCheckProof(rp[:nv], fe)
+        return (proof, ch[:nv], fin) if return_aux else proof
+
+    def verify(self, proof: SumCheckProof, transcript: Transcript):
+        """-> (is_valid, challenges); raises SumCheck("Proof has wrong number of rounds") like sumcheck.rs:118-122"""
+        rp = np.ascontiguousarray(proof.round_polynomials, dtype=np.uint64).reshape(-1, 4, 4)
+        ch = np.zeros((max(rp.shape[0], 1), 4), dtype=np.uint64)
+        valid = C.c_int(0)
+        rc = lib().tsgpu_sumcheck_verify(C.c_uint(self.num_vars), _p(self.claimed_sum), _p(rp), C.c_size_t(rp.shape[0]),
+                                         _p(_fr(proof.final_evaluation, 1)), transcript._h, C.byref(valid), _p(ch))
+        if rc:
+            raise TwistAndShoutError(rc, "Proof has wrong number of rounds")
+        return bool(valid.value), ch[:rp.shape[0]]

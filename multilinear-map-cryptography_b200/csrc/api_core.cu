@@ -101,6 +101,15 @@ int tsgpu_synchronize(tsgpu_ctx* ctx) {
     return TSGPU_OK;
 }
 
+int tsgpu_set_tuning(tsgpu_ctx* ctx, const char* key, long value) {
+    if (!key) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null key");
+    if (!strcmp(key, "tma_min_log2")) {   // tables with >= 2^value positions per stream use the TMA-pipelined kernels; < 0 disables
+        set_tma_min_work(value < 0 || value > 62 ? ~(size_t)0 : (size_t)1 << value);
+        return TSGPU_OK;
+    }
+    return fail(ctx, TSGPU_E_INVALID_PARAMETERS, std::string("unknown tuning key ") + key);
+}
+
 // ------------------------------------------------------------------------------------------- tables
 int tsgpu_table_upload(tsgpu_ctx* ctx, const tsgpu_fr* evals, size_t n, unsigned num_vars, tsgpu_table** out) {
     if (!ctx || !out || (!evals && n)) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");

@@ -17,6 +17,11 @@ namespace tsg {
 
 struct FrP {   // BN254 scalar field r
     static constexpr uint32_t INV = 0xefffffffu;   // -r^-1 mod 2^32
+    static constexpr uint32_t INV29 = 0x0fffffffu; // -r^-1 mod 2^29
+    TSG_HD static constexpr uint32_t mod29(int i) {   // r in radix 2^29
+        constexpr uint32_t m[9] = {0x10000001u, 0x1f0fac9fu, 0xe5c2450u, 0x7d090f3u, 0x1585d283u, 0x2db40c0u, 0xa6e141u, 0xe5c2634u, 0x30644eu};
+        return m[i];
+    }
     TSG_HD static constexpr uint32_t mod(int i) {
         constexpr uint32_t m[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
         return m[i];
@@ -32,6 +37,11 @@ struct FrP {   // BN254 scalar field r
 };
 struct FqP {   // BN254 base field p
     static constexpr uint32_t INV = 0xe4866389u;   // -p^-1 mod 2^32
+    static constexpr uint32_t INV29 = 0x04866389u; // -p^-1 mod 2^29
+    TSG_HD static constexpr uint32_t mod29(int i) {   // p in radix 2^29
+        constexpr uint32_t m[9] = {0x187cfd47u, 0x10460b6u, 0x1c72a34fu, 0x2d522d0u, 0x1585d978u, 0x2db40c0u, 0xa6e141u, 0xe5c2634u, 0x30644eu};
+        return m[i];
+    }
     TSG_HD static constexpr uint32_t mod(int i) {
         constexpr uint32_t m[8] = {0xd87cfd47u, 0x3c208c16u, 0x6871ca8du, 0x97816a91u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
         return m[i];
@@ -280,6 +290,85 @@ TSG_HD void mont_reduce(uint32_t* r, const uint32_t* T) {
     cond_sub_mod<P>(r);
 }
 
+
+// ===================================================================================================
+// Radix-2^29 multiplier.  Measured on B200 (tools/ubench2.cu): IMAD.WIDE.U32 issues at full rate
+// (~18.5 T/s) only WITHOUT a carry predicate; the carry-in/out forms (.X, or carry-out) run at half
+// rate.  With nine 29-bit limbs every 29x29 product is < 2^58, so the 18 column sums of a product plus
+// its Montgomery reduction (<= 18 terms each) fit a 64-bit accumulator with no carry handling at all:
+// 81 + 81 plain IMAD.WIDE, carries resolved once by shifts on the ALU pipe.  The reduction strips
+// 8 x 29 + 24 = 256 bits, so values stay in the reference's 2^256 Montgomery domain.
+// ===================================================================================================
+constexpr uint32_t M29 = 0x1fffffffu;
+
+TSG_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, int sh) {   // bits [sh, sh+32) of hi:lo, 0 < sh < 32
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return (uint32_t)((((uint64_t)hi << 32) | lo) >> sh);
+#endif
+}
+
+// 8 x 32-bit limbs -> 9 x 29-bit limbs
+TSG_HD void to29(uint32_t* o, const uint32_t* x) {
+    o[0] = x[0] & M29;
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+        const int bit = 29 * k, w = bit >> 5, sh = bit & 31;   // sh != 0 for k = 1..7
+        o[k] = funnel_r(x[w], x[w + 1], sh) & M29;
+    }
+    o[8] = x[7] >> 8;
+}
+
+// column accumulators t[0..17) += A * B (81 wide MACs, no carries)
+TSG_HD void mac29(unsigned long long* t, const uint32_t* A, const uint32_t* B) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i)
+#pragma unroll
+        for (int j = 0; j < 9; ++j) t[i + j] += (unsigned long long)A[j] * B[i];
+}
+
+// Montgomery-reduce the 17(+1) column sums by 2^256 and repack to 8 x 32-bit limbs; output < p.
+// Requires sum_k t[k] 2^(29k) < p * 2^256 and every t[k] < 2^62.
+template <class P>
+TSG_HD void redc29(uint32_t* r, unsigned long long* t) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        uint32_t m = ((uint32_t)t[i] * P::INV29) & M29;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) t[i + j] += (unsigned long long)m * P::mod29(j);
+        t[i + 1] += t[i] >> 29;
+    }
+    {   // last step removes only 24 bits: 8 * 29 + 24 = 256
+        uint32_t m = ((uint32_t)t[8] * P::INV29) & 0x00ffffffu;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) t[8 + j] += (unsigned long long)m * P::mod29(j);
+    }
+    // carry-normalise limbs 8..17 (value U = sum t[8+k] 2^(29k), divisible by 2^24)
+#pragma unroll
+    for (int k = 8; k < 17; ++k) { t[k + 1] += t[k] >> 29; t[k] &= M29; }
+    // R = U >> 24: 32-bit word w holds bits [32w + 24, 32w + 56) of U
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        const int bit = 32 * w + 24, k = bit / 29, sh = bit % 29;
+        unsigned long long v = (t[8 + k] >> sh) | (t[8 + k + 1] << (29 - sh));
+        if (29 - sh + 29 < 32) v |= t[8 + k + 2] << (58 - sh);
+        r[w] = (uint32_t)v;
+    }
+    cond_sub_mod<P>(r);
+}
+
+template <class P>
+TSG_HD void mont_mul29(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+    uint32_t A[9], B[9];
+    to29(A, a); to29(B, b);
+    unsigned long long t[18];
+#pragma unroll
+    for (int k = 0; k < 18; ++k) t[k] = 0;
+    mac29(t, A, B);
+    redc29<P>(r, t);
+}
+
 }  // namespace limb
 
 // ---------------------------------------------------------------------------------------------------
@@ -287,6 +376,7 @@ template <class P>
 struct alignas(16) fp {
     uint32_t l[8];
 
+    TSG_HD static constexpr uint32_t modulus_limb(int i) { return P::mod(i); }
     TSG_HD static fp zero() { fp r; for (int i = 0; i < 8; ++i) r.l[i] = 0; return r; }
     TSG_HD static fp one() { fp r; for (int i = 0; i < 8; ++i) r.l[i] = P::one(i); return r; }
     TSG_HD static fp r2() { fp r; for (int i = 0; i < 8; ++i) r.l[i] = P::r2(i); return r; }
@@ -295,8 +385,13 @@ struct alignas(16) fp {
     TSG_HD bool operator!=(const fp& b) const { return !(*this == b); }
     TSG_HD fp operator+(const fp& b) const { fp r; limb::add<P>(r.l, l, b.l); return r; }
     TSG_HD fp operator-(const fp& b) const { fp r; limb::sub<P>(r.l, l, b.l); return r; }
+    #if !defined(TSG_MUL_RADIX29)
     TSG_HD fp operator*(const fp& b) const { fp r; limb::mont_mul<P>(r.l, l, b.l); return r; }
     TSG_HD fp sqr() const { fp r; limb::mont_mul<P>(r.l, l, l); return r; }
+#else
+    TSG_HD fp operator*(const fp& b) const { fp r; limb::mont_mul29<P>(r.l, l, b.l); return r; }
+    TSG_HD fp sqr() const { fp r; limb::mont_mul29<P>(r.l, l, l); return r; }
+#endif
     TSG_HD fp dbl() const { fp r; limb::add<P>(r.l, l, l); return r; }
     TSG_HD fp neg() const { fp z = zero(); fp r; limb::sub<P>(r.l, z.l, l); return r; }
     // Montgomery -> canonical integer limbs
@@ -306,6 +401,7 @@ struct alignas(16) fp {
         fp r; limb::mont_reduce<P>(r.l, T); return r;
     }
     TSG_HD fp to_mont() const { return *this * r2(); }
+    TSG_HD static fp from_u64(unsigned long long v) { fp r = zero(); r.l[0] = (uint32_t)v; r.l[1] = (uint32_t)(v >> 32); return r.to_mont(); }
     // a^e for a 64-bit exponent
     TSG_HD fp pow_u64(unsigned long long e) const {
         fp acc = one(); fp base = *this;
@@ -329,9 +425,10 @@ struct alignas(16) fp {
 typedef fp<FrP> fr_t;
 typedef fp<FqP> fq_t;
 
-// 512-bit lazy accumulator for sums of products of reduced operands
+// Lazy accumulator for sums of products of reduced operands (carry-chain form, 512 bits).  Default
+// (see the measurement note at the radix-2^29 multiplier).
 template <class P>
-struct wide_acc {
+struct wide_acc32 {
     uint32_t t[16];
     int pending;   // products added since the last normalisation
     TSG_HD void clear() { for (int i = 0; i < 16; ++i) t[i] = 0; pending = 0; }
@@ -341,11 +438,72 @@ struct wide_acc {
         limb::wide_add(t, p);
         if (++pending == 16) { limb::wide_normalize<P>(t); pending = 0; }
     }
-    // Montgomery-form value of the accumulated sum
     TSG_HD fp<P> reduce() {
         limb::wide_normalize<P>(t); pending = 0;
         fp<P> r; limb::mont_reduce<P>(r.l, t); return r;
     }
 };
+
+// Lazy accumulator in radix 2^29: 18 column sums of 64 bits; a product costs 81 plain IMAD.WIDE and no
+// carry handling; columns are carry-normalised every 6 products (6 * 9 * 2^58 < 2^64).  reduce() folds
+// everything above 2^512 back with 2^512 mod p, then performs one Montgomery reduction.
+template <class P>
+struct wide_acc29 {
+    unsigned long long t[18];
+    int pending;
+    TSG_HD void clear() { for (int i = 0; i < 18; ++i) t[i] = 0; pending = 0; }
+    TSG_HD void carry() {
+#pragma unroll
+        for (int k = 0; k < 17; ++k) { t[k + 1] += t[k] >> 29; t[k] &= limb::M29; }
+        pending = 0;
+    }
+    TSG_HD void add_product29(const uint32_t* A, const uint32_t* B) {
+        limb::mac29(t, A, B);
+        if (++pending == 6) carry();
+    }
+    TSG_HD void add_product(const fp<P>& a, const fp<P>& b) {
+        uint32_t A[9], B[9];
+        limb::to29(A, a.l); limb::to29(B, b.l);
+        add_product29(A, B);
+    }
+    // Montgomery-form value of the accumulated sum (runs once per thread: clarity over speed)
+    TSG_HD fp<P> reduce() {
+        carry();
+        // repack limbs 0..16 (each < 2^29, 493 bits) into sixteen 32-bit words
+        uint32_t W[16];
+#pragma unroll
+        for (int w = 0; w < 16; ++w) {
+            const int bit = 32 * w, k = bit / 29, sh = bit % 29;
+            unsigned long long v = t[k] >> sh;
+            if (k + 1 < 17) v |= t[k + 1] << (29 - sh);
+            if (k + 2 < 17 && 58 - sh < 32) v |= t[k + 2] << (58 - sh);
+            W[w] = (uint32_t)v;
+        }
+        // t[17] sits at bit 493 = 15 * 32 + 13: it overlaps words 15.. and may exceed 2^512
+        unsigned long long top = t[17];
+        unsigned long long lo = top << 13;            // bits 493.. of the sum, low 64
+        unsigned long long hi = top >> 51;            // spill above
+        uint32_t w15 = ptx::add_cc(W[15], (uint32_t)lo);
+        uint32_t h0 = ptx::addc_cc((uint32_t)(lo >> 32), 0u);
+        uint32_t h1 = ptx::addc_cc((uint32_t)hi, 0u);
+        uint32_t h2 = ptx::addc((uint32_t)(hi >> 32), 0u);
+        W[15] = w15;
+        limb::wide_normalize<P>(W);
+        // (h2:h1:h0) * 2^512 == (h2:h1:h0) * (2^512 mod p)
+        fp<P> hv = fp<P>::zero(); hv.l[0] = h0; hv.l[1] = h1; hv.l[2] = h2;
+        fp<P> r2 = fp<P>::r2();
+        uint32_t prod[16];
+        limb::mul_wide(prod, hv.l, r2.l);
+        limb::wide_add(W, prod);
+        limb::wide_normalize<P>(W);
+        fp<P> r; limb::mont_reduce<P>(r.l, W); return r;
+    }
+};
+
+#if defined(TSG_MUL_RADIX29)
+template <class P> using wide_acc = wide_acc29<P>;
+#else
+template <class P> using wide_acc = wide_acc32<P>;
+#endif
 
 }  // namespace tsg

@@ -4,8 +4,9 @@
 // ptxas into IMAD.WIDE.U32 with a predicate carry, which is what keeps a Montgomery product at
 // ~2n^2+n integer-pipe instructions).  The same functions have a host emulation (explicit carry
 // flag) so the limb algorithms in fp.cuh can be unit-tested bit-for-bit on a CPU-only box
-// (tests/test_limb_arith_host.py); the emulation is NOT a product code path - the shipped library
-// only ever runs the device side.
+// (tests/test_limb_arith_host.py).  The host side is also what the C++ host mirror (host/*.cpp) uses
+// for the handful of field operations that stay on the CPU: transcript serialisation, 4-point
+// interpolation and Horner evaluation of round polynomials, final MSM window combination.
 #pragma once
 #include <cstdint>
 

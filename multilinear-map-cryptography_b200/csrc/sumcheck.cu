@@ -15,6 +15,7 @@
 // low half - again contiguous.  Algorithmic bytes: evaluation 32 d N_k, bind 48 d N_k.
 #include "fr_device.cuh"
 #include "sumcheck.cuh"
+#include "tma_stream.cuh"
 
 namespace tsg {
 
@@ -145,6 +146,97 @@ __global__ void __launch_bounds__(SC_THREADS, (D <= 2 ? 2 : 1)) k_bind_eval(ScTa
     grid_finish_sum<fr_t, EvalAcc<D>::NV>(v, partials, ticket, smem, EvalEpilogue<D>{out4});
 }
 
+
+// ==================================================================================================
+// TMA-pipelined variants for large tables (work a multiple of TMA_THREADS).  Same arithmetic as the
+// simple kernels above; the inputs arrive through the shared-memory ring of tma_stream.cuh.
+// ==================================================================================================
+template <int D>
+__global__ void __launch_bounds__(TMA_THREADS, (D <= 2 ? TMA_MINBLOCKS : 1)) k_round_eval_tma(ScTables tabs, size_t half, fr_t* partials, unsigned int* ticket, fr_t* out4) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ fr_t smem[EvalAcc<D>::NV * 32];
+    typedef tma::Pipeline<2 * D, TMA_THREADS, TMA_STAGES> Pipe;
+    Pipe pipe;
+    const fr_t* streams[2 * D];
+#pragma unroll
+    for (int t = 0; t < D; ++t) { streams[2 * t] = tabs.t[t]; streams[2 * t + 1] = tabs.t[t] + half; }
+    pipe.init(smem_raw, streams, half / TMA_THREADS);
+    EvalAcc<D> acc; acc.clear();
+    for (size_t k = 0; k < pipe.my_tiles; ++k) {
+        fr_t e[2 * D];
+        pipe.fetch(k, e);
+        fr_t lo[D], hi[D];
+#pragma unroll
+        for (int t = 0; t < D; ++t) { lo[t] = e[2 * t]; hi[t] = e[2 * t + 1]; }
+        acc.pair(lo, hi);
+    }
+    fr_t v[EvalAcc<D>::NV];
+    acc.finish(v);
+    grid_finish_sum<fr_t, EvalAcc<D>::NV>(v, partials, ticket, smem, EvalEpilogue<D>{out4});
+}
+
+__global__ void __launch_bounds__(TMA_THREADS, 4) k_bind_tma(fr_t* t, size_t half, const fr_t r) {
+    extern __shared__ unsigned char smem_raw[];
+    typedef tma::Pipeline<2, TMA_THREADS, TMA_STAGES> Pipe;
+    Pipe pipe;
+    const fr_t* streams[2] = {t, t + half};
+    pipe.init(smem_raw, streams, half / TMA_THREADS);
+    for (size_t k = 0; k < pipe.my_tiles; ++k) {
+        fr_t e[2];
+        pipe.fetch(k, e);
+        st256(t + pipe.tile_of(k) * TMA_THREADS + threadIdx.x, e[0] + r * (e[1] - e[0]));
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(TMA_THREADS, (D <= 2 ? TMA_MINBLOCKS : 1)) k_bind_eval_tma(ScTables tabs, size_t quarter, const fr_t r, fr_t* partials,
+                                                                  unsigned int* ticket, fr_t* out4) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ fr_t smem[EvalAcc<D>::NV * 32];
+    typedef tma::Pipeline<4 * D, TMA_THREADS, TMA_STAGES> Pipe;
+    Pipe pipe;
+    const fr_t* streams[4 * D];
+#pragma unroll
+    for (int t = 0; t < D; ++t) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) streams[4 * t + j] = tabs.t[t] + j * quarter;
+    }
+    pipe.init(smem_raw, streams, quarter / TMA_THREADS);
+    EvalAcc<D> acc; acc.clear();
+    for (size_t k = 0; k < pipe.my_tiles; ++k) {
+        fr_t e[4 * D];
+        pipe.fetch(k, e);
+        const size_t p = pipe.tile_of(k) * TMA_THREADS + threadIdx.x;
+        fr_t lo[D], hi[D];
+#pragma unroll
+        for (int t = 0; t < D; ++t) {
+            lo[t] = e[4 * t + 0] + r * (e[4 * t + 2] - e[4 * t + 0]);
+            hi[t] = e[4 * t + 1] + r * (e[4 * t + 3] - e[4 * t + 1]);
+            st256(tabs.t[t] + p, lo[t]);
+            st256(tabs.t[t] + p + quarter, hi[t]);
+        }
+        acc.pair(lo, hi);
+    }
+    fr_t v[EvalAcc<D>::NV];
+    acc.finish(v);
+    grid_finish_sum<fr_t, EvalAcc<D>::NV>(v, partials, ticket, smem, EvalEpilogue<D>{out4});
+}
+
+// Runtime switch between the simple grid-stride kernels and the TMA-pipelined ones: on B200 the rounds are
+// integer-pipe bound with the carry-chain multiplier and the simple kernels measured 5-10% faster
+// (profiles/r01_kernel_variants.md), so the pipelined path is opt-in (tsgpu_set_tuning "tma_min_log2").
+static size_t g_tma_min_work = ~(size_t)0;
+void set_tma_min_work(size_t w) { g_tma_min_work = w < TMA_THREADS ? TMA_THREADS : w; }
+
+template <class K>
+static cudaError_t enable_smem(K kernel, size_t bytes) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+static inline int tma_grid(size_t tiles, int sm_count, int blocks_per_sm) {
+    size_t cap = (size_t)sm_count * blocks_per_sm;
+    return (int)(tiles < cap ? tiles : cap);
+}
+
 // ---------------------------------------------------------------- launch helpers
 static inline int sc_grid(size_t work, int sm_count, int blocks_per_sm) {
     size_t need = (work + SC_THREADS - 1) / SC_THREADS;
@@ -156,6 +248,21 @@ static inline int sc_grid(size_t work, int sm_count, int blocks_per_sm) {
 cudaError_t launch_round_eval(int d, const ScTables& tabs, size_t n, fr_t* partials, unsigned int* ticket, fr_t* out4,
                               int sm_count, cudaStream_t s) {
     size_t half = n / 2;
+    if (half >= g_tma_min_work) {
+        size_t tiles = half / TMA_THREADS;
+        int g = tma_grid(tiles, sm_count, TMA_MINBLOCKS);
+        cudaError_t e;
+        switch (d) {
+            case 1: { size_t sm = tma::Pipeline<2, TMA_THREADS, TMA_STAGES>::SMEM_BYTES; if ((e = enable_smem(k_round_eval_tma<1>, sm))) return e;
+                      k_round_eval_tma<1><<<g, TMA_THREADS, sm, s>>>(tabs, half, partials, ticket, out4); break; }
+            case 2: { size_t sm = tma::Pipeline<4, TMA_THREADS, TMA_STAGES>::SMEM_BYTES; if ((e = enable_smem(k_round_eval_tma<2>, sm))) return e;
+                      k_round_eval_tma<2><<<g, TMA_THREADS, sm, s>>>(tabs, half, partials, ticket, out4); break; }
+            case 3: { size_t sm = tma::Pipeline<6, TMA_THREADS, TMA_STAGES>::SMEM_BYTES; if ((e = enable_smem(k_round_eval_tma<3>, sm))) return e;
+                      k_round_eval_tma<3><<<g, TMA_THREADS, sm, s>>>(tabs, half, partials, ticket, out4); break; }
+            default: return cudaErrorInvalidValue;
+        }
+        return cudaGetLastError();
+    }
     int grid = sc_grid(half, sm_count, SC_BLOCKS_PER_SM);
     switch (d) {
         case 1: k_round_eval<1><<<grid, SC_THREADS, 0, s>>>(tabs, half, partials, ticket, out4); break;
@@ -168,6 +275,13 @@ cudaError_t launch_round_eval(int d, const ScTables& tabs, size_t n, fr_t* parti
 
 cudaError_t launch_bind(fr_t* t, size_t n, const fr_t& r, int sm_count, cudaStream_t s) {
     size_t half = n / 2;
+    if (half >= g_tma_min_work) {
+        size_t sm = tma::Pipeline<2, TMA_THREADS, TMA_STAGES>::SMEM_BYTES;
+        cudaError_t e = enable_smem(k_bind_tma, sm);
+        if (e) return e;
+        k_bind_tma<<<tma_grid(half / TMA_THREADS, sm_count, 4), TMA_THREADS, sm, s>>>(t, half, r);
+        return cudaGetLastError();
+    }
     int grid = sc_grid(half, sm_count, SC_BLOCKS_PER_SM_BIND);
     k_bind<<<grid, SC_THREADS, 0, s>>>(t, half, r);
     return cudaGetLastError();
@@ -183,6 +297,21 @@ cudaError_t launch_bind_to(const fr_t* t, fr_t* out, size_t n, const fr_t& r, in
 cudaError_t launch_bind_eval(int d, const ScTables& tabs, size_t n, const fr_t& r, fr_t* partials, unsigned int* ticket,
                              fr_t* out4, int sm_count, cudaStream_t s) {
     size_t quarter = n / 4;
+    if (quarter >= g_tma_min_work) {
+        size_t tiles = quarter / TMA_THREADS;
+        int g = tma_grid(tiles, sm_count, TMA_MINBLOCKS);
+        cudaError_t e;
+        switch (d) {
+            case 1: { size_t sm = tma::Pipeline<4, TMA_THREADS, TMA_STAGES>::SMEM_BYTES; if ((e = enable_smem(k_bind_eval_tma<1>, sm))) return e;
+                      k_bind_eval_tma<1><<<g, TMA_THREADS, sm, s>>>(tabs, quarter, r, partials, ticket, out4); break; }
+            case 2: { size_t sm = tma::Pipeline<8, TMA_THREADS, TMA_STAGES>::SMEM_BYTES; if ((e = enable_smem(k_bind_eval_tma<2>, sm))) return e;
+                      k_bind_eval_tma<2><<<g, TMA_THREADS, sm, s>>>(tabs, quarter, r, partials, ticket, out4); break; }
+            case 3: { size_t sm = tma::Pipeline<12, TMA_THREADS, TMA_STAGES>::SMEM_BYTES; if ((e = enable_smem(k_bind_eval_tma<3>, sm))) return e;
+                      k_bind_eval_tma<3><<<tma_grid(tiles, sm_count, 1), TMA_THREADS, sm, s>>>(tabs, quarter, r, partials, ticket, out4); break; }
+            default: return cudaErrorInvalidValue;
+        }
+        return cudaGetLastError();
+    }
     int grid = sc_grid(quarter, sm_count, SC_BLOCKS_PER_SM);
     switch (d) {
         case 1: k_bind_eval<1><<<grid, SC_THREADS, 0, s>>>(tabs, quarter, r, partials, ticket, out4); break;

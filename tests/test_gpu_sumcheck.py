@@ -91,3 +91,72 @@ def test_large_round_linearity(ctx, oracle):
     ref = oracle.sumcheck_prove_product([A, B], claimed, mode="tables")
     assert (coeffs == ref["round_polynomials"]).all()
     assert (finals == ref["finals"]).all()
+
+
+@pytest.mark.parametrize("d", [1, 2, 3])
+@pytest.mark.parametrize("fused", [True, False])
+def test_tma_pipelined_path_matches_oracle(ctx, oracle, d, fused):
+    """2^17 entries with the TMA-pipelined kernels switched on (>= 2^12 positions per stream), the
+    later rounds the simple kernels; every round polynomial and the final table values must match."""
+    nv = 17
+    tables = [oracle.chacha_fr_rand(seed_bytes(40 + 3 * d + t), 1 << nv) for t in range(d)]
+    ctx.set_tuning("tma_min_log2", 12)
+    try:
+        coeffs, chals, finals = drive_rounds(ctx, oracle, tables, fused=fused)
+    finally:
+        ctx.set_tuning("tma_min_log2", -1)
+    zero, one = oracle.fr_from_ints([0, 1])
+    claimed = oracle.field_binop("fr", "add", oracle.horner(coeffs[0], zero), oracle.horner(coeffs[0], one))[0]
+    ref = oracle.sumcheck_prove_product(tables, claimed, mode="tables")
+    assert (coeffs == ref["round_polynomials"]).all()
+    assert (chals == ref["challenges"]).all()
+    assert (finals == ref["finals"]).all()
+
+
+@pytest.mark.parametrize("d,nv", [(1, 4), (2, 6), (3, 5), (2, 12)])
+def test_prove_product_host_loop_matches_reference_prove(ctx, tsgpu, oracle, d, nv):
+    """The C++ host loop (host/sumcheck_host.cpp) + device rounds == SumCheck::prove with the product closure:
+    same round polynomials, same final evaluation, same transcript state afterwards; verify() accepts."""
+    n = 1 << nv
+    tables = [oracle.chacha_fr_rand(seed_bytes(60 + 5 * d + t), n) for t in range(d)]
+    ints = [oracle.fr_to_ints(t) for t in tables]
+    claimed = 0
+    for i in range(n):
+        p = 1
+        for t in range(d):
+            p = p * ints[t][i] % oracle.R_MOD
+        claimed = (claimed + p) % oracle.R_MOD
+    claimed_m = oracle.fr_from_ints([claimed])[0]
+    otr = oracle.Transcript()
+    ref = oracle.sumcheck_prove_product(tables, claimed_m, transcript=otr, mode="closure" if nv <= 6 else "tables")
+    tr = tsgpu.Transcript()
+    sc = tsgpu.SumCheck(nv, claimed_m)
+    proof, chals, finals = sc.prove_product(ctx, [ctx.table_upload(t) for t in tables], tr, return_aux=True)
+    assert (proof.round_polynomials == ref["round_polynomials"]).all()
+    assert (proof.final_evaluation == ref["final_evaluation"]).all()
+    assert (chals == ref["challenges"]).all()
+    # both transcripts must now produce the same next challenge
+    assert (tr.challenge_field_element(b"next") == otr.challenge_field_element(b"next")).all()
+    ok, ch2 = sc.verify(proof, tsgpu.Transcript())
+    assert ok and (ch2 == chals).all()
+
+
+def test_wrong_claimed_sum_is_rejected_in_round_zero(ctx, tsgpu, oracle):
+    """sumcheck.rs:77-84: Err(SumCheck("Round 0 consistency check failed"))"""
+    tables = [oracle.chacha_fr_rand(seed_bytes(70 + t), 64) for t in range(2)]
+    with pytest.raises(tsgpu.TwistAndShoutError) as e:
+        tsgpu.SumCheck(6, oracle.fr_from_ints([12345])[0]).prove_product(ctx, [ctx.table_upload(t) for t in tables], tsgpu.Transcript())
+    assert e.value.variant == "SumCheck" and "Round 0 consistency check failed" in str(e.value)
+    with pytest.raises(oracle.SumCheckError):
+        oracle.sumcheck_prove_product(tables, oracle.fr_from_ints([12345])[0], mode="closure")
+
+
+def test_reference_integration_x1_times_x2(ctx, tsgpu, oracle):
+    """tests/integration_tests.rs:263-288 and src/sumcheck.rs:221-245: f(x1,x2) = x1*x2 sums to 1 over {0,1}^2.
+    As tables: A[i] = bit0(i), B[i] = bit1(i)."""
+    A = oracle.fr_from_ints([0, 1, 0, 1]); B = oracle.fr_from_ints([0, 0, 1, 1])
+    one = oracle.fr_from_ints([1])[0]
+    sc = tsgpu.SumCheck(2, one)
+    proof = sc.prove_product(ctx, [ctx.table_upload(A), ctx.table_upload(B)], tsgpu.Transcript(bytes([42]) * 32))
+    ok, _ = sc.verify(proof, tsgpu.Transcript(bytes([42]) * 32))
+    assert ok

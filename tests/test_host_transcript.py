@@ -1,0 +1,52 @@
+"""CPU: the product's host-side Transcript / SumCheck::verify (C++ in host/, through the C ABI) against the
+oracle and the pinned vectors.  No GPU needed - these entry points never touch the device."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import seed_bytes
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_transcript_known_answer(tsgpu, oracle):
+    """src/utils.rs:287-296 test_transcript inputs; expected value from SURVEY.md Appendix C.1."""
+    t = tsgpu.Transcript(bytes([42]) * 32)
+    t.append_field_element(b"test", oracle.fr_from_ints([123])[0])
+    c = t.challenge_field_element(b"challenge")
+    assert oracle.fr_to_ints(c)[0] == 13648926573440158680322210633940909009220968087751212041477676025471912345605
+
+
+def test_transcript_matches_oracle_on_random_sessions(tsgpu, oracle):
+    rng = np.random.default_rng(7)
+    for trial in range(20):
+        a, b = tsgpu.Transcript(), oracle.Transcript()
+        for step in range(int(rng.integers(1, 12))):
+            label = bytes(rng.integers(97, 123, size=int(rng.integers(0, 40)), dtype=np.uint8))
+            if rng.random() < 0.6:
+                n = int(rng.integers(0, 6))
+                xs = oracle.chacha_fr_rand(seed_bytes(trial * 16 + step), n).reshape(n, 4)
+                a.append_field_elements(label, xs); b.append_field_elements(label, xs)
+            else:
+                assert (a.challenge_field_element(label) == b.challenge_field_element(label)).all()
+        assert (a.challenge_field_elements(b"opening_challenges", 3) == b.challenge_field_elements(b"opening_challenges", 3)).all()
+
+
+def test_sumcheck_verify_host(tsgpu, oracle):
+    """verify() replays the transcript and accepts an honest proof / rejects tampering (sumcheck.rs:113-153)."""
+    A = oracle.chacha_fr_rand(seed_bytes(1), 32); B = oracle.chacha_fr_rand(seed_bytes(2), 32)
+    ai, bi = oracle.fr_to_ints(A), oracle.fr_to_ints(B)
+    claimed = oracle.fr_from_ints([sum(x * y for x, y in zip(ai, bi)) % oracle.R_MOD])[0]
+    ref = oracle.sumcheck_prove_product([A, B], claimed, mode="closure")
+    proof = tsgpu.SumCheckProof(ref["round_polynomials"], ref["final_evaluation"])
+    ok, ch = tsgpu.SumCheck(5, claimed).verify(proof, tsgpu.Transcript())
+    assert ok and (ch == ref["challenges"]).all()
+    bad = tsgpu.SumCheckProof(ref["round_polynomials"].copy(), ref["final_evaluation"])
+    bad.round_polynomials[2, 1, 0] ^= 1
+    ok, _ = tsgpu.SumCheck(5, claimed).verify(bad, tsgpu.Transcript())
+    assert not ok
+    with pytest.raises(tsgpu.TwistAndShoutError) as e:
+        tsgpu.SumCheck(4, claimed).verify(proof, tsgpu.Transcript())
+    assert e.value.variant == "SumCheck"

@@ -10,7 +10,8 @@ import oracle as O
 
 nv = int(sys.argv[1]) if len(sys.argv) > 1 else 26
 torch.cuda.init()
-stream = torch.cuda.current_stream()
+stream = torch.cuda.Stream()
+torch.cuda.set_stream(stream)
 ctx = ts.Context(0, stream.cuda_stream)
 w = O.chacha_fr_rand(bytes([4]) * 32, nv)
 r = O.chacha_fr_rand(bytes([6]) * 32, 1)
