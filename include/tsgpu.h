@@ -109,6 +109,42 @@ int tsgpu_sc_bind_eval(tsgpu_sc* sc, const tsgpu_fr* r, tsgpu_fr evals[4]);
 int tsgpu_sc_final(tsgpu_sc* sc, tsgpu_fr* finals);
 void tsgpu_sc_end(tsgpu_sc* sc);
 
+/* ---- SRS: CommitmentParams.g1_powers resident in HBM  (src/utils.rs:53-63, 89-96) ---------------------------
+ * generate: g1_powers[i] = G * tau^i for i < n, what the setup_params loop computes with n = max_degree + 1
+ *           (fixed-base byte windows on the device instead of n serial double-and-add multiplications).
+ * upload:   an existing Vec<G1Projective> (Jacobian) from the host; normalised to affine once on the device.
+ * download: back to the host as Jacobian points with z = 1 (the same group elements). */
+int tsgpu_srs_generate(tsgpu_ctx* ctx, const tsgpu_fr* tau, size_t n, tsgpu_srs** out);
+int tsgpu_srs_upload(tsgpu_ctx* ctx, const tsgpu_g1* powers, size_t n, tsgpu_srs** out);
+int tsgpu_srs_download(tsgpu_ctx* ctx, const tsgpu_srs* srs, size_t first, size_t count, tsgpu_g1* out);
+size_t tsgpu_srs_len(const tsgpu_srs* srs);
+void tsgpu_srs_free(tsgpu_ctx* ctx, tsgpu_srs* srs);
+
+/* ---- coefficient vectors resident in HBM (low -> high, reference order) ---------------------------------- */
+int tsgpu_poly_upload(tsgpu_ctx* ctx, const tsgpu_fr* coeffs, size_t n, tsgpu_poly** out);
+int tsgpu_poly_download(tsgpu_ctx* ctx, const tsgpu_poly* p, tsgpu_fr* out);
+size_t tsgpu_poly_len(const tsgpu_poly* p);
+void tsgpu_poly_free(tsgpu_ctx* ctx, tsgpu_poly* p);
+
+/* ---- CommitmentScheme for KZGCommitment  (src/commitments.rs:156-199) -------------------------------------
+ * commit: C = sum_i polynomial[i] * g1_powers[i]  (Pippenger MSM); TSGPU_E_COMMITMENT
+ *         "Polynomial degree exceeds setup size" when n > srs length (commitments.rs:166-170).
+ * open:   value = P(z) (Horner, :305-313), proof = commit((P - value) / (x - z)) (:317-375, :194).
+ * Results are G1Projective values: any Jacobian representative of the group element. */
+int tsgpu_kzg_commit(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_fr* polynomial, size_t n, tsgpu_g1* out);
+int tsgpu_kzg_open(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_fr* polynomial, size_t n, const tsgpu_fr* z,
+                   tsgpu_fr* value, tsgpu_g1* proof);
+int tsgpu_kzg_commit_dev(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_poly* polynomial, tsgpu_g1* out);
+int tsgpu_kzg_open_dev(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_poly* polynomial, const tsgpu_fr* z,
+                       tsgpu_fr* value, tsgpu_g1* proof);
+/* plain G1 MSM over caller-supplied affine bases: sum_i scalars[i] * bases[i] */
+int tsgpu_msm_g1(tsgpu_ctx* ctx, const tsgpu_g1a* bases, const tsgpu_fr* scalars, size_t n, tsgpu_g1* out);
+/* CPU helpers on single points: KZGCommitmentValue::hash (commitments.rs:73-84), ark-serialize compressed bytes
+ * (commitments.rs:106-118), group equality (derive(PartialEq) on KZGCommitmentValue, commitments.rs:66) */
+void tsgpu_g1_hash(const tsgpu_g1* p, tsgpu_fr* out);
+void tsgpu_g1_compress(const tsgpu_g1* p, uint8_t out[32]);
+int tsgpu_g1_equal(const tsgpu_g1* a, const tsgpu_g1* b);
+
 /* ---- host side of the path: Transcript and the SumCheck::prove / verify loops --------------------------
  * These run on the CPU (the Fiat-Shamir transcript stays on the host) and drive the round kernels above.
  * A Rust host would keep its own Transcript (src/utils.rs:134-204) and call the tsgpu_sc_* entry points;

@@ -7,5 +7,5 @@ The directory name carries a hyphen, so import it with
     host/       C++ host mirror of the reference API (Transcript, SumCheck, KZG, Twist, Shout)
     binding.py  ctypes binding of libtsgpu.so - no CPU fallback
 """
-from .binding import (Context, Table, SumCheckRounds, SumCheck, SumCheckProof, Transcript,  # noqa: F401
-                      TwistAndShoutError, LIB_PATH, lib)
+from .binding import (Context, Table, SumCheckRounds, SumCheck, SumCheckProof, Transcript, Srs, Poly,  # noqa: F401
+                      KZGCommitment, g1_hash, g1_compress, g1_equal, TwistAndShoutError, LIB_PATH, lib)

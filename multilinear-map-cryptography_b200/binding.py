@@ -54,6 +54,15 @@ def lib() -> C.CDLL:
         L.tsgpu_destroy.argtypes = [C.c_void_p]
         L.tsgpu_table_free.argtypes = [C.c_void_p, C.c_void_p]
         L.tsgpu_sc_end.argtypes = [C.c_void_p]
+        L.tsgpu_srs_len.restype = C.c_size_t
+        L.tsgpu_srs_len.argtypes = [C.c_void_p]
+        L.tsgpu_srs_free.argtypes = [C.c_void_p, C.c_void_p]
+        L.tsgpu_poly_len.restype = C.c_size_t
+        L.tsgpu_poly_len.argtypes = [C.c_void_p]
+        L.tsgpu_poly_free.argtypes = [C.c_void_p, C.c_void_p]
+        L.tsgpu_g1_hash.argtypes = [C.c_void_p, C.c_void_p]
+        L.tsgpu_g1_compress.argtypes = [C.c_void_p, C.c_void_p]
+        L.tsgpu_g1_equal.argtypes = [C.c_void_p, C.c_void_p]
         L.tsgpu_transcript_new.restype = C.c_void_p
         L.tsgpu_transcript_new.argtypes = [C.c_void_p]
         L.tsgpu_transcript_free.argtypes = [C.c_void_p]
@@ -164,6 +173,33 @@ class Context:
 
     def sumcheck(self, tables: Sequence["Table"]) -> "SumCheckRounds":
         return SumCheckRounds(self, tables)
+
+    # ---- SRS / KZG
+    def srs_generate(self, tau, n: int) -> "Srs":
+        h = C.c_void_p()
+        self.check(lib().tsgpu_srs_generate(self._h, _p(_fr(tau, 1)), C.c_size_t(n), C.byref(h)))
+        return Srs(self, h)
+
+    def srs_upload(self, powers_jac) -> "Srs":
+        powers_jac = np.ascontiguousarray(powers_jac, dtype=np.uint64).reshape(-1, 12)
+        h = C.c_void_p()
+        self.check(lib().tsgpu_srs_upload(self._h, _p(powers_jac), C.c_size_t(powers_jac.shape[0]), C.byref(h)))
+        return Srs(self, h)
+
+    def poly_upload(self, coeffs) -> "Poly":
+        coeffs = _fr(coeffs)
+        h = C.c_void_p()
+        self.check(lib().tsgpu_poly_upload(self._h, _p(coeffs), C.c_size_t(coeffs.shape[0]), C.byref(h)))
+        return Poly(self, h)
+
+    def msm_g1(self, bases_affine, scalars) -> np.ndarray:
+        bases_affine = np.ascontiguousarray(bases_affine, dtype=np.uint64).reshape(-1, 8)
+        scalars = _fr(scalars)
+        if bases_affine.shape[0] < scalars.shape[0]:
+            raise ValueError("fewer bases than scalars")
+        out = np.empty(12, dtype=np.uint64)
+        self.check(lib().tsgpu_msm_g1(self._h, _p(bases_affine), _p(scalars), C.c_size_t(scalars.shape[0]), _p(out)))
+        return out
 
 
 class Table:
@@ -341,3 +377,111 @@ class SumCheck:
         if rc:
             raise TwistAndShoutError(rc, "Proof has wrong number of rounds")
         return bool(valid.value), ch[:rp.shape[0]]
+
+
+class Srs:
+    """tsgpu_srs: CommitmentParams.g1_powers resident in HBM."""
+
+    def __init__(self, ctx: Context, handle: C.c_void_p):
+        self.ctx = ctx
+        self._h = handle
+
+    def __len__(self) -> int:
+        return int(lib().tsgpu_srs_len(self._h))
+
+    def download(self, first: int = 0, count: Optional[int] = None) -> np.ndarray:
+        count = len(self) - first if count is None else count
+        out = np.empty((count, 12), dtype=np.uint64)
+        self.ctx.check(lib().tsgpu_srs_download(self.ctx._h, self._h, C.c_size_t(first), C.c_size_t(count), _p(out)))
+        return out
+
+    def free(self):
+        if self._h:
+            lib().tsgpu_srs_free(self.ctx._h, self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            if self.ctx._h:
+                self.free()
+        except Exception:
+            pass
+
+
+class Poly:
+    """tsgpu_poly: coefficient vector resident in HBM."""
+
+    def __init__(self, ctx: Context, handle: C.c_void_p):
+        self.ctx = ctx
+        self._h = handle
+
+    def __len__(self) -> int:
+        return int(lib().tsgpu_poly_len(self._h))
+
+    def download(self) -> np.ndarray:
+        out = np.empty((len(self), 4), dtype=np.uint64)
+        self.ctx.check(lib().tsgpu_poly_download(self.ctx._h, self._h, _p(out)))
+        return out
+
+    def free(self):
+        if self._h:
+            lib().tsgpu_poly_free(self.ctx._h, self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            if self.ctx._h:
+                self.free()
+        except Exception:
+            pass
+
+
+class KZGCommitment:
+    """Mirror of `impl CommitmentScheme for KZGCommitment` (src/commitments.rs:156-199): associated functions,
+    no self.  `params` is an Srs handle (CommitmentParams.g1_powers on the device); polynomials are either
+    host arrays (uint64[n,4]) or Poly handles."""
+
+    @staticmethod
+    def commit(params: Srs, polynomial) -> np.ndarray:
+        ctx = params.ctx
+        out = np.empty(12, dtype=np.uint64)
+        if isinstance(polynomial, Poly):
+            ctx.check(lib().tsgpu_kzg_commit_dev(ctx._h, params._h, polynomial._h, _p(out)))
+        else:
+            polynomial = _fr(polynomial)
+            ctx.check(lib().tsgpu_kzg_commit(ctx._h, params._h, _p(polynomial), C.c_size_t(polynomial.shape[0]), _p(out)))
+        return out
+
+    @staticmethod
+    def open(params: Srs, polynomial, point):
+        """-> (value, proof)"""
+        ctx = params.ctx
+        value = np.empty(4, dtype=np.uint64); proof = np.empty(12, dtype=np.uint64)
+        point = _fr(point, 1)
+        if isinstance(polynomial, Poly):
+            ctx.check(lib().tsgpu_kzg_open_dev(ctx._h, params._h, polynomial._h, _p(point), _p(value), _p(proof)))
+        else:
+            polynomial = _fr(polynomial)
+            ctx.check(lib().tsgpu_kzg_open(ctx._h, params._h, _p(polynomial), C.c_size_t(polynomial.shape[0]), _p(point),
+                                           _p(value), _p(proof)))
+        return value, proof
+
+
+def g1_hash(point) -> np.ndarray:
+    """KZGCommitmentValue::hash (src/commitments.rs:73-84); CPU."""
+    point = np.ascontiguousarray(point, dtype=np.uint64).reshape(12)
+    out = np.empty(4, dtype=np.uint64)
+    lib().tsgpu_g1_hash(_p(point), _p(out))
+    return out
+
+
+def g1_compress(point) -> bytes:
+    point = np.ascontiguousarray(point, dtype=np.uint64).reshape(12)
+    out = np.empty(32, dtype=np.uint8)
+    lib().tsgpu_g1_compress(_p(point), _p(out))
+    return out.tobytes()
+
+
+def g1_equal(a, b) -> bool:
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(12); b = np.ascontiguousarray(b, dtype=np.uint64).reshape(12)
+    return bool(lib().tsgpu_g1_equal(_p(a), _p(b)))

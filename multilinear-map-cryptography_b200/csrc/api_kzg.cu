@@ -1,0 +1,266 @@
+// api_kzg.cu - C ABI (include/tsgpu.h): SRS handles, G1 MSM, KZGCommitment::commit / open.
+#include <cstring>
+#include <new>
+#include <vector>
+#include "context.cuh"
+#include "msm.cuh"
+#include "poly.cuh"
+#include "../host/field64.hpp"
+
+using namespace tsg;
+using tsg::host::Fq64;
+using tsg::host::Fr64;
+using tsg::host::G1J;
+
+struct tsgpu_srs {
+    g1_affine* d = nullptr;   // n affine points, identity = (0,0)
+    size_t n = 0;
+};
+struct tsgpu_poly {
+    fr_t* d = nullptr;        // n coefficients, low -> high, natural order
+    size_t n = 0;
+};
+
+static_assert(sizeof(g1_affine) == 64 && sizeof(g1_jac) == 96 && sizeof(g1_xyzz) == 128, "point layouts");
+static_assert(sizeof(tsgpu_g1) == 96 && sizeof(tsgpu_g1a) == 64, "ABI point layouts");
+
+namespace {
+
+// combine W window sums S_w (Jacobian, low window first): sum_w 2^(c w) S_w
+G1J combine_windows(const g1_jac* win, unsigned W, unsigned c) {
+    G1J acc = G1J::identity();
+    for (unsigned w = W; w-- > 0;) {
+        for (unsigned k = 0; k < c; ++k) acc = acc.dbl();
+        G1J s; memcpy(&s, &win[w], 96);
+        acc = acc.add(s);
+    }
+    return acc;
+}
+
+// device MSM over `n` (bases, scalars) already resident; result to host as Jacobian
+int msm_device(tsgpu_ctx* ctx, const g1_affine* bases, const fr_t* scalars, size_t n, tsgpu_g1* out) {
+    if (n == 0) { G1J id = G1J::identity(); memcpy(out, &id, 96); return TSGPU_OK; }
+    MsmLayout L;
+    size_t bytes = msm_scratch_bytes(n, msm_window_bits(n), &L);
+    TempBuf scratch;
+    TSG_CUDA(ctx, scratch.alloc(bytes, ctx->stream));
+    unsigned launches = 0;
+    TSG_CUDA(ctx, msm_run(bases, scalars, n, L, scratch.as<unsigned char>(), ctx->sm_count, ctx->stream, &launches));
+    ctx->launches += launches;
+    std::vector<g1_jac> win(L.W);
+    TSG_CUDA(ctx, cudaMemcpyAsync(win.data(), scratch.as<unsigned char>() + L.window_out, L.W * sizeof(g1_jac), cudaMemcpyDeviceToHost, ctx->stream));
+    TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    G1J r = combine_windows(win.data(), L.W, L.c);
+    memcpy(out, &r, 96);
+    return TSGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ------------------------------------------------------------------------------------------- SRS
+int tsgpu_srs_generate(tsgpu_ctx* ctx, const tsgpu_fr* tau, size_t n, tsgpu_srs** out) {
+    if (!ctx || !tau || !out) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    tsgpu_srs* srs = new (std::nothrow) tsgpu_srs;
+    if (!srs) return fail(ctx, TSGPU_E_PROOF_GENERATION, "out of host memory");
+    srs->n = n;
+    cudaError_t e = cudaMalloc((void**)&srs->d, (n ? n : 1) * sizeof(g1_affine));
+    if (e != cudaSuccess) { delete srs; return cuda_fail(ctx, e, "cudaMalloc(srs)"); }
+    // byte-window table of the generator on the host: table[w * 255 + d - 1] = d * 256^w * G
+    std::vector<g1_affine> table(32 * 255);
+    {
+        G1J base = G1J::generator();
+        std::vector<G1J> jac(32 * 255);
+        for (int w = 0; w < 32; ++w) {
+            G1J acc = base;
+            for (int d = 1; d <= 255; ++d) { jac[w * 255 + d - 1] = acc; acc = acc.add(base); }
+            base = acc;
+        }
+        // batch normalisation (Montgomery trick)
+        std::vector<Fq64> pref(jac.size());
+        Fq64 acc = Fq64::one();
+        for (size_t i = 0; i < jac.size(); ++i) { pref[i] = acc; acc = acc * jac[i].z; }
+        Fq64 inv = acc.inverse();
+        for (size_t i = jac.size(); i-- > 0;) {
+            Fq64 zi = inv * pref[i]; inv = inv * jac[i].z;
+            Fq64 zi2 = zi.sqr();
+            Fq64 ax = jac[i].x * zi2, ay = jac[i].y * zi2 * zi;
+            memcpy(table[i].x.l, ax.l, 32); memcpy(table[i].y.l, ay.l, 32);
+        }
+    }
+    TempBuf dtable, scal, xyzz;
+    TSG_CUDA(ctx, dtable.alloc(table.size() * sizeof(g1_affine), ctx->stream));
+    TSG_CUDA(ctx, scal.alloc(n * sizeof(fr_t), ctx->stream));
+    TSG_CUDA(ctx, xyzz.alloc(n * sizeof(g1_xyzz), ctx->stream));
+    TSG_CUDA(ctx, cudaMemcpyAsync(dtable.p, table.data(), table.size() * sizeof(g1_affine), cudaMemcpyHostToDevice, ctx->stream));
+    fr_t t; memcpy(t.l, tau->l, 32);
+    if (n) {
+        TSG_CUDA(ctx, launch_tau_powers(t, 0, n, scal.as<fr_t>(), ctx->sm_count, ctx->stream));
+        TSG_CUDA(ctx, launch_fixed_base_mul(scal.as<fr_t>(), n, dtable.as<g1_affine>(), xyzz.as<g1_xyzz>(), ctx->sm_count, ctx->stream));
+        TSG_CUDA(ctx, launch_batch_to_affine(xyzz.as<g1_xyzz>(), n, srs->d, ctx->sm_count, ctx->stream));
+        ctx->launches += 3;
+    }
+    TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = srs;
+    return TSGPU_OK;
+}
+
+int tsgpu_srs_upload(tsgpu_ctx* ctx, const tsgpu_g1* powers, size_t n, tsgpu_srs** out) {
+    if (!ctx || !out || (!powers && n)) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    tsgpu_srs* srs = new (std::nothrow) tsgpu_srs;
+    if (!srs) return fail(ctx, TSGPU_E_PROOF_GENERATION, "out of host memory");
+    srs->n = n;
+    cudaError_t e = cudaMalloc((void**)&srs->d, (n ? n : 1) * sizeof(g1_affine));
+    if (e != cudaSuccess) { delete srs; return cuda_fail(ctx, e, "cudaMalloc(srs)"); }
+    TempBuf jac, xyzz;
+    TSG_CUDA(ctx, jac.alloc(n * sizeof(g1_jac), ctx->stream));
+    TSG_CUDA(ctx, xyzz.alloc(n * sizeof(g1_xyzz), ctx->stream));
+    if (n) {
+        TSG_CUDA(ctx, cudaMemcpyAsync(jac.p, powers, n * sizeof(g1_jac), cudaMemcpyHostToDevice, ctx->stream));
+        TSG_CUDA(ctx, launch_jac_to_xyzz(jac.as<g1_jac>(), n, xyzz.as<g1_xyzz>(), ctx->sm_count, ctx->stream));
+        TSG_CUDA(ctx, launch_batch_to_affine(xyzz.as<g1_xyzz>(), n, srs->d, ctx->sm_count, ctx->stream));
+        ctx->launches += 2;
+    }
+    TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = srs;
+    return TSGPU_OK;
+}
+
+int tsgpu_srs_download(tsgpu_ctx* ctx, const tsgpu_srs* srs, size_t first, size_t count, tsgpu_g1* out) {
+    if (!ctx || !srs || (!out && count)) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    if (first + count > srs->n) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "range exceeds SRS length");
+    if (!count) return TSGPU_OK;
+    TempBuf jac;
+    TSG_CUDA(ctx, jac.alloc(count * sizeof(g1_jac), ctx->stream));
+    TSG_CUDA(ctx, launch_affine_to_jac(srs->d + first, count, jac.as<g1_jac>(), ctx->sm_count, ctx->stream));
+    ctx->launches += 1;
+    TSG_CUDA(ctx, cudaMemcpyAsync(out, jac.p, count * sizeof(g1_jac), cudaMemcpyDeviceToHost, ctx->stream));
+    TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return TSGPU_OK;
+}
+
+size_t tsgpu_srs_len(const tsgpu_srs* srs) { return srs ? srs->n : 0; }
+void tsgpu_srs_free(tsgpu_ctx* ctx, tsgpu_srs* srs) {
+    (void)ctx;
+    if (!srs) return;
+    if (srs->d) cudaFree(srs->d);
+    delete srs;
+}
+
+// ------------------------------------------------------------------------------------------- polynomials in HBM
+int tsgpu_poly_upload(tsgpu_ctx* ctx, const tsgpu_fr* coeffs, size_t n, tsgpu_poly** out) {
+    if (!ctx || !out || (!coeffs && n)) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    tsgpu_poly* p = new (std::nothrow) tsgpu_poly;
+    if (!p) return fail(ctx, TSGPU_E_PROOF_GENERATION, "out of host memory");
+    p->n = n;
+    cudaError_t e = cudaMallocAsync((void**)&p->d, (n ? n : 1) * sizeof(fr_t), ctx->stream);
+    if (e != cudaSuccess) { delete p; return cuda_fail(ctx, e, "cudaMallocAsync(poly)"); }
+    if (n) TSG_CUDA(ctx, cudaMemcpyAsync(p->d, coeffs, n * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+    TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = p;
+    return TSGPU_OK;
+}
+int tsgpu_poly_download(tsgpu_ctx* ctx, const tsgpu_poly* p, tsgpu_fr* out) {
+    if (!ctx || !p || (!out && p->n)) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    if (p->n) TSG_CUDA(ctx, cudaMemcpyAsync(out, p->d, p->n * sizeof(fr_t), cudaMemcpyDeviceToHost, ctx->stream));
+    TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return TSGPU_OK;
+}
+size_t tsgpu_poly_len(const tsgpu_poly* p) { return p ? p->n : 0; }
+void tsgpu_poly_free(tsgpu_ctx* ctx, tsgpu_poly* p) {
+    if (!p) return;
+    if (p->d) cudaFreeAsync(p->d, ctx ? ctx->stream : nullptr);
+    delete p;
+}
+
+// ------------------------------------------------------------------------------------------- MSM / KZG
+int tsgpu_msm_g1(tsgpu_ctx* ctx, const tsgpu_g1a* bases, const tsgpu_fr* scalars, size_t n, tsgpu_g1* out) {
+    if (!ctx || !out || ((!bases || !scalars) && n)) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    TempBuf b, s;
+    TSG_CUDA(ctx, b.alloc(n * sizeof(g1_affine), ctx->stream));
+    TSG_CUDA(ctx, s.alloc(n * sizeof(fr_t), ctx->stream));
+    if (n) {
+        TSG_CUDA(ctx, cudaMemcpyAsync(b.p, bases, n * sizeof(g1_affine), cudaMemcpyHostToDevice, ctx->stream));
+        TSG_CUDA(ctx, cudaMemcpyAsync(s.p, scalars, n * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return msm_device(ctx, b.as<g1_affine>(), s.as<fr_t>(), n, out);
+}
+
+int tsgpu_kzg_commit_dev(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_poly* poly, tsgpu_g1* out) {
+    if (!ctx || !srs || !poly || !out) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    if (poly->n > srs->n) return fail(ctx, TSGPU_E_COMMITMENT, "Polynomial degree exceeds setup size");   // commitments.rs:166-170
+    return msm_device(ctx, srs->d, poly->d, poly->n, out);
+}
+
+int tsgpu_kzg_commit(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_fr* polynomial, size_t n, tsgpu_g1* out) {
+    if (!ctx || !srs || !out || (!polynomial && n)) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    if (n > srs->n) return fail(ctx, TSGPU_E_COMMITMENT, "Polynomial degree exceeds setup size");
+    TempBuf s;
+    TSG_CUDA(ctx, s.alloc(n * sizeof(fr_t), ctx->stream));
+    if (n) TSG_CUDA(ctx, cudaMemcpyAsync(s.p, polynomial, n * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+    return msm_device(ctx, srs->d, s.as<fr_t>(), n, out);
+}
+
+// value = P(z), proof = commit((P - value) / (x - z))   (commitments.rs:182-199)
+int tsgpu_kzg_open_dev(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_poly* poly, const tsgpu_fr* z, tsgpu_fr* value, tsgpu_g1* proof) {
+    if (!ctx || !srs || !poly || !z || !value || !proof) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    const size_t n = poly->n;
+    if (n == 0) {   // empty polynomial: value 0, empty quotient (commitments.rs:306-308, 322-324)
+        memset(value, 0, 32);
+        G1J id = G1J::identity(); memcpy(proof, &id, 96);
+        return TSGPU_OK;
+    }
+    if (n - 1 > srs->n) return fail(ctx, TSGPU_E_COMMITMENT, "Polynomial degree exceeds setup size");
+    // scan weights on the host: pw[s] = z^(SPAN 2^s), W = z^(THREADS SPAN)
+    Fr64 zz = Fr64::from_raw(z->l);
+    Fr64 w = zz;
+    for (size_t k = 1; k < POLY_SPAN; k <<= 1) w = w.sqr();   // z^SPAN (SPAN is a power of two)
+    fr_t pw[POLY_PW + 1];
+    for (int s = 0; s <= POLY_PW; ++s) { memcpy(pw[s].l, w.l, 32); w = w.sqr(); }
+    const size_t nblocks = poly_num_blocks(n);
+    TempBuf dpw, totals, carry, q, val;
+    TSG_CUDA(ctx, dpw.alloc(sizeof(pw), ctx->stream));
+    TSG_CUDA(ctx, totals.alloc(nblocks * sizeof(fr_t), ctx->stream));
+    TSG_CUDA(ctx, carry.alloc(nblocks * sizeof(fr_t), ctx->stream));
+    TSG_CUDA(ctx, q.alloc(n * sizeof(fr_t), ctx->stream));
+    TSG_CUDA(ctx, val.alloc(64, ctx->stream));
+    TSG_CUDA(ctx, cudaMemcpyAsync(dpw.p, pw, sizeof(pw), cudaMemcpyHostToDevice, ctx->stream));
+    fr_t zf; memcpy(zf.l, z->l, 32);
+    unsigned launches = 0;
+    TSG_CUDA(ctx, poly_open_launch(poly->d, n, zf, dpw.as<fr_t>(), pw[POLY_PW], totals.as<fr_t>(), carry.as<fr_t>(), q.as<fr_t>(), val.as<fr_t>(),
+                                   ctx->stream, &launches));
+    ctx->launches += launches;
+    TSG_CUDA(ctx, cudaMemcpyAsync(ctx->host_out, val.p, sizeof(fr_t), cudaMemcpyDeviceToHost, ctx->stream));
+    int rc = msm_device(ctx, srs->d, q.as<fr_t>(), n - 1, proof);
+    if (rc) return rc;
+    TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(value, ctx->host_out, 32);
+    return TSGPU_OK;
+}
+
+int tsgpu_kzg_open(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_fr* polynomial, size_t n, const tsgpu_fr* z, tsgpu_fr* value, tsgpu_g1* proof) {
+    tsgpu_poly* p = nullptr;
+    int rc = tsgpu_poly_upload(ctx, polynomial, n, &p);
+    if (rc) return rc;
+    rc = tsgpu_kzg_open_dev(ctx, srs, p, z, value, proof);
+    tsgpu_poly_free(ctx, p);
+    return rc;
+}
+
+// ---- host-side point helpers (CPU only): what the transcript and proof bytes need
+void tsgpu_g1_hash(const tsgpu_g1* p, tsgpu_fr* out) {            // KZGCommitmentValue::hash, commitments.rs:73-84
+    G1J j; memcpy(&j, p, 96);
+    Fr64 h = tsg::host::g1_hash(j);
+    memcpy(out->l, h.l, 32);
+}
+void tsgpu_g1_compress(const tsgpu_g1* p, uint8_t out[32]) {      // ark-serialize compressed (commitments.rs:106-118)
+    G1J j; memcpy(&j, p, 96);
+    tsg::host::g1_compress(j, out);
+}
+int tsgpu_g1_equal(const tsgpu_g1* a, const tsgpu_g1* b) {
+    G1J x, y; memcpy(&x, a, 96); memcpy(&y, b, 96);
+    return x.equals(y) ? 1 : 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,125 @@
+// g1.cuh - BN254 G1 arithmetic (y^2 = x^3 + 3 over Fq) for the KZG commitment MSM.
+//
+// The reference's G1Element is ark-ec's Jacobian G1Projective (src/utils.rs:17) and its commitment is a sum
+// of `generator * coeff` terms (src/commitments.rs:173-177).  Only the resulting group element is
+// observable (equality is cross-multiplied, serialisation normalises to affine), so the device is free to
+// use the cheapest coordinates: bucket sums live in extended Jacobian "XYZZ" form (x = X/ZZ, y = Y/ZZZ,
+// ZZ^3 = ZZZ^2; identity <=> ZZ = 0) where adding an affine SRS point costs 8M + 2S and never needs an
+// inversion.  Formulas: EFD shortw/xyzz (madd-2008-s, mdbl-2008-s-1, add-2008-s, dbl-2008-s-1), a = 0.
+// Host and device share this file (the host uses it for the final window combination).
+#pragma once
+#include "fp.cuh"
+
+namespace tsg {
+
+struct alignas(16) g1_affine {   // identity = (0, 0) (not on the curve), as arkworks' affine zero
+    fq_t x, y;
+    TSG_HD bool is_identity() const { return x.is_zero() && y.is_zero(); }
+};
+
+struct alignas(16) g1_jac {      // reference layout: Jacobian {x, y, z}, identity z = 0
+    fq_t x, y, z;
+};
+
+struct alignas(16) g1_xyzz {
+    fq_t X, Y, ZZ, ZZZ;
+
+    TSG_HD static g1_xyzz identity() { g1_xyzz r; r.X = fq_t::zero(); r.Y = fq_t::zero(); r.ZZ = fq_t::zero(); r.ZZZ = fq_t::zero(); return r; }
+    TSG_HD bool is_identity() const { return ZZ.is_zero(); }
+    TSG_HD static g1_xyzz from_affine(const g1_affine& p) {
+        if (p.is_identity()) return identity();
+        g1_xyzz r; r.X = p.x; r.Y = p.y; r.ZZ = fq_t::one(); r.ZZZ = fq_t::one(); return r;
+    }
+    TSG_HD g1_xyzz neg() const { g1_xyzz r = *this; r.Y = Y.neg(); return r; }
+
+    // 2 * (affine point)   mdbl-2008-s-1
+    TSG_HD static g1_xyzz dbl_affine(const g1_affine& p) {
+        if (p.is_identity() || p.y.is_zero()) return identity();
+        g1_xyzz r;
+        fq_t U = p.y.dbl(), V = U.sqr(), W = U * V, S = p.x * V;
+        fq_t xx = p.x.sqr(), M = xx.dbl() + xx;
+        r.X = M.sqr() - S.dbl();
+        r.Y = M * (S - r.X) - W * p.y;
+        r.ZZ = V; r.ZZZ = W;
+        return r;
+    }
+    // 2 * this   dbl-2008-s-1
+    TSG_HD g1_xyzz dbl() const {
+        if (is_identity() || Y.is_zero()) return identity();
+        g1_xyzz r;
+        fq_t U = Y.dbl(), V = U.sqr(), W = U * V, S = X * V;
+        fq_t xx = X.sqr(), M = xx.dbl() + xx;
+        r.X = M.sqr() - S.dbl();
+        r.Y = M * (S - r.X) - W * Y;
+        r.ZZ = V * ZZ; r.ZZZ = W * ZZZ;
+        return r;
+    }
+    // this + affine (optionally negated)   madd-2008-s
+    TSG_HD g1_xyzz add_affine(const g1_affine& q, bool negate = false) const {
+        if (q.is_identity()) return *this;
+        fq_t qy = negate ? q.y.neg() : q.y;
+        if (is_identity()) { g1_xyzz r; r.X = q.x; r.Y = qy; r.ZZ = fq_t::one(); r.ZZZ = fq_t::one(); return r; }
+        fq_t U2 = q.x * ZZ, S2 = qy * ZZZ;
+        fq_t P = U2 - X, R = S2 - Y;
+        if (P.is_zero()) {
+            if (R.is_zero()) { g1_affine t; t.x = q.x; t.y = qy; return dbl_affine(t); }
+            return identity();
+        }
+        fq_t PP = P.sqr(), PPP = P * PP, Q = X * PP;
+        g1_xyzz r;
+        r.X = R.sqr() - PPP - Q.dbl();
+        r.Y = R * (Q - r.X) - Y * PPP;
+        r.ZZ = ZZ * PP; r.ZZZ = ZZZ * PPP;
+        return r;
+    }
+    // this + o   add-2008-s
+    TSG_HD g1_xyzz add(const g1_xyzz& o) const {
+        if (o.is_identity()) return *this;
+        if (is_identity()) return o;
+        fq_t U1 = X * o.ZZ, U2 = o.X * ZZ, S1 = Y * o.ZZZ, S2 = o.Y * ZZZ;
+        fq_t P = U2 - U1, R = S2 - S1;
+        if (P.is_zero()) {
+            if (R.is_zero()) return dbl();
+            return identity();
+        }
+        fq_t PP = P.sqr(), PPP = P * PP, Q = U1 * PP;
+        g1_xyzz r;
+        r.X = R.sqr() - PPP - Q.dbl();
+        r.Y = R * (Q - r.X) - S1 * PPP;
+        r.ZZ = ZZ * o.ZZ * PP; r.ZZZ = ZZZ * o.ZZZ * PPP;
+        return r;
+    }
+    // k * this for a small scalar (double-and-add, MSB first)
+    TSG_HD g1_xyzz mul_small(unsigned long long k) const {
+        g1_xyzz acc = identity();
+        for (int i = 63; i >= 0; --i) {
+            acc = acc.dbl();
+            if ((k >> i) & 1) acc = acc.add(*this);
+        }
+        return acc;
+    }
+    // Jacobian representative of the same point: (X ZZ^2, Y ZZZ^2, ZZZ)
+    TSG_HD g1_jac to_jacobian() const {
+        g1_jac j;
+        if (is_identity()) { j.x = fq_t::one(); j.y = fq_t::one(); j.z = fq_t::zero(); return j; }
+        j.x = X * ZZ.sqr(); j.y = Y * ZZZ.sqr(); j.z = ZZZ;
+        return j;
+    }
+    TSG_HD static g1_xyzz from_jacobian(const g1_jac& j) {
+        if (j.z.is_zero()) return identity();
+        g1_xyzz r; r.X = j.x; r.Y = j.y; r.ZZ = j.z.sqr(); r.ZZZ = r.ZZ * j.z;
+        return r;
+    }
+    // affine normalisation (one inversion); host-side use
+    TSG_HD g1_affine to_affine() const {
+        g1_affine a;
+        if (is_identity()) { a.x = fq_t::zero(); a.y = fq_t::zero(); return a; }
+        fq_t t = ZZZ.inverse();        // 1/ZZZ
+        fq_t u = ZZ * t;               // ZZ/ZZZ = 1/Z
+        a.x = X * u.sqr();             // X / ZZ
+        a.y = Y * t;
+        return a;
+    }
+};
+
+}  // namespace tsg

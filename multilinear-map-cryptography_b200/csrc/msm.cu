@@ -1,0 +1,326 @@
+// msm.cu - KZG commitment as a Pippenger multi-scalar multiplication on BN254 G1, plus SRS generation.
+//
+// Replaces KZGCommitment::commit (src/commitments.rs:162-180: a serial sum of n double-and-add scalar
+// multiplications) and the g1_powers loop of setup_params (src/utils.rs:89-96).  The group element
+// produced is the same; the algorithm is:
+//   1. scalars Montgomery -> canonical, signed base-2^c digits (c <= 16), W = ceil(255 / c) windows
+//   2. counting sort of (window, |digit|) -> point index lists (histogram, exclusive scan, scatter)
+//   3. bucket accumulation: one thread per work item (a bucket, or a slice of at most MSM_CHUNK entries of
+//      an over-full bucket), XYZZ accumulator + affine SRS point = 8M + 2S, sign applied to y
+//   4. per-window bucket reduction sum_b b * B_b by blocked running sums, then a tree sum per window
+//   5. the W window sums go to the host, which combines them (W * c doublings: microseconds of work)
+// Integer-pipe bound: ~ n * W * 10 Fq products; memory traffic is the 64-byte gathers of step 3.
+#include <cstdio>
+#include "fr_device.cuh"
+#include "g1.cuh"
+#include "msm.cuh"
+
+namespace tsg {
+
+__device__ __forceinline__ g1_affine ld_affine(const g1_affine* p) {
+    g1_affine a;
+    a.x = ld256_nc(&p->x); a.y = ld256_nc(&p->y);
+    return a;
+}
+__device__ __forceinline__ g1_xyzz ld_xyzz(const g1_xyzz* p) {
+    g1_xyzz a;
+    a.X = ld256_cg(&p->X); a.Y = ld256_cg(&p->Y); a.ZZ = ld256_cg(&p->ZZ); a.ZZZ = ld256_cg(&p->ZZZ);
+    return a;
+}
+__device__ __forceinline__ void st_xyzz(g1_xyzz* p, const g1_xyzz& v) {
+    st256(&p->X, v.X); st256(&p->Y, v.Y); st256(&p->ZZ, v.ZZ); st256(&p->ZZZ, v.ZZZ);
+}
+
+// ---------------------------------------------------------------- 1. digits + histogram
+__global__ void k_msm_digits(const fr_t* scalars, size_t n, unsigned c, unsigned W, unsigned* dig, unsigned* hist) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const unsigned nb = 1u << (c - 1);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        fr_t s = ld256_nc(scalars + i).from_mont();
+        unsigned carry = 0;
+        for (unsigned w = 0; w < W; ++w) {
+            unsigned bit = w * c, limb = bit >> 5, off = bit & 31;
+            unsigned long long two = limb < 8 ? s.l[limb] : 0u;
+            if (limb + 1 < 8) two |= (unsigned long long)s.l[limb + 1] << 32;
+            unsigned d = (unsigned)((two >> off) & ((1u << c) - 1)) + carry;
+            unsigned sign = 0;
+            if (d > nb) { d = (1u << c) - d; sign = 1; carry = 1; } else carry = 0;
+            dig[(size_t)w * n + i] = d | (sign << 31);
+            if (d) atomicAdd(&hist[(size_t)w * nb + d - 1], 1u);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- 2. exclusive scan (single block, any length)
+__global__ void k_exclusive_scan(const unsigned* in, unsigned* out, size_t n, unsigned* total) {
+    __shared__ unsigned long long sums[1024];
+    const size_t per = (n + blockDim.x - 1) / blockDim.x;
+    const size_t b = (size_t)threadIdx.x * per, e = b + per < n ? b + per : n;
+    unsigned long long s = 0;
+    for (size_t i = b; i < e; ++i) s += in[i];
+    sums[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long acc = 0;
+        for (unsigned t = 0; t < blockDim.x; ++t) { unsigned long long v = sums[t]; sums[t] = acc; acc += v; }
+        if (total) *total = (unsigned)acc;
+    }
+    __syncthreads();
+    unsigned acc = (unsigned)sums[threadIdx.x];
+    for (size_t i = b; i < e; ++i) { unsigned v = in[i]; out[i] = acc; acc += v; }
+}
+
+// ---------------------------------------------------------------- 3. scatter point indices into bucket order
+__global__ void k_msm_scatter(const unsigned* dig, size_t n, unsigned c, unsigned W, const unsigned* offsets, unsigned* cursor, unsigned* sorted) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const unsigned nb = 1u << (c - 1);
+    const size_t total = (size_t)W * n;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        unsigned v = dig[t];
+        unsigned d = v & 0x7fffffffu;
+        if (!d) continue;
+        size_t w = t / n, i = t - w * n;
+        size_t b = w * nb + d - 1;
+        unsigned pos = offsets[b] + atomicAdd(&cursor[b], 1u);
+        sorted[pos] = (unsigned)i | (v & 0x80000000u);
+    }
+}
+
+// ---------------------------------------------------------------- work items: slices of at most MSM_CHUNK entries
+__global__ void k_msm_item_counts(const unsigned* hist, size_t nbuckets, unsigned* items) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < nbuckets; b += stride)
+        items[b] = (hist[b] + MSM_CHUNK - 1) / MSM_CHUNK;
+}
+__global__ void k_msm_item_fill(const unsigned* items, const unsigned* item_off, size_t nbuckets, unsigned* item_bucket) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < nbuckets; b += stride) {
+        unsigned k = items[b], o = item_off[b];
+        for (unsigned j = 0; j < k; ++j) item_bucket[o + j] = (unsigned)b;
+    }
+}
+
+// ---------------------------------------------------------------- 3b. bucket accumulation (the hot kernel)
+__global__ void __launch_bounds__(MSM_ACC_THREADS) k_msm_accumulate(const g1_affine* bases, const unsigned* sorted, const unsigned* hist, const unsigned* offsets,
+                                                                  const unsigned* item_off, const unsigned* item_bucket, const unsigned* n_items,
+                                                                  g1_xyzz* partial) {
+    const unsigned M = *n_items;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t it = (size_t)blockIdx.x * blockDim.x + threadIdx.x; it < M; it += stride) {
+        unsigned b = item_bucket[it];
+        unsigned k = (unsigned)it - item_off[b];
+        unsigned cnt = hist[b], base = offsets[b];
+        unsigned lo = k * MSM_CHUNK, hi = lo + MSM_CHUNK < cnt ? lo + MSM_CHUNK : cnt;
+        g1_xyzz acc = g1_xyzz::identity();
+        for (unsigned p = lo; p < hi; ++p) {
+            unsigned v = sorted[base + p];
+            g1_affine pt = ld_affine(bases + (v & 0x7fffffffu));
+            acc = acc.add_affine(pt, (v >> 31) != 0);
+        }
+        st_xyzz(partial + it, acc);
+    }
+}
+
+// ---------------------------------------------------------------- 4. window reduction, stage 1:
+// thread t of window w owns MSM_RED_SPAN consecutive buckets; out = sum_j (lo + j) * B_{lo+j}
+__global__ void __launch_bounds__(128) k_msm_bucket_reduce(const g1_xyzz* partial, const unsigned* items, const unsigned* item_off, unsigned c, unsigned W,
+                                                           g1_xyzz* blockres) {
+    const unsigned nb = 1u << (c - 1);
+    const unsigned span = nb < MSM_RED_SPAN ? nb : MSM_RED_SPAN;
+    const unsigned per_window = nb / span;
+    const size_t total = (size_t)W * per_window;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        size_t w = t / per_window; unsigned blk = (unsigned)(t - w * per_window);
+        unsigned lo = blk * span;   // bucket ids lo+1 .. lo+span
+        g1_xyzz running = g1_xyzz::identity(), acc = g1_xyzz::identity();
+        for (unsigned j = span; j-- > 0;) {
+            size_t b = w * nb + lo + j;
+            unsigned k = items[b], o = item_off[b];
+            for (unsigned q = 0; q < k; ++q) running = running.add(ld_xyzz(partial + o + q));
+            acc = acc.add(running);
+        }
+        if (lo) acc = acc.add(running.mul_small(lo));
+        st_xyzz(blockres + t, acc);
+    }
+}
+
+// stage 2: one block per window sums its `count` block results; writes Jacobian {x,y,z}
+__global__ void __launch_bounds__(MSM_SUM_THREADS) k_msm_window_sum(const g1_xyzz* blockres, unsigned count, g1_jac* out) {
+    __shared__ g1_xyzz sh[MSM_SUM_THREADS];
+    const g1_xyzz* src = blockres + (size_t)blockIdx.x * count;
+    g1_xyzz acc = g1_xyzz::identity();
+    for (unsigned i = threadIdx.x; i < count; i += blockDim.x) acc = acc.add(ld_xyzz(src + i));
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (unsigned s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sh[threadIdx.x] = sh[threadIdx.x].add(sh[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        g1_jac j = sh[0].to_jacobian();
+        st256(&out[blockIdx.x].x, j.x); st256(&out[blockIdx.x].y, j.y); st256(&out[blockIdx.x].z, j.z);
+    }
+}
+
+// ---------------------------------------------------------------- SRS generation: out[i] = tau^i * G
+// powers of tau: thread handles MSM_POW_SPAN consecutive exponents
+__global__ void k_tau_powers(const fr_t tau, size_t first, size_t n, fr_t* out) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t nchunks = (n + MSM_POW_SPAN - 1) / MSM_POW_SPAN;
+    for (size_t ch = (size_t)blockIdx.x * blockDim.x + threadIdx.x; ch < nchunks; ch += stride) {
+        size_t b = ch * MSM_POW_SPAN, e = b + MSM_POW_SPAN < n ? b + MSM_POW_SPAN : n;
+        fr_t cur = tau.pow_u64(first + b);
+        for (size_t i = b; i < e; ++i) { st256(out + i, cur); cur = cur * tau; }
+    }
+}
+// fixed-base multiplication with a byte-window table: table[w * 255 + d - 1] = d * 256^w * G (affine)
+__global__ void __launch_bounds__(128) k_fixed_base_mul(const fr_t* scalars, size_t n, const g1_affine* table, g1_xyzz* out) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        fr_t s = ld256_nc(scalars + i).from_mont();
+        g1_xyzz acc = g1_xyzz::identity();
+#pragma unroll 1
+        for (int w = 0; w < 32; ++w) {
+            unsigned d = (s.l[w >> 2] >> (8 * (w & 3))) & 0xffu;
+            if (d) acc = acc.add_affine(ld_affine(table + w * 255 + d - 1));
+        }
+        st_xyzz(out + i, acc);
+    }
+}
+
+// XYZZ -> affine with Montgomery batch inversion over MSM_INV_SPAN points per thread
+__global__ void __launch_bounds__(128) k_batch_to_affine(const g1_xyzz* in, size_t n, g1_affine* out) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t nchunks = (n + MSM_INV_SPAN - 1) / MSM_INV_SPAN;
+    for (size_t ch = (size_t)blockIdx.x * blockDim.x + threadIdx.x; ch < nchunks; ch += stride) {
+        size_t b = ch * MSM_INV_SPAN, e = b + MSM_INV_SPAN < n ? b + MSM_INV_SPAN : n;
+        // forward: out[i].x temporarily holds the prefix product of the ZZZ's before i
+        fq_t acc = fq_t::one();
+        for (size_t i = b; i < e; ++i) {
+            st256(&out[i].x, acc);
+            fq_t z = ld256_nc(&in[i].ZZZ);
+            if (!z.is_zero()) acc = acc * z;
+        }
+        fq_t inv = acc.inverse();
+        for (size_t i = e; i-- > b;) {
+            g1_xyzz p; p.X = ld256_nc(&in[i].X); p.Y = ld256_nc(&in[i].Y); p.ZZ = ld256_nc(&in[i].ZZ); p.ZZZ = ld256_nc(&in[i].ZZZ);
+            if (p.ZZZ.is_zero()) { st256(&out[i].x, fq_t::zero()); st256(&out[i].y, fq_t::zero()); continue; }
+            fq_t pref = ld256(&out[i].x);
+            fq_t t = inv * pref;          // 1 / ZZZ_i
+            inv = inv * p.ZZZ;
+            fq_t u = p.ZZ * t;            // 1 / Z_i
+            st256(&out[i].x, p.X * u.sqr());
+            st256(&out[i].y, p.Y * t);
+        }
+    }
+}
+
+// Jacobian {x,y,z} (reference G1Projective) -> XYZZ, for SRS upload
+__global__ void k_jac_to_xyzz(const g1_jac* in, size_t n, g1_xyzz* out) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        g1_jac j; j.x = ld256_nc(&in[i].x); j.y = ld256_nc(&in[i].y); j.z = ld256_nc(&in[i].z);
+        st_xyzz(out + i, g1_xyzz::from_jacobian(j));
+    }
+}
+// affine -> Jacobian with z = 1 (identity -> z = 0), for returning g1_powers to the host
+__global__ void k_affine_to_jac(const g1_affine* in, size_t n, g1_jac* out) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        g1_affine a = ld_affine(in + i);
+        bool id = a.is_identity();
+        st256(&out[i].x, id ? fq_t::one() : a.x); st256(&out[i].y, id ? fq_t::one() : a.y); st256(&out[i].z, id ? fq_t::zero() : fq_t::one());
+    }
+}
+
+// ---------------------------------------------------------------- launchers
+static inline int gridfor(size_t work, int threads, size_t cap) {
+    size_t g = (work + threads - 1) / threads;
+    if (g < 1) g = 1;
+    return (int)(g < cap ? g : cap);
+}
+
+unsigned msm_window_bits(size_t n) {
+    unsigned lg = 0; while (((size_t)1 << (lg + 1)) <= n) ++lg;
+    int c = (int)lg - 3;
+    if (c < 4) c = 4;
+    if (c > 16) c = 16;
+    return (unsigned)c;
+}
+
+size_t msm_scratch_bytes(size_t n, unsigned c, MsmLayout* L) {
+    const unsigned W = (255 + c - 1) / c;
+    const size_t nb = (size_t)1 << (c - 1), nbuckets = W * nb;
+    const size_t max_items = nbuckets + (W * n) / MSM_CHUNK + 1;
+    const unsigned span = nb < MSM_RED_SPAN ? (unsigned)nb : MSM_RED_SPAN;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    L->c = c; L->W = W; L->nbuckets = nbuckets; L->max_items = max_items; L->blocks_per_window = (unsigned)(nb / span);
+    L->dig = take(W * n * 4);
+    L->sorted = take(W * n * 4);
+    L->hist = take(nbuckets * 4);
+    L->offsets = take(nbuckets * 4);
+    L->cursor = take(nbuckets * 4);
+    L->items = take(nbuckets * 4);
+    L->item_off = take(nbuckets * 4);
+    L->item_bucket = take(max_items * 4);
+    L->n_items = take(256);
+    L->partial = take(max_items * sizeof(g1_xyzz));
+    L->blockres = take((size_t)W * L->blocks_per_window * sizeof(g1_xyzz));
+    L->window_out = take(W * sizeof(g1_jac));
+    return off;
+}
+
+// returns the number of kernels launched through *launches
+cudaError_t msm_run(const g1_affine* bases, const fr_t* scalars, size_t n, const MsmLayout& L, unsigned char* scratch, int sm_count,
+                    cudaStream_t s, unsigned* launches) {
+    unsigned* dig = (unsigned*)(scratch + L.dig); unsigned* sorted = (unsigned*)(scratch + L.sorted);
+    unsigned* hist = (unsigned*)(scratch + L.hist); unsigned* offsets = (unsigned*)(scratch + L.offsets);
+    unsigned* cursor = (unsigned*)(scratch + L.cursor); unsigned* items = (unsigned*)(scratch + L.items);
+    unsigned* item_off = (unsigned*)(scratch + L.item_off); unsigned* item_bucket = (unsigned*)(scratch + L.item_bucket);
+    unsigned* n_items = (unsigned*)(scratch + L.n_items);
+    g1_xyzz* partial = (g1_xyzz*)(scratch + L.partial); g1_xyzz* blockres = (g1_xyzz*)(scratch + L.blockres);
+    g1_jac* wout = (g1_jac*)(scratch + L.window_out);
+    cudaError_t e;
+    // hist and cursor are adjacent-independent regions: clear both
+    if ((e = cudaMemsetAsync(hist, 0, L.nbuckets * 4, s))) return e;
+    if ((e = cudaMemsetAsync(cursor, 0, L.nbuckets * 4, s))) return e;
+    const size_t cap = (size_t)sm_count * 8;
+    k_msm_digits<<<gridfor(n, 256, cap), 256, 0, s>>>(scalars, n, L.c, L.W, dig, hist);
+    k_exclusive_scan<<<1, 1024, 0, s>>>(hist, offsets, L.nbuckets, nullptr);
+    k_msm_scatter<<<gridfor((size_t)L.W * n, 256, cap), 256, 0, s>>>(dig, n, L.c, L.W, offsets, cursor, sorted);
+    k_msm_item_counts<<<gridfor(L.nbuckets, 256, cap), 256, 0, s>>>(hist, L.nbuckets, items);
+    k_exclusive_scan<<<1, 1024, 0, s>>>(items, item_off, L.nbuckets, n_items);
+    k_msm_item_fill<<<gridfor(L.nbuckets, 256, cap), 256, 0, s>>>(items, item_off, L.nbuckets, item_bucket);
+    k_msm_accumulate<<<gridfor(L.max_items, MSM_ACC_THREADS, (size_t)sm_count * 16), MSM_ACC_THREADS, 0, s>>>(bases, sorted, hist, offsets, item_off, item_bucket, n_items, partial);
+    k_msm_bucket_reduce<<<gridfor((size_t)L.W * L.blocks_per_window, 128, cap), 128, 0, s>>>(partial, items, item_off, L.c, L.W, blockres);
+    k_msm_window_sum<<<L.W, MSM_SUM_THREADS, 0, s>>>(blockres, L.blocks_per_window, wout);
+    if (launches) *launches += 9;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tau_powers(const fr_t& tau, size_t first, size_t n, fr_t* out, int sm_count, cudaStream_t s) {
+    size_t chunks = (n + MSM_POW_SPAN - 1) / MSM_POW_SPAN;
+    k_tau_powers<<<gridfor(chunks, 128, (size_t)sm_count * 8), 128, 0, s>>>(tau, first, n, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_fixed_base_mul(const fr_t* scalars, size_t n, const g1_affine* table, g1_xyzz* out, int sm_count, cudaStream_t s) {
+    k_fixed_base_mul<<<gridfor(n, 128, (size_t)sm_count * 16), 128, 0, s>>>(scalars, n, table, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_batch_to_affine(const g1_xyzz* in, size_t n, g1_affine* out, int sm_count, cudaStream_t s) {
+    size_t chunks = (n + MSM_INV_SPAN - 1) / MSM_INV_SPAN;
+    k_batch_to_affine<<<gridfor(chunks, 128, (size_t)sm_count * 16), 128, 0, s>>>(in, n, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_jac_to_xyzz(const g1_jac* in, size_t n, g1_xyzz* out, int sm_count, cudaStream_t s) {
+    k_jac_to_xyzz<<<gridfor(n, 128, (size_t)sm_count * 16), 128, 0, s>>>(in, n, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_affine_to_jac(const g1_affine* in, size_t n, g1_jac* out, int sm_count, cudaStream_t s) {
+    k_affine_to_jac<<<gridfor(n, 256, (size_t)sm_count * 8), 256, 0, s>>>(in, n, out);
+    return cudaGetLastError();
+}
+
+}  // namespace tsg

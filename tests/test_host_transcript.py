@@ -50,3 +50,16 @@ def test_sumcheck_verify_host(tsgpu, oracle):
     with pytest.raises(tsgpu.TwistAndShoutError) as e:
         tsgpu.SumCheck(4, claimed).verify(proof, tsgpu.Transcript())
     assert e.value.variant == "SumCheck"
+
+
+def test_g1_host_helpers_match_oracle(tsgpu, oracle):
+    """hash (commitments.rs:73-84), compressed bytes and equality of G1 points - CPU-only entry points."""
+    g = oracle.g1_generator()
+    pts = [g, oracle.g1_add(g, g), oracle.g1_mul(g, oracle.fr_from_ints([123456789])[0]),
+           oracle.g1_mul(g, oracle.fr_from_ints([oracle.R_MOD - 1])[0]), oracle.g1_mul(g, oracle.fr_from_ints([0])[0])]
+    for p in pts:
+        assert tsgpu.g1_compress(p) == oracle.g1_compress(p)
+        assert (tsgpu.g1_hash(p) == oracle.g1_hash(p)).all()
+    assert tsgpu.g1_compress(g).hex() == "01" + "00" * 31            # SURVEY Appendix C: 1*G = (1, 2)
+    assert tsgpu.g1_equal(pts[1], oracle.g1_mul(g, oracle.fr_from_ints([2])[0]))
+    assert not tsgpu.g1_equal(pts[1], pts[2])
