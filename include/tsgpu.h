@@ -124,6 +124,19 @@ void tsgpu_srs_free(tsgpu_ctx* ctx, tsgpu_srs* srs);
 int tsgpu_poly_upload(tsgpu_ctx* ctx, const tsgpu_fr* coeffs, size_t n, tsgpu_poly** out);
 int tsgpu_poly_download(tsgpu_ctx* ctx, const tsgpu_poly* p, tsgpu_fr* out);
 size_t tsgpu_poly_len(const tsgpu_poly* p);
+/* padded vectors as Twist/Shout::prove build them: Fr::from(v[i]) / given values, zero-filled up to `padded`
+ * (src/twist.rs:115-148, src/shout.rs:105-118) */
+int tsgpu_poly_from_u64(tsgpu_ctx* ctx, const uint64_t* v, size_t n, size_t padded, tsgpu_poly** out);
+int tsgpu_poly_upload_padded(tsgpu_ctx* ctx, const tsgpu_fr* vals, size_t n, size_t padded, tsgpu_poly** out);
+
+/* ---- vector_to_polynomial: poly_utils::lagrange_interpolate over x_i = i  (src/twist.rs:307-315,
+ * src/shout.rs:277-285, src/polynomials.rs:301-352) --------------------------------------------------------
+ * Same (unique) coefficients in O(n log^2 n): Newton differences as a convolution + falling-factorial ->
+ * monomial conversion, NTTs over Fr.  n must be a power of two <= 2^27 (Twist/Shout pad to one);
+ * otherwise TSGPU_E_POLYNOMIAL.  prepare() builds the size-dependent tables once (done implicitly on first use). */
+int tsgpu_interpolate_prepare(tsgpu_ctx* ctx, unsigned log_n);
+int tsgpu_interpolate_iota(tsgpu_ctx* ctx, const tsgpu_fr* values, size_t n, tsgpu_fr* coeffs);
+int tsgpu_poly_interpolate_iota(tsgpu_ctx* ctx, tsgpu_poly* values_to_coeffs_in_place);
 void tsgpu_poly_free(tsgpu_ctx* ctx, tsgpu_poly* p);
 
 /* ---- CommitmentScheme for KZGCommitment  (src/commitments.rs:156-199) -------------------------------------

@@ -192,6 +192,28 @@ class Context:
         self.check(lib().tsgpu_poly_upload(self._h, _p(coeffs), C.c_size_t(coeffs.shape[0]), C.byref(h)))
         return Poly(self, h)
 
+    def poly_from_u64(self, v, padded: Optional[int] = None) -> "Poly":
+        v = np.ascontiguousarray(v, dtype=np.uint64).reshape(-1)
+        h = C.c_void_p()
+        self.check(lib().tsgpu_poly_from_u64(self._h, _p(v), C.c_size_t(v.shape[0]), C.c_size_t(padded or v.shape[0]), C.byref(h)))
+        return Poly(self, h)
+
+    def poly_upload_padded(self, vals, padded: int) -> "Poly":
+        vals = _fr(vals)
+        h = C.c_void_p()
+        self.check(lib().tsgpu_poly_upload_padded(self._h, _p(vals), C.c_size_t(vals.shape[0]), C.c_size_t(padded), C.byref(h)))
+        return Poly(self, h)
+
+    def interpolate_prepare(self, log_n: int):
+        self.check(lib().tsgpu_interpolate_prepare(self._h, C.c_uint(log_n)))
+
+    def interpolate_iota(self, values) -> np.ndarray:
+        """poly_utils::lagrange_interpolate on the points (i, values[i]) (src/polynomials.rs:301-352)"""
+        values = _fr(values)
+        out = np.empty_like(values)
+        self.check(lib().tsgpu_interpolate_iota(self._h, _p(values), C.c_size_t(values.shape[0]), _p(out)))
+        return out
+
     def msm_g1(self, bases_affine, scalars) -> np.ndarray:
         bases_affine = np.ascontiguousarray(bases_affine, dtype=np.uint64).reshape(-1, 8)
         scalars = _fr(scalars)
@@ -422,6 +444,11 @@ class Poly:
         out = np.empty((len(self), 4), dtype=np.uint64)
         self.ctx.check(lib().tsgpu_poly_download(self.ctx._h, self._h, _p(out)))
         return out
+
+    def interpolate_iota(self):
+        """in place: values at 0..n-1 -> monomial coefficients"""
+        self.ctx.check(lib().tsgpu_poly_interpolate_iota(self.ctx._h, self._h))
+        return self
 
     def free(self):
         if self._h:

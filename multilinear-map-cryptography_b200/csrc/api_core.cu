@@ -5,6 +5,7 @@
 #include "context.cuh"
 #include "mle.cuh"
 #include "sumcheck.cuh"
+#include "interp.cuh"
 
 using namespace tsg;
 
@@ -85,6 +86,7 @@ void tsgpu_destroy(tsgpu_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    interp_destroy(ctx);
     if (ctx->partials) cudaFree(ctx->partials);
     if (ctx->ticket) cudaFree(ctx->ticket);
     if (ctx->dev_out) cudaFree(ctx->dev_out);

@@ -5,6 +5,8 @@
 #include "context.cuh"
 #include "msm.cuh"
 #include "poly.cuh"
+#include "interp.cuh"
+#include "mle.cuh"
 #include "../host/field64.hpp"
 
 using namespace tsg;
@@ -172,6 +174,71 @@ void tsgpu_poly_free(tsgpu_ctx* ctx, tsgpu_poly* p) {
     if (!p) return;
     if (p->d) cudaFreeAsync(p->d, ctx ? ctx->stream : nullptr);
     delete p;
+}
+
+// values[i] = Fr::from(v[i]) for i < n, zero-padded to `padded` entries (twist.rs:115-122,141-148)
+int tsgpu_poly_from_u64(tsgpu_ctx* ctx, const uint64_t* v, size_t n, size_t padded, tsgpu_poly** out) {
+    if (!ctx || !out || (!v && n) || padded < n) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "bad argument");
+    tsgpu_poly* p = new (std::nothrow) tsgpu_poly;
+    if (!p) return fail(ctx, TSGPU_E_PROOF_GENERATION, "out of host memory");
+    p->n = padded;
+    cudaError_t e = cudaMallocAsync((void**)&p->d, (padded ? padded : 1) * sizeof(fr_t), ctx->stream);
+    if (e != cudaSuccess) { delete p; return cuda_fail(ctx, e, "cudaMallocAsync(poly)"); }
+    if (padded > n) TSG_CUDA(ctx, cudaMemsetAsync(p->d + n, 0, (padded - n) * sizeof(fr_t), ctx->stream));
+    TempBuf src;
+    TSG_CUDA(ctx, src.alloc(n * 8, ctx->stream));
+    if (n) {
+        TSG_CUDA(ctx, cudaMemcpyAsync(src.p, v, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        TSG_CUDA(ctx, launch_fr_from_u64(src.as<unsigned long long>(), n, p->d, 0, 0, ctx->sm_count, ctx->stream));
+        ctx->launches += 1;
+    }
+    TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = p;
+    return TSGPU_OK;
+}
+// host values, zero-padded to `padded` entries (Vec::resize, twist.rs:146-148)
+int tsgpu_poly_upload_padded(tsgpu_ctx* ctx, const tsgpu_fr* vals, size_t n, size_t padded, tsgpu_poly** out) {
+    if (!ctx || !out || (!vals && n) || padded < n) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "bad argument");
+    tsgpu_poly* p = new (std::nothrow) tsgpu_poly;
+    if (!p) return fail(ctx, TSGPU_E_PROOF_GENERATION, "out of host memory");
+    p->n = padded;
+    cudaError_t e = cudaMallocAsync((void**)&p->d, (padded ? padded : 1) * sizeof(fr_t), ctx->stream);
+    if (e != cudaSuccess) { delete p; return cuda_fail(ctx, e, "cudaMallocAsync(poly)"); }
+    if (padded > n) TSG_CUDA(ctx, cudaMemsetAsync(p->d + n, 0, (padded - n) * sizeof(fr_t), ctx->stream));
+    if (n) TSG_CUDA(ctx, cudaMemcpyAsync(p->d, vals, n * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+    TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = p;
+    return TSGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------- interpolation
+static int log2_exact(size_t n) { int l = 0; while (((size_t)1 << l) < n) ++l; return ((size_t)1 << l) == n ? l : -1; }
+
+int tsgpu_interpolate_prepare(tsgpu_ctx* ctx, unsigned log_n) {
+    if (!ctx) return TSGPU_E_INVALID_PARAMETERS;
+    if (log_n > 27) return fail(ctx, TSGPU_E_POLYNOMIAL, "interpolation size exceeds the 2^28 two-adicity of Fr");
+    TSG_CUDA(ctx, interp_prepare(ctx, log_n));
+    TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return TSGPU_OK;
+}
+// in place: values at x = 0..n-1  ->  monomial coefficients (poly_utils::lagrange_interpolate on x_i = i)
+int tsgpu_poly_interpolate_iota(tsgpu_ctx* ctx, tsgpu_poly* p) {
+    if (!ctx || !p) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    if (p->n == 0) return TSGPU_OK;   // lagrange_interpolate(&[]) = [] (polynomials.rs:303-305)
+    int l = log2_exact(p->n);
+    if (l < 0) return fail(ctx, TSGPU_E_POLYNOMIAL, "interpolation length must be a power of two (Twist/Shout pad first)");
+    if (l > 27) return fail(ctx, TSGPU_E_POLYNOMIAL, "interpolation size exceeds the 2^28 two-adicity of Fr");
+    TSG_CUDA(ctx, interp_run(ctx, p->d, (unsigned)l, p->d));
+    return TSGPU_OK;
+}
+int tsgpu_interpolate_iota(tsgpu_ctx* ctx, const tsgpu_fr* values, size_t n, tsgpu_fr* coeffs) {
+    tsgpu_poly* p = nullptr;
+    int rc = tsgpu_poly_upload(ctx, values, n, &p);
+    if (rc) return rc;
+    rc = tsgpu_poly_interpolate_iota(ctx, p);
+    if (!rc) rc = tsgpu_poly_download(ctx, p, coeffs);
+    tsgpu_poly_free(ctx, p);
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------- MSM / KZG

@@ -20,6 +20,7 @@ struct tsgpu_ctx {
     tsg::fr_t* dev_out = nullptr;      // 8 elements
     tsg::fr_t* host_out = nullptr;     // pinned, 8 elements
     void* comm = nullptr;              // multi-GPU communicator (comm.cu), optional
+    void* interp = nullptr;            // cached interpolation plan (interp.cu)
 };
 
 struct tsgpu_table {
