@@ -179,6 +179,52 @@ int tsgpu_sumcheck_prove_product(tsgpu_ctx* ctx, tsgpu_table* const* tables, int
 int tsgpu_sumcheck_verify(unsigned num_vars, const tsgpu_fr* claimed_sum, const tsgpu_fr* round_polys, size_t num_rounds,
                           const tsgpu_fr* final_evaluation, tsgpu_transcript* transcript, int* valid, tsgpu_fr* challenges);
 
+/* ---- setup_params, Twist::prove / verify, Shout::prove / verify  (host orchestration over the calls above) --
+ * setup_params(log_size) (src/utils.rs:79-131): max_operations = 4 * 2^log_size, tau = first Fr::rand of
+ * ChaCha20Rng::from_seed([42; 32]), g1_powers[0 ..= max_operations] generated on the device, 32-byte
+ * Fiat-Shamir seed from the same rng. */
+typedef struct tsgpu_params tsgpu_params;
+typedef struct tsgpu_proof tsgpu_proof;    /* TwistProof / ShoutProof: 2 commitments, SumCheckProof, 0|2 openings, 0|2 evaluations */
+int tsgpu_setup_params(tsgpu_ctx* ctx, size_t log_size, tsgpu_params** out);
+void tsgpu_params_free(tsgpu_ctx* ctx, tsgpu_params* p);
+size_t tsgpu_params_log_size(const tsgpu_params* p);
+size_t tsgpu_params_max_operations(const tsgpu_params* p);
+void tsgpu_params_tau(const tsgpu_params* p, tsgpu_fr* out);
+void tsgpu_params_fiat_shamir_seed(const tsgpu_params* p, uint8_t out[32]);
+const tsgpu_srs* tsgpu_params_srs(const tsgpu_params* p);
+
+/* Twist::prove(&MemoryTrace) (src/twist.rs:107-252).  operations[i] = {address: addresses[i], value: values[i]},
+ * is_write[i] != 0 for MemoryOp::Write.  TSGPU_E_INVALID_PARAMETERS "Too many operations" beyond max_operations. */
+int tsgpu_twist_prove(tsgpu_ctx* ctx, const tsgpu_params* params, const uint64_t* addresses, const tsgpu_fr* values,
+                      const uint8_t* is_write, size_t num_operations, tsgpu_proof** out);
+/* same with the two zero-padded vectors already in HBM (consumed) */
+int tsgpu_twist_prove_dev(tsgpu_ctx* ctx, const tsgpu_params* params, tsgpu_poly* padded_addresses, tsgpu_poly* padded_values, tsgpu_proof** out);
+/* Shout::prove(&LookupTable) (src/shout.rs:97-222): entries = table.entries, lookup_indices[i] = lookups[i].index.
+ * TSGPU_E_INVALID_PARAMETERS "Too many lookup operations" beyond max_operations. */
+int tsgpu_shout_prove(tsgpu_ctx* ctx, const tsgpu_params* params, const tsgpu_fr* entries, size_t num_entries,
+                      const uint64_t* lookup_indices, size_t num_lookups, tsgpu_proof** out);
+/* Twist::verify / Shout::verify control flow (src/twist.rs:255-304, src/shout.rs:225-274): transcript replay,
+ * SumCheck::verify, opening checks.  The opening check uses the trapdoor kept in the params (src/utils.rs:107)
+ * instead of the pairing of src/commitments.rs:201-228 (CPU pairing verifier: next row). */
+int tsgpu_twist_verify(tsgpu_ctx* ctx, const tsgpu_params* params, const tsgpu_proof* proof, int* valid);
+int tsgpu_shout_verify(tsgpu_ctx* ctx, const tsgpu_params* params, const tsgpu_proof* proof, int* valid);
+
+size_t tsgpu_proof_num_rounds(const tsgpu_proof* p);
+size_t tsgpu_proof_num_openings(const tsgpu_proof* p);
+void tsgpu_proof_commitment(const tsgpu_proof* p, int which, tsgpu_g1* out);
+void tsgpu_proof_round_polynomials(const tsgpu_proof* p, tsgpu_fr* out);           /* num_rounds x 4 */
+void tsgpu_proof_final_evaluation(const tsgpu_proof* p, tsgpu_fr* out);
+void tsgpu_proof_opening(const tsgpu_proof* p, size_t i, tsgpu_g1* proof, tsgpu_fr* value);
+void tsgpu_proof_opening_point(const tsgpu_proof* p, tsgpu_fr* out);
+void tsgpu_proof_set_final_evaluation(tsgpu_proof* p, size_t i, const tsgpu_fr* v);   /* tamper helper for verify tests */
+/* canonical proof bytes (the reference proofs have no serialisation; layout built from ark-serialize encodings,
+ * DESIGN.md "proof bytes"); returns the length, writes when capacity suffices */
+size_t tsgpu_proof_bytes(const tsgpu_proof* p, uint8_t* out, size_t capacity);
+/* CPU conversions: FieldElement::from(u64) and into_bigint() */
+void tsgpu_fr_from_u64(const uint64_t* in, size_t n, tsgpu_fr* out);
+void tsgpu_fr_to_canonical(const tsgpu_fr* in, size_t n, tsgpu_fr* out);
+void tsgpu_proof_free(tsgpu_proof* p);
+
 #ifdef __cplusplus
 }
 #endif

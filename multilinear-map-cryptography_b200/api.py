@@ -1,0 +1,306 @@
+"""Python mirror of the reference crate's public API for the prover path (src/lib.rs:50-56 re-exports):
+setup_params, MemoryTrace / Twist, LookupTable / Shout - same names, argument meaning and error behaviour,
+so the parity tests read like the reference's own tests.  All heavy work happens in libtsgpu.so.
+
+FieldElement values are numpy uint64[4] Montgomery limbs (ark_bn254::Fr's in-memory form); `fe(x)` is
+`FieldElement::from(x as u64)`."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+from .binding import Context, Srs, TwistAndShoutError, _fr, _p, lib
+
+
+def fe(x: int) -> np.ndarray:
+    """FieldElement::from(x as u64)"""
+    v = np.array([x], dtype=np.uint64)
+    out = np.empty((1, 4), dtype=np.uint64)
+    lib().tsgpu_fr_from_u64(_p(v), C.c_size_t(1), _p(out))
+    return out[0]
+
+
+def fe_vec(xs) -> np.ndarray:
+    v = np.ascontiguousarray(xs, dtype=np.uint64).reshape(-1)
+    out = np.empty((v.shape[0], 4), dtype=np.uint64)
+    lib().tsgpu_fr_from_u64(_p(v), C.c_size_t(v.shape[0]), _p(out))
+    return out
+
+
+def fe_to_int(x) -> int:
+    x = _fr(x, 1)
+    out = np.empty_like(x)
+    lib().tsgpu_fr_to_canonical(_p(x), C.c_size_t(1), _p(out))
+    return sum(int(out[0, i]) << (64 * i) for i in range(4))
+
+
+class ProverParams:
+    """src/utils.rs:21-34 (+ the device-resident SRS).  VerifierParams shares the object: the fields the
+    reference copies into it (log_size, max_operations, fiat_shamir_seed) are the same values."""
+
+    def __init__(self, ctx: Context, handle: C.c_void_p):
+        self.ctx = ctx
+        self._h = handle
+        L = lib()
+        L.tsgpu_params_log_size.restype = C.c_size_t; L.tsgpu_params_log_size.argtypes = [C.c_void_p]
+        L.tsgpu_params_max_operations.restype = C.c_size_t; L.tsgpu_params_max_operations.argtypes = [C.c_void_p]
+        L.tsgpu_params_srs.restype = C.c_void_p; L.tsgpu_params_srs.argtypes = [C.c_void_p]
+        L.tsgpu_params_tau.argtypes = [C.c_void_p, C.c_void_p]
+        L.tsgpu_params_fiat_shamir_seed.argtypes = [C.c_void_p, C.c_void_p]
+        L.tsgpu_params_free.argtypes = [C.c_void_p, C.c_void_p]
+        self.log_size = int(L.tsgpu_params_log_size(handle))
+        self.max_operations = int(L.tsgpu_params_max_operations(handle))
+        tau = np.empty(4, dtype=np.uint64); L.tsgpu_params_tau(handle, _p(tau))
+        self.tau = tau
+        seed = np.empty(32, dtype=np.uint8); L.tsgpu_params_fiat_shamir_seed(handle, _p(seed))
+        self.fiat_shamir_seed = seed.tobytes()
+
+    @property
+    def srs(self) -> Srs:
+        """commitment_params.g1_powers on the device (borrowed handle: do not free)"""
+        s = Srs.__new__(Srs)
+        s.ctx = self.ctx
+        s._h = C.c_void_p(lib().tsgpu_params_srs(self._h))
+        s.free = lambda: None
+        return s
+
+    def free(self):
+        if self._h:
+            lib().tsgpu_params_free(self.ctx._h, self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            if self.ctx._h:
+                self.free()
+        except Exception:
+            pass
+
+
+VerifierParams = ProverParams
+
+
+def setup_params(ctx: Context, log_size: int) -> Tuple[ProverParams, VerifierParams]:
+    """setup_params(log_size) -> (ProverParams, VerifierParams)   (src/utils.rs:79-131)"""
+    h = C.c_void_p()
+    ctx.check(lib().tsgpu_setup_params(ctx._h, C.c_size_t(log_size), C.byref(h)))
+    p = ProverParams(ctx, h)
+    return p, p
+
+
+class MemoryOp:
+    """src/twist.rs:16-20"""
+    __slots__ = ("kind", "address", "value")
+
+    def __init__(self, kind: str, address: int, value: np.ndarray):
+        self.kind, self.address, self.value = kind, address, value
+
+
+class MemoryTrace:
+    """src/twist.rs:24-72"""
+
+    def __init__(self, memory_size: int):
+        assert memory_size > 0 and memory_size & (memory_size - 1) == 0, "Memory size must be power of 2"   # twist.rs:38
+        self.memory_size = memory_size
+        self.operations: List[MemoryOp] = []
+        self._memory = {}
+
+    @staticmethod
+    def new(memory_size: int) -> "MemoryTrace":
+        return MemoryTrace(memory_size)
+
+    def write(self, address: int, value) -> None:
+        if address >= self.memory_size:
+            raise TwistAndShoutError(1, "Address out of bounds")                      # twist.rs:49-53
+        value = _fr(value, 1).reshape(4).copy()
+        self._memory[address] = value
+        self.operations.append(MemoryOp("W", address, value))
+
+    def read(self, address: int) -> np.ndarray:
+        if address >= self.memory_size:
+            raise TwistAndShoutError(1, "Address out of bounds")                      # twist.rs:62-66
+        value = self._memory.get(address)
+        if value is None:
+            value = np.zeros(4, dtype=np.uint64)
+        self.operations.append(MemoryOp("R", address, value))
+        return value
+
+    def arrays(self):
+        n = len(self.operations)
+        addr = np.fromiter((op.address for op in self.operations), dtype=np.uint64, count=n)
+        vals = np.stack([op.value for op in self.operations]) if n else np.empty((0, 4), dtype=np.uint64)
+        isw = np.fromiter((op.kind == "W" for op in self.operations), dtype=np.uint8, count=n)
+        return addr, np.ascontiguousarray(vals, dtype=np.uint64), isw
+
+
+class Proof:
+    """TwistProof / ShoutProof (src/twist.rs:76-89, src/shout.rs:64-79)"""
+
+    def __init__(self, handle: C.c_void_p):
+        self._h = handle
+        L = lib()
+        for name in ("tsgpu_proof_num_rounds", "tsgpu_proof_num_openings"):
+            getattr(L, name).restype = C.c_size_t; getattr(L, name).argtypes = [C.c_void_p]
+        L.tsgpu_proof_bytes.restype = C.c_size_t; L.tsgpu_proof_bytes.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.tsgpu_proof_commitment.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.tsgpu_proof_round_polynomials.argtypes = [C.c_void_p, C.c_void_p]
+        L.tsgpu_proof_final_evaluation.argtypes = [C.c_void_p, C.c_void_p]
+        L.tsgpu_proof_opening.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        L.tsgpu_proof_opening_point.argtypes = [C.c_void_p, C.c_void_p]
+        L.tsgpu_proof_set_final_evaluation.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        L.tsgpu_proof_free.argtypes = [C.c_void_p]
+
+    @property
+    def commitments(self) -> np.ndarray:
+        out = np.empty((2, 12), dtype=np.uint64)
+        for i in range(2):
+            lib().tsgpu_proof_commitment(self._h, i, _p(out[i]))
+        return out
+
+    @property
+    def round_polynomials(self) -> np.ndarray:
+        n = int(lib().tsgpu_proof_num_rounds(self._h))
+        out = np.empty((max(n, 1), 4, 4), dtype=np.uint64)
+        lib().tsgpu_proof_round_polynomials(self._h, _p(out))
+        return out[:n]
+
+    @property
+    def final_evaluation(self) -> np.ndarray:
+        out = np.empty(4, dtype=np.uint64); lib().tsgpu_proof_final_evaluation(self._h, _p(out)); return out
+
+    @property
+    def opening_proofs(self) -> np.ndarray:
+        n = int(lib().tsgpu_proof_num_openings(self._h))
+        out = np.empty((n, 12), dtype=np.uint64); v = np.empty(4, dtype=np.uint64)
+        for i in range(n):
+            lib().tsgpu_proof_opening(self._h, i, _p(out[i]), _p(v))
+        return out
+
+    @property
+    def final_evaluations(self) -> np.ndarray:
+        n = int(lib().tsgpu_proof_num_openings(self._h))
+        out = np.empty((n, 4), dtype=np.uint64); g = np.empty(12, dtype=np.uint64)
+        for i in range(n):
+            lib().tsgpu_proof_opening(self._h, i, _p(g), _p(out[i]))
+        return out
+
+    @property
+    def opening_point(self) -> np.ndarray:
+        out = np.empty(4, dtype=np.uint64); lib().tsgpu_proof_opening_point(self._h, _p(out)); return out
+
+    def to_bytes(self) -> bytes:
+        n = int(lib().tsgpu_proof_bytes(self._h, None, 0))
+        buf = np.empty(n, dtype=np.uint8)
+        lib().tsgpu_proof_bytes(self._h, _p(buf), n)
+        return buf.tobytes()
+
+    def tamper_final_evaluation(self, i: int, value):
+        lib().tsgpu_proof_set_final_evaluation(self._h, i, _p(_fr(value, 1)))
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().tsgpu_proof_free(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+
+TwistProof = Proof
+ShoutProof = Proof
+
+
+class Twist:
+    """src/twist.rs:93-316"""
+
+    def __init__(self, prover_params: ProverParams):
+        self.prover_params = prover_params   # the reference clones the params (twist.rs:100-104); a handle is shared here
+
+    @staticmethod
+    def new(prover_params: ProverParams) -> "Twist":
+        return Twist(prover_params)
+
+    def prove(self, trace: MemoryTrace) -> TwistProof:
+        addr, vals, isw = trace.arrays()
+        return self.prove_arrays(addr, vals, isw)
+
+    def prove_arrays(self, addresses: np.ndarray, values: np.ndarray, is_write: Optional[np.ndarray] = None) -> TwistProof:
+        """same as prove() on a trace given as flat arrays (what the C ABI takes)"""
+        ctx = self.prover_params.ctx
+        addresses = np.ascontiguousarray(addresses, dtype=np.uint64).reshape(-1)
+        values = _fr(values)
+        n = addresses.shape[0]
+        if is_write is None:
+            is_write = np.zeros(n, dtype=np.uint8)
+        is_write = np.ascontiguousarray(is_write, dtype=np.uint8)
+        h = C.c_void_p()
+        ctx.check(lib().tsgpu_twist_prove(ctx._h, self.prover_params._h, _p(addresses), _p(values), _p(is_write), C.c_size_t(n), C.byref(h)))
+        return Proof(h)
+
+    def verify(self, proof: TwistProof, verifier_params: VerifierParams) -> bool:
+        ctx = verifier_params.ctx
+        ok = C.c_int(0)
+        ctx.check(lib().tsgpu_twist_verify(ctx._h, verifier_params._h, proof._h, C.byref(ok)))
+        return bool(ok.value)
+
+
+class LookupOp:
+    """src/shout.rs:17-22"""
+    __slots__ = ("index", "value")
+
+    def __init__(self, index: int, value: np.ndarray):
+        self.index, self.value = index, value
+
+
+class LookupTable:
+    """src/shout.rs:26-60"""
+
+    def __init__(self, entries):
+        self.entries = _fr(entries).copy() if len(entries) else np.empty((0, 4), dtype=np.uint64)
+        self.lookups: List[LookupOp] = []
+
+    @staticmethod
+    def new(entries) -> "LookupTable":
+        return LookupTable(entries)
+
+    def lookup(self, index: int) -> np.ndarray:
+        if index >= self.entries.shape[0]:
+            raise TwistAndShoutError(1, "Lookup index out of bounds")                 # shout.rs:44-48
+        value = self.entries[index]
+        self.lookups.append(LookupOp(index, value))
+        return value
+
+    def size(self) -> int:
+        return self.entries.shape[0]
+
+
+class Shout:
+    """src/shout.rs:83-286"""
+
+    def __init__(self, prover_params: ProverParams):
+        self.prover_params = prover_params
+
+    @staticmethod
+    def new(prover_params: ProverParams) -> "Shout":
+        return Shout(prover_params)
+
+    def prove(self, table: LookupTable) -> ShoutProof:
+        idx = np.fromiter((l.index for l in table.lookups), dtype=np.uint64, count=len(table.lookups))
+        return self.prove_arrays(table.entries, idx)
+
+    def prove_arrays(self, entries: np.ndarray, lookup_indices: np.ndarray) -> ShoutProof:
+        ctx = self.prover_params.ctx
+        entries = np.ascontiguousarray(entries, dtype=np.uint64).reshape(-1, 4)
+        lookup_indices = np.ascontiguousarray(lookup_indices, dtype=np.uint64).reshape(-1)
+        h = C.c_void_p()
+        ctx.check(lib().tsgpu_shout_prove(ctx._h, self.prover_params._h, _p(entries), C.c_size_t(entries.shape[0]),
+                                          _p(lookup_indices), C.c_size_t(lookup_indices.shape[0]), C.byref(h)))
+        return Proof(h)
+
+    def verify(self, proof: ShoutProof, verifier_params: VerifierParams) -> bool:
+        ctx = verifier_params.ctx
+        ok = C.c_int(0)
+        ctx.check(lib().tsgpu_shout_verify(ctx._h, verifier_params._h, proof._h, C.byref(ok)))
+        return bool(ok.value)

@@ -1,0 +1,243 @@
+// host/protocols.cpp - host-side mirror of setup_params, Twist::prove and Shout::prove
+// (src/utils.rs:79-131, src/twist.rs:107-252, src/shout.rs:97-222): same inputs, same transcript order, same
+// error behaviour, every heavy step on the device through the C ABI of include/tsgpu.h.
+//
+// Until the pairing verifier exists, verify() replays the transcript and the sum-check exactly
+// as the reference does and checks each KZG opening with the trapdoor the reference keeps in its params
+// (CommitmentParams.tau, src/utils.rs:61,107):  C - v G == (tau - z) pi.
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+#include "../csrc/context.cuh"
+#include "field64.hpp"
+#include "sumcheck_host.hpp"
+#include "transcript.hpp"
+
+using namespace tsg;
+using namespace tsg::host;
+
+struct tsgpu_params {                 // ProverParams (+ the verifier's copy of the seed), src/utils.rs:21-50
+    size_t log_size = 0;
+    size_t max_operations = 0;
+    tsgpu_fr tau;                     // CommitmentParams.tau (always Some)
+    uint8_t fiat_shamir_seed[32];
+    tsgpu_srs* srs = nullptr;         // g1_powers[0 ..= max_degree] on the device
+};
+
+struct tsgpu_proof {                  // TwistProof / ShoutProof (src/twist.rs:76-89, src/shout.rs:64-79)
+    tsgpu_g1 commitments[2];
+    std::vector<tsgpu_fr> round_polynomials;   // rounds x 4
+    tsgpu_fr final_evaluation;
+    std::vector<tsgpu_g1> opening_proofs;      // 0 or 2
+    std::vector<tsgpu_fr> final_evaluations;   // 0 or 2
+    tsgpu_fr opening_point;                    // challenges[0] (not part of the proof; kept for inspection)
+};
+
+namespace {
+
+size_t next_pow2(size_t n) { size_t p = 1; while (p < n) p <<= 1; return p; }   // 0usize.next_power_of_two() == 1
+unsigned log2_of(size_t p) { unsigned l = 0; while (((size_t)1 << l) < p) ++l; return l; }
+
+fr_t fr_of(const tsgpu_fr& x) { fr_t r; memcpy(r.l, x.l, 32); return r; }
+tsgpu_fr abi_of(const fr_t& x) { tsgpu_fr r; memcpy(r.l, x.l, 32); return r; }
+
+// Shared tail of Twist::prove (twist.rs:151-251) and Shout::prove (shout.rs:121-221): the two padded vectors are
+// already on the device as `pa`, `pb` (values, natural order); they are interpolated in place.
+int prove_two_vectors(tsgpu_ctx* ctx, const tsgpu_params* params, tsgpu_poly* pa, tsgpu_poly* pb, const char* label_a, const char* label_b,
+                      unsigned rounds, tsgpu_proof** out) {
+    int rc;
+    if ((rc = tsgpu_poly_interpolate_iota(ctx, pa))) return rc;            // vector_to_polynomial
+    if ((rc = tsgpu_poly_interpolate_iota(ctx, pb))) return rc;
+    tsgpu_proof* pr = new (std::nothrow) tsgpu_proof;
+    if (!pr) return fail(ctx, TSGPU_E_PROOF_GENERATION, "out of host memory");
+    memset(&pr->opening_point, 0, 32);
+    if ((rc = tsgpu_kzg_commit_dev(ctx, params->srs, pa, &pr->commitments[0]))) { delete pr; return rc; }
+    if ((rc = tsgpu_kzg_commit_dev(ctx, params->srs, pb, &pr->commitments[1]))) { delete pr; return rc; }
+    Transcript tr(params->fiat_shamir_seed);
+    tsgpu_fr h;
+    tsgpu_g1_hash(&pr->commitments[0], &h); tr.append_field_element(label_a, fr_of(h));
+    tsgpu_g1_hash(&pr->commitments[1], &h); tr.append_field_element(label_b, fr_of(h));
+    // SumCheck::new(rounds, 0).prove(closure): the reference closure returns zero on every branch
+    // (twist.rs:191-213, shout.rs:166-183), so every round polynomial is the zero cubic, the running sum stays
+    // zero, and only the transcript advances (sumcheck.rs:86-100).  final_evaluation = closure(challenges) = 0.
+    const fr_t zero4[4] = {fr_t::zero(), fr_t::zero(), fr_t::zero(), fr_t::zero()};
+    for (unsigned round = 0; round < rounds; ++round) {
+        for (int k = 0; k < 4; ++k) pr->round_polynomials.push_back(abi_of(zero4[k]));
+        tr.append_field_elements("sumcheck_round_" + std::to_string(round), zero4, 4);
+        (void)tr.challenge_field_element("sumcheck_challenge_" + std::to_string(round));
+    }
+    pr->final_evaluation = abi_of(fr_t::zero());
+    std::vector<fr_t> ch = tr.challenge_field_elements("opening_challenges", rounds);   // twist.rs:219
+    if (!ch.empty()) {                                                                  // twist.rs:226-243
+        tsgpu_fr z = abi_of(ch[0]);
+        pr->opening_point = z;
+        tsgpu_fr v; tsgpu_g1 pi;
+        if ((rc = tsgpu_kzg_open_dev(ctx, params->srs, pa, &z, &v, &pi))) { delete pr; return rc; }
+        pr->opening_proofs.push_back(pi); pr->final_evaluations.push_back(v);
+        if ((rc = tsgpu_kzg_open_dev(ctx, params->srs, pb, &z, &v, &pi))) { delete pr; return rc; }
+        pr->opening_proofs.push_back(pi); pr->final_evaluations.push_back(v);
+    }
+    *out = pr;
+    return TSGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ------------------------------------------------------------------------------------ setup_params
+int tsgpu_setup_params(tsgpu_ctx* ctx, size_t log_size, tsgpu_params** out) {
+    if (!ctx || !out) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    if (log_size > 25) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "log_size too large for the Fr two-adicity");
+    tsgpu_params* p = new (std::nothrow) tsgpu_params;
+    if (!p) return fail(ctx, TSGPU_E_PROOF_GENERATION, "out of host memory");
+    p->log_size = log_size;
+    p->max_operations = (size_t)1 << (log_size + 2);                       // utils.rs:80
+    uint8_t seed[32]; memset(seed, 42, 32);
+    ChaCha20Rng rng(seed);                                                 // utils.rs:81
+    fr_t tau = rng.rand_field<fr_t>();                                     // utils.rs:84
+    p->tau = abi_of(tau);
+    const size_t max_degree = next_pow2(p->max_operations);                // utils.rs:89
+    int rc = tsgpu_srs_generate(ctx, &p->tau, max_degree + 1, &p->srs);    // utils.rs:93-96
+    if (rc) { delete p; return rc; }
+    rng.fill_bytes(p->fiat_shamir_seed, 32);                               // utils.rs:101-102
+    rc = tsgpu_interpolate_prepare(ctx, (unsigned)(log_size + 2));
+    if (rc) { tsgpu_srs_free(ctx, p->srs); delete p; return rc; }
+    *out = p;
+    return TSGPU_OK;
+}
+void tsgpu_params_free(tsgpu_ctx* ctx, tsgpu_params* p) {
+    if (!p) return;
+    tsgpu_srs_free(ctx, p->srs);
+    delete p;
+}
+size_t tsgpu_params_log_size(const tsgpu_params* p) { return p->log_size; }
+size_t tsgpu_params_max_operations(const tsgpu_params* p) { return p->max_operations; }
+void tsgpu_params_tau(const tsgpu_params* p, tsgpu_fr* out) { *out = p->tau; }
+void tsgpu_params_fiat_shamir_seed(const tsgpu_params* p, uint8_t out[32]) { memcpy(out, p->fiat_shamir_seed, 32); }
+const tsgpu_srs* tsgpu_params_srs(const tsgpu_params* p) { return p->srs; }
+
+// ------------------------------------------------------------------------------------ Twist::prove
+// operations[i] = Read/Write { address: addresses[i], value: values[i] } (twist.rs:16-20); is_write is the
+// op_type vector the reference also builds (twist.rs:132-138) - it never influences the proof.
+int tsgpu_twist_prove(tsgpu_ctx* ctx, const tsgpu_params* params, const uint64_t* addresses, const tsgpu_fr* values,
+                      const uint8_t* is_write, size_t num_operations, tsgpu_proof** out) {
+    (void)is_write;
+    if (!ctx || !params || !out || ((!addresses || !values) && num_operations)) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    if (num_operations > params->max_operations) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "Too many operations");   // twist.rs:108-112
+    const size_t padded = next_pow2(num_operations);                        // .next_power_of_two().max(1), twist.rs:141
+    tsgpu_poly *pa = nullptr, *pv = nullptr;
+    int rc = tsgpu_poly_from_u64(ctx, addresses, num_operations, padded, &pa);
+    if (!rc) rc = tsgpu_poly_upload_padded(ctx, values, num_operations, padded, &pv);
+    if (!rc) rc = prove_two_vectors(ctx, params, pa, pv, "address_commitment", "value_commitment", log2_of(padded), out);
+    tsgpu_poly_free(ctx, pa); tsgpu_poly_free(ctx, pv);
+    return rc;
+}
+// same, with the two padded vectors already resident in HBM (consumed: interpolated in place)
+int tsgpu_twist_prove_dev(tsgpu_ctx* ctx, const tsgpu_params* params, tsgpu_poly* padded_addresses, tsgpu_poly* padded_values, tsgpu_proof** out) {
+    if (!ctx || !params || !padded_addresses || !padded_values || !out) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    size_t n = tsgpu_poly_len(padded_addresses);
+    if (n != tsgpu_poly_len(padded_values) || next_pow2(n) != n) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "padded vectors must have equal power-of-two length");
+    if (n > params->max_operations) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "Too many operations");
+    return prove_two_vectors(ctx, params, padded_addresses, padded_values, "address_commitment", "value_commitment", log2_of(n), out);
+}
+
+// ------------------------------------------------------------------------------------ Shout::prove
+int tsgpu_shout_prove(tsgpu_ctx* ctx, const tsgpu_params* params, const tsgpu_fr* entries, size_t num_entries,
+                      const uint64_t* lookup_indices, size_t num_lookups, tsgpu_proof** out) {
+    if (!ctx || !params || !out || (!entries && num_entries) || (!lookup_indices && num_lookups)) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    if (num_lookups > params->max_operations) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "Too many lookup operations");   // shout.rs:98-102
+    const size_t table_size = next_pow2(num_entries);                       // shout.rs:105
+    const size_t lookups_size = next_pow2(num_lookups);                     // shout.rs:116
+    tsgpu_poly *pt = nullptr, *pi = nullptr;
+    int rc = tsgpu_poly_upload_padded(ctx, entries, num_entries, table_size, &pt);
+    if (!rc) rc = tsgpu_poly_from_u64(ctx, lookup_indices, num_lookups, lookups_size, &pi);
+    if (!rc) rc = prove_two_vectors(ctx, params, pt, pi, "table_commitment", "index_commitment", log2_of(lookups_size), out);
+    tsgpu_poly_free(ctx, pt); tsgpu_poly_free(ctx, pi);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------ proof accessors
+size_t tsgpu_proof_num_rounds(const tsgpu_proof* p) { return p->round_polynomials.size() / 4; }
+size_t tsgpu_proof_num_openings(const tsgpu_proof* p) { return p->opening_proofs.size(); }
+void tsgpu_proof_commitment(const tsgpu_proof* p, int which, tsgpu_g1* out) { *out = p->commitments[which ? 1 : 0]; }
+void tsgpu_proof_round_polynomials(const tsgpu_proof* p, tsgpu_fr* out) { if (!p->round_polynomials.empty()) memcpy(out, p->round_polynomials.data(), p->round_polynomials.size() * 32); }
+void tsgpu_proof_final_evaluation(const tsgpu_proof* p, tsgpu_fr* out) { *out = p->final_evaluation; }
+void tsgpu_proof_opening(const tsgpu_proof* p, size_t i, tsgpu_g1* proof, tsgpu_fr* value) { *proof = p->opening_proofs[i]; *value = p->final_evaluations[i]; }
+void tsgpu_proof_opening_point(const tsgpu_proof* p, tsgpu_fr* out) { *out = p->opening_point; }
+void tsgpu_proof_free(tsgpu_proof* p) { delete p; }
+
+// canonical bytes: compressed(C0) | compressed(C1) | u64 rounds | per round (u64 4 | 4 x Fr) |
+// Fr final_evaluation | u64 #openings | compressed... | u64 #evals | Fr...
+size_t tsgpu_proof_bytes(const tsgpu_proof* p, uint8_t* out, size_t capacity) {
+    std::vector<uint8_t> b;
+    auto put_u64 = [&](uint64_t v) { for (int i = 0; i < 8; ++i) b.push_back((uint8_t)(v >> (8 * i))); };
+    auto put_fr = [&](const tsgpu_fr& x) { uint8_t t[32]; fr_to_bytes(fr_of(x), t); b.insert(b.end(), t, t + 32); };
+    auto put_g1 = [&](const tsgpu_g1& g) { uint8_t t[32]; tsgpu_g1_compress(&g, t); b.insert(b.end(), t, t + 32); };
+    put_g1(p->commitments[0]); put_g1(p->commitments[1]);
+    size_t rounds = p->round_polynomials.size() / 4;
+    put_u64(rounds);
+    for (size_t r = 0; r < rounds; ++r) { put_u64(4); for (int k = 0; k < 4; ++k) put_fr(p->round_polynomials[4 * r + k]); }
+    put_fr(p->final_evaluation);
+    put_u64(p->opening_proofs.size()); for (auto& g : p->opening_proofs) put_g1(g);
+    put_u64(p->final_evaluations.size()); for (auto& v : p->final_evaluations) put_fr(v);
+    if (out && capacity >= b.size()) memcpy(out, b.data(), b.size());
+    return b.size();
+}
+
+// ------------------------------------------------------------------------------------ verify (transcript + sum-check + trapdoor KZG)
+// Twist::verify / Shout::verify control flow (twist.rs:255-304, shout.rs:225-274); *valid = 1/0.
+static int verify_common(tsgpu_ctx* ctx, const tsgpu_params* params, const tsgpu_proof* proof, const char* label_a, const char* label_b, int* valid) {
+    if (!params || !proof || !valid) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    Transcript tr(params->fiat_shamir_seed);
+    tsgpu_fr h;
+    tsgpu_g1_hash(&proof->commitments[0], &h); tr.append_field_element(label_a, fr_of(h));
+    tsgpu_g1_hash(&proof->commitments[1], &h); tr.append_field_element(label_b, fr_of(h));
+    const unsigned num_vars = (unsigned)(proof->round_polynomials.size() / 4);          // twist.rs:263
+    SumCheckProof sc;
+    for (unsigned r = 0; r < num_vars; ++r) {
+        std::vector<fr_t> c(4);
+        for (int k = 0; k < 4; ++k) c[k] = fr_of(proof->round_polynomials[4 * r + k]);
+        sc.round_polynomials.push_back(c);
+    }
+    sc.final_evaluation = fr_of(proof->final_evaluation);
+    int ok = sumcheck_verify(num_vars, fr_t::zero(), sc, tr, nullptr);
+    if (ok < 0) return fail(ctx, TSGPU_E_SUMCHECK, "Proof has wrong number of rounds");
+    if (!ok) { *valid = 0; return TSGPU_OK; }
+    std::vector<fr_t> ch = tr.challenge_field_elements("opening_challenges", num_vars);
+    if (!ch.empty() && proof->opening_proofs.size() >= 2 && proof->final_evaluations.size() >= 2) {   // twist.rs:275
+        Fr64 tau = Fr64::from_raw(params->tau.l), z = Fr64::from_raw(ch[0].l);
+        for (int i = 0; i < 2; ++i) {
+            G1J C, pi; memcpy(&C, &proof->commitments[i], 96); memcpy(&pi, &proof->opening_proofs[i], 96);
+            Fr64 v = Fr64::from_raw(proof->final_evaluations[i].l);
+            G1J lhs = C.add(G1J::generator().mul(v).neg());
+            G1J rhs = pi.mul(tau - z);
+            if (!lhs.equals(rhs)) { *valid = 0; return TSGPU_OK; }
+        }
+    }
+    *valid = 1;
+    return TSGPU_OK;
+}
+int tsgpu_twist_verify(tsgpu_ctx* ctx, const tsgpu_params* params, const tsgpu_proof* proof, int* valid) {
+    return verify_common(ctx, params, proof, "address_commitment", "value_commitment", valid);
+}
+int tsgpu_shout_verify(tsgpu_ctx* ctx, const tsgpu_params* params, const tsgpu_proof* proof, int* valid) {
+    return verify_common(ctx, params, proof, "table_commitment", "index_commitment", valid);
+}
+// tamper helper for tests of the verify path: overwrite one final evaluation
+void tsgpu_proof_set_final_evaluation(tsgpu_proof* p, size_t i, const tsgpu_fr* v) { if (i < p->final_evaluations.size()) p->final_evaluations[i] = *v; }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------ small host conversions
+extern "C" {
+// FieldElement::from(u64) (twist.rs:119): canonical small integer -> Montgomery limbs.  CPU.
+void tsgpu_fr_from_u64(const uint64_t* in, size_t n, tsgpu_fr* out) {
+    for (size_t i = 0; i < n; ++i) { Fr64 f = Fr64::from_u64(in[i]); memcpy(out[i].l, f.l, 32); }
+}
+// into_bigint(): Montgomery limbs -> canonical integer limbs.  CPU.
+void tsgpu_fr_to_canonical(const tsgpu_fr* in, size_t n, tsgpu_fr* out) {
+    for (size_t i = 0; i < n; ++i) { Fr64 f = Fr64::from_raw(in[i].l).from_mont(); memcpy(out[i].l, f.l, 32); }
+}
+}
