@@ -62,6 +62,10 @@ int tsgpu_sm_count(const tsgpu_ctx* ctx);
 /* tuning knobs (process-wide): "tma_min_log2" = log2 of the per-stream size from which the sum-check rounds use
  * the TMA bulk-copy pipelined kernels instead of the plain streaming kernels (negative: never; default never) */
 int tsgpu_set_tuning(tsgpu_ctx* ctx, const char* key, long value);
+/* with tuning key "kernel_timing" = 1 the library brackets its main kernels with CUDA events on the context
+ * stream; names: "msm_accumulate", "msm_total", "interpolate", "open_scan", "sc_round_eval", "sc_bind_eval", "bind" */
+int tsgpu_timer_read(tsgpu_ctx* ctx, const char* name, double* total_ms, uint64_t* count);
+void tsgpu_timer_reset(tsgpu_ctx* ctx);
 
 /* ---- MLE tables: MultilinearExtension { num_vars, evaluations }  (src/polynomials.rs:18-82) ------ */
 /* from_evaluations / from_evaluations_vec: `n` host entries, zero-padded or truncated to 2^num_vars
@@ -124,6 +128,7 @@ void tsgpu_srs_free(tsgpu_ctx* ctx, tsgpu_srs* srs);
 int tsgpu_poly_upload(tsgpu_ctx* ctx, const tsgpu_fr* coeffs, size_t n, tsgpu_poly** out);
 int tsgpu_poly_download(tsgpu_ctx* ctx, const tsgpu_poly* p, tsgpu_fr* out);
 size_t tsgpu_poly_len(const tsgpu_poly* p);
+int tsgpu_poly_clone(tsgpu_ctx* ctx, const tsgpu_poly* p, tsgpu_poly** out);
 /* padded vectors as Twist/Shout::prove build them: Fr::from(v[i]) / given values, zero-filled up to `padded`
  * (src/twist.rs:115-148, src/shout.rs:105-118) */
 int tsgpu_poly_from_u64(tsgpu_ctx* ctx, const uint64_t* v, size_t n, size_t padded, tsgpu_poly** out);

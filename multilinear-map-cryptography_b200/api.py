@@ -239,6 +239,13 @@ class Twist:
         ctx.check(lib().tsgpu_twist_prove(ctx._h, self.prover_params._h, _p(addresses), _p(values), _p(is_write), C.c_size_t(n), C.byref(h)))
         return Proof(h)
 
+    def prove_device(self, padded_addresses, padded_values) -> TwistProof:
+        """prove from two zero-padded value vectors already resident in HBM (Poly handles; consumed)"""
+        ctx = self.prover_params.ctx
+        h = C.c_void_p()
+        ctx.check(lib().tsgpu_twist_prove_dev(ctx._h, self.prover_params._h, padded_addresses._h, padded_values._h, C.byref(h)))
+        return Proof(h)
+
     def verify(self, proof: TwistProof, verifier_params: VerifierParams) -> bool:
         ctx = verifier_params.ctx
         ok = C.c_int(0)

@@ -63,6 +63,7 @@ def lib() -> C.CDLL:
         L.tsgpu_g1_hash.argtypes = [C.c_void_p, C.c_void_p]
         L.tsgpu_g1_compress.argtypes = [C.c_void_p, C.c_void_p]
         L.tsgpu_g1_equal.argtypes = [C.c_void_p, C.c_void_p]
+        L.tsgpu_timer_reset.argtypes = [C.c_void_p]
         L.tsgpu_transcript_new.restype = C.c_void_p
         L.tsgpu_transcript_new.argtypes = [C.c_void_p]
         L.tsgpu_transcript_free.argtypes = [C.c_void_p]
@@ -121,6 +122,14 @@ class Context:
 
     def set_tuning(self, key: str, value: int):
         self.check(lib().tsgpu_set_tuning(self._h, key.encode(), C.c_long(value)))
+
+    def timer_read(self, name: str):
+        ms = C.c_double(0); cnt = C.c_uint64(0)
+        self.check(lib().tsgpu_timer_read(self._h, name.encode(), C.byref(ms), C.byref(cnt)))
+        return ms.value, int(cnt.value)
+
+    def timer_reset(self):
+        lib().tsgpu_timer_reset(self._h)
 
     def synchronize(self):
         self.check(lib().tsgpu_synchronize(self._h))
@@ -444,6 +453,11 @@ class Poly:
         out = np.empty((len(self), 4), dtype=np.uint64)
         self.ctx.check(lib().tsgpu_poly_download(self.ctx._h, self._h, _p(out)))
         return out
+
+    def clone(self) -> "Poly":
+        h = C.c_void_p()
+        self.ctx.check(lib().tsgpu_poly_clone(self.ctx._h, self._h, C.byref(h)))
+        return Poly(self.ctx, h)
 
     def interpolate_iota(self):
         """in place: values at 0..n-1 -> monomial coefficients"""

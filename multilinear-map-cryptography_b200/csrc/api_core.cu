@@ -22,6 +22,29 @@ int cuda_fail(tsgpu_ctx* ctx, cudaError_t e, const char* what) {
     return fail(ctx, TSGPU_E_PROOF_GENERATION, m);
 }
 
+void timers_collect(tsgpu_ctx* ctx) {
+    for (auto& p : ctx->pending) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { auto& t = ctx->timers[p.name]; t.first += ms; t.second += 1; }
+        cudaEventDestroy(p.a); cudaEventDestroy(p.b);
+    }
+    ctx->pending.clear();
+    cudaGetLastError();
+}
+
+void* arena_get(tsgpu_ctx* ctx, int slot, size_t bytes, cudaError_t* err) {
+    *err = cudaSuccess;
+    if (ctx->arena_bytes[slot] >= bytes && ctx->arena[slot]) return ctx->arena[slot];
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->arena[slot]) cudaFree(ctx->arena[slot]);
+    ctx->arena[slot] = nullptr; ctx->arena_bytes[slot] = 0;
+    size_t want = bytes + bytes / 8 + (1 << 20);   // head-room so that slightly larger requests do not reallocate
+    *err = cudaMalloc(&ctx->arena[slot], want);
+    if (*err != cudaSuccess) return nullptr;
+    ctx->arena_bytes[slot] = want;
+    return ctx->arena[slot];
+}
+
 int table_alloc(tsgpu_ctx* ctx, unsigned num_vars, tsgpu_table** out) {
     if (num_vars > 34) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "num_vars too large");
     tsgpu_table* t = new (std::nothrow) tsgpu_table;
@@ -87,6 +110,7 @@ void tsgpu_destroy(tsgpu_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     interp_destroy(ctx);
+    for (int i = 0; i < tsgpu_ctx::ARENA_COUNT; ++i) if (ctx->arena[i]) cudaFree(ctx->arena[i]);
     if (ctx->partials) cudaFree(ctx->partials);
     if (ctx->ticket) cudaFree(ctx->ticket);
     if (ctx->dev_out) cudaFree(ctx->dev_out);
@@ -103,12 +127,29 @@ int tsgpu_synchronize(tsgpu_ctx* ctx) {
     return TSGPU_OK;
 }
 
+int tsgpu_timer_read(tsgpu_ctx* ctx, const char* name, double* total_ms, uint64_t* count) {
+    if (!ctx || !name) return TSGPU_E_INVALID_PARAMETERS;
+    cudaStreamSynchronize(ctx->stream);
+    timers_collect(ctx);
+    auto it = ctx->timers.find(name);
+    if (total_ms) *total_ms = it == ctx->timers.end() ? 0.0 : it->second.first;
+    if (count) *count = it == ctx->timers.end() ? 0 : it->second.second;
+    return TSGPU_OK;
+}
+void tsgpu_timer_reset(tsgpu_ctx* ctx) {
+    if (!ctx) return;
+    cudaStreamSynchronize(ctx->stream);
+    timers_collect(ctx);
+    ctx->timers.clear();
+}
+
 int tsgpu_set_tuning(tsgpu_ctx* ctx, const char* key, long value) {
     if (!key) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null key");
     if (!strcmp(key, "tma_min_log2")) {   // tables with >= 2^value positions per stream use the TMA-pipelined kernels; < 0 disables
         set_tma_min_work(value < 0 || value > 62 ? ~(size_t)0 : (size_t)1 << value);
         return TSGPU_OK;
     }
+    if (!strcmp(key, "kernel_timing")) { ctx->timing = value != 0; return TSGPU_OK; }
     return fail(ctx, TSGPU_E_INVALID_PARAMETERS, std::string("unknown tuning key ") + key);
 }
 
@@ -276,7 +317,8 @@ int tsgpu_table_evaluate(tsgpu_ctx* ctx, const tsgpu_table* t, const tsgpu_fr* p
 int tsgpu_table_bind(tsgpu_ctx* ctx, tsgpu_table* t, const tsgpu_fr* r) {
     if (!ctx || !t || !r) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
     if (t->num_vars == 0) return fail(ctx, TSGPU_E_POLYNOMIAL, "Cannot fix more variables than available");
-    TSG_CUDA(ctx, launch_bind(t->d, (size_t)1 << t->num_vars, to_fr(r), ctx->sm_count, ctx->stream));
+    { KernelTimer kt(ctx, "bind");
+      TSG_CUDA(ctx, launch_bind(t->d, (size_t)1 << t->num_vars, to_fr(r), ctx->sm_count, ctx->stream)); }
     ctx->launches += 1;
     t->num_vars -= 1;
     return TSGPU_OK;
@@ -330,6 +372,7 @@ int tsgpu_sc_round_eval(tsgpu_sc* sc, tsgpu_fr evals[4]) {
     if (!sc || !evals) return TSGPU_E_INVALID_PARAMETERS;
     tsgpu_ctx* ctx = sc->ctx;
     if (sc->vars_left == 0) return fail(ctx, TSGPU_E_SUMCHECK, "no variables left to evaluate");
+    KernelTimer kt(ctx, "sc_round_eval");
     TSG_CUDA(ctx, launch_round_eval(sc->d, sc_tabs(sc), (size_t)1 << sc->vars_left, ctx->partials, ctx->ticket, ctx->dev_out, ctx->sm_count, ctx->stream));
     ctx->launches += 1;
     return read_result(ctx, 4, evals);
@@ -352,6 +395,7 @@ int tsgpu_sc_bind_eval(tsgpu_sc* sc, const tsgpu_fr* r, tsgpu_fr evals[4]) {
     if (!sc || !r || !evals) return TSGPU_E_INVALID_PARAMETERS;
     tsgpu_ctx* ctx = sc->ctx;
     if (sc->vars_left < 2) return fail(ctx, TSGPU_E_SUMCHECK, "bind_eval needs at least two unbound variables");
+    KernelTimer kt(ctx, "sc_bind_eval");
     TSG_CUDA(ctx, launch_bind_eval(sc->d, sc_tabs(sc), (size_t)1 << sc->vars_left, to_fr(r), ctx->partials, ctx->ticket, ctx->dev_out, ctx->sm_count, ctx->stream));
     ctx->launches += 1;
     for (int i = 0; i < sc->d; ++i) sc->tables[i]->num_vars -= 1;

@@ -44,14 +44,23 @@ int msm_device(tsgpu_ctx* ctx, const g1_affine* bases, const fr_t* scalars, size
     if (n == 0) { G1J id = G1J::identity(); memcpy(out, &id, 96); return TSGPU_OK; }
     MsmLayout L;
     size_t bytes = msm_scratch_bytes(n, msm_window_bits(n), &L);
-    TempBuf scratch;
-    TSG_CUDA(ctx, scratch.alloc(bytes, ctx->stream));
+    cudaError_t aerr;
+    unsigned char* scratch_p = (unsigned char*)arena_get(ctx, tsgpu_ctx::ARENA_MSM, bytes, &aerr);
+    if (!scratch_p) return cuda_fail(ctx, aerr, "cudaMalloc(msm scratch)");
     unsigned launches = 0;
-    TSG_CUDA(ctx, msm_run(bases, scalars, n, L, scratch.as<unsigned char>(), ctx->sm_count, ctx->stream, &launches));
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    if (ctx->timing) { cudaEventCreate(&ev[0]); cudaEventCreate(&ev[1]); }
+    {
+        KernelTimer kt(ctx, "msm_total");
+        TSG_CUDA(ctx, msm_run(bases, scalars, n, L, scratch_p, ctx->sm_count, ctx->stream, &launches, ctx->timing ? ev : nullptr));
+    }
+    if (ctx->timing) ctx->pending.push_back({"msm_accumulate", ev[0], ev[1]});
+    ctx->msm_points += n;
     ctx->launches += launches;
     std::vector<g1_jac> win(L.W);
-    TSG_CUDA(ctx, cudaMemcpyAsync(win.data(), scratch.as<unsigned char>() + L.window_out, L.W * sizeof(g1_jac), cudaMemcpyDeviceToHost, ctx->stream));
+    TSG_CUDA(ctx, cudaMemcpyAsync(win.data(), scratch_p + L.window_out, L.W * sizeof(g1_jac), cudaMemcpyDeviceToHost, ctx->stream));
     TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    timers_collect(ctx);
     G1J r = combine_windows(win.data(), L.W, L.c);
     memcpy(out, &r, 96);
     return TSGPU_OK;
@@ -170,6 +179,17 @@ int tsgpu_poly_download(tsgpu_ctx* ctx, const tsgpu_poly* p, tsgpu_fr* out) {
     return TSGPU_OK;
 }
 size_t tsgpu_poly_len(const tsgpu_poly* p) { return p ? p->n : 0; }
+int tsgpu_poly_clone(tsgpu_ctx* ctx, const tsgpu_poly* p, tsgpu_poly** out) {
+    if (!ctx || !p || !out) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    tsgpu_poly* c = new (std::nothrow) tsgpu_poly;
+    if (!c) return fail(ctx, TSGPU_E_PROOF_GENERATION, "out of host memory");
+    c->n = p->n;
+    cudaError_t e = cudaMallocAsync((void**)&c->d, (p->n ? p->n : 1) * sizeof(fr_t), ctx->stream);
+    if (e != cudaSuccess) { delete c; return cuda_fail(ctx, e, "cudaMallocAsync(poly)"); }
+    if (p->n) TSG_CUDA(ctx, cudaMemcpyAsync(c->d, p->d, p->n * sizeof(fr_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    *out = c;
+    return TSGPU_OK;
+}
 void tsgpu_poly_free(tsgpu_ctx* ctx, tsgpu_poly* p) {
     if (!p) return;
     if (p->d) cudaFreeAsync(p->d, ctx ? ctx->stream : nullptr);
@@ -228,6 +248,7 @@ int tsgpu_poly_interpolate_iota(tsgpu_ctx* ctx, tsgpu_poly* p) {
     int l = log2_exact(p->n);
     if (l < 0) return fail(ctx, TSGPU_E_POLYNOMIAL, "interpolation length must be a power of two (Twist/Shout pad first)");
     if (l > 27) return fail(ctx, TSGPU_E_POLYNOMIAL, "interpolation size exceeds the 2^28 two-adicity of Fr");
+    KernelTimer kt(ctx, "interpolate");
     TSG_CUDA(ctx, interp_run(ctx, p->d, (unsigned)l, p->d));
     return TSGPU_OK;
 }
@@ -286,20 +307,23 @@ int tsgpu_kzg_open_dev(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_poly* p
     fr_t pw[POLY_PW + 1];
     for (int s = 0; s <= POLY_PW; ++s) { memcpy(pw[s].l, w.l, 32); w = w.sqr(); }
     const size_t nblocks = poly_num_blocks(n);
-    TempBuf dpw, totals, carry, q, val;
+    TempBuf dpw, totals, carry, val;
     TSG_CUDA(ctx, dpw.alloc(sizeof(pw), ctx->stream));
     TSG_CUDA(ctx, totals.alloc(nblocks * sizeof(fr_t), ctx->stream));
     TSG_CUDA(ctx, carry.alloc(nblocks * sizeof(fr_t), ctx->stream));
-    TSG_CUDA(ctx, q.alloc(n * sizeof(fr_t), ctx->stream));
     TSG_CUDA(ctx, val.alloc(64, ctx->stream));
+    cudaError_t aerr;
+    fr_t* q_p = (fr_t*)arena_get(ctx, tsgpu_ctx::ARENA_QUOT, n * sizeof(fr_t), &aerr);
+    if (!q_p) return cuda_fail(ctx, aerr, "cudaMalloc(quotient)");
     TSG_CUDA(ctx, cudaMemcpyAsync(dpw.p, pw, sizeof(pw), cudaMemcpyHostToDevice, ctx->stream));
     fr_t zf; memcpy(zf.l, z->l, 32);
     unsigned launches = 0;
-    TSG_CUDA(ctx, poly_open_launch(poly->d, n, zf, dpw.as<fr_t>(), pw[POLY_PW], totals.as<fr_t>(), carry.as<fr_t>(), q.as<fr_t>(), val.as<fr_t>(),
+    KernelTimer kt_open(ctx, "open_scan");
+    TSG_CUDA(ctx, poly_open_launch(poly->d, n, zf, dpw.as<fr_t>(), pw[POLY_PW], totals.as<fr_t>(), carry.as<fr_t>(), q_p, val.as<fr_t>(),
                                    ctx->stream, &launches));
     ctx->launches += launches;
     TSG_CUDA(ctx, cudaMemcpyAsync(ctx->host_out, val.p, sizeof(fr_t), cudaMemcpyDeviceToHost, ctx->stream));
-    int rc = msm_device(ctx, srs->d, q.as<fr_t>(), n - 1, proof);
+    int rc = msm_device(ctx, srs->d, q_p, n - 1, proof);
     if (rc) return rc;
     TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     memcpy(value, ctx->host_out, 32);

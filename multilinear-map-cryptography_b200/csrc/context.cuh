@@ -2,7 +2,9 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <map>
 #include <string>
+#include <vector>
 #include "../../include/tsgpu.h"
 #include "fp.cuh"
 #include "sumcheck.cuh"
@@ -21,6 +23,17 @@ struct tsgpu_ctx {
     tsg::fr_t* host_out = nullptr;     // pinned, 8 elements
     void* comm = nullptr;              // multi-GPU communicator (comm.cu), optional
     void* interp = nullptr;            // cached interpolation plan (interp.cu)
+    // optional per-kernel device timing (CUDA events on `stream`), enabled by tsgpu_set_tuning("kernel_timing", 1)
+    // grow-only scratch arenas for the large per-call work buffers (MSM sort/bucket scratch, interpolation ping-pong,
+    // quotient) - reused across calls so that the hot path performs no allocation at all
+    enum { ARENA_MSM = 0, ARENA_INTERP = 1, ARENA_QUOT = 2, ARENA_COUNT = 3 };
+    void* arena[ARENA_COUNT] = {nullptr, nullptr, nullptr};
+    size_t arena_bytes[ARENA_COUNT] = {0, 0, 0};
+    uint64_t msm_points = 0;           // points processed by MSMs (for points/s reporting)
+    bool timing = false;
+    struct Pending { std::string name; cudaEvent_t a, b; };
+    std::vector<Pending> pending;
+    std::map<std::string, std::pair<double, uint64_t>> timers;   // name -> (total ms, launches)
 };
 
 struct tsgpu_table {
@@ -60,5 +73,23 @@ struct TempBuf {
 };
 
 int table_alloc(tsgpu_ctx* ctx, unsigned num_vars, tsgpu_table** out);
+// persistent scratch of at least `bytes` (contents undefined); nullptr + *err on failure
+void* arena_get(tsgpu_ctx* ctx, int slot, size_t bytes, cudaError_t* err);
+
+// RAII scope timing one kernel (or a short sequence) on the context stream when timing is enabled
+struct KernelTimer {
+    tsgpu_ctx* ctx; cudaEvent_t a = nullptr, b = nullptr; const char* name;
+    KernelTimer(tsgpu_ctx* c, const char* n) : ctx(c), name(n) {
+        if (!ctx->timing) return;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        cudaEventRecord(a, ctx->stream);
+    }
+    ~KernelTimer() {
+        if (!a) return;
+        cudaEventRecord(b, ctx->stream);
+        ctx->pending.push_back({name, a, b});
+    }
+};
+void timers_collect(tsgpu_ctx* ctx);   // after a stream synchronisation: fold finished event pairs into ctx->timers
 
 }  // namespace tsg

@@ -326,7 +326,8 @@ struct InterpPlan {
         // ---- step A: c = (v / j!) * ((-1)^j / j!)  truncated to n
         fr_t *bufA;
         const unsigned logM = logn + 1; const size_t M = 2 * n;
-        if ((e = cudaMallocAsync((void**)&bufA, M * 32, st()))) return e;
+        bufA = (fr_t*)arena_get(ctx, tsgpu_ctx::ARENA_INTERP, M * 32, &e);
+        if (!bufA) return e;
         if ((e = ensure_bhat(logn))) return e;
         k_mul_table<<<gridfor(M, 256, cap()), 256, 0, st()>>>(bufA, vals, ifact, n, M, 0, 1); ++launches;
         if ((e = conv_with_spectrum(bufA, logM, 1, bhat[logn]))) return e;
@@ -348,7 +349,6 @@ struct InterpPlan {
             if ((e = conv_with_spectrum(V, lM, nblocks, fhat[ls]))) return e;
             k_merge<<<gridfor(n, 256, cap()), 256, 0, st()>>>(coeffs, V, lM, n); ++launches;
         }
-        cudaFreeAsync(bufA, st());
         return cudaGetLastError();
     }
 };

@@ -51,23 +51,74 @@ __global__ void k_msm_digits(const fr_t* scalars, size_t n, unsigned c, unsigned
     }
 }
 
-// ---------------------------------------------------------------- 2. exclusive scan (single block, any length)
-__global__ void k_exclusive_scan(const unsigned* in, unsigned* out, size_t n, unsigned* total) {
-    __shared__ unsigned long long sums[1024];
-    const size_t per = (n + blockDim.x - 1) / blockDim.x;
-    const size_t b = (size_t)threadIdx.x * per, e = b + per < n ? b + per : n;
-    unsigned long long s = 0;
-    for (size_t i = b; i < e; ++i) s += in[i];
-    sums[threadIdx.x] = s;
+// ---------------------------------------------------------------- 2. exclusive scan of u32 counters (three small kernels)
+// tile = SCAN_THREADS * SCAN_ITEMS consecutive counters per block
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ unsigned block_exclusive_scan_u32(unsigned v, unsigned* total) {
+    __shared__ unsigned warp_sums[SCAN_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+    if (lane == 31) warp_sums[warp] = x;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned long long acc = 0;
-        for (unsigned t = 0; t < blockDim.x; ++t) { unsigned long long v = sums[t]; sums[t] = acc; acc += v; }
-        if (total) *total = (unsigned)acc;
+    if (warp == 0) {
+        unsigned w = lane < SCAN_THREADS / 32 ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, w, d); if (lane >= d) w += y; }
+        if (lane < SCAN_THREADS / 32) warp_sums[lane] = w;   // inclusive over warps
     }
     __syncthreads();
-    unsigned acc = (unsigned)sums[threadIdx.x];
-    for (size_t i = b; i < e; ++i) { unsigned v = in[i]; out[i] = acc; acc += v; }
+    unsigned warp_off = warp ? warp_sums[warp - 1] : 0;
+    if (total) *total = warp_sums[SCAN_THREADS / 32 - 1];
+    return warp_off + x - v;   // exclusive prefix of v within the block
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile_sums(const unsigned* in, size_t n, unsigned* tile_sums) {
+    const size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+    unsigned s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) if (base + k < n) s += in[base + k];
+    unsigned tot;
+    block_exclusive_scan_u32(s, &tot);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+}
+// one block: exclusive scan of the tile sums in place (any count), total to *total
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(unsigned* tile_sums, size_t ntiles, unsigned* total) {
+    __shared__ unsigned carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (size_t b = 0; b < ntiles; b += SCAN_THREADS) {
+        size_t i = b + threadIdx.x;
+        unsigned v = i < ntiles ? tile_sums[i] : 0, tot;
+        unsigned ex = block_exclusive_scan_u32(v, &tot);
+        unsigned c = carry;
+        if (i < ntiles) tile_sums[i] = c + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry = c + tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total) *total = carry;
+}
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const unsigned* in, unsigned* out, size_t n, const unsigned* tile_offsets) {
+    const size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+    unsigned v[SCAN_ITEMS], s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) { v[k] = base + k < n ? in[base + k] : 0; s += v[k]; }
+    unsigned acc = tile_offsets[blockIdx.x] + block_exclusive_scan_u32(s, nullptr);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) { if (base + k < n) out[base + k] = acc; acc += v[k]; }
+}
+// out = exclusive scan of in; scratch holds ceil(n / SCAN_TILE) counters
+static cudaError_t exclusive_scan_u32(const unsigned* in, unsigned* out, size_t n, unsigned* scratch, unsigned* total, cudaStream_t s) {
+    const size_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    k_scan_tile_sums<<<(unsigned)ntiles, SCAN_THREADS, 0, s>>>(in, n, scratch);
+    k_scan_tiles<<<1, SCAN_THREADS, 0, s>>>(scratch, ntiles, total);
+    k_scan_apply<<<(unsigned)ntiles, SCAN_THREADS, 0, s>>>(in, out, n, scratch);
+    return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------- 3. scatter point indices into bucket order
@@ -266,6 +317,7 @@ size_t msm_scratch_bytes(size_t n, unsigned c, MsmLayout* L) {
     L->item_off = take(nbuckets * 4);
     L->item_bucket = take(max_items * 4);
     L->n_items = take(256);
+    L->scan_tmp = take((nbuckets / 1024 + 64) * 4);
     L->partial = take(max_items * sizeof(g1_xyzz));
     L->blockres = take((size_t)W * L->blocks_per_window * sizeof(g1_xyzz));
     L->window_out = take(W * sizeof(g1_jac));
@@ -274,7 +326,7 @@ size_t msm_scratch_bytes(size_t n, unsigned c, MsmLayout* L) {
 
 // returns the number of kernels launched through *launches
 cudaError_t msm_run(const g1_affine* bases, const fr_t* scalars, size_t n, const MsmLayout& L, unsigned char* scratch, int sm_count,
-                    cudaStream_t s, unsigned* launches) {
+                    cudaStream_t s, unsigned* launches, cudaEvent_t* acc_events) {
     unsigned* dig = (unsigned*)(scratch + L.dig); unsigned* sorted = (unsigned*)(scratch + L.sorted);
     unsigned* hist = (unsigned*)(scratch + L.hist); unsigned* offsets = (unsigned*)(scratch + L.offsets);
     unsigned* cursor = (unsigned*)(scratch + L.cursor); unsigned* items = (unsigned*)(scratch + L.items);
@@ -288,15 +340,17 @@ cudaError_t msm_run(const g1_affine* bases, const fr_t* scalars, size_t n, const
     if ((e = cudaMemsetAsync(cursor, 0, L.nbuckets * 4, s))) return e;
     const size_t cap = (size_t)sm_count * 8;
     k_msm_digits<<<gridfor(n, 256, cap), 256, 0, s>>>(scalars, n, L.c, L.W, dig, hist);
-    k_exclusive_scan<<<1, 1024, 0, s>>>(hist, offsets, L.nbuckets, nullptr);
+    exclusive_scan_u32(hist, offsets, L.nbuckets, (unsigned*)(scratch + L.scan_tmp), nullptr, s);
     k_msm_scatter<<<gridfor((size_t)L.W * n, 256, cap), 256, 0, s>>>(dig, n, L.c, L.W, offsets, cursor, sorted);
     k_msm_item_counts<<<gridfor(L.nbuckets, 256, cap), 256, 0, s>>>(hist, L.nbuckets, items);
-    k_exclusive_scan<<<1, 1024, 0, s>>>(items, item_off, L.nbuckets, n_items);
+    exclusive_scan_u32(items, item_off, L.nbuckets, (unsigned*)(scratch + L.scan_tmp), n_items, s);
     k_msm_item_fill<<<gridfor(L.nbuckets, 256, cap), 256, 0, s>>>(items, item_off, L.nbuckets, item_bucket);
+    if (acc_events) cudaEventRecord(acc_events[0], s);
     k_msm_accumulate<<<gridfor(L.max_items, MSM_ACC_THREADS, (size_t)sm_count * 16), MSM_ACC_THREADS, 0, s>>>(bases, sorted, hist, offsets, item_off, item_bucket, n_items, partial);
+    if (acc_events) cudaEventRecord(acc_events[1], s);
     k_msm_bucket_reduce<<<gridfor((size_t)L.W * L.blocks_per_window, 128, cap), 128, 0, s>>>(partial, items, item_off, L.c, L.W, blockres);
     k_msm_window_sum<<<L.W, MSM_SUM_THREADS, 0, s>>>(blockres, L.blocks_per_window, wout);
-    if (launches) *launches += 9;
+    if (launches) *launches += 13;
     return cudaGetLastError();
 }
 

@@ -15,14 +15,14 @@ constexpr size_t MSM_INV_SPAN = 32;       // points per batch inversion
 struct MsmLayout {
     unsigned c, W, blocks_per_window;
     size_t nbuckets, max_items;
-    size_t dig, sorted, hist, offsets, cursor, items, item_off, item_bucket, n_items, partial, blockres, window_out;
+    size_t dig, sorted, hist, offsets, cursor, items, item_off, item_bucket, n_items, scan_tmp, partial, blockres, window_out;
 };
 
 unsigned msm_window_bits(size_t n);
 size_t msm_scratch_bytes(size_t n, unsigned c, MsmLayout* L);
 // runs steps 1-4; the W window sums (Jacobian) are left at scratch + L.window_out
 cudaError_t msm_run(const g1_affine* bases, const fr_t* scalars, size_t n, const MsmLayout& L, unsigned char* scratch, int sm_count,
-                    cudaStream_t s, unsigned* launches);
+                    cudaStream_t s, unsigned* launches, cudaEvent_t* acc_events = nullptr);   // acc_events[2]: around the accumulate kernel
 
 cudaError_t launch_tau_powers(const fr_t& tau, size_t first, size_t n, fr_t* out, int sm_count, cudaStream_t s);
 cudaError_t launch_fixed_base_mul(const fr_t* scalars, size_t n, const g1_affine* table, g1_xyzz* out, int sm_count, cudaStream_t s);
