@@ -120,6 +120,8 @@ void tsgpu_sc_end(tsgpu_sc* sc);
  * download: back to the host as Jacobian points with z = 1 (the same group elements). */
 int tsgpu_srs_generate(tsgpu_ctx* ctx, const tsgpu_fr* tau, size_t n, tsgpu_srs** out);
 int tsgpu_srs_upload(tsgpu_ctx* ctx, const tsgpu_g1* powers, size_t n, tsgpu_srs** out);
+/* powers first .. first + n - 1 only: the slice a point-sharded MSM rank holds */
+int tsgpu_srs_generate_range(tsgpu_ctx* ctx, const tsgpu_fr* tau, size_t first, size_t n, tsgpu_srs** out);
 int tsgpu_srs_download(tsgpu_ctx* ctx, const tsgpu_srs* srs, size_t first, size_t count, tsgpu_g1* out);
 size_t tsgpu_srs_len(const tsgpu_srs* srs);
 void tsgpu_srs_free(tsgpu_ctx* ctx, tsgpu_srs* srs);
@@ -162,6 +164,7 @@ int tsgpu_msm_g1(tsgpu_ctx* ctx, const tsgpu_g1a* bases, const tsgpu_fr* scalars
 void tsgpu_g1_hash(const tsgpu_g1* p, tsgpu_fr* out);
 void tsgpu_g1_compress(const tsgpu_g1* p, uint8_t out[32]);
 int tsgpu_g1_equal(const tsgpu_g1* a, const tsgpu_g1* b);
+void tsgpu_g1_add(const tsgpu_g1* a, const tsgpu_g1* b, tsgpu_g1* out);
 
 /* ---- host side of the path: Transcript and the SumCheck::prove / verify loops --------------------------
  * These run on the CPU (the Fiat-Shamir transcript stays on the host) and drive the round kernels above.
@@ -183,6 +186,15 @@ int tsgpu_sumcheck_prove_product(tsgpu_ctx* ctx, tsgpu_table* const* tables, int
 /* SumCheck::verify (sumcheck.rs:113-153): *valid = 1/0; TSGPU_E_SUMCHECK for a wrong number of rounds */
 int tsgpu_sumcheck_verify(unsigned num_vars, const tsgpu_fr* claimed_sum, const tsgpu_fr* round_polys, size_t num_rounds,
                           const tsgpu_fr* final_evaluation, tsgpu_transcript* transcript, int* valid, tsgpu_fr* challenges);
+
+/* CPU helpers for sharded (one process per GPU) provers, see multilinear-map-cryptography_b200/distributed.py:
+ * round coefficients from g(0..3) (sumcheck.rs:201-205), Horner (utils.rs:217-221), field add / mul, and the
+ * conversion of an integer all-reduce result (8 sums of zero-extended 32-bit limbs per element) back to Fr */
+void tsgpu_sumcheck_round_coeffs(const tsgpu_fr evals[4], tsgpu_fr coeffs[4]);
+void tsgpu_horner_eval(const tsgpu_fr* coeffs, size_t n, const tsgpu_fr* x, tsgpu_fr* out);
+void tsgpu_fr_add(const tsgpu_fr* a, const tsgpu_fr* b, tsgpu_fr* out);
+void tsgpu_fr_mul(const tsgpu_fr* a, const tsgpu_fr* b, tsgpu_fr* out);
+void tsgpu_fr_from_limb_sums(const uint64_t* sums, size_t n, tsgpu_fr* out);
 
 /* ---- setup_params, Twist::prove / verify, Shout::prove / verify  (host orchestration over the calls above) --
  * setup_params(log_size) (src/utils.rs:79-131): max_operations = 4 * 2^log_size, tau = first Fr::rand of

@@ -189,6 +189,12 @@ class Context:
         self.check(lib().tsgpu_srs_generate(self._h, _p(_fr(tau, 1)), C.c_size_t(n), C.byref(h)))
         return Srs(self, h)
 
+    def srs_generate_range(self, tau, first: int, n: int) -> "Srs":
+        """g1_powers[first .. first + n) only (the slice a point-sharded MSM rank holds)"""
+        h = C.c_void_p()
+        self.check(lib().tsgpu_srs_generate_range(self._h, _p(_fr(tau, 1)), C.c_size_t(first), C.c_size_t(n), C.byref(h)))
+        return Srs(self, h)
+
     def srs_upload(self, powers_jac) -> "Srs":
         powers_jac = np.ascontiguousarray(powers_jac, dtype=np.uint64).reshape(-1, 12)
         h = C.c_void_p()

@@ -355,3 +355,47 @@ int tsgpu_g1_equal(const tsgpu_g1* a, const tsgpu_g1* b) {
 }
 
 }  // extern "C"
+
+extern "C" {
+// g1_powers[first .. first + n) of setup_params (utils.rs:89-96): the slice a point-sharded MSM rank needs
+int tsgpu_srs_generate_range(tsgpu_ctx* ctx, const tsgpu_fr* tau, size_t first, size_t n, tsgpu_srs** out) {
+    if (!ctx || !tau || !out) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    tsgpu_srs* full = nullptr;
+    if (first == 0) return tsgpu_srs_generate(ctx, tau, n, out);
+    // tau^first * (tau^i G) = (tau^(first+i)) G: generate with scalars tau^(first+i)
+    tsgpu_srs* srs = new (std::nothrow) tsgpu_srs;
+    if (!srs) return fail(ctx, TSGPU_E_PROOF_GENERATION, "out of host memory");
+    (void)full;
+    srs->n = n;
+    cudaError_t e = cudaMalloc((void**)&srs->d, (n ? n : 1) * sizeof(g1_affine));
+    if (e != cudaSuccess) { delete srs; return cuda_fail(ctx, e, "cudaMalloc(srs)"); }
+    // reuse the generator table of tsgpu_srs_generate by generating a 1-point SRS is wasteful; rebuild the table here
+    std::vector<g1_affine> table(32 * 255);
+    {
+        G1J base = G1J::generator();
+        std::vector<G1J> jac(32 * 255);
+        for (int w = 0; w < 32; ++w) { G1J acc = base; for (int d = 1; d <= 255; ++d) { jac[w * 255 + d - 1] = acc; acc = acc.add(base); } base = acc; }
+        for (size_t i = 0; i < jac.size(); ++i) { Fq64 ax, ay; jac[i].to_affine(ax, ay); memcpy(table[i].x.l, ax.l, 32); memcpy(table[i].y.l, ay.l, 32); }
+    }
+    TempBuf dtable, scal, xyzz;
+    TSG_CUDA(ctx, dtable.alloc(table.size() * sizeof(g1_affine), ctx->stream));
+    TSG_CUDA(ctx, scal.alloc(n * sizeof(fr_t), ctx->stream));
+    TSG_CUDA(ctx, xyzz.alloc(n * sizeof(g1_xyzz), ctx->stream));
+    TSG_CUDA(ctx, cudaMemcpyAsync(dtable.p, table.data(), table.size() * sizeof(g1_affine), cudaMemcpyHostToDevice, ctx->stream));
+    fr_t t; memcpy(t.l, tau->l, 32);
+    if (n) {
+        TSG_CUDA(ctx, launch_tau_powers(t, first, n, scal.as<fr_t>(), ctx->sm_count, ctx->stream));
+        TSG_CUDA(ctx, launch_fixed_base_mul(scal.as<fr_t>(), n, dtable.as<g1_affine>(), xyzz.as<g1_xyzz>(), ctx->sm_count, ctx->stream));
+        TSG_CUDA(ctx, launch_batch_to_affine(xyzz.as<g1_xyzz>(), n, srs->d, ctx->sm_count, ctx->stream));
+        ctx->launches += 3;
+    }
+    TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = srs;
+    return TSGPU_OK;
+}
+// group addition of two G1Projective values on the CPU (combining per-rank MSM results)
+void tsgpu_g1_add(const tsgpu_g1* a, const tsgpu_g1* b, tsgpu_g1* out) {
+    G1J x, y; memcpy(&x, a, 96); memcpy(&y, b, 96);
+    G1J r = x.add(y); memcpy(out, &r, 96);
+}
+}

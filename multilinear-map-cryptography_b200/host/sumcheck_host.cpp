@@ -151,3 +151,57 @@ int tsgpu_sumcheck_verify(unsigned num_vars, const tsgpu_fr* claimed_sum, const 
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------ helpers for sharded provers
+#include "field64.hpp"
+extern "C" {
+
+// the 4 coefficients SumCheck::compute_round_polynomial returns for evaluations g(0..3) (sumcheck.rs:201-205)
+void tsgpu_sumcheck_round_coeffs(const tsgpu_fr evals[4], tsgpu_fr coeffs[4]) {
+    fr_t e[4], c[4];
+    for (int i = 0; i < 4; ++i) memcpy(e[i].l, evals[i].l, 32);
+    interpolate4(e, c);
+    for (int i = 0; i < 4; ++i) memcpy(coeffs[i].l, c[i].l, 32);
+}
+// field_utils::horner_eval (utils.rs:217-221)
+void tsgpu_horner_eval(const tsgpu_fr* coeffs, size_t n, const tsgpu_fr* x, tsgpu_fr* out) {
+    std::vector<fr_t> c(n);
+    for (size_t i = 0; i < n; ++i) memcpy(c[i].l, coeffs[i].l, 32);
+    fr_t xx; memcpy(xx.l, x->l, 32);
+    fr_t r = horner_eval(c.data(), n, xx);
+    memcpy(out->l, r.l, 32);
+}
+void tsgpu_fr_add(const tsgpu_fr* a, const tsgpu_fr* b, tsgpu_fr* out) {
+    fr_t x, y; memcpy(x.l, a->l, 32); memcpy(y.l, b->l, 32);
+    fr_t r = x + y; memcpy(out->l, r.l, 32);
+}
+void tsgpu_fr_mul(const tsgpu_fr* a, const tsgpu_fr* b, tsgpu_fr* out) {
+    fr_t x, y; memcpy(x.l, a->l, 32); memcpy(y.l, b->l, 32);
+    fr_t r = x * y; memcpy(out->l, r.l, 32);
+}
+// Collective result -> field element: each element arrives as 8 sums of zero-extended 32-bit limbs (what an
+// integer all-reduce over the ranks produces); value = sum_i limb_sum[i] * 2^(32 i) mod r.  Montgomery form is
+// linear, so summing the limbs of Montgomery representations and reducing gives the Montgomery form of the sum.
+void tsgpu_fr_from_limb_sums(const uint64_t* sums, size_t n, tsgpu_fr* out) {
+    using tsg::host::Fr64;
+    for (size_t e = 0; e < n; ++e) {
+        // carry-propagate into 9 x 32-bit limbs (sums < 2^32 * ranks)
+        uint64_t carry = 0; uint32_t limbs[10];
+        for (int i = 0; i < 8; ++i) { uint64_t v = sums[8 * e + i] + carry; limbs[i] = (uint32_t)v; carry = v >> 32; }
+        limbs[8] = (uint32_t)carry; limbs[9] = (uint32_t)(carry >> 32);
+        // low 256 bits + high * 2^256: 2^256 mod r is the Montgomery one
+        uint64_t lo[4];
+        for (int i = 0; i < 4; ++i) lo[i] = (uint64_t)limbs[2 * i] | ((uint64_t)limbs[2 * i + 1] << 32);
+        while (Fr64::geq_mod(lo)) Fr64::sub_mod(lo);
+        Fr64 acc; memcpy(acc.l, lo, 32);
+        uint64_t hi = (uint64_t)limbs[8] | ((uint64_t)limbs[9] << 32);
+        Fr64 one = Fr64::one();   // raw limbs of 2^256 mod r
+        // hi * (2^256 mod r) by double-and-add on raw residues (hi < number of ranks)
+        Fr64 add = Fr64::zero();
+        for (int b = 63; b >= 0; --b) { add = add + add; if ((hi >> b) & 1) add = add + one; }
+        acc = acc + add;
+        memcpy(out[e].l, acc.l, 32);
+    }
+}
+
+}  // extern "C"
