@@ -127,8 +127,8 @@ TSG_HD void mont_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
         uint32_t bi = b[0];
 #pragma unroll
         for (int j = 0; j < 8; j += 2) {
-            Y[j] = ptx::mul_lo(a[j], bi); Y[j + 1] = ptx::mul_hi(a[j], bi);
-            X[j] = ptx::mul_lo(a[j + 1], bi); X[j + 1] = ptx::mul_hi(a[j + 1], bi);
+            ptx::mul_wide(Y[j], Y[j + 1], a[j], bi);
+            ptx::mul_wide(X[j], X[j + 1], a[j + 1], bi);
         }
         redc_step<P>(X, Y);
     }
@@ -175,8 +175,8 @@ TSG_HD void mul_wide(uint32_t* t, const uint32_t* a, const uint32_t* b) {
     for (int k = 8; k < 16; ++k) { E[k] = 0; O[k] = 0; }
 #pragma unroll
     for (int j = 0; j < 8; j += 2) {
-        E[j] = ptx::mul_lo(a[j], b[0]); E[j + 1] = ptx::mul_hi(a[j], b[0]);
-        O[j] = ptx::mul_lo(a[j + 1], b[0]); O[j + 1] = ptx::mul_hi(a[j + 1], b[0]);
+        ptx::mul_wide(E[j], E[j + 1], a[j], b[0]);
+        ptx::mul_wide(O[j], O[j + 1], a[j + 1], b[0]);
     }
 #pragma unroll
     for (int i = 1; i < 8; ++i) {

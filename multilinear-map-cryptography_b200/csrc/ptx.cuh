@@ -94,6 +94,17 @@ TSG_HD uint32_t mul_hi(uint32_t a, uint32_t b) {
     return hi32(a, b);
 #endif
 }
+// full 32x32 -> 64 product as one IMAD.WIDE (no carry predicate: full issue rate)
+TSG_HD void mul_wide(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    unsigned long long r;
+    asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b));
+    lo = (uint32_t)r; hi = (uint32_t)(r >> 32);
+#else
+    unsigned long long r = (unsigned long long)a * b;
+    lo = (uint32_t)r; hi = (uint32_t)(r >> 32);
+#endif
+}
 TSG_HD uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) {
 #if defined(__CUDA_ARCH__)
     uint32_t r; asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r;
