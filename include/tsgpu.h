@@ -203,6 +203,8 @@ void tsgpu_fr_from_limb_sums(const uint64_t* sums, size_t n, tsgpu_fr* out);
 typedef struct tsgpu_params tsgpu_params;
 typedef struct tsgpu_proof tsgpu_proof;    /* TwistProof / ShoutProof: 2 commitments, SumCheckProof, 0|2 openings, 0|2 evaluations */
 int tsgpu_setup_params(tsgpu_ctx* ctx, size_t log_size, tsgpu_params** out);
+/* VerifierParams only (log_size, max_operations, commitment_vk, fiat_shamir_seed): CPU, no context needed */
+int tsgpu_setup_verifier_params(size_t log_size, tsgpu_params** out);
 void tsgpu_params_free(tsgpu_ctx* ctx, tsgpu_params* p);
 size_t tsgpu_params_log_size(const tsgpu_params* p);
 size_t tsgpu_params_max_operations(const tsgpu_params* p);
@@ -220,11 +222,19 @@ int tsgpu_twist_prove_dev(tsgpu_ctx* ctx, const tsgpu_params* params, tsgpu_poly
  * TSGPU_E_INVALID_PARAMETERS "Too many lookup operations" beyond max_operations. */
 int tsgpu_shout_prove(tsgpu_ctx* ctx, const tsgpu_params* params, const tsgpu_fr* entries, size_t num_entries,
                       const uint64_t* lookup_indices, size_t num_lookups, tsgpu_proof** out);
-/* Twist::verify / Shout::verify control flow (src/twist.rs:255-304, src/shout.rs:225-274): transcript replay,
- * SumCheck::verify, opening checks.  The opening check uses the trapdoor kept in the params (src/utils.rs:107)
- * instead of the pairing of src/commitments.rs:201-228 (CPU pairing verifier: next row). */
+/* Twist::verify / Shout::verify (src/twist.rs:255-304, src/shout.rs:225-274): transcript replay, SumCheck::verify and
+ * the two KZGCommitment::verify pairing checks (src/commitments.rs:201-228) - all on the CPU, as in the reference. */
 int tsgpu_twist_verify(tsgpu_ctx* ctx, const tsgpu_params* params, const tsgpu_proof* proof, int* valid);
 int tsgpu_shout_verify(tsgpu_ctx* ctx, const tsgpu_params* params, const tsgpu_proof* proof, int* valid);
+
+/* KZGCommitment::verify / batch_verify with the verification key held in the params (CPU, BN254 optimal-ate pairing) */
+int tsgpu_kzg_verify(const tsgpu_params* params, const tsgpu_g1* commitment, const tsgpu_fr* point, const tsgpu_fr* value,
+                     const tsgpu_g1* proof, int* valid);
+int tsgpu_kzg_batch_verify(const tsgpu_params* params, const tsgpu_g1* commitments, const tsgpu_fr* points, const tsgpu_fr* values,
+                           const tsgpu_g1* proofs, size_t n, int* valid);
+/* pairing self-test hooks: prod_i e(a_i G1, b_i G2) == 1 ?;  G2 generator on the twist and of order r */
+int tsgpu_pairing_product_of_generators_is_one(const tsgpu_fr* a, const tsgpu_fr* b, size_t n);
+int tsgpu_g2_generator_checks(void);
 
 size_t tsgpu_proof_num_rounds(const tsgpu_proof* p);
 size_t tsgpu_proof_num_openings(const tsgpu_proof* p);

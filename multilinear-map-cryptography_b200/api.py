@@ -82,6 +82,52 @@ class ProverParams:
 VerifierParams = ProverParams
 
 
+class HostVerifierParams:
+    """VerifierParams built without a GPU (src/utils.rs:36-50): what a verifier-only process holds"""
+
+    def __init__(self, log_size: int):
+        self._h = C.c_void_p()
+        rc = lib().tsgpu_setup_verifier_params(C.c_size_t(log_size), C.byref(self._h))
+        if rc:
+            raise TwistAndShoutError(rc, "setup_verifier_params failed")
+        self.log_size = log_size
+        self.max_operations = 4 << log_size
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().tsgpu_params_free(None, self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+
+def kzg_verify(verifier_params, commitment, point, value, proof) -> bool:
+    """KZGCommitment::verify(vk, commitment, point, value, proof) (src/commitments.rs:201-228); CPU pairing"""
+    ok = C.c_int(0)
+    commitment = np.ascontiguousarray(commitment, dtype=np.uint64).reshape(12)
+    proof = np.ascontiguousarray(proof, dtype=np.uint64).reshape(12)
+    rc = lib().tsgpu_kzg_verify(verifier_params._h, _p(commitment), _p(_fr(point, 1)), _p(_fr(value, 1)), _p(proof), C.byref(ok))
+    if rc:
+        raise TwistAndShoutError(rc, "kzg_verify: bad arguments")
+    return bool(ok.value)
+
+
+def kzg_batch_verify(verifier_params, commitments, points, values, proofs) -> bool:
+    """KZGCommitment::batch_verify (src/commitments.rs:230-301)"""
+    commitments = np.ascontiguousarray(commitments, dtype=np.uint64).reshape(-1, 12)
+    proofs = np.ascontiguousarray(proofs, dtype=np.uint64).reshape(-1, 12)
+    points = _fr(points); values = _fr(values)
+    n = commitments.shape[0]
+    if not (points.shape[0] == values.shape[0] == proofs.shape[0] == n):
+        raise TwistAndShoutError(4, "Batch verify input lengths must match")            # commitments.rs:237-243
+    ok = C.c_int(0)
+    rc = lib().tsgpu_kzg_batch_verify(verifier_params._h, _p(commitments), _p(points), _p(values), _p(proofs), C.c_size_t(n), C.byref(ok))
+    if rc:
+        raise TwistAndShoutError(rc, "kzg_batch_verify: bad arguments")
+    return bool(ok.value)
+
+
 def setup_params(ctx: Context, log_size: int) -> Tuple[ProverParams, VerifierParams]:
     """setup_params(log_size) -> (ProverParams, VerifierParams)   (src/utils.rs:79-131)"""
     h = C.c_void_p()

@@ -64,6 +64,9 @@ def lib() -> C.CDLL:
         L.tsgpu_g1_compress.argtypes = [C.c_void_p, C.c_void_p]
         L.tsgpu_g1_equal.argtypes = [C.c_void_p, C.c_void_p]
         L.tsgpu_timer_reset.argtypes = [C.c_void_p]
+        L.tsgpu_params_free.argtypes = [C.c_void_p, C.c_void_p]
+        L.tsgpu_kzg_verify.argtypes = [C.c_void_p] * 5 + [C.c_void_p]
+        L.tsgpu_kzg_batch_verify.argtypes = [C.c_void_p] * 5 + [C.c_size_t, C.c_void_p]
         L.tsgpu_transcript_new.restype = C.c_void_p
         L.tsgpu_transcript_new.argtypes = [C.c_void_p]
         L.tsgpu_transcript_free.argtypes = [C.c_void_p]

@@ -2,15 +2,15 @@
 // (src/utils.rs:79-131, src/twist.rs:107-252, src/shout.rs:97-222): same inputs, same transcript order, same
 // error behaviour, every heavy step on the device through the C ABI of include/tsgpu.h.
 //
-// Until the pairing verifier exists, verify() replays the transcript and the sum-check exactly
-// as the reference does and checks each KZG opening with the trapdoor the reference keeps in its params
-// (CommitmentParams.tau, src/utils.rs:61,107):  C - v G == (tau - z) pi.
+// verify() replays the transcript and the sum-check exactly as the reference does and checks each KZG opening with
+// the pairing equation of src/commitments.rs:201-228 (host/pairing.hpp, CPU).
 #include <cstring>
 #include <new>
 #include <string>
 #include <vector>
 #include "../csrc/context.cuh"
 #include "field64.hpp"
+#include "pairing.hpp"
 #include "sumcheck_host.hpp"
 #include "transcript.hpp"
 
@@ -23,6 +23,7 @@ struct tsgpu_params {                 // ProverParams (+ the verifier's copy of 
     tsgpu_fr tau;                     // CommitmentParams.tau (always Some)
     uint8_t fiat_shamir_seed[32];
     tsgpu_srs* srs = nullptr;         // g1_powers[0 ..= max_degree] on the device
+    VerifyKey vk;                     // CommitmentVerificationKey: g1 generator, g2 generator, g2_tau (utils.rs:110-114)
 };
 
 struct tsgpu_proof {                  // TwistProof / ShoutProof (src/twist.rs:76-89, src/shout.rs:64-79)
@@ -101,15 +102,37 @@ int tsgpu_setup_params(tsgpu_ctx* ctx, size_t log_size, tsgpu_params** out) {
     const size_t max_degree = next_pow2(p->max_operations);                // utils.rs:89
     int rc = tsgpu_srs_generate(ctx, &p->tau, max_degree + 1, &p->srs);    // utils.rs:93-96
     if (rc) { delete p; return rc; }
+    p->vk.g1_generator = G1J::generator();
+    p->vk.g2_generator = G2A::generator();
+    p->vk.g2_tau = p->vk.g2_generator.mul(Fr64::from_raw(p->tau.l));              // utils.rs:98
     rng.fill_bytes(p->fiat_shamir_seed, 32);                               // utils.rs:101-102
     rc = tsgpu_interpolate_prepare(ctx, (unsigned)(log_size + 2));
     if (rc) { tsgpu_srs_free(ctx, p->srs); delete p; return rc; }
     *out = p;
     return TSGPU_OK;
 }
+// VerifierParams only (src/utils.rs:36-50,110-128): no SRS, no GPU - what a verifier process needs
+int tsgpu_setup_verifier_params(size_t log_size, tsgpu_params** out) {
+    if (!out) return TSGPU_E_INVALID_PARAMETERS;
+    tsgpu_params* p = new (std::nothrow) tsgpu_params;
+    if (!p) return TSGPU_E_PROOF_GENERATION;
+    p->log_size = log_size;
+    p->max_operations = (size_t)1 << (log_size + 2);
+    uint8_t seed[32]; memset(seed, 42, 32);
+    ChaCha20Rng rng(seed);
+    fr_t tau = rng.rand_field<fr_t>();
+    p->tau = abi_of(tau);
+    p->vk.g1_generator = G1J::generator();
+    p->vk.g2_generator = G2A::generator();
+    p->vk.g2_tau = p->vk.g2_generator.mul(Fr64::from_raw(p->tau.l));
+    rng.fill_bytes(p->fiat_shamir_seed, 32);
+    p->srs = nullptr;
+    *out = p;
+    return TSGPU_OK;
+}
 void tsgpu_params_free(tsgpu_ctx* ctx, tsgpu_params* p) {
     if (!p) return;
-    tsgpu_srs_free(ctx, p->srs);
+    if (p->srs) tsgpu_srs_free(ctx, p->srs);
     delete p;
 }
 size_t tsgpu_params_log_size(const tsgpu_params* p) { return p->log_size; }
@@ -186,7 +209,7 @@ size_t tsgpu_proof_bytes(const tsgpu_proof* p, uint8_t* out, size_t capacity) {
     return b.size();
 }
 
-// ------------------------------------------------------------------------------------ verify (transcript + sum-check + trapdoor KZG)
+// ------------------------------------------------------------------------------------ verify (transcript + sum-check + pairing KZG)
 // Twist::verify / Shout::verify control flow (twist.rs:255-304, shout.rs:225-274); *valid = 1/0.
 static int verify_common(tsgpu_ctx* ctx, const tsgpu_params* params, const tsgpu_proof* proof, const char* label_a, const char* label_b, int* valid) {
     if (!params || !proof || !valid) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
@@ -207,13 +230,11 @@ static int verify_common(tsgpu_ctx* ctx, const tsgpu_params* params, const tsgpu
     if (!ok) { *valid = 0; return TSGPU_OK; }
     std::vector<fr_t> ch = tr.challenge_field_elements("opening_challenges", num_vars);
     if (!ch.empty() && proof->opening_proofs.size() >= 2 && proof->final_evaluations.size() >= 2) {   // twist.rs:275
-        Fr64 tau = Fr64::from_raw(params->tau.l), z = Fr64::from_raw(ch[0].l);
-        for (int i = 0; i < 2; ++i) {
+        Fr64 z = Fr64::from_raw(ch[0].l);
+        for (int i = 0; i < 2; ++i) {                                                                 // KZGCommitment::verify x 2
             G1J C, pi; memcpy(&C, &proof->commitments[i], 96); memcpy(&pi, &proof->opening_proofs[i], 96);
             Fr64 v = Fr64::from_raw(proof->final_evaluations[i].l);
-            G1J lhs = C.add(G1J::generator().mul(v).neg());
-            G1J rhs = pi.mul(tau - z);
-            if (!lhs.equals(rhs)) { *valid = 0; return TSGPU_OK; }
+            if (!kzg_verify(params->vk, C, z, v, pi)) { *valid = 0; return TSGPU_OK; }
         }
     }
     *valid = 1;
@@ -239,5 +260,59 @@ void tsgpu_fr_from_u64(const uint64_t* in, size_t n, tsgpu_fr* out) {
 // into_bigint(): Montgomery limbs -> canonical integer limbs.  CPU.
 void tsgpu_fr_to_canonical(const tsgpu_fr* in, size_t n, tsgpu_fr* out) {
     for (size_t i = 0; i < n; ++i) { Fr64 f = Fr64::from_raw(in[i].l).from_mont(); memcpy(out[i].l, f.l, 32); }
+}
+}
+
+// ------------------------------------------------------------------------------------ KZG verify / pairing (CPU)
+extern "C" {
+// KZGCommitment::verify(vk, commitment, point, value, proof) (src/commitments.rs:201-228); vk taken from params
+int tsgpu_kzg_verify(const tsgpu_params* params, const tsgpu_g1* commitment, const tsgpu_fr* point, const tsgpu_fr* value,
+                     const tsgpu_g1* proof, int* valid) {
+    if (!params || !commitment || !point || !value || !proof || !valid) return TSGPU_E_INVALID_PARAMETERS;
+    G1J C, pi; memcpy(&C, commitment, 96); memcpy(&pi, proof, 96);
+    *valid = kzg_verify(params->vk, C, Fr64::from_raw(point->l), Fr64::from_raw(value->l), pi) ? 1 : 0;
+    return TSGPU_OK;
+}
+// KZGCommitment::batch_verify (src/commitments.rs:230-301): random linear combination with gamma_i = Fr::rand of
+// ChaCha20Rng::from_seed([42; 32]); TSGPU_E_COMMITMENT "Batch verify input lengths must match" is the caller's
+// concern here (one length parameter).  Empty batch verifies.
+int tsgpu_kzg_batch_verify(const tsgpu_params* params, const tsgpu_g1* commitments, const tsgpu_fr* points, const tsgpu_fr* values,
+                           const tsgpu_g1* proofs, size_t n, int* valid) {
+    if (!params || !valid || (n && (!commitments || !points || !values || !proofs))) return TSGPU_E_INVALID_PARAMETERS;
+    if (n == 0) { *valid = 1; return TSGPU_OK; }
+    uint8_t seed[32]; memset(seed, 42, 32);
+    ChaCha20Rng rng(seed);
+    G1J bc = G1J::identity(), bp = G1J::identity();
+    Fr64 bv = Fr64::zero();
+    G2A bg2 = G2A::infinity();
+    for (size_t i = 0; i < n; ++i) {
+        fr_t g32 = rng.rand_field<fr_t>();
+        Fr64 gamma = Fr64::from_raw(g32.l);
+        G1J C, pi; memcpy(&C, &commitments[i], 96); memcpy(&pi, &proofs[i], 96);
+        bc = bc.add(C.mul(gamma));
+        bv = bv + Fr64::from_raw(values[i].l) * gamma;
+        bp = bp.add(pi.mul(gamma));
+        G2A t = params->vk.g2_tau.add(params->vk.g2_generator.mul(Fr64::from_raw(points[i].l)).neg());
+        bg2 = bg2.add(t.mul(gamma));
+    }
+    G1J left = bc.add(params->vk.g1_generator.mul(bv).neg());
+    *valid = pairing_product_is_one({left, bp.neg()}, {params->vk.g2_generator, bg2}) ? 1 : 0;
+    return TSGPU_OK;
+}
+// prod_i e(a_i * G1, b_i * G2) == 1 ?  (self-test hook for the pairing: bilinearity / non-degeneracy checks)
+int tsgpu_pairing_product_of_generators_is_one(const tsgpu_fr* a, const tsgpu_fr* b, size_t n) {
+    std::vector<G1J> P; std::vector<G2A> Q;
+    for (size_t i = 0; i < n; ++i) {
+        P.push_back(G1J::generator().mul(Fr64::from_raw(a[i].l)));
+        Q.push_back(G2A::generator().mul(Fr64::from_raw(b[i].l)));
+    }
+    return pairing_product_is_one(P, Q) ? 1 : 0;
+}
+int tsgpu_g2_generator_checks(void) {   // on the twist, and of order r: (r - 1) Q + Q = infinity
+    G2A g = G2A::generator();
+    if (!g.on_curve()) return 0;
+    Fr64 m1 = Fr64::zero() - Fr64::one();
+    G2A t = g.mul(m1).add(g);
+    return t.inf ? 1 : 0;
 }
 }
