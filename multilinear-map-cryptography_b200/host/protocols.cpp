@@ -275,7 +275,8 @@ int tsgpu_kzg_verify(const tsgpu_params* params, const tsgpu_g1* commitment, con
 }
 // KZGCommitment::batch_verify (src/commitments.rs:230-301): random linear combination with gamma_i = Fr::rand of
 // ChaCha20Rng::from_seed([42; 32]); TSGPU_E_COMMITMENT "Batch verify input lengths must match" is the caller's
-// concern here (one length parameter).  Empty batch verifies.
+// concern here (one length parameter).  Empty batch verifies.  NOTE: the reference formula applies gamma_i to the proof AND to
+// the G2 side, so it rejects every non-empty batch (it is never called in the reference); mirrored as written.
 int tsgpu_kzg_batch_verify(const tsgpu_params* params, const tsgpu_g1* commitments, const tsgpu_fr* points, const tsgpu_fr* values,
                            const tsgpu_g1* proofs, size_t n, int* valid) {
     if (!params || !valid || (n && (!commitments || !points || !values || !proofs))) return TSGPU_E_INVALID_PARAMETERS;
