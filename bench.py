@@ -3,8 +3,10 @@
 
 Workload (BASELINE.json configs[1]): Twist::prove over a synthetic MemoryTrace of 2^20 read/write operations on
 2^16 memory cells, setup_params(18) (prove rejects more than 4 * 2^log_size operations, src/twist.rs:108).
-A "step" is one Twist::prove: 2 interpolations of 2^20 points, 4 G1 MSMs of 2^20 points (2 commitments + 2
-opening quotients), 2 Horner/quotient scans, the 20-round (all-zero) sum-check transcript on the host.
+A "step" is one Twist::prove.  Default path: 4 G1 MSMs of 2^20 points over the evaluation-basis SRS (2 commitments over the
+raw addresses / values, 2 opening quotients), 2 barycentric evaluation + quotient passes, the 20-round (all-zero) sum-check
+transcript on the host.  `coefficient_path` reports the reference's own sequence (2 interpolations of 2^20 points, 4 full-width
+MSMs, 2 Horner/quotient scans) - identical proof bytes, checked in the run.
 
     python bench.py --gpus N --steps K --warmup W            our arm (torchrun launches N ranks for N > 1)
     python bench.py --impl reference ...                     CPU arm: the oracle port of the reference prover
@@ -212,61 +214,79 @@ def main():
     assert twist.verify(proof, vp), "benchmark proof does not verify"
     proof_len = len(proof.to_bytes())
 
-    # ---- e2e: public API, host buffers
-    for _ in range(W):
-        twist.prove_arrays(addr_h, vals_h, isw)
-    barrier()
-    sampler.mark()
-    l0 = ctx.launch_count
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(K):
-        p = twist.prove_arrays(addr_h, vals_h, isw)
-        _ = p.final_evaluation                                   # D2H'd proof contents are read
-    e1.record(stream)
-    barrier()
-    e2e_ms = e0.elapsed_time(e1) / K
-    e2e_launches = ctx.launch_count - l0
-
-    # ---- device-resident: padded vectors already in HBM
     base_a = ctx.poly_from_u64(addr_h); base_v = ctx.poly_upload_padded(vals_h, n)
-    ctx.set_tuning("kernel_timing", 1)
-    for _ in range(W):
-        twist.prove_device(base_a.clone(), base_v.clone())
-    clones = [(base_a.clone(), base_v.clone()) for _ in range(K)]
-    ctx.timer_reset()
-    barrier()
-    l0 = ctx.launch_count
-    e0.record(stream)
-    for a, v in clones:
-        twist.prove_device(a, v)
-    e1.record(stream)
-    barrier()
-    dev_ms = e0.elapsed_time(e1) / K
-    launches = ctx.launch_count - l0
+
+    def time_e2e():
+        """public API, pinned host buffers in, proof read back: ms per proof, launches per proof"""
+        for _ in range(W):
+            twist.prove_arrays(addr_h, vals_h, isw)
+        barrier()
+        l0 = ctx.launch_count
+        e0.record(stream)
+        for _ in range(K):
+            p = twist.prove_arrays(addr_h, vals_h, isw)
+            _ = p.final_evaluation                               # D2H'd proof contents are read
+        e1.record(stream)
+        barrier()
+        return e0.elapsed_time(e1) / K, (ctx.launch_count - l0) // K
+
+    def time_device():
+        """padded vectors already in HBM: per-proof ms, launches, MSM work counters and kernel timers of the timed region"""
+        for _ in range(W):
+            twist.prove_device(base_a.clone(), base_v.clone())
+        clones = [(base_a.clone(), base_v.clone()) for _ in range(K)]
+        ctx.set_tuning("kernel_timing", 1)
+        ctx.timer_reset()
+        barrier()
+        c0 = {k: ctx.counter(k) for k in ("launches", "msm_calls", "msm_points", "msm_entries")}
+        e0.record(stream)
+        for a, v in clones:
+            twist.prove_device(a, v)
+        e1.record(stream)
+        barrier()
+        r = {"ms": e0.elapsed_time(e1) / K}
+        r.update({k: ctx.counter(k) - c0[k] for k in c0})
+        for name in ("msm_accumulate", "msm_total", "interpolate", "open_bary", "open_scan"):
+            r[name + "_ms"], r[name + "_cnt"] = ctx.timer_read(name)
+        ctx.set_tuning("kernel_timing", 0)
+        return r
+
+    # ---- coefficient path (tuning eval_basis = 0): interpolate -> commit -> open on coefficients, the reference's own sequence of steps
+    ctx.set_tuning("eval_basis", 0)
+    proof_c = twist.prove_arrays(addr_h, vals_h, isw)
+    coef_e2e_ms, coef_e2e_launches = time_e2e()
+    coef = time_device()
+    # ---- default path (evaluation-basis SRS prepared by setup_params): commitments and openings straight from the values
+    ctx.set_tuning("eval_basis", 1)
+    assert twist.prove_arrays(addr_h, vals_h, isw).to_bytes() == proof_c.to_bytes(), "the two paths must give identical proof bytes"
+    sampler.mark()
+    e2e_ms, e2e_launches = time_e2e()
+    dflt = time_device()
     clocks = sampler.stop()
-    acc_ms, acc_cnt = ctx.timer_read("msm_accumulate")
-    msm_ms, msm_cnt = ctx.timer_read("msm_total")
-    interp_ms, interp_cnt = ctx.timer_read("interpolate")
-    ctx.set_tuning("kernel_timing", 0)
+    dev_ms = dflt["ms"]
 
     if world > 1:
-        t = torch.tensor([dev_ms, e2e_ms], device="cuda", dtype=torch.float64)
+        t = torch.tensor([dev_ms, e2e_ms, coef["ms"], coef_e2e_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_ms = float(t[0]), float(t[1])
+        dev_ms, e2e_ms, coef["ms"], coef_e2e_ms = (float(x) for x in t)
 
-    # ---- roofline of the dominant kernel of the step: MSM bucket accumulation (integer-pipe bound)
-    windows = 16                                                 # c = 16 signed digits at n = 2^20
-    imad_per_add = 10 * (2 * 8 * 8 + 8)                          # 8M + 2S Fq products x (2 n^2 + n) 32-bit multiply-adds, n = 8 limbs
-    n_msm = [n, n, n - 1, n - 1]
-    alg_imad_per_launch = float(np.mean(n_msm)) * windows * imad_per_add
-    acc_launch_ms = acc_ms / max(acc_cnt, 1)
-    achieved = alg_imad_per_launch / (acc_launch_ms * 1e-3) / 1e12 if acc_launch_ms > 0 else 0.0
-    roofline = {"kernel": "k_msm_accumulate", "bound": "int32-pipe", "achieved": achieved, "peak": IMAD_PEAK_TOPS, "unit": "TIMAD/s",
-                "frac": achieved / IMAD_PEAK_TOPS, "traffic": None, "launch_ms": acc_launch_ms, "launches": acc_cnt,
-                "share_of_step": acc_ms / K / dev_ms if dev_ms > 0 else None,
-                "peak_source": "tools/ubench.cu on this pool: 18.5 T IMAD.WIDE/s without carry predicate (the carry-chained form issues at half that rate)",
-                "algorithmic_unit": "n x 16 windows x (8M+2S) x 136 IMAD per MSM launch"}
+    # ---- roofline of the dominant kernel of the step: MSM bucket accumulation (integer-pipe bound).
+    # Algorithmic work per launch = bucket entries (non-zero signed 16-bit digits, counted by the library) x one mixed
+    # XYZZ + affine addition (8M + 2S = 10 Fq products) x (2 * 8 * 8 + 8) 32-bit multiply-adds per Montgomery product.
+    imad_per_add = 10 * (2 * 8 * 8 + 8)
+
+    def acc_roofline(r):
+        launch_ms = r["msm_accumulate_ms"] / max(r["msm_accumulate_cnt"], 1)
+        entries = r["msm_entries"] / max(r["msm_calls"], 1)
+        ach = entries * imad_per_add / (launch_ms * 1e-3) / 1e12 if launch_ms > 0 else 0.0
+        return {"kernel": "k_msm_accumulate", "bound": "int32-pipe", "achieved": ach, "peak": IMAD_PEAK_TOPS, "unit": "TIMAD/s",
+                "frac": ach / IMAD_PEAK_TOPS, "traffic": None, "launch_ms": launch_ms, "launches": r["msm_accumulate_cnt"],
+                "entries_per_launch": entries, "share_of_step": r["msm_accumulate_ms"] / K / r["ms"] if r["ms"] > 0 else None}
+
+    roofline = acc_roofline(dflt)
+    roofline["peak_source"] = "tools/ubench.cu on this pool: 18.5 T IMAD.WIDE/s without carry predicate (the carry-chained form the multiplier needs issues at half that rate)"
+    roofline["algorithmic_unit"] = "bucket entries x (8M + 2S) x 136 IMAD per launch (mean over the 4 MSMs of a proof)"
 
     # ---- side measurement (BASELINE metric 'sumcheck fold GB/s'): bind one 2^26-entry table, HBM-bound
     fold = None
@@ -304,23 +324,31 @@ def main():
         cpu = {"value": v, "unit": "ms", "cores": cores, "kind": "port", "sample": sample}
 
     if rank == 0:
+        def breakdown(r):
+            return {"msm_4x": r["msm_total_ms"] / K, "msm_accumulate_4x": r["msm_accumulate_ms"] / K, "interpolate_2x": r["interpolate_ms"] / K,
+                    "open_barycentric_2x": r["open_bary_ms"] / K, "open_scan_2x": r["open_scan_ms"] / K, "bucket_entries": r["msm_entries"] // K,
+                    "gpu_launches": r["launches"] // K}
         line = {
             "metric": "twist_prove_ms_at_2^20_ops", "value": dev_ms, "unit": "ms", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_ms, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32x8 (BN254 Fr/Fq, 256-bit Montgomery on the integer pipe)", "data": "synthetic",
             "config": {"workload": f"Twist::prove, 2^{LOG_CELLS} cells, 2^{LOG_OPS} random read/write ops, setup_params({LOG_SIZE})",
+                       "path": "default: evaluation-basis SRS (commit / open from the values, no interpolation); byte-identical to the coefficient path, which is timed in `coefficient_path`",
                        "per_gpu": "one independent proof per GPU" if world > 1 else "single GPU",
-                       "l2": "per-step working set (2 x 32 MiB vectors, 64 MiB SRS, ~190 MiB MSM scratch per MSM) exceeds the 126 MB L2; no explicit flush",
+                       "l2": "per-step working set (2 x 32 MiB vectors, 2 x 64 MiB SRS, ~200 MiB MSM scratch per MSM) exceeds the 126 MB L2; no explicit flush",
                        "proof_bytes": proof_len, "setup_s": setup_s},
             "clocks": clocks,
             "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": int(addr_h.nbytes + vals_h.nbytes), "d2h_bytes_per_step": int(4 * 16 * 96 + 2 * 32),
-                    "gpu_launches": int(e2e_launches // K)},
-            "gpu_launches": int(launches),
+                    "gpu_launches": int(e2e_launches)},
+            "gpu_launches": int(dflt["launches"]),
             "roofline": roofline,
             "roofline_fold": fold,
             "cpu_baseline": cpu,
-            "breakdown_ms_per_step": {"interpolate_2x": interp_ms / K, "msm_4x": msm_ms / K, "msm_accumulate_4x": acc_ms / K},
-            "msm_points_per_s": float(np.sum(n_msm)) * K / (msm_ms * 1e-3) if msm_ms > 0 else None,
+            "breakdown_ms_per_step": breakdown(dflt),
+            "coefficient_path": {"value": coef["ms"], "unit": "ms", "e2e": coef_e2e_ms, "breakdown_ms_per_step": breakdown(coef), "roofline": acc_roofline(coef),
+                                 "note": "tsgpu_set_tuning(eval_basis, 0): 2 interpolations + 4 full-width MSMs + 2 Horner/quotient scans"},
+            "msm_points_per_s": dflt["msm_points"] / (dflt["msm_total_ms"] * 1e-3) if dflt["msm_total_ms"] > 0 else None,
+            "msm_full_width_points_per_s": coef["msm_points"] / (coef["msm_total_ms"] * 1e-3) if coef["msm_total_ms"] > 0 else None,
             "ops_per_s_all_gpus": world * n / (dev_ms * 1e-3),
         }
         print(json.dumps(line))

@@ -59,6 +59,8 @@ const char* tsgpu_last_error(const tsgpu_ctx* ctx);
 uint64_t tsgpu_launch_count(const tsgpu_ctx* ctx);
 int tsgpu_synchronize(tsgpu_ctx* ctx);
 int tsgpu_sm_count(const tsgpu_ctx* ctx);
+/* work counters since tsgpu_init: "launches", "msm_calls", "msm_points", "msm_entries" (non-zero digits = bucket additions) */
+uint64_t tsgpu_counter_read(const tsgpu_ctx* ctx, const char* name);
 /* tuning knobs (process-wide): "tma_min_log2" = log2 of the per-stream size from which the sum-check rounds use
  * the TMA bulk-copy pipelined kernels instead of the plain streaming kernels (negative: never; default never) */
 int tsgpu_set_tuning(tsgpu_ctx* ctx, const char* key, long value);
@@ -157,6 +159,20 @@ int tsgpu_kzg_open(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_fr* polynom
 int tsgpu_kzg_commit_dev(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_poly* polynomial, tsgpu_g1* out);
 int tsgpu_kzg_open_dev(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_poly* polynomial, const tsgpu_fr* z,
                        tsgpu_fr* value, tsgpu_g1* proof);
+/* ---- evaluation-basis form of vector_to_polynomial + commit / open  (src/twist.rs:151-160,226-243, 307-315) ----
+ * Twist/Shout::prove only ever commit to interpolants of a vector on the nodes 0..m-1.  The commitment is linear in
+ * the VALUES: commit(P) = sum_j v_j * [L_j(tau)]_1.  lagrange_prepare builds those basis points for a power-of-two m
+ * from the trapdoor that setup_params holds (CommitmentParams.tau, src/utils.rs:84,107); an SRS made by
+ * tsgpu_srs_upload has no trapdoor (can_lagrange == 0) and callers stay on interpolate + commit.
+ * commit_values: one MSM over the raw values (same group element as interpolate + commit).
+ * open_values:   value = P(z) by the barycentric formula, proof = sum_j Q(j) [L_j(tau)]_1 with
+ *                Q(j) = (v_j - value) / (j - z); TSGPU_E_POLYNOMIAL if z is one of the nodes. */
+int tsgpu_srs_can_lagrange(const tsgpu_srs* srs);
+int tsgpu_srs_has_lagrange(const tsgpu_srs* srs, size_t m);
+int tsgpu_srs_lagrange_prepare(tsgpu_ctx* ctx, const tsgpu_srs* srs, size_t m);
+int tsgpu_kzg_commit_values_dev(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_poly* values, tsgpu_g1* out);
+int tsgpu_kzg_open_values_dev(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_poly* values, const tsgpu_fr* z,
+                              tsgpu_fr* value, tsgpu_g1* proof);
 /* plain G1 MSM over caller-supplied affine bases: sum_i scalars[i] * bases[i] */
 int tsgpu_msm_g1(tsgpu_ctx* ctx, const tsgpu_g1a* bases, const tsgpu_fr* scalars, size_t n, tsgpu_g1* out);
 /* CPU helpers on single points: KZGCommitmentValue::hash (commitments.rs:73-84), ark-serialize compressed bytes

@@ -47,6 +47,8 @@ def lib() -> C.CDLL:
         L.tsgpu_last_error.argtypes = [C.c_void_p]
         L.tsgpu_launch_count.restype = C.c_uint64
         L.tsgpu_launch_count.argtypes = [C.c_void_p]
+        L.tsgpu_counter_read.restype = C.c_uint64
+        L.tsgpu_counter_read.argtypes = [C.c_void_p, C.c_char_p]
         L.tsgpu_table_num_vars.restype = C.c_uint
         L.tsgpu_table_num_vars.argtypes = [C.c_void_p]
         L.tsgpu_sc_num_vars.restype = C.c_uint
@@ -57,6 +59,8 @@ def lib() -> C.CDLL:
         L.tsgpu_srs_len.restype = C.c_size_t
         L.tsgpu_srs_len.argtypes = [C.c_void_p]
         L.tsgpu_srs_free.argtypes = [C.c_void_p, C.c_void_p]
+        L.tsgpu_srs_can_lagrange.argtypes = [C.c_void_p]
+        L.tsgpu_srs_has_lagrange.argtypes = [C.c_void_p, C.c_size_t]
         L.tsgpu_poly_len.restype = C.c_size_t
         L.tsgpu_poly_len.argtypes = [C.c_void_p]
         L.tsgpu_poly_free.argtypes = [C.c_void_p, C.c_void_p]
@@ -122,6 +126,10 @@ class Context:
     @property
     def sm_count(self) -> int:
         return int(lib().tsgpu_sm_count(self._h))
+
+    def counter(self, name: str) -> int:
+        """work counters: launches, msm_calls, msm_points, msm_entries"""
+        return int(lib().tsgpu_counter_read(self._h, name.encode()))
 
     def set_tuning(self, key: str, value: int):
         self.check(lib().tsgpu_set_tuning(self._h, key.encode(), C.c_long(value)))
@@ -435,6 +443,17 @@ class Srs:
         self.ctx.check(lib().tsgpu_srs_download(self.ctx._h, self._h, C.c_size_t(first), C.c_size_t(count), _p(out)))
         return out
 
+    def can_lagrange(self) -> bool:
+        """True when the handle keeps the trapdoor (made by srs_generate / setup_params): evaluation-basis commits possible"""
+        return bool(lib().tsgpu_srs_can_lagrange(self._h))
+
+    def has_lagrange(self, m: int) -> bool:
+        return bool(lib().tsgpu_srs_has_lagrange(self._h, C.c_size_t(m)))
+
+    def lagrange_prepare(self, m: int):
+        """build [L_j(tau)]_1 for the nodes 0..m-1 (cached in the handle)"""
+        self.ctx.check(lib().tsgpu_srs_lagrange_prepare(self.ctx._h, self._h, C.c_size_t(m)))
+
     def free(self):
         if self._h:
             lib().tsgpu_srs_free(self.ctx._h, self._h)
@@ -514,6 +533,24 @@ class KZGCommitment:
             polynomial = _fr(polynomial)
             ctx.check(lib().tsgpu_kzg_open(ctx._h, params._h, _p(polynomial), C.c_size_t(polynomial.shape[0]), _p(point),
                                            _p(value), _p(proof)))
+        return value, proof
+
+
+    @staticmethod
+    def commit_values(params: Srs, values: "Poly") -> np.ndarray:
+        """commit(vector_to_polynomial(values)) as one MSM over the values (evaluation-basis SRS, csrc/lagrange.cu)"""
+        ctx = params.ctx
+        out = np.empty(12, dtype=np.uint64)
+        ctx.check(lib().tsgpu_kzg_commit_values_dev(ctx._h, params._h, values._h, _p(out)))
+        return out
+
+    @staticmethod
+    def open_values(params: Srs, values: "Poly", point):
+        """open(vector_to_polynomial(values), point) without the coefficients -> (value, proof)"""
+        ctx = params.ctx
+        value = np.empty(4, dtype=np.uint64); proof = np.empty(12, dtype=np.uint64)
+        point = _fr(point, 1)
+        ctx.check(lib().tsgpu_kzg_open_values_dev(ctx._h, params._h, values._h, _p(point), _p(value), _p(proof)))
         return value, proof
 
 

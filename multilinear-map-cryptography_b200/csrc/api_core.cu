@@ -122,6 +122,15 @@ void tsgpu_destroy(tsgpu_ctx* ctx) {
 const char* tsgpu_last_error(const tsgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
 uint64_t tsgpu_launch_count(const tsgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int tsgpu_sm_count(const tsgpu_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+// monotonically increasing work counters: "launches", "msm_calls", "msm_points", "msm_entries" (bucket entries = mixed additions)
+uint64_t tsgpu_counter_read(const tsgpu_ctx* ctx, const char* name) {
+    if (!ctx || !name) return 0;
+    if (!strcmp(name, "launches")) return ctx->launches;
+    if (!strcmp(name, "msm_calls")) return ctx->msm_calls;
+    if (!strcmp(name, "msm_points")) return ctx->msm_points;
+    if (!strcmp(name, "msm_entries")) return ctx->msm_entries;
+    return 0;
+}
 int tsgpu_synchronize(tsgpu_ctx* ctx) {
     TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return TSGPU_OK;
@@ -150,6 +159,7 @@ int tsgpu_set_tuning(tsgpu_ctx* ctx, const char* key, long value) {
         return TSGPU_OK;
     }
     if (!strcmp(key, "kernel_timing")) { ctx->timing = value != 0; return TSGPU_OK; }
+    if (!strcmp(key, "eval_basis")) { ctx->eval_basis = value != 0; return TSGPU_OK; }   // 0: Twist/Shout::prove interpolate and commit coefficients
     return fail(ctx, TSGPU_E_INVALID_PARAMETERS, std::string("unknown tuning key ") + key);
 }
 

@@ -7,6 +7,8 @@
 #include "poly.cuh"
 #include "interp.cuh"
 #include "mle.cuh"
+#include "lagrange.cuh"
+#include <map>
 #include "../host/field64.hpp"
 
 using namespace tsg;
@@ -17,6 +19,12 @@ using tsg::host::G1J;
 struct tsgpu_srs {
     g1_affine* d = nullptr;   // n affine points, identity = (0,0)
     size_t n = 0;
+    // evaluation-basis companion (lagrange.cu): for a domain size m (power of two) the points [L_j(tau)]_1, j < m, of the
+    // Lagrange basis on the nodes 0..m-1.  Built from the trapdoor, which setup_params holds (src/utils.rs:84,107);
+    // an SRS uploaded as bare points has none and the coefficient path (interpolate, then commit) is used.
+    bool has_tau = false;
+    tsgpu_fr tau;
+    std::map<size_t, g1_affine*> lagrange;
 };
 struct tsgpu_poly {
     fr_t* d = nullptr;        // n coefficients, low -> high, natural order
@@ -58,11 +66,54 @@ int msm_device(tsgpu_ctx* ctx, const g1_affine* bases, const fr_t* scalars, size
     ctx->msm_points += n;
     ctx->launches += launches;
     std::vector<g1_jac> win(L.W);
+    unsigned counts[2] = {0, 0};   // work items, bucket entries
     TSG_CUDA(ctx, cudaMemcpyAsync(win.data(), scratch_p + L.window_out, L.W * sizeof(g1_jac), cudaMemcpyDeviceToHost, ctx->stream));
+    TSG_CUDA(ctx, cudaMemcpyAsync(counts, scratch_p + L.n_items, sizeof(counts), cudaMemcpyDeviceToHost, ctx->stream));
     TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->msm_entries += counts[1];
+    ctx->msm_calls += 1;
     timers_collect(ctx);
     G1J r = combine_windows(win.data(), L.W, L.c);
     memcpy(out, &r, 96);
+    return TSGPU_OK;
+}
+
+// byte-window table of the generator for k_fixed_base_mul: table[w * 255 + d - 1] = d * 256^w * G (affine); built once per process
+const std::vector<g1_affine>& generator_table() {
+    static std::vector<g1_affine> table;
+    if (!table.empty()) return table;
+    table.resize(32 * 255);
+    G1J base = G1J::generator();
+    std::vector<G1J> jac(32 * 255);
+    for (int w = 0; w < 32; ++w) {
+        G1J acc = base;
+        for (int d = 1; d <= 255; ++d) { jac[w * 255 + d - 1] = acc; acc = acc.add(base); }
+        base = acc;
+    }
+    // batch normalisation (Montgomery trick)
+    std::vector<Fq64> pref(jac.size());
+    Fq64 acc = Fq64::one();
+    for (size_t i = 0; i < jac.size(); ++i) { pref[i] = acc; acc = acc * jac[i].z; }
+    Fq64 inv = acc.inverse();
+    for (size_t i = jac.size(); i-- > 0;) {
+        Fq64 zi = inv * pref[i]; inv = inv * jac[i].z;
+        Fq64 zi2 = zi.sqr();
+        Fq64 ax = jac[i].x * zi2, ay = jac[i].y * zi2 * zi;
+        memcpy(table[i].x.l, ax.l, 32); memcpy(table[i].y.l, ay.l, 32);
+    }
+    return table;
+}
+// out[i] = scalars[i] * G as affine points (scalars on the device, Montgomery form)
+int fixed_base_points(tsgpu_ctx* ctx, const fr_t* scalars, size_t n, g1_affine* out) {
+    if (!n) return TSGPU_OK;
+    const std::vector<g1_affine>& table = generator_table();
+    TempBuf dtable, xyzz;
+    TSG_CUDA(ctx, dtable.alloc(table.size() * sizeof(g1_affine), ctx->stream));
+    TSG_CUDA(ctx, xyzz.alloc(n * sizeof(g1_xyzz), ctx->stream));
+    TSG_CUDA(ctx, cudaMemcpyAsync(dtable.p, table.data(), table.size() * sizeof(g1_affine), cudaMemcpyHostToDevice, ctx->stream));
+    TSG_CUDA(ctx, launch_fixed_base_mul(scalars, n, dtable.as<g1_affine>(), xyzz.as<g1_xyzz>(), ctx->sm_count, ctx->stream));
+    TSG_CUDA(ctx, launch_batch_to_affine(xyzz.as<g1_xyzz>(), n, out, ctx->sm_count, ctx->stream));
+    ctx->launches += 2;
     return TSGPU_OK;
 }
 
@@ -72,49 +123,9 @@ extern "C" {
 
 // ------------------------------------------------------------------------------------------- SRS
 int tsgpu_srs_generate(tsgpu_ctx* ctx, const tsgpu_fr* tau, size_t n, tsgpu_srs** out) {
-    if (!ctx || !tau || !out) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
-    tsgpu_srs* srs = new (std::nothrow) tsgpu_srs;
-    if (!srs) return fail(ctx, TSGPU_E_PROOF_GENERATION, "out of host memory");
-    srs->n = n;
-    cudaError_t e = cudaMalloc((void**)&srs->d, (n ? n : 1) * sizeof(g1_affine));
-    if (e != cudaSuccess) { delete srs; return cuda_fail(ctx, e, "cudaMalloc(srs)"); }
-    // byte-window table of the generator on the host: table[w * 255 + d - 1] = d * 256^w * G
-    std::vector<g1_affine> table(32 * 255);
-    {
-        G1J base = G1J::generator();
-        std::vector<G1J> jac(32 * 255);
-        for (int w = 0; w < 32; ++w) {
-            G1J acc = base;
-            for (int d = 1; d <= 255; ++d) { jac[w * 255 + d - 1] = acc; acc = acc.add(base); }
-            base = acc;
-        }
-        // batch normalisation (Montgomery trick)
-        std::vector<Fq64> pref(jac.size());
-        Fq64 acc = Fq64::one();
-        for (size_t i = 0; i < jac.size(); ++i) { pref[i] = acc; acc = acc * jac[i].z; }
-        Fq64 inv = acc.inverse();
-        for (size_t i = jac.size(); i-- > 0;) {
-            Fq64 zi = inv * pref[i]; inv = inv * jac[i].z;
-            Fq64 zi2 = zi.sqr();
-            Fq64 ax = jac[i].x * zi2, ay = jac[i].y * zi2 * zi;
-            memcpy(table[i].x.l, ax.l, 32); memcpy(table[i].y.l, ay.l, 32);
-        }
-    }
-    TempBuf dtable, scal, xyzz;
-    TSG_CUDA(ctx, dtable.alloc(table.size() * sizeof(g1_affine), ctx->stream));
-    TSG_CUDA(ctx, scal.alloc(n * sizeof(fr_t), ctx->stream));
-    TSG_CUDA(ctx, xyzz.alloc(n * sizeof(g1_xyzz), ctx->stream));
-    TSG_CUDA(ctx, cudaMemcpyAsync(dtable.p, table.data(), table.size() * sizeof(g1_affine), cudaMemcpyHostToDevice, ctx->stream));
-    fr_t t; memcpy(t.l, tau->l, 32);
-    if (n) {
-        TSG_CUDA(ctx, launch_tau_powers(t, 0, n, scal.as<fr_t>(), ctx->sm_count, ctx->stream));
-        TSG_CUDA(ctx, launch_fixed_base_mul(scal.as<fr_t>(), n, dtable.as<g1_affine>(), xyzz.as<g1_xyzz>(), ctx->sm_count, ctx->stream));
-        TSG_CUDA(ctx, launch_batch_to_affine(xyzz.as<g1_xyzz>(), n, srs->d, ctx->sm_count, ctx->stream));
-        ctx->launches += 3;
-    }
-    TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    *out = srs;
-    return TSGPU_OK;
+    int rc = tsgpu_srs_generate_range(ctx, tau, 0, n, out);
+    if (!rc) { (*out)->has_tau = true; (*out)->tau = *tau; }
+    return rc;
 }
 
 int tsgpu_srs_upload(tsgpu_ctx* ctx, const tsgpu_g1* powers, size_t n, tsgpu_srs** out) {
@@ -156,6 +167,7 @@ void tsgpu_srs_free(tsgpu_ctx* ctx, tsgpu_srs* srs) {
     (void)ctx;
     if (!srs) return;
     if (srs->d) cudaFree(srs->d);
+    for (auto& kv : srs->lagrange) cudaFree(kv.second);
     delete srs;
 }
 
@@ -318,9 +330,11 @@ int tsgpu_kzg_open_dev(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_poly* p
     TSG_CUDA(ctx, cudaMemcpyAsync(dpw.p, pw, sizeof(pw), cudaMemcpyHostToDevice, ctx->stream));
     fr_t zf; memcpy(zf.l, z->l, 32);
     unsigned launches = 0;
-    KernelTimer kt_open(ctx, "open_scan");
-    TSG_CUDA(ctx, poly_open_launch(poly->d, n, zf, dpw.as<fr_t>(), pw[POLY_PW], totals.as<fr_t>(), carry.as<fr_t>(), q_p, val.as<fr_t>(),
-                                   ctx->stream, &launches));
+    {
+        KernelTimer kt_open(ctx, "open_scan");
+        TSG_CUDA(ctx, poly_open_launch(poly->d, n, zf, dpw.as<fr_t>(), pw[POLY_PW], totals.as<fr_t>(), carry.as<fr_t>(), q_p, val.as<fr_t>(),
+                                       ctx->stream, &launches));
+    }
     ctx->launches += launches;
     TSG_CUDA(ctx, cudaMemcpyAsync(ctx->host_out, val.p, sizeof(fr_t), cudaMemcpyDeviceToHost, ctx->stream));
     int rc = msm_device(ctx, srs->d, q_p, n - 1, proof);
@@ -360,37 +374,108 @@ extern "C" {
 // g1_powers[first .. first + n) of setup_params (utils.rs:89-96): the slice a point-sharded MSM rank needs
 int tsgpu_srs_generate_range(tsgpu_ctx* ctx, const tsgpu_fr* tau, size_t first, size_t n, tsgpu_srs** out) {
     if (!ctx || !tau || !out) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
-    tsgpu_srs* full = nullptr;
-    if (first == 0) return tsgpu_srs_generate(ctx, tau, n, out);
-    // tau^first * (tau^i G) = (tau^(first+i)) G: generate with scalars tau^(first+i)
     tsgpu_srs* srs = new (std::nothrow) tsgpu_srs;
     if (!srs) return fail(ctx, TSGPU_E_PROOF_GENERATION, "out of host memory");
-    (void)full;
     srs->n = n;
     cudaError_t e = cudaMalloc((void**)&srs->d, (n ? n : 1) * sizeof(g1_affine));
     if (e != cudaSuccess) { delete srs; return cuda_fail(ctx, e, "cudaMalloc(srs)"); }
-    // reuse the generator table of tsgpu_srs_generate by generating a 1-point SRS is wasteful; rebuild the table here
-    std::vector<g1_affine> table(32 * 255);
-    {
-        G1J base = G1J::generator();
-        std::vector<G1J> jac(32 * 255);
-        for (int w = 0; w < 32; ++w) { G1J acc = base; for (int d = 1; d <= 255; ++d) { jac[w * 255 + d - 1] = acc; acc = acc.add(base); } base = acc; }
-        for (size_t i = 0; i < jac.size(); ++i) { Fq64 ax, ay; jac[i].to_affine(ax, ay); memcpy(table[i].x.l, ax.l, 32); memcpy(table[i].y.l, ay.l, 32); }
-    }
-    TempBuf dtable, scal, xyzz;
-    TSG_CUDA(ctx, dtable.alloc(table.size() * sizeof(g1_affine), ctx->stream));
-    TSG_CUDA(ctx, scal.alloc(n * sizeof(fr_t), ctx->stream));
-    TSG_CUDA(ctx, xyzz.alloc(n * sizeof(g1_xyzz), ctx->stream));
-    TSG_CUDA(ctx, cudaMemcpyAsync(dtable.p, table.data(), table.size() * sizeof(g1_affine), cudaMemcpyHostToDevice, ctx->stream));
+    TempBuf scal;
     fr_t t; memcpy(t.l, tau->l, 32);
+    int rc = TSGPU_OK;
     if (n) {
-        TSG_CUDA(ctx, launch_tau_powers(t, first, n, scal.as<fr_t>(), ctx->sm_count, ctx->stream));
-        TSG_CUDA(ctx, launch_fixed_base_mul(scal.as<fr_t>(), n, dtable.as<g1_affine>(), xyzz.as<g1_xyzz>(), ctx->sm_count, ctx->stream));
-        TSG_CUDA(ctx, launch_batch_to_affine(xyzz.as<g1_xyzz>(), n, srs->d, ctx->sm_count, ctx->stream));
-        ctx->launches += 3;
+        cudaError_t ce = scal.alloc(n * sizeof(fr_t), ctx->stream);
+        if (ce == cudaSuccess) ce = launch_tau_powers(t, first, n, scal.as<fr_t>(), ctx->sm_count, ctx->stream);   // tau^(first + i)
+        if (ce != cudaSuccess) rc = cuda_fail(ctx, ce, "tau powers");
+        ctx->launches += 1;
+        if (!rc) rc = fixed_base_points(ctx, scal.as<fr_t>(), n, srs->d);
     }
-    TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!rc) { cudaError_t ce = cudaStreamSynchronize(ctx->stream); if (ce != cudaSuccess) rc = cuda_fail(ctx, ce, "srs generation"); }
+    if (rc) { tsgpu_srs_free(ctx, srs); return rc; }
     *out = srs;
+    return TSGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------- evaluation-basis KZG
+static g1_affine* lagrange_basis(const tsgpu_srs* srs, size_t m) {
+    auto it = srs->lagrange.find(m);
+    return it == srs->lagrange.end() ? nullptr : it->second;
+}
+int tsgpu_srs_has_lagrange(const tsgpu_srs* srs, size_t m) { return srs && lagrange_basis(srs, m) ? 1 : 0; }
+int tsgpu_srs_can_lagrange(const tsgpu_srs* srs) { return srs && srs->has_tau ? 1 : 0; }
+
+// [L_j(tau)]_1 for the nodes 0..m-1 (m a power of two, m <= SRS length): L_j(tau) = N(tau) w_j / (tau - j) on the device,
+// then the same fixed-base kernel that builds g1_powers.  The handle caches the result (a const handle is a cache here).
+int tsgpu_srs_lagrange_prepare(tsgpu_ctx* ctx, const tsgpu_srs* srs_c, size_t m) {
+    if (!ctx || !srs_c) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    tsgpu_srs* srs = const_cast<tsgpu_srs*>(srs_c);
+    if (lagrange_basis(srs, m)) return TSGPU_OK;
+    if (!srs->has_tau) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "this SRS was uploaded without its trapdoor: no evaluation basis");
+    int lg = log2_exact(m);
+    if (lg < 0 || m > srs->n) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "evaluation-basis size must be a power of two within the SRS");
+    Fr64 tcan = Fr64::from_raw(srs->tau.l).from_mont();
+    if (!tcan.l[1] && !tcan.l[2] && !tcan.l[3] && tcan.l[0] < m) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "tau is an interpolation node");
+    const fr_t* ifact = nullptr;
+    TSG_CUDA(ctx, interp_factorials(ctx, (unsigned)lg, &ifact));
+    g1_affine* basis = nullptr;
+    cudaError_t e = cudaMalloc((void**)&basis, m * sizeof(g1_affine));
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc(lagrange basis)");
+    TempBuf inv, spans, scal, prod;
+    int rc = TSGPU_OK;
+    fr_t t; memcpy(t.l, srs->tau.l, 32);
+    cudaError_t ce = inv.alloc(m * sizeof(fr_t), ctx->stream);
+    if (ce == cudaSuccess) ce = spans.alloc(lag_num_spans(m) * sizeof(fr_t), ctx->stream);
+    if (ce == cudaSuccess) ce = scal.alloc(m * sizeof(fr_t), ctx->stream);
+    if (ce == cudaSuccess) ce = prod.alloc(sizeof(fr_t), ctx->stream);
+    if (ce == cudaSuccess) ce = launch_node_inverses(t, m, inv.as<fr_t>(), spans.as<fr_t>(), prod.as<fr_t>(), ctx->sm_count, ctx->stream);
+    if (ce == cudaSuccess) ce = launch_lagrange_scalars(inv.as<fr_t>(), ifact, prod.as<fr_t>(), m, scal.as<fr_t>(), ctx->sm_count, ctx->stream);
+    ctx->launches += 3;
+    if (ce != cudaSuccess) rc = cuda_fail(ctx, ce, "lagrange scalars");
+    if (!rc) rc = fixed_base_points(ctx, scal.as<fr_t>(), m, basis);
+    if (!rc) { ce = cudaStreamSynchronize(ctx->stream); if (ce != cudaSuccess) rc = cuda_fail(ctx, ce, "lagrange basis"); }
+    if (rc) { cudaFree(basis); return rc; }
+    srs->lagrange[m] = basis;
+    return TSGPU_OK;
+}
+
+// commit(interpolant of values on 0..m-1) = sum_j values[j] * [L_j(tau)]_1 : vector_to_polynomial + commit in one MSM
+int tsgpu_kzg_commit_values_dev(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_poly* values, tsgpu_g1* out) {
+    if (!ctx || !srs || !values || !out) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    if (values->n > srs->n) return fail(ctx, TSGPU_E_COMMITMENT, "Polynomial degree exceeds setup size");
+    if (values->n == 0) { G1J id = G1J::identity(); memcpy(out, &id, 96); return TSGPU_OK; }
+    int rc = tsgpu_srs_lagrange_prepare(ctx, srs, values->n);
+    if (rc) return rc;
+    return msm_device(ctx, lagrange_basis(srs, values->n), values->d, values->n, out);
+}
+
+// KZGCommitment::open on the interpolant of `values`: value = P(z) by the barycentric formula, proof = commitment to the
+// quotient through its values Q(j) = (v_j - value) / (j - z).  z must not be one of the nodes 0..m-1 (TSGPU_E_POLYNOMIAL).
+int tsgpu_kzg_open_values_dev(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_poly* values, const tsgpu_fr* z, tsgpu_fr* value, tsgpu_g1* proof) {
+    if (!ctx || !srs || !values || !z || !value || !proof) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    const size_t m = values->n;
+    if (m == 0) { memset(value, 0, 32); G1J id = G1J::identity(); memcpy(proof, &id, 96); return TSGPU_OK; }
+    Fr64 zcan = Fr64::from_raw(z->l).from_mont();
+    if (!zcan.l[1] && !zcan.l[2] && !zcan.l[3] && zcan.l[0] < m) return fail(ctx, TSGPU_E_POLYNOMIAL, "opening point is an interpolation node");
+    int rc = tsgpu_srs_lagrange_prepare(ctx, srs, m);
+    if (rc) return rc;
+    const fr_t* ifact = nullptr;
+    TSG_CUDA(ctx, interp_factorials(ctx, (unsigned)log2_exact(m), &ifact));
+    cudaError_t aerr;
+    const size_t nsp = lag_num_spans(m);
+    fr_t* buf = (fr_t*)arena_get(ctx, tsgpu_ctx::ARENA_QUOT, (2 * m + nsp + 2) * sizeof(fr_t), &aerr);
+    if (!buf) return cuda_fail(ctx, aerr, "cudaMalloc(quotient)");
+    fr_t *q = buf, *inv = buf + m, *spans = inv + m, *nz = spans + nsp, *val = nz + 1;
+    fr_t zf; memcpy(zf.l, z->l, 32);
+    {
+        KernelTimer kt(ctx, "open_bary");
+        TSG_CUDA(ctx, launch_node_inverses(zf, m, inv, spans, nz, ctx->sm_count, ctx->stream));
+        TSG_CUDA(ctx, launch_bary_open(values->d, inv, ifact, m, nz, ctx->partials, ctx->ticket, val, q, ctx->sm_count, ctx->stream));
+        ctx->launches += 4;
+    }
+    TSG_CUDA(ctx, cudaMemcpyAsync(ctx->host_out, val, sizeof(fr_t), cudaMemcpyDeviceToHost, ctx->stream));
+    rc = msm_device(ctx, lagrange_basis(srs, m), q, m, proof);
+    if (rc) return rc;
+    TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(value, ctx->host_out, 32);
     return TSGPU_OK;
 }
 // group addition of two G1Projective values on the CPU (combining per-rank MSM results)

@@ -30,7 +30,10 @@ struct tsgpu_ctx {
     void* arena[ARENA_COUNT] = {nullptr, nullptr, nullptr};
     size_t arena_bytes[ARENA_COUNT] = {0, 0, 0};
     uint64_t msm_points = 0;           // points processed by MSMs (for points/s reporting)
+    uint64_t msm_entries = 0;          // bucket entries (non-zero signed digits) = mixed additions of k_msm_accumulate
+    uint64_t msm_calls = 0;
     bool timing = false;
+    bool eval_basis = true;            // Twist/Shout::prove commit through the Lagrange-basis SRS when it exists (tuning "eval_basis")
     struct Pending { std::string name; cudaEvent_t a, b; };
     std::vector<Pending> pending;
     std::map<std::string, std::pair<double, uint64_t>> timers;   // name -> (total ms, launches)

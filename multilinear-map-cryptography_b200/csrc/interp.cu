@@ -368,6 +368,12 @@ cudaError_t interp_prepare(tsgpu_ctx* ctx, unsigned logn) {
     ctx->launches += p->launches;
     return e;
 }
+cudaError_t interp_factorials(tsgpu_ctx* ctx, unsigned logn, const fr_t** ifact) {
+    InterpPlan* p = interp_plan(ctx);
+    cudaError_t e = p->ensure_factorials(logn > p->log_max ? logn : p->log_max);
+    *ifact = p->ifact;
+    return e;
+}
 cudaError_t interp_run(tsgpu_ctx* ctx, const fr_t* vals, unsigned logn, fr_t* coeffs) {
     InterpPlan* p = interp_plan(ctx);
     p->launches = 0;

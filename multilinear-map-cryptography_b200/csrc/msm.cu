@@ -35,8 +35,10 @@ __device__ __forceinline__ void st_xyzz(g1_xyzz* p, const g1_xyzz& v) {
 __global__ void k_msm_digits(const fr_t* scalars, size_t n, unsigned c, unsigned W, unsigned* dig, unsigned* hist) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const unsigned nb = 1u << (c - 1);
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        fr_t s = ld256_nc(scalars + i).from_mont();
+    for (size_t i0 = (size_t)blockIdx.x * blockDim.x; i0 < n; i0 += stride) {   // block-uniform bound: warps stay converged for match_any
+        const size_t i = i0 + threadIdx.x;
+        const bool live = i < n;
+        fr_t s = live ? ld256_nc(scalars + i).from_mont() : fr_t::zero();
         unsigned carry = 0;
         for (unsigned w = 0; w < W; ++w) {
             unsigned bit = w * c, limb = bit >> 5, off = bit & 31;
@@ -45,8 +47,11 @@ __global__ void k_msm_digits(const fr_t* scalars, size_t n, unsigned c, unsigned
             unsigned d = (unsigned)((two >> off) & ((1u << c) - 1)) + carry;
             unsigned sign = 0;
             if (d > nb) { d = (1u << c) - d; sign = 1; carry = 1; } else carry = 0;
-            dig[(size_t)w * n + i] = d | (sign << 31);
-            if (d) atomicAdd(&hist[(size_t)w * nb + d - 1], 1u);
+            if (live) dig[(size_t)w * n + i] = d | (sign << 31);
+            // one atomic per distinct bucket in the warp: small scalars put most carries of a window into bucket 1
+            const unsigned key = d ? (unsigned)(w * nb + d - 1) : 0xffffffffu;
+            const unsigned peers = __match_any_sync(0xffffffffu, key);
+            if (d && (unsigned)(__ffs(peers) - 1) == (threadIdx.x & 31)) atomicAdd(&hist[key], (unsigned)__popc(peers));
         }
     }
 }
@@ -126,40 +131,119 @@ __global__ void k_msm_scatter(const unsigned* dig, size_t n, unsigned c, unsigne
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const unsigned nb = 1u << (c - 1);
     const size_t total = (size_t)W * n;
-    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
-        unsigned v = dig[t];
+    const unsigned lane = threadIdx.x & 31;
+    for (size_t t0 = (size_t)blockIdx.x * blockDim.x; t0 < total; t0 += stride) {   // block-uniform bound: whole warps stay converged
+        const size_t t = t0 + threadIdx.x;
+        unsigned v = t < total ? dig[t] : 0u;
         unsigned d = v & 0x7fffffffu;
-        if (!d) continue;
         size_t w = t / n, i = t - w * n;
-        size_t b = w * nb + d - 1;
-        unsigned pos = offsets[b] + atomicAdd(&cursor[b], 1u);
-        sorted[pos] = (unsigned)i | (v & 0x80000000u);
+        const unsigned b = d ? (unsigned)(w * nb + d - 1) : 0xffffffffu;
+        const unsigned peers = __match_any_sync(0xffffffffu, b);
+        const unsigned leader = __ffs(peers) - 1;
+        unsigned base = 0;
+        if (d && lane == leader) base = atomicAdd(&cursor[b], (unsigned)__popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (d) sorted[offsets[b] + base + __popc(peers & ((1u << lane) - 1))] = (unsigned)i | (v & 0x80000000u);
     }
 }
 
 // ---------------------------------------------------------------- work items: slices of at most MSM_CHUNK entries
-__global__ void k_msm_item_counts(const unsigned* hist, size_t nbuckets, unsigned* items) {
+__global__ void k_msm_item_counts(const unsigned* hist, size_t nbuckets, unsigned* items, unsigned* max_chunks) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < nbuckets; b += stride)
-        items[b] = (hist[b] + MSM_CHUNK - 1) / MSM_CHUNK;
-}
-__global__ void k_msm_item_fill(const unsigned* items, const unsigned* item_off, size_t nbuckets, unsigned* item_bucket) {
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    unsigned mx = 0;
     for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < nbuckets; b += stride) {
-        unsigned k = items[b], o = item_off[b];
-        for (unsigned j = 0; j < k; ++j) item_bucket[o + j] = (unsigned)b;
+        unsigned k = (hist[b] + MSM_CHUNK - 1) / MSM_CHUNK;
+        items[b] = k;
+        mx = k > mx ? k : mx;
+    }
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((threadIdx.x & 31) == 0 && mx > 1) atomicMax(max_chunks, mx);
+}
+__global__ void __launch_bounds__(256) k_msm_item_fill(const unsigned* items, const unsigned* item_off, const unsigned* hist, size_t nbuckets,
+                                                       unsigned* item_bucket, unsigned* len_hist) {
+    // len_hist[MSM_CHUNK - len] counts work items by length (longest first), privatised in shared memory
+    __shared__ unsigned sh[MSM_CHUNK + 1];
+    for (unsigned i = threadIdx.x; i <= MSM_CHUNK; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const unsigned lane = threadIdx.x & 31;
+    for (size_t b0 = (size_t)blockIdx.x * blockDim.x; b0 < nbuckets; b0 += stride) {
+        const size_t b = b0 + threadIdx.x;
+        unsigned k = 0, o = 0, cnt = 0;
+        if (b < nbuckets) { k = items[b]; o = item_off[b]; cnt = hist[b]; }
+        if (k <= 8) {
+            for (unsigned j = 0; j < k; ++j) {
+                item_bucket[o + j] = (unsigned)b;
+                unsigned len = cnt - j * MSM_CHUNK; if (len > MSM_CHUNK) len = MSM_CHUNK;
+                atomicAdd(&sh[MSM_CHUNK - len], 1u);
+            }
+        }
+        // buckets split into many chunks (equal scalars, carries of small scalars): the whole warp writes their item records
+        unsigned heavy = __ballot_sync(0xffffffffu, k > 8);
+        while (heavy) {
+            const int src = __ffs(heavy) - 1; heavy &= heavy - 1;
+            const unsigned kb = __shfl_sync(0xffffffffu, k, src), ob = __shfl_sync(0xffffffffu, o, src), cb = __shfl_sync(0xffffffffu, cnt, src);
+            const unsigned bb = (unsigned)(b0 + (threadIdx.x & ~31u) + src);
+            for (unsigned j = lane; j < kb; j += 32) {
+                item_bucket[ob + j] = bb;
+                unsigned len = cb - j * MSM_CHUNK; if (len > MSM_CHUNK) len = MSM_CHUNK;
+                atomicAdd(&sh[MSM_CHUNK - len], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (unsigned i = threadIdx.x; i <= MSM_CHUNK; i += blockDim.x) if (sh[i]) atomicAdd(&len_hist[i], sh[i]);
+}
+// exclusive scan of the MSM_CHUNK + 1 length bins (one block)
+__global__ void __launch_bounds__(SCAN_THREADS) k_msm_len_scan(const unsigned* len_hist, unsigned* len_off) {
+    unsigned v0 = 2 * threadIdx.x <= MSM_CHUNK ? len_hist[2 * threadIdx.x] : 0;
+    unsigned v1 = 2 * threadIdx.x + 1 <= MSM_CHUNK ? len_hist[2 * threadIdx.x + 1] : 0;
+    unsigned ex = block_exclusive_scan_u32(v0 + v1, nullptr);
+    if (2 * threadIdx.x <= MSM_CHUNK) len_off[2 * threadIdx.x] = ex;
+    if (2 * threadIdx.x + 1 <= MSM_CHUNK) len_off[2 * threadIdx.x + 1] = ex + v0;
+}
+// order[] = work items sorted by decreasing length, so that the 32 lanes of a warp of k_msm_accumulate run the
+// same number of additions (bucket loads are Poisson distributed: unsorted, a warp waits for its fullest bucket)
+constexpr int ORDER_TILE = 4;   // items per thread per tile
+__global__ void __launch_bounds__(256) k_msm_order(const unsigned* hist, const unsigned* item_off, const unsigned* item_bucket, const unsigned* n_items,
+                                                   const unsigned* len_off, unsigned* len_cursor, unsigned* order) {
+    __shared__ unsigned sh_cnt[MSM_CHUNK + 1], sh_base[MSM_CHUNK + 1];
+    const unsigned M = *n_items;
+    const unsigned tile = blockDim.x * ORDER_TILE;
+    for (unsigned t0 = blockIdx.x * tile; t0 < M; t0 += gridDim.x * tile) {
+        for (unsigned i = threadIdx.x; i <= MSM_CHUNK; i += blockDim.x) sh_cnt[i] = 0;
+        __syncthreads();
+        unsigned key[ORDER_TILE], rank[ORDER_TILE];
+#pragma unroll
+        for (int q = 0; q < ORDER_TILE; ++q) {
+            unsigned it = t0 + q * blockDim.x + threadIdx.x;
+            key[q] = 0xffffffffu;
+            if (it < M) {
+                unsigned b = item_bucket[it];
+                unsigned len = hist[b] - (it - item_off[b]) * MSM_CHUNK; if (len > MSM_CHUNK) len = MSM_CHUNK;
+                key[q] = MSM_CHUNK - len;
+                rank[q] = atomicAdd(&sh_cnt[key[q]], 1u);
+            }
+        }
+        __syncthreads();
+        for (unsigned i = threadIdx.x; i <= MSM_CHUNK; i += blockDim.x) if (sh_cnt[i]) sh_base[i] = len_off[i] + atomicAdd(&len_cursor[i], sh_cnt[i]);
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < ORDER_TILE; ++q) if (key[q] != 0xffffffffu) order[sh_base[key[q]] + rank[q]] = t0 + q * blockDim.x + threadIdx.x;
+        __syncthreads();
     }
 }
 
 // ---------------------------------------------------------------- 3b. bucket accumulation (the hot kernel)
 __global__ void __launch_bounds__(MSM_ACC_THREADS) k_msm_accumulate(const g1_affine* bases, const unsigned* sorted, const unsigned* hist, const unsigned* offsets,
                                                                   const unsigned* item_off, const unsigned* item_bucket, const unsigned* n_items,
-                                                                  g1_xyzz* partial) {
+                                                                  const unsigned* order, g1_xyzz* partial) {
     const unsigned M = *n_items;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t it = (size_t)blockIdx.x * blockDim.x + threadIdx.x; it < M; it += stride) {
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < M; j += stride) {
+        const unsigned it = order[j];
         unsigned b = item_bucket[it];
-        unsigned k = (unsigned)it - item_off[b];
+        unsigned k = it - item_off[b];
         unsigned cnt = hist[b], base = offsets[b];
         unsigned lo = k * MSM_CHUNK, hi = lo + MSM_CHUNK < cnt ? lo + MSM_CHUNK : cnt;
         g1_xyzz acc = g1_xyzz::identity();
@@ -169,6 +253,22 @@ __global__ void __launch_bounds__(MSM_ACC_THREADS) k_msm_accumulate(const g1_aff
             acc = acc.add_affine(pt, (v >> 31) != 0);
         }
         st_xyzz(partial + it, acc);
+    }
+}
+
+// ---------------------------------------------------------------- 3c. buckets split into several chunks: pairwise tree over their partial sums
+// round with stride s: chunk q of a bucket (q a multiple of 2s) absorbs chunk q + s; after ceil(log2 k) rounds chunk 0 holds the bucket sum
+__global__ void __launch_bounds__(128) k_msm_merge_round(g1_xyzz* partial, const unsigned* items, const unsigned* item_off, const unsigned* item_bucket,
+                                                         const unsigned* n_items, unsigned s) {
+    if (s >= n_items[2]) return;               // n_items[2] = largest chunk count of any bucket
+    const unsigned M = n_items[0];
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t it = (size_t)blockIdx.x * blockDim.x + threadIdx.x; it < M; it += stride) {
+        const unsigned b = item_bucket[it];
+        const unsigned k = items[b];
+        if (k <= s) continue;
+        const unsigned q = (unsigned)it - item_off[b];
+        if ((q & (2 * s - 1)) == 0 && q + s < k) st_xyzz(partial + it, ld_xyzz(partial + it).add(ld_xyzz(partial + it + s)));
     }
 }
 
@@ -187,8 +287,7 @@ __global__ void __launch_bounds__(128) k_msm_bucket_reduce(const g1_xyzz* partia
         g1_xyzz running = g1_xyzz::identity(), acc = g1_xyzz::identity();
         for (unsigned j = span; j-- > 0;) {
             size_t b = w * nb + lo + j;
-            unsigned k = items[b], o = item_off[b];
-            for (unsigned q = 0; q < k; ++q) running = running.add(ld_xyzz(partial + o + q));
+            if (items[b]) running = running.add(ld_xyzz(partial + item_off[b]));
             acc = acc.add(running);
         }
         if (lo) acc = acc.add(running.mul_small(lo));
@@ -317,6 +416,8 @@ size_t msm_scratch_bytes(size_t n, unsigned c, MsmLayout* L) {
     L->item_off = take(nbuckets * 4);
     L->item_bucket = take(max_items * 4);
     L->n_items = take(256);
+    L->order = take(max_items * 4);
+    L->len_hist = take(3 * (MSM_CHUNK + 1) * 4);   // length histogram, offsets, cursors
     L->scan_tmp = take((nbuckets / 1024 + 64) * 4);
     L->partial = take(max_items * sizeof(g1_xyzz));
     L->blockres = take((size_t)W * L->blocks_per_window * sizeof(g1_xyzz));
@@ -338,19 +439,29 @@ cudaError_t msm_run(const g1_affine* bases, const fr_t* scalars, size_t n, const
     // hist and cursor are adjacent-independent regions: clear both
     if ((e = cudaMemsetAsync(hist, 0, L.nbuckets * 4, s))) return e;
     if ((e = cudaMemsetAsync(cursor, 0, L.nbuckets * 4, s))) return e;
+    unsigned* order = (unsigned*)(scratch + L.order);
+    unsigned* len_hist = (unsigned*)(scratch + L.len_hist); unsigned* len_off = len_hist + (MSM_CHUNK + 1); unsigned* len_cursor = len_off + (MSM_CHUNK + 1);
+    if ((e = cudaMemsetAsync(len_hist, 0, 3 * (MSM_CHUNK + 1) * 4, s))) return e;
+    if ((e = cudaMemsetAsync(n_items, 0, 256, s))) return e;
     const size_t cap = (size_t)sm_count * 8;
     k_msm_digits<<<gridfor(n, 256, cap), 256, 0, s>>>(scalars, n, L.c, L.W, dig, hist);
-    exclusive_scan_u32(hist, offsets, L.nbuckets, (unsigned*)(scratch + L.scan_tmp), nullptr, s);
+    exclusive_scan_u32(hist, offsets, L.nbuckets, (unsigned*)(scratch + L.scan_tmp), n_items + 1, s);   // n_items[1] = bucket entries (non-zero digits)
     k_msm_scatter<<<gridfor((size_t)L.W * n, 256, cap), 256, 0, s>>>(dig, n, L.c, L.W, offsets, cursor, sorted);
-    k_msm_item_counts<<<gridfor(L.nbuckets, 256, cap), 256, 0, s>>>(hist, L.nbuckets, items);
+    k_msm_item_counts<<<gridfor(L.nbuckets, 256, cap), 256, 0, s>>>(hist, L.nbuckets, items, n_items + 2);
     exclusive_scan_u32(items, item_off, L.nbuckets, (unsigned*)(scratch + L.scan_tmp), n_items, s);
-    k_msm_item_fill<<<gridfor(L.nbuckets, 256, cap), 256, 0, s>>>(items, item_off, L.nbuckets, item_bucket);
+    k_msm_item_fill<<<gridfor(L.nbuckets, 256, cap), 256, 0, s>>>(items, item_off, hist, L.nbuckets, item_bucket, len_hist);
+    k_msm_len_scan<<<1, SCAN_THREADS, 0, s>>>(len_hist, len_off);
+    k_msm_order<<<gridfor(L.max_items, 256 * ORDER_TILE, cap), 256, 0, s>>>(hist, item_off, item_bucket, n_items, len_off, len_cursor, order);
     if (acc_events) cudaEventRecord(acc_events[0], s);
-    k_msm_accumulate<<<gridfor(L.max_items, MSM_ACC_THREADS, (size_t)sm_count * 16), MSM_ACC_THREADS, 0, s>>>(bases, sorted, hist, offsets, item_off, item_bucket, n_items, partial);
+    k_msm_accumulate<<<gridfor(L.max_items, MSM_ACC_THREADS, (size_t)sm_count * 16), MSM_ACC_THREADS, 0, s>>>(bases, sorted, hist, offsets, item_off, item_bucket, n_items, order, partial);
     if (acc_events) cudaEventRecord(acc_events[1], s);
+    unsigned rounds = 0;
+    for (size_t st = 1; st * MSM_CHUNK < n; st <<= 1, ++rounds)   // a bucket holds at most n entries = ceil(n / MSM_CHUNK) chunks; idle rounds return at once
+        k_msm_merge_round<<<gridfor(L.max_items, 128, cap), 128, 0, s>>>(partial, items, item_off, item_bucket, n_items, (unsigned)st);
+    if (launches) *launches += rounds;
     k_msm_bucket_reduce<<<gridfor((size_t)L.W * L.blocks_per_window, 128, cap), 128, 0, s>>>(partial, items, item_off, L.c, L.W, blockres);
     k_msm_window_sum<<<L.W, MSM_SUM_THREADS, 0, s>>>(blockres, L.blocks_per_window, wout);
-    if (launches) *launches += 13;
+    if (launches) *launches += 15;
     return cudaGetLastError();
 }
 

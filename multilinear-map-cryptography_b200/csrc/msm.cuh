@@ -5,7 +5,7 @@
 
 namespace tsg {
 
-constexpr unsigned MSM_CHUNK = 256;       // max entries one work item adds into its accumulator
+constexpr unsigned MSM_CHUNK = 64;        // max entries one work item adds into its accumulator (bounds the serial chain of one thread)
 constexpr int MSM_ACC_THREADS = 128;
 constexpr unsigned MSM_RED_SPAN = 32;     // buckets per thread in the window reduction
 constexpr int MSM_SUM_THREADS = 128;
@@ -15,7 +15,7 @@ constexpr size_t MSM_INV_SPAN = 32;       // points per batch inversion
 struct MsmLayout {
     unsigned c, W, blocks_per_window;
     size_t nbuckets, max_items;
-    size_t dig, sorted, hist, offsets, cursor, items, item_off, item_bucket, n_items, scan_tmp, partial, blockres, window_out;
+    size_t dig, sorted, hist, offsets, cursor, items, item_off, item_bucket, n_items, order, len_hist, scan_tmp, partial, blockres, window_out;
 };
 
 unsigned msm_window_bits(size_t n);

@@ -48,13 +48,26 @@ tsgpu_fr abi_of(const fr_t& x) { tsgpu_fr r; memcpy(r.l, x.l, 32); return r; }
 int prove_two_vectors(tsgpu_ctx* ctx, const tsgpu_params* params, tsgpu_poly* pa, tsgpu_poly* pb, const char* label_a, const char* label_b,
                       unsigned rounds, tsgpu_proof** out) {
     int rc;
-    if ((rc = tsgpu_poly_interpolate_iota(ctx, pa))) return rc;            // vector_to_polynomial
-    if ((rc = tsgpu_poly_interpolate_iota(ctx, pb))) return rc;
+    // Evaluation-basis path (csrc/lagrange.cu): with [L_j(tau)]_1 available for both vector lengths the commitment is one MSM
+    // over the raw values and vector_to_polynomial is never materialised; same group elements, same bytes.  Otherwise (SRS
+    // uploaded without its trapdoor, or the path switched off) interpolate and commit coefficients as the reference does.
+    bool eval_basis = ctx->eval_basis && tsgpu_srs_can_lagrange(params->srs) &&
+                      tsgpu_srs_lagrange_prepare(ctx, params->srs, tsgpu_poly_len(pa)) == TSGPU_OK &&
+                      tsgpu_srs_lagrange_prepare(ctx, params->srs, tsgpu_poly_len(pb)) == TSGPU_OK;
+    if (!eval_basis) {
+        if ((rc = tsgpu_poly_interpolate_iota(ctx, pa))) return rc;            // vector_to_polynomial
+        if ((rc = tsgpu_poly_interpolate_iota(ctx, pb))) return rc;
+    }
     tsgpu_proof* pr = new (std::nothrow) tsgpu_proof;
     if (!pr) return fail(ctx, TSGPU_E_PROOF_GENERATION, "out of host memory");
     memset(&pr->opening_point, 0, 32);
-    if ((rc = tsgpu_kzg_commit_dev(ctx, params->srs, pa, &pr->commitments[0]))) { delete pr; return rc; }
-    if ((rc = tsgpu_kzg_commit_dev(ctx, params->srs, pb, &pr->commitments[1]))) { delete pr; return rc; }
+    if (eval_basis) {
+        if ((rc = tsgpu_kzg_commit_values_dev(ctx, params->srs, pa, &pr->commitments[0]))) { delete pr; return rc; }
+        if ((rc = tsgpu_kzg_commit_values_dev(ctx, params->srs, pb, &pr->commitments[1]))) { delete pr; return rc; }
+    } else {
+        if ((rc = tsgpu_kzg_commit_dev(ctx, params->srs, pa, &pr->commitments[0]))) { delete pr; return rc; }
+        if ((rc = tsgpu_kzg_commit_dev(ctx, params->srs, pb, &pr->commitments[1]))) { delete pr; return rc; }
+    }
     Transcript tr(params->fiat_shamir_seed);
     tsgpu_fr h;
     tsgpu_g1_hash(&pr->commitments[0], &h); tr.append_field_element(label_a, fr_of(h));
@@ -74,10 +87,20 @@ int prove_two_vectors(tsgpu_ctx* ctx, const tsgpu_params* params, tsgpu_poly* pa
         tsgpu_fr z = abi_of(ch[0]);
         pr->opening_point = z;
         tsgpu_fr v; tsgpu_g1 pi;
-        if ((rc = tsgpu_kzg_open_dev(ctx, params->srs, pa, &z, &v, &pi))) { delete pr; return rc; }
-        pr->opening_proofs.push_back(pi); pr->final_evaluations.push_back(v);
-        if ((rc = tsgpu_kzg_open_dev(ctx, params->srs, pb, &z, &v, &pi))) { delete pr; return rc; }
-        pr->opening_proofs.push_back(pi); pr->final_evaluations.push_back(v);
+        if (eval_basis) {
+            // the barycentric opening needs z outside the nodes 0..n-1 (a 2^-230 event): otherwise finish on coefficients
+            Fr64 zc = Fr64::from_raw(z.l).from_mont();
+            size_t nmax = tsgpu_poly_len(pa) > tsgpu_poly_len(pb) ? tsgpu_poly_len(pa) : tsgpu_poly_len(pb);
+            if (!zc.l[1] && !zc.l[2] && !zc.l[3] && zc.l[0] < nmax) {
+                if ((rc = tsgpu_poly_interpolate_iota(ctx, pa)) || (rc = tsgpu_poly_interpolate_iota(ctx, pb))) { delete pr; return rc; }
+                eval_basis = false;
+            }
+        }
+        for (tsgpu_poly* p : {pa, pb}) {
+            rc = eval_basis ? tsgpu_kzg_open_values_dev(ctx, params->srs, p, &z, &v, &pi) : tsgpu_kzg_open_dev(ctx, params->srs, p, &z, &v, &pi);
+            if (rc) { delete pr; return rc; }
+            pr->opening_proofs.push_back(pi); pr->final_evaluations.push_back(v);
+        }
     }
     *out = pr;
     return TSGPU_OK;
@@ -107,6 +130,7 @@ int tsgpu_setup_params(tsgpu_ctx* ctx, size_t log_size, tsgpu_params** out) {
     p->vk.g2_tau = p->vk.g2_generator.mul(Fr64::from_raw(p->tau.l));              // utils.rs:98
     rng.fill_bytes(p->fiat_shamir_seed, 32);                               // utils.rs:101-102
     rc = tsgpu_interpolate_prepare(ctx, (unsigned)(log_size + 2));
+    if (!rc && ctx->eval_basis) rc = tsgpu_srs_lagrange_prepare(ctx, p->srs, p->max_operations);   // other lengths are built on first use
     if (rc) { tsgpu_srs_free(ctx, p->srs); delete p; return rc; }
     *out = p;
     return TSGPU_OK;
