@@ -173,6 +173,16 @@ int tsgpu_srs_lagrange_prepare(tsgpu_ctx* ctx, const tsgpu_srs* srs, size_t m);
 int tsgpu_kzg_commit_values_dev(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_poly* values, tsgpu_g1* out);
 int tsgpu_kzg_open_values_dev(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_poly* values, const tsgpu_fr* z,
                               tsgpu_fr* value, tsgpu_g1* proof);
+/* ---- batched forms: `count` (<= 4) commitments / openings in ONE MSM pass.  Twist::prove and Shout::prove commit to two
+ * vectors and open both at the same point (src/twist.rs:151-160,226-243): the bucket sets of the MSMs are laid side by
+ * side so that sorting, accumulation, chunk merge and window reduction run once over the union.  Results are the same
+ * group / field elements as `count` separate calls. */
+int tsgpu_kzg_commit_batch_dev(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_poly* const* polynomials, size_t count, tsgpu_g1* outs);
+int tsgpu_kzg_open_batch_dev(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_poly* const* polynomials, size_t count, const tsgpu_fr* z,
+                             tsgpu_fr* values, tsgpu_g1* proofs);
+int tsgpu_kzg_commit_values_batch_dev(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_poly* const* values, size_t count, tsgpu_g1* outs);
+int tsgpu_kzg_open_values_batch_dev(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_poly* const* values, size_t count, const tsgpu_fr* z,
+                                    tsgpu_fr* out_values, tsgpu_g1* proofs);
 /* plain G1 MSM over caller-supplied affine bases: sum_i scalars[i] * bases[i] */
 int tsgpu_msm_g1(tsgpu_ctx* ctx, const tsgpu_g1a* bases, const tsgpu_fr* scalars, size_t n, tsgpu_g1* out);
 /* CPU helpers on single points: KZGCommitmentValue::hash (commitments.rs:73-84), ark-serialize compressed bytes

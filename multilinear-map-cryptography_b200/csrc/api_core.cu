@@ -1,6 +1,7 @@
 // api_core.cu - C ABI (include/tsgpu.h): context, MLE tables, evaluate / partial evaluate, sum-check rounds.
 #include <cstdio>
 #include <cstring>
+#include <set>
 #include <new>
 #include "context.cuh"
 #include "mle.cuh"
@@ -23,11 +24,13 @@ int cuda_fail(tsgpu_ctx* ctx, cudaError_t e, const char* what) {
 }
 
 void timers_collect(tsgpu_ctx* ctx) {
+    std::set<cudaEvent_t> events;   // consecutive phases share their boundary event: destroy each once, after all pairs are read
     for (auto& p : ctx->pending) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { auto& t = ctx->timers[p.name]; t.first += ms; t.second += 1; }
-        cudaEventDestroy(p.a); cudaEventDestroy(p.b);
+        events.insert(p.a); events.insert(p.b);
     }
+    for (cudaEvent_t e : events) cudaEventDestroy(e);
     ctx->pending.clear();
     cudaGetLastError();
 }
@@ -159,6 +162,7 @@ int tsgpu_set_tuning(tsgpu_ctx* ctx, const char* key, long value) {
         return TSGPU_OK;
     }
     if (!strcmp(key, "kernel_timing")) { ctx->timing = value != 0; return TSGPU_OK; }
+    if (!strcmp(key, "msm_tables")) { ctx->msm_tables = value != 0; return TSGPU_OK; }   // 0: per-window bucket sets on the plain SRS points
     if (!strcmp(key, "eval_basis")) { ctx->eval_basis = value != 0; return TSGPU_OK; }   // 0: Twist/Shout::prove interpolate and commit coefficients
     return fail(ctx, TSGPU_E_INVALID_PARAMETERS, std::string("unknown tuning key ") + key);
 }

@@ -25,7 +25,13 @@ struct tsgpu_srs {
     bool has_tau = false;
     tsgpu_fr tau;
     std::map<size_t, g1_affine*> lagrange;
+    // precomputed window tables (msm.cu): table[w * n + i] = 2^(c w) * point_i, so that all digit positions of a scalar feed
+    // ONE bucket set: fewer, wider windows (c = 20 at 2^20 points: 13 additions per point instead of 16) and a single reduction
+    g1_affine* table = nullptr; unsigned table_c = 0;
+    std::map<size_t, std::pair<g1_affine*, unsigned>> lagrange_table;
 };
+// a base array the MSM can run on: plain points and, optionally, their window tables
+struct MsmBasis { const g1_affine* pts; size_t n; const g1_affine* table; unsigned table_c; };
 struct tsgpu_poly {
     fr_t* d = nullptr;        // n coefficients, low -> high, natural order
     size_t n = 0;
@@ -47,36 +53,77 @@ G1J combine_windows(const g1_jac* win, unsigned W, unsigned c) {
     return acc;
 }
 
-// device MSM over `n` (bases, scalars) already resident; result to host as Jacobian
-int msm_device(tsgpu_ctx* ctx, const g1_affine* bases, const fr_t* scalars, size_t n, tsgpu_g1* out) {
-    if (n == 0) { G1J id = G1J::identity(); memcpy(out, &id, 96); return TSGPU_OK; }
+// K independent device MSMs in one pass (bases and scalars resident); results to the host as Jacobian points.
+// Mode: precomputed tables (one shared bucket set per job) when every job has a table of the same window width and uses at
+// least a quarter of it; otherwise per-window bucket sets on the plain points.
+int msm_device_batch(tsgpu_ctx* ctx, int K, const MsmBasis* basis, const fr_t* const* scalars, const size_t* n, tsgpu_g1* out) {
+    size_t nmax = 0;
+    for (int k = 0; k < K; ++k) nmax = n[k] > nmax ? n[k] : nmax;
+    if (nmax == 0) { G1J id = G1J::identity(); for (int k = 0; k < K; ++k) memcpy(&out[k], &id, 96); return TSGPU_OK; }
+    bool shared = ctx->msm_tables;
+    for (int k = 0; k < K && shared; ++k)
+        shared = basis[k].table && basis[k].table_c == basis[0].table_c && n[k] * 4 >= basis[k].n && (255 + basis[k].table_c - 1) / basis[k].table_c * basis[k].n < ((size_t)1 << 31);
+    const unsigned c = shared ? basis[0].table_c : msm_window_bits(nmax);
     MsmLayout L;
-    size_t bytes = msm_scratch_bytes(n, msm_window_bits(n), &L);
+    size_t bytes = msm_scratch_bytes(nmax, K, c, shared, &L);
     cudaError_t aerr;
     unsigned char* scratch_p = (unsigned char*)arena_get(ctx, tsgpu_ctx::ARENA_MSM, bytes, &aerr);
     if (!scratch_p) return cuda_fail(ctx, aerr, "cudaMalloc(msm scratch)");
+    MsmJob jobs[MSM_MAX_BATCH];
+    for (int k = 0; k < K; ++k) jobs[k] = MsmJob{shared ? basis[k].table : basis[k].pts, basis[k].n, scalars[k], n[k]};
     unsigned launches = 0;
-    cudaEvent_t ev[2] = {nullptr, nullptr};
-    if (ctx->timing) { cudaEventCreate(&ev[0]); cudaEventCreate(&ev[1]); }
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (ctx->timing) for (auto& x : ev) cudaEventCreate(&x);
     {
         KernelTimer kt(ctx, "msm_total");
-        TSG_CUDA(ctx, msm_run(bases, scalars, n, L, scratch_p, ctx->sm_count, ctx->stream, &launches, ctx->timing ? ev : nullptr));
+        TSG_CUDA(ctx, msm_run(jobs, K, L, scratch_p, ctx->sm_count, ctx->stream, &launches, ctx->timing ? ev : nullptr));
     }
-    if (ctx->timing) ctx->pending.push_back({"msm_accumulate", ev[0], ev[1]});
-    ctx->msm_points += n;
+    if (ctx->timing) {
+        // four phases share five events (timers_collect destroys each event once)
+        static const char* names[4] = {"msm_sort", "msm_accumulate", "msm_merge", "msm_reduce"};
+        for (int k = 0; k < 4; ++k) ctx->pending.push_back({names[k], ev[k], ev[k + 1]});
+    }
+    for (int k = 0; k < K; ++k) ctx->msm_points += n[k];
     ctx->launches += launches;
-    std::vector<g1_jac> win(L.W);
+    std::vector<g1_jac> win(L.sets);
     unsigned counts[2] = {0, 0};   // work items, bucket entries
-    TSG_CUDA(ctx, cudaMemcpyAsync(win.data(), scratch_p + L.window_out, L.W * sizeof(g1_jac), cudaMemcpyDeviceToHost, ctx->stream));
+    TSG_CUDA(ctx, cudaMemcpyAsync(win.data(), scratch_p + L.window_out, L.sets * sizeof(g1_jac), cudaMemcpyDeviceToHost, ctx->stream));
     TSG_CUDA(ctx, cudaMemcpyAsync(counts, scratch_p + L.n_items, sizeof(counts), cudaMemcpyDeviceToHost, ctx->stream));
     TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->msm_entries += counts[1];
     ctx->msm_calls += 1;
     timers_collect(ctx);
-    G1J r = combine_windows(win.data(), L.W, L.c);
-    memcpy(out, &r, 96);
+    const unsigned per_job = L.sets / L.K;
+    for (int k = 0; k < K; ++k) {
+        G1J r = combine_windows(win.data() + (size_t)k * per_job, per_job, L.c);   // one set per job in table mode: nothing to combine
+        memcpy(&out[k], &r, 96);
+    }
     return TSGPU_OK;
 }
+int msm_device(tsgpu_ctx* ctx, const MsmBasis& basis, const fr_t* scalars, size_t n, tsgpu_g1* out) {
+    return msm_device_batch(ctx, 1, &basis, &scalars, &n, out);
+}
+
+// window tables of a base array (device), allocated here; *table = nullptr when the mode is switched off
+int build_tables(tsgpu_ctx* ctx, const g1_affine* pts, size_t n, g1_affine** table, unsigned* table_c) {
+    *table = nullptr; *table_c = 0;
+    if (!ctx->msm_tables || n == 0) return TSGPU_OK;
+    const unsigned c = msm_table_window_bits(n), W = (255 + c - 1) / c;
+    if ((size_t)W * n >= ((size_t)1 << 31)) return TSGPU_OK;   // entry indices are 31 bits: stay on per-window buckets
+    g1_affine* t = nullptr;
+    cudaError_t e = cudaMalloc((void**)&t, (size_t)W * n * sizeof(g1_affine));
+    if (e != cudaSuccess) { cudaGetLastError(); return TSGPU_OK; }   // not enough memory for the tables: per-window buckets still work
+    TempBuf cur;
+    unsigned launches = 0;
+    e = cur.alloc(n * sizeof(g1_xyzz), ctx->stream);
+    if (e == cudaSuccess) e = msm_build_table(pts, n, c, t, cur.as<g1_xyzz>(), ctx->sm_count, ctx->stream, &launches);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    ctx->launches += launches;
+    if (e != cudaSuccess) { cudaFree(t); return cuda_fail(ctx, e, "msm window tables"); }
+    *table = t; *table_c = c;
+    return TSGPU_OK;
+}
+MsmBasis srs_basis(const tsgpu_srs* srs) { return MsmBasis{srs->d, srs->n, srs->table, srs->table_c}; }
 
 // byte-window table of the generator for k_fixed_base_mul: table[w * 255 + d - 1] = d * 256^w * G (affine); built once per process
 const std::vector<g1_affine>& generator_table() {
@@ -145,6 +192,8 @@ int tsgpu_srs_upload(tsgpu_ctx* ctx, const tsgpu_g1* powers, size_t n, tsgpu_srs
         ctx->launches += 2;
     }
     TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int trc = build_tables(ctx, srs->d, n, &srs->table, &srs->table_c);
+    if (trc) { tsgpu_srs_free(ctx, srs); return trc; }
     *out = srs;
     return TSGPU_OK;
 }
@@ -168,6 +217,8 @@ void tsgpu_srs_free(tsgpu_ctx* ctx, tsgpu_srs* srs) {
     if (!srs) return;
     if (srs->d) cudaFree(srs->d);
     for (auto& kv : srs->lagrange) cudaFree(kv.second);
+    for (auto& kv : srs->lagrange_table) cudaFree(kv.second.first);
+    if (srs->table) cudaFree(srs->table);
     delete srs;
 }
 
@@ -284,13 +335,28 @@ int tsgpu_msm_g1(tsgpu_ctx* ctx, const tsgpu_g1a* bases, const tsgpu_fr* scalars
         TSG_CUDA(ctx, cudaMemcpyAsync(b.p, bases, n * sizeof(g1_affine), cudaMemcpyHostToDevice, ctx->stream));
         TSG_CUDA(ctx, cudaMemcpyAsync(s.p, scalars, n * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
     }
-    return msm_device(ctx, b.as<g1_affine>(), s.as<fr_t>(), n, out);
+    return msm_device(ctx, MsmBasis{b.as<g1_affine>(), n, nullptr, 0}, s.as<fr_t>(), n, out);
 }
 
+// `count` commitments over the same SRS in one MSM pass (the two commitments of a Twist / Shout proof)
+int tsgpu_kzg_commit_batch_dev(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_poly* const* polys, size_t count, tsgpu_g1* outs) {
+    if (!ctx || !srs || (count && (!polys || !outs))) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    for (size_t i = 0; i < count; ++i) {
+        if (!polys[i]) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+        if (polys[i]->n > srs->n) return fail(ctx, TSGPU_E_COMMITMENT, "Polynomial degree exceeds setup size");   // commitments.rs:166-170
+    }
+    for (size_t i0 = 0; i0 < count; i0 += MSM_MAX_BATCH) {
+        const int K = (int)(count - i0 < (size_t)MSM_MAX_BATCH ? count - i0 : MSM_MAX_BATCH);
+        MsmBasis basis[MSM_MAX_BATCH]; const fr_t* sc[MSM_MAX_BATCH]; size_t n[MSM_MAX_BATCH];
+        for (int k = 0; k < K; ++k) { basis[k] = srs_basis(srs); sc[k] = polys[i0 + k]->d; n[k] = polys[i0 + k]->n; }
+        int rc = msm_device_batch(ctx, K, basis, sc, n, outs + i0);
+        if (rc) return rc;
+    }
+    return TSGPU_OK;
+}
 int tsgpu_kzg_commit_dev(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_poly* poly, tsgpu_g1* out) {
-    if (!ctx || !srs || !poly || !out) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
-    if (poly->n > srs->n) return fail(ctx, TSGPU_E_COMMITMENT, "Polynomial degree exceeds setup size");   // commitments.rs:166-170
-    return msm_device(ctx, srs->d, poly->d, poly->n, out);
+    if (!poly || !out) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    return tsgpu_kzg_commit_batch_dev(ctx, srs, &poly, 1, out);
 }
 
 int tsgpu_kzg_commit(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_fr* polynomial, size_t n, tsgpu_g1* out) {
@@ -299,49 +365,64 @@ int tsgpu_kzg_commit(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_fr* polyn
     TempBuf s;
     TSG_CUDA(ctx, s.alloc(n * sizeof(fr_t), ctx->stream));
     if (n) TSG_CUDA(ctx, cudaMemcpyAsync(s.p, polynomial, n * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
-    return msm_device(ctx, srs->d, s.as<fr_t>(), n, out);
+    return msm_device(ctx, srs_basis(srs), s.as<fr_t>(), n, out);
 }
 
 // value = P(z), proof = commit((P - value) / (x - z))   (commitments.rs:182-199)
-int tsgpu_kzg_open_dev(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_poly* poly, const tsgpu_fr* z, tsgpu_fr* value, tsgpu_g1* proof) {
-    if (!ctx || !srs || !poly || !z || !value || !proof) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
-    const size_t n = poly->n;
-    if (n == 0) {   // empty polynomial: value 0, empty quotient (commitments.rs:306-308, 322-324)
-        memset(value, 0, 32);
-        G1J id = G1J::identity(); memcpy(proof, &id, 96);
-        return TSGPU_OK;
+// `count` (<= MSM_MAX_BATCH) openings at the same point: the value / quotient scans run back to back, the quotient commitments as one MSM pass
+int tsgpu_kzg_open_batch_dev(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_poly* const* polys, size_t count, const tsgpu_fr* z, tsgpu_fr* values, tsgpu_g1* proofs) {
+    if (!ctx || !srs || !z || (count && (!polys || !values || !proofs))) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    if (count > (size_t)MSM_MAX_BATCH) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "too many openings in one batch");
+    size_t total = 0;
+    for (size_t i = 0; i < count; ++i) {
+        if (!polys[i]) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+        if (polys[i]->n && polys[i]->n - 1 > srs->n) return fail(ctx, TSGPU_E_COMMITMENT, "Polynomial degree exceeds setup size");
+        total += polys[i]->n;
     }
-    if (n - 1 > srs->n) return fail(ctx, TSGPU_E_COMMITMENT, "Polynomial degree exceeds setup size");
     // scan weights on the host: pw[s] = z^(SPAN 2^s), W = z^(THREADS SPAN)
     Fr64 zz = Fr64::from_raw(z->l);
     Fr64 w = zz;
     for (size_t k = 1; k < POLY_SPAN; k <<= 1) w = w.sqr();   // z^SPAN (SPAN is a power of two)
     fr_t pw[POLY_PW + 1];
     for (int s = 0; s <= POLY_PW; ++s) { memcpy(pw[s].l, w.l, 32); w = w.sqr(); }
-    const size_t nblocks = poly_num_blocks(n);
     TempBuf dpw, totals, carry, val;
     TSG_CUDA(ctx, dpw.alloc(sizeof(pw), ctx->stream));
-    TSG_CUDA(ctx, totals.alloc(nblocks * sizeof(fr_t), ctx->stream));
-    TSG_CUDA(ctx, carry.alloc(nblocks * sizeof(fr_t), ctx->stream));
-    TSG_CUDA(ctx, val.alloc(64, ctx->stream));
+    TSG_CUDA(ctx, val.alloc(MSM_MAX_BATCH * sizeof(fr_t), ctx->stream));
     cudaError_t aerr;
-    fr_t* q_p = (fr_t*)arena_get(ctx, tsgpu_ctx::ARENA_QUOT, n * sizeof(fr_t), &aerr);
-    if (!q_p) return cuda_fail(ctx, aerr, "cudaMalloc(quotient)");
+    fr_t* q_all = (fr_t*)arena_get(ctx, tsgpu_ctx::ARENA_QUOT, (total + 1) * sizeof(fr_t), &aerr);
+    if (!q_all) return cuda_fail(ctx, aerr, "cudaMalloc(quotient)");
     TSG_CUDA(ctx, cudaMemcpyAsync(dpw.p, pw, sizeof(pw), cudaMemcpyHostToDevice, ctx->stream));
+    TSG_CUDA(ctx, cudaMemsetAsync(val.p, 0, MSM_MAX_BATCH * sizeof(fr_t), ctx->stream));   // empty polynomial: value 0, empty quotient (commitments.rs:306-308, 322-324)
     fr_t zf; memcpy(zf.l, z->l, 32);
-    unsigned launches = 0;
-    {
-        KernelTimer kt_open(ctx, "open_scan");
-        TSG_CUDA(ctx, poly_open_launch(poly->d, n, zf, dpw.as<fr_t>(), pw[POLY_PW], totals.as<fr_t>(), carry.as<fr_t>(), q_p, val.as<fr_t>(),
-                                       ctx->stream, &launches));
+    MsmBasis basis[MSM_MAX_BATCH]; const fr_t* sc[MSM_MAX_BATCH]; size_t qn[MSM_MAX_BATCH];
+    size_t off = 0;
+    for (size_t i = 0; i < count; ++i) {
+        const size_t n = polys[i]->n;
+        basis[i] = srs_basis(srs); sc[i] = q_all + off; qn[i] = n ? n - 1 : 0;
+        if (n) {
+            const size_t nblocks = poly_num_blocks(n);
+            TSG_CUDA(ctx, totals.alloc(nblocks * sizeof(fr_t), ctx->stream));
+            TSG_CUDA(ctx, carry.alloc(nblocks * sizeof(fr_t), ctx->stream));
+            unsigned launches = 0;
+            KernelTimer kt_open(ctx, "open_scan");
+            TSG_CUDA(ctx, poly_open_launch(polys[i]->d, n, zf, dpw.as<fr_t>(), pw[POLY_PW], totals.as<fr_t>(), carry.as<fr_t>(), q_all + off, val.as<fr_t>() + i,
+                                           ctx->stream, &launches));
+            ctx->launches += launches;
+            cudaFreeAsync(totals.p, ctx->stream); totals.p = nullptr;
+            cudaFreeAsync(carry.p, ctx->stream); carry.p = nullptr;
+        }
+        off += n;
     }
-    ctx->launches += launches;
-    TSG_CUDA(ctx, cudaMemcpyAsync(ctx->host_out, val.p, sizeof(fr_t), cudaMemcpyDeviceToHost, ctx->stream));
-    int rc = msm_device(ctx, srs->d, q_p, n - 1, proof);
+    TSG_CUDA(ctx, cudaMemcpyAsync(ctx->host_out, val.p, count * sizeof(fr_t), cudaMemcpyDeviceToHost, ctx->stream));
+    int rc = msm_device_batch(ctx, (int)count, basis, sc, qn, proofs);
     if (rc) return rc;
     TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    memcpy(value, ctx->host_out, 32);
+    memcpy(values, ctx->host_out, count * 32);
     return TSGPU_OK;
+}
+int tsgpu_kzg_open_dev(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_poly* poly, const tsgpu_fr* z, tsgpu_fr* value, tsgpu_g1* proof) {
+    if (!poly || !value || !proof) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    return tsgpu_kzg_open_batch_dev(ctx, srs, &poly, 1, z, value, proof);
 }
 
 int tsgpu_kzg_open(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_fr* polynomial, size_t n, const tsgpu_fr* z, tsgpu_fr* value, tsgpu_g1* proof) {
@@ -390,6 +471,7 @@ int tsgpu_srs_generate_range(tsgpu_ctx* ctx, const tsgpu_fr* tau, size_t first, 
         if (!rc) rc = fixed_base_points(ctx, scal.as<fr_t>(), n, srs->d);
     }
     if (!rc) { cudaError_t ce = cudaStreamSynchronize(ctx->stream); if (ce != cudaSuccess) rc = cuda_fail(ctx, ce, "srs generation"); }
+    if (!rc) rc = build_tables(ctx, srs->d, n, &srs->table, &srs->table_c);
     if (rc) { tsgpu_srs_free(ctx, srs); return rc; }
     *out = srs;
     return TSGPU_OK;
@@ -399,6 +481,10 @@ int tsgpu_srs_generate_range(tsgpu_ctx* ctx, const tsgpu_fr* tau, size_t first, 
 static g1_affine* lagrange_basis(const tsgpu_srs* srs, size_t m) {
     auto it = srs->lagrange.find(m);
     return it == srs->lagrange.end() ? nullptr : it->second;
+}
+static MsmBasis lagrange_msm_basis(const tsgpu_srs* srs, size_t m) {
+    auto it = srs->lagrange_table.find(m);
+    return MsmBasis{lagrange_basis(srs, m), m, it == srs->lagrange_table.end() ? nullptr : it->second.first, it == srs->lagrange_table.end() ? 0u : it->second.second};
 }
 int tsgpu_srs_has_lagrange(const tsgpu_srs* srs, size_t m) { return srs && lagrange_basis(srs, m) ? 1 : 0; }
 int tsgpu_srs_can_lagrange(const tsgpu_srs* srs) { return srs && srs->has_tau ? 1 : 0; }
@@ -426,57 +512,113 @@ int tsgpu_srs_lagrange_prepare(tsgpu_ctx* ctx, const tsgpu_srs* srs_c, size_t m)
     if (ce == cudaSuccess) ce = spans.alloc(lag_num_spans(m) * sizeof(fr_t), ctx->stream);
     if (ce == cudaSuccess) ce = scal.alloc(m * sizeof(fr_t), ctx->stream);
     if (ce == cudaSuccess) ce = prod.alloc(sizeof(fr_t), ctx->stream);
-    if (ce == cudaSuccess) ce = launch_node_inverses(t, m, inv.as<fr_t>(), spans.as<fr_t>(), prod.as<fr_t>(), ctx->sm_count, ctx->stream);
+    if (ce == cudaSuccess) ce = launch_node_inverses(t, m, inv.as<fr_t>(), spans.as<fr_t>(), ctx->sm_count, ctx->stream);
+    if (ce == cudaSuccess) ce = launch_fr_product(spans.as<fr_t>(), lag_num_spans(m), prod.as<fr_t>(), ctx->stream);
     if (ce == cudaSuccess) ce = launch_lagrange_scalars(inv.as<fr_t>(), ifact, prod.as<fr_t>(), m, scal.as<fr_t>(), ctx->sm_count, ctx->stream);
     ctx->launches += 3;
     if (ce != cudaSuccess) rc = cuda_fail(ctx, ce, "lagrange scalars");
     if (!rc) rc = fixed_base_points(ctx, scal.as<fr_t>(), m, basis);
     if (!rc) { ce = cudaStreamSynchronize(ctx->stream); if (ce != cudaSuccess) rc = cuda_fail(ctx, ce, "lagrange basis"); }
     if (rc) { cudaFree(basis); return rc; }
+    g1_affine* table = nullptr; unsigned table_c = 0;
+    if ((rc = build_tables(ctx, basis, m, &table, &table_c))) { cudaFree(basis); return rc; }
     srs->lagrange[m] = basis;
+    if (table) srs->lagrange_table[m] = {table, table_c};
     return TSGPU_OK;
 }
 
-// commit(interpolant of values on 0..m-1) = sum_j values[j] * [L_j(tau)]_1 : vector_to_polynomial + commit in one MSM
+// commit(interpolant of values on 0..m-1) = sum_j values[j] * [L_j(tau)]_1 : vector_to_polynomial + commit in one MSM.
+// `count` vectors (their lengths may differ: each uses the basis of its own length) in one MSM pass.
+int tsgpu_kzg_commit_values_batch_dev(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_poly* const* values, size_t count, tsgpu_g1* outs) {
+    if (!ctx || !srs || (count && (!values || !outs))) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    if (count > (size_t)MSM_MAX_BATCH) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "too many commitments in one batch");
+    MsmBasis basis[MSM_MAX_BATCH]; const fr_t* sc[MSM_MAX_BATCH]; size_t n[MSM_MAX_BATCH];
+    for (size_t i = 0; i < count; ++i) {
+        if (!values[i]) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+        if (values[i]->n > srs->n) return fail(ctx, TSGPU_E_COMMITMENT, "Polynomial degree exceeds setup size");
+        n[i] = values[i]->n; sc[i] = values[i]->d;
+        basis[i] = MsmBasis{nullptr, 0, nullptr, 0};
+        if (n[i]) {
+            int rc = tsgpu_srs_lagrange_prepare(ctx, srs, n[i]);
+            if (rc) return rc;
+            basis[i] = lagrange_msm_basis(srs, n[i]);
+        }
+    }
+    return msm_device_batch(ctx, (int)count, basis, sc, n, outs);
+}
 int tsgpu_kzg_commit_values_dev(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_poly* values, tsgpu_g1* out) {
-    if (!ctx || !srs || !values || !out) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
-    if (values->n > srs->n) return fail(ctx, TSGPU_E_COMMITMENT, "Polynomial degree exceeds setup size");
-    if (values->n == 0) { G1J id = G1J::identity(); memcpy(out, &id, 96); return TSGPU_OK; }
-    int rc = tsgpu_srs_lagrange_prepare(ctx, srs, values->n);
-    if (rc) return rc;
-    return msm_device(ctx, lagrange_basis(srs, values->n), values->d, values->n, out);
+    if (!values || !out) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    return tsgpu_kzg_commit_values_batch_dev(ctx, srs, &values, 1, out);
 }
 
-// KZGCommitment::open on the interpolant of `values`: value = P(z) by the barycentric formula, proof = commitment to the
-// quotient through its values Q(j) = (v_j - value) / (j - z).  z must not be one of the nodes 0..m-1 (TSGPU_E_POLYNOMIAL).
-int tsgpu_kzg_open_values_dev(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_poly* values, const tsgpu_fr* z, tsgpu_fr* value, tsgpu_g1* proof) {
-    if (!ctx || !srs || !values || !z || !value || !proof) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
-    const size_t m = values->n;
-    if (m == 0) { memset(value, 0, 32); G1J id = G1J::identity(); memcpy(proof, &id, 96); return TSGPU_OK; }
+// KZGCommitment::open on the interpolants of `count` value vectors at one point: value = P(z) by the barycentric formula,
+// proof = commitment to the quotient through its values Q(j) = (v_j - value) / (j - z), the quotient commitments as one MSM
+// pass.  z must not be one of the nodes (TSGPU_E_POLYNOMIAL).  The node inverses 1/(z - j) are computed once for the longest vector.
+int tsgpu_kzg_open_values_batch_dev(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_poly* const* values, size_t count, const tsgpu_fr* z,
+                                    tsgpu_fr* out_values, tsgpu_g1* proofs) {
+    if (!ctx || !srs || !z || (count && (!values || !out_values || !proofs))) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    if (count > (size_t)MSM_MAX_BATCH) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "too many openings in one batch");
+    size_t mmax = 0, total = 0;
+    for (size_t i = 0; i < count; ++i) {
+        if (!values[i]) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+        mmax = values[i]->n > mmax ? values[i]->n : mmax; total += values[i]->n;
+    }
+    if (mmax == 0) {
+        G1J id = G1J::identity();
+        for (size_t i = 0; i < count; ++i) { memset(&out_values[i], 0, 32); memcpy(&proofs[i], &id, 96); }
+        return TSGPU_OK;
+    }
     Fr64 zcan = Fr64::from_raw(z->l).from_mont();
-    if (!zcan.l[1] && !zcan.l[2] && !zcan.l[3] && zcan.l[0] < m) return fail(ctx, TSGPU_E_POLYNOMIAL, "opening point is an interpolation node");
-    int rc = tsgpu_srs_lagrange_prepare(ctx, srs, m);
-    if (rc) return rc;
+    if (!zcan.l[1] && !zcan.l[2] && !zcan.l[3] && zcan.l[0] < mmax) return fail(ctx, TSGPU_E_POLYNOMIAL, "opening point is an interpolation node");
     const fr_t* ifact = nullptr;
-    TSG_CUDA(ctx, interp_factorials(ctx, (unsigned)log2_exact(m), &ifact));
+    TSG_CUDA(ctx, interp_factorials(ctx, (unsigned)log2_exact(mmax), &ifact));
     cudaError_t aerr;
-    const size_t nsp = lag_num_spans(m);
-    fr_t* buf = (fr_t*)arena_get(ctx, tsgpu_ctx::ARENA_QUOT, (2 * m + nsp + 2) * sizeof(fr_t), &aerr);
-    if (!buf) return cuda_fail(ctx, aerr, "cudaMalloc(quotient)");
-    fr_t *q = buf, *inv = buf + m, *spans = inv + m, *nz = spans + nsp, *val = nz + 1;
+    fr_t* q_all = (fr_t*)arena_get(ctx, tsgpu_ctx::ARENA_QUOT, (total + 2 * MSM_MAX_BATCH) * sizeof(fr_t), &aerr);
+    if (!q_all) return cuda_fail(ctx, aerr, "cudaMalloc(quotient)");
+    fr_t *nz = q_all + total, *val = nz + MSM_MAX_BATCH;
+    // 1/(z - j) and the span products depend on z only; a shorter vector uses a prefix of them
+    const bool hit = ctx->bary_inv && !memcmp(&ctx->bary_z, z, 32) && mmax <= ctx->bary_n;
     fr_t zf; memcpy(zf.l, z->l, 32);
+    MsmBasis basis[MSM_MAX_BATCH]; const fr_t* sc[MSM_MAX_BATCH]; size_t n[MSM_MAX_BATCH];
     {
         KernelTimer kt(ctx, "open_bary");
-        TSG_CUDA(ctx, launch_node_inverses(zf, m, inv, spans, nz, ctx->sm_count, ctx->stream));
-        TSG_CUDA(ctx, launch_bary_open(values->d, inv, ifact, m, nz, ctx->partials, ctx->ticket, val, q, ctx->sm_count, ctx->stream));
-        ctx->launches += 4;
+        if (!hit) {
+            fr_t* inv = (fr_t*)arena_get(ctx, tsgpu_ctx::ARENA_BARY, (mmax + lag_num_spans(mmax)) * sizeof(fr_t), &aerr);
+            if (!inv) return cuda_fail(ctx, aerr, "cudaMalloc(node inverses)");
+            ctx->bary_inv = inv; ctx->bary_spans = inv + mmax; ctx->bary_n = mmax; ctx->bary_z = *z;
+            TSG_CUDA(ctx, launch_node_inverses(zf, mmax, inv, (fr_t*)ctx->bary_spans, ctx->sm_count, ctx->stream));
+            ctx->launches += 1;
+        }
+        size_t off = 0;
+        for (size_t i = 0; i < count; ++i) {
+            const size_t m = values[i]->n;
+            n[i] = m; sc[i] = q_all + off; basis[i] = MsmBasis{nullptr, 0, nullptr, 0};
+            if (m) {
+                if (log2_exact(m) < 0) return fail(ctx, TSGPU_E_POLYNOMIAL, "evaluation-basis vectors have power-of-two length");
+                int rc = tsgpu_srs_lagrange_prepare(ctx, srs, m);
+                if (rc) return rc;
+                basis[i] = lagrange_msm_basis(srs, m);
+                // N(z) over the nodes 0..m-1: product of whole spans, or (m < span) a fresh small product
+                if (m % LAG_SPAN == 0 || m == ctx->bary_n) TSG_CUDA(ctx, launch_fr_product((const fr_t*)ctx->bary_spans, lag_num_spans(m), nz + i, ctx->stream));
+                else TSG_CUDA(ctx, launch_node_product(zf, m, nz + i, ctx->stream));
+                TSG_CUDA(ctx, launch_bary_open(values[i]->d, (const fr_t*)ctx->bary_inv, ifact, m, nz + i, ctx->partials, ctx->ticket, val + i, q_all + off, ctx->sm_count, ctx->stream));
+                ctx->launches += 3;
+            } else {
+                TSG_CUDA(ctx, cudaMemsetAsync(val + i, 0, sizeof(fr_t), ctx->stream));
+            }
+            off += m;
+        }
     }
-    TSG_CUDA(ctx, cudaMemcpyAsync(ctx->host_out, val, sizeof(fr_t), cudaMemcpyDeviceToHost, ctx->stream));
-    rc = msm_device(ctx, lagrange_basis(srs, m), q, m, proof);
+    TSG_CUDA(ctx, cudaMemcpyAsync(ctx->host_out, val, count * sizeof(fr_t), cudaMemcpyDeviceToHost, ctx->stream));
+    int rc = msm_device_batch(ctx, (int)count, basis, sc, n, proofs);
     if (rc) return rc;
     TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    memcpy(value, ctx->host_out, 32);
+    memcpy(out_values, ctx->host_out, count * 32);
     return TSGPU_OK;
+}
+int tsgpu_kzg_open_values_dev(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_poly* values, const tsgpu_fr* z, tsgpu_fr* value, tsgpu_g1* proof) {
+    if (!values || !value || !proof) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    return tsgpu_kzg_open_values_batch_dev(ctx, srs, &values, 1, z, value, proof);
 }
 // group addition of two G1Projective values on the CPU (combining per-rank MSM results)
 void tsgpu_g1_add(const tsgpu_g1* a, const tsgpu_g1* b, tsgpu_g1* out) {

@@ -26,13 +26,16 @@ struct tsgpu_ctx {
     // optional per-kernel device timing (CUDA events on `stream`), enabled by tsgpu_set_tuning("kernel_timing", 1)
     // grow-only scratch arenas for the large per-call work buffers (MSM sort/bucket scratch, interpolation ping-pong,
     // quotient) - reused across calls so that the hot path performs no allocation at all
-    enum { ARENA_MSM = 0, ARENA_INTERP = 1, ARENA_QUOT = 2, ARENA_COUNT = 3 };
-    void* arena[ARENA_COUNT] = {nullptr, nullptr, nullptr};
-    size_t arena_bytes[ARENA_COUNT] = {0, 0, 0};
+    enum { ARENA_MSM = 0, ARENA_INTERP = 1, ARENA_QUOT = 2, ARENA_BARY = 3, ARENA_COUNT = 4 };
+    void* arena[ARENA_COUNT] = {nullptr, nullptr, nullptr, nullptr};
+    size_t arena_bytes[ARENA_COUNT] = {0, 0, 0, 0};
+    // node inverses 1/(z - j) of the last barycentric opening (lagrange.cu), reused while the opening point stays the same
+    void* bary_inv = nullptr; void* bary_spans = nullptr; size_t bary_n = 0; tsgpu_fr bary_z;
     uint64_t msm_points = 0;           // points processed by MSMs (for points/s reporting)
     uint64_t msm_entries = 0;          // bucket entries (non-zero signed digits) = mixed additions of k_msm_accumulate
     uint64_t msm_calls = 0;
     bool timing = false;
+    bool msm_tables = true;            // SRS handles carry precomputed window tables (tuning "msm_tables", read when an SRS / basis is built)
     bool eval_basis = true;            // Twist/Shout::prove commit through the Lagrange-basis SRS when it exists (tuning "eval_basis")
     struct Pending { std::string name; cudaEvent_t a, b; };
     std::vector<Pending> pending;

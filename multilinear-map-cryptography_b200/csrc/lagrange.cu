@@ -100,10 +100,24 @@ __global__ void __launch_bounds__(256) k_bary_quotient(const fr_t* vals, const f
         st256(q + j, (v - ld256_nc(vals + j)) * ld256_nc(inv + j));
 }
 
-cudaError_t launch_node_inverses(const fr_t& pt, size_t n, fr_t* inv, fr_t* span_prod, fr_t* prod_out, int sm_count, cudaStream_t s) {
+cudaError_t launch_node_inverses(const fr_t& pt, size_t n, fr_t* inv, fr_t* span_prod, int sm_count, cudaStream_t s) {
     const size_t nch = lag_num_spans(n);
     k_node_inverses<<<gridfor(nch, 128, (size_t)sm_count * 16), 128, 0, s>>>(pt, n, inv, span_prod);
-    k_fr_product<<<1, LAG_PROD_THREADS, 0, s>>>(span_prod, nch, prod_out);
+    return cudaGetLastError();
+}
+// out[0] = prod_{j < m} (pt - j) for a short node range (m below one span)
+__global__ void k_node_product(const fr_t pt, size_t m, fr_t* out) {
+    fr_t acc = fr_t::one(), d = pt;
+    const fr_t one = fr_t::one();
+    for (size_t j = 0; j < m; ++j) { acc = acc * d; d = d - one; }
+    out[0] = acc;
+}
+cudaError_t launch_node_product(const fr_t& pt, size_t m, fr_t* out, cudaStream_t s) {
+    k_node_product<<<1, 1, 0, s>>>(pt, m, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_fr_product(const fr_t* in, size_t count, fr_t* out, cudaStream_t s) {
+    k_fr_product<<<1, LAG_PROD_THREADS, 0, s>>>(in, count, out);
     return cudaGetLastError();
 }
 cudaError_t launch_lagrange_scalars(const fr_t* inv, const fr_t* ifact, const fr_t* ntau, size_t n, fr_t* scal, int sm_count, cudaStream_t s) {

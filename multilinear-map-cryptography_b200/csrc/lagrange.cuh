@@ -9,8 +9,12 @@ constexpr size_t LAG_SPAN = 32;            // nodes per batch inversion (one Fer
 constexpr int LAG_PROD_THREADS = 512;
 inline size_t lag_num_spans(size_t n) { return (n + LAG_SPAN - 1) / LAG_SPAN; }
 
-// inv[j] = 1/(pt - j), j < n; span_prod: lag_num_spans(n) scratch elements; *prod_out = prod_j (pt - j).  2 launches.
-cudaError_t launch_node_inverses(const fr_t& pt, size_t n, fr_t* inv, fr_t* span_prod, fr_t* prod_out, int sm_count, cudaStream_t s);
+// inv[j] = 1/(pt - j), j < n; span_prod[ch] = product of (pt - j) over span ch (lag_num_spans(n) elements)
+cudaError_t launch_node_inverses(const fr_t& pt, size_t n, fr_t* inv, fr_t* span_prod, int sm_count, cudaStream_t s);
+// *out = product of in[0 .. count)   (one block)
+cudaError_t launch_fr_product(const fr_t* in, size_t count, fr_t* out, cudaStream_t s);
+// *out = prod_{j < m} (pt - j), for m below one span (one thread)
+cudaError_t launch_node_product(const fr_t& pt, size_t m, fr_t* out, cudaStream_t s);
 // scal[j] = L_j(tau) from inv[j] = 1/(tau - j), *ntau = prod (tau - k), ifact[k] = 1/k!.  1 launch.
 cudaError_t launch_lagrange_scalars(const fr_t* inv, const fr_t* ifact, const fr_t* ntau, size_t n, fr_t* scal, int sm_count, cudaStream_t s);
 // *value = P(z) (barycentric), q[j] = Q(j) for j < n.  partials / ticket: the context's grid-reduction scratch.  2 launches.

@@ -11,6 +11,7 @@
 //   5. the W window sums go to the host, which combines them (W * c doublings: microseconds of work)
 // Integer-pipe bound: ~ n * W * 10 Fq products; memory traffic is the 64-byte gathers of step 3.
 #include <cstdio>
+#include <cooperative_groups.h>
 #include "fr_device.cuh"
 #include "g1.cuh"
 #include "msm.cuh"
@@ -32,7 +33,8 @@ __device__ __forceinline__ void st_xyzz(g1_xyzz* p, const g1_xyzz& v) {
 }
 
 // ---------------------------------------------------------------- 1. digits + histogram
-__global__ void k_msm_digits(const fr_t* scalars, size_t n, unsigned c, unsigned W, unsigned* dig, unsigned* hist) {
+// set_stride = buckets per window when every window owns a bucket set, 0 when all windows of the job share one set (precomputed tables)
+__global__ void k_msm_digits(const fr_t* scalars, size_t n, unsigned c, unsigned W, unsigned* dig, unsigned* hist, unsigned set_stride) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const unsigned nb = 1u << (c - 1);
     for (size_t i0 = (size_t)blockIdx.x * blockDim.x; i0 < n; i0 += stride) {   // block-uniform bound: warps stay converged for match_any
@@ -49,7 +51,7 @@ __global__ void k_msm_digits(const fr_t* scalars, size_t n, unsigned c, unsigned
             if (d > nb) { d = (1u << c) - d; sign = 1; carry = 1; } else carry = 0;
             if (live) dig[(size_t)w * n + i] = d | (sign << 31);
             // one atomic per distinct bucket in the warp: small scalars put most carries of a window into bucket 1
-            const unsigned key = d ? (unsigned)(w * nb + d - 1) : 0xffffffffu;
+            const unsigned key = d ? (unsigned)(w * set_stride + d - 1) : 0xffffffffu;
             const unsigned peers = __match_any_sync(0xffffffffu, key);
             if (d && (unsigned)(__ffs(peers) - 1) == (threadIdx.x & 31)) atomicAdd(&hist[key], (unsigned)__popc(peers));
         }
@@ -127,9 +129,10 @@ static cudaError_t exclusive_scan_u32(const unsigned* in, unsigned* out, size_t 
 }
 
 // ---------------------------------------------------------------- 3. scatter point indices into bucket order
-__global__ void k_msm_scatter(const unsigned* dig, size_t n, unsigned c, unsigned W, const unsigned* offsets, unsigned* cursor, unsigned* sorted) {
+// entry = index into the job's base array (+ sign): i for per-window bucket sets, w * point_stride + i into the precomputed tables
+__global__ void k_msm_scatter(const unsigned* dig, size_t n, unsigned c, unsigned W, const unsigned* offsets, unsigned* cursor, unsigned* sorted,
+                              unsigned set_stride, size_t point_stride) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    const unsigned nb = 1u << (c - 1);
     const size_t total = (size_t)W * n;
     const unsigned lane = threadIdx.x & 31;
     for (size_t t0 = (size_t)blockIdx.x * blockDim.x; t0 < total; t0 += stride) {   // block-uniform bound: whole warps stay converged
@@ -137,13 +140,13 @@ __global__ void k_msm_scatter(const unsigned* dig, size_t n, unsigned c, unsigne
         unsigned v = t < total ? dig[t] : 0u;
         unsigned d = v & 0x7fffffffu;
         size_t w = t / n, i = t - w * n;
-        const unsigned b = d ? (unsigned)(w * nb + d - 1) : 0xffffffffu;
+        const unsigned b = d ? (unsigned)(w * set_stride + d - 1) : 0xffffffffu;
         const unsigned peers = __match_any_sync(0xffffffffu, b);
         const unsigned leader = __ffs(peers) - 1;
         unsigned base = 0;
         if (d && lane == leader) base = atomicAdd(&cursor[b], (unsigned)__popc(peers));
         base = __shfl_sync(0xffffffffu, base, leader);
-        if (d) sorted[offsets[b] + base + __popc(peers & ((1u << lane) - 1))] = (unsigned)i | (v & 0x80000000u);
+        if (d) sorted[offsets[b] + base + __popc(peers & ((1u << lane) - 1))] = (unsigned)(w * point_stride + i) | (v & 0x80000000u);
     }
 }
 
@@ -235,7 +238,7 @@ __global__ void __launch_bounds__(256) k_msm_order(const unsigned* hist, const u
 }
 
 // ---------------------------------------------------------------- 3b. bucket accumulation (the hot kernel)
-__global__ void __launch_bounds__(MSM_ACC_THREADS) k_msm_accumulate(const g1_affine* bases, const unsigned* sorted, const unsigned* hist, const unsigned* offsets,
+__global__ void __launch_bounds__(MSM_ACC_THREADS) k_msm_accumulate(const MsmBases jobs, unsigned buckets_per_job, const unsigned* sorted, const unsigned* hist, const unsigned* offsets,
                                                                   const unsigned* item_off, const unsigned* item_bucket, const unsigned* n_items,
                                                                   const unsigned* order, g1_xyzz* partial) {
     const unsigned M = *n_items;
@@ -246,6 +249,7 @@ __global__ void __launch_bounds__(MSM_ACC_THREADS) k_msm_accumulate(const g1_aff
         unsigned k = it - item_off[b];
         unsigned cnt = hist[b], base = offsets[b];
         unsigned lo = k * MSM_CHUNK, hi = lo + MSM_CHUNK < cnt ? lo + MSM_CHUNK : cnt;
+        const g1_affine* bases = jobs.p[b / buckets_per_job];
         g1_xyzz acc = g1_xyzz::identity();
         for (unsigned p = lo; p < hi; ++p) {
             unsigned v = sorted[base + p];
@@ -257,59 +261,101 @@ __global__ void __launch_bounds__(MSM_ACC_THREADS) k_msm_accumulate(const g1_aff
 }
 
 // ---------------------------------------------------------------- 3c. buckets split into several chunks: pairwise tree over their partial sums
-// round with stride s: chunk q of a bucket (q a multiple of 2s) absorbs chunk q + s; after ceil(log2 k) rounds chunk 0 holds the bucket sum
-__global__ void __launch_bounds__(128) k_msm_merge_round(g1_xyzz* partial, const unsigned* items, const unsigned* item_off, const unsigned* item_bucket,
-                                                         const unsigned* n_items, unsigned s) {
-    if (s >= n_items[2]) return;               // n_items[2] = largest chunk count of any bucket
+// round with stride s: chunk q of a bucket (q a multiple of 2s) absorbs chunk q + s; after ceil(log2 k) rounds chunk 0 holds the bucket sum.
+// One cooperative launch runs every round (grid.sync between rounds) and returns at once when no bucket was split.
+__global__ void __launch_bounds__(128) k_msm_merge_chunks(g1_xyzz* partial, const unsigned* items, const unsigned* item_off, const unsigned* item_bucket,
+                                                          const unsigned* n_items) {
+    const unsigned max_chunks = n_items[2];    // largest chunk count of any bucket (0 when none exceeds one chunk)
+    if (max_chunks <= 1) return;
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     const unsigned M = n_items[0];
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t it = (size_t)blockIdx.x * blockDim.x + threadIdx.x; it < M; it += stride) {
-        const unsigned b = item_bucket[it];
-        const unsigned k = items[b];
-        if (k <= s) continue;
-        const unsigned q = (unsigned)it - item_off[b];
-        if ((q & (2 * s - 1)) == 0 && q + s < k) st_xyzz(partial + it, ld_xyzz(partial + it).add(ld_xyzz(partial + it + s)));
+    for (unsigned s = 1; s < max_chunks; s <<= 1) {
+        for (size_t it = (size_t)blockIdx.x * blockDim.x + threadIdx.x; it < M; it += stride) {
+            const unsigned b = item_bucket[it];
+            const unsigned k = items[b];
+            if (k <= s) continue;
+            const unsigned q = (unsigned)it - item_off[b];
+            if ((q & (2 * s - 1)) == 0 && q + s < k) st_xyzz(partial + it, ld_xyzz(partial + it).add(ld_xyzz(partial + it + s)));
+        }
+        grid.sync();
     }
 }
 
-// ---------------------------------------------------------------- 4. window reduction, stage 1:
-// thread t of window w owns MSM_RED_SPAN consecutive buckets; out = sum_j (lo + j) * B_{lo+j}
-__global__ void __launch_bounds__(128) k_msm_bucket_reduce(const g1_xyzz* partial, const unsigned* items, const unsigned* item_off, unsigned c, unsigned W,
-                                                           g1_xyzz* blockres) {
-    const unsigned nb = 1u << (c - 1);
-    const unsigned span = nb < MSM_RED_SPAN ? nb : MSM_RED_SPAN;
-    const unsigned per_window = nb / span;
-    const size_t total = (size_t)W * per_window;
+// ---------------------------------------------------------------- 4. window reduction  S_w = sum_b (b + 1) * B_{w,b}
+// Three short launches with a shallow dependency chain (a lone XYZZ addition has ~6 us latency, so depth is what costs):
+//   a. span sums: thread per span of S consecutive buckets: R = sum B, L = sum_j (j + 1) B_{lo + j}   (2 S additions deep)
+//      S_w = sum_spans L + S * sum_sp sp * R_sp
+//   b. the index-weighted sum by bits of sp: sum_sp sp R_sp = sum_k 2^k (sum over sp with bit k set of R_sp): one block per
+//      (window, bit) tree-sums its half of the R's and doubles the result k + log2 S times; one more block per window sums the L's
+//   c. one warp-sized block per window adds the (bits + 1) block results and writes the window sum as a Jacobian point
+__global__ void __launch_bounds__(128) k_msm_span_sums(const g1_xyzz* partial, const unsigned* items, const unsigned* item_off, unsigned nb, unsigned S,
+                                                       size_t total_spans, g1_xyzz* R, g1_xyzz* L) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
-        size_t w = t / per_window; unsigned blk = (unsigned)(t - w * per_window);
-        unsigned lo = blk * span;   // bucket ids lo+1 .. lo+span
+    const unsigned T = nb / S;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total_spans; t += stride) {
+        const size_t w = t / T; const unsigned lo = (unsigned)(t - w * T) * S;
         g1_xyzz running = g1_xyzz::identity(), acc = g1_xyzz::identity();
-        for (unsigned j = span; j-- > 0;) {
-            size_t b = w * nb + lo + j;
+        for (unsigned j = S; j-- > 0;) {
+            const size_t b = w * nb + lo + j;
             if (items[b]) running = running.add(ld_xyzz(partial + item_off[b]));
             acc = acc.add(running);
         }
-        if (lo) acc = acc.add(running.mul_small(lo));
-        st_xyzz(blockres + t, acc);
+        st_xyzz(R + t, running); st_xyzz(L + t, acc);
     }
 }
-
-// stage 2: one block per window sums its `count` block results; writes Jacobian {x,y,z}
-__global__ void __launch_bounds__(MSM_SUM_THREADS) k_msm_window_sum(const g1_xyzz* blockres, unsigned count, g1_jac* out) {
+__global__ void __launch_bounds__(MSM_SUM_THREADS) k_msm_bit_sums(const g1_xyzz* R, const g1_xyzz* L, unsigned T, unsigned nbits, g1_xyzz* parts) {
+    // block (k, w, p): slice p of gridDim.z of the elements that bit k selects (k == nbits: all L's) of bucket set w
     __shared__ g1_xyzz sh[MSM_SUM_THREADS];
-    const g1_xyzz* src = blockres + (size_t)blockIdx.x * count;
+    const unsigned k = blockIdx.x, w = blockIdx.y, p = blockIdx.z, P = gridDim.z;
+    const unsigned U = k == nbits ? T : T / 2;
+    const unsigned u0 = (unsigned)((unsigned long long)U * p / P), u1 = (unsigned)((unsigned long long)U * (p + 1) / P);
     g1_xyzz acc = g1_xyzz::identity();
-    for (unsigned i = threadIdx.x; i < count; i += blockDim.x) acc = acc.add(ld_xyzz(src + i));
+    if (k == nbits) {
+        for (unsigned i = u0 + threadIdx.x; i < u1; i += blockDim.x) acc = acc.add(ld_xyzz(L + (size_t)w * T + i));
+    } else {
+        for (unsigned u = u0 + threadIdx.x; u < u1; u += blockDim.x) {
+            const unsigned t = ((u >> k) << (k + 1)) | (1u << k) | (u & ((1u << k) - 1));
+            acc = acc.add(ld_xyzz(R + (size_t)w * T + t));
+        }
+    }
     sh[threadIdx.x] = acc;
     __syncthreads();
     for (unsigned s = blockDim.x / 2; s > 0; s >>= 1) {
         if (threadIdx.x < s) sh[threadIdx.x] = sh[threadIdx.x].add(sh[threadIdx.x + s]);
         __syncthreads();
     }
+    if (threadIdx.x == 0) st_xyzz(parts + ((size_t)w * (nbits + 1) + k) * P + p, sh[0]);
+}
+// block (k, w): adds the P <= 32 slice sums and applies the weight 2^(k + log2 S) of bit k (none for the L sum)
+__global__ void __launch_bounds__(32) k_msm_bit_finish(const g1_xyzz* parts, unsigned P, unsigned nbits, unsigned logS, g1_xyzz* bits) {
+    __shared__ g1_xyzz sh[32];
+    const unsigned k = blockIdx.x, w = blockIdx.y;
+    const size_t slot = (size_t)w * (nbits + 1) + k;
+    sh[threadIdx.x] = threadIdx.x < P ? ld_xyzz(parts + slot * P + threadIdx.x) : g1_xyzz::identity();
+    __syncwarp();
+    for (unsigned s = 16; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sh[threadIdx.x] = sh[threadIdx.x].add(sh[threadIdx.x + s]);
+        __syncwarp();
+    }
+    if (threadIdx.x == 0) {
+        g1_xyzz r = sh[0];
+        if (k != nbits) for (unsigned d = 0; d < k + logS; ++d) r = r.dbl();
+        st_xyzz(bits + slot, r);
+    }
+}
+__global__ void __launch_bounds__(32) k_msm_window_finish(const g1_xyzz* bits, unsigned nbits, g1_jac* out) {
+    __shared__ g1_xyzz sh[32];
+    const unsigned w = blockIdx.x;
+    sh[threadIdx.x] = threadIdx.x <= nbits ? ld_xyzz(bits + (size_t)w * (nbits + 1) + threadIdx.x) : g1_xyzz::identity();
+    __syncwarp();
+    for (unsigned s = 16; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sh[threadIdx.x] = sh[threadIdx.x].add(sh[threadIdx.x + s]);
+        __syncwarp();
+    }
     if (threadIdx.x == 0) {
         g1_jac j = sh[0].to_jacobian();
-        st256(&out[blockIdx.x].x, j.x); st256(&out[blockIdx.x].y, j.y); st256(&out[blockIdx.x].z, j.z);
+        st256(&out[w].x, j.x); st256(&out[w].y, j.y); st256(&out[w].z, j.z);
     }
 }
 
@@ -399,16 +445,28 @@ unsigned msm_window_bits(size_t n) {
     return (unsigned)c;
 }
 
-size_t msm_scratch_bytes(size_t n, unsigned c, MsmLayout* L) {
+// window width of the precomputed-table mode for a base array of n points
+unsigned msm_table_window_bits(size_t n) {
+    unsigned lg = 0; while (((size_t)1 << (lg + 1)) <= n) ++lg;
+    if (lg < 8) lg = 8;
+    if (lg > 20) lg = 20;
+    return lg;
+}
+
+size_t msm_scratch_bytes(size_t nmax, int K, unsigned c, bool shared, MsmLayout* L) {
     const unsigned W = (255 + c - 1) / c;
-    const size_t nb = (size_t)1 << (c - 1), nbuckets = W * nb;
-    const size_t max_items = nbuckets + (W * n) / MSM_CHUNK + 1;
+    const unsigned sets = (unsigned)K * (shared ? 1u : W);            // bucket sets = windows seen by the reduction
+    const size_t nb = (size_t)1 << (c - 1), nbuckets = sets * nb;
+    const size_t entries = (size_t)K * W * nmax;
+    const size_t max_items = nbuckets + entries / MSM_CHUNK + 1;
     const unsigned span = nb < MSM_RED_SPAN ? (unsigned)nb : MSM_RED_SPAN;
+    unsigned nbits = 0; while (((size_t)span << nbits) < nb) ++nbits;   // spans per bucket set = 2^nbits
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
-    L->c = c; L->W = W; L->nbuckets = nbuckets; L->max_items = max_items; L->blocks_per_window = (unsigned)(nb / span);
-    L->dig = take(W * n * 4);
-    L->sorted = take(W * n * 4);
+    L->c = c; L->W = W; L->K = (unsigned)K; L->sets = sets; L->shared = shared; L->nmax = nmax;
+    L->nbuckets = nbuckets; L->max_items = max_items; L->blocks_per_window = (unsigned)(nb / span); L->span = span; L->span_bits = nbits;
+    L->dig = take(entries * 4);
+    L->sorted = take(entries * 4);
     L->hist = take(nbuckets * 4);
     L->offsets = take(nbuckets * 4);
     L->cursor = take(nbuckets * 4);
@@ -420,14 +478,17 @@ size_t msm_scratch_bytes(size_t n, unsigned c, MsmLayout* L) {
     L->len_hist = take(3 * (MSM_CHUNK + 1) * 4);   // length histogram, offsets, cursors
     L->scan_tmp = take((nbuckets / 1024 + 64) * 4);
     L->partial = take(max_items * sizeof(g1_xyzz));
-    L->blockres = take((size_t)W * L->blocks_per_window * sizeof(g1_xyzz));
-    L->window_out = take(W * sizeof(g1_jac));
+    L->blockres = take((size_t)2 * sets * L->blocks_per_window * sizeof(g1_xyzz));   // span sums R, then L
+    L->bits = take((size_t)sets * (nbits + 1) * 33 * sizeof(g1_xyzz));   // weighted bit sums, then up to 32 slice sums of each
+    L->window_out = take(sets * sizeof(g1_jac));
     return off;
 }
 
-// returns the number of kernels launched through *launches
-cudaError_t msm_run(const g1_affine* bases, const fr_t* scalars, size_t n, const MsmLayout& L, unsigned char* scratch, int sm_count,
-                    cudaStream_t s, unsigned* launches, cudaEvent_t* acc_events) {
+// K independent MSMs in one pass (same window width): their bucket sets are laid side by side, so every phase after the
+// per-job digit extraction / scatter runs once over the union and the latency-bound tails (chunk chains, tree merge, window
+// reduction) overlap across jobs.  Results: L.sets Jacobian points at scratch + L.window_out (job-major).
+cudaError_t msm_run(const MsmJob* jobs, int K, const MsmLayout& L, unsigned char* scratch, int sm_count,
+                    cudaStream_t s, unsigned* launches, cudaEvent_t* ev) {
     unsigned* dig = (unsigned*)(scratch + L.dig); unsigned* sorted = (unsigned*)(scratch + L.sorted);
     unsigned* hist = (unsigned*)(scratch + L.hist); unsigned* offsets = (unsigned*)(scratch + L.offsets);
     unsigned* cursor = (unsigned*)(scratch + L.cursor); unsigned* items = (unsigned*)(scratch + L.items);
@@ -436,6 +497,7 @@ cudaError_t msm_run(const g1_affine* bases, const fr_t* scalars, size_t n, const
     g1_xyzz* partial = (g1_xyzz*)(scratch + L.partial); g1_xyzz* blockres = (g1_xyzz*)(scratch + L.blockres);
     g1_jac* wout = (g1_jac*)(scratch + L.window_out);
     cudaError_t e;
+    if (ev) cudaEventRecord(ev[0], s);
     // hist and cursor are adjacent-independent regions: clear both
     if ((e = cudaMemsetAsync(hist, 0, L.nbuckets * 4, s))) return e;
     if ((e = cudaMemsetAsync(cursor, 0, L.nbuckets * 4, s))) return e;
@@ -444,24 +506,83 @@ cudaError_t msm_run(const g1_affine* bases, const fr_t* scalars, size_t n, const
     if ((e = cudaMemsetAsync(len_hist, 0, 3 * (MSM_CHUNK + 1) * 4, s))) return e;
     if ((e = cudaMemsetAsync(n_items, 0, 256, s))) return e;
     const size_t cap = (size_t)sm_count * 8;
-    k_msm_digits<<<gridfor(n, 256, cap), 256, 0, s>>>(scalars, n, L.c, L.W, dig, hist);
+    const unsigned nb = 1u << (L.c - 1);
+    const unsigned set_stride = L.shared ? 0u : nb;
+    const size_t buckets_per_job = (size_t)(L.sets / L.K) * nb;
+    MsmBases bases;
+    for (int k = 0; k < MSM_MAX_BATCH; ++k) bases.p[k] = k < K ? jobs[k].bases : nullptr;
+    for (int k = 0; k < K; ++k)
+        k_msm_digits<<<gridfor(jobs[k].n, 256, cap), 256, 0, s>>>(jobs[k].scalars, jobs[k].n, L.c, L.W, dig + (size_t)k * L.W * L.nmax,
+                                                                   hist + k * buckets_per_job, set_stride);
     exclusive_scan_u32(hist, offsets, L.nbuckets, (unsigned*)(scratch + L.scan_tmp), n_items + 1, s);   // n_items[1] = bucket entries (non-zero digits)
-    k_msm_scatter<<<gridfor((size_t)L.W * n, 256, cap), 256, 0, s>>>(dig, n, L.c, L.W, offsets, cursor, sorted);
+    for (int k = 0; k < K; ++k)
+        k_msm_scatter<<<gridfor((size_t)L.W * jobs[k].n, 256, cap), 256, 0, s>>>(dig + (size_t)k * L.W * L.nmax, jobs[k].n, L.c, L.W, offsets + k * buckets_per_job,
+                                                                                 cursor + k * buckets_per_job, sorted, set_stride, L.shared ? jobs[k].stride : 0);
     k_msm_item_counts<<<gridfor(L.nbuckets, 256, cap), 256, 0, s>>>(hist, L.nbuckets, items, n_items + 2);
     exclusive_scan_u32(items, item_off, L.nbuckets, (unsigned*)(scratch + L.scan_tmp), n_items, s);
     k_msm_item_fill<<<gridfor(L.nbuckets, 256, cap), 256, 0, s>>>(items, item_off, hist, L.nbuckets, item_bucket, len_hist);
     k_msm_len_scan<<<1, SCAN_THREADS, 0, s>>>(len_hist, len_off);
     k_msm_order<<<gridfor(L.max_items, 256 * ORDER_TILE, cap), 256, 0, s>>>(hist, item_off, item_bucket, n_items, len_off, len_cursor, order);
-    if (acc_events) cudaEventRecord(acc_events[0], s);
-    k_msm_accumulate<<<gridfor(L.max_items, MSM_ACC_THREADS, (size_t)sm_count * 16), MSM_ACC_THREADS, 0, s>>>(bases, sorted, hist, offsets, item_off, item_bucket, n_items, order, partial);
-    if (acc_events) cudaEventRecord(acc_events[1], s);
-    unsigned rounds = 0;
-    for (size_t st = 1; st * MSM_CHUNK < n; st <<= 1, ++rounds)   // a bucket holds at most n entries = ceil(n / MSM_CHUNK) chunks; idle rounds return at once
-        k_msm_merge_round<<<gridfor(L.max_items, 128, cap), 128, 0, s>>>(partial, items, item_off, item_bucket, n_items, (unsigned)st);
-    if (launches) *launches += rounds;
-    k_msm_bucket_reduce<<<gridfor((size_t)L.W * L.blocks_per_window, 128, cap), 128, 0, s>>>(partial, items, item_off, L.c, L.W, blockres);
-    k_msm_window_sum<<<L.W, MSM_SUM_THREADS, 0, s>>>(blockres, L.blocks_per_window, wout);
-    if (launches) *launches += 15;
+    if (ev) cudaEventRecord(ev[1], s);
+    k_msm_accumulate<<<gridfor(L.max_items, MSM_ACC_THREADS, (size_t)sm_count * 16), MSM_ACC_THREADS, 0, s>>>(bases, (unsigned)buckets_per_job, sorted, hist, offsets, item_off,
+                                                                                                                item_bucket, n_items, order, partial);
+    if (ev) cudaEventRecord(ev[2], s);
+    {
+        static int coop_blocks_per_sm = 0;
+        if (!coop_blocks_per_sm) {
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&coop_blocks_per_sm, k_msm_merge_chunks, 128, 0) != cudaSuccess || coop_blocks_per_sm < 1) coop_blocks_per_sm = 1;
+            if (coop_blocks_per_sm > 4) coop_blocks_per_sm = 4;
+        }
+        void* args[] = {(void*)&partial, (void*)&items, (void*)&item_off, (void*)&item_bucket, (void*)&n_items};
+        if ((e = cudaLaunchCooperativeKernel((const void*)k_msm_merge_chunks, dim3(sm_count * coop_blocks_per_sm), dim3(128), args, 0, s))) return e;
+    }
+    if (ev) cudaEventRecord(ev[3], s);
+    {
+        const size_t spans = (size_t)L.sets * L.blocks_per_window;
+        g1_xyzz* spanR = blockres; g1_xyzz* spanL = blockres + spans; g1_xyzz* bits = (g1_xyzz*)(scratch + L.bits);
+        unsigned logS = 0; while ((1u << logS) < L.span) ++logS;
+        k_msm_span_sums<<<gridfor(spans, 128, (size_t)sm_count * 16), 128, 0, s>>>(partial, items, item_off, nb, L.span, spans, spanR, spanL);
+        // enough slices per (set, bit) to put ~4 blocks on every SM, at least one block-load of elements each
+        unsigned P = (unsigned)((4 * (size_t)sm_count + (L.span_bits + 1) * L.sets - 1) / ((L.span_bits + 1) * L.sets));
+        const unsigned maxP = L.blocks_per_window / (2 * MSM_SUM_THREADS);
+        if (P > maxP) P = maxP;
+        if (P > 32) P = 32;
+        if (P < 1) P = 1;
+        g1_xyzz* parts = bits + (size_t)L.sets * (L.span_bits + 1);
+        k_msm_bit_sums<<<dim3(L.span_bits + 1, L.sets, P), MSM_SUM_THREADS, 0, s>>>(spanR, spanL, L.blocks_per_window, L.span_bits, parts);
+        k_msm_bit_finish<<<dim3(L.span_bits + 1, L.sets), 32, 0, s>>>(parts, P, L.span_bits, logS, bits);
+        k_msm_window_finish<<<L.sets, 32, 0, s>>>(bits, L.span_bits, wout);
+    }
+    if (ev) cudaEventRecord(ev[4], s);
+    if (launches) *launches += 16 + 2 * (unsigned)K;
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- precomputed window tables: table[w * n + i] = 2^(c w) * bases[i]
+// cur (XYZZ) <- 2^c * cur, one thread per point
+__global__ void __launch_bounds__(128) k_msm_table_step(g1_xyzz* cur, size_t n, unsigned c) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        g1_xyzz p = ld_xyzz(cur + i);
+        for (unsigned k = 0; k < c; ++k) p = p.dbl();
+        st_xyzz(cur + i, p);
+    }
+}
+__global__ void k_affine_to_xyzz(const g1_affine* in, size_t n, g1_xyzz* out) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) st_xyzz(out + i, g1_xyzz::from_affine(ld_affine(in + i)));
+}
+// table: W * n affine points (window 0 = a copy of bases); cur: n XYZZ scratch points
+cudaError_t msm_build_table(const g1_affine* bases, size_t n, unsigned c, g1_affine* table, g1_xyzz* cur, int sm_count, cudaStream_t s, unsigned* launches) {
+    const unsigned W = (255 + c - 1) / c;
+    cudaError_t e;
+    if ((e = cudaMemcpyAsync(table, bases, n * sizeof(g1_affine), cudaMemcpyDeviceToDevice, s))) return e;
+    k_affine_to_xyzz<<<gridfor(n, 256, (size_t)sm_count * 8), 256, 0, s>>>(bases, n, cur);
+    for (unsigned w = 1; w < W; ++w) {
+        k_msm_table_step<<<gridfor(n, 128, (size_t)sm_count * 16), 128, 0, s>>>(cur, n, c);
+        if ((e = launch_batch_to_affine(cur, n, table + (size_t)w * n, sm_count, s))) return e;
+    }
+    if (launches) *launches += 2 * W - 1;
     return cudaGetLastError();
 }
 

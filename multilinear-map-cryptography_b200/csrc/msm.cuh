@@ -7,22 +7,36 @@ namespace tsg {
 
 constexpr unsigned MSM_CHUNK = 64;        // max entries one work item adds into its accumulator (bounds the serial chain of one thread)
 constexpr int MSM_ACC_THREADS = 128;
-constexpr unsigned MSM_RED_SPAN = 32;     // buckets per thread in the window reduction
-constexpr int MSM_SUM_THREADS = 128;
+constexpr unsigned MSM_RED_SPAN = 8;      // buckets per thread in the window reduction (2 x span additions deep)
+constexpr int MSM_SUM_THREADS = 256;
 constexpr size_t MSM_POW_SPAN = 64;       // consecutive tau powers per thread
 constexpr size_t MSM_INV_SPAN = 32;       // points per batch inversion
 
+constexpr int MSM_MAX_BATCH = 4;          // independent MSMs processed in one pass
+
+struct MsmJob {
+    const g1_affine* bases;   // n points, or (precomputed-table mode) W tables of `stride` points: table[w * stride + i] = 2^(c w) * P_i
+    size_t stride;
+    const fr_t* scalars;      // n scalars, Montgomery form
+    size_t n;
+};
+struct MsmBases { const g1_affine* p[MSM_MAX_BATCH]; };
+
 struct MsmLayout {
-    unsigned c, W, blocks_per_window;
-    size_t nbuckets, max_items;
-    size_t dig, sorted, hist, offsets, cursor, items, item_off, item_bucket, n_items, order, len_hist, scan_tmp, partial, blockres, window_out;
+    unsigned c, W, K, sets, blocks_per_window, span, span_bits;   // sets = bucket sets = K * (shared ? 1 : W); blocks_per_window = spans per set = 2^span_bits
+    bool shared;                                                 // all W digit positions of a job feed one bucket set (needs the precomputed tables)
+    size_t nmax, nbuckets, max_items;
+    size_t dig, sorted, hist, offsets, cursor, items, item_off, item_bucket, n_items, order, len_hist, scan_tmp, partial, blockres, bits, window_out;
 };
 
 unsigned msm_window_bits(size_t n);
-size_t msm_scratch_bytes(size_t n, unsigned c, MsmLayout* L);
-// runs steps 1-4; the W window sums (Jacobian) are left at scratch + L.window_out
-cudaError_t msm_run(const g1_affine* bases, const fr_t* scalars, size_t n, const MsmLayout& L, unsigned char* scratch, int sm_count,
-                    cudaStream_t s, unsigned* launches, cudaEvent_t* acc_events = nullptr);   // acc_events[2]: around the accumulate kernel
+unsigned msm_table_window_bits(size_t n);
+size_t msm_scratch_bytes(size_t nmax, int K, unsigned c, bool shared, MsmLayout* L);
+// runs every device phase; the L.sets bucket-set sums (Jacobian, job-major) are left at scratch + L.window_out
+cudaError_t msm_run(const MsmJob* jobs, int K, const MsmLayout& L, unsigned char* scratch, int sm_count,
+                    cudaStream_t s, unsigned* launches, cudaEvent_t* ev = nullptr);   // ev[5]: start | sort done | accumulate done | chunk merge done | reduce done
+// table[w * n + i] = 2^(c w) * bases[i] for w < ceil(255 / c); cur: n XYZZ points of scratch
+cudaError_t msm_build_table(const g1_affine* bases, size_t n, unsigned c, g1_affine* table, g1_xyzz* cur, int sm_count, cudaStream_t s, unsigned* launches);
 
 cudaError_t launch_tau_powers(const fr_t& tau, size_t first, size_t n, fr_t* out, int sm_count, cudaStream_t s);
 cudaError_t launch_fixed_base_mul(const fr_t* scalars, size_t n, const g1_affine* table, g1_xyzz* out, int sm_count, cudaStream_t s);

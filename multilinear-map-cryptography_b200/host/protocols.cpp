@@ -61,13 +61,10 @@ int prove_two_vectors(tsgpu_ctx* ctx, const tsgpu_params* params, tsgpu_poly* pa
     tsgpu_proof* pr = new (std::nothrow) tsgpu_proof;
     if (!pr) return fail(ctx, TSGPU_E_PROOF_GENERATION, "out of host memory");
     memset(&pr->opening_point, 0, 32);
-    if (eval_basis) {
-        if ((rc = tsgpu_kzg_commit_values_dev(ctx, params->srs, pa, &pr->commitments[0]))) { delete pr; return rc; }
-        if ((rc = tsgpu_kzg_commit_values_dev(ctx, params->srs, pb, &pr->commitments[1]))) { delete pr; return rc; }
-    } else {
-        if ((rc = tsgpu_kzg_commit_dev(ctx, params->srs, pa, &pr->commitments[0]))) { delete pr; return rc; }
-        if ((rc = tsgpu_kzg_commit_dev(ctx, params->srs, pb, &pr->commitments[1]))) { delete pr; return rc; }
-    }
+    const tsgpu_poly* both[2] = {pa, pb};
+    rc = eval_basis ? tsgpu_kzg_commit_values_batch_dev(ctx, params->srs, both, 2, pr->commitments)     // both commitments in one MSM pass
+                    : tsgpu_kzg_commit_batch_dev(ctx, params->srs, both, 2, pr->commitments);
+    if (rc) { delete pr; return rc; }
     Transcript tr(params->fiat_shamir_seed);
     tsgpu_fr h;
     tsgpu_g1_hash(&pr->commitments[0], &h); tr.append_field_element(label_a, fr_of(h));
@@ -86,7 +83,6 @@ int prove_two_vectors(tsgpu_ctx* ctx, const tsgpu_params* params, tsgpu_poly* pa
     if (!ch.empty()) {                                                                  // twist.rs:226-243
         tsgpu_fr z = abi_of(ch[0]);
         pr->opening_point = z;
-        tsgpu_fr v; tsgpu_g1 pi;
         if (eval_basis) {
             // the barycentric opening needs z outside the nodes 0..n-1 (a 2^-230 event): otherwise finish on coefficients
             Fr64 zc = Fr64::from_raw(z.l).from_mont();
@@ -96,11 +92,11 @@ int prove_two_vectors(tsgpu_ctx* ctx, const tsgpu_params* params, tsgpu_poly* pa
                 eval_basis = false;
             }
         }
-        for (tsgpu_poly* p : {pa, pb}) {
-            rc = eval_basis ? tsgpu_kzg_open_values_dev(ctx, params->srs, p, &z, &v, &pi) : tsgpu_kzg_open_dev(ctx, params->srs, p, &z, &v, &pi);
-            if (rc) { delete pr; return rc; }
-            pr->opening_proofs.push_back(pi); pr->final_evaluations.push_back(v);
-        }
+        tsgpu_fr vs[2]; tsgpu_g1 pis[2];
+        rc = eval_basis ? tsgpu_kzg_open_values_batch_dev(ctx, params->srs, both, 2, &z, vs, pis)       // both openings: one MSM pass over the two quotients
+                        : tsgpu_kzg_open_batch_dev(ctx, params->srs, both, 2, &z, vs, pis);
+        if (rc) { delete pr; return rc; }
+        for (int i = 0; i < 2; ++i) { pr->opening_proofs.push_back(pis[i]); pr->final_evaluations.push_back(vs[i]); }
     }
     *out = pr;
     return TSGPU_OK;

@@ -119,3 +119,39 @@ def test_open_at_zero_and_one(ctx, tsgpu, oracle, srs_small):
         v_ref, q_ref = oracle.kzg_value_quotient(poly, z)
         assert (value == v_ref).all()
         assert oracle.g1_compress(proof) == oracle.g1_compress(oracle.msm_pippenger(oracle.g1_batch_to_affine(ref[:599]), q_ref))
+
+
+@pytest.mark.parametrize("n", [1100, 2000, 4096, 4097])
+def test_commit_table_mode_matches_oracle_msm(ctx, tsgpu, oracle, srs_small, n):
+    """polynomials covering >= 1/4 of the SRS run on the precomputed window tables (one shared bucket set, csrc/msm.cu);
+    same group element as the CPU Pippenger over the plain points"""
+    srs, ref = srs_small
+    poly = oracle.chacha_fr_rand(seed_bytes(n % 251), n).reshape(n, 4)
+    got = tsgpu.KZGCommitment.commit(srs, poly)
+    want = oracle.msm_pippenger(oracle.g1_batch_to_affine(ref[:n]), poly)
+    assert tsgpu.g1_compress(got) == oracle.g1_compress(want)
+
+
+def test_commit_without_window_tables(ctx, tsgpu, oracle, srs_small):
+    """tuning msm_tables = 0: SRS handles built without tables use per-window bucket sets; identical commitments"""
+    srs, ref = srs_small
+    tau, _ = oracle.setup_scalars()
+    try:
+        ctx.set_tuning("msm_tables", 0)
+        plain = ctx.srs_generate(tau, 3000)
+    finally:
+        ctx.set_tuning("msm_tables", 1)
+    for n in (1, 700, 3000):
+        poly = oracle.chacha_fr_rand(seed_bytes(n % 250 + 1), n).reshape(n, 4)
+        assert tsgpu.g1_compress(tsgpu.KZGCommitment.commit(plain, poly)) == tsgpu.g1_compress(tsgpu.KZGCommitment.commit(srs, poly))
+
+
+def test_commit_edge_scalars_table_mode(ctx, tsgpu, oracle, srs_small):
+    """heavy buckets in table mode: equal scalars put every point of a window into one bucket (chunked + tree-merged)"""
+    srs, ref = srs_small
+    n = 4000
+    aff = oracle.g1_batch_to_affine(ref[:n])
+    for ints in ([1] * n, [123456789] * n, [oracle.R_MOD - 1] * n, [(1 << 253) + 5] * n, [i % 7 for i in range(n)]):
+        poly = oracle.fr_from_ints(ints)
+        got = tsgpu.KZGCommitment.commit(srs, poly)
+        assert tsgpu.g1_compress(got) == oracle.g1_compress(oracle.msm_pippenger(aff, poly))

@@ -37,9 +37,10 @@ def main():
             ctx.synchronize()
             wall = (time.perf_counter() - t0) / reps * 1e3
             tot, _ = ctx.timer_read("msm_total"); acc, _ = ctx.timer_read("msm_accumulate")
+            phases = {k: ctx.timer_read("msm_" + k)[0] / reps for k in ("sort", "merge", "reduce")}
             ctx.set_tuning("kernel_timing", 0)
             ent = (ctx.counter("msm_entries") - c0) / reps
-            out.append({"log_n": lg, "scalars": name, "wall_ms": wall, "msm_total_ms": tot / reps, "accumulate_ms": acc / reps, "entries": ent,
+            out.append({"log_n": lg, "scalars": name, "wall_ms": wall, "msm_total_ms": tot / reps, "accumulate_ms": acc / reps, "sort_ms": phases["sort"], "merge_ms": phases["merge"], "reduce_ms": phases["reduce"], "entries": ent,
                         "points_per_s": n / (wall * 1e-3), "acc_TIMAD_s": ent * 1360 / (acc / reps * 1e-3) / 1e12 if acc else None})
             print(json.dumps(out[-1]), flush=True)
         del cases, srs
