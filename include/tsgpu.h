@@ -110,6 +110,8 @@ int tsgpu_sc_round_eval(tsgpu_sc* sc, tsgpu_fr evals[4]);
 int tsgpu_sc_bind(tsgpu_sc* sc, const tsgpu_fr* r);
 /* fused: bind to r, then evaluate the next round's g(0..3) in the same pass */
 int tsgpu_sc_bind_eval(tsgpu_sc* sc, const tsgpu_fr* r, tsgpu_fr evals[4]);
+/* same with the running claim g_k(r) of SumCheck::prove (src/sumcheck.rs:86-100) supplied: g(1) = claim - g(0) is derived, not summed */
+int tsgpu_sc_bind_eval_claim(tsgpu_sc* sc, const tsgpu_fr* r, const tsgpu_fr* claim, tsgpu_fr evals[4]);
 /* after all variables are bound: the d table values mle_t(r_0..r_{n-1}); their product is
  * SumCheckProof.final_evaluation (sumcheck.rs:104) */
 int tsgpu_sc_final(tsgpu_sc* sc, tsgpu_fr* finals);

@@ -323,10 +323,15 @@ class SumCheckRounds:
         r = _fr(r, 1)
         self.ctx.check(lib().tsgpu_sc_bind(self._h, _p(r)))
 
-    def bind_eval(self, r) -> np.ndarray:
+    def bind_eval(self, r, claim=None) -> np.ndarray:
+        """fused bind(r) + evaluation of the next round; with `claim` (= g(r) of the round just bound) g(1) is derived as claim - g(0)"""
         r = _fr(r, 1)
         out = np.empty((4, 4), dtype=np.uint64)
-        self.ctx.check(lib().tsgpu_sc_bind_eval(self._h, _p(r), _p(out)))
+        if claim is None:
+            self.ctx.check(lib().tsgpu_sc_bind_eval(self._h, _p(r), _p(out)))
+        else:
+            claim = _fr(claim, 1)
+            self.ctx.check(lib().tsgpu_sc_bind_eval_claim(self._h, _p(r), _p(claim), _p(out)))
         return out
 
     def final(self) -> np.ndarray:

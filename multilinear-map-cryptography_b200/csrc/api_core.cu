@@ -405,16 +405,26 @@ int tsgpu_sc_bind(tsgpu_sc* sc, const tsgpu_fr* r) {
     return TSGPU_OK;
 }
 
-int tsgpu_sc_bind_eval(tsgpu_sc* sc, const tsgpu_fr* r, tsgpu_fr evals[4]) {
+static int sc_bind_eval_impl(tsgpu_sc* sc, const tsgpu_fr* r, const tsgpu_fr* claim, tsgpu_fr evals[4]) {
     if (!sc || !r || !evals) return TSGPU_E_INVALID_PARAMETERS;
     tsgpu_ctx* ctx = sc->ctx;
     if (sc->vars_left < 2) return fail(ctx, TSGPU_E_SUMCHECK, "bind_eval needs at least two unbound variables");
     KernelTimer kt(ctx, "sc_bind_eval");
-    TSG_CUDA(ctx, launch_bind_eval(sc->d, sc_tabs(sc), (size_t)1 << sc->vars_left, to_fr(r), ctx->partials, ctx->ticket, ctx->dev_out, ctx->sm_count, ctx->stream));
+    fr_t cl; if (claim) cl = to_fr(claim);
+    TSG_CUDA(ctx, launch_bind_eval(sc->d, sc_tabs(sc), (size_t)1 << sc->vars_left, to_fr(r), claim ? &cl : nullptr, ctx->partials, ctx->ticket, ctx->dev_out,
+                                   ctx->sm_count, ctx->stream));
     ctx->launches += 1;
     for (int i = 0; i < sc->d; ++i) sc->tables[i]->num_vars -= 1;
     sc->vars_left -= 1;
     return read_result(ctx, 4, evals);
+}
+int tsgpu_sc_bind_eval(tsgpu_sc* sc, const tsgpu_fr* r, tsgpu_fr evals[4]) { return sc_bind_eval_impl(sc, r, nullptr, evals); }
+// same, given the claim of the round being evaluated (g_k(r) of the round just bound): g(0) + g(1) = claim is then an identity
+// (the reference checks it every round, src/sumcheck.rs:77-84; it can only fail in round 0, which tsgpu_sc_round_eval computes in full),
+// so the kernel sums g(0) and g(2) only and returns g(1) = claim - g(0).  Same four values.
+int tsgpu_sc_bind_eval_claim(tsgpu_sc* sc, const tsgpu_fr* r, const tsgpu_fr* claim, tsgpu_fr evals[4]) {
+    if (!claim) return TSGPU_E_INVALID_PARAMETERS;
+    return sc_bind_eval_impl(sc, r, claim, evals);
 }
 
 int tsgpu_sc_final(tsgpu_sc* sc, tsgpu_fr* finals) {

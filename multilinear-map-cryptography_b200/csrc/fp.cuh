@@ -291,6 +291,82 @@ TSG_HD void mont_reduce(uint32_t* r, const uint32_t* T) {
 }
 
 
+// ---- multiplication by a per-launch constant -------------------------------------------------------
+// The fold of a sum-check round multiplies every table difference by the SAME challenge r.  With the
+// eight residues  T[k] = r_canonical * 2^(32 k + 64) mod p  prepared once on the host,
+//     a * r  ==  ( sum_k a_k T[k] ) * 2^-64   (mod p)          (a_k = 32-bit limbs of a)
+// so the product needs the 64 limb products (all landing on the same ten limbs: no shifted rows), two
+// Montgomery word steps (2 x 8 products) to strip the 2^64, and one conditional subtraction - about
+// 80 wide multiply-adds instead of the 128 + 8 of a full Montgomery product.  For a in Montgomery
+// form the result is the Montgomery form of the product: the same bits mont_mul(a, r_mont) returns.
+// Bounds: sum < 8 * 2^32 * p; after the first word step < 9 p; after the second < 2 p.
+template <class P>
+TSG_HD void mul_ctab(uint32_t* r, const uint32_t* a, const uint32_t (*T)[8]) {
+    uint32_t E[9], O[9];   // E aligned at limb 0, O at limb 1 (value = E + O * 2^32)
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+        ptx::mul_wide(E[j], E[j + 1], a[0], T[0][j]);
+        ptx::mul_wide(O[j], O[j + 1], a[0], T[0][j + 1]);
+    }
+    E[8] = 0; O[8] = 0;
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+        const uint32_t ak = a[k];
+        E[0] = ptx::mad_lo_cc(ak, T[k][0], E[0]);
+        E[1] = ptx::madc_hi_cc(ak, T[k][0], E[1]);
+        E[2] = ptx::madc_lo_cc(ak, T[k][2], E[2]);
+        E[3] = ptx::madc_hi_cc(ak, T[k][2], E[3]);
+        E[4] = ptx::madc_lo_cc(ak, T[k][4], E[4]);
+        E[5] = ptx::madc_hi_cc(ak, T[k][4], E[5]);
+        E[6] = ptx::madc_lo_cc(ak, T[k][6], E[6]);
+        E[7] = ptx::madc_hi_cc(ak, T[k][6], E[7]);
+        E[8] = ptx::addc(E[8], 0u);
+        O[0] = ptx::mad_lo_cc(ak, T[k][1], O[0]);
+        O[1] = ptx::madc_hi_cc(ak, T[k][1], O[1]);
+        O[2] = ptx::madc_lo_cc(ak, T[k][3], O[2]);
+        O[3] = ptx::madc_hi_cc(ak, T[k][3], O[3]);
+        O[4] = ptx::madc_lo_cc(ak, T[k][5], O[4]);
+        O[5] = ptx::madc_hi_cc(ak, T[k][5], O[5]);
+        O[6] = ptx::madc_lo_cc(ak, T[k][7], O[6]);
+        O[7] = ptx::madc_hi_cc(ak, T[k][7], O[7]);
+        O[8] = ptx::addc(O[8], 0u);
+    }
+    uint32_t S[10];
+    S[0] = E[0];
+    S[1] = ptx::add_cc(E[1], O[0]);
+#pragma unroll
+    for (int k = 2; k < 9; ++k) S[k] = ptx::addc_cc(E[k], O[k - 1]);
+    S[9] = ptx::addc(O[8], 0u);
+    // two Montgomery word steps: S <- (S + m p) / 2^32 with m cancelling the low limb
+#pragma unroll
+    for (int st = 0; st < 2; ++st) {
+        uint32_t* V = S + st;
+        const uint32_t m = ptx::mul_lo(V[0], P::INV);
+        V[0] = ptx::mad_lo_cc(P::mod(0), m, V[0]);
+        V[1] = ptx::madc_hi_cc(P::mod(0), m, V[1]);
+        V[2] = ptx::madc_lo_cc(P::mod(2), m, V[2]);
+        V[3] = ptx::madc_hi_cc(P::mod(2), m, V[3]);
+        V[4] = ptx::madc_lo_cc(P::mod(4), m, V[4]);
+        V[5] = ptx::madc_hi_cc(P::mod(4), m, V[5]);
+        V[6] = ptx::madc_lo_cc(P::mod(6), m, V[6]);
+        V[7] = ptx::madc_hi_cc(P::mod(6), m, V[7]);
+        if (st == 0) { V[8] = ptx::addc_cc(V[8], 0u); V[9] = ptx::addc(V[9], 0u); }
+        else V[8] = ptx::addc(V[8], 0u);
+        V[1] = ptx::mad_lo_cc(P::mod(1), m, V[1]);
+        V[2] = ptx::madc_hi_cc(P::mod(1), m, V[2]);
+        V[3] = ptx::madc_lo_cc(P::mod(3), m, V[3]);
+        V[4] = ptx::madc_hi_cc(P::mod(3), m, V[4]);
+        V[5] = ptx::madc_lo_cc(P::mod(5), m, V[5]);
+        V[6] = ptx::madc_hi_cc(P::mod(5), m, V[6]);
+        V[7] = ptx::madc_lo_cc(P::mod(7), m, V[7]);
+        if (st == 0) { V[8] = ptx::madc_hi_cc(P::mod(7), m, V[8]); V[9] = ptx::addc(V[9], 0u); }
+        else V[8] = ptx::madc_hi(P::mod(7), m, V[8]);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] = S[k + 2];
+    cond_sub_mod<P>(r);
+}
+
 // ===================================================================================================
 // Radix-2^29 multiplier.  Measured on B200 (tools/ubench2.cu): IMAD.WIDE.U32 issues at full rate
 // (~18.5 T/s) only WITHOUT a carry predicate; the carry-in/out forms (.X, or carry-out) run at half
@@ -424,6 +500,28 @@ struct alignas(16) fp {
 
 typedef fp<FrP> fr_t;
 typedef fp<FqP> fq_t;
+
+// multiplier table of a per-launch constant (limb::mul_ctab): passed to kernels by value, so the 64 table limbs are
+// constant-bank operands of the multiply-adds and cost no registers
+template <class P>
+struct fp_ctab {
+    uint32_t t[8][8];
+    // T[k] = canonical(r * 2^(32 k + 64)); r in Montgomery form
+    TSG_HD static fp_ctab make(const fp<P>& r) {
+        fp_ctab c;
+        const fp<P> w = fp<P>::from_u64(1ull << 32);
+        fp<P> cur = r * w * w;
+        for (int k = 0; k < 8; ++k) {
+            fp<P> can = cur.from_mont();
+            for (int i = 0; i < 8; ++i) c.t[k][i] = can.l[i];
+            cur = cur * w;
+        }
+        return c;
+    }
+    // a * r (Montgomery form in, Montgomery form out): bit-identical to a * r_mont
+    TSG_HD fp<P> mul(const fp<P>& a) const { fp<P> r; limb::mul_ctab<P>(r.l, a.l, t); return r; }
+};
+typedef fp_ctab<FrP> fr_ctab;
 
 // Lazy accumulator for sums of products of reduced operands (carry-chain form, 512 bits).  Default
 // (see the measurement note at the radix-2^29 multiplier).

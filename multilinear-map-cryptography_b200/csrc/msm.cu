@@ -449,7 +449,8 @@ unsigned msm_window_bits(size_t n) {
 unsigned msm_table_window_bits(size_t n) {
     unsigned lg = 0; while (((size_t)1 << (lg + 1)) <= n) ++lg;
     if (lg < 8) lg = 8;
-    if (lg > 20) lg = 20;
+    if (lg >= 24) return 22;   // 12 windows; 2^21 buckets still hold ~100 entries each
+    if (lg > 20) lg = 20;      // 13 windows (21 would not save one)
     return lg;
 }
 

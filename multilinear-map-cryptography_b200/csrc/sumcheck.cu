@@ -56,6 +56,29 @@ template <> struct EvalAcc<2> {
     }
 };
 
+// d = 2 when the round's claim is known: g(0) + g(1) = claim (the identity SumCheck::prove checks, src/sumcheck.rs:77-84, which
+// holds by construction once round 0 has been checked in full), so only g(0) and g(2) are accumulated: two lazy products per pair.
+struct EvalAcc2Claim {
+    static constexpr int NV = 2;
+    wide_acc<FrP> a0, a2;
+    __device__ __forceinline__ void clear() { a0.clear(); a2.clear(); }
+    __device__ __forceinline__ void pair(const fr_t* lo, const fr_t* hi) {
+        a0.add_product(lo[0], lo[1]);
+        fr_t x = hi[0] + (hi[0] - lo[0]);
+        fr_t y = hi[1] + (hi[1] - lo[1]);
+        a2.add_product(x, y);
+    }
+    __device__ __forceinline__ void finish(fr_t (&v)[NV]) { v[0] = a0.reduce(); v[1] = a2.reduce(); }
+};
+struct EvalClaimEpilogue {
+    fr_t* out4; fr_t claim;
+    __device__ void operator()(fr_t (&v)[2]) const {
+        fr_t g1 = claim - v[0];
+        fr_t d = v[1] - g1;
+        out4[0] = v[0]; out4[1] = g1; out4[2] = v[1]; out4[3] = v[0] + d + d + d;
+    }
+};
+
 // d = 3: cubic; all four points, one Montgomery product + one lazy product per point.
 template <> struct EvalAcc<3> {
     static constexpr int NV = 4;
@@ -102,19 +125,19 @@ __global__ void __launch_bounds__(SC_THREADS, (D <= 2 ? 2 : 1)) k_round_eval(ScT
 }
 
 // ---------------------------------------------------------------- K1: bind (fold) one table in place
-__global__ void __launch_bounds__(SC_THREADS) k_bind(fr_t* t, size_t half, const fr_t r) {
+__global__ void __launch_bounds__(SC_THREADS) k_bind(fr_t* t, size_t half, const fr_ctab r) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < half; p += stride) {
         fr_t lo = ld256_stream(t + p), hi = ld256_stream(t + p + half);
-        st256(t + p, lo + r * (hi - lo));
+        st256(t + p, lo + r.mul(hi - lo));
     }
 }
 // out-of-place variant (keeps the source table intact; used by partial_evaluate on borrowed tables)
-__global__ void __launch_bounds__(SC_THREADS) k_bind_to(const fr_t* t, fr_t* out, size_t half, const fr_t r) {
+__global__ void __launch_bounds__(SC_THREADS) k_bind_to(const fr_t* t, fr_t* out, size_t half, const fr_ctab r) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < half; p += stride) {
         fr_t lo = ld256_nc(t + p), hi = ld256_nc(t + p + half);
-        st256(out + p, lo + r * (hi - lo));
+        st256(out + p, lo + r.mul(hi - lo));
     }
 }
 
@@ -122,7 +145,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_bind_to(const fr_t* t, fr_t* out
 // Thread p < quarter owns positions p, p+q, p+2q, p+3q of each table: top position bit = variable k
 // (bound now), next bit = variable k+1 (evaluated now).  Writes the bound table to positions [0, 2q).
 template <int D>
-__global__ void __launch_bounds__(SC_THREADS, (D <= 2 ? 2 : 1)) k_bind_eval(ScTables tabs, size_t quarter, const fr_t r, fr_t* partials,
+__global__ void __launch_bounds__(SC_THREADS, (D <= 2 ? 2 : 1)) k_bind_eval(ScTables tabs, size_t quarter, const fr_ctab r, fr_t* partials,
                                                           unsigned int* ticket, fr_t* out4) {
     __shared__ fr_t smem[EvalAcc<D>::NV * 32];
     EvalAcc<D> acc; acc.clear();
@@ -134,8 +157,8 @@ __global__ void __launch_bounds__(SC_THREADS, (D <= 2 ? 2 : 1)) k_bind_eval(ScTa
             fr_t* base = tabs.t[t];
             fr_t a0 = ld256_stream(base + p), a1 = ld256_stream(base + p + quarter);
             fr_t b0 = ld256_stream(base + p + 2 * quarter), b1 = ld256_stream(base + p + 3 * quarter);
-            lo[t] = a0 + r * (b0 - a0);
-            hi[t] = a1 + r * (b1 - a1);
+            lo[t] = a0 + r.mul(b0 - a0);
+            hi[t] = a1 + r.mul(b1 - a1);
             st256(base + p, lo[t]);
             st256(base + p + quarter, hi[t]);
         }
@@ -146,6 +169,31 @@ __global__ void __launch_bounds__(SC_THREADS, (D <= 2 ? 2 : 1)) k_bind_eval(ScTa
     grid_finish_sum<fr_t, EvalAcc<D>::NV>(v, partials, ticket, smem, EvalEpilogue<D>{out4});
 }
 
+
+// d = 2 with the claim of the round being evaluated (= g_k(r), known to the host before the launch)
+__global__ void __launch_bounds__(SC_THREADS, 2) k_bind_eval2_claim(ScTables tabs, size_t quarter, const fr_ctab r, const fr_t claim, fr_t* partials,
+                                                                   unsigned int* ticket, fr_t* out4) {
+    __shared__ fr_t smem[2 * 32];
+    EvalAcc2Claim acc; acc.clear();
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < quarter; p += stride) {
+        fr_t lo[2], hi[2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            fr_t* base = tabs.t[t];
+            fr_t a0 = ld256_stream(base + p), a1 = ld256_stream(base + p + quarter);
+            fr_t b0 = ld256_stream(base + p + 2 * quarter), b1 = ld256_stream(base + p + 3 * quarter);
+            lo[t] = a0 + r.mul(b0 - a0);
+            hi[t] = a1 + r.mul(b1 - a1);
+            st256(base + p, lo[t]);
+            st256(base + p + quarter, hi[t]);
+        }
+        acc.pair(lo, hi);
+    }
+    fr_t v[2];
+    acc.finish(v);
+    grid_finish_sum<fr_t, 2>(v, partials, ticket, smem, EvalClaimEpilogue{out4, claim});
+}
 
 // ==================================================================================================
 // TMA-pipelined variants for large tables (work a multiple of TMA_THREADS).  Same arithmetic as the
@@ -175,7 +223,7 @@ __global__ void __launch_bounds__(TMA_THREADS, (D <= 2 ? TMA_MINBLOCKS : 1)) k_r
     grid_finish_sum<fr_t, EvalAcc<D>::NV>(v, partials, ticket, smem, EvalEpilogue<D>{out4});
 }
 
-__global__ void __launch_bounds__(TMA_THREADS, 4) k_bind_tma(fr_t* t, size_t half, const fr_t r) {
+__global__ void __launch_bounds__(TMA_THREADS, 4) k_bind_tma(fr_t* t, size_t half, const fr_ctab r) {
     extern __shared__ unsigned char smem_raw[];
     typedef tma::Pipeline<2, TMA_THREADS, TMA_STAGES> Pipe;
     Pipe pipe;
@@ -184,12 +232,12 @@ __global__ void __launch_bounds__(TMA_THREADS, 4) k_bind_tma(fr_t* t, size_t hal
     for (size_t k = 0; k < pipe.my_tiles; ++k) {
         fr_t e[2];
         pipe.fetch(k, e);
-        st256(t + pipe.tile_of(k) * TMA_THREADS + threadIdx.x, e[0] + r * (e[1] - e[0]));
+        st256(t + pipe.tile_of(k) * TMA_THREADS + threadIdx.x, e[0] + r.mul(e[1] - e[0]));
     }
 }
 
 template <int D>
-__global__ void __launch_bounds__(TMA_THREADS, (D <= 2 ? TMA_MINBLOCKS : 1)) k_bind_eval_tma(ScTables tabs, size_t quarter, const fr_t r, fr_t* partials,
+__global__ void __launch_bounds__(TMA_THREADS, (D <= 2 ? TMA_MINBLOCKS : 1)) k_bind_eval_tma(ScTables tabs, size_t quarter, const fr_ctab r, fr_t* partials,
                                                                   unsigned int* ticket, fr_t* out4) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ fr_t smem[EvalAcc<D>::NV * 32];
@@ -210,8 +258,8 @@ __global__ void __launch_bounds__(TMA_THREADS, (D <= 2 ? TMA_MINBLOCKS : 1)) k_b
         fr_t lo[D], hi[D];
 #pragma unroll
         for (int t = 0; t < D; ++t) {
-            lo[t] = e[4 * t + 0] + r * (e[4 * t + 2] - e[4 * t + 0]);
-            hi[t] = e[4 * t + 1] + r * (e[4 * t + 3] - e[4 * t + 1]);
+            lo[t] = e[4 * t + 0] + r.mul(e[4 * t + 2] - e[4 * t + 0]);
+            hi[t] = e[4 * t + 1] + r.mul(e[4 * t + 3] - e[4 * t + 1]);
             st256(tabs.t[t] + p, lo[t]);
             st256(tabs.t[t] + p + quarter, hi[t]);
         }
@@ -273,7 +321,8 @@ cudaError_t launch_round_eval(int d, const ScTables& tabs, size_t n, fr_t* parti
     return cudaGetLastError();
 }
 
-cudaError_t launch_bind(fr_t* t, size_t n, const fr_t& r, int sm_count, cudaStream_t s) {
+cudaError_t launch_bind(fr_t* t, size_t n, const fr_t& r_elem, int sm_count, cudaStream_t s) {
+    const fr_ctab r = fr_ctab::make(r_elem);   // T[k] = r 2^(32k+64) mod p: the fold multiplies by this one constant
     size_t half = n / 2;
     if (half >= g_tma_min_work) {
         size_t sm = tma::Pipeline<2, TMA_THREADS, TMA_STAGES>::SMEM_BYTES;
@@ -287,16 +336,22 @@ cudaError_t launch_bind(fr_t* t, size_t n, const fr_t& r, int sm_count, cudaStre
     return cudaGetLastError();
 }
 
-cudaError_t launch_bind_to(const fr_t* t, fr_t* out, size_t n, const fr_t& r, int sm_count, cudaStream_t s) {
+cudaError_t launch_bind_to(const fr_t* t, fr_t* out, size_t n, const fr_t& r_elem, int sm_count, cudaStream_t s) {
+    const fr_ctab r = fr_ctab::make(r_elem);
     size_t half = n / 2;
     int grid = sc_grid(half, sm_count, SC_BLOCKS_PER_SM_BIND);
     k_bind_to<<<grid, SC_THREADS, 0, s>>>(t, out, half, r);
     return cudaGetLastError();
 }
 
-cudaError_t launch_bind_eval(int d, const ScTables& tabs, size_t n, const fr_t& r, fr_t* partials, unsigned int* ticket,
+cudaError_t launch_bind_eval(int d, const ScTables& tabs, size_t n, const fr_t& r_elem, const fr_t* claim, fr_t* partials, unsigned int* ticket,
                              fr_t* out4, int sm_count, cudaStream_t s) {
+    const fr_ctab r = fr_ctab::make(r_elem);
     size_t quarter = n / 4;
+    if (claim && d == 2 && quarter < g_tma_min_work) {
+        k_bind_eval2_claim<<<sc_grid(quarter, sm_count, SC_BLOCKS_PER_SM), SC_THREADS, 0, s>>>(tabs, quarter, r, *claim, partials, ticket, out4);
+        return cudaGetLastError();
+    }
     if (quarter >= g_tma_min_work) {
         size_t tiles = quarter / TMA_THREADS;
         int g = tma_grid(tiles, sm_count, TMA_MINBLOCKS);

@@ -36,7 +36,8 @@ cudaError_t launch_round_eval(int d, const ScTables& tabs, size_t n, fr_t* parti
                               int sm_count, cudaStream_t s);
 cudaError_t launch_bind(fr_t* t, size_t n, const fr_t& r, int sm_count, cudaStream_t s);
 cudaError_t launch_bind_to(const fr_t* t, fr_t* out, size_t n, const fr_t& r, int sm_count, cudaStream_t s);
-cudaError_t launch_bind_eval(int d, const ScTables& tabs, size_t n, const fr_t& r, fr_t* partials, unsigned int* ticket,
+// claim (optional): the value g(0) + g(1) of the round being evaluated must have; with it the d = 2 kernel derives g(1) instead of summing it
+cudaError_t launch_bind_eval(int d, const ScTables& tabs, size_t n, const fr_t& r, const fr_t* claim, fr_t* partials, unsigned int* ticket,
                              fr_t* out4, int sm_count, cudaStream_t s);
 
 }  // namespace tsg

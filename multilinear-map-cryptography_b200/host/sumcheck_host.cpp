@@ -9,7 +9,8 @@ namespace host {
 void interpolate4(const fr_t e[4], fr_t c[4]) {
     // forward differences on x = 0,1,2,3, then Newton -> monomial:
     //   P = e0 + D1 x + D2 x(x-1)/2 + D3 x(x-1)(x-2)/6
-    const fr_t inv2 = fr_t::from_u64(2).inverse(), inv3 = fr_t::from_u64(3).inverse(), inv6 = inv2 * inv3;
+    // constants once per process: the host runs the device limb code with an emulated carry flag, where a Fermat inverse costs ~0.1 ms
+    static const fr_t inv2 = fr_t::from_u64(2).inverse(), inv3 = fr_t::from_u64(3).inverse(), inv6 = inv2 * inv3;
     fr_t d1 = e[1] - e[0];
     fr_t d2 = e[2] - e[1] - e[1] + e[0];
     fr_t d3 = e[3] - e[2] - e[2] - e[2] + e[1] + e[1] + e[1] - e[0];
@@ -52,7 +53,8 @@ int sumcheck_prove_product(tsgpu_ctx* ctx, tsgpu_table* const* tables, int d, co
         if (challenges) challenges->push_back(r);
         current = horner_eval(coeffs, 4, r);
         tsgpu_fr rr; to_abi(r, &rr);
-        if (round + 1 < num_vars) rc = tsgpu_sc_bind_eval(sc, &rr, ev);   // fused bind + next round
+        tsgpu_fr cur; to_abi(current, &cur);
+        if (round + 1 < num_vars) rc = tsgpu_sc_bind_eval_claim(sc, &rr, &cur, ev);   // fused bind + next round; its g(0) + g(1) is `current`
         else rc = tsgpu_sc_bind(sc, &rr);
         if (rc) goto cuda_fail;
     }

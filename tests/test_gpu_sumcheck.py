@@ -160,3 +160,31 @@ def test_reference_integration_x1_times_x2(ctx, tsgpu, oracle):
     proof = sc.prove_product(ctx, [ctx.table_upload(A), ctx.table_upload(B)], tsgpu.Transcript(bytes([42]) * 32))
     ok, _ = sc.verify(proof, tsgpu.Transcript(bytes([42]) * 32))
     assert ok
+
+
+@pytest.mark.parametrize("nv", [2, 3, 7, 12, 17])
+def test_bind_eval_with_claim_returns_the_same_four_values(ctx, oracle, nv):
+    """tsgpu_sc_bind_eval_claim derives g(1) = claim - g(0): with the true claim g_k(r) the four evaluations equal the fully summed ones"""
+    A = oracle.chacha_fr_rand(seed_bytes(nv + 40), 1 << nv).reshape(-1, 4)
+    B = oracle.chacha_fr_rand(seed_bytes(nv + 41), 1 << nv).reshape(-1, 4)
+    rs = oracle.chacha_fr_rand(seed_bytes(nv + 42), nv).reshape(-1, 4)
+    full = ctx.sumcheck([ctx.table_upload(A), ctx.table_upload(B)])
+    fast = ctx.sumcheck([ctx.table_upload(A), ctx.table_upload(B)])
+    ev = full.round_eval()
+    assert (fast.round_eval() == ev).all()
+    for k in range(nv - 1):
+        # claim of the next round = g_k(r_k): Lagrange evaluation of the cubic through ev at r_k, done by the oracle's field ops
+        c = ints = oracle.fr_to_ints(ev)
+        r = oracle.fr_to_ints(rs[k:k + 1])[0]
+        P = oracle.R_MOD
+        g = 0
+        for i in range(4):
+            num, den = 1, 1
+            for j in range(4):
+                if j != i:
+                    num = num * (r - j) % P; den = den * (i - j) % P
+            g = (g + ints[i] * num * pow(den, -1, P)) % P
+        claim = oracle.fr_from_ints([g])
+        ev = full.bind_eval(rs[k:k + 1])
+        got = fast.bind_eval(rs[k:k + 1], claim=claim)
+        assert (got == ev).all(), (nv, k)

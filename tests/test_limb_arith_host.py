@@ -45,7 +45,8 @@ def test_add_sub_mul_match_oracle(harness, oracle, field):
     a = oracle.ints_to_limbs(xs); b = oracle.ints_to_limbs(ys); n = len(xs)
     f = 0 if field == "fr" else 1
     # op 2: product path the kernels use; op 3: carry-chain wide product + normalise + reduce; op 8: carry-chain product; op 9: radix-2^29 product
-    for op, name in ((0, "add"), (1, "sub"), (2, "mul"), (3, "mul"), (8, "mul"), (9, "mul")):
+    # op 10: multiplication through the per-launch constant table (sum-check fold)
+    for op, name in ((0, "add"), (1, "sub"), (2, "mul"), (3, "mul"), (8, "mul"), (9, "mul"), (10, "mul")):
         out = np.empty_like(a)
         harness.limb_binop(f, op, _p(a), _p(b), C.c_size_t(n), _p(out))
         assert (out == oracle.field_binop(field, name, a, b)).all(), (field, op)

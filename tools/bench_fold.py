@@ -44,11 +44,13 @@ ms = timeit(lambda sc: sc.round_eval(), mk)
 res["eval2_ms"] = ms; res["eval2_gbs"] = 64.0 * N / (ms * 1e-3) / 1e9
 ms = timeit(lambda sc: sc.bind_eval(r), mk)
 res["bind_eval2_ms"] = ms; res["bind_eval2_gbs"] = 96.0 * N / (ms * 1e-3) / 1e9
+ms = timeit(lambda sc: sc.bind_eval(r, claim=r), mk)     # timing only: any claim value costs the same
+res["bind_eval2_claim_ms"] = ms; res["bind_eval2_claim_gbs"] = 96.0 * N / (ms * 1e-3) / 1e9
 # full sum-check d=2 with random challenges (no transcript) - device time only
 def full(sc):
     sc.round_eval()
     while sc.vars_left > 1:
-        sc.bind_eval(r)
+        sc.bind_eval(r, claim=r)
     sc.bind(r)
 ms = timeit(full, mk, reps=3)
 res["sumcheck2_ms"] = ms; res["sumcheck2_gbs"] = 256.0 * N / (ms * 1e-3) / 1e9
