@@ -184,6 +184,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line (NCCL_DEBUG=VERSION prints to stdout otherwise)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ts = importlib.import_module(PKG)
     stream = torch.cuda.Stream()

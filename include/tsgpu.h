@@ -224,6 +224,24 @@ void tsgpu_fr_add(const tsgpu_fr* a, const tsgpu_fr* b, tsgpu_fr* out);
 void tsgpu_fr_mul(const tsgpu_fr* a, const tsgpu_fr* b, tsgpu_fr* out);
 void tsgpu_fr_from_limb_sums(const uint64_t* sums, size_t n, tsgpu_fr* out);
 
+/* ---- multi-GPU: one process per GPU, one NCCL communicator per context ---------------------------------
+ * The host program moves the 128-byte unique id from rank 0 to every rank (torch.distributed, MPI, a file ...).  NCCL is
+ * loaded at run time; a single rank needs neither NCCL nor an id.  The number of ranks must be a power of two. */
+int tsgpu_comm_unique_id(uint8_t out[128]);
+int tsgpu_comm_init(tsgpu_ctx* ctx, int nranks, int rank, const uint8_t id[128]);
+int tsgpu_comm_size(const tsgpu_ctx* ctx);
+int tsgpu_comm_rank(const tsgpu_ctx* ctx);
+void tsgpu_comm_destroy(tsgpu_ctx* ctx);
+/* all-gather of `bytes` (multiple of 8) per rank, host to host: e.g. per-rank partial MSM results (point-sliced commitment),
+ * which the caller adds with tsgpu_g1_add */
+int tsgpu_comm_allgather(tsgpu_ctx* ctx, const void* in, size_t bytes, void* out);
+/* SumCheck::prove for a product of tables (src/sumcheck.rs:56-110) with the hypercube sliced over the ranks: `tables` are this
+ * rank's slices (reference index high bits = rank; num_vars - log2(ranks) variables; consumed).  One 256-byte integer
+ * all-reduce of the round evaluations per round; every rank returns the same proof.  Outputs as tsgpu_sumcheck_prove_product. */
+int tsgpu_sumcheck_prove_product_sharded(tsgpu_ctx* ctx, tsgpu_table* const* tables, int d, unsigned num_vars, const tsgpu_fr* claimed_sum,
+                                         tsgpu_transcript* transcript, tsgpu_fr* round_polys, tsgpu_fr* final_evaluation,
+                                         tsgpu_fr* challenges, tsgpu_fr* table_finals);
+
 /* ---- setup_params, Twist::prove / verify, Shout::prove / verify  (host orchestration over the calls above) --
  * setup_params(log_size) (src/utils.rs:79-131): max_operations = 4 * 2^log_size, tau = first Fr::rand of
  * ChaCha20Rng::from_seed([42; 32]), g1_powers[0 ..= max_operations] generated on the device, 32-byte

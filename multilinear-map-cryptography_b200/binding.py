@@ -127,6 +127,36 @@ class Context:
     def sm_count(self) -> int:
         return int(lib().tsgpu_sm_count(self._h))
 
+    # ---- multi-GPU: one process per GPU, NCCL communicator inside the library (csrc/comm.cu)
+    def comm_init(self, nranks: int, rank: int, unique_id: Optional[bytes] = None):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id) if unique_id is not None else None
+        self.check(lib().tsgpu_comm_init(self._h, C.c_int(nranks), C.c_int(rank), buf))
+
+    def comm_init_torch(self, group=None):
+        """create the library communicator over the ranks of an initialised torch.distributed group: rank 0 draws the
+        NCCL unique id, torch.distributed (any backend) carries its 128 bytes to the other ranks"""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        ids = [unique_id() if rank == 0 and world > 1 else None]
+        if world > 1:
+            dist.broadcast_object_list(ids, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        self.comm_init(world, rank, ids[0])
+
+    @property
+    def comm_size(self) -> int:
+        return int(lib().tsgpu_comm_size(self._h))
+
+    @property
+    def comm_rank(self) -> int:
+        return int(lib().tsgpu_comm_rank(self._h))
+
+    def comm_allgather(self, x: np.ndarray) -> np.ndarray:
+        """(m,) uint64 per rank -> (ranks, m) on every rank"""
+        x = np.ascontiguousarray(x, dtype=np.uint64).reshape(-1)
+        out = np.empty((self.comm_size, x.shape[0]), dtype=np.uint64)
+        self.check(lib().tsgpu_comm_allgather(self._h, _p(x), C.c_size_t(x.nbytes), _p(out)))
+        return out
+
     def counter(self, name: str) -> int:
         """work counters: launches, msm_calls, msm_points, msm_entries"""
         return int(lib().tsgpu_counter_read(self._h, name.encode()))
@@ -420,6 +450,21 @@ class SumCheck:
         proof = SumCheckProof(rp[:nv], fe)
         return (proof, ch[:nv], fin) if return_aux else proof
 
+    def prove_product_sharded(self, ctx: Context, local_tables: Sequence[Table], transcript: Transcript, return_aux: bool = False):
+        """same proof with the hypercube sliced over the ranks of ctx's communicator (ctx.comm_init*): `local_tables` are this
+        rank's slices (high index bits = rank), num_vars - log2(ranks) variables each; one 256-byte all-reduce per round"""
+        tables = list(local_tables)
+        nv, d = self.num_vars, len(tables)
+        arr = (C.c_void_p * d)(*[t._h for t in tables])
+        rp = np.zeros((max(nv, 1), 4, 4), dtype=np.uint64)
+        fe = np.zeros(4, dtype=np.uint64)
+        ch = np.zeros((max(nv, 1), 4), dtype=np.uint64)
+        fin = np.zeros((d, 4), dtype=np.uint64)
+        ctx.check(lib().tsgpu_sumcheck_prove_product_sharded(ctx._h, arr, C.c_int(d), C.c_uint(nv), _p(self.claimed_sum), transcript._h,
+                                                             _p(rp), _p(fe), _p(ch), _p(fin)))
+        proof = SumCheckProof(rp[:nv], fe)
+        return (proof, ch[:nv], fin) if return_aux else proof
+
     def verify(self, proof: SumCheckProof, transcript: Transcript):
         """-> (is_valid, challenges); raises SumCheck("Proof has wrong number of rounds") like sumcheck.rs:118-122"""
         rp = np.ascontiguousarray(proof.round_polynomials, dtype=np.uint64).reshape(-1, 4, 4)
@@ -557,6 +602,14 @@ class KZGCommitment:
         point = _fr(point, 1)
         ctx.check(lib().tsgpu_kzg_open_values_dev(ctx._h, params._h, values._h, _p(point), _p(value), _p(proof)))
         return value, proof
+
+
+def unique_id() -> bytes:
+    """ncclGetUniqueId (to be created on rank 0 and handed to every rank's Context.comm_init)"""
+    buf = (C.c_uint8 * 128)()
+    if lib().tsgpu_comm_unique_id(buf):
+        raise RuntimeError("NCCL is not available: cannot create a communicator id")
+    return bytes(buf)
 
 
 def g1_hash(point) -> np.ndarray:

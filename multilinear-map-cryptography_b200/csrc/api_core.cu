@@ -112,6 +112,7 @@ void tsgpu_destroy(tsgpu_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    tsgpu_comm_destroy(ctx);
     interp_destroy(ctx);
     for (int i = 0; i < tsgpu_ctx::ARENA_COUNT; ++i) if (ctx->arena[i]) cudaFree(ctx->arena[i]);
     if (ctx->partials) cudaFree(ctx->partials);

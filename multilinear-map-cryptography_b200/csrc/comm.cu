@@ -1,0 +1,273 @@
+// comm.cu - one-process-per-GPU sharding of the sum-check inside the library: an NCCL communicator per
+// context and the sharded form of SumCheck::prove (src/sumcheck.rs:56-110) for products of MLE tables.
+//
+// Rank g owns the slice of every table whose reference index has high bits g.  The rounds over the local variables run
+// the same kernels as the single-GPU path; after each round kernel the four partial evaluations are widened to 32
+// zero-extended 64-bit limbs on the device, summed over the ranks with ONE ncclAllReduce (ncclUint64 / ncclSum: an integer
+// sum is exact, a modular one is not an NCCL reduction) on the context stream, copied to the host (256 bytes), carried and
+// reduced mod r.  Every rank feeds the same transcript and draws the same challenge.  With one entry per table left per
+// rank the G x d values are all-gathered and the last log2 G rounds are finished on every host.
+//
+// NCCL is bound at run time (dlopen "libnccl.so.2"): single-GPU users do not need it, and in a torch process the already
+// loaded NCCL is the one used.  The host exchanges the 128-byte unique id however it likes (torch.distributed, MPI, a file).
+#include <dlfcn.h>
+#include <nccl.h>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "context.cuh"
+#include "fr_device.cuh"
+#include "sumcheck.cuh"
+#include "../host/field64.hpp"
+#include "../host/sumcheck_host.hpp"
+#include "../host/transcript.hpp"
+
+using namespace tsg;
+using namespace tsg::host;
+
+namespace {
+
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    std::string err;
+    bool load() {
+        if (handle) return true;
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+            handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (handle) break;
+        }
+        if (!handle) { err = std::string("cannot load NCCL: ") + dlerror(); return false; }
+        auto sym = [&](const char* n) { void* p = dlsym(handle, n); if (!p) err = std::string("NCCL symbol missing: ") + n; return p; };
+        GetUniqueId = (decltype(GetUniqueId))sym("ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))sym("ncclCommInitRank");
+        CommDestroy = (decltype(CommDestroy))sym("ncclCommDestroy");
+        AllReduce = (decltype(AllReduce))sym("ncclAllReduce");
+        AllGather = (decltype(AllGather))sym("ncclAllGather");
+        GetErrorString = (decltype(GetErrorString))sym("ncclGetErrorString");
+        if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce || !AllGather || !GetErrorString) { dlclose(handle); handle = nullptr; return false; }
+        return true;
+    }
+};
+NcclApi& nccl() { static NcclApi api; return api; }
+
+struct Comm {
+    ncclComm_t comm = nullptr;
+    int nranks = 1, rank = 0;
+    unsigned long long* dev = nullptr;     // 32 limb sums, then gather staging: nranks * 3 field elements
+    unsigned long long* host = nullptr;    // pinned mirror
+    size_t words = 0;
+};
+
+int nccl_fail(tsgpu_ctx* ctx, ncclResult_t r, const char* what) {
+    return fail(ctx, TSGPU_E_PROOF_GENERATION, std::string(what) + ": " + (nccl().GetErrorString ? nccl().GetErrorString(r) : "NCCL error"));
+}
+#define TSG_NCCL(ctx, call)                                              \
+    do {                                                                 \
+        ncclResult_t _r = (call);                                        \
+        if (_r != ncclSuccess) return nccl_fail((ctx), _r, #call);       \
+    } while (0)
+
+// limbs[8 e + i] = (u64) limb i of element e
+__global__ void k_fr_to_limb_sums(const fr_t* in, unsigned n, unsigned long long* limbs) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < 8 * n) limbs[t] = in[t >> 3].l[t & 7];
+}
+
+Comm* comm_of(tsgpu_ctx* ctx) { return (Comm*)ctx->comm; }
+
+// exact field sum over the ranks of `n` (<= 4) elements at ctx->dev_out; result to `out` on the host of every rank
+int allreduce_dev_out(tsgpu_ctx* ctx, unsigned n, fr_t* out) {
+    Comm* c = comm_of(ctx);
+    if (!c || c->nranks == 1) {
+        TSG_CUDA(ctx, cudaMemcpyAsync(ctx->host_out, ctx->dev_out, n * sizeof(fr_t), cudaMemcpyDeviceToHost, ctx->stream));
+        TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        memcpy(out, ctx->host_out, n * sizeof(fr_t));
+        return TSGPU_OK;
+    }
+    k_fr_to_limb_sums<<<1, 32, 0, ctx->stream>>>(ctx->dev_out, n, c->dev);
+    ctx->launches += 1;
+    TSG_NCCL(ctx, nccl().AllReduce(c->dev, c->dev, 8 * n, ncclUint64, ncclSum, c->comm, ctx->stream));
+    TSG_CUDA(ctx, cudaMemcpyAsync(c->host, c->dev, 8 * n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    tsgpu_fr tmp[4];
+    tsgpu_fr_from_limb_sums((const uint64_t*)c->host, n, tmp);
+    memcpy(out, tmp, n * sizeof(fr_t));
+    return TSGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+// rank 0 creates the id; the host program hands the 128 bytes to every rank
+int tsgpu_comm_unique_id(uint8_t out[128]) {
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    if (!out || !nccl().load()) return TSGPU_E_PROOF_GENERATION;
+    ncclUniqueId id;
+    if (nccl().GetUniqueId(&id) != ncclSuccess) return TSGPU_E_PROOF_GENERATION;
+    memcpy(out, &id, 128);
+    return TSGPU_OK;
+}
+
+int tsgpu_comm_init(tsgpu_ctx* ctx, int nranks, int rank, const uint8_t id[128]) {
+    if (!ctx || nranks < 1 || rank < 0 || rank >= nranks || (nranks > 1 && !id)) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "bad communicator arguments");
+    if (nranks & (nranks - 1)) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "number of ranks must be a power of two");
+    if (ctx->comm) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "communicator already initialised");
+    Comm* c = new (std::nothrow) Comm;
+    if (!c) return fail(ctx, TSGPU_E_PROOF_GENERATION, "out of host memory");
+    c->nranks = nranks; c->rank = rank;
+    c->words = 32 + (size_t)nranks * 3 * 4 + 16;
+    if (nranks > 1) {
+        if (!nccl().load()) { delete c; return fail(ctx, TSGPU_E_PROOF_GENERATION, nccl().err); }
+        ncclUniqueId uid; memcpy(&uid, id, 128);
+        cudaSetDevice(ctx->device);
+        ncclResult_t r = nccl().CommInitRank(&c->comm, nranks, uid, rank);
+        if (r != ncclSuccess) { delete c; return nccl_fail(ctx, r, "ncclCommInitRank"); }
+    }
+    if (cudaMalloc((void**)&c->dev, c->words * 8) != cudaSuccess || cudaMallocHost((void**)&c->host, c->words * 8) != cudaSuccess) {
+        cudaGetLastError();
+        if (c->comm) nccl().CommDestroy(c->comm);
+        if (c->dev) cudaFree(c->dev);
+        delete c;
+        return fail(ctx, TSGPU_E_PROOF_GENERATION, "communicator buffers");
+    }
+    ctx->comm = c;
+    return TSGPU_OK;
+}
+int tsgpu_comm_size(const tsgpu_ctx* ctx) { return ctx && ctx->comm ? ((Comm*)ctx->comm)->nranks : 1; }
+int tsgpu_comm_rank(const tsgpu_ctx* ctx) { return ctx && ctx->comm ? ((Comm*)ctx->comm)->rank : 0; }
+void tsgpu_comm_destroy(tsgpu_ctx* ctx) {
+    if (!ctx || !ctx->comm) return;
+    Comm* c = (Comm*)ctx->comm;
+    cudaStreamSynchronize(ctx->stream);
+    if (c->comm) nccl().CommDestroy(c->comm);
+    if (c->dev) cudaFree(c->dev);
+    if (c->host) cudaFreeHost(c->host);
+    delete c;
+    ctx->comm = nullptr;
+}
+
+// all-gather of `bytes` (a multiple of 8, at most 96 * 4) per rank from and to host memory: partial MSM results (one G1Projective per
+// rank, summed by the caller with tsgpu_g1_add - group addition is not an NCCL reduction)
+int tsgpu_comm_allgather(tsgpu_ctx* ctx, const void* in, size_t bytes, void* out) {
+    if (!ctx || !in || !out || bytes % 8) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "bad all-gather arguments");
+    Comm* c = comm_of(ctx);
+    if (!c || c->nranks == 1) { memcpy(out, in, bytes); return TSGPU_OK; }
+    const size_t w = bytes / 8;
+    TempBuf s, r;
+    TSG_CUDA(ctx, s.alloc(bytes, ctx->stream));
+    TSG_CUDA(ctx, r.alloc(bytes * c->nranks, ctx->stream));
+    TSG_CUDA(ctx, cudaMemcpyAsync(s.p, in, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    TSG_NCCL(ctx, nccl().AllGather(s.p, r.p, w, ncclUint64, c->comm, ctx->stream));
+    TSG_CUDA(ctx, cudaMemcpyAsync(out, r.p, bytes * c->nranks, cudaMemcpyDeviceToHost, ctx->stream));
+    TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return TSGPU_OK;
+}
+
+// SumCheck::new(num_vars, claimed_sum).prove(|v| prod_t mle_t.evaluate(v), transcript) with the hypercube sliced over the ranks of
+// the context's communicator.  tables: this rank's slices (num_vars - log2 G variables each, consumed).  Every rank returns the same
+// round polynomials (num_vars x 4), final evaluation, challenges (num_vars) and fully bound table values (d).
+int tsgpu_sumcheck_prove_product_sharded(tsgpu_ctx* ctx, tsgpu_table* const* tables, int d, unsigned num_vars, const tsgpu_fr* claimed_sum,
+                                         tsgpu_transcript* transcript, tsgpu_fr* round_polys, tsgpu_fr* final_evaluation,
+                                         tsgpu_fr* challenges, tsgpu_fr* table_finals) {
+    if (!ctx || !tables || !claimed_sum || !transcript || !round_polys || !final_evaluation) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    if (d < 1 || d > SC_MAX_TABLES) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "sum-check supports products of 1..3 tables");
+    Comm* c = comm_of(ctx);
+    const int G = c ? c->nranks : 1;
+    unsigned logG = 0; while ((1 << logG) < G) ++logG;
+    if (num_vars < logG) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "more ranks than table entries");
+    const unsigned n_local = num_vars - logG;
+    for (int t = 0; t < d; ++t)
+        if (!tables[t] || tables[t]->num_vars != n_local) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "Number of variables must match");
+    Transcript& tr = *tsgpu_transcript_inner(transcript);
+    ScTables tabs; for (int i = 0; i < SC_MAX_TABLES; ++i) tabs.t[i] = i < d ? tables[i]->d : nullptr;
+    fr_t current; memcpy(current.l, claimed_sum->l, 32);
+    std::vector<fr_t> chal;
+    auto absorb = [&](unsigned round, const fr_t e[4], fr_t* r_out) -> int {
+        fr_t coeffs[4];
+        interpolate4(e, coeffs);
+        fr_t g0 = horner_eval(coeffs, 4, fr_t::zero()), g1 = horner_eval(coeffs, 4, fr_t::one());
+        if (g0 + g1 != current) return fail(ctx, TSGPU_E_SUMCHECK, "Round " + std::to_string(round) + " consistency check failed");   // sumcheck.rs:77-84
+        for (int k = 0; k < 4; ++k) memcpy(round_polys[4 * round + k].l, coeffs[k].l, 32);
+        tr.append_field_elements("sumcheck_round_" + std::to_string(round), coeffs, 4);
+        fr_t r = tr.challenge_field_element("sumcheck_challenge_" + std::to_string(round));
+        chal.push_back(r);
+        current = horner_eval(coeffs, 4, r);
+        *r_out = r;
+        return TSGPU_OK;
+    };
+    int rc;
+    // ---- rounds over the local variables
+    fr_t ev[4];
+    if (n_local) {
+        TSG_CUDA(ctx, launch_round_eval(d, tabs, (size_t)1 << n_local, ctx->partials, ctx->ticket, ctx->dev_out, ctx->sm_count, ctx->stream));
+        ctx->launches += 1;
+        if ((rc = allreduce_dev_out(ctx, 4, ev))) return rc;
+    }
+    for (unsigned round = 0; round < n_local; ++round) {
+        fr_t r;
+        if ((rc = absorb(round, ev, &r))) return rc;
+        const size_t n = (size_t)1 << (n_local - round);
+        if (round + 1 < n_local) {
+            // d = 2: the kernel sums g(0) and g(2) only (claim form with claim 0 leaves g(1) slot = -g(0), unused); g(1) follows from
+            // the GLOBAL claim after the all-reduce: g(1) = current - g(0), g(3) = g(0) - 3 g(1) + 3 g(2)
+            const fr_t zero = fr_t::zero();
+            TSG_CUDA(ctx, launch_bind_eval(d, tabs, n, r, d == 2 ? &zero : nullptr, ctx->partials, ctx->ticket, ctx->dev_out, ctx->sm_count, ctx->stream));
+            ctx->launches += 1;
+            if ((rc = allreduce_dev_out(ctx, 4, ev))) return rc;
+            if (d == 2) {
+                ev[1] = current - ev[0];
+                fr_t dd = ev[2] - ev[1];
+                ev[3] = ev[0] + dd + dd + dd;
+            }
+        } else {
+            for (int t = 0; t < d; ++t) { TSG_CUDA(ctx, launch_bind(tables[t]->d, n, r, ctx->sm_count, ctx->stream)); ctx->launches += 1; }
+        }
+        for (int t = 0; t < d; ++t) tables[t]->num_vars -= 1;
+    }
+    // ---- one entry per table per rank: gather (rank = high index bits) and finish the last log2 G rounds on every host
+    std::vector<fr_t> tail((size_t)G * d);
+    {
+        std::vector<fr_t> mine((size_t)d);
+        for (int t = 0; t < d; ++t) TSG_CUDA(ctx, cudaMemcpyAsync(ctx->dev_out + t, tables[t]->d, sizeof(fr_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        TSG_CUDA(ctx, cudaMemcpyAsync(ctx->host_out, ctx->dev_out, d * sizeof(fr_t), cudaMemcpyDeviceToHost, ctx->stream));
+        TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        memcpy(mine.data(), ctx->host_out, d * sizeof(fr_t));
+        if ((rc = tsgpu_comm_allgather(ctx, mine.data(), d * sizeof(fr_t), tail.data()))) return rc;   // tail[g * d + t]
+    }
+    std::vector<std::vector<fr_t>> T((size_t)d, std::vector<fr_t>((size_t)G));
+    for (int g = 0; g < G; ++g) for (int t = 0; t < d; ++t) T[t][g] = tail[(size_t)g * d + t];
+    size_t len = (size_t)G;
+    for (unsigned k = 0; k < logG; ++k) {
+        // round over variable n_local + k = bit k of the rank index: pairs (2 j, 2 j + 1) in natural order
+        fr_t e[4] = {fr_t::zero(), fr_t::zero(), fr_t::zero(), fr_t::zero()};
+        for (size_t j = 0; j < len / 2; ++j) {
+            fr_t v[SC_MAX_TABLES], dlt[SC_MAX_TABLES];
+            for (int t = 0; t < d; ++t) { v[t] = T[t][2 * j]; dlt[t] = T[t][2 * j + 1] - T[t][2 * j]; }
+            for (int x = 0; x < 4; ++x) {
+                fr_t p = v[0];
+                for (int t = 1; t < d; ++t) p = p * v[t];
+                e[x] = e[x] + p;
+                for (int t = 0; t < d; ++t) v[t] = v[t] + dlt[t];
+            }
+        }
+        fr_t r;
+        if ((rc = absorb(n_local + k, e, &r))) return rc;
+        for (size_t j = 0; j < len / 2; ++j)
+            for (int t = 0; t < d; ++t) T[t][j] = T[t][2 * j] + r * (T[t][2 * j + 1] - T[t][2 * j]);
+        len /= 2;
+    }
+    fr_t fe = fr_t::one();
+    for (int t = 0; t < d; ++t) { fe = fe * T[t][0]; if (table_finals) memcpy(table_finals[t].l, T[t][0].l, 32); }
+    memcpy(final_evaluation->l, fe.l, 32);                                    // polynomial(&fixed_variables), sumcheck.rs:104
+    if (challenges) for (size_t i = 0; i < chal.size(); ++i) memcpy(challenges[i].l, chal[i].l, 32);
+    return TSGPU_OK;
+}
+
+}  // extern "C"

@@ -101,6 +101,7 @@ using namespace tsg;
 using namespace tsg::host;
 
 struct tsgpu_transcript { Transcript tr; };
+tsg::host::Transcript* tsgpu_transcript_inner(tsgpu_transcript* t) { return &t->tr; }
 
 extern "C" {
 

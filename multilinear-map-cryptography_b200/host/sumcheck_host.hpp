@@ -34,3 +34,7 @@ int sumcheck_verify(unsigned num_vars, const fr_t& claimed_sum, const SumCheckPr
 
 }  // namespace host
 }  // namespace tsg
+
+// the Transcript behind an opaque tsgpu_transcript handle (for library-internal host loops)
+tsg::host::Transcript* tsgpu_transcript_inner(tsgpu_transcript* t);
+

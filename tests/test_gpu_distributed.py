@@ -28,6 +28,81 @@ def test_sharded_driver_world1_matches_oracle(ctx, tsgpu, oracle):
     assert (finals == ref["finals"]).all()
 
 
+@pytest.mark.parametrize("nv,d", [(1, 2), (5, 1), (12, 2), (9, 3)])
+def test_native_sharded_prove_one_rank_equals_unsharded(tsgpu, oracle, nv, d):
+    """tsgpu_sumcheck_prove_product_sharded with a one-rank communicator (no NCCL needed): same proof as the oracle"""
+    c = tsgpu.Context(0)
+    try:
+        c.comm_init(1, 0)
+        assert c.comm_size == 1 and c.comm_rank == 0
+        tables = [oracle.chacha_fr_rand(seed_bytes(30 + 4 * d + t + nv), 1 << nv) for t in range(d)]
+        ev = c.sumcheck([c.table_upload(t) for t in tables]).round_eval()
+        import importlib
+        dd = importlib.import_module(PKG + ".distributed")
+        claimed = dd.fr_add(ev[0], ev[1])
+        ref = oracle.sumcheck_prove_product(tables, claimed, mode="tables")
+        proof, chals, finals = tsgpu.SumCheck(nv, claimed).prove_product_sharded(c, [c.table_upload(t) for t in tables], tsgpu.Transcript(), return_aux=True)
+        assert (proof.round_polynomials == ref["round_polynomials"]).all() and (proof.final_evaluation == ref["final_evaluation"]).all()
+        assert (finals == ref["finals"]).all()
+        with pytest.raises(tsgpu.TwistAndShoutError) as e:       # wrong claim: the reference's round-0 error
+            tsgpu.SumCheck(nv, tsgpu.fe(12345)).prove_product_sharded(c, [c.table_upload(t) for t in tables], tsgpu.Transcript())
+        assert e.value.variant == "SumCheck" and "Round 0 consistency check failed" in str(e.value)
+    finally:
+        c.close()
+
+
+def _native_worker(rank, world, port, nv, d, q):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import importlib
+    import torch.distributed as dist
+    ts = importlib.import_module(PKG)
+    dd = importlib.import_module(PKG + ".distributed")
+    import oracle as O
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)          # only carries the NCCL id; the data path is the library's NCCL
+    try:
+        ctx = ts.Context(rank)
+        ctx.comm_init_torch()
+        n = 1 << nv
+        tables = [O.chacha_fr_rand(bytes([70 + t]) * 32, n) for t in range(d)]
+        lo, hi = dd.slice_bounds(n, rank, world)
+        full = [np.asarray(t).reshape(n, 4) for t in tables]
+        ints = [O.fr_to_ints(t) for t in full]
+        tot = 0
+        for i in range(n):
+            p = 1
+            for t in range(d):
+                p = p * ints[t][i] % O.R_MOD
+            tot = (tot + p) % O.R_MOD
+        claimed = O.fr_from_ints([tot])[0]
+        ref = O.sumcheck_prove_product(tables, claimed, mode="tables")
+        proof, chals, finals = ts.SumCheck(nv, claimed).prove_product_sharded(ctx, [ctx.table_upload(t[lo:hi]) for t in full], ts.Transcript(), return_aux=True)
+        ok = (proof.round_polynomials == ref["round_polynomials"]).all() and (proof.final_evaluation == ref["final_evaluation"]).all()
+        ok = ok and (finals == ref["finals"]).all()
+        # host all-gather through the library communicator
+        g = ctx.comm_allgather(np.arange(12, dtype=np.uint64) + 100 * rank)
+        ok = ok and all((g[r] == np.arange(12, dtype=np.uint64) + 100 * r).all() for r in range(world))
+        q.put((rank, bool(ok)))
+        ctx.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+@pytest.mark.parametrize("nv,d", [(13, 2), (10, 3), (2, 2)])
+def test_native_sharded_sumcheck_two_gpus_library_nccl(nv, d):
+    import torch.multiprocessing as mp
+    mpctx = mp.get_context("spawn")
+    q = mpctx.Queue()
+    procs = [mpctx.Process(target=_native_worker, args=(r, 2, 29873 + nv, nv, d, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+    assert sorted(q.get(timeout=5) for _ in range(2)) == [(0, True), (1, True)]
+
+
 def _nccl_worker(rank, world, port, nv, q):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import importlib

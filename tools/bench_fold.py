@@ -9,10 +9,12 @@ ts = importlib.import_module("multilinear-map-cryptography_b200")
 import oracle as O
 
 nv = int(sys.argv[1]) if len(sys.argv) > 1 else 26
+tma_log = int(sys.argv[2]) if len(sys.argv) > 2 else -1      # >= 0: tables with at least 2^tma_log positions per stream use the TMA-ring kernels
 torch.cuda.init()
 stream = torch.cuda.Stream()
 torch.cuda.set_stream(stream)
 ctx = ts.Context(0, stream.cuda_stream)
+ctx.set_tuning("tma_min_log2", tma_log)
 w = O.chacha_fr_rand(bytes([4]) * 32, nv)
 r = O.chacha_fr_rand(bytes([6]) * 32, 1)
 t0 = time.time()
@@ -21,7 +23,7 @@ B = ctx.table_eq(w[::-1].copy())
 ctx.synchronize()
 print("generated 2 tables of 2^%d in %.2fs" % (nv, time.time() - t0), flush=True)
 N = 1 << nv
-res = {"nv": nv}
+res = {"nv": nv, "tma_min_log2": tma_log}
 
 def timeit(fn, setup, reps=5):
     best = 1e9

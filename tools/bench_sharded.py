@@ -17,6 +17,10 @@ if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ctx = ts.Context(local)
 coll = dd.Collective()
+if world > 1:
+    ctx.comm_init_torch()          # library-side NCCL communicator (csrc/comm.cu); torch.distributed only carries the id
+else:
+    ctx.comm_init(1, 0)
 logG = world.bit_length() - 1
 rng = np.random.default_rng(4)
 w = rng.integers(0, 1 << 62, size=(LOG, 4), dtype=np.uint64); w[:, 3] &= (1 << 60) - 1
@@ -36,13 +40,16 @@ def run_c4():
         tt = [t.clone() for t in tabs]
         if world > 1: dist.barrier()
         torch.cuda.synchronize(); t0 = time.perf_counter()
-        dd.ShardedSumCheck(LOG, claimed, coll).prove_product(dd.DeviceRoundEngine(ctx), tt, ts.Transcript(), device_tables=True)
+        if os.environ.get("C4_DRIVER", "native") == "native":
+            ts.SumCheck(LOG, claimed).prove_product_sharded(ctx, tt, ts.Transcript())      # C++ loop, one ncclAllReduce per round on the library stream
+        else:
+            dd.ShardedSumCheck(LOG, claimed, coll).prove_product(dd.DeviceRoundEngine(ctx), tt, ts.Transcript(), device_tables=True)
         torch.cuda.synchronize(); dt = time.perf_counter() - t0
         t = torch.tensor([dt], device="cuda", dtype=torch.float64)
         if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
         best = min(best, float(t[0]))
     if rank == 0:
-        print(json.dumps({"config": "C4", "n_gpus": world, "log_entries_total": LOG, "ms": best * 1e3,
+        print(json.dumps({"config": "C4", "driver": os.environ.get("C4_DRIVER", "native"), "n_gpus": world, "log_entries_total": LOG, "ms": best * 1e3,
                           "algorithmic_GBps_all_gpus": 256.0 * (1 << LOG) / best / 1e9, "scaling": "strong"}))
 
 def run_c5():
@@ -50,8 +57,8 @@ def run_c5():
     a, b = dd.slice_bounds(n, rank, world)
     tau = ts.fe(987654321)
     srs = ctx.srs_generate_range(tau, a, b - a)
-    sc = rng.integers(0, 1 << 62, size=(b - a, 4), dtype=np.uint64); sc[:, 3] &= (1 << 60) - 1
-    poly = ctx.poly_upload(sc)
+    full = np.random.default_rng(5).integers(0, 1 << 62, size=(n, 4), dtype=np.uint64); full[:, 3] &= (1 << 60) - 1   # same vector on every rank
+    poly = ctx.poly_upload(np.ascontiguousarray(full[a:b])); del full
     best = 1e9
     for it in range(4):
         if world > 1: dist.barrier()

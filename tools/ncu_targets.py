@@ -1,5 +1,6 @@
-"""Tiny workload for `ncu --set full`: one G1 MSM of 2^18 points, one fold (bind) and one fused bind+eval of 2^24-entry
-tables.  Keep it short - ncu replays every profiled kernel ~40 times."""
+"""Tiny workload for `ncu --set full`: one G1 MSM of 2^18 points (precomputed window tables, one shared bucket set), one fold
+(bind), one round evaluation and one fused bind+eval (claim form) of 2^24-entry tables, one barycentric opening pass.
+Keep it short - ncu replays every profiled kernel ~40 times."""
 import importlib, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -16,6 +17,8 @@ w = sc[:24].copy(); r = sc[30:31].copy()
 A = ctx.table_eq(w); B = ctx.table_eq(w[::-1].copy())
 A.clone().bind(r)
 s = ctx.sumcheck([A, B])
-s.round_eval(); s.bind_eval(r)
+s.round_eval(); s.bind_eval(r, claim=r)
+pv = ctx.poly_upload(sc)
+ts.KZGCommitment.open_values(srs, pv, r)
 ctx.synchronize()
 print("ok", ts.g1_compress(c).hex()[:16])
