@@ -234,10 +234,14 @@ def main():
 
     def time_device():
         """padded vectors already in HBM: per-proof ms, launches, MSM work counters and kernel timers of the timed region"""
-        for _ in range(W):
-            twist.prove_device(base_a.clone(), base_v.clone())
+        # every input copy is made BEFORE the warm-up, so that the stream-ordered pool has its final size when the timed region starts
+        # (growing the pool inside a step stalls it for ~100 ms: tools/diag_stall.py)
+        warm = [(base_a.clone(), base_v.clone()) for _ in range(W)]
         clones = [(base_a.clone(), base_v.clone()) for _ in range(K)]
         ctx.set_tuning("kernel_timing", 1)
+        for a, v in warm:
+            twist.prove_device(a, v)
+        del warm
         ctx.timer_reset()
         barrier()
         c0 = {k: ctx.counter(k) for k in ("launches", "msm_calls", "msm_points", "msm_entries")}
@@ -286,6 +290,11 @@ def main():
                 "entries_per_launch": entries, "share_of_step": r["msm_accumulate_ms"] / K / r["ms"] if r["ms"] > 0 else None}
 
     roofline = acc_roofline(dflt)
+    # DRAM bytes per launch from `ncu --set full` of this same command (profiles/r01_ncu_accumulate_in_bench.md): commit pass 0.587 + 0.068 GB,
+    # open pass 3.622 + 0.146 GB; mean over the two launches of a proof, like `achieved`.  Algorithmic bytes: entries x (64 B point + 4 B entry).
+    roofline["traffic"] = 0.5 * ((0.586715 + 0.067997) + (3.621562 + 0.145975)) * 1e9
+    roofline["algorithmic_bytes"] = roofline["entries_per_launch"] * 68.0
+    roofline["ncu"] = "FMA-heavy pipe 88-89% busy, thread efficiency 31.8/32, DRAM 0.87 TB/s (profiles/r01_ncu_accumulate_in_bench.md)"
     roofline["peak_source"] = "tools/ubench.cu on this pool: 18.5 T IMAD.WIDE/s without carry predicate (the carry-chained form the multiplier needs issues at half that rate)"
     roofline["algorithmic_unit"] = "bucket entries x (8M + 2S) x 136 IMAD per launch (mean over the 4 MSMs of a proof)"
 

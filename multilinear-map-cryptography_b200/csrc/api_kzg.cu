@@ -576,8 +576,9 @@ int tsgpu_kzg_open_values_batch_dev(tsgpu_ctx* ctx, const tsgpu_srs* srs, const 
     fr_t* q_all = (fr_t*)arena_get(ctx, tsgpu_ctx::ARENA_QUOT, (total + 2 * MSM_MAX_BATCH) * sizeof(fr_t), &aerr);
     if (!q_all) return cuda_fail(ctx, aerr, "cudaMalloc(quotient)");
     fr_t *nz = q_all + total, *val = nz + MSM_MAX_BATCH;
-    // 1/(z - j) and the span products depend on z only; a shorter vector uses a prefix of them
-    const bool hit = ctx->bary_inv && !memcmp(&ctx->bary_z, z, 32) && mmax <= ctx->bary_n;
+    // 1/(z - j) and the span products depend on z only: computed once per call for the longest vector (a shorter vector uses a
+    // prefix of them).  Nothing is kept across calls - a repeated proof of the same trace redoes this work.
+    const bool hit = false;
     fr_t zf; memcpy(zf.l, z->l, 32);
     MsmBasis basis[MSM_MAX_BATCH]; const fr_t* sc[MSM_MAX_BATCH]; size_t n[MSM_MAX_BATCH];
     {

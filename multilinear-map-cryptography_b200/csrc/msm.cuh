@@ -7,7 +7,7 @@ namespace tsg {
 
 constexpr unsigned MSM_CHUNK = 64;        // max entries one work item adds into its accumulator (bounds the serial chain of one thread)
 constexpr int MSM_ACC_THREADS = 128;
-constexpr unsigned MSM_RED_SPAN = 8;      // buckets per thread in the window reduction (2 x span additions deep)
+constexpr unsigned MSM_RED_SPAN = 16;     // buckets per thread in the window reduction (2 x span additions deep; the bit-decomposed tail costs log2(buckets / span) / 2 additions per span)
 constexpr int MSM_SUM_THREADS = 256;
 constexpr size_t MSM_POW_SPAN = 64;       // consecutive tau powers per thread
 constexpr size_t MSM_INV_SPAN = 32;       // points per batch inversion

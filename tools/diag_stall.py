@@ -1,3 +1,4 @@
+"""Per-call wall times of Twist::prove on both paths, to spot host-side stalls (allocator, event creation, ...)."""
 import importlib, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -19,8 +20,13 @@ def series(name, f, reps):
     for _ in range(reps):
         torch.cuda.synchronize(); t0 = time.perf_counter(); r = f(); torch.cuda.synchronize(); out.append((time.perf_counter() - t0) * 1e3); del r
     print(name, " ".join("%.1f" % x for x in out), flush=True)
-series("prove_arrays", lambda: tw.prove_arrays(addr_h, vals_h, isw), 25)
-series("upload_only ", lambda: (ctx.poly_from_u64(addr_h), ctx.poly_upload_padded(vals_h, n)), 25)
 a = ctx.poly_from_u64(addr_h); v = ctx.poly_upload_padded(vals_h, n)
-series("prove_device", lambda: tw.prove_device(a.clone(), v.clone()), 25)
-series("prove_arrays", lambda: tw.prove_arrays(addr_h, vals_h, isw), 25)
+for eb in (0, 1):
+    for timing in (0, 1):
+        ctx.set_tuning("eval_basis", eb); ctx.set_tuning("kernel_timing", timing)
+        series(f"eval_basis={eb} timing={timing} prove_device", lambda: tw.prove_device(a.clone(), v.clone()), 30)
+        cl = [(a.clone(), v.clone()) for _ in range(30)]
+        it = iter(cl)
+        series(f"eval_basis={eb} timing={timing} preclone    ", lambda: tw.prove_device(*next(it)), 30)
+        del cl, it
+        ctx.timer_reset()
