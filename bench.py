@@ -252,7 +252,7 @@ def main():
         barrier()
         r = {"ms": e0.elapsed_time(e1) / K}
         r.update({k: ctx.counter(k) - c0[k] for k in c0})
-        for name in ("msm_accumulate", "msm_total", "interpolate", "open_bary", "open_scan"):
+        for name in ("msm_accumulate", "msm_total", "msm_sort", "msm_merge", "msm_reduce", "interpolate", "open_bary", "open_scan"):
             r[name + "_ms"], r[name + "_cnt"] = ctx.timer_read(name)
         ctx.set_tuning("kernel_timing", 0)
         return r
@@ -335,7 +335,8 @@ def main():
 
     if rank == 0:
         def breakdown(r):
-            return {"msm_4x": r["msm_total_ms"] / K, "msm_accumulate_4x": r["msm_accumulate_ms"] / K, "interpolate_2x": r["interpolate_ms"] / K,
+            return {"msm_4x": r["msm_total_ms"] / K, "msm_accumulate_4x": r["msm_accumulate_ms"] / K, "msm_sort_4x": r["msm_sort_ms"] / K,
+                    "msm_chunk_merge_4x": r["msm_merge_ms"] / K, "msm_window_reduce_4x": r["msm_reduce_ms"] / K, "interpolate_2x": r["interpolate_ms"] / K,
                     "open_barycentric_2x": r["open_bary_ms"] / K, "open_scan_2x": r["open_scan_ms"] / K, "bucket_entries": r["msm_entries"] // K,
                     "gpu_launches": r["launches"] // K}
         line = {

@@ -102,6 +102,7 @@ int tsgpu_init(int device, void* stream, tsgpu_ctx** out) {
               cudaMalloc((void**)&ctx->ticket, 64) == cudaSuccess &&
               cudaMalloc((void**)&ctx->dev_out, 8 * sizeof(fr_t)) == cudaSuccess &&
               cudaMallocHost((void**)&ctx->host_out, 8 * sizeof(fr_t)) == cudaSuccess &&
+              cudaMallocHost((void**)&ctx->host_scratch, 64 * sizeof(fr_t)) == cudaSuccess &&
               cudaMemset(ctx->ticket, 0, 64) == cudaSuccess;
     if (!ok) { cudaGetLastError(); tsgpu_destroy(ctx); return TSGPU_E_PROOF_GENERATION; }
     *out = ctx;
@@ -119,6 +120,7 @@ void tsgpu_destroy(tsgpu_ctx* ctx) {
     if (ctx->ticket) cudaFree(ctx->ticket);
     if (ctx->dev_out) cudaFree(ctx->dev_out);
     if (ctx->host_out) cudaFreeHost(ctx->host_out);
+    if (ctx->host_scratch) cudaFreeHost(ctx->host_scratch);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -29,9 +29,12 @@ struct tsgpu_srs {
     // ONE bucket set: fewer, wider windows (c = 20 at 2^20 points: 13 additions per point instead of 16) and a single reduction
     g1_affine* table = nullptr; unsigned table_c = 0;
     std::map<size_t, std::pair<g1_affine*, unsigned>> lagrange_table;
+    // second, short table per Lagrange basis for value vectors whose entries fit 64 bits (addresses, u64 memory values, table indices):
+    // 16-bit windows, only the five lowest - the bucket set is 16 times smaller, and so is the window reduction
+    std::map<size_t, g1_affine*> lagrange_short_table;
 };
 // a base array the MSM can run on: plain points and, optionally, their window tables
-struct MsmBasis { const g1_affine* pts; size_t n; const g1_affine* table; unsigned table_c; };
+struct MsmBasis { const g1_affine* pts; size_t n; const g1_affine* table; unsigned table_c; const g1_affine* short_table = nullptr; unsigned short_c = 0, short_windows = 0; };
 struct tsgpu_poly {
     fr_t* d = nullptr;        // n coefficients, low -> high, natural order
     size_t n = 0;
@@ -56,21 +59,37 @@ G1J combine_windows(const g1_jac* win, unsigned W, unsigned c) {
 // K independent device MSMs in one pass (bases and scalars resident); results to the host as Jacobian points.
 // Mode: precomputed tables (one shared bucket set per job) when every job has a table of the same window width and uses at
 // least a quarter of it; otherwise per-window bucket sets on the plain points.
-int msm_device_batch(tsgpu_ctx* ctx, int K, const MsmBasis* basis, const fr_t* const* scalars, const size_t* n, tsgpu_g1* out) {
+int msm_device_batch(tsgpu_ctx* ctx, int K, const MsmBasis* basis, const fr_t* const* scalars, const size_t* n, tsgpu_g1* out, bool maybe_short = false) {
     size_t nmax = 0;
     for (int k = 0; k < K; ++k) nmax = n[k] > nmax ? n[k] : nmax;
     if (nmax == 0) { G1J id = G1J::identity(); for (int k = 0; k < K; ++k) memcpy(&out[k], &id, 96); return TSGPU_OK; }
     bool shared = ctx->msm_tables;
     for (int k = 0; k < K && shared; ++k)
         shared = basis[k].table && basis[k].table_c == basis[0].table_c && n[k] * 4 >= basis[k].n && (255 + basis[k].table_c - 1) / basis[k].table_c * basis[k].n < ((size_t)1 << 31);
-    const unsigned c = shared ? basis[0].table_c : msm_window_bits(nmax);
+    // value vectors (commitments over the Lagrange basis) are usually short scalars: probe, and if every entry fits 64 bits use the short tables
+    bool use_short = false;
+    if (maybe_short && shared) {
+        use_short = true;
+        for (int k = 0; k < K; ++k) use_short = use_short && basis[k].short_table && basis[k].short_c == basis[0].short_c;
+        if (use_short) {
+            unsigned* flag = (unsigned*)(ctx->dev_out + 7);   // last result slot doubles as the probe flag
+            TSG_CUDA(ctx, cudaMemsetAsync(flag, 0, 4, ctx->stream));
+            for (int k = 0; k < K; ++k) TSG_CUDA(ctx, launch_scalar_probe(scalars[k], n[k], flag, ctx->sm_count, ctx->stream));
+            ctx->launches += K;
+            unsigned* hflag = (unsigned*)(ctx->host_out + 7);
+            TSG_CUDA(ctx, cudaMemcpyAsync(hflag, flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            use_short = *hflag == 0;
+        }
+    }
+    const unsigned c = use_short ? basis[0].short_c : shared ? basis[0].table_c : msm_window_bits(nmax);
     MsmLayout L;
-    size_t bytes = msm_scratch_bytes(nmax, K, c, shared, &L);
+    size_t bytes = msm_scratch_bytes(nmax, K, c, shared, &L, use_short ? basis[0].short_windows : 0);
     cudaError_t aerr;
     unsigned char* scratch_p = (unsigned char*)arena_get(ctx, tsgpu_ctx::ARENA_MSM, bytes, &aerr);
     if (!scratch_p) return cuda_fail(ctx, aerr, "cudaMalloc(msm scratch)");
     MsmJob jobs[MSM_MAX_BATCH];
-    for (int k = 0; k < K; ++k) jobs[k] = MsmJob{shared ? basis[k].table : basis[k].pts, basis[k].n, scalars[k], n[k]};
+    for (int k = 0; k < K; ++k) jobs[k] = MsmJob{use_short ? basis[k].short_table : shared ? basis[k].table : basis[k].pts, basis[k].n, scalars[k], n[k]};
     unsigned launches = 0;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     if (ctx->timing) for (auto& x : ev) cudaEventCreate(&x);
@@ -85,14 +104,25 @@ int msm_device_batch(tsgpu_ctx* ctx, int K, const MsmBasis* basis, const fr_t* c
     }
     for (int k = 0; k < K; ++k) ctx->msm_points += n[k];
     ctx->launches += launches;
-    std::vector<g1_jac> win(L.sets);
+    const unsigned per_set = L.span_bits + 2;
+    std::vector<g1_jac> raw((size_t)L.sets * per_set), win(L.sets);
     unsigned counts[2] = {0, 0};   // work items, bucket entries
-    TSG_CUDA(ctx, cudaMemcpyAsync(win.data(), scratch_p + L.window_out, L.sets * sizeof(g1_jac), cudaMemcpyDeviceToHost, ctx->stream));
+    TSG_CUDA(ctx, cudaMemcpyAsync(raw.data(), scratch_p + L.window_out, raw.size() * sizeof(g1_jac), cudaMemcpyDeviceToHost, ctx->stream));
     TSG_CUDA(ctx, cudaMemcpyAsync(counts, scratch_p + L.n_items, sizeof(counts), cudaMemcpyDeviceToHost, ctx->stream));
     TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->msm_entries += counts[1];
     ctx->msm_calls += 1;
     timers_collect(ctx);
+    // bucket-set sums: S = span * sum_k 2^k P[k] + P[span_bits] + P[span_bits + 1]  (Horner over the index-bit sums, then the span-local part)
+    unsigned logS = 0; while ((1u << logS) < L.span) ++logS;
+    for (unsigned w = 0; w < L.sets; ++w) {
+        const g1_jac* P = raw.data() + (size_t)w * per_set;
+        G1J acc = G1J::identity();
+        for (unsigned k = L.span_bits; k-- > 0;) { acc = acc.dbl(); G1J t; memcpy(&t, &P[k], 96); acc = acc.add(t); }
+        for (unsigned d = 0; d < logS; ++d) acc = acc.dbl();
+        for (unsigned h = 0; h < 2; ++h) { G1J l; memcpy(&l, &P[L.span_bits + h], 96); acc = acc.add(l); }
+        memcpy(&win[w], &acc, 96);
+    }
     const unsigned per_job = L.sets / L.K;
     for (int k = 0; k < K; ++k) {
         G1J r = combine_windows(win.data() + (size_t)k * per_job, per_job, L.c);   // one set per job in table mode: nothing to combine
@@ -218,6 +248,7 @@ void tsgpu_srs_free(tsgpu_ctx* ctx, tsgpu_srs* srs) {
     if (srs->d) cudaFree(srs->d);
     for (auto& kv : srs->lagrange) cudaFree(kv.second);
     for (auto& kv : srs->lagrange_table) cudaFree(kv.second.first);
+    for (auto& kv : srs->lagrange_short_table) cudaFree(kv.second);
     if (srs->table) cudaFree(srs->table);
     delete srs;
 }
@@ -484,7 +515,13 @@ static g1_affine* lagrange_basis(const tsgpu_srs* srs, size_t m) {
 }
 static MsmBasis lagrange_msm_basis(const tsgpu_srs* srs, size_t m) {
     auto it = srs->lagrange_table.find(m);
-    return MsmBasis{lagrange_basis(srs, m), m, it == srs->lagrange_table.end() ? nullptr : it->second.first, it == srs->lagrange_table.end() ? 0u : it->second.second};
+    MsmBasis b{lagrange_basis(srs, m), m, it == srs->lagrange_table.end() ? nullptr : it->second.first, it == srs->lagrange_table.end() ? 0u : it->second.second};
+    // short scalars (< 2^64): a dedicated table of MSM_SHORT_C-bit windows when the full table's windows are wider, else the low
+    // windows of the full table itself
+    auto sh = srs->lagrange_short_table.find(m);
+    if (sh != srs->lagrange_short_table.end()) { b.short_table = sh->second; b.short_c = MSM_SHORT_C; b.short_windows = MSM_SHORT_WINDOWS; }
+    else if (b.table && b.table_c <= MSM_SHORT_C) { b.short_table = b.table; b.short_c = b.table_c; b.short_windows = (65 + b.table_c - 1) / b.table_c; }
+    return b;
 }
 int tsgpu_srs_has_lagrange(const tsgpu_srs* srs, size_t m) { return srs && lagrange_basis(srs, m) ? 1 : 0; }
 int tsgpu_srs_can_lagrange(const tsgpu_srs* srs) { return srs && srs->has_tau ? 1 : 0; }
@@ -505,17 +542,20 @@ int tsgpu_srs_lagrange_prepare(tsgpu_ctx* ctx, const tsgpu_srs* srs_c, size_t m)
     g1_affine* basis = nullptr;
     cudaError_t e = cudaMalloc((void**)&basis, m * sizeof(g1_affine));
     if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc(lagrange basis)");
-    TempBuf inv, spans, scal, prod;
+    TempBuf inv, scratch, scal, prod;
     int rc = TSGPU_OK;
     fr_t t; memcpy(t.l, srs->tau.l, 32);
+    fr_t ntau;
+    unsigned launches = 0;
     cudaError_t ce = inv.alloc(m * sizeof(fr_t), ctx->stream);
-    if (ce == cudaSuccess) ce = spans.alloc(lag_num_spans(m) * sizeof(fr_t), ctx->stream);
+    if (ce == cudaSuccess) ce = scratch.alloc(lag_binv_scratch(m) * sizeof(fr_t), ctx->stream);
     if (ce == cudaSuccess) ce = scal.alloc(m * sizeof(fr_t), ctx->stream);
     if (ce == cudaSuccess) ce = prod.alloc(sizeof(fr_t), ctx->stream);
-    if (ce == cudaSuccess) ce = launch_node_inverses(t, m, inv.as<fr_t>(), spans.as<fr_t>(), ctx->sm_count, ctx->stream);
-    if (ce == cudaSuccess) ce = launch_fr_product(spans.as<fr_t>(), lag_num_spans(m), prod.as<fr_t>(), ctx->stream);
+    if (ce == cudaSuccess) ce = launch_node_inverses(t, m, inv.as<fr_t>(), scratch.as<fr_t>(), ctx->host_scratch, &ntau, ctx->sm_count, ctx->stream, &launches);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(prod.p, &ntau, sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream);
     if (ce == cudaSuccess) ce = launch_lagrange_scalars(inv.as<fr_t>(), ifact, prod.as<fr_t>(), m, scal.as<fr_t>(), ctx->sm_count, ctx->stream);
-    ctx->launches += 3;
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);   // ntau is a stack variable
+    ctx->launches += launches + 1;
     if (ce != cudaSuccess) rc = cuda_fail(ctx, ce, "lagrange scalars");
     if (!rc) rc = fixed_base_points(ctx, scal.as<fr_t>(), m, basis);
     if (!rc) { ce = cudaStreamSynchronize(ctx->stream); if (ce != cudaSuccess) rc = cuda_fail(ctx, ce, "lagrange basis"); }
@@ -524,6 +564,18 @@ int tsgpu_srs_lagrange_prepare(tsgpu_ctx* ctx, const tsgpu_srs* srs_c, size_t m)
     if ((rc = build_tables(ctx, basis, m, &table, &table_c))) { cudaFree(basis); return rc; }
     srs->lagrange[m] = basis;
     if (table) srs->lagrange_table[m] = {table, table_c};
+    if (table && table_c > MSM_SHORT_C) {   // dedicated short-scalar table when the full table's bucket set is the larger one
+        g1_affine* st = nullptr;
+        if (cudaMalloc((void**)&st, (size_t)MSM_SHORT_WINDOWS * m * sizeof(g1_affine)) == cudaSuccess) {
+            TempBuf cur; unsigned launches = 0;
+            cudaError_t e = cur.alloc(m * sizeof(g1_xyzz), ctx->stream);
+            if (e == cudaSuccess) e = msm_build_table(basis, m, MSM_SHORT_C, st, cur.as<g1_xyzz>(), ctx->sm_count, ctx->stream, &launches, MSM_SHORT_WINDOWS);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            ctx->launches += launches;
+            if (e != cudaSuccess) { cudaFree(st); return cuda_fail(ctx, e, "short window tables"); }
+            srs->lagrange_short_table[m] = st;
+        } else cudaGetLastError();
+    }
     return TSGPU_OK;
 }
 
@@ -544,7 +596,7 @@ int tsgpu_kzg_commit_values_batch_dev(tsgpu_ctx* ctx, const tsgpu_srs* srs, cons
             basis[i] = lagrange_msm_basis(srs, n[i]);
         }
     }
-    return msm_device_batch(ctx, (int)count, basis, sc, n, outs);
+    return msm_device_batch(ctx, (int)count, basis, sc, n, outs, /*maybe_short=*/true);
 }
 int tsgpu_kzg_commit_values_dev(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_poly* values, tsgpu_g1* out) {
     if (!values || !out) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
@@ -578,17 +630,19 @@ int tsgpu_kzg_open_values_batch_dev(tsgpu_ctx* ctx, const tsgpu_srs* srs, const 
     fr_t *nz = q_all + total, *val = nz + MSM_MAX_BATCH;
     // 1/(z - j) and the span products depend on z only: computed once per call for the longest vector (a shorter vector uses a
     // prefix of them).  Nothing is kept across calls - a repeated proof of the same trace redoes this work.
-    const bool hit = false;
     fr_t zf; memcpy(zf.l, z->l, 32);
     MsmBasis basis[MSM_MAX_BATCH]; const fr_t* sc[MSM_MAX_BATCH]; size_t n[MSM_MAX_BATCH];
     {
         KernelTimer kt(ctx, "open_bary");
-        if (!hit) {
-            fr_t* inv = (fr_t*)arena_get(ctx, tsgpu_ctx::ARENA_BARY, (mmax + lag_num_spans(mmax)) * sizeof(fr_t), &aerr);
+        fr_t nz_max;   // N(z) over the nodes of the longest vector, from the host leg of the batch inversion
+        {
+            fr_t* inv = (fr_t*)arena_get(ctx, tsgpu_ctx::ARENA_BARY, (mmax + lag_binv_scratch(mmax)) * sizeof(fr_t), &aerr);
             if (!inv) return cuda_fail(ctx, aerr, "cudaMalloc(node inverses)");
             ctx->bary_inv = inv; ctx->bary_spans = inv + mmax; ctx->bary_n = mmax; ctx->bary_z = *z;
-            TSG_CUDA(ctx, launch_node_inverses(zf, mmax, inv, (fr_t*)ctx->bary_spans, ctx->sm_count, ctx->stream));
-            ctx->launches += 1;
+            unsigned launches = 0;
+            TSG_CUDA(ctx, launch_node_inverses(zf, mmax, inv, (fr_t*)ctx->bary_spans, ctx->host_scratch, &nz_max, ctx->sm_count, ctx->stream, &launches));
+            ctx->launches += launches;
+            memcpy(ctx->host_scratch + 40, &nz_max, sizeof(fr_t));   // pinned copy for the upload below
         }
         size_t off = 0;
         for (size_t i = 0; i < count; ++i) {
@@ -600,7 +654,8 @@ int tsgpu_kzg_open_values_batch_dev(tsgpu_ctx* ctx, const tsgpu_srs* srs, const 
                 if (rc) return rc;
                 basis[i] = lagrange_msm_basis(srs, m);
                 // N(z) over the nodes 0..m-1: product of whole spans, or (m < span) a fresh small product
-                if (m % LAG_SPAN == 0 || m == ctx->bary_n) TSG_CUDA(ctx, launch_fr_product((const fr_t*)ctx->bary_spans, lag_num_spans(m), nz + i, ctx->stream));
+                if (m == mmax) TSG_CUDA(ctx, cudaMemcpyAsync(nz + i, ctx->host_scratch + 40, sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+                else if (m % LAG_SPAN == 0) TSG_CUDA(ctx, launch_fr_product((const fr_t*)ctx->bary_spans, lag_num_spans(m), nz + i, ctx->stream));
                 else TSG_CUDA(ctx, launch_node_product(zf, m, nz + i, ctx->stream));
                 TSG_CUDA(ctx, launch_bary_open(values[i]->d, (const fr_t*)ctx->bary_inv, ifact, m, nz + i, ctx->partials, ctx->ticket, val + i, q_all + off, ctx->sm_count, ctx->stream));
                 ctx->launches += 3;

@@ -21,6 +21,7 @@ struct tsgpu_ctx {
     unsigned int* ticket = nullptr;
     tsg::fr_t* dev_out = nullptr;      // 8 elements
     tsg::fr_t* host_out = nullptr;     // pinned, 8 elements
+    tsg::fr_t* host_scratch = nullptr; // pinned, 64 elements (host leg of the batch inversion, lagrange.cu)
     void* comm = nullptr;              // multi-GPU communicator (comm.cu), optional
     void* interp = nullptr;            // cached interpolation plan (interp.cu)
     // optional per-kernel device timing (CUDA events on `stream`), enabled by tsgpu_set_tuning("kernel_timing", 1)

@@ -15,6 +15,9 @@
 // The kernels below are streaming passes with a Montgomery batch inversion per thread.
 #include "fr_device.cuh"
 #include "lagrange.cuh"
+#include <cstring>
+#include <vector>
+#include "../host/field64.hpp"
 
 namespace tsg {
 
@@ -24,23 +27,45 @@ static inline int gridfor(size_t work, int threads, size_t cap) {
     return (int)(g < cap ? g : cap);
 }
 
-// inv[j] = 1 / (pt - j) for j < n (pt must not be one of 0..n-1);  span_prod[ch] = prod_{j in span ch} (pt - j)
-__global__ void __launch_bounds__(128) k_node_inverses(const fr_t pt, size_t n, fr_t* inv, fr_t* span_prod) {
+// ---- batch inversion of d_j = pt - j (j < n) with ONE field inversion, done on the host ------------------------------------
+// A Fermat inversion is a chain of ~380 dependent products (~0.13 ms for a lone thread), so the classic per-thread Montgomery
+// trick is latency-bound.  Here the prefix-product / back-substitution passes are applied level by level: level 0 over the
+// d_j in spans of LAG_SPAN, level 1 over the span products, ... until at most LAG_SPAN products remain; those go to the host
+// (1 KiB), which inverts them with its native 64-bit arithmetic (microseconds) and sends the inverses back; the levels are
+// then unwound.  Every launch is at most 2 x LAG_SPAN products deep.
+// up:   pre[j] = product of the elements before j in its span; span_prod[ch] = product of span ch
+template <bool GEN>
+__global__ void __launch_bounds__(128) k_binv_up(const fr_t pt, const fr_t* elems, size_t n, fr_t* pre, fr_t* span_prod) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const size_t nch = (n + LAG_SPAN - 1) / LAG_SPAN;
     const fr_t one = fr_t::one();
     for (size_t ch = (size_t)blockIdx.x * blockDim.x + threadIdx.x; ch < nch; ch += stride) {
         const size_t b = ch * LAG_SPAN, e = b + LAG_SPAN < n ? b + LAG_SPAN : n;
-        fr_t d = pt - fr_t::from_u64(b);          // pt - j, stepped by -1
+        fr_t d = GEN ? pt - fr_t::from_u64(b) : fr_t::zero();
         fr_t acc = one;
-        for (size_t j = b; j < e; ++j) { st256(inv + j, acc); acc = acc * d; d = d - one; }
+        for (size_t j = b; j < e; ++j) {
+            st256(pre + j, acc);
+            if (GEN) { acc = acc * d; d = d - one; } else acc = acc * ld256(elems + j);
+        }
         st256(span_prod + ch, acc);
-        fr_t ia = acc.inverse();
+    }
+}
+// down: span_inv[ch] = 1 / (product of span ch); pre[j] (prefix products) is replaced by 1 / element_j
+template <bool GEN>
+__global__ void __launch_bounds__(128) k_binv_down(const fr_t pt, const fr_t* elems, size_t n, fr_t* pre, const fr_t* span_inv) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t nch = (n + LAG_SPAN - 1) / LAG_SPAN;
+    const fr_t one = fr_t::one();
+    for (size_t ch = (size_t)blockIdx.x * blockDim.x + threadIdx.x; ch < nch; ch += stride) {
+        const size_t b = ch * LAG_SPAN, e = b + LAG_SPAN < n ? b + LAG_SPAN : n;
+        fr_t ia = ld256(span_inv + ch);
+        fr_t d = GEN ? pt - fr_t::from_u64(e) : fr_t::zero();   // stepped up to pt - j below
         for (size_t j = e; j-- > b;) {
-            d = d + one;                          // back to pt - j
-            fr_t pref = ld256(inv + j);
-            st256(inv + j, ia * pref);
-            ia = ia * d;
+            fr_t el;
+            if (GEN) { d = d + one; el = d; } else el = ld256(elems + j);
+            fr_t p = ld256(pre + j);
+            st256(pre + j, ia * p);
+            ia = ia * el;
         }
     }
 }
@@ -100,9 +125,70 @@ __global__ void __launch_bounds__(256) k_bary_quotient(const fr_t* vals, const f
         st256(q + j, (v - ld256_nc(vals + j)) * ld256_nc(inv + j));
 }
 
-cudaError_t launch_node_inverses(const fr_t& pt, size_t n, fr_t* inv, fr_t* span_prod, int sm_count, cudaStream_t s) {
-    const size_t nch = lag_num_spans(n);
-    k_node_inverses<<<gridfor(nch, 128, (size_t)sm_count * 16), 128, 0, s>>>(pt, n, inv, span_prod);
+// scratch: lag_binv_scratch(n) elements.  inv[j] = 1/(pt - j); span_prod (level-0 span products) is left at scratch[0 .. lag_num_spans(n));
+// *total = prod_j (pt - j) on the HOST.  Synchronises the stream once (the host inversion sits in the middle).
+size_t lag_binv_scratch(size_t n) {
+    size_t tot = 0, m = n;
+    do { m = lag_num_spans(m); tot += 2 * m; } while (m > LAG_SPAN);
+    return tot + 2 * LAG_SPAN;
+}
+cudaError_t launch_node_inverses(const fr_t& pt, size_t n, fr_t* inv, fr_t* scratch, fr_t* host_pinned, fr_t* total_host, int sm_count, cudaStream_t s,
+                                 unsigned* launches) {
+    // level sizes: n -> spans(n) -> ... -> top (<= LAG_SPAN elements)
+    std::vector<size_t> size{n};
+    while (size.back() > LAG_SPAN) size.push_back(lag_num_spans(size.back()));
+    const size_t levels = size.size() - 1;     // number of up passes that produce a further device level
+    // layout: prod[l] (level l+1 elements = span products of level l) and pre[l] (prefix scratch of level l+1), l = 0 .. levels-1
+    std::vector<fr_t*> prod(levels + 1), pre(levels + 1);
+    fr_t* p = scratch;
+    for (size_t l = 0; l < levels; ++l) { prod[l] = p; p += size[l + 1]; }
+    for (size_t l = 1; l <= levels; ++l) { pre[l] = p; p += size[l]; }
+    const size_t cap = (size_t)sm_count * 16;
+    // up
+    for (size_t l = 0; l < levels; ++l) {
+        const size_t nch = size[l + 1];
+        if (l == 0) k_binv_up<true><<<gridfor(nch, 128, cap), 128, 0, s>>>(pt, nullptr, size[0], inv, prod[0]);
+        else k_binv_up<false><<<gridfor(nch, 128, cap), 128, 0, s>>>(pt, prod[l - 1], size[l], pre[l], prod[l]);
+        if (launches) ++*launches;
+    }
+    // top level on the host: elements = prod[levels-1] (or, when n <= LAG_SPAN, the d_j themselves)
+    const size_t top = size[levels];
+    cudaError_t e;
+    if (levels == 0) {
+        // tiny n: one span; run the up pass to get prefixes, invert the single product on the host
+        k_binv_up<true><<<1, 128, 0, s>>>(pt, nullptr, n, inv, scratch);
+        if (launches) ++*launches;
+        if ((e = cudaMemcpyAsync(host_pinned, scratch, sizeof(fr_t), cudaMemcpyDeviceToHost, s))) return e;
+        if ((e = cudaStreamSynchronize(s))) return e;
+        host::Fr64 t = host::Fr64::from_raw((const uint64_t*)host_pinned[0].l);
+        memcpy(total_host->l, t.l, 32);
+        host::Fr64 ti = t.inverse();
+        memcpy(host_pinned[1].l, ti.l, 32);
+        if ((e = cudaMemcpyAsync(scratch + 1, host_pinned + 1, sizeof(fr_t), cudaMemcpyHostToDevice, s))) return e;
+        k_binv_down<true><<<1, 128, 0, s>>>(pt, nullptr, n, inv, scratch + 1);
+        if (launches) ++*launches;
+        return cudaGetLastError();
+    }
+    if ((e = cudaMemcpyAsync(host_pinned, prod[levels - 1], top * sizeof(fr_t), cudaMemcpyDeviceToHost, s))) return e;
+    if ((e = cudaStreamSynchronize(s))) return e;
+    {
+        std::vector<host::Fr64> el(top), prefix(top);
+        host::Fr64 acc = host::Fr64::one();
+        for (size_t i = 0; i < top; ++i) { el[i] = host::Fr64::from_raw((const uint64_t*)host_pinned[i].l); prefix[i] = acc; acc = acc * el[i]; }
+        memcpy(total_host->l, acc.l, 32);
+        host::Fr64 ia = acc.inverse();
+        for (size_t i = top; i-- > 0;) { host::Fr64 r = ia * prefix[i]; ia = ia * el[i]; memcpy(host_pinned[i].l, r.l, 32); }
+    }
+    fr_t* top_inv = p;   // top <= LAG_SPAN elements
+    if ((e = cudaMemcpyAsync(top_inv, host_pinned, top * sizeof(fr_t), cudaMemcpyHostToDevice, s))) return e;
+    // down: level l elements get their inverses from the inverses of level l+1
+    const fr_t* upper_inv = top_inv;
+    for (size_t l = levels; l-- > 0;) {
+        const size_t nch = size[l + 1];
+        if (l == 0) k_binv_down<true><<<gridfor(nch, 128, cap), 128, 0, s>>>(pt, nullptr, size[0], inv, upper_inv);
+        else { k_binv_down<false><<<gridfor(nch, 128, cap), 128, 0, s>>>(pt, prod[l - 1], size[l], pre[l], upper_inv); upper_inv = pre[l]; }
+        if (launches) ++*launches;
+    }
     return cudaGetLastError();
 }
 // out[0] = prod_{j < m} (pt - j) for a short node range (m below one span)

@@ -9,8 +9,12 @@ constexpr size_t LAG_SPAN = 32;            // nodes per batch inversion (one Fer
 constexpr int LAG_PROD_THREADS = 512;
 inline size_t lag_num_spans(size_t n) { return (n + LAG_SPAN - 1) / LAG_SPAN; }
 
-// inv[j] = 1/(pt - j), j < n; span_prod[ch] = product of (pt - j) over span ch (lag_num_spans(n) elements)
-cudaError_t launch_node_inverses(const fr_t& pt, size_t n, fr_t* inv, fr_t* span_prod, int sm_count, cudaStream_t s);
+// inv[j] = 1/(pt - j), j < n, by a multi-level batch inversion whose single field inversion runs on the host (synchronises the stream once).
+// scratch: lag_binv_scratch(n) device elements; its first lag_num_spans(n) elements are left holding the span products of (pt - j);
+// host_pinned: >= LAG_SPAN pinned elements; *total_host = prod_j (pt - j).
+size_t lag_binv_scratch(size_t n);
+cudaError_t launch_node_inverses(const fr_t& pt, size_t n, fr_t* inv, fr_t* scratch, fr_t* host_pinned, fr_t* total_host, int sm_count, cudaStream_t s,
+                                 unsigned* launches);
 // *out = product of in[0 .. count)   (one block)
 cudaError_t launch_fr_product(const fr_t* in, size_t count, fr_t* out, cudaStream_t s);
 // *out = prod_{j < m} (pt - j), for m below one span (one thread)

@@ -11,6 +11,7 @@
 //   5. the W window sums go to the host, which combines them (W * c doublings: microseconds of work)
 // Integer-pipe bound: ~ n * W * 10 Fq products; memory traffic is the 64-byte gathers of step 3.
 #include <cstdio>
+#include <cstdlib>
 #include <cooperative_groups.h>
 #include "fr_device.cuh"
 #include "g1.cuh"
@@ -56,6 +57,24 @@ __global__ void k_msm_digits(const fr_t* scalars, size_t n, unsigned c, unsigned
             if (d && (unsigned)(__ffs(peers) - 1) == (threadIdx.x & 31)) atomicAdd(&hist[key], (unsigned)__popc(peers));
         }
     }
+}
+
+// *flag != 0 afterwards iff some scalar (canonical form) does not fit 64 bits
+__global__ void k_msm_scalar_probe(const fr_t* scalars, size_t n, unsigned* flag) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    unsigned wide = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        fr_t s = ld256_nc(scalars + i);
+        if (s.is_zero()) continue;
+        s = s.from_mont();
+        wide |= s.l[2] | s.l[3] | s.l[4] | s.l[5] | s.l[6] | s.l[7];
+    }
+    if (__any_sync(0xffffffffu, wide != 0) && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
+}
+cudaError_t launch_scalar_probe(const fr_t* scalars, size_t n, unsigned* flag, int sm_count, cudaStream_t s) {
+    size_t g = (n + 255) / 256; size_t cap = (size_t)sm_count * 8;
+    k_msm_scalar_probe<<<(unsigned)(g < 1 ? 1 : (g < cap ? g : cap)), 256, 0, s>>>(scalars, n, flag);
+    return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------- 2. exclusive scan of u32 counters (three small kernels)
@@ -307,12 +326,15 @@ __global__ void __launch_bounds__(128) k_msm_span_sums(const g1_xyzz* partial, c
 __global__ void __launch_bounds__(MSM_SUM_THREADS) k_msm_bit_sums(const g1_xyzz* R, const g1_xyzz* L, unsigned T, unsigned nbits, g1_xyzz* parts) {
     // block (k, w, p): slice p of gridDim.z of the elements that bit k selects (k == nbits: all L's) of bucket set w
     __shared__ g1_xyzz sh[MSM_SUM_THREADS];
+    // slots k < nbits: the R's whose span index has bit k set; slots nbits and nbits + 1: the two halves of the L's (so that every
+    // block sums the same number of elements, T / 2 / P)
     const unsigned k = blockIdx.x, w = blockIdx.y, p = blockIdx.z, P = gridDim.z;
-    const unsigned U = k == nbits ? T : T / 2;
+    const unsigned U = T > 1 ? T / 2 : (k == nbits ? 1 : 0);
     const unsigned u0 = (unsigned)((unsigned long long)U * p / P), u1 = (unsigned)((unsigned long long)U * (p + 1) / P);
     g1_xyzz acc = g1_xyzz::identity();
-    if (k == nbits) {
-        for (unsigned i = u0 + threadIdx.x; i < u1; i += blockDim.x) acc = acc.add(ld_xyzz(L + (size_t)w * T + i));
+    if (k >= nbits) {
+        const unsigned base = k == nbits ? 0 : U;
+        for (unsigned i = u0 + threadIdx.x; i < u1; i += blockDim.x) acc = acc.add(ld_xyzz(L + (size_t)w * T + base + i));
     } else {
         for (unsigned u = u0 + threadIdx.x; u < u1; u += blockDim.x) {
             const unsigned t = ((u >> k) << (k + 1)) | (1u << k) | (u & ((1u << k) - 1));
@@ -325,37 +347,24 @@ __global__ void __launch_bounds__(MSM_SUM_THREADS) k_msm_bit_sums(const g1_xyzz*
         if (threadIdx.x < s) sh[threadIdx.x] = sh[threadIdx.x].add(sh[threadIdx.x + s]);
         __syncthreads();
     }
-    if (threadIdx.x == 0) st_xyzz(parts + ((size_t)w * (nbits + 1) + k) * P + p, sh[0]);
+    if (threadIdx.x == 0) st_xyzz(parts + ((size_t)w * (nbits + 2) + k) * P + p, sh[0]);
 }
-// block (k, w): adds the P <= 32 slice sums and applies the weight 2^(k + log2 S) of bit k (none for the L sum)
-__global__ void __launch_bounds__(32) k_msm_bit_finish(const g1_xyzz* parts, unsigned P, unsigned nbits, unsigned logS, g1_xyzz* bits) {
+// block (k, w): adds the P <= 32 slice sums of (set w, bit k) and writes the sum as a Jacobian point.  The weights 2^(k + log2 S) and the
+// final additions are a Horner evaluation over span_bits + 1 points per set: ~40 group operations, done by the host in microseconds
+// (on the device they would be a chain of ~20 dependent doublings, ~0.1 ms of pure latency)
+__global__ void __launch_bounds__(32) k_msm_bit_finish(const g1_xyzz* parts, unsigned P, unsigned nbits, g1_jac* out) {
     __shared__ g1_xyzz sh[32];
     const unsigned k = blockIdx.x, w = blockIdx.y;
-    const size_t slot = (size_t)w * (nbits + 1) + k;
+    const size_t slot = (size_t)w * (nbits + 2) + k;
     sh[threadIdx.x] = threadIdx.x < P ? ld_xyzz(parts + slot * P + threadIdx.x) : g1_xyzz::identity();
     __syncwarp();
     for (unsigned s = 16; s > 0; s >>= 1) {
-        if (threadIdx.x < s) sh[threadIdx.x] = sh[threadIdx.x].add(sh[threadIdx.x + s]);
-        __syncwarp();
-    }
-    if (threadIdx.x == 0) {
-        g1_xyzz r = sh[0];
-        if (k != nbits) for (unsigned d = 0; d < k + logS; ++d) r = r.dbl();
-        st_xyzz(bits + slot, r);
-    }
-}
-__global__ void __launch_bounds__(32) k_msm_window_finish(const g1_xyzz* bits, unsigned nbits, g1_jac* out) {
-    __shared__ g1_xyzz sh[32];
-    const unsigned w = blockIdx.x;
-    sh[threadIdx.x] = threadIdx.x <= nbits ? ld_xyzz(bits + (size_t)w * (nbits + 1) + threadIdx.x) : g1_xyzz::identity();
-    __syncwarp();
-    for (unsigned s = 16; s > 0; s >>= 1) {
-        if (threadIdx.x < s) sh[threadIdx.x] = sh[threadIdx.x].add(sh[threadIdx.x + s]);
+        if (threadIdx.x < s && threadIdx.x + s < P) sh[threadIdx.x] = sh[threadIdx.x].add(sh[threadIdx.x + s]);
         __syncwarp();
     }
     if (threadIdx.x == 0) {
         g1_jac j = sh[0].to_jacobian();
-        st256(&out[w].x, j.x); st256(&out[w].y, j.y); st256(&out[w].z, j.z);
+        st256(&out[slot].x, j.x); st256(&out[slot].y, j.y); st256(&out[slot].z, j.z);
     }
 }
 
@@ -447,6 +456,7 @@ unsigned msm_window_bits(size_t n) {
 
 // window width of the precomputed-table mode for a base array of n points
 unsigned msm_table_window_bits(size_t n) {
+    if (const char* env = getenv("TSGPU_TABLE_WINDOW_BITS")) { int v = atoi(env); if (v >= 4 && v <= 24) return (unsigned)v; }   // experiments
     unsigned lg = 0; while (((size_t)1 << (lg + 1)) <= n) ++lg;
     if (lg < 8) lg = 8;
     if (lg >= 24) return 22;   // 12 windows; 2^21 buckets still hold ~100 entries each
@@ -454,13 +464,17 @@ unsigned msm_table_window_bits(size_t n) {
     return lg;
 }
 
-size_t msm_scratch_bytes(size_t nmax, int K, unsigned c, bool shared, MsmLayout* L) {
-    const unsigned W = (255 + c - 1) / c;
+size_t msm_scratch_bytes(size_t nmax, int K, unsigned c, bool shared, MsmLayout* L, unsigned windows) {
+    const unsigned W = windows ? windows : (255 + c - 1) / c;   // windows: only the low digit positions are scanned (scalars known to be short)
     const unsigned sets = (unsigned)K * (shared ? 1u : W);            // bucket sets = windows seen by the reduction
     const size_t nb = (size_t)1 << (c - 1), nbuckets = sets * nb;
     const size_t entries = (size_t)K * W * nmax;
     const size_t max_items = nbuckets + entries / MSM_CHUNK + 1;
-    const unsigned span = nb < MSM_RED_SPAN ? (unsigned)nb : MSM_RED_SPAN;
+    // span of the window reduction: long spans when there are many buckets (throughput-bound), short ones when the dependency
+    // chain of 2 x span additions would dominate (aim at >= 32768 span threads)
+    unsigned span = MSM_RED_SPAN;
+    while (span > 2 && nbuckets / span < 65536) span >>= 1;
+    if (span > nb) span = (unsigned)nb;
     unsigned nbits = 0; while (((size_t)span << nbits) < nb) ++nbits;   // spans per bucket set = 2^nbits
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
@@ -480,14 +494,15 @@ size_t msm_scratch_bytes(size_t nmax, int K, unsigned c, bool shared, MsmLayout*
     L->scan_tmp = take((nbuckets / 1024 + 64) * 4);
     L->partial = take(max_items * sizeof(g1_xyzz));
     L->blockres = take((size_t)2 * sets * L->blocks_per_window * sizeof(g1_xyzz));   // span sums R, then L
-    L->bits = take((size_t)sets * (nbits + 1) * 33 * sizeof(g1_xyzz));   // weighted bit sums, then up to 32 slice sums of each
-    L->window_out = take(sets * sizeof(g1_jac));
+    L->bits = take((size_t)sets * (nbits + 2) * 32 * sizeof(g1_xyzz));   // up to 32 slice sums per (set, slot)
+    L->window_out = take((size_t)sets * (nbits + 2) * sizeof(g1_jac));   // per set: span_bits index-bit sums, then the sums of the two halves of the L's
     return off;
 }
 
 // K independent MSMs in one pass (same window width): their bucket sets are laid side by side, so every phase after the
 // per-job digit extraction / scatter runs once over the union and the latency-bound tails (chunk chains, tree merge, window
-// reduction) overlap across jobs.  Results: L.sets Jacobian points at scratch + L.window_out (job-major).
+// reduction) overlap across jobs.  Results at scratch + L.window_out, per bucket set (job-major) span_bits + 2 Jacobian points:
+// the sums selected by each bit of the span index, then the two halves of the sum of the span-local weighted sums; msm_combine_set() finishes on the host.
 cudaError_t msm_run(const MsmJob* jobs, int K, const MsmLayout& L, unsigned char* scratch, int sm_count,
                     cudaStream_t s, unsigned* launches, cudaEvent_t* ev) {
     unsigned* dig = (unsigned*)(scratch + L.dig); unsigned* sorted = (unsigned*)(scratch + L.sorted);
@@ -541,18 +556,16 @@ cudaError_t msm_run(const MsmJob* jobs, int K, const MsmLayout& L, unsigned char
     {
         const size_t spans = (size_t)L.sets * L.blocks_per_window;
         g1_xyzz* spanR = blockres; g1_xyzz* spanL = blockres + spans; g1_xyzz* bits = (g1_xyzz*)(scratch + L.bits);
-        unsigned logS = 0; while ((1u << logS) < L.span) ++logS;
         k_msm_span_sums<<<gridfor(spans, 128, (size_t)sm_count * 16), 128, 0, s>>>(partial, items, item_off, nb, L.span, spans, spanR, spanL);
-        // enough slices per (set, bit) to put ~4 blocks on every SM, at least one block-load of elements each
-        unsigned P = (unsigned)((4 * (size_t)sm_count + (L.span_bits + 1) * L.sets - 1) / ((L.span_bits + 1) * L.sets));
+        // two blocks of the bit-sum kernel fit an SM (128 registers x 256 threads): slice every (set, slot) sum so that one wave covers the machine
+        unsigned P = (unsigned)(2 * (size_t)sm_count / ((L.span_bits + 2) * L.sets));
         const unsigned maxP = L.blocks_per_window / (2 * MSM_SUM_THREADS);
         if (P > maxP) P = maxP;
         if (P > 32) P = 32;
         if (P < 1) P = 1;
-        g1_xyzz* parts = bits + (size_t)L.sets * (L.span_bits + 1);
-        k_msm_bit_sums<<<dim3(L.span_bits + 1, L.sets, P), MSM_SUM_THREADS, 0, s>>>(spanR, spanL, L.blocks_per_window, L.span_bits, parts);
-        k_msm_bit_finish<<<dim3(L.span_bits + 1, L.sets), 32, 0, s>>>(parts, P, L.span_bits, logS, bits);
-        k_msm_window_finish<<<L.sets, 32, 0, s>>>(bits, L.span_bits, wout);
+        g1_xyzz* parts = bits;
+        k_msm_bit_sums<<<dim3(L.span_bits + 2, L.sets, P), MSM_SUM_THREADS, 0, s>>>(spanR, spanL, L.blocks_per_window, L.span_bits, parts);
+        k_msm_bit_finish<<<dim3(L.span_bits + 2, L.sets), 32, 0, s>>>(parts, P, L.span_bits, wout);
     }
     if (ev) cudaEventRecord(ev[4], s);
     if (launches) *launches += 16 + 2 * (unsigned)K;
@@ -574,8 +587,9 @@ __global__ void k_affine_to_xyzz(const g1_affine* in, size_t n, g1_xyzz* out) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) st_xyzz(out + i, g1_xyzz::from_affine(ld_affine(in + i)));
 }
 // table: W * n affine points (window 0 = a copy of bases); cur: n XYZZ scratch points
-cudaError_t msm_build_table(const g1_affine* bases, size_t n, unsigned c, g1_affine* table, g1_xyzz* cur, int sm_count, cudaStream_t s, unsigned* launches) {
-    const unsigned W = (255 + c - 1) / c;
+cudaError_t msm_build_table(const g1_affine* bases, size_t n, unsigned c, g1_affine* table, g1_xyzz* cur, int sm_count, cudaStream_t s, unsigned* launches,
+                            unsigned windows) {
+    const unsigned W = windows ? windows : (255 + c - 1) / c;
     cudaError_t e;
     if ((e = cudaMemcpyAsync(table, bases, n * sizeof(g1_affine), cudaMemcpyDeviceToDevice, s))) return e;
     k_affine_to_xyzz<<<gridfor(n, 256, (size_t)sm_count * 8), 256, 0, s>>>(bases, n, cur);

@@ -7,7 +7,8 @@ namespace tsg {
 
 constexpr unsigned MSM_CHUNK = 64;        // max entries one work item adds into its accumulator (bounds the serial chain of one thread)
 constexpr int MSM_ACC_THREADS = 128;
-constexpr unsigned MSM_RED_SPAN = 16;     // buckets per thread in the window reduction (2 x span additions deep; the bit-decomposed tail costs log2(buckets / span) / 2 additions per span)
+constexpr unsigned MSM_RED_SPAN = 8;      // most buckets per thread in the window reduction (2 x span additions deep; the bit-decomposed tail costs
+                                          // log2(buckets / span) / 2 additions per span); small bucket sets use shorter spans to keep the chain short
 constexpr int MSM_SUM_THREADS = 256;
 constexpr size_t MSM_POW_SPAN = 64;       // consecutive tau powers per thread
 constexpr size_t MSM_INV_SPAN = 32;       // points per batch inversion
@@ -31,12 +32,18 @@ struct MsmLayout {
 
 unsigned msm_window_bits(size_t n);
 unsigned msm_table_window_bits(size_t n);
-size_t msm_scratch_bytes(size_t nmax, int K, unsigned c, bool shared, MsmLayout* L);
-// runs every device phase; the L.sets bucket-set sums (Jacobian, job-major) are left at scratch + L.window_out
+size_t msm_scratch_bytes(size_t nmax, int K, unsigned c, bool shared, MsmLayout* L, unsigned windows = 0);   // windows > 0: scan only that many low digit positions
+// runs every device phase; per bucket set (job-major) span_bits + 2 Jacobian points are left at scratch + L.window_out:
+// S_w = 2^log2(span) * sum_k 2^k P[k] + P[span_bits] + P[span_bits + 1]  (finished on the host: a Horner pass of ~40 group operations)
 cudaError_t msm_run(const MsmJob* jobs, int K, const MsmLayout& L, unsigned char* scratch, int sm_count,
                     cudaStream_t s, unsigned* launches, cudaEvent_t* ev = nullptr);   // ev[5]: start | sort done | accumulate done | chunk merge done | reduce done
 // table[w * n + i] = 2^(c w) * bases[i] for w < ceil(255 / c); cur: n XYZZ points of scratch
-cudaError_t msm_build_table(const g1_affine* bases, size_t n, unsigned c, g1_affine* table, g1_xyzz* cur, int sm_count, cudaStream_t s, unsigned* launches);
+cudaError_t msm_build_table(const g1_affine* bases, size_t n, unsigned c, g1_affine* table, g1_xyzz* cur, int sm_count, cudaStream_t s, unsigned* launches,
+                            unsigned windows = 0);
+// *flag (zeroed by the caller) becomes non-zero iff some scalar does not fit 64 bits
+cudaError_t launch_scalar_probe(const fr_t* scalars, size_t n, unsigned* flag, int sm_count, cudaStream_t s);
+constexpr unsigned MSM_SHORT_C = 17;        // table mode for scalars below 2^64: 17-bit windows (16-bit addresses stay positive digits: no carry bucket) ...
+constexpr unsigned MSM_SHORT_WINDOWS = 4;   // ... of which four cover 64 bits plus the signed-digit carry
 
 cudaError_t launch_tau_powers(const fr_t& tau, size_t first, size_t n, fr_t* out, int sm_count, cudaStream_t s);
 cudaError_t launch_fixed_base_mul(const fr_t* scalars, size_t n, const g1_affine* table, g1_xyzz* out, int sm_count, cudaStream_t s);
