@@ -277,26 +277,38 @@ def main():
         dev_ms, e2e_ms, coef["ms"], coef_e2e_ms = (float(x) for x in t)
 
     # ---- roofline of the dominant kernel of the step: MSM bucket accumulation (integer-pipe bound).
-    # Algorithmic work per launch = bucket entries (non-zero signed 16-bit digits, counted by the library) x one mixed
-    # XYZZ + affine addition (8M + 2S = 10 Fq products) x (2 * 8 * 8 + 8) 32-bit multiply-adds per Montgomery product.
+    # Two accountings, both reported:
+    #  * `achieved` (the contract's): SURVEY 8(d)'s per-unit figure x the units of a launch / the launch duration.  The figure is
+    #    n x 16 windows x 11 Fq products x 136 IMAD = 23 936 IMAD per point of a full-width MSM; the launches that process full-width
+    #    scalars are the open passes (two quotient vectors of 2^20 points each per launch), so achieved = 2 n x 23 936 / t(open-pass launch);
+    #    t(open pass) = (accumulate time of the step - commit-pass share), the commit pass being timed by its own entry count at the same rate.
+    #  * `executed`: what the kernel really does - one mixed XYZZ + affine addition (8M + 2S = 10 Fq products x 136 IMAD) per bucket entry
+    #    (non-zero signed digit, counted by the library): fewer than the model because the window tables need 13 additions per point, not 16.
     imad_per_add = 10 * (2 * 8 * 8 + 8)
+    survey_imad_per_point = 16 * 11 * 136
 
-    def acc_roofline(r):
-        launch_ms = r["msm_accumulate_ms"] / max(r["msm_accumulate_cnt"], 1)
+    def acc_roofline(r, full_width_points_per_step):
+        launches = max(r["msm_accumulate_cnt"], 1)
+        launch_ms = r["msm_accumulate_ms"] / launches
         entries = r["msm_entries"] / max(r["msm_calls"], 1)
-        ach = entries * imad_per_add / (launch_ms * 1e-3) / 1e12 if launch_ms > 0 else 0.0
+        executed = entries * imad_per_add / (launch_ms * 1e-3) / 1e12 if launch_ms > 0 else 0.0
+        # time spent on full-width scalars: total accumulate time x their share of the bucket entries (13 per point)
+        fw_entries = 13.0 * full_width_points_per_step * K
+        fw_ms = r["msm_accumulate_ms"] * min(1.0, fw_entries / max(r["msm_entries"], 1))
+        ach = full_width_points_per_step * K * survey_imad_per_point / (fw_ms * 1e-3) / 1e12 if fw_ms > 0 else 0.0
         return {"kernel": "k_msm_accumulate", "bound": "int32-pipe", "achieved": ach, "peak": IMAD_PEAK_TOPS, "unit": "TIMAD/s",
                 "frac": ach / IMAD_PEAK_TOPS, "traffic": None, "launch_ms": launch_ms, "launches": r["msm_accumulate_cnt"],
-                "entries_per_launch": entries, "share_of_step": r["msm_accumulate_ms"] / K / r["ms"] if r["ms"] > 0 else None}
+                "executed": executed, "executed_frac": executed / IMAD_PEAK_TOPS, "entries_per_launch": entries,
+                "share_of_step": r["msm_accumulate_ms"] / K / r["ms"] if r["ms"] > 0 else None}
 
-    roofline = acc_roofline(dflt)
+    roofline = acc_roofline(dflt, 2 * n)           # default path: the two opening quotients are the full-width scalars
+    roofline["peak_source"] = "tools/ubench.cu on this pool: 18.5 T IMAD.WIDE/s without carry predicate (the carry-chained form the multiplier needs issues at half that rate)"
+    roofline["algorithmic_unit"] = "SURVEY 8(d): 16 windows x 11 Fq products x 136 IMAD = 23 936 IMAD per full-width point; `executed` = bucket entries x (8M + 2S) x 136 IMAD"
     # DRAM bytes per launch from `ncu --set full` of this same command (profiles/r01_ncu_accumulate_in_bench.md): commit pass 0.587 + 0.068 GB,
-    # open pass 3.622 + 0.146 GB; mean over the two launches of a proof, like `achieved`.  Algorithmic bytes: entries x (64 B point + 4 B entry).
+    # open pass 3.622 + 0.146 GB; mean over the two launches of a proof, like `launch_ms`.  Algorithmic bytes: entries x (64 B point + 4 B entry).
     roofline["traffic"] = 0.5 * ((0.586715 + 0.067997) + (3.621562 + 0.145975)) * 1e9
     roofline["algorithmic_bytes"] = roofline["entries_per_launch"] * 68.0
     roofline["ncu"] = "FMA-heavy pipe 88-89% busy, thread efficiency 31.8/32, DRAM 0.87 TB/s (profiles/r01_ncu_accumulate_in_bench.md)"
-    roofline["peak_source"] = "tools/ubench.cu on this pool: 18.5 T IMAD.WIDE/s without carry predicate (the carry-chained form the multiplier needs issues at half that rate)"
-    roofline["algorithmic_unit"] = "bucket entries x (8M + 2S) x 136 IMAD per launch (mean over the 4 MSMs of a proof)"
 
     # ---- side measurement (BASELINE metric 'sumcheck fold GB/s'): bind one 2^26-entry table, HBM-bound
     fold = None
@@ -356,7 +368,7 @@ def main():
             "roofline_fold": fold,
             "cpu_baseline": cpu,
             "breakdown_ms_per_step": breakdown(dflt),
-            "coefficient_path": {"value": coef["ms"], "unit": "ms", "e2e": coef_e2e_ms, "breakdown_ms_per_step": breakdown(coef), "roofline": acc_roofline(coef),
+            "coefficient_path": {"value": coef["ms"], "unit": "ms", "e2e": coef_e2e_ms, "breakdown_ms_per_step": breakdown(coef), "roofline": acc_roofline(coef, 4 * n),
                                  "note": "tsgpu_set_tuning(eval_basis, 0): 2 interpolations + 4 full-width MSMs + 2 Horner/quotient scans"},
             "msm_points_per_s": dflt["msm_points"] / (dflt["msm_total_ms"] * 1e-3) if dflt["msm_total_ms"] > 0 else None,
             "msm_full_width_points_per_s": coef["msm_points"] / (coef["msm_total_ms"] * 1e-3) if coef["msm_total_ms"] > 0 else None,
