@@ -118,6 +118,31 @@ TSG_HD void redc_step(uint32_t* X, uint32_t* Y) {
     X[7] = ptx::addc(X[7], 0u);
 }
 
+// Same word step with the 8 products formed by plain mul.wide (IMAD.WIDE without a carry predicate: full issue rate on the FMA-heavy
+// pipe) and added with add.cc chains on the ALU pipe.  The carry-chained IMAD.WIDE.U32.X occupies the FMA-heavy pipe twice as long, and
+// that pipe bounds every arithmetic kernel here, so trading some of those for ALU additions balances the two pipes (see TSG_MIX_ROWS).
+template <class P>
+TSG_HD void redc_step_plain(uint32_t* X, uint32_t* Y) {
+    uint32_t m = ptx::mul_lo(Y[0], P::INV);
+    uint32_t t[8], u[8];
+    ptx::mul_wide(t[0], t[1], P::mod(1), m); ptx::mul_wide(t[2], t[3], P::mod(3), m);
+    ptx::mul_wide(t[4], t[5], P::mod(5), m); ptx::mul_wide(t[6], t[7], P::mod(7), m);
+    ptx::mul_wide(u[0], u[1], P::mod(0), m); ptx::mul_wide(u[2], u[3], P::mod(2), m);
+    ptx::mul_wide(u[4], u[5], P::mod(4), m); ptx::mul_wide(u[6], u[7], P::mod(6), m);
+    X[0] = ptx::add_cc(X[0], t[0]);
+#pragma unroll
+    for (int k = 1; k < 7; ++k) X[k] = ptx::addc_cc(X[k], t[k]);
+    X[7] = ptx::addc(X[7], t[7]);
+    Y[0] = ptx::add_cc(Y[0], u[0]);
+#pragma unroll
+    for (int k = 1; k < 8; ++k) Y[k] = ptx::addc_cc(Y[k], u[k]);
+    X[7] = ptx::addc(X[7], 0u);
+}
+
+#ifndef TSG_MIX_ROWS
+#define TSG_MIX_ROWS 0      // number of word steps (0..8) whose reduction rows use plain products + ALU additions
+#endif
+
 // r = a * b * 2^-256 mod p, inputs < p, output < p
 template <class P>
 TSG_HD void mont_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
@@ -130,7 +155,7 @@ TSG_HD void mont_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
             ptx::mul_wide(Y[j], Y[j + 1], a[j], bi);
             ptx::mul_wide(X[j], X[j + 1], a[j + 1], bi);
         }
-        redc_step<P>(X, Y);
+        if (0 < TSG_MIX_ROWS) redc_step_plain<P>(X, Y); else redc_step<P>(X, Y);
     }
 #pragma unroll
     for (int i = 1; i < 8; ++i) {
@@ -155,7 +180,7 @@ TSG_HD void mont_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
         Y[6] = ptx::madc_lo_cc(a[6], bi, Y[6]);
         Y[7] = ptx::madc_hi_cc(a[6], bi, Y[7]);
         X[7] = ptx::addc(X[7], 0u);
-        redc_step<P>(X, Y);
+        if (i < TSG_MIX_ROWS) redc_step_plain<P>(X, Y); else redc_step<P>(X, Y);
     }
     // after step 7: Y = acc[1] (Y[0] == 0), X = acc[0]; result = X + (Y >> 32)
     {

@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 @pytest.fixture(scope="module")
 def harness():
     out = os.path.join(tempfile.gettempdir(), f"tsg_limb_harness_{os.getpid()}.so")
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas",
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas", *os.environ.get("TSG_HARNESS_CXXFLAGS", "").split(),
                            "-I", os.path.join(ROOT, "multilinear-map-cryptography_b200", "csrc"),
                            "-o", out, os.path.join(ROOT, "tests", "helpers", "limb_harness.cpp")])
     lib = C.CDLL(out)
