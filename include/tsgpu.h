@@ -146,7 +146,7 @@ int tsgpu_poly_upload_padded(tsgpu_ctx* ctx, const tsgpu_fr* vals, size_t n, siz
  * monomial conversion, NTTs over Fr.  n must be a power of two <= 2^27 (Twist/Shout pad to one);
  * otherwise TSGPU_E_POLYNOMIAL.  prepare() builds the size-dependent tables once (done implicitly on first use). */
 int tsgpu_interpolate_prepare(tsgpu_ctx* ctx, unsigned log_n);
-int tsgpu_interpolate_iota(tsgpu_ctx* ctx, const tsgpu_fr* values, size_t n, tsgpu_fr* coeffs);
+int tsgpu_interpolate_iota(tsgpu_ctx* ctx, const tsgpu_fr* values, size_t n, tsgpu_fr* coeffs);   /* any n (host buffers) */
 int tsgpu_poly_interpolate_iota(tsgpu_ctx* ctx, tsgpu_poly* values_to_coeffs_in_place);
 void tsgpu_poly_free(tsgpu_ctx* ctx, tsgpu_poly* p);
 
@@ -185,6 +185,12 @@ int tsgpu_kzg_open_batch_dev(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_p
 int tsgpu_kzg_commit_values_batch_dev(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_poly* const* values, size_t count, tsgpu_g1* outs);
 int tsgpu_kzg_open_values_batch_dev(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_poly* const* values, size_t count, const tsgpu_fr* z,
                                     tsgpu_fr* out_values, tsgpu_g1* proofs);
+/* ---- VectorCommitmentScheme for KZGVectorCommitment  (src/commitments.rs:378-483) ------------------------------
+ * commit: KZG commitment to lagrange_interpolate((i, vector[i])) - any length, degree < len.
+ * open:   (vector[index], opening proof at the point Fr::from(index)); TSGPU_E_COMMITMENT "Index out of bounds".
+ * verify: the KZG pairing check at that point (CPU). */
+int tsgpu_vector_commit(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_fr* vector, size_t n, tsgpu_g1* out);
+int tsgpu_vector_open(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_fr* vector, size_t n, size_t index, tsgpu_fr* value, tsgpu_g1* proof);
 /* plain G1 MSM over caller-supplied affine bases: sum_i scalars[i] * bases[i] */
 int tsgpu_msm_g1(tsgpu_ctx* ctx, const tsgpu_g1a* bases, const tsgpu_fr* scalars, size_t n, tsgpu_g1* out);
 /* CPU helpers on single points: KZGCommitmentValue::hash (commitments.rs:73-84), ark-serialize compressed bytes
@@ -235,6 +241,9 @@ void tsgpu_comm_destroy(tsgpu_ctx* ctx);
 /* all-gather of `bytes` (multiple of 8) per rank, host to host: e.g. per-rank partial MSM results (point-sliced commitment),
  * which the caller adds with tsgpu_g1_add */
 int tsgpu_comm_allgather(tsgpu_ctx* ctx, const void* in, size_t bytes, void* out);
+/* MultilinearExtension::evaluate of a table sliced over the ranks (`local`: this rank's slice, num_vars - log2(ranks) variables);
+ * one local pass + an all-reduce of one field element; every rank gets the value */
+int tsgpu_table_evaluate_sharded(tsgpu_ctx* ctx, const tsgpu_table* local, unsigned num_vars, const tsgpu_fr* point, tsgpu_fr* out);
 /* SumCheck::prove for a product of tables (src/sumcheck.rs:56-110) with the hypercube sliced over the ranks: `tables` are this
  * rank's slices (reference index high bits = rank; num_vars - log2(ranks) variables; consumed).  One 256-byte integer
  * all-reduce of the round evaluations per round; every rank returns the same proof.  Outputs as tsgpu_sumcheck_prove_product. */
@@ -276,6 +285,8 @@ int tsgpu_shout_verify(tsgpu_ctx* ctx, const tsgpu_params* params, const tsgpu_p
 /* KZGCommitment::verify / batch_verify with the verification key held in the params (CPU, BN254 optimal-ate pairing) */
 int tsgpu_kzg_verify(const tsgpu_params* params, const tsgpu_g1* commitment, const tsgpu_fr* point, const tsgpu_fr* value,
                      const tsgpu_g1* proof, int* valid);
+/* KZGVectorCommitment::verify (src/commitments.rs:471-481) */
+int tsgpu_vector_verify(const tsgpu_params* params, const tsgpu_g1* commitment, size_t index, const tsgpu_fr* value, const tsgpu_g1* proof, int* valid);
 int tsgpu_kzg_batch_verify(const tsgpu_params* params, const tsgpu_g1* commitments, const tsgpu_fr* points, const tsgpu_fr* values,
                            const tsgpu_g1* proofs, size_t n, int* valid);
 /* pairing self-test hooks: prod_i e(a_i G1, b_i G2) == 1 ?;  G2 generator on the twist and of order r */

@@ -113,6 +113,38 @@ def kzg_verify(verifier_params, commitment, point, value, proof) -> bool:
     return bool(ok.value)
 
 
+class KZGVectorCommitment:
+    """Mirror of `impl VectorCommitmentScheme for KZGVectorCommitment` (src/commitments.rs:407-483): associated functions.
+    `params` is an Srs handle; vectors are host arrays uint64[n, 4] of any length."""
+
+    @staticmethod
+    def commit(params: Srs, vector) -> np.ndarray:
+        ctx = params.ctx
+        vector = _fr(vector) if len(vector) else np.empty((0, 4), dtype=np.uint64)
+        out = np.empty(12, dtype=np.uint64)
+        ctx.check(lib().tsgpu_vector_commit(ctx._h, params._h, _p(vector), C.c_size_t(vector.shape[0]), _p(out)))
+        return out
+
+    @staticmethod
+    def open(params: Srs, vector, index: int):
+        """-> (value, proof); Commitment("Index out of bounds") beyond the vector"""
+        ctx = params.ctx
+        vector = _fr(vector) if len(vector) else np.empty((0, 4), dtype=np.uint64)
+        value = np.empty(4, dtype=np.uint64); proof = np.empty(12, dtype=np.uint64)
+        ctx.check(lib().tsgpu_vector_open(ctx._h, params._h, _p(vector), C.c_size_t(vector.shape[0]), C.c_size_t(index), _p(value), _p(proof)))
+        return value, proof
+
+    @staticmethod
+    def verify(verifier_params, commitment, index: int, value, proof) -> bool:
+        ok = C.c_int(0)
+        commitment = np.ascontiguousarray(commitment, dtype=np.uint64).reshape(12)
+        proof = np.ascontiguousarray(proof, dtype=np.uint64).reshape(12)
+        rc = lib().tsgpu_vector_verify(verifier_params._h, _p(commitment), C.c_size_t(index), _p(_fr(value, 1)), _p(proof), C.byref(ok))
+        if rc:
+            raise TwistAndShoutError(rc, "vector verify: bad arguments")
+        return bool(ok.value)
+
+
 def kzg_batch_verify(verifier_params, commitments, points, values, proofs) -> bool:
     """KZGCommitment::batch_verify (src/commitments.rs:230-301)"""
     commitments = np.ascontiguousarray(commitments, dtype=np.uint64).reshape(-1, 12)

@@ -307,6 +307,13 @@ class Table:
         self.ctx.check(lib().tsgpu_table_evaluate(self.ctx._h, self._h, _p(point), _p(out)))
         return out
 
+    def evaluate_sharded(self, num_vars: int, point) -> np.ndarray:
+        """this table is the local slice (high index bits = rank) of a num_vars-variable MLE spread over ctx's communicator"""
+        point = _fr(point, num_vars)
+        out = np.empty(4, dtype=np.uint64)
+        self.ctx.check(lib().tsgpu_table_evaluate_sharded(self.ctx._h, self._h, C.c_uint(num_vars), _p(point), _p(out)))
+        return out
+
     def partial_evaluate(self, fixed) -> "Table":
         fixed = _fr(fixed)
         h = C.c_void_p()

@@ -346,12 +346,31 @@ int tsgpu_poly_interpolate_iota(tsgpu_ctx* ctx, tsgpu_poly* p) {
     TSG_CUDA(ctx, interp_run(ctx, p->d, (unsigned)l, p->d));
     return TSGPU_OK;
 }
-int tsgpu_interpolate_iota(tsgpu_ctx* ctx, const tsgpu_fr* values, size_t n, tsgpu_fr* coeffs) {
+// lagrange_interpolate on (i, values[i]), i < n, for ANY n: the Newton coefficients of the n points, zero-extended to the next power of
+// two, are converted to the monomial basis at that size (higher Newton terms being zero does not change the polynomial); n coefficients back
+static int interpolate_any_dev(tsgpu_ctx* ctx, const tsgpu_fr* values, size_t n, tsgpu_poly** out) {
+    size_t N = 1; while (N < n) N <<= 1;
+    int l = log2_exact(N);
+    if (l > 27) return fail(ctx, TSGPU_E_POLYNOMIAL, "interpolation size exceeds the 2^28 two-adicity of Fr");
     tsgpu_poly* p = nullptr;
-    int rc = tsgpu_poly_upload(ctx, values, n, &p);
+    int rc = tsgpu_poly_upload_padded(ctx, values, n, N, &p);
     if (rc) return rc;
-    rc = tsgpu_poly_interpolate_iota(ctx, p);
-    if (!rc) rc = tsgpu_poly_download(ctx, p, coeffs);
+    {
+        KernelTimer kt(ctx, "interpolate");
+        cudaError_t e = interp_run(ctx, p->d, (unsigned)l, p->d, n);
+        if (e != cudaSuccess) { tsgpu_poly_free(ctx, p); return cuda_fail(ctx, e, "interpolation"); }
+    }
+    p->n = n;       // degree < n: the tail of the buffer is zero
+    *out = p;
+    return TSGPU_OK;
+}
+int tsgpu_interpolate_iota(tsgpu_ctx* ctx, const tsgpu_fr* values, size_t n, tsgpu_fr* coeffs) {
+    if (!ctx || (n && (!values || !coeffs))) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    if (n == 0) return TSGPU_OK;   // lagrange_interpolate(&[]) = [] (polynomials.rs:303-305)
+    tsgpu_poly* p = nullptr;
+    int rc = interpolate_any_dev(ctx, values, n, &p);
+    if (rc) return rc;
+    rc = tsgpu_poly_download(ctx, p, coeffs);
     tsgpu_poly_free(ctx, p);
     return rc;
 }
@@ -676,6 +695,38 @@ int tsgpu_kzg_open_values_dev(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_
     if (!values || !value || !proof) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
     return tsgpu_kzg_open_values_batch_dev(ctx, srs, &values, 1, z, value, proof);
 }
+// ------------------------------------------------------------------------------------------- KZGVectorCommitment (src/commitments.rs:407-483)
+// commit(vector) = KZGCommitment::commit(lagrange_interpolate((i, vector[i]))) - any length (no padding: the degree is < len)
+int tsgpu_vector_commit(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_fr* vector, size_t n, tsgpu_g1* out) {
+    if (!ctx || !srs || !out || (!vector && n)) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    if (n > srs->n) return fail(ctx, TSGPU_E_COMMITMENT, "Polynomial degree exceeds setup size");
+    if (n == 0) { G1J id = G1J::identity(); memcpy(out, &id, 96); return TSGPU_OK; }
+    tsgpu_poly* p = nullptr;
+    int rc = interpolate_any_dev(ctx, vector, n, &p);
+    if (rc) return rc;
+    rc = tsgpu_kzg_commit_dev(ctx, srs, p, out);
+    tsgpu_poly_free(ctx, p);
+    return rc;
+}
+// open(vector, index): (vector[index], KZGCommitment::open(poly, Fr::from(index)).1); "Index out of bounds" beyond the vector
+int tsgpu_vector_open(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_fr* vector, size_t n, size_t index, tsgpu_fr* value, tsgpu_g1* proof) {
+    if (!ctx || !srs || !value || !proof || (!vector && n)) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    if (index >= n) return fail(ctx, TSGPU_E_COMMITMENT, "Index out of bounds");                       // commitments.rs:436-440
+    if (n - 1 > srs->n) return fail(ctx, TSGPU_E_COMMITMENT, "Polynomial degree exceeds setup size");
+    tsgpu_poly* p = nullptr;
+    int rc = interpolate_any_dev(ctx, vector, n, &p);
+    if (rc) return rc;
+    Fr64 pt = Fr64::from_u64((uint64_t)index);
+    tsgpu_fr z; memcpy(z.l, pt.l, 32);
+    tsgpu_fr opened;
+    rc = tsgpu_kzg_open_dev(ctx, srs, p, &z, &opened, proof);
+    tsgpu_poly_free(ctx, p);
+    if (rc) return rc;
+    if (memcmp(opened.l, vector[index].l, 32)) return fail(ctx, TSGPU_E_COMMITMENT, "Opened value does not match vector entry");   // commitments.rs:461-465
+    *value = vector[index];
+    return TSGPU_OK;
+}
+
 // group addition of two G1Projective values on the CPU (combining per-rank MSM results)
 void tsgpu_g1_add(const tsgpu_g1* a, const tsgpu_g1* b, tsgpu_g1* out) {
     G1J x, y; memcpy(&x, a, 96); memcpy(&y, b, 96);

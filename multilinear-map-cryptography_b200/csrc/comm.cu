@@ -170,6 +170,32 @@ int tsgpu_comm_allgather(tsgpu_ctx* ctx, const void* in, size_t bytes, void* out
     return TSGPU_OK;
 }
 
+// MultilinearExtension::evaluate (src/polynomials.rs:85-122) of a table sliced over the ranks: rank g holds the entries whose index has
+// high bits g (num_vars - log2 G local variables).  evaluate(point) = sum_g eq(point_high, g) * local_g.evaluate(point_low): one local
+// streaming pass, one scalar weight on the host, one exact all-reduce of a single field element.  Every rank gets the value.
+int tsgpu_table_evaluate_sharded(tsgpu_ctx* ctx, const tsgpu_table* local, unsigned num_vars, const tsgpu_fr* point, tsgpu_fr* out) {
+    if (!ctx || !local || !point || !out) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    Comm* c = comm_of(ctx);
+    const int G = c ? c->nranks : 1, rank = c ? c->rank : 0;
+    unsigned logG = 0; while ((1 << logG) < G) ++logG;
+    if (num_vars < logG || local->num_vars != num_vars - logG) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "Number of variables must match");
+    const unsigned n_local = num_vars - logG;
+    tsgpu_fr v;
+    int rc = tsgpu_table_evaluate(ctx, local, point, &v);          // uses point[0 .. n_local)
+    if (rc) return rc;
+    fr_t acc; memcpy(acc.l, v.l, 32);
+    for (unsigned k = 0; k < logG; ++k) {
+        fr_t p; memcpy(p.l, point[n_local + k].l, 32);
+        acc = acc * (((rank >> k) & 1) ? p : fr_t::one() - p);
+    }
+    memcpy(ctx->host_out, acc.l, 32);
+    TSG_CUDA(ctx, cudaMemcpyAsync(ctx->dev_out, ctx->host_out, sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+    fr_t total;
+    if ((rc = allreduce_dev_out(ctx, 1, &total))) return rc;
+    memcpy(out->l, total.l, 32);
+    return TSGPU_OK;
+}
+
 // SumCheck::new(num_vars, claimed_sum).prove(|v| prod_t mle_t.evaluate(v), transcript) with the hypercube sliced over the ranks of
 // the context's communicator.  tables: this rank's slices (num_vars - log2 G variables each, consumed).  Every rank returns the same
 // round polynomials (num_vars x 4), final evaluation, challenges (num_vars) and fully bound table values (d).

@@ -314,7 +314,8 @@ struct InterpPlan {
     }
 
     // vals (n = 2^logn entries, natural order) -> coeffs (n entries, low -> high).  vals and coeffs may alias.
-    cudaError_t run(const fr_t* vals, unsigned logn, fr_t* coeffs) {
+    // n_valid < n: only the first n_valid values are interpolation data (degree < n_valid); the Newton coefficients beyond are zero
+    cudaError_t run(const fr_t* vals, unsigned logn, fr_t* coeffs, size_t n_valid) {
         cudaError_t e;
         const size_t n = (size_t)1 << logn;
         if ((e = prepare(logn))) return e;
@@ -332,6 +333,7 @@ struct InterpPlan {
         k_mul_table<<<gridfor(M, 256, cap()), 256, 0, st()>>>(bufA, vals, ifact, n, M, 0, 1); ++launches;
         if ((e = conv_with_spectrum(bufA, logM, 1, bhat[logn]))) return e;
         if ((e = cudaMemcpyAsync(coeffs, bufA, n * 32, cudaMemcpyDeviceToDevice, st()))) return e;
+        if (n_valid < n && (e = cudaMemsetAsync(coeffs + n_valid, 0, (n - n_valid) * 32, st()))) return e;
         // ---- step B base: blocks of min(n, 32)
         const unsigned blen_log = logn < BASE_LOG ? logn : BASE_LOG;
         const size_t blen = (size_t)1 << blen_log, nblk = n >> blen_log;
@@ -374,10 +376,10 @@ cudaError_t interp_factorials(tsgpu_ctx* ctx, unsigned logn, const fr_t** ifact)
     *ifact = p->ifact;
     return e;
 }
-cudaError_t interp_run(tsgpu_ctx* ctx, const fr_t* vals, unsigned logn, fr_t* coeffs) {
+cudaError_t interp_run(tsgpu_ctx* ctx, const fr_t* vals, unsigned logn, fr_t* coeffs, size_t n_valid) {
     InterpPlan* p = interp_plan(ctx);
     p->launches = 0;
-    cudaError_t e = p->run(vals, logn, coeffs);
+    cudaError_t e = p->run(vals, logn, coeffs, n_valid ? n_valid : (size_t)1 << logn);
     ctx->launches += p->launches;
     return e;
 }

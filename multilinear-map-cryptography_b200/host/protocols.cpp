@@ -293,6 +293,12 @@ int tsgpu_kzg_verify(const tsgpu_params* params, const tsgpu_g1* commitment, con
     *valid = kzg_verify(params->vk, C, Fr64::from_raw(point->l), Fr64::from_raw(value->l), pi) ? 1 : 0;
     return TSGPU_OK;
 }
+// KZGVectorCommitment::verify (src/commitments.rs:471-481): the KZG check at point Fr::from(index)
+int tsgpu_vector_verify(const tsgpu_params* params, const tsgpu_g1* commitment, size_t index, const tsgpu_fr* value, const tsgpu_g1* proof, int* valid) {
+    Fr64 pt = Fr64::from_u64((uint64_t)index);
+    tsgpu_fr z; memcpy(z.l, pt.l, 32);
+    return tsgpu_kzg_verify(params, commitment, &z, value, proof, valid);
+}
 // KZGCommitment::batch_verify (src/commitments.rs:230-301): random linear combination with gamma_i = Fr::rand of
 // ChaCha20Rng::from_seed([42; 32]); TSGPU_E_COMMITMENT "Batch verify input lengths must match" is the caller's
 // concern here (one length parameter).  Empty batch verifies.  NOTE: the reference formula applies gamma_i to the proof AND to

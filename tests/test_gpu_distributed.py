@@ -44,6 +44,8 @@ def test_native_sharded_prove_one_rank_equals_unsharded(tsgpu, oracle, nv, d):
         proof, chals, finals = tsgpu.SumCheck(nv, claimed).prove_product_sharded(c, [c.table_upload(t) for t in tables], tsgpu.Transcript(), return_aux=True)
         assert (proof.round_polynomials == ref["round_polynomials"]).all() and (proof.final_evaluation == ref["final_evaluation"]).all()
         assert (finals == ref["finals"]).all()
+        pt = oracle.chacha_fr_rand(seed_bytes(nv + 3), nv).reshape(nv, 4)
+        assert (c.table_upload(tables[0]).evaluate_sharded(nv, pt) == oracle.mle_evaluate(tables[0], pt, fold=True)).all()
         with pytest.raises(tsgpu.TwistAndShoutError) as e:       # wrong claim: the reference's round-0 error
             tsgpu.SumCheck(nv, tsgpu.fe(12345)).prove_product_sharded(c, [c.table_upload(t) for t in tables], tsgpu.Transcript())
         assert e.value.variant == "SumCheck" and "Round 0 consistency check failed" in str(e.value)
@@ -80,6 +82,10 @@ def _native_worker(rank, world, port, nv, d, q):
         proof, chals, finals = ts.SumCheck(nv, claimed).prove_product_sharded(ctx, [ctx.table_upload(t[lo:hi]) for t in full], ts.Transcript(), return_aux=True)
         ok = (proof.round_polynomials == ref["round_polynomials"]).all() and (proof.final_evaluation == ref["final_evaluation"]).all()
         ok = ok and (finals == ref["finals"]).all()
+        # sharded MultilinearExtension::evaluate of table 0
+        pt = O.chacha_fr_rand(bytes([90]) * 32, nv).reshape(nv, 4)
+        got = ctx.table_upload(full[0][lo:hi]).evaluate_sharded(nv, pt)
+        ok = ok and (got == O.mle_evaluate(tables[0], pt, fold=True)).all()
         # host all-gather through the library communicator
         g = ctx.comm_allgather(np.arange(12, dtype=np.uint64) + 100 * rank)
         ok = ok and all((g[r] == np.arange(12, dtype=np.uint64) + 100 * r).all() for r in range(world))

@@ -52,7 +52,12 @@ def test_large_roundtrip_by_evaluation(ctx, oracle):
     assert (got == oracle.interpolate_iota_fast(vals)).all()
 
 
-def test_non_power_of_two_is_polynomial_error(ctx, tsgpu, oracle):
+def test_non_power_of_two_lengths(ctx, tsgpu, oracle):
+    """the host-buffer entry point interpolates any length (reference semantics: n points, degree < n); the in-place device form,
+    which Twist/Shout feed with padded vectors, still insists on a power of two"""
+    got = ctx.interpolate_iota(oracle.fr_from_ints([1, 2, 3]))
+    assert (got == oracle.lagrange_interpolate(oracle.fr_from_ints([0, 1, 2]), oracle.fr_from_ints([1, 2, 3]))).all()
+    p = ctx.poly_upload(oracle.fr_from_ints([1, 2, 3]))
     with pytest.raises(tsgpu.TwistAndShoutError) as e:
-        ctx.interpolate_iota(oracle.fr_from_ints([1, 2, 3]))
+        p.interpolate_iota()
     assert e.value.variant == "Polynomial"
