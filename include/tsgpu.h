@@ -191,6 +191,16 @@ int tsgpu_kzg_open_values_batch_dev(tsgpu_ctx* ctx, const tsgpu_srs* srs, const 
  * verify: the KZG pairing check at that point (CPU). */
 int tsgpu_vector_commit(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_fr* vector, size_t n, tsgpu_g1* out);
 int tsgpu_vector_open(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_fr* vector, size_t n, size_t index, tsgpu_fr* value, tsgpu_g1* proof);
+/* ---- sharded evaluation-basis commit / open: this rank holds the nodes [first, first + count) of the m-node domain --------
+ * (count = length of the value slices).  commit: partial commitments, to be added over the ranks.  open, phase 1: out[0] = product
+ * of this rank's (z - j), out[1 + i] = this rank's partial barycentric sum of slice i; the caller multiplies the products of all ranks
+ * (N(z)), adds the partial sums and forms value_i = N(z) * sum_i.  open, phase 2: partial quotient commitments for those values. */
+int tsgpu_srs_lagrange_prepare_range(tsgpu_ctx* ctx, const tsgpu_srs* srs, size_t m, size_t first, size_t count);
+int tsgpu_kzg_commit_values_slice_batch_dev(tsgpu_ctx* ctx, const tsgpu_srs* srs, size_t m, size_t first, const tsgpu_poly* const* slices, size_t k,
+                                            tsgpu_g1* partials);
+int tsgpu_kzg_open_values_slice_partial(tsgpu_ctx* ctx, size_t m, size_t first, const tsgpu_poly* const* slices, size_t k, const tsgpu_fr* z, tsgpu_fr* out);
+int tsgpu_kzg_open_values_slice_finish(tsgpu_ctx* ctx, const tsgpu_srs* srs, size_t m, size_t first, const tsgpu_poly* const* slices, size_t k,
+                                       const tsgpu_fr* values, tsgpu_g1* partial_proofs);
 /* plain G1 MSM over caller-supplied affine bases: sum_i scalars[i] * bases[i] */
 int tsgpu_msm_g1(tsgpu_ctx* ctx, const tsgpu_g1a* bases, const tsgpu_fr* scalars, size_t n, tsgpu_g1* out);
 /* CPU helpers on single points: KZGCommitmentValue::hash (commitments.rs:73-84), ark-serialize compressed bytes
@@ -273,6 +283,11 @@ int tsgpu_twist_prove(tsgpu_ctx* ctx, const tsgpu_params* params, const uint64_t
                       const uint8_t* is_write, size_t num_operations, tsgpu_proof** out);
 /* same with the two zero-padded vectors already in HBM (consumed) */
 int tsgpu_twist_prove_dev(tsgpu_ctx* ctx, const tsgpu_params* params, tsgpu_poly* padded_addresses, tsgpu_poly* padded_values, tsgpu_proof** out);
+/* ONE proof sharded over the ranks of the context's communicator (tsgpu_comm_init): rank r passes the operations of the padded
+ * positions [r m / G, (r + 1) m / G), m = next_power_of_two(total_operations) - num_local of them exist.  Three small all-gathers
+ * (partial commitments, opening sums, partial opening proofs); every rank returns the same proof, byte-identical to tsgpu_twist_prove. */
+int tsgpu_twist_prove_sharded(tsgpu_ctx* ctx, const tsgpu_params* params, const uint64_t* addresses, const tsgpu_fr* values, size_t num_local,
+                              size_t total_operations, tsgpu_proof** out);
 /* Shout::prove(&LookupTable) (src/shout.rs:97-222): entries = table.entries, lookup_indices[i] = lookups[i].index.
  * TSGPU_E_INVALID_PARAMETERS "Too many lookup operations" beyond max_operations. */
 int tsgpu_shout_prove(tsgpu_ctx* ctx, const tsgpu_params* params, const tsgpu_fr* entries, size_t num_entries,

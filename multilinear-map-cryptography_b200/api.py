@@ -317,6 +317,28 @@ class Twist:
         ctx.check(lib().tsgpu_twist_prove(ctx._h, self.prover_params._h, _p(addresses), _p(values), _p(is_write), C.c_size_t(n), C.byref(h)))
         return Proof(h)
 
+    def prove_sharded(self, local_addresses: np.ndarray, local_values: np.ndarray, total_operations: int) -> TwistProof:
+        """ONE proof sharded over the ranks of the context's communicator (ctx.comm_init*): this rank passes the operations that fall in
+        its range [rank m / G, (rank + 1) m / G) of the padded trace (m = next power of two of total_operations).  Every rank gets the
+        same proof, byte-identical to prove() on one GPU."""
+        ctx = self.prover_params.ctx
+        local_addresses = np.ascontiguousarray(local_addresses, dtype=np.uint64).reshape(-1)
+        local_values = _fr(local_values) if len(local_values) else np.empty((0, 4), dtype=np.uint64)
+        h = C.c_void_p()
+        ctx.check(lib().tsgpu_twist_prove_sharded(ctx._h, self.prover_params._h, _p(local_addresses), _p(local_values),
+                                                  C.c_size_t(local_addresses.shape[0]), C.c_size_t(total_operations), C.byref(h)))
+        return Proof(h)
+
+    @staticmethod
+    def shard_range(total_operations: int, rank: int, world: int):
+        """[lo, hi) of the operations rank `rank` passes to prove_sharded"""
+        m = 1
+        while m < total_operations:
+            m <<= 1
+        count = m // world
+        lo = min(rank * count, total_operations)
+        return lo, min(lo + count, total_operations) if rank * count < total_operations else lo
+
     def prove_device(self, padded_addresses, padded_values) -> TwistProof:
         """prove from two zero-padded value vectors already resident in HBM (Poly handles; consumed)"""
         ctx = self.prover_params.ctx

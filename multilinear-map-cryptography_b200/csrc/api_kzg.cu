@@ -9,6 +9,7 @@
 #include "mle.cuh"
 #include "lagrange.cuh"
 #include <map>
+#include <tuple>
 #include "../host/field64.hpp"
 
 using namespace tsg;
@@ -32,6 +33,9 @@ struct tsgpu_srs {
     // second, short table per Lagrange basis for value vectors whose entries fit 64 bits (addresses, u64 memory values, table indices):
     // 16-bit windows, only the five lowest - the bucket set is 16 times smaller, and so is the window reduction
     std::map<size_t, g1_affine*> lagrange_short_table;
+    // per-rank slices of an evaluation basis (sharded proving): nodes first .. first + count - 1 of the m-node domain, with their tables
+    struct Slice { g1_affine* pts = nullptr; g1_affine* table = nullptr; unsigned table_c = 0; g1_affine* short_table = nullptr; };
+    std::map<std::tuple<size_t, size_t, size_t>, Slice> lagrange_slices;
 };
 // a base array the MSM can run on: plain points and, optionally, their window tables
 struct MsmBasis { const g1_affine* pts; size_t n; const g1_affine* table; unsigned table_c; const g1_affine* short_table = nullptr; unsigned short_c = 0, short_windows = 0; };
@@ -249,6 +253,7 @@ void tsgpu_srs_free(tsgpu_ctx* ctx, tsgpu_srs* srs) {
     for (auto& kv : srs->lagrange) cudaFree(kv.second);
     for (auto& kv : srs->lagrange_table) cudaFree(kv.second.first);
     for (auto& kv : srs->lagrange_short_table) cudaFree(kv.second);
+    for (auto& kv : srs->lagrange_slices) { cudaFree(kv.second.pts); if (kv.second.table) cudaFree(kv.second.table); if (kv.second.short_table) cudaFree(kv.second.short_table); }
     if (srs->table) cudaFree(srs->table);
     delete srs;
 }
@@ -545,57 +550,159 @@ static MsmBasis lagrange_msm_basis(const tsgpu_srs* srs, size_t m) {
 int tsgpu_srs_has_lagrange(const tsgpu_srs* srs, size_t m) { return srs && lagrange_basis(srs, m) ? 1 : 0; }
 int tsgpu_srs_can_lagrange(const tsgpu_srs* srs) { return srs && srs->has_tau ? 1 : 0; }
 
-// [L_j(tau)]_1 for the nodes 0..m-1 (m a power of two, m <= SRS length): L_j(tau) = N(tau) w_j / (tau - j) on the device,
-// then the same fixed-base kernel that builds g1_powers.  The handle caches the result (a const handle is a cache here).
-int tsgpu_srs_lagrange_prepare(tsgpu_ctx* ctx, const tsgpu_srs* srs_c, size_t m) {
-    if (!ctx || !srs_c) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
-    tsgpu_srs* srs = const_cast<tsgpu_srs*>(srs_c);
-    if (lagrange_basis(srs, m)) return TSGPU_OK;
+// [L_j(tau)]_1 for the nodes first .. first + count - 1 of the m-node domain (m a power of two, m <= SRS length):
+// L_j(tau) = N(tau) w_j / (tau - j) on the device, then the same fixed-base kernel that builds g1_powers, then the window tables.
+static int build_lagrange_range(tsgpu_ctx* ctx, tsgpu_srs* srs, size_t m, size_t first, size_t count, tsgpu_srs::Slice* out) {
     if (!srs->has_tau) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "this SRS was uploaded without its trapdoor: no evaluation basis");
     int lg = log2_exact(m);
-    if (lg < 0 || m > srs->n) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "evaluation-basis size must be a power of two within the SRS");
+    if (lg < 0 || m > srs->n || first + count > m || count == 0) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "evaluation-basis size must be a power of two within the SRS");
     Fr64 tcan = Fr64::from_raw(srs->tau.l).from_mont();
     if (!tcan.l[1] && !tcan.l[2] && !tcan.l[3] && tcan.l[0] < m) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "tau is an interpolation node");
     const fr_t* ifact = nullptr;
     TSG_CUDA(ctx, interp_factorials(ctx, (unsigned)lg, &ifact));
     g1_affine* basis = nullptr;
-    cudaError_t e = cudaMalloc((void**)&basis, m * sizeof(g1_affine));
+    cudaError_t e = cudaMalloc((void**)&basis, count * sizeof(g1_affine));
     if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc(lagrange basis)");
     TempBuf inv, scratch, scal, prod;
     int rc = TSGPU_OK;
     fr_t t; memcpy(t.l, srs->tau.l, 32);
     fr_t ntau;
     unsigned launches = 0;
+    // inverses over the WHOLE domain (N(tau) is a product over all nodes; 0.2 ms at 2^20), scalars and points only for the range
     cudaError_t ce = inv.alloc(m * sizeof(fr_t), ctx->stream);
     if (ce == cudaSuccess) ce = scratch.alloc(lag_binv_scratch(m) * sizeof(fr_t), ctx->stream);
-    if (ce == cudaSuccess) ce = scal.alloc(m * sizeof(fr_t), ctx->stream);
+    if (ce == cudaSuccess) ce = scal.alloc(count * sizeof(fr_t), ctx->stream);
     if (ce == cudaSuccess) ce = prod.alloc(sizeof(fr_t), ctx->stream);
     if (ce == cudaSuccess) ce = launch_node_inverses(t, m, inv.as<fr_t>(), scratch.as<fr_t>(), ctx->host_scratch, &ntau, ctx->sm_count, ctx->stream, &launches);
     if (ce == cudaSuccess) ce = cudaMemcpyAsync(prod.p, &ntau, sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream);
-    if (ce == cudaSuccess) ce = launch_lagrange_scalars(inv.as<fr_t>(), ifact, prod.as<fr_t>(), m, scal.as<fr_t>(), ctx->sm_count, ctx->stream);
+    if (ce == cudaSuccess) ce = launch_lagrange_scalars(inv.as<fr_t>() + first, ifact, prod.as<fr_t>(), m, first, count, scal.as<fr_t>(), ctx->sm_count, ctx->stream);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);   // ntau is a stack variable
     ctx->launches += launches + 1;
     if (ce != cudaSuccess) rc = cuda_fail(ctx, ce, "lagrange scalars");
-    if (!rc) rc = fixed_base_points(ctx, scal.as<fr_t>(), m, basis);
+    if (!rc) rc = fixed_base_points(ctx, scal.as<fr_t>(), count, basis);
     if (!rc) { ce = cudaStreamSynchronize(ctx->stream); if (ce != cudaSuccess) rc = cuda_fail(ctx, ce, "lagrange basis"); }
     if (rc) { cudaFree(basis); return rc; }
-    g1_affine* table = nullptr; unsigned table_c = 0;
-    if ((rc = build_tables(ctx, basis, m, &table, &table_c))) { cudaFree(basis); return rc; }
-    srs->lagrange[m] = basis;
-    if (table) srs->lagrange_table[m] = {table, table_c};
-    if (table && table_c > MSM_SHORT_C) {   // dedicated short-scalar table when the full table's bucket set is the larger one
+    out->pts = basis;
+    if ((rc = build_tables(ctx, basis, count, &out->table, &out->table_c))) { cudaFree(basis); out->pts = nullptr; return rc; }
+    if (out->table && out->table_c > MSM_SHORT_C) {   // dedicated short-scalar table when the full table's bucket set is the larger one
         g1_affine* st = nullptr;
-        if (cudaMalloc((void**)&st, (size_t)MSM_SHORT_WINDOWS * m * sizeof(g1_affine)) == cudaSuccess) {
-            TempBuf cur; unsigned launches = 0;
-            cudaError_t e = cur.alloc(m * sizeof(g1_xyzz), ctx->stream);
-            if (e == cudaSuccess) e = msm_build_table(basis, m, MSM_SHORT_C, st, cur.as<g1_xyzz>(), ctx->sm_count, ctx->stream, &launches, MSM_SHORT_WINDOWS);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-            ctx->launches += launches;
-            if (e != cudaSuccess) { cudaFree(st); return cuda_fail(ctx, e, "short window tables"); }
-            srs->lagrange_short_table[m] = st;
+        if (cudaMalloc((void**)&st, (size_t)MSM_SHORT_WINDOWS * count * sizeof(g1_affine)) == cudaSuccess) {
+            TempBuf cur; unsigned l2 = 0;
+            cudaError_t e2 = cur.alloc(count * sizeof(g1_xyzz), ctx->stream);
+            if (e2 == cudaSuccess) e2 = msm_build_table(basis, count, MSM_SHORT_C, st, cur.as<g1_xyzz>(), ctx->sm_count, ctx->stream, &l2, MSM_SHORT_WINDOWS);
+            if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(ctx->stream);
+            ctx->launches += l2;
+            if (e2 != cudaSuccess) { cudaFree(st); return cuda_fail(ctx, e2, "short window tables"); }
+            out->short_table = st;
         } else cudaGetLastError();
     }
     return TSGPU_OK;
+}
+// the whole basis of an m-node domain; the handle caches the result (a const handle is a cache here)
+int tsgpu_srs_lagrange_prepare(tsgpu_ctx* ctx, const tsgpu_srs* srs_c, size_t m) {
+    if (!ctx || !srs_c) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    tsgpu_srs* srs = const_cast<tsgpu_srs*>(srs_c);
+    if (lagrange_basis(srs, m)) return TSGPU_OK;
+    tsgpu_srs::Slice sl;
+    int rc = build_lagrange_range(ctx, srs, m, 0, m, &sl);
+    if (rc) return rc;
+    srs->lagrange[m] = sl.pts;
+    if (sl.table) srs->lagrange_table[m] = {sl.table, sl.table_c};
+    if (sl.short_table) srs->lagrange_short_table[m] = sl.short_table;
+    return TSGPU_OK;
+}
+// one rank's slice of it (sharded proving): nodes first .. first + count - 1
+int tsgpu_srs_lagrange_prepare_range(tsgpu_ctx* ctx, const tsgpu_srs* srs_c, size_t m, size_t first, size_t count) {
+    if (!ctx || !srs_c) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    tsgpu_srs* srs = const_cast<tsgpu_srs*>(srs_c);
+    auto key = std::make_tuple(m, first, count);
+    if (srs->lagrange_slices.count(key)) return TSGPU_OK;
+    tsgpu_srs::Slice sl;
+    int rc = build_lagrange_range(ctx, srs, m, first, count, &sl);
+    if (rc) return rc;
+    srs->lagrange_slices[key] = sl;
+    return TSGPU_OK;
+}
+static MsmBasis lagrange_slice_basis(const tsgpu_srs* srs, size_t m, size_t first, size_t count) {
+    const tsgpu_srs::Slice& sl = srs->lagrange_slices.at(std::make_tuple(m, first, count));
+    MsmBasis b{sl.pts, count, sl.table, sl.table_c};
+    if (sl.short_table) { b.short_table = sl.short_table; b.short_c = MSM_SHORT_C; b.short_windows = MSM_SHORT_WINDOWS; }
+    else if (b.table && b.table_c <= MSM_SHORT_C) { b.short_table = b.table; b.short_c = b.table_c; b.short_windows = (65 + b.table_c - 1) / b.table_c; }
+    return b;
+}
+
+// ---- sharded evaluation-basis commit / open: each rank holds the nodes [first, first + count) of the m-node domain -----------------
+// partial commitments of `k` value slices over this rank's basis slice (one batched MSM pass); the caller sums them over the ranks
+int tsgpu_kzg_commit_values_slice_batch_dev(tsgpu_ctx* ctx, const tsgpu_srs* srs, size_t m, size_t first, const tsgpu_poly* const* slices, size_t k, tsgpu_g1* partials) {
+    if (!ctx || !srs || !slices || !partials || k == 0 || k > (size_t)MSM_MAX_BATCH) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "bad argument");
+    const size_t count = slices[0]->n;
+    for (size_t i = 0; i < k; ++i) if (!slices[i] || slices[i]->n != count) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "slices must have equal length");
+    int rc = tsgpu_srs_lagrange_prepare_range(ctx, srs, m, first, count);
+    if (rc) return rc;
+    MsmBasis basis[MSM_MAX_BATCH]; const fr_t* sc[MSM_MAX_BATCH]; size_t n[MSM_MAX_BATCH];
+    for (size_t i = 0; i < k; ++i) { basis[i] = lagrange_slice_basis(srs, m, first, count); sc[i] = slices[i]->d; n[i] = count; }
+    return msm_device_batch(ctx, (int)k, basis, sc, n, partials, /*maybe_short=*/true);
+}
+// opening, phase 1: out[0] = prod over this rank's nodes of (z - j); out[1 + i] = sum over this rank's nodes of w_j v_j / (z - j) for slice i.
+// The caller multiplies the products of all ranks (= N(z)), adds the partial sums of all ranks and gets value_i = N(z) * sum_i.
+int tsgpu_kzg_open_values_slice_partial(tsgpu_ctx* ctx, size_t m, size_t first, const tsgpu_poly* const* slices, size_t k, const tsgpu_fr* z, tsgpu_fr* out) {
+    if (!ctx || !slices || !z || !out || k == 0 || k > (size_t)MSM_MAX_BATCH) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "bad argument");
+    const size_t count = slices[0]->n;
+    int lg = log2_exact(m);
+    if (lg < 0 || first + count > m) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "bad slice");
+    Fr64 zcan = Fr64::from_raw(z->l).from_mont();
+    if (!zcan.l[1] && !zcan.l[2] && !zcan.l[3] && zcan.l[0] < m) return fail(ctx, TSGPU_E_POLYNOMIAL, "opening point is an interpolation node");
+    const fr_t* ifact = nullptr;
+    TSG_CUDA(ctx, interp_factorials(ctx, (unsigned)lg, &ifact));
+    cudaError_t aerr;
+    fr_t* inv = (fr_t*)arena_get(ctx, tsgpu_ctx::ARENA_BARY, (count + lag_binv_scratch(count) + 8) * sizeof(fr_t), &aerr);
+    if (!inv) return cuda_fail(ctx, aerr, "cudaMalloc(node inverses)");
+    ctx->bary_inv = inv; ctx->bary_spans = inv + count; ctx->bary_n = count; ctx->bary_z = *z;
+    // 1 / (z - first - j): the batch inversion counts nodes from 0, so it is run at the shifted point z - first
+    Fr64 zs = Fr64::from_raw(z->l) - Fr64::from_u64((uint64_t)first);
+    fr_t zf; memcpy(zf.l, zs.l, 32);
+    fr_t slice_prod;
+    unsigned launches = 0;
+    KernelTimer kt(ctx, "open_bary");
+    TSG_CUDA(ctx, launch_node_inverses(zf, count, inv, (fr_t*)ctx->bary_spans, ctx->host_scratch, &slice_prod, ctx->sm_count, ctx->stream, &launches));
+    ctx->launches += launches;
+    memcpy(out[0].l, slice_prod.l, 32);
+    fr_t* one_dev = (fr_t*)ctx->bary_spans + lag_binv_scratch(count);
+    fr_t one = fr_t::one();
+    memcpy(ctx->host_scratch + 41, &one, sizeof(fr_t));
+    TSG_CUDA(ctx, cudaMemcpyAsync(one_dev, ctx->host_scratch + 41, sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+    for (size_t i = 0; i < k; ++i) {
+        if (!slices[i] || slices[i]->n != count) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "slices must have equal length");
+        TSG_CUDA(ctx, launch_bary_partial(slices[i]->d, inv, ifact, m, first, count, one_dev, ctx->partials, ctx->ticket, ctx->dev_out + i, ctx->sm_count, ctx->stream));
+        ctx->launches += 1;
+    }
+    TSG_CUDA(ctx, cudaMemcpyAsync(ctx->host_out, ctx->dev_out, k * sizeof(fr_t), cudaMemcpyDeviceToHost, ctx->stream));
+    TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(out + 1, ctx->host_out, k * sizeof(fr_t));
+    return TSGPU_OK;
+}
+// opening, phase 2 (after phase 1 with the same z on this context): quotient values over this rank's nodes for the global values[i],
+// committed over the basis slice in one batched pass; the caller sums the partial proofs over the ranks
+int tsgpu_kzg_open_values_slice_finish(tsgpu_ctx* ctx, const tsgpu_srs* srs, size_t m, size_t first, const tsgpu_poly* const* slices, size_t k,
+                                       const tsgpu_fr* values, tsgpu_g1* partial_proofs) {
+    if (!ctx || !srs || !slices || !values || !partial_proofs || k == 0 || k > (size_t)MSM_MAX_BATCH) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "bad argument");
+    const size_t count = slices[0]->n;
+    if (!ctx->bary_inv || ctx->bary_n != count) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "open_values_slice_partial must run first");
+    int rc = tsgpu_srs_lagrange_prepare_range(ctx, srs, m, first, count);
+    if (rc) return rc;
+    cudaError_t aerr;
+    fr_t* q_all = (fr_t*)arena_get(ctx, tsgpu_ctx::ARENA_QUOT, (k * count + MSM_MAX_BATCH) * sizeof(fr_t), &aerr);
+    if (!q_all) return cuda_fail(ctx, aerr, "cudaMalloc(quotient)");
+    fr_t* val = q_all + k * count;
+    memcpy(ctx->host_scratch + 44, values, k * sizeof(fr_t));
+    TSG_CUDA(ctx, cudaMemcpyAsync(val, ctx->host_scratch + 44, k * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+    MsmBasis basis[MSM_MAX_BATCH]; const fr_t* sc[MSM_MAX_BATCH]; size_t n[MSM_MAX_BATCH];
+    for (size_t i = 0; i < k; ++i) {
+        TSG_CUDA(ctx, launch_bary_quotient(slices[i]->d, (const fr_t*)ctx->bary_inv, val + i, count, q_all + i * count, ctx->sm_count, ctx->stream));
+        ctx->launches += 1;
+        basis[i] = lagrange_slice_basis(srs, m, first, count); sc[i] = q_all + i * count; n[i] = count;
+    }
+    return msm_device_batch(ctx, (int)k, basis, sc, n, partial_proofs);
 }
 
 // commit(interpolant of values on 0..m-1) = sum_j values[j] * [L_j(tau)]_1 : vector_to_polynomial + commit in one MSM.

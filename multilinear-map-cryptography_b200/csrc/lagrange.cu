@@ -91,11 +91,12 @@ __device__ __forceinline__ fr_t node_weight(const fr_t* ifact, size_t j, size_t 
 }
 
 // scal[j] = L_j(tau) = N(tau) w_j / (tau - j);  inv holds 1/(tau - j) on entry, *ntau = N(tau)
-__global__ void __launch_bounds__(256) k_lagrange_scalars(const fr_t* inv, const fr_t* ifact, const fr_t* ntau, size_t n, fr_t* scal) {
+// slice form: inv / scal hold the `count` nodes first .. first + count - 1 of the n-node domain
+__global__ void __launch_bounds__(256) k_lagrange_scalars(const fr_t* inv, const fr_t* ifact, const fr_t* ntau, size_t n, size_t first, size_t count, fr_t* scal) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const fr_t N = *ntau;
-    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride)
-        st256(scal + j, node_weight(ifact, j, n) * ld256_nc(inv + j) * N);
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += stride)
+        st256(scal + j, node_weight(ifact, first + j, n) * ld256_nc(inv + j) * N);
 }
 
 // out[0] = N(z) * sum_j w_j v_j / (z - j)
@@ -103,15 +104,16 @@ struct BaryEpilogue {
     const fr_t* nz; fr_t* out;
     __device__ void operator()(fr_t (&v)[1]) const { *out = v[0] * *nz; }
 };
-__global__ void __launch_bounds__(256) k_bary_sum(const fr_t* vals, const fr_t* inv, const fr_t* ifact, size_t n, const fr_t* nz,
+// vals / inv hold the `count` nodes first .. first + count - 1 of the n-node domain (the whole domain: first = 0, count = n)
+__global__ void __launch_bounds__(256) k_bary_sum(const fr_t* vals, const fr_t* inv, const fr_t* ifact, size_t n, size_t first, size_t count, const fr_t* nz,
                                                   fr_t* partials, unsigned int* ticket, fr_t* out) {
     __shared__ fr_t smem[32];
     wide_acc<FrP> acc; acc.clear();
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += stride) {
         fr_t v = ld256_nc(vals + j);
         if (v.is_zero()) continue;                 // zero padding and never-written cells
-        acc.add_product(v * ld256_nc(inv + j), node_weight(ifact, j, n));
+        acc.add_product(v * ld256_nc(inv + j), node_weight(ifact, first + j, n));
     }
     fr_t v[1]; v[0] = acc.reduce();
     grid_finish_sum<fr_t, 1>(v, partials, ticket, smem, BaryEpilogue{nz, out});
@@ -206,14 +208,25 @@ cudaError_t launch_fr_product(const fr_t* in, size_t count, fr_t* out, cudaStrea
     k_fr_product<<<1, LAG_PROD_THREADS, 0, s>>>(in, count, out);
     return cudaGetLastError();
 }
-cudaError_t launch_lagrange_scalars(const fr_t* inv, const fr_t* ifact, const fr_t* ntau, size_t n, fr_t* scal, int sm_count, cudaStream_t s) {
-    k_lagrange_scalars<<<gridfor(n, 256, (size_t)sm_count * 8), 256, 0, s>>>(inv, ifact, ntau, n, scal);
+cudaError_t launch_lagrange_scalars(const fr_t* inv, const fr_t* ifact, const fr_t* ntau, size_t n, size_t first, size_t count, fr_t* scal, int sm_count, cudaStream_t s) {
+    k_lagrange_scalars<<<gridfor(count, 256, (size_t)sm_count * 8), 256, 0, s>>>(inv, ifact, ntau, n, first, count, scal);
     return cudaGetLastError();
 }
 cudaError_t launch_bary_open(const fr_t* vals, const fr_t* inv, const fr_t* ifact, size_t n, const fr_t* nz, fr_t* partials, unsigned int* ticket,
                              fr_t* value, fr_t* q, int sm_count, cudaStream_t s) {
-    k_bary_sum<<<gridfor(n, 256, (size_t)sm_count * 2), 256, 0, s>>>(vals, inv, ifact, n, nz, partials, ticket, value);
+    k_bary_sum<<<gridfor(n, 256, (size_t)sm_count * 2), 256, 0, s>>>(vals, inv, ifact, n, 0, n, nz, partials, ticket, value);
     k_bary_quotient<<<gridfor(n, 256, (size_t)sm_count * 8), 256, 0, s>>>(vals, inv, value, n, q);
+    return cudaGetLastError();
+}
+// sharded opening, first half: *partial = scale * sum over this rank's nodes of w_j v_j / (z - j)   (scale = 1 for a raw partial sum)
+cudaError_t launch_bary_partial(const fr_t* vals, const fr_t* inv, const fr_t* ifact, size_t n, size_t first, size_t count, const fr_t* scale,
+                                fr_t* partials, unsigned int* ticket, fr_t* partial, int sm_count, cudaStream_t s) {
+    k_bary_sum<<<gridfor(count, 256, (size_t)sm_count * 2), 256, 0, s>>>(vals, inv, ifact, n, first, count, scale, partials, ticket, partial);
+    return cudaGetLastError();
+}
+// second half: q[j] = (*value - v_j) / (z - j) over this rank's nodes
+cudaError_t launch_bary_quotient(const fr_t* vals, const fr_t* inv, const fr_t* value, size_t count, fr_t* q, int sm_count, cudaStream_t s) {
+    k_bary_quotient<<<gridfor(count, 256, (size_t)sm_count * 8), 256, 0, s>>>(vals, inv, value, count, q);
     return cudaGetLastError();
 }
 

@@ -17,6 +17,9 @@
 #include "sumcheck.cuh"
 #include "tma_stream.cuh"
 
+#ifndef TSG_BE_MINB
+#define TSG_BE_MINB 2
+#endif
 namespace tsg {
 
 // ---------------------------------------------------------------- per-pair evaluation contributions
@@ -171,7 +174,7 @@ __global__ void __launch_bounds__(SC_THREADS, (D <= 2 ? 2 : 1)) k_bind_eval(ScTa
 
 
 // d = 2 with the claim of the round being evaluated (= g_k(r), known to the host before the launch)
-__global__ void __launch_bounds__(SC_THREADS, 2) k_bind_eval2_claim(ScTables tabs, size_t quarter, const fr_ctab r, const fr_t claim, fr_t* partials,
+__global__ void __launch_bounds__(SC_THREADS, TSG_BE_MINB) k_bind_eval2_claim(ScTables tabs, size_t quarter, const fr_ctab r, const fr_t claim, fr_t* partials,
                                                                    unsigned int* ticket, fr_t* out4) {
     __shared__ fr_t smem[2 * 32];
     EvalAcc2Claim acc; acc.clear();
@@ -349,7 +352,7 @@ cudaError_t launch_bind_eval(int d, const ScTables& tabs, size_t n, const fr_t& 
     const fr_ctab r = fr_ctab::make(r_elem);
     size_t quarter = n / 4;
     if (claim && d == 2 && quarter < g_tma_min_work) {
-        k_bind_eval2_claim<<<sc_grid(quarter, sm_count, SC_BLOCKS_PER_SM), SC_THREADS, 0, s>>>(tabs, quarter, r, *claim, partials, ticket, out4);
+        k_bind_eval2_claim<<<sc_grid(quarter, sm_count, TSG_BE_MINB), SC_THREADS, 0, s>>>(tabs, quarter, r, *claim, partials, ticket, out4);
         return cudaGetLastError();
     }
     if (quarter >= g_tma_min_work) {

@@ -186,6 +186,90 @@ int tsgpu_twist_prove_dev(tsgpu_ctx* ctx, const tsgpu_params* params, tsgpu_poly
     return prove_two_vectors(ctx, params, padded_addresses, padded_values, "address_commitment", "value_commitment", log2_of(n), out);
 }
 
+// ------------------------------------------------------------------------------------ Twist::prove, one proof sharded over the ranks
+// The padded operation vectors (length m = next_power_of_two(total_operations)) are sliced by position over the G ranks of the context's
+// communicator: rank r passes the operations [r m / G, (r + 1) m / G) that exist (num_local of them; the rest of its range is the zero
+// padding).  Each rank commits its slices over ITS slice of the evaluation basis; the partial commitments (one G1 point per vector and
+// rank) are all-gathered and added - the "MSM sliced by points with a final cross-GPU sum".  All ranks run the same transcript.  The
+// opening value P(z) = N(z) sum_j w_j v_j / (z - j) needs one more all-gather (per rank: the product of its (z - j) and its partial
+// sums), the quotient commitment a third.  Every rank returns the same proof, byte-identical to tsgpu_twist_prove on one GPU.
+int tsgpu_twist_prove_sharded(tsgpu_ctx* ctx, const tsgpu_params* params, const uint64_t* addresses, const tsgpu_fr* values, size_t num_local,
+                              size_t total_operations, tsgpu_proof** out) {
+    if (!ctx || !params || !out || ((!addresses || !values) && num_local)) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    if (total_operations > params->max_operations) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "Too many operations");   // twist.rs:108-112
+    const size_t G = (size_t)tsgpu_comm_size(ctx), rank = (size_t)tsgpu_comm_rank(ctx);
+    const size_t m = next_pow2(total_operations);
+    if (m < G || !tsgpu_srs_can_lagrange(params->srs)) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "sharded proving needs at least one padded operation per rank and an SRS with its trapdoor");
+    const size_t count = m / G, first = rank * count;
+    const size_t expect = total_operations > first ? (total_operations - first < count ? total_operations - first : count) : 0;
+    if (num_local != expect) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "this rank must pass exactly the operations of its range");
+    const unsigned rounds = log2_of(m);
+    tsgpu_poly *pa = nullptr, *pv = nullptr;
+    int rc = tsgpu_poly_from_u64(ctx, addresses, num_local, count, &pa);
+    if (!rc) rc = tsgpu_poly_upload_padded(ctx, values, num_local, count, &pv);
+    tsgpu_proof* pr = rc ? nullptr : new (std::nothrow) tsgpu_proof;
+    if (!rc && !pr) rc = fail(ctx, TSGPU_E_PROOF_GENERATION, "out of host memory");
+    auto sum_over_ranks = [&](const tsgpu_g1* mine, tsgpu_g1* total) -> int {      // mine[2] -> all-gather -> total[2]
+        std::vector<tsgpu_g1> all(2 * G);
+        int r = tsgpu_comm_allgather(ctx, mine, 2 * sizeof(tsgpu_g1), all.data());
+        if (r) return r;
+        for (int i = 0; i < 2; ++i) {
+            G1J acc = G1J::identity();
+            for (size_t g = 0; g < G; ++g) { G1J p; memcpy(&p, &all[2 * g + i], 96); acc = acc.add(p); }
+            memcpy(&total[i], &acc, 96);
+        }
+        return TSGPU_OK;
+    };
+    const tsgpu_poly* both[2] = {pa, pv};
+    if (!rc) {
+        memset(&pr->opening_point, 0, 32);
+        tsgpu_g1 part[2];
+        rc = tsgpu_kzg_commit_values_slice_batch_dev(ctx, params->srs, m, first, both, 2, part);
+        if (!rc) rc = sum_over_ranks(part, pr->commitments);
+    }
+    if (!rc) {
+        Transcript tr(params->fiat_shamir_seed);
+        tsgpu_fr h;
+        tsgpu_g1_hash(&pr->commitments[0], &h); tr.append_field_element("address_commitment", fr_of(h));
+        tsgpu_g1_hash(&pr->commitments[1], &h); tr.append_field_element("value_commitment", fr_of(h));
+        const fr_t zero4[4] = {fr_t::zero(), fr_t::zero(), fr_t::zero(), fr_t::zero()};
+        for (unsigned round = 0; round < rounds; ++round) {
+            for (int k = 0; k < 4; ++k) pr->round_polynomials.push_back(abi_of(zero4[k]));
+            tr.append_field_elements("sumcheck_round_" + std::to_string(round), zero4, 4);
+            (void)tr.challenge_field_element("sumcheck_challenge_" + std::to_string(round));
+        }
+        pr->final_evaluation = abi_of(fr_t::zero());
+        std::vector<fr_t> ch = tr.challenge_field_elements("opening_challenges", rounds);
+        if (!ch.empty()) {
+            tsgpu_fr z = abi_of(ch[0]);
+            pr->opening_point = z;
+            tsgpu_fr mine[3];                                   // product of this rank's (z - j), partial sums of the two vectors
+            rc = tsgpu_kzg_open_values_slice_partial(ctx, m, first, both, 2, &z, mine);
+            std::vector<tsgpu_fr> all(3 * G);
+            if (!rc) rc = tsgpu_comm_allgather(ctx, mine, sizeof(mine), all.data());
+            tsgpu_fr vs[2];
+            if (!rc) {
+                Fr64 nz = Fr64::one(), sa = Fr64::zero(), sb = Fr64::zero();
+                for (size_t g = 0; g < G; ++g) {
+                    nz = nz * Fr64::from_raw(all[3 * g].l);
+                    sa = sa + Fr64::from_raw(all[3 * g + 1].l);
+                    sb = sb + Fr64::from_raw(all[3 * g + 2].l);
+                }
+                Fr64 va = nz * sa, vb = nz * sb;
+                memcpy(vs[0].l, va.l, 32); memcpy(vs[1].l, vb.l, 32);
+                tsgpu_g1 part[2], pis[2];
+                rc = tsgpu_kzg_open_values_slice_finish(ctx, params->srs, m, first, both, 2, vs, part);
+                if (!rc) rc = sum_over_ranks(part, pis);
+                if (!rc) for (int i = 0; i < 2; ++i) { pr->opening_proofs.push_back(pis[i]); pr->final_evaluations.push_back(vs[i]); }
+            }
+        }
+    }
+    tsgpu_poly_free(ctx, pa); tsgpu_poly_free(ctx, pv);
+    if (rc) { delete pr; return rc; }
+    *out = pr;
+    return TSGPU_OK;
+}
+
 // ------------------------------------------------------------------------------------ Shout::prove
 int tsgpu_shout_prove(tsgpu_ctx* ctx, const tsgpu_params* params, const tsgpu_fr* entries, size_t num_entries,
                       const uint64_t* lookup_indices, size_t num_lookups, tsgpu_proof** out) {

@@ -109,6 +109,69 @@ def test_native_sharded_sumcheck_two_gpus_library_nccl(nv, d):
     assert sorted(q.get(timeout=5) for _ in range(2)) == [(0, True), (1, True)]
 
 
+def test_sharded_twist_one_rank_equals_plain_prove(tsgpu):
+    """tsgpu_twist_prove_sharded with a one-rank communicator: the slice code path (basis slice = whole basis) gives the same bytes"""
+    c = tsgpu.Context(0)
+    try:
+        c.comm_init(1, 0)
+        pp, vp = tsgpu.setup_params(c, 10)
+        for nops in (2, 37, 1000, 4096):
+            rng = np.random.default_rng(nops)
+            addr = rng.integers(0, 1 << 10, size=nops).astype(np.uint64)
+            vals = tsgpu.fe_vec(rng.integers(0, 1 << 63, size=nops, dtype=np.uint64))
+            tw = tsgpu.Twist.new(pp)
+            a = tw.prove_arrays(addr, vals)
+            b = tw.prove_sharded(addr, vals, nops)
+            assert a.to_bytes() == b.to_bytes() and tw.verify(b, vp)
+    finally:
+        c.close()
+
+
+def _twist_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import importlib
+    import torch.distributed as dist
+    ts = importlib.import_module(PKG)
+    import oracle as O
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ctx = ts.Context(rank)
+        ctx.comm_init_torch()
+        pp, vp = ts.setup_params(ctx, 14)
+        ok = True
+        for nops, wide in ((2, False), (5, False), (1000, False), (4096, True), ((1 << 16) - 77, False), (1 << 16, True)):
+            rng = np.random.default_rng(nops)                       # same trace on every rank
+            addr = rng.integers(0, 1 << 14, size=nops).astype(np.uint64)
+            vals = O.chacha_fr_rand(bytes([nops % 251]) * 32, nops).reshape(nops, 4) if wide else ts.fe_vec(rng.integers(0, 1 << 63, size=nops, dtype=np.uint64))
+            tw = ts.Twist.new(pp)
+            lo, hi = tw.shard_range(nops, rank, world)
+            sharded = tw.prove_sharded(addr[lo:hi], vals[lo:hi], nops)
+            ok = ok and tw.verify(sharded, vp)
+            if rank == 0:
+                ok = ok and sharded.to_bytes() == tw.prove_arrays(addr, vals).to_bytes()      # one-GPU proof of the whole trace
+            gathered = ctx.comm_allgather(np.frombuffer(sharded.to_bytes()[:64], dtype=np.uint64))
+            ok = ok and (gathered[0] == gathered[1]).all()                                    # both ranks hold the same commitments
+        q.put((rank, bool(ok)))
+        ctx.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_sharded_twist_two_gpus_same_bytes_as_one_gpu():
+    import torch.multiprocessing as mp
+    mpctx = mp.get_context("spawn")
+    q = mpctx.Queue()
+    procs = [mpctx.Process(target=_twist_worker, args=(r, 2, 29891, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+    assert sorted(q.get(timeout=5) for _ in range(2)) == [(0, True), (1, True)]
+
+
 def _nccl_worker(rank, world, port, nv, q):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import importlib
