@@ -292,6 +292,12 @@ int tsgpu_twist_prove_sharded(tsgpu_ctx* ctx, const tsgpu_params* params, const 
  * TSGPU_E_INVALID_PARAMETERS "Too many lookup operations" beyond max_operations. */
 int tsgpu_shout_prove(tsgpu_ctx* ctx, const tsgpu_params* params, const tsgpu_fr* entries, size_t num_entries,
                       const uint64_t* lookup_indices, size_t num_lookups, tsgpu_proof** out);
+/* ONE Shout proof sharded over the ranks (BASELINE config 3 at 2/4/8 GPUs): rank r passes the table entries of the padded positions
+ * [r mt / G, (r + 1) mt / G), mt = next_power_of_two(total_entries), and the lookup indices of [r ml / G, (r + 1) ml / G),
+ * ml = next_power_of_two(total_lookups).  Same all-gathers as the Twist form (two more when mt != ml: the two openings then run one
+ * after the other); every rank returns the same proof, byte-identical to tsgpu_shout_prove. */
+int tsgpu_shout_prove_sharded(tsgpu_ctx* ctx, const tsgpu_params* params, const tsgpu_fr* entries, size_t num_local_entries, size_t total_entries,
+                              const uint64_t* lookup_indices, size_t num_local_lookups, size_t total_lookups, tsgpu_proof** out);
 /* Twist::verify / Shout::verify (src/twist.rs:255-304, src/shout.rs:225-274): transcript replay, SumCheck::verify and
  * the two KZGCommitment::verify pairing checks (src/commitments.rs:201-228) - all on the CPU, as in the reference. */
 int tsgpu_twist_verify(tsgpu_ctx* ctx, const tsgpu_params* params, const tsgpu_proof* proof, int* valid);

@@ -406,6 +406,21 @@ class Shout:
                                           _p(lookup_indices), C.c_size_t(lookup_indices.shape[0]), C.byref(h)))
         return Proof(h)
 
+    def prove_sharded(self, local_entries: np.ndarray, total_entries: int, local_lookup_indices: np.ndarray, total_lookups: int) -> ShoutProof:
+        """ONE proof sharded over the ranks of the context's communicator: this rank passes the table entries and the lookup indices that
+        fall in its ranges of the padded table / padded lookup vector (Twist.shard_range gives both).  Every rank gets the same proof,
+        byte-identical to prove() on one GPU."""
+        ctx = self.prover_params.ctx
+        local_entries = _fr(local_entries) if len(local_entries) else np.empty((0, 4), dtype=np.uint64)
+        local_lookup_indices = np.ascontiguousarray(local_lookup_indices, dtype=np.uint64).reshape(-1)
+        h = C.c_void_p()
+        ctx.check(lib().tsgpu_shout_prove_sharded(ctx._h, self.prover_params._h, _p(local_entries), C.c_size_t(local_entries.shape[0]),
+                                                  C.c_size_t(total_entries), _p(local_lookup_indices), C.c_size_t(local_lookup_indices.shape[0]),
+                                                  C.c_size_t(total_lookups), C.byref(h)))
+        return Proof(h)
+
+    shard_range = staticmethod(Twist.shard_range)
+
     def verify(self, proof: ShoutProof, verifier_params: VerifierParams) -> bool:
         ctx = verifier_params.ctx
         ok = C.c_int(0)

@@ -186,29 +186,28 @@ int tsgpu_twist_prove_dev(tsgpu_ctx* ctx, const tsgpu_params* params, tsgpu_poly
     return prove_two_vectors(ctx, params, padded_addresses, padded_values, "address_commitment", "value_commitment", log2_of(n), out);
 }
 
-// ------------------------------------------------------------------------------------ Twist::prove, one proof sharded over the ranks
-// The padded operation vectors (length m = next_power_of_two(total_operations)) are sliced by position over the G ranks of the context's
-// communicator: rank r passes the operations [r m / G, (r + 1) m / G) that exist (num_local of them; the rest of its range is the zero
-// padding).  Each rank commits its slices over ITS slice of the evaluation basis; the partial commitments (one G1 point per vector and
-// rank) are all-gathered and added - the "MSM sliced by points with a final cross-GPU sum".  All ranks run the same transcript.  The
-// opening value P(z) = N(z) sum_j w_j v_j / (z - j) needs one more all-gather (per rank: the product of its (z - j) and its partial
-// sums), the quotient commitment a third.  Every rank returns the same proof, byte-identical to tsgpu_twist_prove on one GPU.
-int tsgpu_twist_prove_sharded(tsgpu_ctx* ctx, const tsgpu_params* params, const uint64_t* addresses, const tsgpu_fr* values, size_t num_local,
-                              size_t total_operations, tsgpu_proof** out) {
-    if (!ctx || !params || !out || ((!addresses || !values) && num_local)) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
-    if (total_operations > params->max_operations) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "Too many operations");   // twist.rs:108-112
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------ Twist::prove / Shout::prove, one proof sharded over the ranks
+// The two padded vectors (lengths ma, mb: powers of two, each >= G) are sliced by position over the G ranks of the context's
+// communicator: rank r holds the entries [r m / G, (r + 1) m / G) of each (`pa`, `pb`: this rank's slices, zero padded).  Each rank
+// commits its slices over ITS slice of the evaluation basis; the partial commitments (one G1 point per vector and rank) are
+// all-gathered and added - the "MSM sliced by points with a final cross-GPU sum".  All ranks run the same transcript.  The opening
+// value P(z) = N(z) sum_j w_j v_j / (z - j) needs one more all-gather (per rank: the product of its (z - j) and its partial sums),
+// the quotient commitment a third.  Vectors of equal length (always so for Twist) share every pass and every all-gather; vectors of
+// different lengths (Shout: table and lookups) are opened one after the other (two more small all-gathers).  Every rank returns the
+// same proof, byte-identical to the one-GPU proof.
+namespace {
+int prove_two_vectors_sharded(tsgpu_ctx* ctx, const tsgpu_params* params, tsgpu_poly* pa, size_t ma, tsgpu_poly* pb, size_t mb,
+                              const char* label_a, const char* label_b, unsigned rounds, tsgpu_proof** out) {
     const size_t G = (size_t)tsgpu_comm_size(ctx), rank = (size_t)tsgpu_comm_rank(ctx);
-    const size_t m = next_pow2(total_operations);
-    if (m < G || !tsgpu_srs_can_lagrange(params->srs)) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "sharded proving needs at least one padded operation per rank and an SRS with its trapdoor");
-    const size_t count = m / G, first = rank * count;
-    const size_t expect = total_operations > first ? (total_operations - first < count ? total_operations - first : count) : 0;
-    if (num_local != expect) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "this rank must pass exactly the operations of its range");
-    const unsigned rounds = log2_of(m);
-    tsgpu_poly *pa = nullptr, *pv = nullptr;
-    int rc = tsgpu_poly_from_u64(ctx, addresses, num_local, count, &pa);
-    if (!rc) rc = tsgpu_poly_upload_padded(ctx, values, num_local, count, &pv);
-    tsgpu_proof* pr = rc ? nullptr : new (std::nothrow) tsgpu_proof;
-    if (!rc && !pr) rc = fail(ctx, TSGPU_E_PROOF_GENERATION, "out of host memory");
+    const size_t m[2] = {ma, mb};
+    const size_t first[2] = {rank * (ma / G), rank * (mb / G)};
+    const tsgpu_poly* both[2] = {pa, pb};
+    const bool same = ma == mb;
+    tsgpu_proof* pr = new (std::nothrow) tsgpu_proof;
+    if (!pr) return fail(ctx, TSGPU_E_PROOF_GENERATION, "out of host memory");
+    memset(&pr->opening_point, 0, 32);
     auto sum_over_ranks = [&](const tsgpu_g1* mine, tsgpu_g1* total) -> int {      // mine[2] -> all-gather -> total[2]
         std::vector<tsgpu_g1> all(2 * G);
         int r = tsgpu_comm_allgather(ctx, mine, 2 * sizeof(tsgpu_g1), all.data());
@@ -220,18 +219,30 @@ int tsgpu_twist_prove_sharded(tsgpu_ctx* ctx, const tsgpu_params* params, const 
         }
         return TSGPU_OK;
     };
-    const tsgpu_poly* both[2] = {pa, pv};
-    if (!rc) {
-        memset(&pr->opening_point, 0, 32);
-        tsgpu_g1 part[2];
-        rc = tsgpu_kzg_commit_values_slice_batch_dev(ctx, params->srs, m, first, both, 2, part);
-        if (!rc) rc = sum_over_ranks(part, pr->commitments);
+    // value_i = (prod over ranks of slice products) * (sum over ranks of partial sums), from the gathered (product, sums...) records
+    auto combine = [&](const std::vector<tsgpu_fr>& all, size_t rec, size_t k, tsgpu_fr* vs) {
+        Fr64 nz = Fr64::one();
+        for (size_t g = 0; g < G; ++g) nz = nz * Fr64::from_raw(all[rec * g].l);
+        for (size_t i = 0; i < k; ++i) {
+            Fr64 s = Fr64::zero();
+            for (size_t g = 0; g < G; ++g) s = s + Fr64::from_raw(all[rec * g + 1 + i].l);
+            Fr64 v = nz * s;
+            memcpy(vs[i].l, v.l, 32);
+        }
+    };
+    int rc;
+    tsgpu_g1 part[2];
+    if (same) rc = tsgpu_kzg_commit_values_slice_batch_dev(ctx, params->srs, ma, first[0], both, 2, part);
+    else {
+        rc = tsgpu_kzg_commit_values_slice_batch_dev(ctx, params->srs, m[0], first[0], &both[0], 1, &part[0]);
+        if (!rc) rc = tsgpu_kzg_commit_values_slice_batch_dev(ctx, params->srs, m[1], first[1], &both[1], 1, &part[1]);
     }
+    if (!rc) rc = sum_over_ranks(part, pr->commitments);
     if (!rc) {
         Transcript tr(params->fiat_shamir_seed);
         tsgpu_fr h;
-        tsgpu_g1_hash(&pr->commitments[0], &h); tr.append_field_element("address_commitment", fr_of(h));
-        tsgpu_g1_hash(&pr->commitments[1], &h); tr.append_field_element("value_commitment", fr_of(h));
+        tsgpu_g1_hash(&pr->commitments[0], &h); tr.append_field_element(label_a, fr_of(h));
+        tsgpu_g1_hash(&pr->commitments[1], &h); tr.append_field_element(label_b, fr_of(h));
         const fr_t zero4[4] = {fr_t::zero(), fr_t::zero(), fr_t::zero(), fr_t::zero()};
         for (unsigned round = 0; round < rounds; ++round) {
             for (int k = 0; k < 4; ++k) pr->round_polynomials.push_back(abi_of(zero4[k]));
@@ -243,31 +254,79 @@ int tsgpu_twist_prove_sharded(tsgpu_ctx* ctx, const tsgpu_params* params, const 
         if (!ch.empty()) {
             tsgpu_fr z = abi_of(ch[0]);
             pr->opening_point = z;
-            tsgpu_fr mine[3];                                   // product of this rank's (z - j), partial sums of the two vectors
-            rc = tsgpu_kzg_open_values_slice_partial(ctx, m, first, both, 2, &z, mine);
-            std::vector<tsgpu_fr> all(3 * G);
-            if (!rc) rc = tsgpu_comm_allgather(ctx, mine, sizeof(mine), all.data());
-            tsgpu_fr vs[2];
-            if (!rc) {
-                Fr64 nz = Fr64::one(), sa = Fr64::zero(), sb = Fr64::zero();
-                for (size_t g = 0; g < G; ++g) {
-                    nz = nz * Fr64::from_raw(all[3 * g].l);
-                    sa = sa + Fr64::from_raw(all[3 * g + 1].l);
-                    sb = sb + Fr64::from_raw(all[3 * g + 2].l);
+            tsgpu_fr vs[2]; tsgpu_g1 pis[2];
+            if (same) {
+                tsgpu_fr mine[3];                               // product of this rank's (z - j), partial sums of the two vectors
+                rc = tsgpu_kzg_open_values_slice_partial(ctx, ma, first[0], both, 2, &z, mine);
+                std::vector<tsgpu_fr> all(3 * G);
+                if (!rc) rc = tsgpu_comm_allgather(ctx, mine, sizeof(mine), all.data());
+                if (!rc) {
+                    combine(all, 3, 2, vs);
+                    rc = tsgpu_kzg_open_values_slice_finish(ctx, params->srs, ma, first[0], both, 2, vs, part);
                 }
-                Fr64 va = nz * sa, vb = nz * sb;
-                memcpy(vs[0].l, va.l, 32); memcpy(vs[1].l, vb.l, 32);
-                tsgpu_g1 part[2], pis[2];
-                rc = tsgpu_kzg_open_values_slice_finish(ctx, params->srs, m, first, both, 2, vs, part);
-                if (!rc) rc = sum_over_ranks(part, pis);
-                if (!rc) for (int i = 0; i < 2; ++i) { pr->opening_proofs.push_back(pis[i]); pr->final_evaluations.push_back(vs[i]); }
+            } else {
+                for (int i = 0; i < 2 && !rc; ++i) {            // the node inverses of a slice live in the context between the two phases
+                    tsgpu_fr mine[2];
+                    rc = tsgpu_kzg_open_values_slice_partial(ctx, m[i], first[i], &both[i], 1, &z, mine);
+                    std::vector<tsgpu_fr> all(2 * G);
+                    if (!rc) rc = tsgpu_comm_allgather(ctx, mine, sizeof(mine), all.data());
+                    if (!rc) {
+                        combine(all, 2, 1, &vs[i]);
+                        rc = tsgpu_kzg_open_values_slice_finish(ctx, params->srs, m[i], first[i], &both[i], 1, &vs[i], &part[i]);
+                    }
+                }
             }
+            if (!rc) rc = sum_over_ranks(part, pis);
+            if (!rc) for (int i = 0; i < 2; ++i) { pr->opening_proofs.push_back(pis[i]); pr->final_evaluations.push_back(vs[i]); }
         }
     }
-    tsgpu_poly_free(ctx, pa); tsgpu_poly_free(ctx, pv);
     if (rc) { delete pr; return rc; }
     *out = pr;
     return TSGPU_OK;
+}
+// how many of `total` real entries fall into this rank's range [rank m / G, (rank + 1) m / G) of a vector padded to m
+size_t shard_expect(size_t total, size_t m, size_t G, size_t rank) {
+    const size_t count = m / G, first = rank * count;
+    return total > first ? (total - first < count ? total - first : count) : 0;
+}
+}  // namespace
+
+extern "C" {
+// rank r passes the operations [r m / G, (r + 1) m / G) that exist, m = next_power_of_two(total_operations) (num_local of them; the rest
+// of its range is the zero padding)
+int tsgpu_twist_prove_sharded(tsgpu_ctx* ctx, const tsgpu_params* params, const uint64_t* addresses, const tsgpu_fr* values, size_t num_local,
+                              size_t total_operations, tsgpu_proof** out) {
+    if (!ctx || !params || !out || ((!addresses || !values) && num_local)) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    if (total_operations > params->max_operations) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "Too many operations");   // twist.rs:108-112
+    const size_t G = (size_t)tsgpu_comm_size(ctx), rank = (size_t)tsgpu_comm_rank(ctx);
+    const size_t m = next_pow2(total_operations);
+    if (m < G || !tsgpu_srs_can_lagrange(params->srs)) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "sharded proving needs at least one padded operation per rank and an SRS with its trapdoor");
+    if (num_local != shard_expect(total_operations, m, G, rank)) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "this rank must pass exactly the operations of its range");
+    tsgpu_poly *pa = nullptr, *pv = nullptr;
+    int rc = tsgpu_poly_from_u64(ctx, addresses, num_local, m / G, &pa);
+    if (!rc) rc = tsgpu_poly_upload_padded(ctx, values, num_local, m / G, &pv);
+    if (!rc) rc = prove_two_vectors_sharded(ctx, params, pa, m, pv, m, "address_commitment", "value_commitment", log2_of(m), out);
+    tsgpu_poly_free(ctx, pa); tsgpu_poly_free(ctx, pv);
+    return rc;
+}
+// Shout::prove (shout.rs:97-222) sharded the same way: rank r passes the table entries and the lookup indices that fall into its range of the
+// padded table (length next_power_of_two(total_entries)) resp. of the padded lookup vector (length next_power_of_two(total_lookups)).
+int tsgpu_shout_prove_sharded(tsgpu_ctx* ctx, const tsgpu_params* params, const tsgpu_fr* entries, size_t num_local_entries, size_t total_entries,
+                              const uint64_t* lookup_indices, size_t num_local_lookups, size_t total_lookups, tsgpu_proof** out) {
+    if (!ctx || !params || !out || (!entries && num_local_entries) || (!lookup_indices && num_local_lookups)) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    if (total_lookups > params->max_operations) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "Too many lookup operations");   // shout.rs:98-102
+    const size_t G = (size_t)tsgpu_comm_size(ctx), rank = (size_t)tsgpu_comm_rank(ctx);
+    const size_t mt = next_pow2(total_entries), ml = next_pow2(total_lookups);                // shout.rs:105,116
+    if (mt < G || ml < G || !tsgpu_srs_can_lagrange(params->srs)) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "sharded proving needs at least one padded entry and one padded lookup per rank and an SRS with its trapdoor");
+    if (mt > tsgpu_srs_len(params->srs)) return fail(ctx, TSGPU_E_COMMITMENT, "Polynomial degree exceeds setup size");               // commitments.rs:166-170
+    if (num_local_entries != shard_expect(total_entries, mt, G, rank) || num_local_lookups != shard_expect(total_lookups, ml, G, rank))
+        return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "this rank must pass exactly the entries and lookups of its ranges");
+    tsgpu_poly *pt = nullptr, *pi = nullptr;
+    int rc = tsgpu_poly_upload_padded(ctx, entries, num_local_entries, mt / G, &pt);
+    if (!rc) rc = tsgpu_poly_from_u64(ctx, lookup_indices, num_local_lookups, ml / G, &pi);
+    if (!rc) rc = prove_two_vectors_sharded(ctx, params, pt, mt, pi, ml, "table_commitment", "index_commitment", log2_of(ml), out);
+    tsgpu_poly_free(ctx, pt); tsgpu_poly_free(ctx, pi);
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------ Shout::prove

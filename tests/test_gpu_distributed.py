@@ -127,6 +127,30 @@ def test_sharded_twist_one_rank_equals_plain_prove(tsgpu):
         c.close()
 
 
+def test_sharded_shout_one_rank_equals_plain_prove(tsgpu):
+    """tsgpu_shout_prove_sharded with a one-rank communicator, table and lookup vectors of equal and of different padded lengths"""
+    c = tsgpu.Context(0)
+    try:
+        c.comm_init(1, 0)
+        pp, vp = tsgpu.setup_params(c, 10)
+        sh = tsgpu.Shout.new(pp)
+        for nent, nlook in ((3, 4), (8, 5), (1000, 37), (64, 4096), (1024, 1024), (4096, 1)):
+            rng = np.random.default_rng(nent * 7 + nlook)
+            entries = tsgpu.fe_vec(rng.integers(0, 1 << 63, size=nent, dtype=np.uint64))
+            idx = rng.integers(0, nent, size=nlook).astype(np.uint64)
+            a = sh.prove_arrays(entries, idx)
+            b = sh.prove_sharded(entries, nent, idx, nlook)
+            assert a.to_bytes() == b.to_bytes() and sh.verify(b, vp)
+        with pytest.raises(tsgpu.TwistAndShoutError) as e:
+            sh.prove_sharded(entries, 4096, np.zeros(4097, dtype=np.uint64), 4097)
+        assert e.value.message == "Too many lookup operations"
+        with pytest.raises(tsgpu.TwistAndShoutError) as e:                       # a rank must pass exactly its range
+            sh.prove_sharded(entries[:10], 4096, idx, 1)
+        assert e.value.variant == "InvalidParameters"
+    finally:
+        c.close()
+
+
 def _twist_worker(rank, world, port, q):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import importlib
@@ -153,6 +177,18 @@ def _twist_worker(rank, world, port, q):
                 ok = ok and sharded.to_bytes() == tw.prove_arrays(addr, vals).to_bytes()      # one-GPU proof of the whole trace
             gathered = ctx.comm_allgather(np.frombuffer(sharded.to_bytes()[:64], dtype=np.uint64))
             ok = ok and (gathered[0] == gathered[1]).all()                                    # both ranks hold the same commitments
+        sh = ts.Shout.new(pp)
+        for nent, nlook in ((2, 2), (3, 7), (1000, 4096), (1 << 14, 1 << 16), (1 << 12, (1 << 12) - 5), ((1 << 14) - 3, 100)):
+            rng = np.random.default_rng(nent + 3 * nlook)
+            entries = O.chacha_fr_rand(bytes([nent % 251]) * 32, nent).reshape(nent, 4) if nent == 1000 else ts.fe_vec(rng.integers(0, 1 << 63, size=nent, dtype=np.uint64))
+            idx = rng.integers(0, nent, size=nlook).astype(np.uint64)
+            elo, ehi = sh.shard_range(nent, rank, world); llo, lhi = sh.shard_range(nlook, rank, world)
+            sharded = sh.prove_sharded(entries[elo:ehi], nent, idx[llo:lhi], nlook)
+            ok = ok and sh.verify(sharded, vp)
+            if rank == 0:
+                ok = ok and sharded.to_bytes() == sh.prove_arrays(entries, idx).to_bytes()
+            gathered = ctx.comm_allgather(np.frombuffer(sharded.to_bytes()[:64], dtype=np.uint64))
+            ok = ok and (gathered[0] == gathered[1]).all()
         q.put((rank, bool(ok)))
         ctx.close()
     finally:
@@ -160,7 +196,7 @@ def _twist_worker(rank, world, port, q):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
-def test_sharded_twist_two_gpus_same_bytes_as_one_gpu():
+def test_sharded_twist_and_shout_two_gpus_same_bytes_as_one_gpu():
     import torch.multiprocessing as mp
     mpctx = mp.get_context("spawn")
     q = mpctx.Queue()
