@@ -85,6 +85,22 @@ void tsgpu_table_free(tsgpu_ctx* ctx, tsgpu_table* t);
 int tsgpu_table_eq(tsgpu_ctx* ctx, const tsgpu_fr* w, unsigned num_vars, tsgpu_table** out);
 int tsgpu_table_one_hot_rows(tsgpu_ctx* ctx, const uint64_t* idx, size_t rows, unsigned log_k, unsigned num_vars, tsgpu_table** out);
 int tsgpu_table_from_u64(tsgpu_ctx* ctx, const uint64_t* v, size_t n, unsigned num_vars, tsgpu_table** out);
+/* MultilinearExtension::one_hot(num_vars, index) (src/polynomials.rs:71-82).  index >= 2^num_vars panics in the reference
+ * ("Index {i} out of bounds for size {n}"): TSGPU_E_POLYNOMIAL with that message here. */
+int tsgpu_table_one_hot(tsgpu_ctx* ctx, unsigned num_vars, size_t index, tsgpu_table** out);
+/* MultilinearExtension::from_sparse(num_vars, &[(index, value)]) (src/polynomials.rs:52-67): a repeated index keeps its last value;
+ * the same out-of-bounds behaviour as one_hot. */
+int tsgpu_table_from_sparse(tsgpu_ctx* ctx, unsigned num_vars, const uint64_t* indices, const tsgpu_fr* values, size_t count, tsgpu_table** out);
+/* LessThanPolynomial::new(num_vars).to_multilinear_extension() (src/polynomials.rs:243-263): 2 * num_vars variables, entry at
+ * reference index a | (b << num_vars) = lt(a, b), decided by the first differing bit counted from bit 0 (src/polynomials.rs:222-239). */
+int tsgpu_table_less_than(tsgpu_ctx* ctx, unsigned num_vars, tsgpu_table** out);
+/* LessThanPolynomial::evaluate_at_field_elements (src/polynomials.rs:213-220): the low num_vars bits of the canonical integers.  Host. */
+void tsgpu_lt_evaluate_at_field_elements(unsigned num_vars, const tsgpu_fr* a, const tsgpu_fr* b, tsgpu_fr* out);
+/* MultilinearExtension::add / scalar_mul / sum_evaluations (src/polynomials.rs:164-195).  add: TSGPU_E_POLYNOMIAL
+ * "Number of variables must match" where the reference asserts. */
+int tsgpu_table_add(tsgpu_ctx* ctx, const tsgpu_table* a, const tsgpu_table* b, tsgpu_table** out);
+int tsgpu_table_scalar_mul(tsgpu_ctx* ctx, const tsgpu_table* a, const tsgpu_fr* scalar, tsgpu_table** out);
+int tsgpu_table_sum_evaluations(tsgpu_ctx* ctx, const tsgpu_table* t, tsgpu_fr* out);
 
 /* ---- MultilinearExtension::evaluate / partial_evaluate  (src/polynomials.rs:85-161) -------------- */
 /* host-buffer forms (copy in, compute, copy out) */

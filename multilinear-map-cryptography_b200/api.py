@@ -11,7 +11,7 @@ from typing import List, Optional, Tuple
 
 import numpy as np
 
-from .binding import Context, Srs, TwistAndShoutError, _fr, _p, lib
+from .binding import Context, Srs, Table, TwistAndShoutError, _fr, _p, lib
 
 
 def fe(x: int) -> np.ndarray:
@@ -34,6 +34,91 @@ def fe_to_int(x) -> int:
     out = np.empty_like(x)
     lib().tsgpu_fr_to_canonical(_p(x), C.c_size_t(1), _p(out))
     return sum(int(out[0, i]) << (64 * i) for i in range(4))
+
+
+class MultilinearExtension:
+    """src/polynomials.rs:18-196 - the dense table lives in HBM (a `Table`); `num_vars` and `evaluations` read like the reference's
+    public fields.  Where the reference panics (asserts) this mirror raises: ValueError for the constructor's length assert,
+    TwistAndShoutError(Polynomial) with the reference's message for the others."""
+
+    def __init__(self, table: Table):
+        self.table = table
+
+    @property
+    def ctx(self) -> Context:
+        return self.table.ctx
+
+    @property
+    def num_vars(self) -> int:
+        return self.table.num_vars
+
+    @property
+    def evaluations(self) -> np.ndarray:
+        return self.table.download()
+
+    @staticmethod
+    def from_evaluations(ctx: Context, evaluations) -> "MultilinearExtension":
+        return MultilinearExtension(ctx.table_upload(evaluations))                       # polynomials.rs:28-37 (length must be a power of two)
+
+    @staticmethod
+    def from_evaluations_vec(ctx: Context, num_vars: int, evaluations) -> "MultilinearExtension":
+        return MultilinearExtension(ctx.table_upload(evaluations, num_vars))             # polynomials.rs:40-50 (pad / truncate)
+
+    @staticmethod
+    def from_sparse(ctx: Context, num_vars: int, sparse_entries) -> "MultilinearExtension":
+        return MultilinearExtension(ctx.table_from_sparse(num_vars, sparse_entries))     # polynomials.rs:52-67
+
+    @staticmethod
+    def one_hot(ctx: Context, num_vars: int, index: int) -> "MultilinearExtension":
+        return MultilinearExtension(ctx.table_one_hot(num_vars, index))                  # polynomials.rs:71-82
+
+    def evaluate(self, point) -> np.ndarray:
+        point = np.ascontiguousarray(point, dtype=np.uint64).reshape(-1, 4)
+        if point.shape[0] != self.num_vars:
+            raise TwistAndShoutError(5, "Point dimension must match number of variables")   # polynomials.rs:86
+        return self.table.evaluate(point)
+
+    def partial_evaluate(self, fixed_vars) -> "MultilinearExtension":
+        return MultilinearExtension(self.table.partial_evaluate(fixed_vars))             # polynomials.rs:126-161
+
+    def add(self, other: "MultilinearExtension") -> "MultilinearExtension":
+        return MultilinearExtension(self.table.add(other.table))                         # polynomials.rs:164-176
+
+    def scalar_mul(self, scalar) -> "MultilinearExtension":
+        return MultilinearExtension(self.table.scalar_mul(scalar))                       # polynomials.rs:179-189
+
+    def sum_evaluations(self) -> np.ndarray:
+        return self.table.sum_evaluations()                                              # polynomials.rs:192-195
+
+
+class LessThanPolynomial:
+    """src/polynomials.rs:201-293"""
+
+    def __init__(self, num_vars: int):
+        self.num_vars = num_vars
+
+    @staticmethod
+    def new(num_vars: int) -> "LessThanPolynomial":
+        return LessThanPolynomial(num_vars)
+
+    def evaluate_at_bits(self, a_bits, b_bits) -> np.ndarray:
+        if len(a_bits) != self.num_vars or len(b_bits) != self.num_vars:
+            raise ValueError("bit vectors must have num_vars entries")                    # assert_eq!, polynomials.rs:224-225
+        for x, y in zip(a_bits, b_bits):                                                  # polynomials.rs:229-238
+            if x and not y:
+                return fe(0)
+            if (not x) and y:
+                return fe(1)
+        return fe(0)
+
+    def evaluate_at_field_elements(self, a, b) -> np.ndarray:
+        a = _fr(a, 1); b = _fr(b, 1)
+        out = np.empty(4, dtype=np.uint64)
+        lib().tsgpu_lt_evaluate_at_field_elements(C.c_uint(self.num_vars), _p(a), _p(b), _p(out))
+        return out
+
+    def to_multilinear_extension(self, ctx: Context) -> MultilinearExtension:
+        return MultilinearExtension(ctx.table_less_than(self.num_vars))                  # polynomials.rs:243-263
 
 
 class ProverParams:

@@ -206,6 +206,26 @@ class Context:
         self.check(lib().tsgpu_table_from_u64(self._h, _p(v), C.c_size_t(v.shape[0]), C.c_uint(num_vars), C.byref(h)))
         return Table(self, h)
 
+    def table_one_hot(self, num_vars: int, index: int) -> "Table":
+        """MultilinearExtension::one_hot (polynomials.rs:71-82)"""
+        h = C.c_void_p()
+        self.check(lib().tsgpu_table_one_hot(self._h, C.c_uint(num_vars), C.c_size_t(index), C.byref(h)))
+        return Table(self, h)
+
+    def table_from_sparse(self, num_vars: int, sparse_entries) -> "Table":
+        """MultilinearExtension::from_sparse (polynomials.rs:52-67): sparse_entries = [(index, value)], a repeated index keeps its last value"""
+        idx = np.ascontiguousarray([int(i) for i, _ in sparse_entries], dtype=np.uint64).reshape(-1)
+        vals = _fr(np.stack([np.asarray(v, dtype=np.uint64).reshape(4) for _, v in sparse_entries])) if len(sparse_entries) else np.empty((0, 4), dtype=np.uint64)
+        h = C.c_void_p()
+        self.check(lib().tsgpu_table_from_sparse(self._h, C.c_uint(num_vars), _p(idx), _p(vals), C.c_size_t(idx.shape[0]), C.byref(h)))
+        return Table(self, h)
+
+    def table_less_than(self, num_vars: int) -> "Table":
+        """LessThanPolynomial::new(num_vars).to_multilinear_extension() (polynomials.rs:243-263), generated on the device"""
+        h = C.c_void_p()
+        self.check(lib().tsgpu_table_less_than(self._h, C.c_uint(num_vars), C.byref(h)))
+        return Table(self, h)
+
     # ---- host-buffer MLE calls
     def mle_evaluate(self, evals, point) -> np.ndarray:
         evals = _fr(evals); nv = evals.shape[0].bit_length() - 1
@@ -323,6 +343,26 @@ class Table:
     def bind(self, r):
         r = _fr(r, 1)
         self.ctx.check(lib().tsgpu_table_bind(self.ctx._h, self._h, _p(r)))
+
+    def add(self, other: "Table") -> "Table":
+        """MultilinearExtension::add (polynomials.rs:164-176)"""
+        h = C.c_void_p()
+        self.ctx.check(lib().tsgpu_table_add(self.ctx._h, self._h, other._h, C.byref(h)))
+        return Table(self.ctx, h)
+
+    def scalar_mul(self, scalar) -> "Table":
+        """MultilinearExtension::scalar_mul (polynomials.rs:179-189)"""
+        scalar = _fr(scalar, 1)
+        h = C.c_void_p()
+        self.ctx.check(lib().tsgpu_table_scalar_mul(self.ctx._h, self._h, _p(scalar), C.byref(h)))
+        return Table(self.ctx, h)
+
+    def sum_evaluations(self) -> np.ndarray:
+        """MultilinearExtension::sum_evaluations (polynomials.rs:192-195)"""
+        out = np.empty(4, dtype=np.uint64)
+        self.ctx.check(lib().tsgpu_table_sum_evaluations(self.ctx._h, self._h, _p(out)))
+        return out
+
 
     def free(self):
         if self._h:

@@ -1,8 +1,11 @@
 // api_core.cu - C ABI (include/tsgpu.h): context, MLE tables, evaluate / partial evaluate, sum-check rounds.
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <set>
 #include <new>
+#include <string>
+#include <vector>
 #include "context.cuh"
 #include "mle.cuh"
 #include "sumcheck.cuh"
@@ -272,6 +275,99 @@ int tsgpu_table_from_u64(tsgpu_ctx* ctx, const uint64_t* v, size_t n, unsigned n
     TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *out = t;
     return TSGPU_OK;
+}
+
+static int read_result(tsgpu_ctx* ctx, int count, tsgpu_fr* out);
+// MultilinearExtension::one_hot(num_vars, index) (src/polynomials.rs:71-82); the reference asserts index < 2^num_vars
+int tsgpu_table_one_hot(tsgpu_ctx* ctx, unsigned num_vars, size_t index, tsgpu_table** out) {
+    if (!ctx || !out) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    if (num_vars > 40 || index >= ((size_t)1 << num_vars)) {
+        std::string m = "Index " + std::to_string(index) + " out of bounds for size " + std::to_string((size_t)1 << (num_vars > 40 ? 40 : num_vars));
+        return fail(ctx, TSGPU_E_POLYNOMIAL, m.c_str());
+    }
+    const uint64_t idx = (uint64_t)index;
+    return tsgpu_table_one_hot_rows(ctx, &idx, 1, num_vars, num_vars, out);
+}
+
+// MultilinearExtension::from_sparse(num_vars, &[(index, value)]) (src/polynomials.rs:52-67): zero table, then evaluations[index] = value
+// in slice order - a repeated index keeps its LAST value.  The host drops the overwritten entries, the device scatters the rest.
+int tsgpu_table_from_sparse(tsgpu_ctx* ctx, unsigned num_vars, const uint64_t* indices, const tsgpu_fr* values, size_t count, tsgpu_table** out) {
+    if (!ctx || !out || ((!indices || !values) && count)) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    if (num_vars > 40) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "too many variables");
+    const size_t size = (size_t)1 << num_vars;
+    for (size_t i = 0; i < count; ++i) if (indices[i] >= size) {
+        std::string m = "Index " + std::to_string(indices[i]) + " out of bounds for size " + std::to_string(size);
+        return fail(ctx, TSGPU_E_POLYNOMIAL, m.c_str());
+    }
+    std::vector<uint64_t> idx; std::vector<tsgpu_fr> val;
+    {   // keep the last occurrence of every index
+        std::vector<size_t> order(count);
+        for (size_t i = 0; i < count; ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return indices[a] < indices[b]; });
+        for (size_t k = 0; k < count; ++k)
+            if (k + 1 == count || indices[order[k + 1]] != indices[order[k]]) { idx.push_back(indices[order[k]]); val.push_back(values[order[k]]); }
+    }
+    tsgpu_table* t = nullptr;
+    int rc = table_alloc(ctx, num_vars, &t);
+    if (rc) return rc;
+    TSG_CUDA(ctx, cudaMemsetAsync(t->d, 0, size * sizeof(fr_t), ctx->stream));
+    TempBuf di, dv;
+    TSG_CUDA(ctx, di.alloc(idx.size() * 8, ctx->stream));
+    TSG_CUDA(ctx, dv.alloc(idx.size() * sizeof(fr_t), ctx->stream));
+    if (!idx.empty()) {
+        TSG_CUDA(ctx, cudaMemcpyAsync(di.p, idx.data(), idx.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        TSG_CUDA(ctx, cudaMemcpyAsync(dv.p, val.data(), idx.size() * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+        TSG_CUDA(ctx, launch_sparse_scatter(di.as<unsigned long long>(), dv.as<fr_t>(), idx.size(), num_vars, t->d, ctx->sm_count, ctx->stream));
+        ctx->launches += 1;
+    }
+    TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = t;
+    return TSGPU_OK;
+}
+
+// LessThanPolynomial::new(num_vars).to_multilinear_extension() (src/polynomials.rs:243-263): 2 * num_vars variables, generated on the device
+int tsgpu_table_less_than(tsgpu_ctx* ctx, unsigned num_vars, tsgpu_table** out) {
+    if (!ctx || !out) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    if (num_vars > 16) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "less-than table limited to 16-bit operands (2^32 entries)");
+    tsgpu_table* t = nullptr;
+    int rc = table_alloc(ctx, 2 * num_vars, &t);
+    if (rc) return rc;
+    TSG_CUDA(ctx, launch_lt_table(num_vars, t->d, ctx->sm_count, ctx->stream));
+    ctx->launches += 1;
+    *out = t;
+    return TSGPU_OK;
+}
+
+// MultilinearExtension::add (src/polynomials.rs:164-176); the reference asserts equal num_vars ("Number of variables must match")
+int tsgpu_table_add(tsgpu_ctx* ctx, const tsgpu_table* a, const tsgpu_table* b, tsgpu_table** out) {
+    if (!ctx || !a || !b || !out) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    if (a->num_vars != b->num_vars) return fail(ctx, TSGPU_E_POLYNOMIAL, "Number of variables must match");
+    tsgpu_table* t = nullptr;
+    int rc = table_alloc(ctx, a->num_vars, &t);
+    if (rc) return rc;
+    TSG_CUDA(ctx, launch_table_add(a->d, b->d, t->d, (size_t)1 << a->num_vars, ctx->sm_count, ctx->stream));
+    ctx->launches += 1;
+    *out = t;
+    return TSGPU_OK;
+}
+// MultilinearExtension::scalar_mul (src/polynomials.rs:179-189)
+int tsgpu_table_scalar_mul(tsgpu_ctx* ctx, const tsgpu_table* a, const tsgpu_fr* scalar, tsgpu_table** out) {
+    if (!ctx || !a || !scalar || !out) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    tsgpu_table* t = nullptr;
+    int rc = table_alloc(ctx, a->num_vars, &t);
+    if (rc) return rc;
+    TSG_CUDA(ctx, launch_table_scale(a->d, t->d, (size_t)1 << a->num_vars, to_fr(scalar), ctx->sm_count, ctx->stream));
+    ctx->launches += 1;
+    *out = t;
+    return TSGPU_OK;
+}
+// MultilinearExtension::sum_evaluations (src/polynomials.rs:192-195)
+int tsgpu_table_sum_evaluations(tsgpu_ctx* ctx, const tsgpu_table* t, tsgpu_fr* out) {
+    if (!ctx || !t || !out) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    { KernelTimer kt(ctx, "table_sum");
+      TSG_CUDA(ctx, launch_table_sum(t->d, (size_t)1 << t->num_vars, ctx->partials, ctx->ticket, ctx->dev_out, ctx->sm_count, ctx->stream)); }
+    ctx->launches += 1;
+    return read_result(ctx, 1, out);
 }
 
 // ------------------------------------------------------------------------------- evaluate / partial

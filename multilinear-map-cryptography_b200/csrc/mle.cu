@@ -63,6 +63,60 @@ __global__ void k_fr_from_u64(const unsigned long long* src, size_t n, fr_t* dst
     }
 }
 
+// sparse entries: table[bitrev(idx[i])] = vals[i]; table pre-zeroed, indices unique (the host keeps the LAST occurrence of a
+// repeated index, which is what the sequential loop of MultilinearExtension::from_sparse leaves, src/polynomials.rs:52-67)
+__global__ void k_sparse_scatter(const unsigned long long* idx, const fr_t* vals, size_t count, unsigned bits, fr_t* table) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
+        st256(table + bitrev64(idx[i], bits), ld256_nc(vals + i));
+}
+
+// LessThanPolynomial::to_multilinear_extension (src/polynomials.rs:243-263): 2n variables, reference index i = a | (b << n),
+// entry = lt(a, b) where the FIRST differing bit counted from bit 0 decides (src/polynomials.rs:222-239): a < b iff at the
+// lowest set bit of a ^ b the bit of b is set.  One thread per position (coalesced 256-bit stores), i = bitrev(position).
+__global__ void k_lt_table(unsigned n, fr_t* out, size_t size) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const unsigned long long mask = n >= 64 ? ~0ull : ((1ull << n) - 1);
+    const fr_t one = fr_t::one(), zero = fr_t::zero();
+    for (size_t pos = (size_t)blockIdx.x * blockDim.x + threadIdx.x; pos < size; pos += stride) {
+        const unsigned long long i = bitrev64(pos, 2 * n);
+        const unsigned long long a = i & mask, b = i >> n;
+        const unsigned long long x = a ^ b, low = x & (0ull - x);
+        st256(out + pos, (b & low) ? one : zero);
+    }
+}
+
+// MultilinearExtension::add (src/polynomials.rs:164-176) and scalar_mul (:179-189): elementwise, so the layout does not matter.
+// HBM-bound: 96 resp. 64 bytes per entry; the scalar goes through the per-launch constant table like a fold challenge.
+__global__ void __launch_bounds__(MLE_THREADS) k_table_add(const fr_t* a, const fr_t* b, fr_t* out, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        st256(out + i, ld256_stream(a + i) + ld256_stream(b + i));
+}
+__global__ void __launch_bounds__(MLE_THREADS) k_table_scale(const fr_t* a, fr_t* out, size_t n, const fr_ctab s) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        st256(out + i, s.mul(ld256_stream(a + i)));
+}
+// MultilinearExtension::sum_evaluations (src/polynomials.rs:192-195): one streaming pass, 32 bytes per entry
+struct SumEpilogue {
+    fr_t* out;
+    __device__ void operator()(fr_t (&v)[1]) const { *out = v[0]; }
+};
+__global__ void __launch_bounds__(MLE_THREADS) k_table_sum(const fr_t* a, size_t n, fr_t* partials, unsigned int* ticket, fr_t* out) {
+    __shared__ fr_t smem[32];
+    fr_t acc0 = fr_t::zero(), acc1 = fr_t::zero();
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + stride < n; i += 2 * stride) {         // two loads in flight, two independent add chains
+        fr_t x = ld256_stream(a + i), y = ld256_stream(a + i + stride);
+        acc0 = acc0 + x; acc1 = acc1 + y;
+    }
+    if (i < n) acc0 = acc0 + ld256_stream(a + i);
+    fr_t v[1]; v[0] = acc0 + acc1;
+    grid_finish_sum<fr_t, 1>(v, partials, ticket, smem, SumEpilogue{out});
+}
+
 // ---------------------------------------------------------------- weighted column sum
 // out_partial[split][c] = sum_{row in split} W[row] * T[row * cols + c]
 // grid.x covers columns, grid.y = row splits.
@@ -134,6 +188,28 @@ cudaError_t launch_one_hot_scatter(const unsigned long long* idx, size_t rows, u
 }
 cudaError_t launch_fr_from_u64(const unsigned long long* src, size_t n, fr_t* dst, unsigned bits, int bitrev, int sm_count, cudaStream_t s) {
     k_fr_from_u64<<<grid_for(n, 256, (size_t)sm_count * 8), 256, 0, s>>>(src, n, dst, bits, bitrev);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sparse_scatter(const unsigned long long* idx, const fr_t* vals, size_t count, unsigned bits, fr_t* table, int sm_count, cudaStream_t s) {
+    k_sparse_scatter<<<grid_for(count, 256, (size_t)sm_count * 8), 256, 0, s>>>(idx, vals, count, bits, table);
+    return cudaGetLastError();
+}
+cudaError_t launch_lt_table(unsigned n, fr_t* out, int sm_count, cudaStream_t s) {
+    size_t size = (size_t)1 << (2 * n);
+    k_lt_table<<<grid_for(size, 256, (size_t)sm_count * 8), 256, 0, s>>>(n, out, size);
+    return cudaGetLastError();
+}
+cudaError_t launch_table_add(const fr_t* a, const fr_t* b, fr_t* out, size_t n, int sm_count, cudaStream_t s) {
+    k_table_add<<<grid_for(n, MLE_THREADS, (size_t)sm_count * 8), MLE_THREADS, 0, s>>>(a, b, out, n);
+    return cudaGetLastError();
+}
+cudaError_t launch_table_scale(const fr_t* a, fr_t* out, size_t n, const fr_t& scalar, int sm_count, cudaStream_t s) {
+    k_table_scale<<<grid_for(n, MLE_THREADS, (size_t)sm_count * 8), MLE_THREADS, 0, s>>>(a, out, n, fr_ctab::make(scalar));
+    return cudaGetLastError();
+}
+cudaError_t launch_table_sum(const fr_t* a, size_t n, fr_t* partials, unsigned int* ticket, fr_t* out, int sm_count, cudaStream_t s) {
+    k_table_sum<<<grid_for(n, MLE_THREADS, (size_t)sm_count * 4), MLE_THREADS, 0, s>>>(a, n, partials, ticket, out);
     return cudaGetLastError();
 }
 

@@ -420,6 +420,18 @@ extern "C" {
 void tsgpu_fr_from_u64(const uint64_t* in, size_t n, tsgpu_fr* out) {
     for (size_t i = 0; i < n; ++i) { Fr64 f = Fr64::from_u64(in[i]); memcpy(out[i].l, f.l, 32); }
 }
+// LessThanPolynomial::evaluate_at_field_elements (polynomials.rs:213-220): field_to_bits takes the low num_vars bits of into_bigint()
+// (bits beyond 256 read as false), evaluate_at_bits returns on the first differing bit counted from bit 0 (polynomials.rs:222-239).  CPU.
+void tsgpu_lt_evaluate_at_field_elements(unsigned num_vars, const tsgpu_fr* a, const tsgpu_fr* b, tsgpu_fr* out) {
+    Fr64 ca = Fr64::from_raw(a->l).from_mont(), cb = Fr64::from_raw(b->l).from_mont();
+    Fr64 res = Fr64::zero();
+    for (unsigned i = 0; i < num_vars && i < 256; ++i) {
+        const bool ba = (ca.l[i / 64] >> (i % 64)) & 1, bb = (cb.l[i / 64] >> (i % 64)) & 1;
+        if (ba && !bb) break;
+        if (!ba && bb) { res = Fr64::one(); break; }
+    }
+    memcpy(out->l, res.l, 32);
+}
 // into_bigint(): Montgomery limbs -> canonical integer limbs.  CPU.
 void tsgpu_fr_to_canonical(const tsgpu_fr* in, size_t n, tsgpu_fr* out) {
     for (size_t i = 0; i < n; ++i) { Fr64 f = Fr64::from_raw(in[i].l).from_mont(); memcpy(out[i].l, f.l, 32); }
