@@ -1,0 +1,86 @@
+//! Raw `extern "C"` declarations of include/tsgpu.h (abi version 1).  Layout contract: `ark_bn254::Fr` is one
+//! `BigInt<4>` = `[u64; 4]` (little-endian limbs of a * 2^256 mod r) = `tsgpu_fr`; `G1Projective` is Jacobian
+//! `{x, y, z: Fq}` = 96 bytes = `tsgpu_g1` (ark-ff / ark-ec 0.4.2; asserted in lib.rs).
+#![allow(non_camel_case_types, dead_code)]
+use ark_bn254::{Fr, G1Projective};
+use std::os::raw::{c_char, c_int, c_uint, c_void};
+
+macro_rules! opaque { ($($n:ident),*) => { $( #[repr(C)] pub struct $n { _p: [u8; 0] } )* } }
+opaque!(Ctx, Table, Sc, Srs, Poly, Params, Proof, TranscriptH);
+
+extern "C" {
+    pub fn tsgpu_abi_version() -> c_int;
+    pub fn tsgpu_init(device: c_int, stream: *mut c_void, out: *mut *mut Ctx) -> c_int;
+    pub fn tsgpu_destroy(ctx: *mut Ctx);
+    pub fn tsgpu_last_error(ctx: *const Ctx) -> *const c_char;
+    pub fn tsgpu_launch_count(ctx: *const Ctx) -> u64;
+
+    // MultilinearExtension (src/polynomials.rs:18-196)
+    pub fn tsgpu_table_upload(ctx: *mut Ctx, evals: *const Fr, n: usize, num_vars: c_uint, out: *mut *mut Table) -> c_int;
+    pub fn tsgpu_table_download(ctx: *mut Ctx, t: *const Table, out: *mut Fr) -> c_int;
+    pub fn tsgpu_table_num_vars(t: *const Table) -> c_uint;
+    pub fn tsgpu_table_free(ctx: *mut Ctx, t: *mut Table);
+    pub fn tsgpu_table_one_hot(ctx: *mut Ctx, num_vars: c_uint, index: usize, out: *mut *mut Table) -> c_int;
+    pub fn tsgpu_table_from_sparse(ctx: *mut Ctx, num_vars: c_uint, indices: *const u64, values: *const Fr, count: usize, out: *mut *mut Table) -> c_int;
+    pub fn tsgpu_table_less_than(ctx: *mut Ctx, num_vars: c_uint, out: *mut *mut Table) -> c_int;
+    pub fn tsgpu_table_add(ctx: *mut Ctx, a: *const Table, b: *const Table, out: *mut *mut Table) -> c_int;
+    pub fn tsgpu_table_scalar_mul(ctx: *mut Ctx, a: *const Table, scalar: *const Fr, out: *mut *mut Table) -> c_int;
+    pub fn tsgpu_table_sum_evaluations(ctx: *mut Ctx, t: *const Table, out: *mut Fr) -> c_int;
+    pub fn tsgpu_mle_evaluate(ctx: *mut Ctx, evals: *const Fr, num_vars: c_uint, point: *const Fr, out: *mut Fr) -> c_int;
+    pub fn tsgpu_mle_partial_evaluate(ctx: *mut Ctx, evals: *const Fr, num_vars: c_uint, fixed: *const Fr, k: c_uint, out: *mut Fr) -> c_int;
+
+    // sum-check rounds, the transcript stays with the caller (src/sumcheck.rs:56-110,156-207)
+    pub fn tsgpu_sc_begin(ctx: *mut Ctx, tables: *const *mut Table, d: c_int, out: *mut *mut Sc) -> c_int;
+    pub fn tsgpu_sc_num_vars(sc: *const Sc) -> c_uint;
+    pub fn tsgpu_sc_round_eval(sc: *mut Sc, evals: *mut Fr) -> c_int;
+    pub fn tsgpu_sc_bind(sc: *mut Sc, r: *const Fr) -> c_int;
+    pub fn tsgpu_sc_bind_eval(sc: *mut Sc, r: *const Fr, evals: *mut Fr) -> c_int;
+    pub fn tsgpu_sc_bind_eval_claim(sc: *mut Sc, r: *const Fr, claim: *const Fr, evals: *mut Fr) -> c_int;
+    pub fn tsgpu_sc_final(sc: *mut Sc, finals: *mut Fr) -> c_int;
+    pub fn tsgpu_sc_end(sc: *mut Sc);
+
+    // SRS + KZG (src/utils.rs:89-96, src/commitments.rs:162-199)
+    pub fn tsgpu_srs_generate(ctx: *mut Ctx, tau: *const Fr, n: usize, out: *mut *mut Srs) -> c_int;
+    pub fn tsgpu_srs_upload(ctx: *mut Ctx, powers: *const G1Projective, n: usize, out: *mut *mut Srs) -> c_int;
+    pub fn tsgpu_srs_download(ctx: *mut Ctx, srs: *const Srs, first: usize, count: usize, out: *mut G1Projective) -> c_int;
+    pub fn tsgpu_srs_len(srs: *const Srs) -> usize;
+    pub fn tsgpu_srs_free(ctx: *mut Ctx, srs: *mut Srs);
+    pub fn tsgpu_kzg_commit(ctx: *mut Ctx, srs: *const Srs, poly: *const Fr, n: usize, out: *mut G1Projective) -> c_int;
+    pub fn tsgpu_kzg_open(ctx: *mut Ctx, srs: *const Srs, poly: *const Fr, n: usize, z: *const Fr, value: *mut Fr, proof: *mut G1Projective) -> c_int;
+    pub fn tsgpu_interpolate_iota(ctx: *mut Ctx, values: *const Fr, n: usize, coeffs: *mut Fr) -> c_int;
+    pub fn tsgpu_msm_g1(ctx: *mut Ctx, bases_affine_xy: *const c_void, scalars: *const Fr, n: usize, out: *mut G1Projective) -> c_int;
+
+    // whole-protocol entry points (host/protocols.cpp): setup_params, Twist / Shout prove + verify
+    pub fn tsgpu_setup_params(ctx: *mut Ctx, log_size: usize, out: *mut *mut Params) -> c_int;
+    pub fn tsgpu_params_free(ctx: *mut Ctx, p: *mut Params);
+    pub fn tsgpu_params_max_operations(p: *const Params) -> usize;
+    pub fn tsgpu_params_tau(p: *const Params, out: *mut Fr);
+    pub fn tsgpu_params_fiat_shamir_seed(p: *const Params, out: *mut u8);
+    pub fn tsgpu_params_srs(p: *const Params) -> *const Srs;
+    pub fn tsgpu_twist_prove(ctx: *mut Ctx, params: *const Params, addresses: *const u64, values: *const Fr, is_write: *const u8,
+                             num_operations: usize, out: *mut *mut Proof) -> c_int;
+    pub fn tsgpu_shout_prove(ctx: *mut Ctx, params: *const Params, entries: *const Fr, num_entries: usize, lookup_indices: *const u64,
+                             num_lookups: usize, out: *mut *mut Proof) -> c_int;
+    pub fn tsgpu_twist_prove_sharded(ctx: *mut Ctx, params: *const Params, addresses: *const u64, values: *const Fr, num_local: usize,
+                                     total_operations: usize, out: *mut *mut Proof) -> c_int;
+    pub fn tsgpu_shout_prove_sharded(ctx: *mut Ctx, params: *const Params, entries: *const Fr, num_local_entries: usize, total_entries: usize,
+                                     lookup_indices: *const u64, num_local_lookups: usize, total_lookups: usize, out: *mut *mut Proof) -> c_int;
+    pub fn tsgpu_twist_verify(ctx: *mut Ctx, params: *const Params, proof: *const Proof, valid: *mut c_int) -> c_int;
+    pub fn tsgpu_shout_verify(ctx: *mut Ctx, params: *const Params, proof: *const Proof, valid: *mut c_int) -> c_int;
+    pub fn tsgpu_proof_num_rounds(p: *const Proof) -> usize;
+    pub fn tsgpu_proof_num_openings(p: *const Proof) -> usize;
+    pub fn tsgpu_proof_commitment(p: *const Proof, which: c_int, out: *mut G1Projective);
+    pub fn tsgpu_proof_round_polynomials(p: *const Proof, out: *mut Fr);
+    pub fn tsgpu_proof_final_evaluation(p: *const Proof, out: *mut Fr);
+    pub fn tsgpu_proof_opening(p: *const Proof, i: usize, proof: *mut G1Projective, value: *mut Fr);
+    pub fn tsgpu_proof_bytes(p: *const Proof, out: *mut u8, capacity: usize) -> usize;
+    pub fn tsgpu_proof_free(p: *mut Proof);
+
+    // multi-GPU (one process per GPU; the host program carries the 128-byte NCCL id)
+    pub fn tsgpu_comm_unique_id(out: *mut u8) -> c_int;
+    pub fn tsgpu_comm_init(ctx: *mut Ctx, nranks: c_int, rank: c_int, id: *const u8) -> c_int;
+    pub fn tsgpu_comm_allgather(ctx: *mut Ctx, input: *const c_void, bytes: usize, out: *mut c_void) -> c_int;
+    pub fn tsgpu_sumcheck_prove_product_sharded(ctx: *mut Ctx, tables: *const *mut Table, d: c_int, num_vars: c_uint, claimed_sum: *const Fr,
+                                                transcript: *mut TranscriptH, round_polys: *mut Fr, final_evaluation: *mut Fr,
+                                                challenges: *mut Fr, table_finals: *mut Fr) -> c_int;
+}
