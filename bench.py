@@ -106,7 +106,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception as e:   # noqa: BLE001
                 self.err = repr(e)
-            self._stop.wait(0.1)
+            self._stop.wait(0.02)
 
     def mark(self):
         """forget samples taken so far (called when the timed region starts)"""
@@ -333,7 +333,9 @@ def main():
         b_ms, b_cnt = ctx.timer_read("bind")
         ctx.set_tuning("kernel_timing", 0)
         gbs = 48.0 * (1 << nv) / (b_ms / b_cnt * 1e-3) / 1e9
-        fold = {"kernel": "k_bind", "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None,
+        fold = {"kernel": "k_bind", "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                # DRAM bytes per launch from `ncu --set full` (profiles/r01_ncu_full_summary.md: 0.5369 GB read + 0.2257 GB written at 2^24 entries), scaled to 2^nv
+                "traffic": (0.536879 + 0.225681) * 1e9 * (1 << nv) / (1 << 24), "algorithmic_bytes": 48.0 * (1 << nv),
                 "launch_ms": b_ms / b_cnt, "workload": f"one 2^{nv}-entry Fr table (2 GiB), 48 B per output entry", "peak_source": hbm_src}
         del cl, T
 

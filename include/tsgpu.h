@@ -101,6 +101,15 @@ void tsgpu_lt_evaluate_at_field_elements(unsigned num_vars, const tsgpu_fr* a, c
 int tsgpu_table_add(tsgpu_ctx* ctx, const tsgpu_table* a, const tsgpu_table* b, tsgpu_table** out);
 int tsgpu_table_scalar_mul(tsgpu_ctx* ctx, const tsgpu_table* a, const tsgpu_fr* scalar, tsgpu_table** out);
 int tsgpu_table_sum_evaluations(tsgpu_ctx* ctx, const tsgpu_table* t, tsgpu_fr* out);
+/* Lookup-argument building blocks: the one-hot matrix ra(x, j) = [idx[j] == x] of Shout (src/polynomials.rs:71-82 row by row) applied
+ * to a vector without materialising its 2^log_k x n entries.
+ *   scatter_add: out[x] = sum over j < n with idx[j] == x of weights[j]   (ra~(., r) for weights = eq(r, .))
+ *   gather:      out[j] = src[idx[j]] for j < n, zero up to 2^num_vars
+ *   inner_product: field_utils::inner_product (src/utils.rs:210-213) of two tables of equal size
+ * An index >= the table size is TSGPU_E_INVALID_PARAMETERS "Lookup index out of bounds" (src/shout.rs:44-48). */
+int tsgpu_table_scatter_add(tsgpu_ctx* ctx, const tsgpu_table* weights, const uint64_t* idx, size_t n, unsigned log_k, tsgpu_table** out);
+int tsgpu_table_gather(tsgpu_ctx* ctx, const tsgpu_table* src, const uint64_t* idx, size_t n, unsigned num_vars, tsgpu_table** out);
+int tsgpu_table_inner_product(tsgpu_ctx* ctx, const tsgpu_table* a, const tsgpu_table* b, tsgpu_fr* out);
 
 /* ---- MultilinearExtension::evaluate / partial_evaluate  (src/polynomials.rs:85-161) -------------- */
 /* host-buffer forms (copy in, compute, copy out) */
@@ -314,6 +323,24 @@ int tsgpu_shout_prove(tsgpu_ctx* ctx, const tsgpu_params* params, const tsgpu_fr
  * after the other); every rank returns the same proof, byte-identical to tsgpu_shout_prove. */
 int tsgpu_shout_prove_sharded(tsgpu_ctx* ctx, const tsgpu_params* params, const tsgpu_fr* entries, size_t num_local_entries, size_t total_entries,
                               const uint64_t* lookup_indices, size_t num_local_lookups, size_t total_lookups, tsgpu_proof** out);
+/* ---- The lookup-correctness sum-check the reference leaves as a stub (src/shout.rs:157-184: the closure returns zero on every branch
+ * and says "In a production implementation, this would involve more complex constraints").  NOT part of the reference's proofs - a
+ * separate, explicitly non-parity mode; Shout::prove above stays byte-identical to the reference.
+ * Statement: lookup j < num_lookups reads entries[lookup_indices[j]] and returns lookup_values[j] (LookupOp { index, value }).
+ * Protocol (core Shout read-checking): r = transcript.challenge_field_elements("read_check_point", log2 L) with L the padded number
+ * of lookups; claim = rv~(r), the multilinear extension of the returned values, appended as "read_check_claim"; then
+ * SumCheck::new(log2 K, claim).prove(|x| ra~(x, r) * Val~(x)) (src/sumcheck.rs:56-110, same labels) over the K padded table entries,
+ * with ra~(x, r) = sum_j eq(r, j) [idx_j == x] built by scatter_add and never as a K x L matrix.  A wrong returned value makes the
+ * prover fail with the reference's own error, TSGPU_E_SUMCHECK "Round 0 consistency check failed".
+ * round_polys: log2 K x 4 coefficients; challenges (optional): log2 K elements.
+ * verify: replays the transcript, SumCheck::verify, and closes with final_evaluation == ra~(x*, r) * Val~(x*) computed from the
+ * statement (gather + inner product + MultilinearExtension::evaluate on the device). */
+int tsgpu_shout_read_check_prove(tsgpu_ctx* ctx, const tsgpu_fr* entries, size_t num_entries, const uint64_t* lookup_indices,
+                                 const tsgpu_fr* lookup_values, size_t num_lookups, tsgpu_transcript* transcript,
+                                 tsgpu_fr* claimed_sum, tsgpu_fr* round_polys, tsgpu_fr* final_evaluation, tsgpu_fr* challenges);
+int tsgpu_shout_read_check_verify(tsgpu_ctx* ctx, const tsgpu_fr* entries, size_t num_entries, const uint64_t* lookup_indices,
+                                  const tsgpu_fr* lookup_values, size_t num_lookups, tsgpu_transcript* transcript,
+                                  const tsgpu_fr* round_polys, size_t num_rounds, const tsgpu_fr* final_evaluation, int* valid);
 /* Twist::verify / Shout::verify (src/twist.rs:255-304, src/shout.rs:225-274): transcript replay, SumCheck::verify and
  * the two KZGCommitment::verify pairing checks (src/commitments.rs:201-228) - all on the CPU, as in the reference. */
 int tsgpu_twist_verify(tsgpu_ctx* ctx, const tsgpu_params* params, const tsgpu_proof* proof, int* valid);

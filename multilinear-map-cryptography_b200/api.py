@@ -11,7 +11,7 @@ from typing import List, Optional, Tuple
 
 import numpy as np
 
-from .binding import Context, Srs, Table, TwistAndShoutError, _fr, _p, lib
+from .binding import Context, Srs, SumCheckProof, Table, Transcript, TwistAndShoutError, _fr, _p, lib
 
 
 def fe(x: int) -> np.ndarray:
@@ -510,4 +510,50 @@ class Shout:
         ctx = verifier_params.ctx
         ok = C.c_int(0)
         ctx.check(lib().tsgpu_shout_verify(ctx._h, verifier_params._h, proof._h, C.byref(ok)))
+        return bool(ok.value)
+
+
+class ShoutReadCheck:
+    """The lookup-correctness sum-check the reference leaves as a stub (src/shout.rs:157-184) - core Shout read-checking,
+    rv~(r) = sum_x ra~(x, r) Val~(x).  NOT part of the reference's proofs (non-parity extension): Shout.prove stays
+    byte-identical to the reference; this proves that every LookupOp { index, value } of a LookupTable returns entries[index]."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+
+    @staticmethod
+    def _statement(table: LookupTable):
+        idx = np.fromiter((l.index for l in table.lookups), dtype=np.uint64, count=len(table.lookups))
+        vals = np.stack([np.asarray(l.value, dtype=np.uint64).reshape(4) for l in table.lookups]) if table.lookups else np.empty((0, 4), dtype=np.uint64)
+        return idx, vals
+
+    def prove(self, table: LookupTable, transcript: Transcript):
+        idx, vals = self._statement(table)
+        return self.prove_arrays(table.entries, idx, vals, transcript)
+
+    def prove_arrays(self, entries, lookup_indices, lookup_values, transcript: Transcript):
+        """-> (claimed_sum, SumCheckProof, challenges)"""
+        entries = _fr(entries) if len(entries) else np.empty((0, 4), dtype=np.uint64)
+        idx = np.ascontiguousarray(lookup_indices, dtype=np.uint64).reshape(-1)
+        vals = _fr(lookup_values) if len(lookup_values) else np.empty((0, 4), dtype=np.uint64)
+        k = max(entries.shape[0] - 1, 0).bit_length()
+        claimed = np.zeros(4, dtype=np.uint64); fe = np.zeros(4, dtype=np.uint64)
+        rp = np.zeros((max(k, 1), 4, 4), dtype=np.uint64); ch = np.zeros((max(k, 1), 4), dtype=np.uint64)
+        self.ctx.check(lib().tsgpu_shout_read_check_prove(self.ctx._h, _p(entries), C.c_size_t(entries.shape[0]), _p(idx), _p(vals), C.c_size_t(idx.shape[0]),
+                                                          transcript._h, _p(claimed), _p(rp), _p(fe), _p(ch)))
+        return claimed, SumCheckProof(rp[:k], fe), ch[:k]
+
+    def verify(self, table: LookupTable, proof: SumCheckProof, transcript: Transcript) -> bool:
+        idx, vals = self._statement(table)
+        return self.verify_arrays(table.entries, idx, vals, proof, transcript)
+
+    def verify_arrays(self, entries, lookup_indices, lookup_values, proof: SumCheckProof, transcript: Transcript) -> bool:
+        entries = _fr(entries) if len(entries) else np.empty((0, 4), dtype=np.uint64)
+        idx = np.ascontiguousarray(lookup_indices, dtype=np.uint64).reshape(-1)
+        vals = _fr(lookup_values) if len(lookup_values) else np.empty((0, 4), dtype=np.uint64)
+        rp = np.ascontiguousarray(proof.round_polynomials, dtype=np.uint64).reshape(-1, 4, 4)
+        fe = _fr(proof.final_evaluation, 1)
+        ok = C.c_int(0)
+        self.ctx.check(lib().tsgpu_shout_read_check_verify(self.ctx._h, _p(entries), C.c_size_t(entries.shape[0]), _p(idx), _p(vals), C.c_size_t(idx.shape[0]),
+                                                           transcript._h, _p(rp), C.c_size_t(rp.shape[0]), _p(fe), C.byref(ok)))
         return bool(ok.value)

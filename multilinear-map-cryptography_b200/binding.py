@@ -357,6 +357,26 @@ class Table:
         self.ctx.check(lib().tsgpu_table_scalar_mul(self.ctx._h, self._h, _p(scalar), C.byref(h)))
         return Table(self.ctx, h)
 
+    def scatter_add(self, idx, log_k: int) -> "Table":
+        """out[x] = sum over j with idx[j] == x of self[j]: the one-hot lookup matrix applied to this weight vector"""
+        idx = np.ascontiguousarray(idx, dtype=np.uint64).reshape(-1)
+        h = C.c_void_p()
+        self.ctx.check(lib().tsgpu_table_scatter_add(self.ctx._h, self._h, _p(idx), C.c_size_t(idx.shape[0]), C.c_uint(log_k), C.byref(h)))
+        return Table(self.ctx, h)
+
+    def gather(self, idx, num_vars: int) -> "Table":
+        """out[j] = self[idx[j]], zero padded to 2^num_vars entries"""
+        idx = np.ascontiguousarray(idx, dtype=np.uint64).reshape(-1)
+        h = C.c_void_p()
+        self.ctx.check(lib().tsgpu_table_gather(self.ctx._h, self._h, _p(idx), C.c_size_t(idx.shape[0]), C.c_uint(num_vars), C.byref(h)))
+        return Table(self.ctx, h)
+
+    def inner_product(self, other: "Table") -> np.ndarray:
+        """field_utils::inner_product (utils.rs:210-213)"""
+        out = np.empty(4, dtype=np.uint64)
+        self.ctx.check(lib().tsgpu_table_inner_product(self.ctx._h, self._h, other._h, _p(out)))
+        return out
+
     def sum_evaluations(self) -> np.ndarray:
         """MultilinearExtension::sum_evaluations (polynomials.rs:192-195)"""
         out = np.empty(4, dtype=np.uint64)

@@ -10,6 +10,7 @@
 #include "mle.cuh"
 #include "sumcheck.cuh"
 #include "interp.cuh"
+#include "lookup.cuh"
 
 using namespace tsg;
 
@@ -366,6 +367,55 @@ int tsgpu_table_sum_evaluations(tsgpu_ctx* ctx, const tsgpu_table* t, tsgpu_fr* 
     if (!ctx || !t || !out) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
     { KernelTimer kt(ctx, "table_sum");
       TSG_CUDA(ctx, launch_table_sum(t->d, (size_t)1 << t->num_vars, ctx->partials, ctx->ticket, ctx->dev_out, ctx->sm_count, ctx->stream)); }
+    ctx->launches += 1;
+    return read_result(ctx, 1, out);
+}
+
+// ---- lookup-argument building blocks (csrc/lookup.cu): the one-hot matrix ra(x, j) = [idx_j == x] applied without materialising it
+// out[x] = sum over j < n with idx[j] == x of weights[j], x < 2^log_k   (weights: a table of at least n entries)
+int tsgpu_table_scatter_add(tsgpu_ctx* ctx, const tsgpu_table* weights, const uint64_t* idx, size_t n, unsigned log_k, tsgpu_table** out) {
+    if (!ctx || !weights || !out || (!idx && n)) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    if (log_k > 32 || n > ((size_t)1 << weights->num_vars)) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "more indices than weights");
+    const size_t K = (size_t)1 << log_k;
+    for (size_t j = 0; j < n; ++j) if (idx[j] >= K) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "Lookup index out of bounds");   // shout.rs:44-48
+    tsgpu_table* t = nullptr;
+    int rc = table_alloc(ctx, log_k, &t);
+    if (rc) return rc;
+    TempBuf di, acc;
+    TSG_CUDA(ctx, di.alloc(n * 8, ctx->stream));
+    TSG_CUDA(ctx, acc.alloc(K * 64, ctx->stream));
+    if (n) TSG_CUDA(ctx, cudaMemcpyAsync(di.p, idx, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    TSG_CUDA(ctx, cudaMemsetAsync(acc.p, 0, K * 64, ctx->stream));
+    TSG_CUDA(ctx, launch_weighted_hist(weights->d, weights->num_vars, di.as<unsigned long long>(), n, acc.as<unsigned long long>(), ctx->sm_count, ctx->stream));
+    TSG_CUDA(ctx, launch_limb_sums_to_table(acc.as<unsigned long long>(), log_k, t->d, ctx->sm_count, ctx->stream));
+    ctx->launches += n ? 2 : 1;
+    TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // `idx` is borrowed
+    *out = t;
+    return TSGPU_OK;
+}
+// out[j] = src[idx[j]] for j < n, zero for n <= j < 2^num_vars
+int tsgpu_table_gather(tsgpu_ctx* ctx, const tsgpu_table* src, const uint64_t* idx, size_t n, unsigned num_vars, tsgpu_table** out) {
+    if (!ctx || !src || !out || (!idx && n)) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    if (num_vars > 40 || n > ((size_t)1 << num_vars)) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "more indices than output entries");
+    const size_t K = (size_t)1 << src->num_vars;
+    for (size_t j = 0; j < n; ++j) if (idx[j] >= K) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "Lookup index out of bounds");
+    tsgpu_table* t = nullptr;
+    int rc = table_alloc(ctx, num_vars, &t);
+    if (rc) return rc;
+    TempBuf di;
+    TSG_CUDA(ctx, di.alloc(n * 8, ctx->stream));
+    if (n) TSG_CUDA(ctx, cudaMemcpyAsync(di.p, idx, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    TSG_CUDA(ctx, launch_table_gather(src->d, src->num_vars, di.as<unsigned long long>(), n, num_vars, t->d, ctx->sm_count, ctx->stream));
+    ctx->launches += 1;
+    TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = t;
+    return TSGPU_OK;
+}
+// field_utils::inner_product (src/utils.rs:210-213) of two tables of equal size: lazy 512-bit dot product, one pass
+int tsgpu_table_inner_product(tsgpu_ctx* ctx, const tsgpu_table* a, const tsgpu_table* b, tsgpu_fr* out) {
+    if (!ctx || !a || !b || !out) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    if (a->num_vars != b->num_vars) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "Vector lengths must match");
+    TSG_CUDA(ctx, launch_dot(a->d, b->d, (size_t)1 << a->num_vars, ctx->partials, ctx->ticket, ctx->dev_out, ctx->sm_count, ctx->stream));
     ctx->launches += 1;
     return read_result(ctx, 1, out);
 }

@@ -1,0 +1,83 @@
+// lookup.cu - kernels of the lookup (read-checking) argument: the sparse one-hot matrix ra(x, j) = [idx_j == x] of Shout is never
+// materialised (K x T entries); what the sum-check needs is its product with a weight vector,
+//     A[x] = sum_{j : idx_j = x} W[j]                      (A = ra~(., r) for W = eq(r, .)),
+// and the gather G[j] = S[idx_j] for the verifier's closing check.  This is the constraint the reference leaves as a stub
+// (src/shout.rs:157-184: "In a production implementation, this would involve more complex constraints ...").
+//
+// Field elements cannot be added atomically, but their limbs can: the Montgomery representation is linear, so A[x] is the sum
+// of the 256-bit integers W[j] reduced mod r once at the end.  Every bucket owns eight 64-bit counters, one per 32-bit limb
+// (exact for up to 2^32 contributions per bucket); a second kernel carries and reduces them.  The result does not depend on the
+// order of the atomics, so it is deterministic.  Tables are in the bit-reversed position order of sumcheck.cu.
+#include "fr_device.cuh"
+#include "lookup.cuh"
+
+namespace tsg {
+
+__device__ __forceinline__ unsigned long long bitrev_u64(unsigned long long x, unsigned bits) {
+    return bits ? (__brevll(x) >> (64 - bits)) : 0ull;
+}
+
+// j runs in natural order: the index loads are coalesced, the weight loads are whole 32-byte sectors
+__global__ void __launch_bounds__(256) k_weighted_hist(const fr_t* W, unsigned l, const unsigned long long* idx, size_t n, unsigned long long* acc) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        const fr_t w = ld256_nc(W + bitrev_u64(j, l));
+        unsigned long long* a = acc + 8 * idx[j];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) if (w.l[i]) atomicAdd(a + i, (unsigned long long)w.l[i]);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_limb_sums_to_table(const unsigned long long* acc, unsigned k, fr_t* out) {
+    const size_t K = (size_t)1 << k;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < K; x += stride) {
+        // carry-propagate the eight limb sums into 256 low bits + a 64-bit high part
+        fr_t lo;
+        unsigned long long carry = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const unsigned long long s = acc[8 * x + i];
+            const unsigned long long v = (s & 0xffffffffull) + (carry & 0xffffffffull);
+            lo.l[i] = (uint32_t)v;
+            carry = (s >> 32) + (carry >> 32) + (v >> 32);
+        }
+        // low part < 2^256 < 6 r: at most five subtractions; high part: hi * 2^256 mod r is the Montgomery form of hi
+#pragma unroll
+        for (int t = 0; t < 5; ++t) limb::cond_sub_mod<FrP>(lo.l);
+        fr_t r = lo;
+        if (carry) r = r + fr_t::from_u64(carry);
+        st256(out + bitrev_u64(x, k), r);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_table_gather(const fr_t* src, unsigned k, const unsigned long long* idx, size_t n, unsigned l, fr_t* out) {
+    const size_t L = (size_t)1 << l;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < L; j += stride) {
+        fr_t v = fr_t::zero();
+        if (j < n) v = ld256_nc(src + bitrev_u64(idx[j], k));
+        st256(out + bitrev_u64(j, l), v);
+    }
+}
+
+static inline int grid_for(size_t work, int threads, size_t cap) {
+    size_t g = (work + threads - 1) / threads;
+    if (g < 1) g = 1;
+    return (int)(g < cap ? g : cap);
+}
+cudaError_t launch_weighted_hist(const fr_t* W, unsigned l, const unsigned long long* idx, size_t n, unsigned long long* acc, int sm_count, cudaStream_t s) {
+    if (!n) return cudaSuccess;
+    k_weighted_hist<<<grid_for(n, 256, (size_t)sm_count * 8), 256, 0, s>>>(W, l, idx, n, acc);
+    return cudaGetLastError();
+}
+cudaError_t launch_limb_sums_to_table(const unsigned long long* acc, unsigned k, fr_t* out, int sm_count, cudaStream_t s) {
+    k_limb_sums_to_table<<<grid_for((size_t)1 << k, 256, (size_t)sm_count * 8), 256, 0, s>>>(acc, k, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_table_gather(const fr_t* src, unsigned k, const unsigned long long* idx, size_t n, unsigned l, fr_t* out, int sm_count, cudaStream_t s) {
+    k_table_gather<<<grid_for((size_t)1 << l, 256, (size_t)sm_count * 8), 256, 0, s>>>(src, k, idx, n, l, out);
+    return cudaGetLastError();
+}
+
+}  // namespace tsg
