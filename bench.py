@@ -276,6 +276,35 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms, e2e_ms, coef["ms"], coef_e2e_ms = (float(x) for x in t)
 
+    # ---- N > 1, strong-scaling companion: ONE proof of the same trace shape sharded over the ranks (evaluation-basis slices per rank, three small
+    # all-gathers over the library's NCCL communicator; byte-identical to the one-GPU proof, tests/test_gpu_distributed.py).  Reported beside the
+    # weak-scaling headline (one independent proof per GPU); host buffers in, proof out, CUDA events, max over ranks.
+    sharded = None
+    if world > 1:
+        try:
+            ctx.comm_init_torch()
+            addr0, vals0_u64, _ = synthetic_trace(LOG_OPS, LOG_CELLS, seed=2)                    # the same trace on every rank; each passes its slice
+            lo, hi = twist.shard_range(n, rank, world)
+            a_pin = torch.empty(hi - lo, dtype=torch.int64, pin_memory=True); a_pin.numpy().view(np.uint64)[:] = addr0[lo:hi]
+            v_pin = torch.empty((hi - lo, 4), dtype=torch.int64, pin_memory=True); v_pin.numpy().view(np.uint64)[:] = ts.fe_vec(vals0_u64[lo:hi])
+            a_s = a_pin.numpy().view(np.uint64); v_s = v_pin.numpy().view(np.uint64)
+            ps = twist.prove_sharded(a_s, v_s, n)
+            assert twist.verify(ps, vp), "sharded proof does not verify"
+            for _ in range(W):
+                twist.prove_sharded(a_s, v_s, n)
+            barrier()
+            e0.record(stream)
+            for _ in range(K):
+                twist.prove_sharded(a_s, v_s, n)
+            e1.record(stream)
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1) / K], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sharded = {"value": float(t[0]), "unit": "ms", "scaling": "strong", "ops_per_s": n / (float(t[0]) * 1e-3),
+                       "what": "ONE Twist::prove of 2^20 ops sharded over the ranks (tsgpu_twist_prove_sharded), host buffers"}
+        except Exception as e:   # noqa: BLE001
+            sharded = {"error": repr(e)}
+
     # ---- roofline of the dominant kernel of the step: MSM bucket accumulation (integer-pipe bound).
     # Two accountings, both reported:
     #  * `achieved` (the contract's): SURVEY 8(d)'s per-unit figure x the units of a launch / the launch duration.  The figure is
@@ -375,6 +404,7 @@ def main():
             "msm_points_per_s": dflt["msm_points"] / (dflt["msm_total_ms"] * 1e-3) if dflt["msm_total_ms"] > 0 else None,
             "msm_full_width_points_per_s": coef["msm_points"] / (coef["msm_total_ms"] * 1e-3) if coef["msm_total_ms"] > 0 else None,
             "ops_per_s_all_gpus": world * n / (dev_ms * 1e-3),
+            "one_proof_sharded": sharded,
         }
         print(json.dumps(line))
     if world > 1:

@@ -13,7 +13,7 @@ import oracle as O
 args = sys.argv[1:]
 def opt(name, default):
     return int(args[args.index(name) + 1]) if name in args else default
-which = [a for a in args if a in ("c3", "c4", "c5")] or ["c3", "c4", "c5"]
+which = [a for a in args if a in ("c3", "c3check", "c4", "c5")] or ["c3", "c3check", "c4", "c5"]
 C3_T, C3_L = opt("--c3-table-log", 20), opt("--c3-lookups-log", 22)
 C4_LOG, C5_LOG = opt("--c4-log", 26), opt("--c5-log", 24)
 
@@ -33,6 +33,24 @@ def timed(fn, reps=5, warm=2):
         e0.record(stream); fn(); e1.record(stream); torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
     return best
+
+
+def c3check():
+    """the real lookup-correctness sum-check (non-parity mode, host/read_check.cpp) on the C3 statement: prove + verify"""
+    T, L = 1 << C3_T, 1 << C3_L
+    entries = ts.fe_vec(np.arange(T, dtype=np.uint64) ** 2)
+    idx = O.chacha_u64(bytes([3]) * 32, L) % np.uint64(T)
+    vals = np.ascontiguousarray(entries[idx.astype(np.int64)])
+    rc = ts.ShoutReadCheck(ctx)
+    claim, proof, _ = rc.prove_arrays(entries, idx, vals, ts.Transcript())
+    assert rc.verify_arrays(entries, idx, vals, proof, ts.Transcript())
+    out = {"config": "C3-read-check", "workload": f"Shout read-checking sum-check, 2^{C3_T}-entry table, 2^{C3_L} lookups (host buffers in, proof out)", "n_gpus": 1,
+           "rounds": int(proof.round_polynomials.shape[0])}
+    out["prove_ms"] = timed(lambda: rc.prove_arrays(entries, idx, vals, ts.Transcript()), reps=3, warm=1)
+    out["verify_ms"] = timed(lambda: rc.verify_arrays(entries, idx, vals, proof, ts.Transcript()), reps=3, warm=1)
+    out["h2d_bytes"] = int(entries.nbytes + idx.nbytes + vals.nbytes)
+    out["lookups_per_s"] = L / (out["prove_ms"] * 1e-3)
+    print(json.dumps(out), flush=True)
 
 
 def c3():
@@ -105,5 +123,5 @@ def c5():
 
 
 for name in which:
-    {"c3": c3, "c4": c4, "c5": c5}[name]()
+    {"c3": c3, "c3check": c3check, "c4": c4, "c5": c5}[name]()
 ctx.close()
