@@ -1,6 +1,7 @@
 // context.cuh - internal definitions behind the opaque handles of include/tsgpu.h
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <cstdint>
 #include <map>
 #include <string>
@@ -84,9 +85,12 @@ int table_alloc(tsgpu_ctx* ctx, unsigned num_vars, tsgpu_table** out);
 void* arena_get(tsgpu_ctx* ctx, int slot, size_t bytes, cudaError_t* err);
 
 // RAII scope timing one kernel (or a short sequence) on the context stream when timing is enabled
+// It also opens an NVTX range of the same name (header-only nvtx3: a no-op unless a profiler is attached), so `ncu --nvtx
+// --nvtx-include "msm_total/"` or an nsys timeline groups the kernels by phase.
 struct KernelTimer {
     tsgpu_ctx* ctx; cudaEvent_t a = nullptr, b = nullptr; const char* name;
-    KernelTimer(tsgpu_ctx* c, const char* n) : ctx(c), name(n) {
+    struct Nvtx { explicit Nvtx(const char* n) { nvtxRangePushA(n); } ~Nvtx() { nvtxRangePop(); } } nvtx;
+    KernelTimer(tsgpu_ctx* c, const char* n) : ctx(c), name(n), nvtx(n) {
         if (!ctx->timing) return;
         cudaEventCreate(&a); cudaEventCreate(&b);
         cudaEventRecord(a, ctx->stream);

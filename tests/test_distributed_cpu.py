@@ -127,3 +127,26 @@ def test_limb_sum_conversion_single_process(tsgpu, oracle):
     assert oracle.limbs_to_ints(dd.from_limb_sums(s)) == [8 * x % oracle.R_MOD for x in xs]
     ev = oracle.fr_from_ints([54, 54 + 51 + 3, 54 + 102 + 12, 54 + 153 + 27])      # 54 + 51x + 3x^2 at 0..3 (Appendix C.3)
     assert oracle.fr_to_ints(dd.round_coeffs(ev)) == [54, 51, 3, 0]
+
+
+def test_shard_ranges_partition_the_padded_vectors():
+    """Twist.shard_range / Shout.shard_range (what tsgpu_twist_prove_sharded / tsgpu_shout_prove_sharded expect from rank r): contiguous,
+    disjoint, covering exactly the real operations, each inside the rank's slice [r m / G, (r + 1) m / G) of the padded length m"""
+    import importlib
+    ts = importlib.import_module("multilinear-map-cryptography_b200")
+    for total in (0, 1, 2, 3, 5, 8, 37, 1000, 4096, (1 << 16) - 77, 1 << 16):
+        m = 1
+        while m < total:
+            m <<= 1
+        for world in (1, 2, 4, 8):
+            if m < world:
+                continue
+            prev = 0
+            for rank in range(world):
+                lo, hi = ts.Twist.shard_range(total, rank, world)
+                assert (lo, hi) == ts.Shout.shard_range(total, rank, world)
+                assert lo == prev and lo <= hi <= total
+                count = m // world
+                assert hi - lo <= count and (hi == lo or (lo >= rank * count and hi <= (rank + 1) * count))
+                prev = hi
+            assert prev == total

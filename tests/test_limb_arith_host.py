@@ -14,10 +14,12 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.fixture(scope="module")
-def harness():
-    out = os.path.join(tempfile.gettempdir(), f"tsg_limb_harness_{os.getpid()}.so")
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas", *os.environ.get("TSG_HARNESS_CXXFLAGS", "").split(),
+# the second build runs the same checks under UBSan (shift widths, signed overflow, misaligned access abort the process): the host-side
+# stand-in for compute-sanitizer, which is closed on the GPU pool
+@pytest.fixture(scope="module", params=["", "-fsanitize=undefined -fno-sanitize-recover=all"], ids=["plain", "ubsan"])
+def harness(request):
+    out = os.path.join(tempfile.gettempdir(), f"tsg_limb_harness_{os.getpid()}_{request.param_index}.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas", *request.param.split(), *os.environ.get("TSG_HARNESS_CXXFLAGS", "").split(),
                            "-I", os.path.join(ROOT, "multilinear-map-cryptography_b200", "csrc"),
                            "-o", out, os.path.join(ROOT, "tests", "helpers", "limb_harness.cpp")])
     lib = C.CDLL(out)
