@@ -168,6 +168,10 @@ int tsgpu_set_tuning(tsgpu_ctx* ctx, const char* key, long value) {
         set_tma_min_work(value < 0 || value > 62 ? ~(size_t)0 : (size_t)1 << value);
         return TSGPU_OK;
     }
+    if (!strcmp(key, "prefetch_min_log2")) {   // d = 2 rounds with >= 2^value positions per launch use the warp-private prefetch kernels; < 0 disables
+        set_prefetch_min_work(value < 0 || value > 61 ? (size_t)1 << 62 : (size_t)1 << value);
+        return TSGPU_OK;
+    }
     if (!strcmp(key, "kernel_timing")) { ctx->timing = value != 0; return TSGPU_OK; }
     if (!strcmp(key, "msm_tables")) { ctx->msm_tables = value != 0; return TSGPU_OK; }   // 0: per-window bucket sets on the plain SRS points
     if (!strcmp(key, "eval_basis")) { ctx->eval_basis = value != 0; return TSGPU_OK; }   // 0: Twist/Shout::prove interpolate and commit coefficients

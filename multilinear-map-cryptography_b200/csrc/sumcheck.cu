@@ -273,6 +273,108 @@ __global__ void __launch_bounds__(TMA_THREADS, (D <= 2 ? TMA_MINBLOCKS : 1)) k_b
     grid_finish_sum<fr_t, EvalAcc<D>::NV>(v, partials, ticket, smem, EvalEpilogue<D>{out4});
 }
 
+// ---------------------------------------------------------------- warp-private prefetch variants
+// The ncu capture of the plain kernels shows the FMA-heavy pipe 67-69% busy with `long_scoreboard` (waiting for the loads at the top of
+// the loop) as the largest stall: 16 warps per SM cannot both hide HBM latency and keep the multiplier fed, and the 64 registers that a
+// register-level prefetch of the next eight elements would need do not exist (128 per thread already).  Here the NEXT iteration's data
+// waits in shared memory instead: every warp owns one slot (rows x 32 lanes x 32 bytes) and one mbarrier; lane 0 posts one 1 KiB bulk
+// copy (cp.async.bulk, the TMA engine) per row for the warp's next tile right after the warp has pulled the current tile into registers,
+// so a whole iteration of arithmetic (~2000 cycles) covers the copy.  No CTA-wide barrier, the same 2 x 256 threads per SM and the same
+// register budget as the plain kernels; 64 KiB (fused) / 32 KiB (evaluation) of dynamic shared memory per CTA.
+constexpr int PF_WARPS = SC_THREADS / 32;
+
+template <int ROWS>
+struct WarpPrefetch {
+    unsigned char* slot; uint64_t* bar; uint32_t phase; unsigned lane;
+    __device__ __forceinline__ void init(unsigned char* dyn, uint64_t* bars) {
+        const unsigned warp = threadIdx.x >> 5; lane = threadIdx.x & 31;
+        slot = dyn + (size_t)warp * ROWS * 1024; bar = bars + warp; phase = 0;
+        if (lane == 0) { tma::mbar_init(bar, 1); tma::fence_barrier_init(); }
+        __syncwarp();
+    }
+    // rows[i] = address of this warp's 32 consecutive elements of stream i
+    __device__ __forceinline__ void issue(const fr_t* const (&rows)[ROWS]) {
+        if (lane == 0) {
+            tma::mbar_expect_tx(bar, ROWS * 1024u);
+#pragma unroll
+            for (int i = 0; i < ROWS; ++i) tma::bulk_g2s(slot + i * 1024, rows[i], 1024u, bar);
+        }
+    }
+    __device__ __forceinline__ void fetch(fr_t (&e)[ROWS]) {
+        tma::mbar_wait(bar, phase); phase ^= 1;
+#pragma unroll
+        for (int i = 0; i < ROWS; ++i) e[i] = ((const fr_t*)(slot + i * 1024))[lane];
+        __syncwarp();          // every lane has read the slot before lane 0 lets the copy engine overwrite it
+    }
+};
+
+__global__ void __launch_bounds__(SC_THREADS, 2) k_bind_eval2_claim_pf(ScTables tabs, size_t quarter, const fr_ctab r, const fr_t claim, fr_t* partials,
+                                                                        unsigned int* ticket, fr_t* out4) {
+    extern __shared__ __align__(128) unsigned char dyn[];
+    __shared__ fr_t smem[2 * 32];
+    __shared__ uint64_t bars[PF_WARPS];
+    WarpPrefetch<8> pf; pf.init(dyn, bars);
+    EvalAcc2Claim acc; acc.clear();
+    const size_t tiles = quarter / 32, nw = (size_t)gridDim.x * PF_WARPS;
+    size_t tile = (size_t)blockIdx.x * PF_WARPS + (threadIdx.x >> 5);
+    auto post = [&](size_t t) {
+        const fr_t* rows[8];
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rows[4 * k + j] = tabs.t[k] + j * quarter + t * 32;
+        pf.issue(rows);
+    };
+    if (tile < tiles) post(tile);
+    for (; tile < tiles; tile += nw) {
+        fr_t e[8];
+        pf.fetch(e);
+        if (tile + nw < tiles) post(tile + nw);
+        const size_t p = tile * 32 + pf.lane;
+        fr_t lo[2], hi[2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            lo[t] = e[4 * t + 0] + r.mul(e[4 * t + 2] - e[4 * t + 0]);
+            hi[t] = e[4 * t + 1] + r.mul(e[4 * t + 3] - e[4 * t + 1]);
+            st256(tabs.t[t] + p, lo[t]);
+            st256(tabs.t[t] + p + quarter, hi[t]);
+        }
+        acc.pair(lo, hi);
+    }
+    fr_t v[2];
+    acc.finish(v);
+    grid_finish_sum<fr_t, 2>(v, partials, ticket, smem, EvalClaimEpilogue{out4, claim});
+}
+
+__global__ void __launch_bounds__(SC_THREADS, 2) k_round_eval2_pf(ScTables tabs, size_t half, fr_t* partials, unsigned int* ticket, fr_t* out4) {
+    extern __shared__ __align__(128) unsigned char dyn[];
+    __shared__ fr_t smem[EvalAcc<2>::NV * 32];
+    __shared__ uint64_t bars[PF_WARPS];
+    WarpPrefetch<4> pf; pf.init(dyn, bars);
+    EvalAcc<2> acc; acc.clear();
+    const size_t tiles = half / 32, nw = (size_t)gridDim.x * PF_WARPS;
+    size_t tile = (size_t)blockIdx.x * PF_WARPS + (threadIdx.x >> 5);
+    auto post = [&](size_t t) {
+        const fr_t* rows[4] = {tabs.t[0] + t * 32, tabs.t[0] + half + t * 32, tabs.t[1] + t * 32, tabs.t[1] + half + t * 32};
+        pf.issue(rows);
+    };
+    if (tile < tiles) post(tile);
+    for (; tile < tiles; tile += nw) {
+        fr_t e[4];
+        pf.fetch(e);
+        if (tile + nw < tiles) post(tile + nw);
+        fr_t lo[2] = {e[0], e[2]}, hi[2] = {e[1], e[3]};
+        acc.pair(lo, hi);
+    }
+    fr_t v[EvalAcc<2>::NV];
+    acc.finish(v);
+    grid_finish_sum<fr_t, EvalAcc<2>::NV>(v, partials, ticket, smem, EvalEpilogue<2>{out4});
+}
+// positions per launch from which the prefetch variants run (tuning "prefetch_min_log2").  Measured on B200 (tools/bench_fold.py): +5.7% on the fused
+// kernel and +3% on the evaluation kernel at 2^26 entries, +3-5% down to 2^22, neutral below (the tables then sit in the 126 MB L2).
+static size_t g_pf_min_work = (size_t)1 << 21;
+void set_prefetch_min_work(size_t w) { g_pf_min_work = w < 1024 ? 1024 : w; }
+
 // Runtime switch between the simple grid-stride kernels and the TMA-pipelined ones: on B200 the rounds are
 // integer-pipe bound with the carry-chain multiplier and the simple kernels measured 5-10% faster
 // (profiles/r01_kernel_variants.md), so the pipelined path is opt-in (tsgpu_set_tuning "tma_min_log2").
@@ -314,6 +416,13 @@ cudaError_t launch_round_eval(int d, const ScTables& tabs, size_t n, fr_t* parti
         }
         return cudaGetLastError();
     }
+    if (d == 2 && half >= g_pf_min_work && half % 32 == 0) {
+        const size_t sm = (size_t)PF_WARPS * 4 * 1024;
+        cudaError_t e = enable_smem(k_round_eval2_pf, sm);
+        if (e) return e;
+        k_round_eval2_pf<<<sc_grid(half, sm_count, 2), SC_THREADS, sm, s>>>(tabs, half, partials, ticket, out4);
+        return cudaGetLastError();
+    }
     int grid = sc_grid(half, sm_count, SC_BLOCKS_PER_SM);
     switch (d) {
         case 1: k_round_eval<1><<<grid, SC_THREADS, 0, s>>>(tabs, half, partials, ticket, out4); break;
@@ -352,6 +461,13 @@ cudaError_t launch_bind_eval(int d, const ScTables& tabs, size_t n, const fr_t& 
     const fr_ctab r = fr_ctab::make(r_elem);
     size_t quarter = n / 4;
     if (claim && d == 2 && quarter < g_tma_min_work) {
+        if (quarter >= g_pf_min_work && quarter % 32 == 0) {
+            const size_t sm = (size_t)PF_WARPS * 8 * 1024;
+            cudaError_t e = enable_smem(k_bind_eval2_claim_pf, sm);
+            if (e) return e;
+            k_bind_eval2_claim_pf<<<sc_grid(quarter, sm_count, 2), SC_THREADS, sm, s>>>(tabs, quarter, r, *claim, partials, ticket, out4);
+            return cudaGetLastError();
+        }
         k_bind_eval2_claim<<<sc_grid(quarter, sm_count, TSG_BE_MINB), SC_THREADS, 0, s>>>(tabs, quarter, r, *claim, partials, ticket, out4);
         return cudaGetLastError();
     }

@@ -32,6 +32,7 @@ struct ScTables { fr_t* t[SC_MAX_TABLES]; };
 inline int sc_max_grid(int sm_count) { return sm_count * SC_BLOCKS_PER_SM_BIND; }
 
 void set_tma_min_work(size_t positions);
+void set_prefetch_min_work(size_t positions);   // d = 2 round kernels with a warp-private shared-memory prefetch of the next tile
 cudaError_t launch_round_eval(int d, const ScTables& tabs, size_t n, fr_t* partials, unsigned int* ticket, fr_t* out4,
                               int sm_count, cudaStream_t s);
 cudaError_t launch_bind(fr_t* t, size_t n, const fr_t& r, int sm_count, cudaStream_t s);

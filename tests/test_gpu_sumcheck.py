@@ -113,6 +113,26 @@ def test_tma_pipelined_path_matches_oracle(ctx, oracle, d, fused):
     assert (finals == ref["finals"]).all()
 
 
+@pytest.mark.parametrize("nv", [12, 17, 18])
+def test_warp_prefetch_path_matches_oracle(ctx, tsgpu, oracle, nv):
+    """d = 2 with the warp-private prefetch kernels (cp.async.bulk into one shared-memory slot per warp) switched on for every launch
+    of at least 2^10 positions, the later rounds on the plain kernels: the full proof through the C++ host loop (round 0 evaluation
+    kernel, then the fused claim form) must equal the oracle's, and so must the round-by-round drive without the claim."""
+    tables = [oracle.chacha_fr_rand(seed_bytes(80 + t + nv), 1 << nv) for t in range(2)]
+    ctx.set_tuning("prefetch_min_log2", 10)
+    try:
+        coeffs, chals, finals = drive_rounds(ctx, oracle, tables, fused=False)        # k_round_eval2_pf every round
+        zero, one = oracle.fr_from_ints([0, 1])
+        claimed = oracle.field_binop("fr", "add", oracle.horner(coeffs[0], zero), oracle.horner(coeffs[0], one))[0]
+        proof, ch2, fin2 = tsgpu.SumCheck(nv, claimed).prove_product(ctx, [ctx.table_upload(t) for t in tables], tsgpu.Transcript(), return_aux=True)
+    finally:
+        ctx.set_tuning("prefetch_min_log2", -1)
+    ref = oracle.sumcheck_prove_product(tables, claimed, mode="tables")
+    assert (coeffs == ref["round_polynomials"]).all() and (chals == ref["challenges"]).all() and (finals == ref["finals"]).all()
+    assert (proof.round_polynomials == ref["round_polynomials"]).all() and (proof.final_evaluation == ref["final_evaluation"]).all()
+    assert (ch2 == ref["challenges"]).all() and (fin2 == ref["finals"]).all()
+
+
 @pytest.mark.parametrize("d,nv", [(1, 4), (2, 6), (3, 5), (2, 12)])
 def test_prove_product_host_loop_matches_reference_prove(ctx, tsgpu, oracle, d, nv):
     """The C++ host loop (host/sumcheck_host.cpp) + device rounds == SumCheck::prove with the product closure:
