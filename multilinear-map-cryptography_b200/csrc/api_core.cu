@@ -425,6 +425,12 @@ int tsgpu_table_inner_product(tsgpu_ctx* ctx, const tsgpu_table* a, const tsgpu_
 }
 
 // ------------------------------------------------------------------------------- evaluate / partial
+// results that a kernel wrote directly into the pinned mirror: wait for the stream, copy out
+static int read_host_result(tsgpu_ctx* ctx, int count, tsgpu_fr* out) {
+    TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(out, ctx->host_out, count * sizeof(fr_t));
+    return TSGPU_OK;
+}
 static int read_result(tsgpu_ctx* ctx, int count, tsgpu_fr* out) {
     TSG_CUDA(ctx, cudaMemcpyAsync(ctx->host_out, ctx->dev_out, count * sizeof(fr_t), cudaMemcpyDeviceToHost, ctx->stream));
     TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -540,9 +546,10 @@ int tsgpu_sc_round_eval(tsgpu_sc* sc, tsgpu_fr evals[4]) {
     tsgpu_ctx* ctx = sc->ctx;
     if (sc->vars_left == 0) return fail(ctx, TSGPU_E_SUMCHECK, "no variables left to evaluate");
     KernelTimer kt(ctx, "sc_round_eval");
-    TSG_CUDA(ctx, launch_round_eval(sc->d, sc_tabs(sc), (size_t)1 << sc->vars_left, ctx->partials, ctx->ticket, ctx->dev_out, ctx->sm_count, ctx->stream));
+    // the finishing block writes the four values straight into the pinned host mirror (unified addressing: no D2H copy to enqueue per round)
+    TSG_CUDA(ctx, launch_round_eval(sc->d, sc_tabs(sc), (size_t)1 << sc->vars_left, ctx->partials, ctx->ticket, ctx->host_out, ctx->sm_count, ctx->stream));
     ctx->launches += 1;
-    return read_result(ctx, 4, evals);
+    return read_host_result(ctx, 4, evals);
 }
 
 int tsgpu_sc_bind(tsgpu_sc* sc, const tsgpu_fr* r) {
@@ -564,12 +571,12 @@ static int sc_bind_eval_impl(tsgpu_sc* sc, const tsgpu_fr* r, const tsgpu_fr* cl
     if (sc->vars_left < 2) return fail(ctx, TSGPU_E_SUMCHECK, "bind_eval needs at least two unbound variables");
     KernelTimer kt(ctx, "sc_bind_eval");
     fr_t cl; if (claim) cl = to_fr(claim);
-    TSG_CUDA(ctx, launch_bind_eval(sc->d, sc_tabs(sc), (size_t)1 << sc->vars_left, to_fr(r), claim ? &cl : nullptr, ctx->partials, ctx->ticket, ctx->dev_out,
+    TSG_CUDA(ctx, launch_bind_eval(sc->d, sc_tabs(sc), (size_t)1 << sc->vars_left, to_fr(r), claim ? &cl : nullptr, ctx->partials, ctx->ticket, ctx->host_out,
                                    ctx->sm_count, ctx->stream));
     ctx->launches += 1;
     for (int i = 0; i < sc->d; ++i) sc->tables[i]->num_vars -= 1;
     sc->vars_left -= 1;
-    return read_result(ctx, 4, evals);
+    return read_host_result(ctx, 4, evals);
 }
 int tsgpu_sc_bind_eval(tsgpu_sc* sc, const tsgpu_fr* r, tsgpu_fr evals[4]) { return sc_bind_eval_impl(sc, r, nullptr, evals); }
 // same, given the claim of the round being evaluated (g_k(r) of the round just bound): g(0) + g(1) = claim is then an identity

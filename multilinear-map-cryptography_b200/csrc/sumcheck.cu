@@ -16,6 +16,7 @@
 #include "fr_device.cuh"
 #include "sumcheck.cuh"
 #include "tma_stream.cuh"
+#include "../host/field64.hpp"
 
 #ifndef TSG_BE_MINB
 #define TSG_BE_MINB 2
@@ -390,6 +391,21 @@ static inline int tma_grid(size_t tiles, int sm_count, int blocks_per_sm) {
     return (int)(tiles < cap ? tiles : cap);
 }
 
+// fr_ctab::make with native 64-bit host arithmetic (the generic one runs ~19 products of the 32-bit limb code with an emulated carry flag,
+// ~5 us per round): T[k] = canonical(r * 2^(32 k + 64)), the same limbs
+static fr_ctab make_ctab_host(const fr_t& r_elem) {
+    using host::Fr64;
+    static const Fr64 w = Fr64::from_u64(1ull << 32);
+    fr_ctab c;
+    Fr64 cur = Fr64::from_raw(r_elem.l) * w * w;
+    for (int k = 0; k < 8; ++k) {
+        const Fr64 can = cur.from_mont();
+        memcpy(c.t[k], can.l, 32);
+        cur = cur * w;
+    }
+    return c;
+}
+
 // ---------------------------------------------------------------- launch helpers
 static inline int sc_grid(size_t work, int sm_count, int blocks_per_sm) {
     size_t need = (work + SC_THREADS - 1) / SC_THREADS;
@@ -434,7 +450,7 @@ cudaError_t launch_round_eval(int d, const ScTables& tabs, size_t n, fr_t* parti
 }
 
 cudaError_t launch_bind(fr_t* t, size_t n, const fr_t& r_elem, int sm_count, cudaStream_t s) {
-    const fr_ctab r = fr_ctab::make(r_elem);   // T[k] = r 2^(32k+64) mod p: the fold multiplies by this one constant
+    const fr_ctab r = make_ctab_host(r_elem);   // T[k] = r 2^(32k+64) mod p: the fold multiplies by this one constant
     size_t half = n / 2;
     if (half >= g_tma_min_work) {
         size_t sm = tma::Pipeline<2, TMA_THREADS, TMA_STAGES>::SMEM_BYTES;
@@ -449,7 +465,7 @@ cudaError_t launch_bind(fr_t* t, size_t n, const fr_t& r_elem, int sm_count, cud
 }
 
 cudaError_t launch_bind_to(const fr_t* t, fr_t* out, size_t n, const fr_t& r_elem, int sm_count, cudaStream_t s) {
-    const fr_ctab r = fr_ctab::make(r_elem);
+    const fr_ctab r = make_ctab_host(r_elem);
     size_t half = n / 2;
     int grid = sc_grid(half, sm_count, SC_BLOCKS_PER_SM_BIND);
     k_bind_to<<<grid, SC_THREADS, 0, s>>>(t, out, half, r);
@@ -458,7 +474,7 @@ cudaError_t launch_bind_to(const fr_t* t, fr_t* out, size_t n, const fr_t& r_ele
 
 cudaError_t launch_bind_eval(int d, const ScTables& tabs, size_t n, const fr_t& r_elem, const fr_t* claim, fr_t* partials, unsigned int* ticket,
                              fr_t* out4, int sm_count, cudaStream_t s) {
-    const fr_ctab r = fr_ctab::make(r_elem);
+    const fr_ctab r = make_ctab_host(r_elem);
     size_t quarter = n / 4;
     if (claim && d == 2 && quarter < g_tma_min_work) {
         if (quarter >= g_pf_min_work && quarter % 32 == 0) {

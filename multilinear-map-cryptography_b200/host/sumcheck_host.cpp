@@ -2,23 +2,28 @@
 #include "sumcheck_host.hpp"
 #include <cstring>
 #include "../csrc/context.cuh"
+#include "field64.hpp"
 
 namespace tsg {
 namespace host {
 
-void interpolate4(const fr_t e[4], fr_t c[4]) {
+// native 64-bit limbs for the per-round host arithmetic (fr_t on the host runs the device limb code with an emulated carry flag, ~10x slower)
+static inline Fr64 w64(const fr_t& x) { return Fr64::from_raw(x.l); }
+static inline fr_t n32(const Fr64& x) { fr_t r; memcpy(r.l, x.l, 32); return r; }
+
+void interpolate4(const fr_t e32[4], fr_t c[4]) {
     // forward differences on x = 0,1,2,3, then Newton -> monomial:
     //   P = e0 + D1 x + D2 x(x-1)/2 + D3 x(x-1)(x-2)/6
-    // constants once per process: the host runs the device limb code with an emulated carry flag, where a Fermat inverse costs ~0.1 ms
-    static const fr_t inv2 = fr_t::from_u64(2).inverse(), inv3 = fr_t::from_u64(3).inverse(), inv6 = inv2 * inv3;
-    fr_t d1 = e[1] - e[0];
-    fr_t d2 = e[2] - e[1] - e[1] + e[0];
-    fr_t d3 = e[3] - e[2] - e[2] - e[2] + e[1] + e[1] + e[1] - e[0];
-    fr_t h2 = d2 * inv2;
-    c[0] = e[0];
-    c[1] = d1 - h2 + d3 * inv3;
-    c[2] = h2 - d3 * inv2;
-    c[3] = d3 * inv6;
+    static const Fr64 inv2 = Fr64::from_u64(2).inverse(), inv3 = Fr64::from_u64(3).inverse(), inv6 = inv2 * inv3;
+    const Fr64 e[4] = {w64(e32[0]), w64(e32[1]), w64(e32[2]), w64(e32[3])};
+    Fr64 d1 = e[1] - e[0];
+    Fr64 d2 = e[2] - e[1] - e[1] + e[0];
+    Fr64 d3 = e[3] - e[2] - e[2] - e[2] + e[1] + e[1] + e[1] - e[0];
+    Fr64 h2 = d2 * inv2;
+    c[0] = e32[0];
+    c[1] = n32(d1 - h2 + d3 * inv3);
+    c[2] = n32(h2 - d3 * inv2);
+    c[3] = n32(d3 * inv6);
 }
 
 static inline void to_abi(const fr_t& x, tsgpu_fr* o) { memcpy(o->l, x.l, 32); }

@@ -3,6 +3,7 @@
 #include <string>
 #include <vector>
 #include "../../include/tsgpu.h"
+#include "field64.hpp"
 #include "transcript.hpp"
 
 namespace tsg {
@@ -10,9 +11,11 @@ namespace host {
 
 // field_utils::horner_eval (src/utils.rs:217-221)
 inline fr_t horner_eval(const fr_t* coeffs, size_t n, const fr_t& x) {
-    fr_t acc = fr_t::zero();
-    for (size_t i = n; i-- > 0;) acc = acc * x + coeffs[i];
-    return acc;
+    const Fr64 x64 = Fr64::from_raw(x.l);          // native 64-bit limbs (see field64.hpp)
+    Fr64 acc = Fr64::zero();
+    for (size_t i = n; i-- > 0;) acc = acc * x64 + Fr64::from_raw(coeffs[i].l);
+    fr_t r; memcpy(r.l, acc.l, 32);
+    return r;
 }
 
 // The 4 monomial coefficients of the cubic through (0,e0),(1,e1),(2,e2),(3,e3): what

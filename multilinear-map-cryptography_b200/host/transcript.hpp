@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 #include "../csrc/fp.cuh"
+#include "field64.hpp"
 
 namespace tsg {
 namespace host {
@@ -22,6 +23,9 @@ class SipHasher13 {
     SipHasher13() : v0_(0x736f6d6570736575ull), v1_(0x646f72616e646f6dull), v2_(0x6c7967656e657261ull), v3_(0x7465646279746573ull), tail_(0), ntail_(0), len_(0) {}
     void write(const uint8_t* p, size_t n) {
         len_ += n;
+        if (ntail_ == 0) {                       // whole little-endian words straight from the buffer (the transcript is re-hashed at every challenge)
+            while (n >= 8) { uint64_t m; memcpy(&m, p, 8); compress(m); p += 8; n -= 8; }
+        }
         while (n) {
             tail_ |= (uint64_t)(*p) << (8 * ntail_);
             ++p; --n;
@@ -53,16 +57,20 @@ class SipHasher13 {
 
 class ChaCha20Rng {
   public:
-    explicit ChaCha20Rng(const uint8_t seed[32]) : counter_(0), pos_(64) { memcpy(key_, seed, 32); }
+    // rand_chacha buffers four 64-byte blocks per refill; the blocks of the current buffer are generated on demand here (a challenge
+    // reads 8 words), which changes nothing in the word sequence
+    explicit ChaCha20Rng(const uint8_t seed[32]) : counter_(0), pos_(64), have_(0) { memcpy(key_, seed, 32); }
     uint32_t next_u32() {
         if (pos_ >= 64) { refill(); pos_ = 0; }
+        need(pos_);
         return buf_[pos_++];
     }
     uint64_t next_u64() {   // rand_core BlockRng::next_u64 (incl. the straddling case at word 63)
-        if (pos_ < 63) { uint64_t v = ((uint64_t)buf_[pos_ + 1] << 32) | buf_[pos_]; pos_ += 2; return v; }
-        if (pos_ >= 64) { refill(); pos_ = 2; return ((uint64_t)buf_[1] << 32) | buf_[0]; }
+        if (pos_ < 63) { need(pos_ + 1); uint64_t v = ((uint64_t)buf_[pos_ + 1] << 32) | buf_[pos_]; pos_ += 2; return v; }
+        if (pos_ >= 64) { refill(); pos_ = 2; need(1); return ((uint64_t)buf_[1] << 32) | buf_[0]; }
+        need(63);
         uint64_t lo = buf_[63];
-        refill(); pos_ = 1;
+        refill(); pos_ = 1; need(0);
         return ((uint64_t)buf_[0] << 32) | lo;
     }
     void fill_bytes(uint8_t* out, size_t n) {
@@ -97,8 +105,10 @@ class ChaCha20Rng {
         x[a] += x[b]; x[d] = rotl(x[d] ^ x[a], 8);
         x[c] += x[d]; x[b] = rotl(x[b] ^ x[c], 7);
     }
-    void refill() {
-        for (int blk = 0; blk < 4; ++blk) {
+    void refill() { if (started_) counter_ += 4; started_ = 1; have_ = 0; }   // move to the next buffer of four blocks (none generated yet)
+    void need(int word) {                       // make buf_[0 .. word] valid
+        while (have_ <= word) {
+            const int blk = have_ / 16;
             uint32_t in[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u};
             memcpy(in + 4, key_, 32);
             uint64_t c = counter_ + blk;
@@ -109,18 +119,20 @@ class ChaCha20Rng {
                 qr(x, 0, 5, 10, 15); qr(x, 1, 6, 11, 12); qr(x, 2, 7, 8, 13); qr(x, 3, 4, 9, 14);
             }
             for (int i = 0; i < 16; ++i) buf_[16 * blk + i] = x[i] + in[i];
+            have_ += 16;
         }
-        counter_ += 4;
     }
     uint32_t key_[8];
-    uint64_t counter_;
+    uint64_t counter_;      // block counter of the first block of the current buffer
     uint32_t buf_[64];
     int pos_;
+    int have_;              // valid words of the current buffer
+    int started_ = 0;       // 0 until the first buffer exists
 };
 
 // ark-serialize compressed field element: canonical integer, 32 bytes LE
 inline void fr_to_bytes(const fr_t& x, uint8_t out[32]) {
-    fr_t c = x.from_mont();
+    Fr64 c = Fr64::from_raw(x.l).from_mont();     // native 64-bit limbs: the 32-bit limb code runs with an emulated carry flag on the host
     memcpy(out, c.l, 32);
 }
 
