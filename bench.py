@@ -191,6 +191,9 @@ def main():
     torch.cuda.set_stream(stream)
     ctx = ts.Context(local, stream.cuda_stream)
     W = max(args.warmup, 3); K = max(args.steps, 1)
+    for kv in filter(None, os.environ.get("TSGPU_TUNING", "").split(",")):      # A/B switches for experiments, e.g. TSGPU_TUNING=msm_acc_waves=0,msm_two_level=0
+        key, val = kv.split("=")
+        ctx.set_tuning(key, int(val))
 
     def barrier():
         if world > 1:

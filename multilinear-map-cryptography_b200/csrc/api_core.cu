@@ -11,6 +11,7 @@
 #include "sumcheck.cuh"
 #include "interp.cuh"
 #include "lookup.cuh"
+#include "msm.cuh"
 
 using namespace tsg;
 
@@ -172,6 +173,8 @@ int tsgpu_set_tuning(tsgpu_ctx* ctx, const char* key, long value) {
         set_prefetch_min_work(value < 0 || value > 61 ? (size_t)1 << 62 : (size_t)1 << value);
         return TSGPU_OK;
     }
+    if (!strcmp(key, "msm_acc_waves")) { set_msm_acc_waves((int)value); return TSGPU_OK; }
+    if (!strcmp(key, "msm_two_level")) { set_msm_two_level(value != 0); return TSGPU_OK; }
     if (!strcmp(key, "kernel_timing")) { ctx->timing = value != 0; return TSGPU_OK; }
     if (!strcmp(key, "msm_tables")) { ctx->msm_tables = value != 0; return TSGPU_OK; }   // 0: per-window bucket sets on the plain SRS points
     if (!strcmp(key, "eval_basis")) { ctx->eval_basis = value != 0; return TSGPU_OK; }   // 0: Twist/Shout::prove interpolate and commit coefficients
