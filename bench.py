@@ -36,6 +36,7 @@ LOG_CELLS = 16
 LOG_SIZE = 18            # setup_params(18): max_operations = 2^20
 CPU_SAMPLE_LOG = 16      # CPU arms time a 2^16-op sample and scale linearly (optimistic for the CPU: the work is n log^2 n)
 FOLD_LOG = 26            # side measurement: sum-check fold of one 2^26-entry table (BASELINE metric "sumcheck fold GB/s")
+JSON_OUT = sys.stdout
 IMAD_PEAK_TOPS = 18.5    # measured on this pool with tools/ubench.cu (plain IMAD.WIDE issue rate, profiles/r01_ubench.json)
 
 
@@ -162,7 +163,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=JSON_OUT, flush=True)
 
 
 def main():
@@ -174,6 +175,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fold", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON: keep a private handle to it and point fd 1 at stderr for everything else that writes there
+    # (NCCL prints its version line to stdout from inside the library communicator at N > 1, whatever NCCL_DEBUG_FILE says)
+    global JSON_OUT
+    sys.stdout.flush()
+    JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -409,7 +416,7 @@ def main():
             "ops_per_s_all_gpus": world * n / (dev_ms * 1e-3),
             "one_proof_sharded": sharded,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), file=JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
