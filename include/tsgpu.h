@@ -323,6 +323,18 @@ int tsgpu_shout_prove(tsgpu_ctx* ctx, const tsgpu_params* params, const tsgpu_fr
  * after the other); every rank returns the same proof, byte-identical to tsgpu_shout_prove. */
 int tsgpu_shout_prove_sharded(tsgpu_ctx* ctx, const tsgpu_params* params, const tsgpu_fr* entries, size_t num_local_entries, size_t total_entries,
                               const uint64_t* lookup_indices, size_t num_local_lookups, size_t total_lookups, tsgpu_proof** out);
+/* Read/write memory (Twist) tables over (cell x, cycle j), reference index x + 2^log_cells * j - the layout of BASELINE config 4.
+ *   memory_values:   Val(x, j) = content of cell x just before operation j (MemoryTrace semantics, src/twist.rs:48-70; zero-initialised memory)
+ *   one_hot_weighted: out[addresses[j] + 2^log_cells j] = weights[j] for the operations with select[j] == flag (weights: 2^log_cycles entries)
+ *   mul:             elementwise product;   lt_point: out[a] = LT~(a, point), [a < c] in the natural integer order, multilinear in c
+ * An address >= 2^log_cells is TSGPU_E_INVALID_PARAMETERS "Address out of bounds" (src/twist.rs:49-53). */
+int tsgpu_table_memory_values(tsgpu_ctx* ctx, const uint64_t* addresses, const uint8_t* is_write, const tsgpu_fr* values, size_t n, unsigned log_cells,
+                              unsigned log_cycles, tsgpu_table** out);
+int tsgpu_table_one_hot_weighted(tsgpu_ctx* ctx, const tsgpu_table* weights, const uint64_t* addresses, const uint8_t* select, int flag, size_t n,
+                                 unsigned log_cells, tsgpu_table** out);
+int tsgpu_table_mul(tsgpu_ctx* ctx, const tsgpu_table* a, const tsgpu_table* b, tsgpu_table** out);
+int tsgpu_table_lt_point(tsgpu_ctx* ctx, const tsgpu_fr* point, unsigned num_vars, tsgpu_table** out);
+
 /* ---- The lookup-correctness sum-check the reference leaves as a stub (src/shout.rs:157-184: the closure returns zero on every branch
  * and says "In a production implementation, this would involve more complex constraints").  NOT part of the reference's proofs - a
  * separate, explicitly non-parity mode; Shout::prove above stays byte-identical to the reference.
@@ -341,6 +353,26 @@ int tsgpu_shout_read_check_prove(tsgpu_ctx* ctx, const tsgpu_fr* entries, size_t
 int tsgpu_shout_read_check_verify(tsgpu_ctx* ctx, const tsgpu_fr* entries, size_t num_entries, const uint64_t* lookup_indices,
                                   const tsgpu_fr* lookup_values, size_t num_lookups, tsgpu_transcript* transcript,
                                   const tsgpu_fr* round_polys, size_t num_rounds, const tsgpu_fr* final_evaluation, int* valid);
+/* ---- The memory-consistency sum-checks the reference leaves as a stub (src/twist.rs:181-214: the closure returns zero on every branch;
+ * "In a production implementation, this would involve a more complex constraint").  NOT part of the reference's proofs - the second half of the
+ * non-parity mode; Twist::prove above stays byte-identical to the reference.
+ * Statement: operation j < n is Read/Write { address, value } on a zero-initialised memory of memory_size = 2^k cells; every Read must return the
+ * value last written to its address (0 if none).  T = 2^t = the padded number of operations.  Two sum-checks on one transcript:
+ *   1. read-checking over (x, j), k + t rounds:   sum_j eq(r, j) [read_j] value_j  =  sum_{x, j} ( eq(r, j) [read_j] ra(x, j) ) * Val(x, j)
+ *      r = challenge_field_elements("memory_check_point", t); claim appended as "memory_read_claim"; ra(x, j) = [address_j == x];
+ *      Val(x, j) = content of cell x before operation j.  Ends at a point (x*, j*); the prover sends Val~(x*, j*) ("memory_val_claim").
+ *   2. Val-evaluation over j', t rounds:   Val~(x*, j*)  =  sum_j' ( Inc_j' eq(x*, address_j') ) * LT~(j', j*)
+ *      Inc_j' = value written minus the previous content (0 for reads); LT = [j' < j] in the natural order.
+ * Both are the reference's own SumCheck::prove (src/sumcheck.rs:56-110) on those product closures.  A read that returns a wrong value makes the
+ * prover fail with TSGPU_E_SUMCHECK "Round 0 consistency check failed".
+ * Outputs: claims[2] = {read claim, Val~(x*, j*)}; rounds1 (k + t) x 4, final1; rounds2 t x 4, final2.
+ * verify recomputes both claims' closing values from the statement (device gathers / inner products) after SumCheck::verify of each part. */
+int tsgpu_twist_memory_check_prove(tsgpu_ctx* ctx, const uint64_t* addresses, const tsgpu_fr* values, const uint8_t* is_write, size_t num_operations,
+                                   size_t memory_size, tsgpu_transcript* transcript, tsgpu_fr claims[2], tsgpu_fr* rounds1, tsgpu_fr* final1,
+                                   tsgpu_fr* rounds2, tsgpu_fr* final2);
+int tsgpu_twist_memory_check_verify(tsgpu_ctx* ctx, const uint64_t* addresses, const tsgpu_fr* values, const uint8_t* is_write, size_t num_operations,
+                                    size_t memory_size, tsgpu_transcript* transcript, const tsgpu_fr claims[2], const tsgpu_fr* rounds1, size_t num_rounds1,
+                                    const tsgpu_fr* final1, const tsgpu_fr* rounds2, size_t num_rounds2, const tsgpu_fr* final2, int* valid);
 /* Twist::verify / Shout::verify (src/twist.rs:255-304, src/shout.rs:225-274): transcript replay, SumCheck::verify and
  * the two KZGCommitment::verify pairing checks (src/commitments.rs:201-228) - all on the CPU, as in the reference. */
 int tsgpu_twist_verify(tsgpu_ctx* ctx, const tsgpu_params* params, const tsgpu_proof* proof, int* valid);

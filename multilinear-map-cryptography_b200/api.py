@@ -557,3 +557,56 @@ class ShoutReadCheck:
         self.ctx.check(lib().tsgpu_shout_read_check_verify(self.ctx._h, _p(entries), C.c_size_t(entries.shape[0]), _p(idx), _p(vals), C.c_size_t(idx.shape[0]),
                                                            transcript._h, _p(rp), C.c_size_t(rp.shape[0]), _p(fe), C.byref(ok)))
         return bool(ok.value)
+
+
+class TwistMemoryCheck:
+    """The memory-consistency sum-checks the reference leaves as a stub (src/twist.rs:181-214): read-checking over (cell, cycle) and the
+    Val-evaluation sum-check, on one transcript.  NOT part of the reference's proofs (non-parity extension): Twist.prove stays
+    byte-identical to the reference; this proves that every Read of a MemoryTrace returns the value last written to its address."""
+
+    class Proof:
+        def __init__(self, claims, part1: SumCheckProof, part2: SumCheckProof):
+            self.claims, self.read_check, self.val_evaluation = claims, part1, part2
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+
+    def prove(self, trace: "MemoryTrace", transcript: Transcript) -> "TwistMemoryCheck.Proof":
+        addr, vals, isw = trace.arrays()
+        return self.prove_arrays(addr, vals, isw, trace.memory_size, transcript)
+
+    @staticmethod
+    def _shape(n: int, memory_size: int):
+        k = max(memory_size - 1, 0).bit_length()
+        t = max(n - 1, 0).bit_length()
+        return k, t
+
+    def prove_arrays(self, addresses, values, is_write, memory_size: int, transcript: Transcript) -> "TwistMemoryCheck.Proof":
+        addr = np.ascontiguousarray(addresses, dtype=np.uint64).reshape(-1)
+        vals = _fr(values) if len(values) else np.empty((0, 4), dtype=np.uint64)
+        isw = np.ascontiguousarray(is_write, dtype=np.uint8).reshape(-1)
+        k, t = self._shape(addr.shape[0], memory_size)
+        claims = np.zeros((2, 4), dtype=np.uint64)
+        r1 = np.zeros((max(k + t, 1), 4, 4), dtype=np.uint64); f1 = np.zeros(4, dtype=np.uint64)
+        r2 = np.zeros((max(t, 1), 4, 4), dtype=np.uint64); f2 = np.zeros(4, dtype=np.uint64)
+        self.ctx.check(lib().tsgpu_twist_memory_check_prove(self.ctx._h, _p(addr), _p(vals), _p(isw), C.c_size_t(addr.shape[0]), C.c_size_t(memory_size),
+                                                            transcript._h, _p(claims), _p(r1), _p(f1), _p(r2), _p(f2)))
+        return TwistMemoryCheck.Proof(claims, SumCheckProof(r1[:k + t], f1), SumCheckProof(r2[:t], f2))
+
+    def verify(self, trace: "MemoryTrace", proof: "TwistMemoryCheck.Proof", transcript: Transcript) -> bool:
+        addr, vals, isw = trace.arrays()
+        return self.verify_arrays(addr, vals, isw, trace.memory_size, proof, transcript)
+
+    def verify_arrays(self, addresses, values, is_write, memory_size: int, proof: "TwistMemoryCheck.Proof", transcript: Transcript) -> bool:
+        addr = np.ascontiguousarray(addresses, dtype=np.uint64).reshape(-1)
+        vals = _fr(values) if len(values) else np.empty((0, 4), dtype=np.uint64)
+        isw = np.ascontiguousarray(is_write, dtype=np.uint8).reshape(-1)
+        claims = np.ascontiguousarray(proof.claims, dtype=np.uint64).reshape(2, 4)
+        r1 = np.ascontiguousarray(proof.read_check.round_polynomials, dtype=np.uint64).reshape(-1, 4, 4)
+        r2 = np.ascontiguousarray(proof.val_evaluation.round_polynomials, dtype=np.uint64).reshape(-1, 4, 4)
+        f1 = _fr(proof.read_check.final_evaluation, 1); f2 = _fr(proof.val_evaluation.final_evaluation, 1)
+        ok = C.c_int(0)
+        self.ctx.check(lib().tsgpu_twist_memory_check_verify(self.ctx._h, _p(addr), _p(vals), _p(isw), C.c_size_t(addr.shape[0]), C.c_size_t(memory_size),
+                                                             transcript._h, _p(claims), _p(r1), C.c_size_t(r1.shape[0]), _p(f1),
+                                                             _p(r2), C.c_size_t(r2.shape[0]), _p(f2), C.byref(ok)))
+        return bool(ok.value)

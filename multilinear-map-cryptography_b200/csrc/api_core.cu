@@ -427,6 +427,81 @@ int tsgpu_table_inner_product(tsgpu_ctx* ctx, const tsgpu_table* a, const tsgpu_
     return read_result(ctx, 1, out);
 }
 
+// ---- read/write memory (Twist) tables over (cell x, cycle j), reference index x + 2^log_cells * j (csrc/lookup.cu)
+// Val(x, j): content of cell x just before operation j of the trace (zero-initialised memory, MemoryTrace semantics, src/twist.rs:48-70)
+int tsgpu_table_memory_values(tsgpu_ctx* ctx, const uint64_t* addresses, const uint8_t* is_write, const tsgpu_fr* values, size_t n, unsigned log_cells,
+                              unsigned log_cycles, tsgpu_table** out) {
+    if (!ctx || !out || ((!addresses || !is_write || !values) && n)) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    if (log_cells + log_cycles > 30 || n > ((size_t)1 << log_cycles)) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "memory table too large");
+    for (size_t j = 0; j < n; ++j) if (addresses[j] >> log_cells) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "Address out of bounds");   // twist.rs:49-53
+    tsgpu_table* t = nullptr;
+    int rc = table_alloc(ctx, log_cells + log_cycles, &t);
+    if (rc) return rc;
+    TempBuf da, dw, dv;
+    TSG_CUDA(ctx, da.alloc(n * 8, ctx->stream)); TSG_CUDA(ctx, dw.alloc(n, ctx->stream)); TSG_CUDA(ctx, dv.alloc(n * sizeof(fr_t), ctx->stream));
+    if (n) {
+        TSG_CUDA(ctx, cudaMemcpyAsync(da.p, addresses, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        TSG_CUDA(ctx, cudaMemcpyAsync(dw.p, is_write, n, cudaMemcpyHostToDevice, ctx->stream));
+        TSG_CUDA(ctx, cudaMemcpyAsync(dv.p, values, n * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    TSG_CUDA(ctx, launch_val_table(da.as<unsigned long long>(), dw.as<unsigned char>(), dv.as<fr_t>(), n, log_cells, log_cycles, t->d, ctx->sm_count, ctx->stream));
+    ctx->launches += 1;
+    TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = t;
+    return TSGPU_OK;
+}
+// out[addresses[j] + 2^log_cells * j] = weights[j] for the j < n with select[j] == flag, zero elsewhere: the address one-hot matrix with weighted rows
+int tsgpu_table_one_hot_weighted(tsgpu_ctx* ctx, const tsgpu_table* weights, const uint64_t* addresses, const uint8_t* select, int flag, size_t n,
+                                 unsigned log_cells, tsgpu_table** out) {
+    if (!ctx || !weights || !out || ((!addresses || !select) && n)) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    const unsigned t = weights->num_vars;
+    if (log_cells + t > 30 || n > ((size_t)1 << t)) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "memory table too large");
+    for (size_t j = 0; j < n; ++j) if (addresses[j] >> log_cells) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "Address out of bounds");
+    tsgpu_table* o = nullptr;
+    int rc = table_alloc(ctx, log_cells + t, &o);
+    if (rc) return rc;
+    TSG_CUDA(ctx, cudaMemsetAsync(o->d, 0, ((size_t)1 << (log_cells + t)) * sizeof(fr_t), ctx->stream));
+    TempBuf da, ds;
+    TSG_CUDA(ctx, da.alloc(n * 8, ctx->stream)); TSG_CUDA(ctx, ds.alloc(n, ctx->stream));
+    if (n) {
+        TSG_CUDA(ctx, cudaMemcpyAsync(da.p, addresses, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        TSG_CUDA(ctx, cudaMemcpyAsync(ds.p, select, n, cudaMemcpyHostToDevice, ctx->stream));
+        TSG_CUDA(ctx, launch_one_hot_weighted(weights->d, da.as<unsigned long long>(), ds.as<unsigned char>(), (unsigned char)(flag != 0), n, log_cells, t, o->d,
+                                              ctx->sm_count, ctx->stream));
+        ctx->launches += 1;
+    }
+    TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = o;
+    return TSGPU_OK;
+}
+// elementwise product of two tables of equal size
+int tsgpu_table_mul(tsgpu_ctx* ctx, const tsgpu_table* a, const tsgpu_table* b, tsgpu_table** out) {
+    if (!ctx || !a || !b || !out) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    if (a->num_vars != b->num_vars) return fail(ctx, TSGPU_E_POLYNOMIAL, "Number of variables must match");
+    tsgpu_table* t = nullptr;
+    int rc = table_alloc(ctx, a->num_vars, &t);
+    if (rc) return rc;
+    TSG_CUDA(ctx, launch_table_mul(a->d, b->d, t->d, (size_t)1 << a->num_vars, ctx->sm_count, ctx->stream));
+    ctx->launches += 1;
+    *out = t;
+    return TSGPU_OK;
+}
+// out[a] = LT~(a, point), a in {0,1}^num_vars: [a < c] in the natural integer order (bit num_vars - 1 most significant), multilinear in c, at c = point
+int tsgpu_table_lt_point(tsgpu_ctx* ctx, const tsgpu_fr* point, unsigned num_vars, tsgpu_table** out) {
+    if (!ctx || !out || (!point && num_vars)) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    tsgpu_table* t = nullptr;
+    int rc = table_alloc(ctx, num_vars, &t);
+    if (rc) return rc;
+    TempBuf pd;
+    TSG_CUDA(ctx, pd.alloc((num_vars + 1) * sizeof(fr_t), ctx->stream));
+    if (num_vars) TSG_CUDA(ctx, cudaMemcpyAsync(pd.p, point, num_vars * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+    TSG_CUDA(ctx, launch_lt_point_table(pd.as<fr_t>(), num_vars, t->d, ctx->sm_count, ctx->stream));
+    ctx->launches += 1;
+    TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = t;
+    return TSGPU_OK;
+}
+
 // ------------------------------------------------------------------------------- evaluate / partial
 // results that a kernel wrote directly into the pinned mirror: wait for the stream, copy out
 static int read_host_result(tsgpu_ctx* ctx, int count, tsgpu_fr* out) {

@@ -81,3 +81,80 @@ cudaError_t launch_table_gather(const fr_t* src, unsigned k, const unsigned long
 }
 
 }  // namespace tsg
+
+// ================================================================ read/write memory (Twist) tables
+// Dense tables over (cell x, cycle j), reference index i = x + K j (K = 2^k cells in the low variables, T = 2^t cycles in the high
+// ones: the layout of BASELINE config 4), stored at the bit-reversed position (bitrev_k(x) << t) | bitrev_t(j).
+namespace tsg {
+
+// Val(x, j) = content of cell x just before operation j (zero-initialised memory; for j >= n: the final content).  One thread per cell
+// walks the operation stream (every thread reads the same addresses: broadcast loads) and writes its own row of T entries.
+__global__ void __launch_bounds__(128) k_val_table(const unsigned long long* addr, const unsigned char* is_write, const fr_t* values, size_t n,
+                                                   unsigned k, unsigned t, fr_t* out) {
+    const size_t K = (size_t)1 << k, T = (size_t)1 << t;
+    for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < K; x += (size_t)gridDim.x * blockDim.x) {
+        fr_t cur = fr_t::zero();
+        fr_t* row = out + (bitrev_u64(x, k) << t);
+        for (size_t j = 0; j < T; ++j) {
+            st256(row + bitrev_u64(j, t), cur);
+            if (j < n && is_write[j] && addr[j] == x) cur = ld256_nc(values + j);
+        }
+    }
+}
+
+// out[(x = addr[j]) + K j] = W[j] for every j < n with keep[j] == flag (table pre-zeroed): the one-hot matrix with weighted rows
+__global__ void __launch_bounds__(256) k_one_hot_weighted(const fr_t* W, const unsigned long long* addr, const unsigned char* sel, unsigned char flag, size_t n,
+                                                          unsigned k, unsigned t, fr_t* out) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        if (sel[j] != flag) continue;
+        const unsigned long long jr = bitrev_u64(j, t);
+        st256(out + ((bitrev_u64(addr[j], k) << t) | jr), ld256_nc(W + jr));
+    }
+}
+
+// out = a * b elementwise (full Montgomery products; layout-agnostic)
+__global__ void __launch_bounds__(256) k_table_mul(const fr_t* a, const fr_t* b, fr_t* out, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) st256(out + i, ld256_stream(a + i) * ld256_stream(b + i));
+}
+
+// V[a] = LT~(a, b) for every boolean a in {0,1}^t and a field point b (device array of t elements): the multilinear extension in the
+// second argument of [a < c] (integers, bit t - 1 most significant), evaluated at c = b:
+//     LT~(a, b) = sum_i (1 - a_i) b_i prod_{l > i} eq(a_l, b_l),   eq(a_l, b_l) = a_l ? b_l : 1 - b_l
+__global__ void __launch_bounds__(256) k_lt_point_table(const fr_t* b, unsigned t, fr_t* out) {
+    const size_t T = (size_t)1 << t;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t pos = (size_t)blockIdx.x * blockDim.x + threadIdx.x; pos < T; pos += stride) {
+        const unsigned long long a = bitrev_u64(pos, t);
+        fr_t prefix = fr_t::one(), acc = fr_t::zero();
+        for (int i = (int)t - 1; i >= 0; --i) {
+            const fr_t bi = b[i];
+            if ((a >> i) & 1) prefix = prefix * bi;
+            else { acc = acc + prefix * bi; prefix = prefix * (fr_t::one() - bi); }
+        }
+        st256(out + pos, acc);
+    }
+}
+
+cudaError_t launch_val_table(const unsigned long long* addr, const unsigned char* is_write, const fr_t* values, size_t n, unsigned k, unsigned t, fr_t* out,
+                             int sm_count, cudaStream_t s) {
+    k_val_table<<<grid_for((size_t)1 << k, 128, (size_t)sm_count * 8), 128, 0, s>>>(addr, is_write, values, n, k, t, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_one_hot_weighted(const fr_t* W, const unsigned long long* addr, const unsigned char* sel, unsigned char flag, size_t n, unsigned k, unsigned t,
+                                    fr_t* out, int sm_count, cudaStream_t s) {
+    if (!n) return cudaSuccess;
+    k_one_hot_weighted<<<grid_for(n, 256, (size_t)sm_count * 8), 256, 0, s>>>(W, addr, sel, flag, n, k, t, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_table_mul(const fr_t* a, const fr_t* b, fr_t* out, size_t n, int sm_count, cudaStream_t s) {
+    k_table_mul<<<grid_for(n, 256, (size_t)sm_count * 8), 256, 0, s>>>(a, b, out, n);
+    return cudaGetLastError();
+}
+cudaError_t launch_lt_point_table(const fr_t* b_dev, unsigned t, fr_t* out, int sm_count, cudaStream_t s) {
+    k_lt_point_table<<<grid_for((size_t)1 << t, 256, (size_t)sm_count * 8), 256, 0, s>>>(b_dev, t, out);
+    return cudaGetLastError();
+}
+
+}  // namespace tsg

@@ -1,0 +1,207 @@
+"""GPU: the memory-consistency sum-checks of Twist (read-checking over (cell, cycle) + Val-evaluation) that the reference leaves as a stub
+(src/twist.rs:181-214), and their table builders.  Both parts are the reference's own SumCheck::prove (src/sumcheck.rs:56-110) applied to
+product closures: the CPU oracle runs exactly that on the same transcript (closure form at tiny sizes, table form above) over tables built
+here in plain Python, and the device result must match bit for bit.  Non-parity mode: Twist::prove itself is unchanged."""
+import numpy as np
+import pytest
+
+from conftest import seed_bytes
+
+pytestmark = pytest.mark.gpu
+
+
+def _trace(oracle, tsgpu, K, n, seed, wide=False):
+    """random trace on K cells: (addresses, values Fr, is_write) with reads returning the simulated content (MemoryTrace semantics)"""
+    rng = np.random.default_rng(seed)
+    addr = rng.integers(0, K, size=n).astype(np.uint64)
+    isw = rng.integers(0, 2, size=n).astype(np.uint8)
+    fresh = oracle.chacha_fr_rand(seed_bytes(seed), max(n, 1)).reshape(-1, 4) if wide else tsgpu.fe_vec(rng.integers(1, 1 << 63, size=max(n, 1), dtype=np.uint64))
+    vals = np.zeros((n, 4), dtype=np.uint64)
+    mem = {}
+    for j in range(n):
+        a = int(addr[j])
+        if isw[j]:
+            mem[a] = fresh[j]
+        vals[j] = mem.get(a, np.zeros(4, dtype=np.uint64))
+    return addr, vals, isw
+
+
+def _eq_ints(oracle, pt):
+    return oracle.fr_to_ints(oracle.eq_table(pt.reshape(-1, 4))) if pt.shape[0] else [1]
+
+
+def _lt_point_ints(oracle, b_ints, t, p):
+    out = []
+    for a in range(1 << t):
+        prefix, acc = 1, 0
+        for i in range(t - 1, -1, -1):
+            bi = b_ints[i]
+            if (a >> i) & 1:
+                prefix = prefix * bi % p
+            else:
+                acc = (acc + prefix * bi) % p
+                prefix = prefix * (1 - bi) % p
+        out.append(acc)
+    return out
+
+
+def _oracle_memory_check(oracle, addr, vals, isw, K, mode):
+    """host/memory_check.cpp restated with oracle primitives and Python integers"""
+    p = oracle.R_MOD
+    n = addr.shape[0]
+    T = 1 << max(n - 1, 0).bit_length()
+    k, t = K.bit_length() - 1, T.bit_length() - 1
+    vi = oracle.fr_to_ints(vals) if n else []
+    tr = oracle.Transcript()
+    r = tr.challenge_field_elements(b"memory_check_point", t)
+    eq = _eq_ints(oracle, r)
+    claim1 = sum(eq[j] * vi[j] for j in range(n) if not isw[j]) % p
+    claim1_fr = oracle.fr_from_ints([claim1])[0]
+    tr.append_field_element(b"memory_read_claim", claim1_fr)
+    # tables over index x + K j
+    RA = [0] * (K * T); VAL = [0] * (K * T)
+    mem = [0] * K; inc = [0] * T
+    for j in range(T):
+        for x in range(K):
+            VAL[x + K * j] = mem[x]
+        if j < n:
+            a = int(addr[j])
+            if isw[j]:
+                inc[j] = (vi[j] - mem[a]) % p
+                mem[a] = vi[j]
+            else:
+                RA[a + K * j] = eq[j]
+    ref1 = oracle.sumcheck_prove_product([oracle.fr_from_ints(RA), oracle.fr_from_ints(VAL)], claim1_fr, transcript=tr, mode=mode)
+    ch = ref1["challenges"].reshape(-1, 4)
+    val_claim = oracle.mle_evaluate(oracle.fr_from_ints(VAL), ch, fold=(mode == "tables")).reshape(4)   # Val~(x*, j*): MultilinearExtension::evaluate
+    tr.append_field_element(b"memory_val_claim", val_claim)
+    x_star, j_star = ch[:k], ch[k:]
+    eqx = _eq_ints(oracle, x_star)
+    U = [inc[j] * eqx[int(addr[j])] % p if j < n else 0 for j in range(T)]
+    V = _lt_point_ints(oracle, oracle.fr_to_ints(j_star) if t else [], t, p)
+    ref2 = oracle.sumcheck_prove_product([oracle.fr_from_ints(U), oracle.fr_from_ints(V)], val_claim, transcript=tr, mode=mode)
+    return claim1_fr, val_claim, ref1, ref2
+
+
+@pytest.mark.parametrize("K,n,mode", [(1, 1, "closure"), (2, 2, "closure"), (4, 3, "closure"), (2, 8, "closure"), (8, 6, "closure"),
+                                      (4, 16, "tables"), (16, 50, "tables"), (64, 64, "tables"), (8, 500, "tables"), (256, 30, "tables")])
+def test_memory_check_matches_reference_sumcheck_on_the_real_closures(ctx, tsgpu, oracle, K, n, mode):
+    addr, vals, isw = _trace(oracle, tsgpu, K, n, seed=K * 1000 + n, wide=(n % 2 == 0))
+    mc = tsgpu.TwistMemoryCheck(ctx)
+    proof = mc.prove_arrays(addr, vals, isw, K, tsgpu.Transcript())
+    c1, c2, ref1, ref2 = _oracle_memory_check(oracle, addr, vals, isw, K, mode)
+    assert (proof.claims[0] == c1).all() and (proof.claims[1] == c2).all()
+    assert (proof.read_check.round_polynomials == ref1["round_polynomials"]).all() and (proof.read_check.final_evaluation == ref1["final_evaluation"]).all()
+    assert (proof.val_evaluation.round_polynomials == ref2["round_polynomials"]).all() and (proof.val_evaluation.final_evaluation == ref2["final_evaluation"]).all()
+    assert mc.verify_arrays(addr, vals, isw, K, proof, tsgpu.Transcript())
+
+
+def test_memory_check_reference_demo_trace(ctx, tsgpu, oracle):
+    """examples/demo.rs:33-46: 8 cells, W(0,42) W(1,100) R(0) R(1) W(0,43) R(0); README: 256 cells, W(0,42) W(1,100) R(0)"""
+    for cells, ops in ((8, [("W", 0, 42), ("W", 1, 100), ("R", 0, 0), ("R", 1, 0), ("W", 0, 43), ("R", 0, 0)]), (256, [("W", 0, 42), ("W", 1, 100), ("R", 0, 0)])):
+        trace = tsgpu.MemoryTrace.new(cells)
+        for kind, a, v in ops:
+            trace.write(a, tsgpu.fe(v)) if kind == "W" else trace.read(a)
+        mc = tsgpu.TwistMemoryCheck(ctx)
+        proof = mc.prove(trace, tsgpu.Transcript())
+        assert proof.read_check.round_polynomials.shape[0] == (cells.bit_length() - 1) + (len(ops) - 1).bit_length()
+        assert proof.read_check.round_polynomials.any()               # a real constraint: not the all-zero cubics of the stub
+        assert mc.verify(trace, proof, tsgpu.Transcript())
+
+
+def test_inconsistent_read_is_rejected(ctx, tsgpu, oracle):
+    K, n = 16, 40
+    addr, vals, isw = _trace(oracle, tsgpu, K, n, seed=77)
+    mc = tsgpu.TwistMemoryCheck(ctx)
+    j = int(np.flatnonzero(isw == 0)[3])
+    bad = vals.copy(); bad[j] = tsgpu.fe(123456789)                                   # this read returns something that was never written there
+    with pytest.raises(tsgpu.TwistAndShoutError) as e:                                 # the prover's own check (sumcheck.rs:77-84)
+        mc.prove_arrays(addr, bad, isw, K, tsgpu.Transcript())
+    assert e.value.variant == "SumCheck" and e.value.message == "Round 0 consistency check failed"
+    proof = mc.prove_arrays(addr, vals, isw, K, tsgpu.Transcript())
+    assert mc.verify_arrays(addr, vals, isw, K, proof, tsgpu.Transcript())
+    assert not mc.verify_arrays(addr, bad, isw, K, proof, tsgpu.Transcript())         # the honest proof does not fit the false statement
+    addr2 = addr.copy(); addr2[j] = (addr2[j] + 1) % K
+    assert not mc.verify_arrays(addr2, vals, isw, K, proof, tsgpu.Transcript())
+    for part in ("read_check", "val_evaluation"):                                      # tampering with either part
+        t = tsgpu.TwistMemoryCheck.Proof(proof.claims.copy(), tsgpu.SumCheckProof(proof.read_check.round_polynomials.copy(), proof.read_check.final_evaluation.copy()),
+                                         tsgpu.SumCheckProof(proof.val_evaluation.round_polynomials.copy(), proof.val_evaluation.final_evaluation.copy()))
+        getattr(t, part).final_evaluation[0] ^= 1
+        assert not mc.verify_arrays(addr, vals, isw, K, t, tsgpu.Transcript())
+    t = tsgpu.TwistMemoryCheck.Proof(proof.claims.copy(), proof.read_check, proof.val_evaluation)
+    t.claims[1][0] ^= 1                                                                # a wrong Val~(x*, j*)
+    assert not mc.verify_arrays(addr, vals, isw, K, t, tsgpu.Transcript())
+    with pytest.raises(tsgpu.TwistAndShoutError) as e:                                 # twist.rs:49-53
+        mc.prove_arrays(np.array([K], dtype=np.uint64), vals[:1], isw[:1], K, tsgpu.Transcript())
+    assert e.value.message == "Address out of bounds"
+    with pytest.raises(tsgpu.TwistAndShoutError) as e:                                 # twist.rs:38
+        mc.prove_arrays(addr, vals, isw, 12, tsgpu.Transcript())
+    assert e.value.message == "Memory size must be power of 2"
+
+
+@pytest.mark.parametrize("k,t", [(0, 0), (3, 2), (2, 6), (6, 7)])
+def test_memory_table_builders(ctx, tsgpu, oracle, k, t):
+    """Val(x, j), the weighted one-hot matrix, the elementwise product and LT~(., b) against plain Python"""
+    import ctypes as C
+    import importlib
+    bd = importlib.import_module(tsgpu.__name__ + ".binding")
+    p = oracle.R_MOD
+    K, T = 1 << k, 1 << t
+    n = T - T // 4
+    addr, vals, isw = _trace(oracle, tsgpu, K, n, seed=5 * k + t, wide=True)
+    vi = oracle.fr_to_ints(vals) if n else []
+    h = C.c_void_p()
+    ctx.check(tsgpu.lib().tsgpu_table_memory_values(ctx._h, bd._p(addr), bd._p(isw), bd._p(vals), C.c_size_t(n), C.c_uint(k), C.c_uint(t), C.byref(h)))
+    got = oracle.fr_to_ints(bd.Table(ctx, h).download())
+    mem = [0] * K
+    for j in range(T):
+        assert [got[x + K * j] for x in range(K)] == mem, f"Val(., {j})"
+        if j < n and isw[j]:
+            mem[int(addr[j])] = vi[j]
+    w = oracle.chacha_fr_rand(seed_bytes(31 + t), T).reshape(T, 4)
+    W = ctx.table_upload(w, t)
+    wi = oracle.fr_to_ints(w)
+    for flag in (0, 1):
+        h = C.c_void_p()
+        ctx.check(tsgpu.lib().tsgpu_table_one_hot_weighted(ctx._h, W._h, bd._p(addr), bd._p(isw), C.c_int(flag), C.c_size_t(n), C.c_uint(k), C.byref(h)))
+        got = oracle.fr_to_ints(bd.Table(ctx, h).download())
+        want = [0] * (K * T)
+        for j in range(n):
+            if isw[j] == flag:
+                want[int(addr[j]) + K * j] = wi[j]
+        assert got == want
+    h = C.c_void_p()
+    ctx.check(tsgpu.lib().tsgpu_table_mul(ctx._h, W._h, W._h, C.byref(h)))
+    assert oracle.fr_to_ints(bd.Table(ctx, h).download()) == [x * x % p for x in wi]
+    b = oracle.chacha_fr_rand(seed_bytes(41 + t), max(t, 1)).reshape(-1, 4)[:t]
+    h = C.c_void_p()
+    ctx.check(tsgpu.lib().tsgpu_table_lt_point(ctx._h, bd._p(np.ascontiguousarray(b)) if t else None, C.c_uint(t), C.byref(h)))
+    lt = bd.Table(ctx, h)
+    assert oracle.fr_to_ints(lt.download()) == _lt_point_ints(oracle, oracle.fr_to_ints(b) if t else [], t, p)
+    # at a boolean point c the table is the indicator [a < c]
+    if t:
+        c = 5 % T
+        bits = oracle.fr_from_ints([(c >> i) & 1 for i in range(t)])
+        h = C.c_void_p()
+        ctx.check(tsgpu.lib().tsgpu_table_lt_point(ctx._h, bd._p(bits), C.c_uint(t), C.byref(h)))
+        assert oracle.fr_to_ints(bd.Table(ctx, h).download()) == [1 if a < c else 0 for a in range(T)]
+
+
+def test_memory_check_config4_shape(ctx, tsgpu, oracle):
+    """2^8 cells x 2^14 cycles = 2^22-entry tables (BASELINE config 4 scaled down 16x): the reference generator pattern of src/benchmarks.rs:88-99
+    proves and verifies; 22 + 14 rounds"""
+    K, n = 1 << 8, 1 << 14
+    i = np.arange(n, dtype=np.uint64)
+    isw = (i % 3 == 0).astype(np.uint8)
+    addr = np.where(isw == 1, i % K, (i // 2) % K).astype(np.uint64)
+    vals_u = np.zeros(n, dtype=np.uint64); mem = {}
+    for j in range(n):
+        a = int(addr[j])
+        if isw[j]:
+            mem[a] = 42 * j
+        vals_u[j] = mem.get(a, 0)
+    vals = tsgpu.fe_vec(vals_u)
+    mc = tsgpu.TwistMemoryCheck(ctx)
+    proof = mc.prove_arrays(addr, vals, isw, K, tsgpu.Transcript())
+    assert proof.read_check.round_polynomials.shape == (22, 4, 4) and proof.val_evaluation.round_polynomials.shape == (14, 4, 4)
+    assert mc.verify_arrays(addr, vals, isw, K, proof, tsgpu.Transcript())
