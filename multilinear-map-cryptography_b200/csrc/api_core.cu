@@ -437,15 +437,34 @@ int tsgpu_table_memory_values(tsgpu_ctx* ctx, const uint64_t* addresses, const u
     tsgpu_table* t = nullptr;
     int rc = table_alloc(ctx, log_cells + log_cycles, &t);
     if (rc) return rc;
-    TempBuf da, dw, dv;
-    TSG_CUDA(ctx, da.alloc(n * 8, ctx->stream)); TSG_CUDA(ctx, dw.alloc(n, ctx->stream)); TSG_CUDA(ctx, dv.alloc(n * sizeof(fr_t), ctx->stream));
-    if (n) {
-        TSG_CUDA(ctx, cudaMemcpyAsync(da.p, addresses, n * 8, cudaMemcpyHostToDevice, ctx->stream));
-        TSG_CUDA(ctx, cudaMemcpyAsync(dw.p, is_write, n, cudaMemcpyHostToDevice, ctx->stream));
-        TSG_CUDA(ctx, cudaMemcpyAsync(dv.p, values, n * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+    // the writes, each with the next write to the same address (or T): one backward pass over the trace
+    const uint64_t T = (uint64_t)1 << log_cycles;
+    std::vector<uint64_t> wa, wj, wnext; std::vector<tsgpu_fr> wv;
+    {
+        std::vector<uint64_t> next_of_cell((size_t)1 << log_cells, T);
+        size_t nw = 0;
+        for (size_t j = 0; j < n; ++j) nw += is_write[j] ? 1 : 0;
+        wa.resize(nw); wj.resize(nw); wnext.resize(nw); wv.resize(nw);
+        size_t w = nw;
+        for (size_t j = n; j-- > 0;) if (is_write[j]) {
+            --w; wa[w] = addresses[j]; wj[w] = j; wnext[w] = next_of_cell[addresses[j]]; wv[w] = values[j];
+            next_of_cell[addresses[j]] = j + 1;    // the run of the previous write to this cell ends where this write takes effect (cycle j + 1)
+        }
     }
-    TSG_CUDA(ctx, launch_val_table(da.as<unsigned long long>(), dw.as<unsigned char>(), dv.as<fr_t>(), n, log_cells, log_cycles, t->d, ctx->sm_count, ctx->stream));
-    ctx->launches += 1;
+    const size_t nw = wa.size();
+    TSG_CUDA(ctx, cudaMemsetAsync(t->d, 0, ((size_t)1 << (log_cells + log_cycles)) * sizeof(fr_t), ctx->stream));
+    TempBuf da, dj, dn, dv;
+    TSG_CUDA(ctx, da.alloc(nw * 8, ctx->stream)); TSG_CUDA(ctx, dj.alloc(nw * 8, ctx->stream)); TSG_CUDA(ctx, dn.alloc(nw * 8, ctx->stream));
+    TSG_CUDA(ctx, dv.alloc(nw * sizeof(fr_t), ctx->stream));
+    if (nw) {
+        TSG_CUDA(ctx, cudaMemcpyAsync(da.p, wa.data(), nw * 8, cudaMemcpyHostToDevice, ctx->stream));
+        TSG_CUDA(ctx, cudaMemcpyAsync(dj.p, wj.data(), nw * 8, cudaMemcpyHostToDevice, ctx->stream));
+        TSG_CUDA(ctx, cudaMemcpyAsync(dn.p, wnext.data(), nw * 8, cudaMemcpyHostToDevice, ctx->stream));
+        TSG_CUDA(ctx, cudaMemcpyAsync(dv.p, wv.data(), nw * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+        TSG_CUDA(ctx, launch_val_fill(da.as<unsigned long long>(), dj.as<unsigned long long>(), dn.as<unsigned long long>(), dv.as<fr_t>(), nw, log_cells, log_cycles,
+                                      t->d, ctx->sm_count, ctx->stream));
+        ctx->launches += 1;
+    }
     TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *out = t;
     return TSGPU_OK;

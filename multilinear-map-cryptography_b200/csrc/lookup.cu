@@ -87,18 +87,18 @@ cudaError_t launch_table_gather(const fr_t* src, unsigned k, const unsigned long
 // ones: the layout of BASELINE config 4), stored at the bit-reversed position (bitrev_k(x) << t) | bitrev_t(j).
 namespace tsg {
 
-// Val(x, j) = content of cell x just before operation j (zero-initialised memory; for j >= n: the final content).  One thread per cell
-// walks the operation stream (every thread reads the same addresses: broadcast loads) and writes its own row of T entries.
-__global__ void __launch_bounds__(128) k_val_table(const unsigned long long* addr, const unsigned char* is_write, const fr_t* values, size_t n,
-                                                   unsigned k, unsigned t, fr_t* out) {
-    const size_t K = (size_t)1 << k, T = (size_t)1 << t;
-    for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < K; x += (size_t)gridDim.x * blockDim.x) {
-        fr_t cur = fr_t::zero();
-        fr_t* row = out + (bitrev_u64(x, k) << t);
-        for (size_t j = 0; j < T; ++j) {
-            st256(row + bitrev_u64(j, t), cur);
-            if (j < n && is_write[j] && addr[j] == x) cur = ld256_nc(values + j);
-        }
+// Val(x, j) = content of cell x just before operation j (zero-initialised memory; for j >= n: the final content).  A cell's row changes only
+// at the writes to it: write number w (operation wj[w], address wa[w], value wv[w]) holds for the cycles wj[w] + 1 .. wnext[w] - 1, where
+// wnext[w] is the next write to the same address (or T).  One block per write fills that run of the pre-zeroed table; the runs are disjoint
+// and cover everything that is not zero.  (The host derives wnext in one pass over the trace.)
+__global__ void __launch_bounds__(256) k_val_fill(const unsigned long long* wa, const unsigned long long* wj, const unsigned long long* wnext, const fr_t* wv,
+                                                  size_t nwrites, unsigned k, unsigned t, fr_t* out) {
+    for (size_t w = blockIdx.x; w < nwrites; w += gridDim.x) {
+        const fr_t v = ld256_nc(wv + w);
+        if (v.is_zero()) continue;
+        fr_t* row = out + (bitrev_u64(wa[w], k) << t);
+        const unsigned long long end = wnext[w];
+        for (unsigned long long j = wj[w] + 1 + threadIdx.x; j < end; j += blockDim.x) st256(row + bitrev_u64(j, t), v);
     }
 }
 
@@ -137,9 +137,11 @@ __global__ void __launch_bounds__(256) k_lt_point_table(const fr_t* b, unsigned 
     }
 }
 
-cudaError_t launch_val_table(const unsigned long long* addr, const unsigned char* is_write, const fr_t* values, size_t n, unsigned k, unsigned t, fr_t* out,
-                             int sm_count, cudaStream_t s) {
-    k_val_table<<<grid_for((size_t)1 << k, 128, (size_t)sm_count * 8), 128, 0, s>>>(addr, is_write, values, n, k, t, out);
+cudaError_t launch_val_fill(const unsigned long long* wa, const unsigned long long* wj, const unsigned long long* wnext, const fr_t* wv, size_t nwrites,
+                            unsigned k, unsigned t, fr_t* out, int sm_count, cudaStream_t s) {
+    if (!nwrites) return cudaSuccess;
+    size_t cap = (size_t)sm_count * 16;
+    k_val_fill<<<(unsigned)(nwrites < cap ? nwrites : cap), 256, 0, s>>>(wa, wj, wnext, wv, nwrites, k, t, out);
     return cudaGetLastError();
 }
 cudaError_t launch_one_hot_weighted(const fr_t* W, const unsigned long long* addr, const unsigned char* sel, unsigned char flag, size_t n, unsigned k, unsigned t,

@@ -13,9 +13,10 @@ cudaError_t launch_limb_sums_to_table(const unsigned long long* acc, unsigned k,
 cudaError_t launch_table_gather(const fr_t* src, unsigned k, const unsigned long long* idx, size_t n, unsigned l, fr_t* out, int sm_count, cudaStream_t s);
 
 // ---- read/write memory (Twist) tables over (cell x, cycle j), reference index x + 2^k j
-// Val(x, j): content of cell x just before operation j (2^(k + t) entries)
-cudaError_t launch_val_table(const unsigned long long* addr, const unsigned char* is_write, const fr_t* values, size_t n, unsigned k, unsigned t, fr_t* out,
-                             int sm_count, cudaStream_t s);
+// Val(x, j): content of cell x just before operation j (2^(k + t) entries, pre-zeroed): write w (address wa[w], operation wj[w], value wv[w]) fills the
+// cycles wj[w] + 1 .. wnext[w] - 1 of its cell's row
+cudaError_t launch_val_fill(const unsigned long long* wa, const unsigned long long* wj, const unsigned long long* wnext, const fr_t* wv, size_t nwrites,
+                            unsigned k, unsigned t, fr_t* out, int sm_count, cudaStream_t s);
 // out[addr[j] + 2^k j] = W[j] for j < n with sel[j] == flag (pre-zeroed 2^(k + t) table; W: 2^t entries in table order)
 cudaError_t launch_one_hot_weighted(const fr_t* W, const unsigned long long* addr, const unsigned char* sel, unsigned char flag, size_t n, unsigned k, unsigned t,
                                     fr_t* out, int sm_count, cudaStream_t s);
