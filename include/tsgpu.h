@@ -388,6 +388,7 @@ int tsgpu_kzg_batch_verify(const tsgpu_params* params, const tsgpu_g1* commitmen
 /* pairing self-test hooks: prod_i e(a_i G1, b_i G2) == 1 ?;  G2 generator on the twist and of order r */
 int tsgpu_pairing_product_of_generators_is_one(const tsgpu_fr* a, const tsgpu_fr* b, size_t n);
 int tsgpu_g2_generator_checks(void);
+int tsgpu_pairing_self_check(void);   /* split final exponentiation == plain power, Fq12 inverse / square / Frobenius, Jacobian G2 multiplication: 1 when all agree */
 
 size_t tsgpu_proof_num_rounds(const tsgpu_proof* p);
 size_t tsgpu_proof_num_openings(const tsgpu_proof* p);

@@ -5,8 +5,9 @@
 //
 // ark-bn254 0.4.0 parameters: Fq2 = Fq[u]/(u^2 + 1), xi = 9 + u, Fq12 = Fq2[w]/(w^6 - xi), D-type twist
 // E': y^2 = x^3 + 3/xi, curve parameter x = 4965661367192848881, Miller loop over 6x + 2 followed by the two
-// Frobenius line additions, final exponentiation by (p^12 - 1)/r.  Deliberately simple (affine twist arithmetic,
-// schoolbook Fq12, plain square-and-multiply final exponentiation): ~25 ms per pairing product, correctness first.
+// Frobenius line additions, final exponentiation by (p^12 - 1)/r split into its easy part (conjugation, inversion, Frobenius) and a
+// square-and-multiply over (p^4 - p^2 + 1)/r.  Deliberately simple (affine twist arithmetic in the Miller loop, schoolbook Fq12): ~10 ms per
+// pairing product, correctness first.
 // Only the BOOLEAN result of a verification is observable, and it is the same for any correct bilinear pairing.
 #pragma once
 #include <vector>
@@ -65,7 +66,55 @@ struct Fq12 {
         for (int i = 6; i < 11; ++i) r.c[i - 6] = r.c[i - 6] + t[i] * x;
         return r;
     }
-    Fq12 sqr() const { return *this * *this; }
+    Fq12 sqr() const {   // symmetric schoolbook: 21 instead of 36 Fq2 products
+        Fq2 t[11];
+        for (auto& x : t) x = Fq2::zero();
+        for (int i = 0; i < 6; ++i) {
+            if (c[i].is_zero()) continue;
+            t[2 * i] = t[2 * i] + c[i].sqr();
+            for (int j = i + 1; j < 6; ++j) { if (c[j].is_zero()) continue; t[i + j] = t[i + j] + (c[i] * c[j]).dbl(); }
+        }
+        Fq12 r; const Fq2 x = xi();
+        for (int i = 0; i < 6; ++i) r.c[i] = t[i];
+        for (int i = 6; i < 11; ++i) r.c[i - 6] = r.c[i - 6] + t[i] * x;
+        return r;
+    }
+    // f^(p^6): w^(p^6) = -w and Fq2 is fixed, so the odd coefficients change sign
+    Fq12 conj6() const { Fq12 r = *this; r.c[1] = c[1].neg(); r.c[3] = c[3].neg(); r.c[5] = c[5].neg(); return r; }
+    // f^p: coefficient i -> conj(c_i) * gamma^i, gamma = xi^((p - 1) / 6)
+    Fq12 frobenius() const {
+        static const Fq2 gamma = [] { uint64_t e[4]; for (int i = 0; i < 4; ++i) e[i] = Fq64::modl(i); e[0] -= 1;
+                                      unsigned __int128 rem = 0; for (int i = 3; i >= 0; --i) { unsigned __int128 cur = (rem << 64) | e[i]; e[i] = (uint64_t)(cur / 6); rem = cur % 6; }
+                                      return xi().pow(e, 4); }();
+        Fq12 r; Fq2 g = Fq2::one();
+        for (int i = 0; i < 6; ++i) { r.c[i] = c[i].conj() * g; g = g * gamma; }
+        return r;
+    }
+    // inverse through Fq12 = Fq6[w] / (w^2 - v), Fq6 = Fq2[v] / (v^3 - xi), v = w^2:  f = a + w b,  1/f = (a - w b) / (a^2 - v b^2)
+    Fq12 inverse() const {
+        struct F6 {
+            Fq2 a0, a1, a2;
+            F6 mul(const F6& o) const {
+                const Fq2 x = xi();
+                return {a0 * o.a0 + (a1 * o.a2 + a2 * o.a1) * x, a0 * o.a1 + a1 * o.a0 + a2 * o.a2 * x, a0 * o.a2 + a1 * o.a1 + a2 * o.a0};
+            }
+            F6 sub(const F6& o) const { return {a0 - o.a0, a1 - o.a1, a2 - o.a2}; }
+            F6 mul_v() const { return {a2 * xi(), a0, a1}; }
+            F6 inverse() const {
+                const Fq2 x = xi();
+                Fq2 t0 = a0.sqr() - a1 * a2 * x, t1 = a2.sqr() * x - a0 * a1, t2 = a1.sqr() - a0 * a2;
+                Fq2 d = (a0 * t0 + (a2 * t1 + a1 * t2) * x).inverse();
+                return {t0 * d, t1 * d, t2 * d};
+            }
+        };
+        F6 a = {c[0], c[2], c[4]}, b = {c[1], c[3], c[5]};
+        F6 n = a.mul(a).sub(b.mul(b).mul_v()).inverse();
+        F6 ra = a.mul(n), rb = b.mul(n);
+        Fq12 r;
+        r.c[0] = ra.a0; r.c[2] = ra.a1; r.c[4] = ra.a2;
+        r.c[1] = rb.a0.neg(); r.c[3] = rb.a1.neg(); r.c[5] = rb.a2.neg();
+        return r;
+    }
     Fq12 pow(const uint64_t* e, int nlimbs) const {
         Fq12 acc = one();
         bool started = false;
@@ -103,11 +152,46 @@ struct G2A {
         Fq2 x3 = lam.sqr() - x - o.x;
         return {x3, lam * (x - x3) - y, false};
     }
+    // scalar multiplication in Jacobian coordinates (a = 0: dbl-2009-l, madd-2007-bl), one inversion at the end instead of one per step
     G2A mul(const Fr64& k) const {
+        if (inf) return *this;
         Fr64 c = k.from_mont();
-        G2A acc = infinity();
-        for (int i = 255; i >= 0; --i) { acc = acc.add(acc); if ((c.l[i >> 6] >> (i & 63)) & 1) acc = acc.add(*this); }
-        return acc;
+        Fq2 X = Fq2::zero(), Y = Fq2::one(), Z = Fq2::zero();   // identity: Z = 0
+        for (int i = 255; i >= 0; --i) {
+            if (!Z.is_zero()) {                                   // double
+                Fq2 A = X.sqr(), B = Y.sqr(), Cc = B.sqr();
+                Fq2 D = ((X + B).sqr() - A - Cc).dbl();
+                Fq2 E = A.dbl() + A, F = E.sqr();
+                Fq2 X3 = F - D.dbl();
+                Fq2 Y3 = E * (D - X3) - Cc.dbl().dbl().dbl();
+                Fq2 Z3 = (Y * Z).dbl();
+                X = X3; Y = Y3; Z = Z3;
+            }
+            if ((c.l[i >> 6] >> (i & 63)) & 1) {
+                if (Z.is_zero()) { X = x; Y = y; Z = Fq2::one(); continue; }
+                Fq2 Z1Z1 = Z.sqr(), U2 = x * Z1Z1, S2 = y * Z * Z1Z1;
+                if (U2 == X) {
+                    if (S2 == Y) {                                // acc == this: double (same formulas)
+                        Fq2 A = X.sqr(), B = Y.sqr(), Cc = B.sqr();
+                        Fq2 D = ((X + B).sqr() - A - Cc).dbl();
+                        Fq2 E = A.dbl() + A, F = E.sqr();
+                        Fq2 X3 = F - D.dbl();
+                        Fq2 Y3 = E * (D - X3) - Cc.dbl().dbl().dbl();
+                        Fq2 Z3 = (Y * Z).dbl();
+                        X = X3; Y = Y3; Z = Z3;
+                    } else { X = Fq2::zero(); Y = Fq2::one(); Z = Fq2::zero(); }
+                    continue;
+                }
+                Fq2 H = U2 - X, HH = H.sqr(), I = HH.dbl().dbl(), J = H * I, rr = (S2 - Y).dbl(), V = X * I;
+                Fq2 X3 = rr.sqr() - J - V.dbl();
+                Fq2 Y3 = rr * (V - X3) - (Y * J).dbl();
+                Fq2 Z3 = (Z + H).sqr() - Z1Z1 - HH;
+                X = X3; Y = Y3; Z = Z3;
+            }
+        }
+        if (Z.is_zero()) return infinity();
+        Fq2 zi = Z.inverse(), zi2 = zi.sqr();
+        return {X * zi2, Y * zi2 * zi, false};
     }
 };
 
@@ -180,7 +264,18 @@ inline Fq12 miller_loop(const Fq64& xP, const Fq64& yP, bool p_inf, const G2A& Q
     return f;
 }
 
+// f^((p^12 - 1) / r) = ((f^(p^6 - 1))^(p^2 + 1))^((p^4 - p^2 + 1) / r): the easy part by one conjugation, one inversion and two Frobenius maps,
+// the hard part by square-and-multiply over its 761-bit exponent (exactly the same GT element as a plain power by (p^12 - 1) / r)
 inline Fq12 final_exponentiation(const Fq12& f) {
+    static const uint64_t E[12] = {
+        0xe81bb482ccdf42b1ull, 0x5abf5cc4f49c36d4ull, 0xf1154e7e1da014fdull, 0xdcc7b44c87cdbacfull, 0xaaa441e3954bcf8aull, 0x6b887d56d5095f23ull,
+        0x79581e16f3fd90c6ull, 0x3b1b1355d189227dull, 0x4e529a5861876f6bull, 0x6c0eb522d5b12278ull, 0x331ec15183177fafull, 0x01baaa710b0759adull};   // (p^4 - p^2 + 1) / r
+    Fq12 t = f.conj6() * f.inverse();          // f^(p^6 - 1)
+    t = t.frobenius().frobenius() * t;         // ^(p^2 + 1)
+    return t.pow(E, 12);
+}
+// the plain power by (p^12 - 1) / r (44 limbs): kept as the cross-check of the split form (tests/test_host_pairing.py)
+inline Fq12 final_exponentiation_plain(const Fq12& f) {
     static const uint64_t E[44] = {
         0x86964b64ca86f120ull, 0x40a4efb7e54523a4ull, 0x837fa97896e84abbull, 0x361102b6b9b2b918ull, 0xc0de81def35692daull, 0xbe04c7e8a6c3c760ull,
         0xd766f9c9d570bb7full, 0xc230974d83561841ull, 0x5bba1668c3be69a3ull, 0x7f3811c410526294ull, 0x29baee7ddadda71cull, 0xbf813b8d145da900ull,

@@ -490,6 +490,25 @@ int tsgpu_pairing_product_of_generators_is_one(const tsgpu_fr* a, const tsgpu_fr
     }
     return pairing_product_is_one(P, Q) ? 1 : 0;
 }
+// self-check of the faster pairing pieces: the split final exponentiation equals the plain power by (p^12 - 1) / r, the Fq12 inverse and
+// the symmetric square agree with the product, the Jacobian G2 scalar multiplication equals repeated affine additions
+int tsgpu_pairing_self_check(void) {
+    Fq64 ax, ay;
+    G1J P = G1J::generator().mul(Fr64::from_u64(12345));
+    P.to_affine(ax, ay);
+    G2A Q = G2A::generator();
+    Fq12 f = miller_loop(ax, ay, false, Q);
+    if (!(final_exponentiation(f) == final_exponentiation_plain(f))) return 0;
+    if (!(f * f.inverse()).is_one()) return 0;
+    if (!(f.sqr() == f * f)) return 0;
+    if (!(f.frobenius().frobenius().frobenius().frobenius().frobenius().frobenius() == f.conj6())) return 0;   // (f^p)^..6 times = f^(p^6)
+    G2A acc = G2A::infinity();
+    for (int i = 0; i < 11; ++i) acc = acc.add(Q);
+    G2A m = Q.mul(Fr64::from_u64(11));
+    if (m.inf || !(m.x == acc.x) || !(m.y == acc.y)) return 0;
+    if (!Q.mul(Fr64::from_u64(1)).on_curve() || !(Q.mul(Fr64::from_u64(2)).x == Q.add(Q).x)) return 0;
+    return 1;
+}
 int tsgpu_g2_generator_checks(void) {   // on the twist, and of order r: (r - 1) Q + Q = infinity
     G2A g = G2A::generator();
     if (!g.on_curve()) return 0;

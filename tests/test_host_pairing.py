@@ -73,3 +73,8 @@ def test_kzg_batch_verify_mirrors_reference_formula(tsgpu, oracle):
     with pytest.raises(tsgpu.TwistAndShoutError) as e:
         tsgpu.kzg_batch_verify(vp, Cs, zs[:2], vs, pis)
     assert e.value.variant == "Commitment"
+
+
+def test_pairing_fast_paths_agree_with_the_plain_ones(tsgpu):
+    """split final exponentiation == f^((p^12 - 1) / r), Fq12 inverse / symmetric square / Frobenius^6 == conjugation, Jacobian G2 multiplication"""
+    assert tsgpu.lib().tsgpu_pairing_self_check() == 1
