@@ -29,6 +29,17 @@ extern "C" {
     pub fn tsgpu_mle_evaluate(ctx: *mut Ctx, evals: *const Fr, num_vars: c_uint, point: *const Fr, out: *mut Fr) -> c_int;
     pub fn tsgpu_mle_partial_evaluate(ctx: *mut Ctx, evals: *const Fr, num_vars: c_uint, fixed: *const Fr, k: c_uint, out: *mut Fr) -> c_int;
 
+    // lookup / memory-checking building blocks (csrc/lookup.cu)
+    pub fn tsgpu_table_scatter_add(ctx: *mut Ctx, weights: *const Table, idx: *const u64, n: usize, log_k: c_uint, out: *mut *mut Table) -> c_int;
+    pub fn tsgpu_table_gather(ctx: *mut Ctx, src: *const Table, idx: *const u64, n: usize, num_vars: c_uint, out: *mut *mut Table) -> c_int;
+    pub fn tsgpu_table_inner_product(ctx: *mut Ctx, a: *const Table, b: *const Table, out: *mut Fr) -> c_int;
+    pub fn tsgpu_table_mul(ctx: *mut Ctx, a: *const Table, b: *const Table, out: *mut *mut Table) -> c_int;
+    pub fn tsgpu_table_memory_values(ctx: *mut Ctx, addresses: *const u64, is_write: *const u8, values: *const Fr, n: usize, log_cells: c_uint,
+                                     log_cycles: c_uint, out: *mut *mut Table) -> c_int;
+    pub fn tsgpu_table_one_hot_weighted(ctx: *mut Ctx, weights: *const Table, addresses: *const u64, select: *const u8, flag: c_int, n: usize,
+                                        log_cells: c_uint, out: *mut *mut Table) -> c_int;
+    pub fn tsgpu_table_lt_point(ctx: *mut Ctx, point: *const Fr, num_vars: c_uint, out: *mut *mut Table) -> c_int;
+
     // sum-check rounds, the transcript stays with the caller (src/sumcheck.rs:56-110,156-207)
     pub fn tsgpu_sc_begin(ctx: *mut Ctx, tables: *const *mut Table, d: c_int, out: *mut *mut Sc) -> c_int;
     pub fn tsgpu_sc_num_vars(sc: *const Sc) -> c_uint;
@@ -75,6 +86,23 @@ extern "C" {
     pub fn tsgpu_proof_opening(p: *const Proof, i: usize, proof: *mut G1Projective, value: *mut Fr);
     pub fn tsgpu_proof_bytes(p: *const Proof, out: *mut u8, capacity: usize) -> usize;
     pub fn tsgpu_proof_free(p: *mut Proof);
+
+    // the real constraint sum-checks the reference leaves as stubs (non-parity mode; host/read_check.cpp, host/memory_check.cpp).
+    // `transcript` is the library's own Transcript handle (tsgpu_transcript_new): these protocols draw their challenges inside the call.
+    pub fn tsgpu_transcript_new(seed32: *const u8) -> *mut TranscriptH;
+    pub fn tsgpu_transcript_free(t: *mut TranscriptH);
+    pub fn tsgpu_shout_read_check_prove(ctx: *mut Ctx, entries: *const Fr, num_entries: usize, lookup_indices: *const u64, lookup_values: *const Fr,
+                                        num_lookups: usize, transcript: *mut TranscriptH, claimed_sum: *mut Fr, round_polys: *mut Fr,
+                                        final_evaluation: *mut Fr, challenges: *mut Fr) -> c_int;
+    pub fn tsgpu_shout_read_check_verify(ctx: *mut Ctx, entries: *const Fr, num_entries: usize, lookup_indices: *const u64, lookup_values: *const Fr,
+                                         num_lookups: usize, transcript: *mut TranscriptH, round_polys: *const Fr, num_rounds: usize,
+                                         final_evaluation: *const Fr, valid: *mut c_int) -> c_int;
+    pub fn tsgpu_twist_memory_check_prove(ctx: *mut Ctx, addresses: *const u64, values: *const Fr, is_write: *const u8, num_operations: usize,
+                                          memory_size: usize, transcript: *mut TranscriptH, claims: *mut Fr, rounds1: *mut Fr, final1: *mut Fr,
+                                          rounds2: *mut Fr, final2: *mut Fr) -> c_int;
+    pub fn tsgpu_twist_memory_check_verify(ctx: *mut Ctx, addresses: *const u64, values: *const Fr, is_write: *const u8, num_operations: usize,
+                                           memory_size: usize, transcript: *mut TranscriptH, claims: *const Fr, rounds1: *const Fr, num_rounds1: usize,
+                                           final1: *const Fr, rounds2: *const Fr, num_rounds2: usize, final2: *const Fr, valid: *mut c_int) -> c_int;
 
     // multi-GPU (one process per GPU; the host program carries the 128-byte NCCL id)
     pub fn tsgpu_comm_unique_id(out: *mut u8) -> c_int;
