@@ -11,4 +11,5 @@ from .binding import (Context, Table, SumCheckRounds, SumCheck, SumCheckProof, T
                       KZGCommitment, g1_hash, g1_compress, g1_equal, unique_id, TwistAndShoutError, LIB_PATH, lib)
 from .api import (setup_params, ProverParams, VerifierParams, MemoryTrace, MemoryOp, Twist, TwistProof,  # noqa: F401,E402
                   LookupTable, LookupOp, Shout, ShoutProof, fe, fe_vec, fe_to_int, HostVerifierParams, kzg_verify, kzg_batch_verify, KZGVectorCommitment,
-                  MultilinearExtension, LessThanPolynomial, ShoutReadCheck, TwistMemoryCheck)
+                  MultilinearExtension, LessThanPolynomial, ShoutReadCheck, TwistMemoryCheck,
+                  fe_from_int, fe_add, fe_mul, fe_inverse, field_utils, poly_utils, polynomial_division)

@@ -610,3 +610,127 @@ class TwistMemoryCheck:
                                                              transcript._h, _p(claims), _p(r1), C.c_size_t(r1.shape[0]), _p(f1),
                                                              _p(r2), C.c_size_t(r2.shape[0]), _p(f2), C.byref(ok)))
         return bool(ok.value)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# Small host-side helpers of the reference that are not on the GPU path (src/utils.rs:207-269 `field_utils`, src/polynomials.rs:296-371
+# `poly_utils`, src/commitments.rs:317-375 `polynomial_division`): mirrored so that the reference's own tests can be restated one for one.
+# Plain Python integers on canonical values; only lagrange_interpolate on the nodes 0..n-1 and inner_product of tables run on the device.
+R_MODULUS = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+_R2 = pow(1 << 256, 2, R_MODULUS)
+
+
+def fe_from_int(x: int) -> np.ndarray:
+    """canonical integer (any size, reduced mod r) -> FieldElement"""
+    raw = np.array([[(x % R_MODULUS) >> (64 * i) & 0xFFFFFFFFFFFFFFFF for i in range(4)]], dtype=np.uint64)
+    r2 = np.array([[_R2 >> (64 * i) & 0xFFFFFFFFFFFFFFFF for i in range(4)]], dtype=np.uint64)
+    out = np.empty((1, 4), dtype=np.uint64)
+    lib().tsgpu_fr_mul(_p(raw), _p(r2), _p(out))          # raw * R^2 / R = raw * R: the Montgomery form
+    return out[0]
+
+
+def fe_add(a, b) -> np.ndarray:
+    a = _fr(a, 1); b = _fr(b, 1); out = np.empty((1, 4), dtype=np.uint64)
+    lib().tsgpu_fr_add(_p(a), _p(b), _p(out))
+    return out[0]
+
+
+def fe_mul(a, b) -> np.ndarray:
+    a = _fr(a, 1); b = _fr(b, 1); out = np.empty((1, 4), dtype=np.uint64)
+    lib().tsgpu_fr_mul(_p(a), _p(b), _p(out))
+    return out[0]
+
+
+def fe_inverse(a) -> np.ndarray:
+    return fe_from_int(pow(fe_to_int(a), -1, R_MODULUS))
+
+
+class field_utils:                                       # noqa: N801 - the reference's module name
+    """src/utils.rs:207-269"""
+
+    @staticmethod
+    def inner_product(a, b) -> np.ndarray:
+        a = _fr(a); b = _fr(b)
+        assert a.shape[0] == b.shape[0], "Vector lengths must match"
+        return fe_from_int(sum(fe_to_int(x) * fe_to_int(y) for x, y in zip(a, b)))
+
+    @staticmethod
+    def horner_eval(coeffs, point) -> np.ndarray:
+        coeffs = _fr(coeffs) if len(coeffs) else np.empty((0, 4), dtype=np.uint64)
+        point = _fr(point, 1); out = np.empty((1, 4), dtype=np.uint64)
+        lib().tsgpu_horner_eval(_p(coeffs), C.c_size_t(coeffs.shape[0]), _p(point), _p(out))
+        return out[0]
+
+    @staticmethod
+    def powers(x, n: int) -> np.ndarray:
+        xi, cur, out = fe_to_int(x), 1, []
+        for _ in range(n):
+            out.append(fe_from_int(cur)); cur = cur * xi % R_MODULUS
+        return np.stack(out) if out else np.empty((0, 4), dtype=np.uint64)
+
+    @staticmethod
+    def vanishing_poly_eval(points, point) -> np.ndarray:
+        z, acc = fe_to_int(point), 1
+        for s in _fr(points):
+            acc = acc * (z - fe_to_int(s)) % R_MODULUS
+        return fe_from_int(acc)
+
+    @staticmethod
+    def batch_inverse(elements) -> np.ndarray:
+        els = [fe_to_int(e) for e in _fr(elements)] if len(elements) else []
+        return np.stack([fe_from_int(pow(e, -1, R_MODULUS)) for e in els]) if els else np.empty((0, 4), dtype=np.uint64)
+
+
+class poly_utils:                                        # noqa: N801
+    """src/polynomials.rs:296-371"""
+
+    @staticmethod
+    def lagrange_interpolate(ctx: Context, points) -> np.ndarray:
+        """points = [(x_i, y_i)]; on the nodes x_i = i (the only use on the prove path, src/twist.rs:307-315) the device interpolation runs,
+        any other node set takes the reference's own O(n^2) formula on the host"""
+        xs = [fe_to_int(x) for x, _ in points]
+        ys = np.stack([np.asarray(y, dtype=np.uint64).reshape(4) for _, y in points]) if points else np.empty((0, 4), dtype=np.uint64)
+        if xs == list(range(len(xs))):
+            return ctx.interpolate_iota(ys) if xs else ys
+        n, yi, p = len(xs), [fe_to_int(y) for y in ys], R_MODULUS
+        coeffs = [0] * n
+        for i in range(n):
+            basis, denom = [1], 1
+            for j in range(n):
+                if j != i:
+                    basis = [(a - xs[j] * b) % p for a, b in zip([0] + basis, basis + [0])]
+                    denom = denom * (xs[i] - xs[j]) % p
+            scale = yi[i] * pow(denom, -1, p) % p
+            coeffs = [(c + scale * b) % p for c, b in zip(coeffs, basis)]
+        return np.stack([fe_from_int(c) for c in coeffs])
+
+    @staticmethod
+    def evaluate_polynomial(coeffs, point) -> np.ndarray:
+        return field_utils.horner_eval(coeffs, point)
+
+    @staticmethod
+    def derivative(coeffs) -> np.ndarray:
+        cs = [fe_to_int(c) for c in _fr(coeffs)] if len(coeffs) else []
+        if len(cs) <= 1:
+            return fe(0).reshape(1, 4)
+        return np.stack([fe_from_int(c * i) for i, c in enumerate(cs) if i >= 1])
+
+
+def polynomial_division(dividend, divisor) -> np.ndarray:
+    """src/commitments.rs:317-375: quotient of the long division; TwistAndShoutError(Polynomial, "Cannot divide by zero polynomial")"""
+    p = R_MODULUS
+    a = [fe_to_int(c) for c in _fr(dividend)] if len(dividend) else []
+    b = [fe_to_int(c) for c in _fr(divisor)] if len(divisor) else []
+    while b and b[-1] == 0:
+        b.pop()
+    if not b:
+        raise TwistAndShoutError(5, "Cannot divide by zero polynomial")
+    if len(a) < len(b):
+        return np.empty((0, 4), dtype=np.uint64)
+    q = [0] * (len(a) - len(b) + 1)
+    inv = pow(b[-1], -1, p)
+    for k in range(len(q) - 1, -1, -1):
+        q[k] = a[k + len(b) - 1] * inv % p
+        for j, bj in enumerate(b):
+            a[k + j] = (a[k + j] - q[k] * bj) % p
+    return np.stack([fe_from_int(c) for c in q])
