@@ -131,6 +131,9 @@ int tsgpu_sc_begin(tsgpu_ctx* ctx, tsgpu_table* const* tables, int d, tsgpu_sc**
 unsigned tsgpu_sc_num_vars(const tsgpu_sc* sc);   /* variables still unbound */
 /* g(0), g(1), g(2), g(3) of the current round (sumcheck.rs:175-198) */
 int tsgpu_sc_round_eval(tsgpu_sc* sc, tsgpu_fr evals[4]);
+/* the same four values for d = 2 when g(0) + g(1) = claim is vouched for by the caller, who then owes the check of the claim itself (the library's
+ * SumCheck::prove loop pays it at the end, see tsgpu_sumcheck_prove_product): two products per pair instead of three.  d != 2: plain evaluation. */
+int tsgpu_sc_round_eval_claim(tsgpu_sc* sc, const tsgpu_fr* claim, tsgpu_fr evals[4]);
 /* bind the current variable to r (sumcheck.rs:99) */
 int tsgpu_sc_bind(tsgpu_sc* sc, const tsgpu_fr* r);
 /* fused: bind to r, then evaluate the next round's g(0..3) in the same pass */

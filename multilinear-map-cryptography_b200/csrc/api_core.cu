@@ -173,6 +173,7 @@ int tsgpu_set_tuning(tsgpu_ctx* ctx, const char* key, long value) {
         set_prefetch_min_work(value < 0 || value > 61 ? (size_t)1 << 62 : (size_t)1 << value);
         return TSGPU_OK;
     }
+    if (!strcmp(key, "deferred_claim_check")) { ctx->deferred_claim_check = value != 0; return TSGPU_OK; }
     if (!strcmp(key, "msm_acc_waves")) { set_msm_acc_waves((int)value); return TSGPU_OK; }
     if (!strcmp(key, "msm_two_level")) { set_msm_two_level(value != 0); return TSGPU_OK; }
     if (!strcmp(key, "kernel_timing")) { ctx->timing = value != 0; return TSGPU_OK; }
@@ -645,6 +646,20 @@ int tsgpu_sc_round_eval(tsgpu_sc* sc, tsgpu_fr evals[4]) {
     KernelTimer kt(ctx, "sc_round_eval");
     // the finishing block writes the four values straight into the pinned host mirror (unified addressing: no D2H copy to enqueue per round)
     TSG_CUDA(ctx, launch_round_eval(sc->d, sc_tabs(sc), (size_t)1 << sc->vars_left, ctx->partials, ctx->ticket, ctx->host_out, ctx->sm_count, ctx->stream));
+    ctx->launches += 1;
+    return read_host_result(ctx, 4, evals);
+}
+
+// tsgpu_sc_round_eval for d = 2 when the caller vouches for g(0) + g(1) = claim (it must then check the claim by other means: the host loop of
+// host/sumcheck_host.cpp does so at the end of the protocol); for d != 2 the claim is ignored and the full evaluation runs
+int tsgpu_sc_round_eval_claim(tsgpu_sc* sc, const tsgpu_fr* claim, tsgpu_fr evals[4]) {
+    if (!sc || !evals || !claim) return TSGPU_E_INVALID_PARAMETERS;
+    tsgpu_ctx* ctx = sc->ctx;
+    if (sc->vars_left == 0) return fail(ctx, TSGPU_E_SUMCHECK, "no variables left to evaluate");
+    KernelTimer kt(ctx, "sc_round_eval");
+    const fr_t cl = to_fr(claim);
+    TSG_CUDA(ctx, launch_round_eval(sc->d, sc_tabs(sc), (size_t)1 << sc->vars_left, ctx->partials, ctx->ticket, ctx->host_out, ctx->sm_count, ctx->stream,
+                                    sc->d == 2 ? &cl : nullptr));
     ctx->launches += 1;
     return read_host_result(ctx, 4, evals);
 }

@@ -128,6 +128,22 @@ __global__ void __launch_bounds__(SC_THREADS, (D <= 2 ? 2 : 1)) k_round_eval(ScT
     grid_finish_sum<fr_t, EvalAcc<D>::NV>(v, partials, ticket, smem, EvalEpilogue<D>{out4});
 }
 
+// d = 2 evaluation with the claim g(0) + g(1) known: sums g(0) and g(2) only (two lazy products per pair instead of three)
+__global__ void __launch_bounds__(SC_THREADS, 2) k_round_eval2_claim(ScTables tabs, size_t half, const fr_t claim, fr_t* partials, unsigned int* ticket, fr_t* out4) {
+    __shared__ fr_t smem[2 * 32];
+    EvalAcc2Claim acc; acc.clear();
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < half; p += stride) {
+        fr_t lo[2], hi[2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) { lo[t] = ld256_stream(tabs.t[t] + p); hi[t] = ld256_stream(tabs.t[t] + p + half); }
+        acc.pair(lo, hi);
+    }
+    fr_t v[2];
+    acc.finish(v);
+    grid_finish_sum<fr_t, 2>(v, partials, ticket, smem, EvalClaimEpilogue{out4, claim});
+}
+
 // ---------------------------------------------------------------- K1: bind (fold) one table in place
 __global__ void __launch_bounds__(SC_THREADS) k_bind(fr_t* t, size_t half, const fr_ctab r) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -371,6 +387,30 @@ __global__ void __launch_bounds__(SC_THREADS, 2) k_round_eval2_pf(ScTables tabs,
     acc.finish(v);
     grid_finish_sum<fr_t, EvalAcc<2>::NV>(v, partials, ticket, smem, EvalEpilogue<2>{out4});
 }
+__global__ void __launch_bounds__(SC_THREADS, 2) k_round_eval2_claim_pf(ScTables tabs, size_t half, const fr_t claim, fr_t* partials, unsigned int* ticket, fr_t* out4) {
+    extern __shared__ __align__(128) unsigned char dyn[];
+    __shared__ fr_t smem[2 * 32];
+    __shared__ uint64_t bars[PF_WARPS];
+    WarpPrefetch<4> pf; pf.init(dyn, bars);
+    EvalAcc2Claim acc; acc.clear();
+    const size_t tiles = half / 32, nw = (size_t)gridDim.x * PF_WARPS;
+    size_t tile = (size_t)blockIdx.x * PF_WARPS + (threadIdx.x >> 5);
+    auto post = [&](size_t t) {
+        const fr_t* rows[4] = {tabs.t[0] + t * 32, tabs.t[0] + half + t * 32, tabs.t[1] + t * 32, tabs.t[1] + half + t * 32};
+        pf.issue(rows);
+    };
+    if (tile < tiles) post(tile);
+    for (; tile < tiles; tile += nw) {
+        fr_t e[4];
+        pf.fetch(e);
+        if (tile + nw < tiles) post(tile + nw);
+        fr_t lo[2] = {e[0], e[2]}, hi[2] = {e[1], e[3]};
+        acc.pair(lo, hi);
+    }
+    fr_t v[2];
+    acc.finish(v);
+    grid_finish_sum<fr_t, 2>(v, partials, ticket, smem, EvalClaimEpilogue{out4, claim});
+}
 // positions per launch from which the prefetch variants run (tuning "prefetch_min_log2").  Measured on B200 (tools/bench_fold.py): +5.7% on the fused
 // kernel and +3% on the evaluation kernel at 2^26 entries, +3-5% down to 2^22, neutral below (the tables then sit in the 126 MB L2).
 static size_t g_pf_min_work = (size_t)1 << 21;
@@ -415,8 +455,19 @@ static inline int sc_grid(size_t work, int sm_count, int blocks_per_sm) {
 }
 
 cudaError_t launch_round_eval(int d, const ScTables& tabs, size_t n, fr_t* partials, unsigned int* ticket, fr_t* out4,
-                              int sm_count, cudaStream_t s) {
+                              int sm_count, cudaStream_t s, const fr_t* claim) {
     size_t half = n / 2;
+    if (claim && d == 2) {
+        if (half >= g_pf_min_work && half % 32 == 0) {
+            const size_t sm = (size_t)PF_WARPS * 4 * 1024;
+            cudaError_t e = enable_smem(k_round_eval2_claim_pf, sm);
+            if (e) return e;
+            k_round_eval2_claim_pf<<<sc_grid(half, sm_count, 2), SC_THREADS, sm, s>>>(tabs, half, *claim, partials, ticket, out4);
+        } else {
+            k_round_eval2_claim<<<sc_grid(half, sm_count, SC_BLOCKS_PER_SM), SC_THREADS, 0, s>>>(tabs, half, *claim, partials, ticket, out4);
+        }
+        return cudaGetLastError();
+    }
     if (half >= g_tma_min_work) {
         size_t tiles = half / TMA_THREADS;
         int g = tma_grid(tiles, sm_count, TMA_MINBLOCKS);

@@ -33,8 +33,9 @@ inline int sc_max_grid(int sm_count) { return sm_count * SC_BLOCKS_PER_SM_BIND; 
 
 void set_tma_min_work(size_t positions);
 void set_prefetch_min_work(size_t positions);   // d = 2 round kernels with a warp-private shared-memory prefetch of the next tile
+// claim (optional, d = 2 only): the value g(0) + g(1) must have; the kernel then sums g(0) and g(2) and derives g(1)
 cudaError_t launch_round_eval(int d, const ScTables& tabs, size_t n, fr_t* partials, unsigned int* ticket, fr_t* out4,
-                              int sm_count, cudaStream_t s);
+                              int sm_count, cudaStream_t s, const fr_t* claim = nullptr);
 cudaError_t launch_bind(fr_t* t, size_t n, const fr_t& r, int sm_count, cudaStream_t s);
 cudaError_t launch_bind_to(const fr_t* t, fr_t* out, size_t n, const fr_t& r, int sm_count, cudaStream_t s);
 // claim (optional): the value g(0) + g(1) of the round being evaluated must have; with it the d = 2 kernel derives g(1) instead of summing it

@@ -39,7 +39,18 @@ int sumcheck_prove_product(tsgpu_ctx* ctx, tsgpu_table* const* tables, int d, co
     if (challenges) challenges->clear();
     fr_t current = claimed_sum;
     tsgpu_fr ev[4];
-    if (num_vars) { rc = tsgpu_sc_round_eval(sc, ev); if (rc) goto cuda_fail; }
+    // d = 2: round 0 also runs in the claim form (g(1) = claimed_sum - g(0): a third of its products saved).  The reference's round-0 check
+    // g(0) + g(1) == claimed_sum (sumcheck.rs:77-84) - the only one that can fail for honest tables - is then paid at the END: a wrong claim off by
+    // delta shifts every later running sum by delta * prod_i L_1(r_i) (L_1 = the Lagrange basis polynomial of node 1), so the product of the
+    // bound tables differs from the last running sum unless some challenge hits a root of L_1 (probability ~ 2 n / |Fr|, ~2^-247).  On a mismatch
+    // the transcript is rolled back to its state at entry (the reference fails before touching it) and the same error is returned.
+    const bool deferred = d == 2 && num_vars > 0 && ctx->deferred_claim_check;
+    const size_t transcript_mark = tr.state_len();
+    if (num_vars) {
+        tsgpu_fr cl; to_abi(claimed_sum, &cl);
+        rc = deferred ? tsgpu_sc_round_eval_claim(sc, &cl, ev) : tsgpu_sc_round_eval(sc, ev);
+        if (rc) goto cuda_fail;
+    }
     for (unsigned round = 0; round < num_vars; ++round) {
         fr_t e[4], coeffs[4];
         for (int i = 0; i < 4; ++i) e[i] = from_abi(ev[i]);
@@ -72,6 +83,14 @@ int sumcheck_prove_product(tsgpu_ctx* ctx, tsgpu_table* const* tables, int d, co
         if (table_finals) table_finals->clear();
         for (int t = 0; t < d; ++t) { fr_t v = from_abi(fin[t]); fe = fe * v; if (table_finals) table_finals->push_back(v); }
         proof.final_evaluation = fe;
+        if (deferred && fe != current) {       // the deferred round-0 check
+            tsgpu_sc_end(sc);
+            tr.truncate(transcript_mark);
+            proof.round_polynomials.clear();
+            if (challenges) challenges->clear();
+            err = "Round 0 consistency check failed";
+            return TSGPU_E_SUMCHECK;
+        }
     }
     tsgpu_sc_end(sc);
     return TSGPU_OK;

@@ -163,6 +163,7 @@ class Transcript {
         return out;
     }
     size_t state_len() const { return state_.size(); }
+    void truncate(size_t len) { if (len < state_.size()) state_.resize(len); }   // roll back to an earlier state (error paths that must leave no trace)
   private:
     std::vector<uint8_t> state_;
 };

@@ -171,6 +171,37 @@ def test_wrong_claimed_sum_is_rejected_in_round_zero(ctx, tsgpu, oracle):
         oracle.sumcheck_prove_product(tables, oracle.fr_from_ints([12345])[0], mode="closure")
 
 
+@pytest.mark.parametrize("nv", [1, 2, 7, 13])
+def test_deferred_round_zero_check_keeps_the_reference_error_behaviour(ctx, tsgpu, oracle, nv):
+    """d = 2: round 0 runs in the claim form and the claimed sum is checked at the end of the protocol.  A wrong claim must still give
+    Err(SumCheck("Round 0 consistency check failed")) (sumcheck.rs:77-84) and leave the transcript exactly as the reference does (untouched: it
+    fails before the first append); a right claim gives the same proof with the deferred check on and off."""
+    n = 1 << nv
+    tables = [oracle.chacha_fr_rand(seed_bytes(90 + t + nv), n) for t in range(2)]
+    ai, bi = oracle.fr_to_ints(tables[0]), oracle.fr_to_ints(tables[1])
+    claimed = sum(x * y for x, y in zip(ai, bi)) % oracle.R_MOD
+    good = oracle.fr_from_ints([claimed])[0]
+    for delta in (1, oracle.R_MOD - 1, 123456789):
+        bad = oracle.fr_from_ints([(claimed + delta) % oracle.R_MOD])[0]
+        tr = tsgpu.Transcript()
+        tr.append_field_element(b"before", tsgpu.fe(7))
+        mark = tr.state_len
+        with pytest.raises(tsgpu.TwistAndShoutError) as e:
+            tsgpu.SumCheck(nv, bad).prove_product(ctx, [ctx.table_upload(t) for t in tables], tr)
+        assert e.value.variant == "SumCheck" and e.value.message == "Round 0 consistency check failed"
+        assert tr.state_len == mark                                   # rolled back: the next challenge is what the reference would draw
+        otr = oracle.Transcript(); otr.append_field_element(b"before", tsgpu.fe(7))
+        assert (tr.challenge_field_element(b"next") == otr.challenge_field_element(b"next")).all()
+    ref = oracle.sumcheck_prove_product(tables, good, mode="tables")
+    for flag in (1, 0):
+        ctx.set_tuning("deferred_claim_check", flag)
+        try:
+            proof = tsgpu.SumCheck(nv, good).prove_product(ctx, [ctx.table_upload(t) for t in tables], tsgpu.Transcript())
+        finally:
+            ctx.set_tuning("deferred_claim_check", 1)
+        assert (proof.round_polynomials == ref["round_polynomials"]).all() and (proof.final_evaluation == ref["final_evaluation"]).all()
+
+
 def test_reference_integration_x1_times_x2(ctx, tsgpu, oracle):
     """tests/integration_tests.rs:263-288 and src/sumcheck.rs:221-245: f(x1,x2) = x1*x2 sums to 1 over {0,1}^2.
     As tables: A[i] = bit0(i), B[i] = bit1(i)."""
