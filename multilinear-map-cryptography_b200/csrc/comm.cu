@@ -215,11 +215,19 @@ int tsgpu_sumcheck_prove_product_sharded(tsgpu_ctx* ctx, tsgpu_table* const* tab
     ScTables tabs; for (int i = 0; i < SC_MAX_TABLES; ++i) tabs.t[i] = i < d ? tables[i]->d : nullptr;
     fr_t current; memcpy(current.l, claimed_sum->l, 32);
     std::vector<fr_t> chal;
+    // d = 2: round 0 also in the claim form, the claimed sum checked later (host/sumcheck_host.cpp explains why this is the reference's round-0
+    // check in effect): with a wrong claim the first FULL evaluation - a tail round, or the final product - disagrees with the running sum
+    const bool deferred = d == 2 && n_local > 0 && ctx->deferred_claim_check;
+    const size_t transcript_mark = tr.state_len();
+    auto claim_failed = [&]() -> int {
+        tr.truncate(transcript_mark);
+        return fail(ctx, TSGPU_E_SUMCHECK, "Round 0 consistency check failed");
+    };
     auto absorb = [&](unsigned round, const fr_t e[4], fr_t* r_out) -> int {
         fr_t coeffs[4];
         interpolate4(e, coeffs);
         fr_t g0 = horner_eval(coeffs, 4, fr_t::zero()), g1 = horner_eval(coeffs, 4, fr_t::one());
-        if (g0 + g1 != current) return fail(ctx, TSGPU_E_SUMCHECK, "Round " + std::to_string(round) + " consistency check failed");   // sumcheck.rs:77-84
+        if (g0 + g1 != current) return deferred ? claim_failed() : fail(ctx, TSGPU_E_SUMCHECK, "Round " + std::to_string(round) + " consistency check failed");   // sumcheck.rs:77-84
         for (int k = 0; k < 4; ++k) memcpy(round_polys[4 * round + k].l, coeffs[k].l, 32);
         tr.append_field_elements("sumcheck_round_" + std::to_string(round), coeffs, 4);
         fr_t r = tr.challenge_field_element("sumcheck_challenge_" + std::to_string(round));
@@ -232,9 +240,15 @@ int tsgpu_sumcheck_prove_product_sharded(tsgpu_ctx* ctx, tsgpu_table* const* tab
     // ---- rounds over the local variables
     fr_t ev[4];
     if (n_local) {
-        TSG_CUDA(ctx, launch_round_eval(d, tabs, (size_t)1 << n_local, ctx->partials, ctx->ticket, ctx->dev_out, ctx->sm_count, ctx->stream));
+        const fr_t zero = fr_t::zero();
+        TSG_CUDA(ctx, launch_round_eval(d, tabs, (size_t)1 << n_local, ctx->partials, ctx->ticket, ctx->dev_out, ctx->sm_count, ctx->stream, deferred ? &zero : nullptr));
         ctx->launches += 1;
         if ((rc = allreduce_dev_out(ctx, 4, ev))) return rc;
+        if (deferred) {                       // g(1) from the GLOBAL claim after the all-reduce, as in the later rounds
+            ev[1] = current - ev[0];
+            fr_t dd = ev[2] - ev[1];
+            ev[3] = ev[0] + dd + dd + dd;
+        }
     }
     for (unsigned round = 0; round < n_local; ++round) {
         fr_t r;
@@ -291,6 +305,7 @@ int tsgpu_sumcheck_prove_product_sharded(tsgpu_ctx* ctx, tsgpu_table* const* tab
     }
     fr_t fe = fr_t::one();
     for (int t = 0; t < d; ++t) { fe = fe * T[t][0]; if (table_finals) memcpy(table_finals[t].l, T[t][0].l, 32); }
+    if (deferred && fe != current) return claim_failed();                     // the deferred round-0 check when no tail round ran a full evaluation
     memcpy(final_evaluation->l, fe.l, 32);                                    // polynomial(&fixed_variables), sumcheck.rs:104
     if (challenges) for (size_t i = 0; i < chal.size(); ++i) memcpy(challenges[i].l, chal[i].l, 32);
     return TSGPU_OK;
