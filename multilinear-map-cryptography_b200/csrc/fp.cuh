@@ -316,6 +316,25 @@ TSG_HD void mont_reduce(uint32_t* r, const uint32_t* T) {
 }
 
 
+// r = (a b - c d) * 2^-256 mod p with ONE Montgomery reduction: the two 512-bit products are subtracted first (p * 2^256 is added back when the
+// difference is negative, which leaves the residue unchanged), so 2 x 64 + 72 multiply-adds replace the 2 x 136 of two Montgomery products.
+// Inputs < p, output < p: both products are < p^2 < p * 2^256, hence the adjusted difference is in [0, p * 2^256) as mont_reduce requires.
+template <class P>
+TSG_HD void mont_mul_sub(uint32_t* r, const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* d) {
+    uint32_t W[16], V[16];
+    mul_wide(W, a, b);
+    mul_wide(V, c, d);
+    W[0] = ptx::sub_cc(W[0], V[0]);
+#pragma unroll
+    for (int i = 1; i < 16; ++i) W[i] = ptx::subc_cc(W[i], V[i]);
+    const uint32_t borrow = ptx::subc(0u, 0u);   // 0 or 0xffffffff
+    W[8] = ptx::add_cc(W[8], P::mod(0) & borrow);
+#pragma unroll
+    for (int i = 1; i < 7; ++i) W[8 + i] = ptx::addc_cc(W[8 + i], P::mod(i) & borrow);
+    W[15] = ptx::addc(W[15], P::mod(7) & borrow);
+    mont_reduce<P>(r, W);
+}
+
 // ---- multiplication by a per-launch constant -------------------------------------------------------
 // The fold of a sum-check round multiplies every table difference by the SAME challenge r.  With the
 // eight residues  T[k] = r_canonical * 2^(32 k + 64) mod p  prepared once on the host,
@@ -489,6 +508,8 @@ struct alignas(16) fp {
     #if !defined(TSG_MUL_RADIX29)
     TSG_HD fp operator*(const fp& b) const { fp r; limb::mont_mul<P>(r.l, l, b.l); return r; }
     TSG_HD fp sqr() const { fp r; limb::mont_mul<P>(r.l, l, l); return r; }
+    // a * b - c * d with a single reduction (limb::mont_mul_sub)
+    TSG_HD static fp mul_sub(const fp& a, const fp& b, const fp& c, const fp& d) { fp r; limb::mont_mul_sub<P>(r.l, a.l, b.l, c.l, d.l); return r; }
 #else
     TSG_HD fp operator*(const fp& b) const { fp r; limb::mont_mul29<P>(r.l, l, b.l); return r; }
     TSG_HD fp sqr() const { fp r; limb::mont_mul29<P>(r.l, l, l); return r; }

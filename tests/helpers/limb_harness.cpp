@@ -55,4 +55,11 @@ extern "C" void limb_dot29(int field, const uint32_t* a, const uint32_t* b, size
         fq_t r = acc.reduce(); memcpy(out, r.l, 32);
     }
 }
+// r_i = a_i b_i - c_i d_i with one reduction (limb::mont_mul_sub)
+extern "C" void limb_mul_sub(int field, const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* d, size_t n, uint32_t* out) {
+    for (size_t i = 0; i < n; ++i) {
+        if (field == 0) limb::mont_mul_sub<FrP>(out + 8 * i, a + 8 * i, b + 8 * i, c + 8 * i, d + 8 * i);
+        else limb::mont_mul_sub<FqP>(out + 8 * i, a + 8 * i, b + 8 * i, c + 8 * i, d + 8 * i);
+    }
+}
 extern "C" void limb_mul_wide(const uint32_t* a, const uint32_t* b, uint32_t* out16) { limb::mul_wide(out16, a, b); }

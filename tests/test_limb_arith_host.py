@@ -94,3 +94,21 @@ def test_lazy_dot_product(harness, oracle, field):
     for fn in (harness.limb_dot, harness.limb_dot29):
         fn(f, _p(big), _p(big), C.c_size_t(200), _p(o))
         assert oracle.limbs_to_ints(o)[0] == 200 * (mod - 1) ** 2 * rinv % mod
+
+
+@pytest.mark.parametrize("field", ["fr", "fq"])
+def test_mul_sub_single_reduction_matches_two_products(harness, oracle, field):
+    """limb::mont_mul_sub: (a b - c d) R^-1 with ONE Montgomery reduction (the Y coordinate of the mixed point addition) equals the
+    difference of two Montgomery products, including every combination of the edge values (a b < c d, equal products, zeros, p - 1)"""
+    mod = oracle.R_MOD if field == "fr" else oracle.P_MOD
+    rnd = random.Random(5)
+    edge = [0, 1, 2, mod - 1, mod - 2, mod >> 1, (1 << 253), (1 << 128) - 1]
+    quads = [(a, b, c, d) for a in edge for b in edge[:4] for c in edge[:4] for d in edge] + [(7, 9, 9, 7), (mod - 1, mod - 1, mod - 1, mod - 1)]
+    quads += [tuple(rnd.randrange(mod) for _ in range(4)) for _ in range(3000)]
+    cols = [oracle.ints_to_limbs([q[k] for q in quads]) for k in range(4)]
+    n = len(quads)
+    out = np.empty_like(cols[0])
+    harness.limb_mul_sub(C.c_int(0 if field == "fr" else 1), _p(cols[0]), _p(cols[1]), _p(cols[2]), _p(cols[3]), C.c_size_t(n), _p(out))
+    rinv = pow(1 << 256, -1, mod)
+    want = [((a * b - c * d) * rinv) % mod for a, b, c, d in quads]
+    assert oracle.limbs_to_ints(out) == want
