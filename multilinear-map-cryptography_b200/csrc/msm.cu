@@ -257,13 +257,14 @@ __global__ void __launch_bounds__(256) k_msm_order(const unsigned* hist, const u
 }
 
 // ---------------------------------------------------------------- 3b. bucket accumulation (the hot kernel)
-// Register allocation: without a min-blocks bound ptxas settles on 104 registers (4 blocks of 128 threads per SM), which measured best:
+// Register allocation: without a min-blocks bound ptxas settles on 122 registers (4 blocks of 128 threads per SM: up to 128 registers fit four), which measured best:
 // 96 registers / 5 blocks (small spills) 4.86 ms, 80 / 6 blocks 5.00 ms, 130 / 3 blocks 5.00 ms against 4.81 ms per 2^20-op proof (-DTSG_ACC_MINB=k to try)
 #ifdef TSG_ACC_MINB
-__global__ void __launch_bounds__(MSM_ACC_THREADS, TSG_ACC_MINB) k_msm_accumulate(
+#define TSG_ACC_BOUNDS __launch_bounds__(MSM_ACC_THREADS, TSG_ACC_MINB)
 #else
-__global__ void __launch_bounds__(MSM_ACC_THREADS) k_msm_accumulate(
-#endifconst MsmBases jobs, unsigned buckets_per_job, const unsigned* sorted, const unsigned* hist, const unsigned* offsets,
+#define TSG_ACC_BOUNDS __launch_bounds__(MSM_ACC_THREADS)
+#endif
+__global__ void TSG_ACC_BOUNDS k_msm_accumulate(const MsmBases jobs, unsigned buckets_per_job, const unsigned* sorted, const unsigned* hist, const unsigned* offsets,
                                                                   const unsigned* item_off, const unsigned* item_bucket, const unsigned* n_items,
                                                                   const unsigned* order, g1_xyzz* partial) {
     const unsigned M = *n_items;
