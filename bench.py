@@ -321,9 +321,9 @@ def main():
     #    n x 16 windows x 11 Fq products x 136 IMAD = 23 936 IMAD per point of a full-width MSM; the launches that process full-width
     #    scalars are the open passes (two quotient vectors of 2^20 points each per launch), so achieved = 2 n x 23 936 / t(open-pass launch);
     #    t(open pass) = (accumulate time of the step - commit-pass share), the commit pass being timed by its own entry count at the same rate.
-    #  * `executed`: what the kernel really does - one mixed XYZZ + affine addition (8M + 2S = 10 Fq products x 136 IMAD) per bucket entry
+    #  * `executed`: what the kernel really does - one mixed XYZZ + affine addition (8M + 2S: 8 Fq products x 136 IMAD + 200 for the fused Y coordinate = 1288) per bucket entry
     #    (non-zero signed digit, counted by the library): fewer than the model because the window tables need 13 additions per point, not 16.
-    imad_per_add = 10 * (2 * 8 * 8 + 8)
+    imad_per_add = 8 * (2 * 8 * 8 + 8) + (2 * 64 + 72)     # 8 Montgomery products + the fused a b - c d of the Y coordinate (one reduction)
     survey_imad_per_point = 16 * 11 * 136
 
     def acc_roofline(r, full_width_points_per_step):
@@ -342,7 +342,7 @@ def main():
 
     roofline = acc_roofline(dflt, 2 * n)           # default path: the two opening quotients are the full-width scalars
     roofline["peak_source"] = "tools/ubench.cu on this pool: 18.5 T IMAD.WIDE/s without carry predicate (the carry-chained form the multiplier needs issues at half that rate)"
-    roofline["algorithmic_unit"] = "SURVEY 8(d): 16 windows x 11 Fq products x 136 IMAD = 23 936 IMAD per full-width point; `executed` = bucket entries x (8M + 2S) x 136 IMAD"
+    roofline["algorithmic_unit"] = "SURVEY 8(d): 16 windows x 11 Fq products x 136 IMAD = 23 936 IMAD per full-width point; `executed` = bucket entries x 1288 IMAD (8M + 2S with the Y coordinate's two products sharing one reduction)"
     # DRAM bytes per launch from `ncu --set full` of this same command (profiles/r01_ncu_accumulate_in_bench.md): commit pass 0.587 + 0.068 GB,
     # open pass 3.622 + 0.146 GB; mean over the two launches of a proof, like `launch_ms`.  Algorithmic bytes: entries x (64 B point + 4 B entry).
     roofline["traffic"] = 0.5 * ((0.586715 + 0.067997) + (3.621562 + 0.145975)) * 1e9
