@@ -316,6 +316,66 @@ TSG_HD void mont_reduce(uint32_t* r, const uint32_t* T) {
 }
 
 
+// t[0..16) = a * a: the 28 off-diagonal limb products once (doubled afterwards) + the 8 squares = 36 wide multiply-adds instead of 64.
+// Row i multiplies a_i by a_j, j > i; a product lands on limbs (i + j, i + j + 1), so the j of one parity form a contiguous carry chain that
+// starts at an odd limb (j - i odd: accumulator O) and those of the other parity one that starts at an even limb (accumulator E).  The carry
+// out of a chain goes to the next limb, which at that point holds nothing but earlier carries (rows run in increasing i).
+TSG_HD void sqr_wide(uint32_t* t, const uint32_t* a) {
+    uint32_t E[16], O[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { E[k] = 0; O[k] = 0; }
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+        {   // j = i + 1, i + 3, ...
+            O[2 * i + 1] = ptx::mad_lo_cc(a[i], a[i + 1], O[2 * i + 1]);
+            O[2 * i + 2] = ptx::madc_hi_cc(a[i], a[i + 1], O[2 * i + 2]);
+            int j = i + 3;
+#pragma unroll
+            for (; j <= 7; j += 2) {
+                O[i + j] = ptx::madc_lo_cc(a[i], a[j], O[i + j]);
+                O[i + j + 1] = ptx::madc_hi_cc(a[i], a[j], O[i + j + 1]);
+            }
+            O[i + j] = ptx::addc(O[i + j], 0u);          // i + j <= 15
+        }
+        if (i + 2 <= 7) {   // j = i + 2, i + 4, ...
+            E[2 * i + 2] = ptx::mad_lo_cc(a[i], a[i + 2], E[2 * i + 2]);
+            E[2 * i + 3] = ptx::madc_hi_cc(a[i], a[i + 2], E[2 * i + 3]);
+            int j = i + 4;
+#pragma unroll
+            for (; j <= 7; j += 2) {
+                E[i + j] = ptx::madc_lo_cc(a[i], a[j], E[i + j]);
+                E[i + j + 1] = ptx::madc_hi_cc(a[i], a[j], E[i + j + 1]);
+            }
+            E[i + j] = ptx::addc(E[i + j], 0u);          // i + j <= 14
+        }
+    }
+    // S = E + O (< 2^511), doubled, plus the diagonal
+    uint32_t s[16];
+    s[0] = ptx::add_cc(E[0], O[0]);
+#pragma unroll
+    for (int k = 1; k < 15; ++k) s[k] = ptx::addc_cc(E[k], O[k]);
+    s[15] = ptx::addc(E[15], O[15]);
+#pragma unroll
+    for (int k = 15; k > 0; --k) t[k] = (s[k] << 1) | (s[k - 1] >> 31);
+    t[0] = s[0] << 1;
+    t[0] = ptx::mad_lo_cc(a[0], a[0], t[0]);
+    t[1] = ptx::madc_hi_cc(a[0], a[0], t[1]);
+#pragma unroll
+    for (int i = 1; i < 7; ++i) {
+        t[2 * i] = ptx::madc_lo_cc(a[i], a[i], t[2 * i]);
+        t[2 * i + 1] = ptx::madc_hi_cc(a[i], a[i], t[2 * i + 1]);
+    }
+    t[14] = ptx::madc_lo_cc(a[7], a[7], t[14]);
+    t[15] = ptx::madc_hi(a[7], a[7], t[15]);
+}
+// r = a^2 * 2^-256 mod p: 36 + 72 multiply-adds instead of 136 (a^2 < p^2 < p * 2^256 as mont_reduce requires)
+template <class P>
+TSG_HD void mont_sqr(uint32_t* r, const uint32_t* a) {
+    uint32_t t[16];
+    sqr_wide(t, a);
+    mont_reduce<P>(r, t);
+}
+
 // r = (a b - c d) * 2^-256 mod p with ONE Montgomery reduction: the two 512-bit products are subtracted first (p * 2^256 is added back when the
 // difference is negative, which leaves the residue unchanged), so 2 x 64 + 72 multiply-adds replace the 2 x 136 of two Montgomery products.
 // Inputs < p, output < p: both products are < p^2 < p * 2^256, hence the adjusted difference is in [0, p * 2^256) as mont_reduce requires.
@@ -507,7 +567,12 @@ struct alignas(16) fp {
     TSG_HD fp operator-(const fp& b) const { fp r; limb::sub<P>(r.l, l, b.l); return r; }
     #if !defined(TSG_MUL_RADIX29)
     TSG_HD fp operator*(const fp& b) const { fp r; limb::mont_mul<P>(r.l, l, b.l); return r; }
+#ifdef TSG_FAST_SQR
+    TSG_HD fp sqr() const { fp r; limb::mont_sqr<P>(r.l, l); return r; }
+#else
     TSG_HD fp sqr() const { fp r; limb::mont_mul<P>(r.l, l, l); return r; }
+#endif
+    TSG_HD fp sqr_dedicated() const { fp r; limb::mont_sqr<P>(r.l, l); return r; }
     // a * b - c * d with a single reduction (limb::mont_mul_sub)
     TSG_HD static fp mul_sub(const fp& a, const fp& b, const fp& c, const fp& d) { fp r; limb::mont_mul_sub<P>(r.l, a.l, b.l, c.l, d.l); return r; }
 #else

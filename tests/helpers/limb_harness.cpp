@@ -22,7 +22,8 @@ static void binop(int op, const uint32_t* a, const uint32_t* b, size_t n, uint32
             case 7: r = x.neg(); break;
             case 8: limb::mont_mul<P>(r.l, x.l, y.l); break;
             case 9: limb::mont_mul29<P>(r.l, x.l, y.l); break;
-            case 10: r = fp_ctab<P>::make(y).mul(x); break;   // constant-multiplier table of y applied to x
+            case 10: r = fp_ctab<P>::make(y).mul(x); break;
+            case 11: r = x.sqr_dedicated(); break;                // 36 + 72 multiply-adds (limb::mont_sqr)   // constant-multiplier table of y applied to x
             default: r = fp<P>::zero();
         }
         memcpy(out + 8 * i, r.l, 32);

@@ -112,3 +112,15 @@ def test_mul_sub_single_reduction_matches_two_products(harness, oracle, field):
     rinv = pow(1 << 256, -1, mod)
     want = [((a * b - c * d) * rinv) % mod for a, b, c, d in quads]
     assert oracle.limbs_to_ints(out) == want
+
+
+@pytest.mark.parametrize("field", ["fr", "fq"])
+def test_dedicated_squaring_matches_product(harness, oracle, field):
+    """limb::mont_sqr (28 doubled off-diagonal products + 8 squares, then one reduction) == a * a * R^-1"""
+    mod = oracle.R_MOD if field == "fr" else oracle.P_MOD
+    xs, _ = _cases(mod, 6000, 21)
+    xs += [(1 << 256) % mod, mod - 3, 0xFFFFFFFF, 0xFFFFFFFF << 32, ((1 << 254) - 1) % mod] + [((1 << k) - 1) % mod for k in range(1, 255, 7)]
+    a = oracle.ints_to_limbs(xs); out = np.empty_like(a)
+    harness.limb_binop(C.c_int(0 if field == "fr" else 1), C.c_int(11), _p(a), _p(a), C.c_size_t(len(xs)), _p(out))
+    rinv = pow(1 << 256, -1, mod)
+    assert oracle.limbs_to_ints(out) == [x * x * rinv % mod for x in xs]
