@@ -15,10 +15,10 @@ use ark_ff::{One, Zero};
 use std::ffi::CStr;
 use std::os::raw::c_int;
 use std::ptr;
-use twist_and_shout::commitments::{CommitmentParams, CommitmentScheme, CommitmentVerificationKey, KZGCommitment, KZGCommitmentValue, KZGProof};
+use twist_and_shout::commitments::{CommitmentScheme, KZGCommitment, KZGCommitmentValue, KZGProof};
 use twist_and_shout::polynomials::{poly_utils, MultilinearExtension};
 use twist_and_shout::sumcheck::{SumCheck, SumCheckProof};
-use twist_and_shout::utils::{field_utils, ProverParams, Transcript, VerifierParams};
+use twist_and_shout::utils::{field_utils, CommitmentParams, CommitmentVerificationKey, ProverParams, Transcript, VerifierParams};   // the two commitment structs live in utils.rs:52-76
 use twist_and_shout::{LookupTable, MemoryOp, MemoryTrace, Result, ShoutProof, TwistAndShoutError, TwistProof};
 
 // layout contract of the boundary (ark-ff / ark-ec 0.4.2): no conversion on either side
@@ -153,7 +153,7 @@ pub fn sumcheck_prove_product(ctx: &Context, sc: &SumCheck, tables: &[Multilinea
     }
     let mut raw_sc = ptr::null_mut();
     if let Err(e) = ctx.check(unsafe { ffi::tsgpu_sc_begin(ctx.raw, handles.as_ptr(), handles.len() as c_int, &mut raw_sc) }) { free_all(&handles); return Err(e); }
-    let result = (|| {
+    let result = (|| -> Result<SumCheckProof> {
         let xs: Vec<Fr> = (0..4u64).map(Fr::from).collect();
         let mut round_polynomials = Vec::with_capacity(sc.num_vars);
         let mut current_sum = sc.claimed_sum;
