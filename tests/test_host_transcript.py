@@ -63,3 +63,34 @@ def test_g1_host_helpers_match_oracle(tsgpu, oracle):
     assert tsgpu.g1_compress(g).hex() == "01" + "00" * 31            # 1*G = (1, 2)
     assert tsgpu.g1_equal(pts[1], oracle.g1_mul(g, oracle.fr_from_ints([2])[0]))
     assert not tsgpu.g1_equal(pts[1], pts[2])
+
+
+def test_transcript_long_session_covers_rejections_and_growing_state(tsgpu, oracle):
+    """500 challenges over a state that grows to ~36 KB: Fp::rand rejects a draw with probability ~1/4, so runs of 3+ rejections (ChaCha blocks
+    generated on demand beyond the first, host/transcript.hpp) and every state length modulo 8 (the word-wise SipHash tail) occur."""
+    a, b = tsgpu.Transcript(), oracle.Transcript()
+    xs = oracle.chacha_fr_rand(seed_bytes(9), 4).reshape(4, 4)
+    for i in range(500):
+        label = b"r" * (i % 11)
+        a.append_field_elements(label, xs[: i % 5]); b.append_field_elements(label, xs[: i % 5])
+        assert (a.challenge_field_element(b"c%d" % i) == b.challenge_field_element(b"c%d" % i)).all(), i
+    assert a.state_len > 30000
+
+
+def test_less_than_on_field_elements_host(tsgpu, oracle):
+    """LessThanPolynomial::evaluate_at_field_elements (src/polynomials.rs:213-220, :266-283): the low num_vars bits of the canonical integers,
+    first differing bit from bit 0 decides; host-only entry point"""
+    rng = np.random.default_rng(3)
+    for nv in (1, 3, 8, 64, 70, 254):
+        lt = tsgpu.LessThanPolynomial.new(nv)
+        for _ in range(40):
+            x, y = int(rng.integers(0, 1 << 62)) << int(rng.integers(0, 190)), int(rng.integers(0, 1 << 62)) << int(rng.integers(0, 190))
+            x %= oracle.R_MOD; y %= oracle.R_MOD
+            want = 0
+            for i in range(nv):
+                bx, by = (x >> i) & 1, (y >> i) & 1
+                if bx != by:
+                    want = 1 if by else 0
+                    break
+            got = lt.evaluate_at_field_elements(oracle.fr_from_ints([x])[0], oracle.fr_from_ints([y])[0])
+            assert oracle.fr_to_ints(got) == [want]
