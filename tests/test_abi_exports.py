@@ -60,3 +60,17 @@ def test_reference_arm_prints_one_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and d["vs_baseline"] is None and d["gpu_launches"] == 0
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/tsgpu.h is the drop-in boundary: it must compile as C99 (and as C++) on its own, and a C program must link against libtsgpu.so"""
+    import subprocess
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "tsgpu.h"\nint main(void) { return tsgpu_abi_version() == 1 ? 0 : 1; }\n')
+    inc = os.path.join(ROOT, "include")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-fsyntax-only", str(src)])
+    subprocess.check_call(["g++", "-std=c++11", "-Wall", "-Werror", "-I", inc, "-fsyntax-only", "-x", "c++", str(src)])
+    libdir = os.path.join(ROOT, "multilinear-map-cryptography_b200")
+    exe = tmp_path / "hdr"
+    subprocess.check_call(["gcc", "-std=c99", "-I", inc, str(src), "-o", str(exe), "-L", libdir, "-ltsgpu", "-Wl,-rpath," + libdir])
+    assert subprocess.call([str(exe)]) == 0
