@@ -74,3 +74,33 @@ def test_header_is_plain_c(tmp_path):
     exe = tmp_path / "hdr"
     subprocess.check_call(["gcc", "-std=c99", "-I", inc, str(src), "-o", str(exe), "-L", libdir, "-ltsgpu", "-Wl,-rpath," + libdir])
     assert subprocess.call([str(exe)]) == 0
+
+
+def _build_demo(tmp_path):
+    import subprocess
+    libdir = os.path.join(ROOT, "multilinear-map-cryptography_b200")
+    exe = tmp_path / "demo"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "demo.c"),
+                           "-o", str(exe), "-L", libdir, "-ltsgpu", "-Wl,-rpath," + libdir])
+    return str(exe)
+
+
+def test_c_demo_builds_and_fails_loudly_without_a_gpu(tmp_path):
+    """examples/demo.c (the reference's examples/demo.rs over the C ABI) compiles warning-free; without a CUDA device it stops at tsgpu_init"""
+    import subprocess
+    import torch
+    exe = _build_demo(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: see test_c_demo_on_gpu")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 1 and "tsgpu_init failed (2)" in r.stderr
+
+
+@pytest.mark.gpu
+def test_c_demo_on_gpu(tmp_path):
+    """the C demo proves and verifies the reference's demo trace and lookup table, and reports the reference's limit error"""
+    import subprocess
+    r = subprocess.run([_build_demo(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "Twist::verify -> true" in r.stdout and "Shout::verify -> true" in r.stdout
+    assert "error 1: Too many operations" in r.stdout
