@@ -45,7 +45,7 @@ def test_integration__full_memory_consistency_workflow(ts, ctx):
     trace.write(0, F(ts, 43)); trace.write(3, F(ts, 300))
     assert eq(trace.read(0), F(ts, 43)) and eq(trace.read(3), F(ts, 300))
     _, ok, _, _ = prove_verify_twist(ts, ctx, 3, trace)
-    assert ok, "Full memory workflow should produce valid proof"
+    assert ok
 
 
 @pytest.mark.gpu
@@ -54,7 +54,7 @@ def test_integration__full_lookup_workflow(ts, ctx):
     for i, sq in ((3, 9), (5, 25), (0, 0), (7, 49)):
         assert eq(table.lookup(i), F(ts, sq))
     _, ok = prove_verify_shout(ts, ctx, 3, table)
-    assert ok, "Full lookup workflow should produce valid proof"
+    assert ok
 
 
 @pytest.mark.gpu
@@ -64,8 +64,8 @@ def test_integration__commitment_scheme_integration(ts, ctx):
     commitment = ts.KZGCommitment.commit(pp.srs, poly)
     for x in (0, 1, 2, 5):
         value, proof = ts.KZGCommitment.open(pp.srs, poly, F(ts, x))
-        assert ts.kzg_verify(vp, commitment, F(ts, x), value, proof), f"KZG opening should be valid for point {x}"
-        assert ts.fe_to_int(value) == 1 + 2 * x + 3 * x * x, "Opened value should match polynomial evaluation"
+        assert ts.kzg_verify(vp, commitment, F(ts, x), value, proof)
+        assert ts.fe_to_int(value) == 1 + 2 * x + 3 * x * x
 
 
 @pytest.mark.gpu
@@ -81,8 +81,8 @@ def test_integration__combined_twist_and_shout(ts, ctx):
     assert eq(memory.read(2), F(ts, 100))
     opcodes.lookup(7)
     twist, shout = ts.Twist.new(pp), ts.Shout.new(pp)
-    assert twist.verify(twist.prove(memory), vp), "Memory consistency proof should be valid"
-    assert shout.verify(shout.prove(opcodes), vp), "Opcode lookup proof should be valid"
+    assert twist.verify(twist.prove(memory), vp)
+    assert shout.verify(shout.prove(opcodes), vp)
 
 
 @pytest.mark.gpu
@@ -95,7 +95,7 @@ def test_integration__polynomial_commitment_consistency(ts, ctx):
     coeffs = ts.poly_utils.lagrange_interpolate(ctx, [(F(ts, i), ev[i]) for i in range(ev.shape[0])])
     commitment = ts.KZGCommitment.commit(pp.srs, coeffs)
     value, proof = ts.KZGCommitment.open(pp.srs, coeffs, F(ts, 10))
-    assert ts.kzg_verify(vp, commitment, F(ts, 10), value, proof), "Polynomial commitment opening should be valid"
+    assert ts.kzg_verify(vp, commitment, F(ts, 10), value, proof)
     mle.evaluate(np.stack([fixed[0], fixed[1], F(ts, 10)]))
 
 
@@ -106,7 +106,7 @@ def test_integration__parameter_compatibility(ts, ctx):
     poly = ts.fe_vec([1, 2])
     commitment = ts.KZGCommitment.commit(pp.srs, poly)
     value, proof = ts.KZGCommitment.open(pp.srs, poly, F(ts, 5))
-    assert ts.kzg_verify(vp, commitment, F(ts, 5), value, proof), "Prover and verifier parameters should be compatible"
+    assert ts.kzg_verify(vp, commitment, F(ts, 5), value, proof)
 
 
 def _sumcheck_x1_times_x2(ts, ctx):
@@ -120,7 +120,7 @@ def _sumcheck_x1_times_x2(ts, ctx):
 
 @pytest.mark.gpu
 def test_integration__sumcheck_protocol_basic(ts, ctx):
-    assert _sumcheck_x1_times_x2(ts, ctx), "Sum-check proof should be valid"
+    assert _sumcheck_x1_times_x2(ts, ctx)
 
 
 @pytest.mark.gpu
@@ -270,8 +270,8 @@ def test_production__twist_with_opening_proofs(ts, ctx):
     trace.write(0, F(ts, 999)); trace.write(1, F(ts, 888))
     assert eq(trace.read(0), F(ts, 999)) and eq(trace.read(1), F(ts, 888))
     proof, ok, _, _ = prove_verify_twist(ts, ctx, 4, trace)
-    assert ok, "Production Twist proof should be valid"
-    assert proof.round_polynomials.shape[0] > 0, "Should have sum-check rounds"
+    assert ok
+    assert proof.round_polynomials.shape[0] > 0
 
 
 @pytest.mark.gpu
@@ -280,8 +280,8 @@ def test_production__shout_with_opening_proofs(ts, ctx):
     for i in (0, 2, 4, 1, 3):
         table.lookup(i)
     proof, ok = prove_verify_shout(ts, ctx, 4, table)
-    assert ok, "Production Shout proof should be valid"
-    assert proof.round_polynomials.shape[0] > 0, "Should have sum-check rounds"
+    assert ok
+    assert proof.round_polynomials.shape[0] > 0
 
 
 @pytest.mark.gpu
@@ -292,7 +292,7 @@ def test_production__twist_with_multilinear_extensions(ts, ctx):
     for i in reversed(range(8)):
         trace.read(i)
     proof, ok, _, _ = prove_verify_twist(ts, ctx, 3, trace)
-    assert ok, "Production Twist proof with MLE should be valid"
+    assert ok
     assert proof.round_polynomials.shape[0] == 4                                   # 16 operations -> log_ops = 4
 
 
@@ -301,11 +301,11 @@ def test_production__shout_edge_cases(ts, ctx):
     pp, vp = ts.setup_params(ctx, 2)
     shout = ts.Shout.new(pp)
     small = ts.LookupTable.new(ts.fe_vec([123])); small.lookup(0)
-    assert shout.verify(shout.prove(small), vp), "Single entry lookup should be valid"
+    assert shout.verify(shout.prove(small), vp)
     rep = ts.LookupTable.new(ts.fe_vec([456, 789]))
     for i in (0, 0, 1, 0):
         rep.lookup(i)
-    assert shout.verify(shout.prove(rep), vp), "Repeated lookups should be valid"
+    assert shout.verify(shout.prove(rep), vp)
 
 
 @pytest.mark.gpu
@@ -360,37 +360,37 @@ def _shout_case(ts, ctx, log_size, entries, lookups):
 
 @pytest.mark.gpu
 def test_shout__protocol_basic_lookup(ts, ctx):
-    assert _shout_case(ts, ctx, 3, [100, 200, 300, 400], [0, 2, 3, 1]), "Shout proof should be valid for correct lookups"
+    assert _shout_case(ts, ctx, 3, [100, 200, 300, 400], [0, 2, 3, 1])
 
 
 @pytest.mark.gpu
 def test_shout__protocol_no_lookups(ts, ctx):
-    assert _shout_case(ts, ctx, 2, [10, 20, 30, 40], []), "Table with no lookups should have valid proof"
+    assert _shout_case(ts, ctx, 2, [10, 20, 30, 40], [])
 
 
 @pytest.mark.gpu
 def test_shout__protocol_single_lookup(ts, ctx):
-    assert _shout_case(ts, ctx, 2, [1000, 2000], [1]), "Single lookup should have valid proof"
+    assert _shout_case(ts, ctx, 2, [1000, 2000], [1])
 
 
 @pytest.mark.gpu
 def test_shout__protocol_repeated_lookups(ts, ctx):
-    assert _shout_case(ts, ctx, 2, [111, 222, 333], [0, 0, 1, 0, 2, 1]), "Repeated lookups should have valid proof"
+    assert _shout_case(ts, ctx, 2, [111, 222, 333], [0, 0, 1, 0, 2, 1])
 
 
 @pytest.mark.gpu
 def test_shout__protocol_all_indices(ts, ctx):
-    assert _shout_case(ts, ctx, 2, [10, 20, 30, 40], range(4)), "Lookup of all indices should have valid proof"
+    assert _shout_case(ts, ctx, 2, [10, 20, 30, 40], range(4))
 
 
 @pytest.mark.gpu
 def test_shout__protocol_reverse_order(ts, ctx):
-    assert _shout_case(ts, ctx, 2, [100, 200, 300, 400], reversed(range(4))), "Reverse order lookups should have valid proof"
+    assert _shout_case(ts, ctx, 2, [100, 200, 300, 400], reversed(range(4)))
 
 
 @pytest.mark.gpu
 def test_shout__protocol_large_table(ts, ctx):
-    assert _shout_case(ts, ctx, 4, [i * 10 for i in range(16)], [0, 5, 10, 15, 2, 8, 1, 14]), "Large table lookups should have valid proof"
+    assert _shout_case(ts, ctx, 4, [i * 10 for i in range(16)], [0, 5, 10, 15, 2, 8, 1, 14])
 
 
 @pytest.mark.gpu
@@ -409,14 +409,12 @@ def test_shout__lookup_op_structure(ts):
 
 @pytest.mark.gpu
 def test_shout__protocol_zero_values(ts, ctx):
-    assert _shout_case(ts, ctx, 2, [0, 100, 0, 200], [0, 1, 2, 3]), "Lookups with zero values should have valid proof"
+    assert _shout_case(ts, ctx, 2, [0, 100, 0, 200], [0, 1, 2, 3])
 
 
 @pytest.mark.gpu
 def test_shout__protocol_duplicate_values(ts, ctx):
-    assert _shout_case(ts, ctx, 2, [100, 200, 100, 300], [0, 2, 1]), "Lookups with duplicate values should have valid proof"
-
-
+    assert _shout_case(ts, ctx, 2, [100, 200, 100, 300], [0, 2, 1])
 # ================================================================================================ tests/twist_tests.rs
 def test_twist__memory_trace_basic_operations(ts):
     trace = ts.MemoryTrace.new(16)
@@ -450,32 +448,32 @@ def _twist_case(ts, ctx, log_size, cells, ops):
 
 @pytest.mark.gpu
 def test_twist__protocol_small_trace(ts, ctx):
-    assert _twist_case(ts, ctx, 3, 8, [("W", 0, 10), ("W", 1, 20), ("R", 0), ("W", 2, 30), ("R", 1), ("R", 2)]), "Twist proof should be valid for correct memory trace"
+    assert _twist_case(ts, ctx, 3, 8, [("W", 0, 10), ("W", 1, 20), ("R", 0), ("W", 2, 30), ("R", 1), ("R", 2)])
 
 
 @pytest.mark.gpu
 def test_twist__protocol_empty_trace(ts, ctx):
-    assert _twist_case(ts, ctx, 2, 4, []), "Empty memory trace should have valid proof"
+    assert _twist_case(ts, ctx, 2, 4, [])
 
 
 @pytest.mark.gpu
 def test_twist__protocol_only_reads(ts, ctx):
-    assert _twist_case(ts, ctx, 2, 4, [("R", i) for i in range(4)]), "Read-only trace should have valid proof"
+    assert _twist_case(ts, ctx, 2, 4, [("R", i) for i in range(4)])
 
 
 @pytest.mark.gpu
 def test_twist__protocol_only_writes(ts, ctx):
-    assert _twist_case(ts, ctx, 2, 4, [("W", i, i + 1) for i in range(4)]), "Write-only trace should have valid proof"
+    assert _twist_case(ts, ctx, 2, 4, [("W", i, i + 1) for i in range(4)])
 
 
 @pytest.mark.gpu
 def test_twist__protocol_repeated_operations(ts, ctx):
-    assert _twist_case(ts, ctx, 2, 4, [("W", 0, 100), ("R", 0), ("W", 0, 200), ("R", 0), ("W", 0, 300), ("R", 0)]), "Trace with repeated operations should have valid proof"
+    assert _twist_case(ts, ctx, 2, 4, [("W", 0, 100), ("R", 0), ("W", 0, 200), ("R", 0), ("W", 0, 300), ("R", 0)])
 
 
 @pytest.mark.gpu
 def test_twist__protocol_max_operations(ts, ctx):
-    assert _twist_case(ts, ctx, 2, 4, [("W", i % 4, i + 1) for i in range(15)]), "Trace at operation limit should have valid proof"
+    assert _twist_case(ts, ctx, 2, 4, [("W", i % 4, i + 1) for i in range(15)])
 
 
 @pytest.mark.gpu
