@@ -413,3 +413,85 @@ def shout_prove(powers_jac: np.ndarray, max_operations: int, entries_mont: np.nd
     if rc:
         raise ProveError(rc)
     return out[:ln.value].tobytes(), z
+
+
+# ----------------------------------------------------------------- the real constraint sum-checks (non-parity mode of the product)
+# The reference's Twist / Shout closures return zero (src/twist.rs:181-214, src/shout.rs:157-184).  The product offers, beside the
+# byte-identical prove, the sum-checks those stubs stand for (host/read_check.cpp, host/memory_check.cpp).  Their CPU restatement is the
+# reference's own SumCheck::prove (orc_sumcheck_prove_product: closure form or table form) applied to tables built here with Python integers.
+def _eq_ints(pt: np.ndarray) -> List[int]:
+    return fr_to_ints(eq_table(pt.reshape(-1, 4))) if pt.shape[0] else [1]
+
+
+def lt_point_ints(b_ints: Sequence[int], t: int) -> List[int]:
+    """[LT~(a, b) for a in range(2^t)]: [a < c] in the natural integer order, multilinear in c, at the field point b (t canonical integers)"""
+    p = R_MOD
+    out = []
+    for a in range(1 << t):
+        prefix, acc = 1, 0
+        for i in range(t - 1, -1, -1):
+            bi = b_ints[i]
+            if (a >> i) & 1:
+                prefix = prefix * bi % p
+            else:
+                acc = (acc + prefix * bi) % p
+                prefix = prefix * (1 - bi) % p
+        out.append(acc)
+    return out
+
+
+def shout_read_check_prove(entries: np.ndarray, idx: np.ndarray, vals: np.ndarray, mode: str = "tables"):
+    """core Shout read-checking rv~(r) = sum_x ra~(x, r) Val~(x) on a fresh transcript -> (claim, sum-check result dict)"""
+    p = R_MOD
+    nent, nlook = entries.shape[0], idx.shape[0]
+    K = 1 << max(nent - 1, 0).bit_length(); L = 1 << max(nlook - 1, 0).bit_length()
+    l = L.bit_length() - 1
+    tr = Transcript()
+    r = tr.challenge_field_elements(b"read_check_point", l)
+    eq = _eq_ints(r)
+    vi = fr_to_ints(vals) if nlook else []
+    claim = sum(e * v for e, v in zip(eq, vi)) % p
+    claim_fr = fr_from_ints([claim])[0]
+    tr.append_field_element(b"read_check_claim", claim_fr)
+    A = [0] * K
+    for j in range(nlook):
+        A[int(idx[j])] = (A[int(idx[j])] + eq[j]) % p
+    V = fr_to_ints(entries) + [0] * (K - nent)
+    return claim_fr, sumcheck_prove_product([fr_from_ints(A), fr_from_ints(V)], claim_fr, transcript=tr, mode=mode)
+
+
+def twist_memory_check_prove(addr: np.ndarray, vals: np.ndarray, isw: np.ndarray, K: int, mode: str = "tables"):
+    """Twist read-checking over (cell, cycle) + Val-evaluation on a fresh transcript -> (read claim, Val~(x*, j*), part 1, part 2)"""
+    p = R_MOD
+    n = addr.shape[0]
+    T = 1 << max(n - 1, 0).bit_length()
+    k, t = K.bit_length() - 1, T.bit_length() - 1
+    vi = fr_to_ints(vals) if n else []
+    tr = Transcript()
+    r = tr.challenge_field_elements(b"memory_check_point", t)
+    eq = _eq_ints(r)
+    claim1 = sum(eq[j] * vi[j] for j in range(n) if not isw[j]) % p
+    claim1_fr = fr_from_ints([claim1])[0]
+    tr.append_field_element(b"memory_read_claim", claim1_fr)
+    RA = [0] * (K * T); VAL = [0] * (K * T)          # tables over index x + K j
+    mem = [0] * K; inc = [0] * T
+    for j in range(T):
+        for x in range(K):
+            VAL[x + K * j] = mem[x]
+        if j < n:
+            a = int(addr[j])
+            if isw[j]:
+                inc[j] = (vi[j] - mem[a]) % p
+                mem[a] = vi[j]
+            else:
+                RA[a + K * j] = eq[j]
+    ref1 = sumcheck_prove_product([fr_from_ints(RA), fr_from_ints(VAL)], claim1_fr, transcript=tr, mode=mode)
+    ch = ref1["challenges"].reshape(-1, 4)
+    val_claim = mle_evaluate(fr_from_ints(VAL), ch, fold=(mode == "tables")).reshape(4)   # Val~(x*, j*): MultilinearExtension::evaluate
+    tr.append_field_element(b"memory_val_claim", val_claim)
+    x_star, j_star = ch[:k], ch[k:]
+    eqx = _eq_ints(x_star)
+    U = [inc[j] * eqx[int(addr[j])] % p if j < n else 0 for j in range(T)]
+    V = lt_point_ints(fr_to_ints(j_star) if t else [], t)
+    ref2 = sumcheck_prove_product([fr_from_ints(U), fr_from_ints(V)], val_claim, transcript=tr, mode=mode)
+    return claim1_fr, val_claim, ref1, ref2

@@ -27,60 +27,16 @@ def _trace(oracle, tsgpu, K, n, seed, wide=False):
 
 
 def _eq_ints(oracle, pt):
-    return oracle.fr_to_ints(oracle.eq_table(pt.reshape(-1, 4))) if pt.shape[0] else [1]
+    return oracle._eq_ints(pt)
 
 
 def _lt_point_ints(oracle, b_ints, t, p):
-    out = []
-    for a in range(1 << t):
-        prefix, acc = 1, 0
-        for i in range(t - 1, -1, -1):
-            bi = b_ints[i]
-            if (a >> i) & 1:
-                prefix = prefix * bi % p
-            else:
-                acc = (acc + prefix * bi) % p
-                prefix = prefix * (1 - bi) % p
-        out.append(acc)
-    return out
+    return oracle.lt_point_ints(b_ints, t)
 
 
 def _oracle_memory_check(oracle, addr, vals, isw, K, mode):
-    """host/memory_check.cpp restated with oracle primitives and Python integers"""
-    p = oracle.R_MOD
-    n = addr.shape[0]
-    T = 1 << max(n - 1, 0).bit_length()
-    k, t = K.bit_length() - 1, T.bit_length() - 1
-    vi = oracle.fr_to_ints(vals) if n else []
-    tr = oracle.Transcript()
-    r = tr.challenge_field_elements(b"memory_check_point", t)
-    eq = _eq_ints(oracle, r)
-    claim1 = sum(eq[j] * vi[j] for j in range(n) if not isw[j]) % p
-    claim1_fr = oracle.fr_from_ints([claim1])[0]
-    tr.append_field_element(b"memory_read_claim", claim1_fr)
-    # tables over index x + K j
-    RA = [0] * (K * T); VAL = [0] * (K * T)
-    mem = [0] * K; inc = [0] * T
-    for j in range(T):
-        for x in range(K):
-            VAL[x + K * j] = mem[x]
-        if j < n:
-            a = int(addr[j])
-            if isw[j]:
-                inc[j] = (vi[j] - mem[a]) % p
-                mem[a] = vi[j]
-            else:
-                RA[a + K * j] = eq[j]
-    ref1 = oracle.sumcheck_prove_product([oracle.fr_from_ints(RA), oracle.fr_from_ints(VAL)], claim1_fr, transcript=tr, mode=mode)
-    ch = ref1["challenges"].reshape(-1, 4)
-    val_claim = oracle.mle_evaluate(oracle.fr_from_ints(VAL), ch, fold=(mode == "tables")).reshape(4)   # Val~(x*, j*): MultilinearExtension::evaluate
-    tr.append_field_element(b"memory_val_claim", val_claim)
-    x_star, j_star = ch[:k], ch[k:]
-    eqx = _eq_ints(oracle, x_star)
-    U = [inc[j] * eqx[int(addr[j])] % p if j < n else 0 for j in range(T)]
-    V = _lt_point_ints(oracle, oracle.fr_to_ints(j_star) if t else [], t, p)
-    ref2 = oracle.sumcheck_prove_product([oracle.fr_from_ints(U), oracle.fr_from_ints(V)], val_claim, transcript=tr, mode=mode)
-    return claim1_fr, val_claim, ref1, ref2
+    """host/memory_check.cpp restated with oracle primitives and Python integers (oracle/oracle.py: twist_memory_check_prove)"""
+    return oracle.twist_memory_check_prove(addr, vals, isw, K, mode)
 
 
 @pytest.mark.parametrize("K,n,mode", [(1, 1, "closure"), (2, 2, "closure"), (4, 3, "closure"), (2, 8, "closure"), (8, 6, "closure"),

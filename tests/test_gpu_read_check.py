@@ -18,24 +18,8 @@ def _statement(oracle, tsgpu, nent, nlook, seed, wide=True):
 
 
 def _oracle_read_check(oracle, entries, idx, vals, mode):
-    """the protocol of host/read_check.cpp restated with oracle primitives (Transcript, eq table, SumCheck::prove)"""
-    p = oracle.R_MOD
-    nent, nlook = entries.shape[0], idx.shape[0]
-    K = 1 << max(nent - 1, 0).bit_length(); L = 1 << max(nlook - 1, 0).bit_length()
-    k, l = K.bit_length() - 1, L.bit_length() - 1
-    tr = oracle.Transcript()
-    r = tr.challenge_field_elements(b"read_check_point", l)
-    eq = oracle.fr_to_ints(oracle.eq_table(r.reshape(l, 4))) if l else [1]
-    vi = oracle.fr_to_ints(vals) if nlook else []
-    claim = sum(e * v for e, v in zip(eq, vi)) % p
-    claim_fr = oracle.fr_from_ints([claim])[0]
-    tr.append_field_element(b"read_check_claim", claim_fr)
-    A = [0] * K
-    for j in range(nlook):
-        A[int(idx[j])] = (A[int(idx[j])] + eq[j]) % p
-    V = oracle.fr_to_ints(entries) + [0] * (K - nent)
-    ref = oracle.sumcheck_prove_product([oracle.fr_from_ints(A), oracle.fr_from_ints(V)], claim_fr, transcript=tr, mode=mode)
-    return claim_fr, ref
+    """the protocol of host/read_check.cpp restated with oracle primitives (oracle/oracle.py: shout_read_check_prove)"""
+    return oracle.shout_read_check_prove(entries, idx, vals, mode)
 
 
 @pytest.mark.parametrize("nent,nlook,mode", [(1, 1, "closure"), (2, 1, "closure"), (3, 4, "closure"), (8, 5, "closure"), (16, 37, "closure"),
