@@ -115,3 +115,31 @@ def test_fast_tier_equals_verbatim_tier(oracle):
     b1, _ = oracle.twist_prove(pw, 512, addr, vals, isw, fast=False)
     b2, _ = oracle.twist_prove(pw, 512, addr, vals, isw, fast=True)
     assert b1 == b2
+
+
+def test_constraint_sumchecks_are_consistent_on_the_reference_sumcheck(oracle):
+    """The identities behind the non-parity constraint mode, checked by the reference's own SumCheck::prove (closure form: every round's
+    g(0) + g(1) check, src/sumcheck.rs:77-84): rv~(r) = sum_x ra~(x, r) Val~(x) for lookups, and for memory
+    sum_j eq(r, j)[read_j] v_j = sum_{x,j} eq(r, j)[read_j] ra(x, j) Val(x, j) together with Val~(x*, j*) = sum_j' Inc_j' eq(x*, a_j') LT~(j', j*).
+    A wrong returned value must break round 0."""
+    rng = np.random.default_rng(11)
+    entries = oracle.chacha_fr_rand(bytes([3]) * 32, 8).reshape(8, 4)
+    idx = rng.integers(0, 8, size=5).astype(np.uint64)
+    vals = entries[idx.astype(np.int64)]
+    claim, ref = oracle.shout_read_check_prove(entries, idx, vals, mode="closure")
+    assert ref["round_polynomials"].shape == (3, 4, 4) and ref["round_polynomials"].any()
+    bad = vals.copy(); bad[2] = entries[(int(idx[2]) + 1) % 8]
+    with pytest.raises(oracle.SumCheckError):
+        oracle.shout_read_check_prove(entries, idx, bad, mode="closure")
+    # memory: 4 cells, W(0,a) W(1,b) R(0) W(0,c) R(0) R(1) R(3)
+    v = oracle.fr_to_ints(oracle.chacha_fr_rand(bytes([4]) * 32, 3))
+    addr = np.array([0, 1, 0, 0, 0, 1, 3], dtype=np.uint64)
+    isw = np.array([1, 1, 0, 1, 0, 0, 0], dtype=np.uint8)
+    mvals = oracle.fr_from_ints([v[0], v[1], v[0], v[2], v[2], v[1], 0])
+    c1, c2, r1, r2 = oracle.twist_memory_check_prove(addr, mvals, isw, 4, mode="closure")
+    assert r1["round_polynomials"].shape == (5, 4, 4) and r2["round_polynomials"].shape == (3, 4, 4)
+    wrong = oracle.fr_from_ints([v[0], v[1], v[0], v[2], v[0], v[1], 0])          # the second read of cell 0 returns the overwritten value
+    with pytest.raises(oracle.SumCheckError):
+        oracle.twist_memory_check_prove(addr, wrong, isw, 4, mode="closure")
+    # LT~ at a boolean point is the indicator of the natural order
+    assert oracle.lt_point_ints([1, 0, 1], 3) == [1 if a < 5 else 0 for a in range(8)]
