@@ -342,8 +342,9 @@ int tsgpu_table_lt_point(tsgpu_ctx* ctx, const tsgpu_fr* point, unsigned num_var
  * and says "In a production implementation, this would involve more complex constraints").  NOT part of the reference's proofs - a
  * separate, explicitly non-parity mode; Shout::prove above stays byte-identical to the reference.
  * Statement: lookup j < num_lookups reads entries[lookup_indices[j]] and returns lookup_values[j] (LookupOp { index, value }).
- * Protocol (core Shout read-checking): r = transcript.challenge_field_elements("read_check_point", log2 L) with L the padded number
- * of lookups; claim = rv~(r), the multilinear extension of the returned values, appended as "read_check_claim"; then
+ * Protocol (core Shout read-checking): the statement is bound first - a BLAKE2b-256 tree digest of (sizes, entries, indices, values)
+ * (host/statement_digest.hpp) is appended as two field elements under "read_check_statement", so that every challenge depends on the
+ * whole statement; then r = transcript.challenge_field_elements("read_check_point", log2 L) with L the padded number of lookups; claim = rv~(r), the multilinear extension of the returned values, appended as "read_check_claim"; then
  * SumCheck::new(log2 K, claim).prove(|x| ra~(x, r) * Val~(x)) (src/sumcheck.rs:56-110, same labels) over the K padded table entries,
  * with ra~(x, r) = sum_j eq(r, j) [idx_j == x] built by scatter_add and never as a K x L matrix.  A wrong returned value makes the
  * prover fail with the reference's own error, TSGPU_E_SUMCHECK "Round 0 consistency check failed".
@@ -362,6 +363,7 @@ int tsgpu_shout_read_check_verify(tsgpu_ctx* ctx, const tsgpu_fr* entries, size_
  * Statement: operation j < n is Read/Write { address, value } on a zero-initialised memory of memory_size = 2^k cells; every Read must return the
  * value last written to its address (0 if none).  T = 2^t = the padded number of operations.  Two sum-checks on one transcript:
  *   1. read-checking over (x, j), k + t rounds:   sum_j eq(r, j) [read_j] value_j  =  sum_{x, j} ( eq(r, j) [read_j] ra(x, j) ) * Val(x, j)
+ *      the digest of (n, memory_size, addresses, values, is_write) is appended first ("memory_check_statement", two field elements), then
  *      r = challenge_field_elements("memory_check_point", t); claim appended as "memory_read_claim"; ra(x, j) = [address_j == x];
  *      Val(x, j) = content of cell x before operation j.  Ends at a point (x*, j*); the prover sends Val~(x*, j*) ("memory_val_claim").
  *   2. Val-evaluation over j', t rounds:   Val~(x*, j*)  =  sum_j' ( Inc_j' eq(x*, address_j') ) * LT~(j', j*)
@@ -408,6 +410,16 @@ size_t tsgpu_proof_bytes(const tsgpu_proof* p, uint8_t* out, size_t capacity);
 void tsgpu_fr_from_u64(const uint64_t* in, size_t n, tsgpu_fr* out);
 void tsgpu_fr_to_canonical(const tsgpu_fr* in, size_t n, tsgpu_fr* out);
 void tsgpu_proof_free(tsgpu_proof* p);
+
+/* ---- Host helpers around the path (no device work).
+ * tsgpu_chacha20_u64: n outputs of ChaCha20Rng::from_seed(seed32).next_u64() (rand_chacha 0.3.1 / rand_core BlockRng word order) - the
+ * generator the reference draws tau, the Fiat-Shamir challenges (src/utils.rs:81,172-192) and its benchmark traces from; exported so that
+ * callers can build SURVEY 8(d)'s seeded synthetic traces (distribution B) without a second implementation.
+ * tsgpu_statement_digest: the 32-byte binding digest the non-parity constraint sum-checks absorb before their first challenge
+ * (host/statement_digest.hpp: two-level BLAKE2b-256 tree; domain = at most 16 bytes). */
+void tsgpu_chacha20_u64(const uint8_t* seed32, size_t n, uint64_t* out);
+void tsgpu_statement_digest(const char* domain, const uint64_t* header, size_t num_header, const void* const* segments,
+                            const size_t* segment_bytes, size_t num_segments, uint8_t out32[32]);
 
 #ifdef __cplusplus
 }

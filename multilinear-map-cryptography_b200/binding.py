@@ -679,6 +679,25 @@ def unique_id() -> bytes:
     return bytes(buf)
 
 
+def chacha20_u64(seed: bytes, n: int) -> np.ndarray:
+    """n outputs of ChaCha20Rng::from_seed(seed).next_u64() (the generator behind tau, the challenges and the seeded benchmark traces); CPU."""
+    assert len(seed) == 32
+    out = np.empty(n, dtype=np.uint64)
+    lib().tsgpu_chacha20_u64(seed, C.c_size_t(n), _p(out))
+    return out
+
+
+def statement_digest(domain: bytes, header, segments) -> bytes:
+    """the 32-byte binding digest the non-parity constraint sum-checks absorb first (host/statement_digest.hpp); CPU."""
+    hdr = np.ascontiguousarray(header, dtype=np.uint64)
+    segs = [np.frombuffer(bytes(s), dtype=np.uint8) if not isinstance(s, np.ndarray) else np.ascontiguousarray(s).view(np.uint8).reshape(-1) for s in segments]
+    ptrs = (C.c_void_p * max(len(segs), 1))(*[s.ctypes.data if s.size else None for s in segs])
+    lens = (C.c_size_t * max(len(segs), 1))(*[s.size for s in segs])
+    out = np.empty(32, dtype=np.uint8)
+    lib().tsgpu_statement_digest(domain, _p(hdr), C.c_size_t(hdr.size), ptrs, lens, C.c_size_t(len(segs)), _p(out))
+    return out.tobytes()
+
+
 def g1_hash(point) -> np.ndarray:
     """KZGCommitmentValue::hash (src/commitments.rs:73-84); CPU."""
     point = np.ascontiguousarray(point, dtype=np.uint64).reshape(12)

@@ -6,6 +6,7 @@
 //               every Read returns the value last written to its address
 //   tables      over (cell x, cycle j), index x + 2^k j - the shape of BASELINE config 4 (2^10 x 2^16 = 2^26 entries):
 //               ra(x, j) = [address_j == x],  Val(x, j) = content of x before operation j,  Inc_j = written value - previous content
+//   0. transcript <- digest(statement) (host/statement_digest.hpp), so that every challenge depends on the whole trace
 //   1. read-checking   sum_j eq(r, j) [read_j] value_j = sum_{x, j} ( eq(r, j) [read_j] ra(x, j) ) * Val(x, j)          k + t rounds
 //   2. Val-evaluation  Val~(x*, j*) = sum_j' ( Inc_j' eq(x*, address_j') ) * LT~(j', j*)                                  t rounds
 //   Both are SumCheck::prove (src/sumcheck.rs:56-110) on the product closures, driven by host/sumcheck_host.cpp on one transcript.
@@ -15,6 +16,7 @@
 #include <vector>
 #include "../csrc/context.cuh"
 #include "field64.hpp"
+#include "statement_digest.hpp"
 #include "sumcheck_host.hpp"
 #include "transcript.hpp"
 
@@ -54,6 +56,20 @@ int check_statement(tsgpu_ctx* ctx, const uint64_t* addresses, const tsgpu_fr* v
 
 // r, eq(r, .) and the read claim sum_j eq(r, j) [read_j] value_j - the opening both sides share
 int open_statement(tsgpu_ctx* ctx, const Statement& st, Transcript& tr, Tables& tabs, tsgpu_table** eq_r, tsgpu_fr* claim) {
+    {   // the statement enters the transcript (two field elements: low / high 128 bits of its digest) before any challenge is drawn
+        const uint64_t header[2] = {(uint64_t)st.n, (uint64_t)1 << st.k};
+        const StatementSegment segs[3] = {{st.addr, 8 * st.n}, {st.values, 32 * st.n}, {st.is_write, st.n}};
+        uint8_t d[32];
+        statement_digest("twist_memory_chk", header, 2, segs, 3, d);
+        fr_t fe[2];
+        for (int h = 0; h < 2; ++h) {
+            Fr64 x = Fr64::zero();
+            memcpy(x.l, d + 16 * h, 16);
+            x = x * Fr64::r2();
+            memcpy(fe[h].l, x.l, 32);
+        }
+        tr.append_field_elements("memory_check_statement", fe, 2);
+    }
     std::vector<fr_t> r = tr.challenge_field_elements("memory_check_point", st.t);
     std::vector<tsgpu_fr> r_abi(st.t ? st.t : 1);
     for (unsigned i = 0; i < st.t; ++i) r_abi[i] = abi_of(r[i]);

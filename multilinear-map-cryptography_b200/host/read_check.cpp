@@ -5,7 +5,8 @@
 //   statement   lookup j reads entries[idx_j] and returns v_j                       (LookupOp { index, value }, shout.rs:17-22)
 //   identity    for every r:  rv~(r) = sum_{x in {0,1}^k} ra~(x, r) * Val~(x)
 //               rv~ = MLE of the returned values, Val~ = MLE of the padded table, ra(x, j) = [idx_j == x]
-//   protocol    r <- transcript; claim = rv~(r); SumCheck::new(k, claim).prove(|x| ra~(x, r) * Val~(x))   (sumcheck.rs:56-110)
+//   protocol    transcript <- digest(statement) (host/statement_digest.hpp: every challenge depends on the whole statement);
+//               r <- transcript; claim = rv~(r); SumCheck::new(k, claim).prove(|x| ra~(x, r) * Val~(x))   (sumcheck.rs:56-110)
 //   verifier    SumCheck::verify (sumcheck.rs:113-153) + final_evaluation == ra~(x*, r) * Val~(x*) from the statement
 //
 // All field work runs on the device through the table calls of include/tsgpu.h; the transcript and the round checks are host code.
@@ -13,6 +14,8 @@
 #include <string>
 #include <vector>
 #include "../csrc/context.cuh"
+#include "field64.hpp"
+#include "statement_digest.hpp"
 #include "sumcheck_host.hpp"
 #include "transcript.hpp"
 
@@ -34,9 +37,27 @@ struct Tables {                       // frees whatever was created, on every pa
     tsgpu_table** slot() { t.push_back(nullptr); return &t.back(); }
 };
 
-// the common opening of prover and verifier: the point r, the eq(r, .) table and the claim rv~(r)
-int open_statement(tsgpu_ctx* ctx, const tsgpu_fr* lookup_values, size_t num_lookups, unsigned l, Transcript& tr, Tables& tabs,
-                   tsgpu_table** eq_r, tsgpu_fr* claim) {
+// the statement enters the transcript as two field elements (low / high 128 bits of its digest) before any challenge is drawn
+void absorb_statement(Transcript& tr, const tsgpu_fr* entries, size_t num_entries, const uint64_t* lookup_indices, const tsgpu_fr* lookup_values,
+                      size_t num_lookups) {
+    const uint64_t header[2] = {(uint64_t)num_entries, (uint64_t)num_lookups};
+    const StatementSegment segs[3] = {{entries, 32 * num_entries}, {lookup_indices, 8 * num_lookups}, {lookup_values, 32 * num_lookups}};
+    uint8_t d[32];
+    statement_digest("shout_read_check", header, 2, segs, 3, d);
+    fr_t fe[2];
+    for (int h = 0; h < 2; ++h) {
+        Fr64 x = Fr64::zero();
+        memcpy(x.l, d + 16 * h, 16);
+        x = x * Fr64::r2();
+        memcpy(fe[h].l, x.l, 32);
+    }
+    tr.append_field_elements("read_check_statement", fe, 2);
+}
+
+// the common opening of prover and verifier: the statement digest, the point r, the eq(r, .) table and the claim rv~(r)
+int open_statement(tsgpu_ctx* ctx, const tsgpu_fr* entries, size_t num_entries, const uint64_t* lookup_indices, const tsgpu_fr* lookup_values,
+                   size_t num_lookups, unsigned l, Transcript& tr, Tables& tabs, tsgpu_table** eq_r, tsgpu_fr* claim) {
+    absorb_statement(tr, entries, num_entries, lookup_indices, lookup_values, num_lookups);
     std::vector<fr_t> r = tr.challenge_field_elements("read_check_point", l);
     std::vector<tsgpu_fr> r_abi(l ? l : 1);
     for (unsigned i = 0; i < l; ++i) r_abi[i] = abi_of(r[i]);
@@ -70,7 +91,7 @@ int tsgpu_shout_read_check_prove(tsgpu_ctx* ctx, const tsgpu_fr* entries, size_t
     Transcript& tr = *tsgpu_transcript_inner(transcript);
     Tables tabs(ctx);
     tsgpu_table* eq_r = nullptr;
-    int rc = open_statement(ctx, lookup_values, num_lookups, l, tr, tabs, &eq_r, claimed_sum);
+    int rc = open_statement(ctx, entries, num_entries, lookup_indices, lookup_values, num_lookups, l, tr, tabs, &eq_r, claimed_sum);
     if (rc) return rc;
     // the two sum-check tables over the table index x: ra~(x, r) and Val(x); consumed (folded in place) by the rounds
     tsgpu_table* pair[2] = {nullptr, nullptr};
@@ -106,7 +127,7 @@ int tsgpu_shout_read_check_verify(tsgpu_ctx* ctx, const tsgpu_fr* entries, size_
     Tables tabs(ctx);
     tsgpu_table* eq_r = nullptr;
     tsgpu_fr claim;
-    int rc = open_statement(ctx, lookup_values, num_lookups, l, tr, tabs, &eq_r, &claim);
+    int rc = open_statement(ctx, entries, num_entries, lookup_indices, lookup_values, num_lookups, l, tr, tabs, &eq_r, &claim);
     if (rc) return rc;
     SumCheckProof proof;
     for (size_t round = 0; round < num_rounds; ++round) {

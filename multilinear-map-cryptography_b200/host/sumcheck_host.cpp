@@ -3,6 +3,7 @@
 #include <cstring>
 #include "../csrc/context.cuh"
 #include "field64.hpp"
+#include "statement_digest.hpp"
 
 namespace tsg {
 namespace host {
@@ -141,6 +142,17 @@ void tsgpu_transcript_challenge(tsgpu_transcript* t, const char* label, size_t l
     memcpy(out->l, c.l, 32);
 }
 size_t tsgpu_transcript_state_len(const tsgpu_transcript* t) { return t->tr.state_len(); }
+
+void tsgpu_chacha20_u64(const uint8_t* seed32, size_t n, uint64_t* out) {
+    ChaCha20Rng rng(seed32);
+    for (size_t i = 0; i < n; ++i) out[i] = rng.next_u64();
+}
+void tsgpu_statement_digest(const char* domain, const uint64_t* header, size_t num_header, const void* const* segments,
+                            const size_t* segment_bytes, size_t num_segments, uint8_t out32[32]) {
+    std::vector<StatementSegment> segs(num_segments);
+    for (size_t i = 0; i < num_segments; ++i) segs[i] = {segments[i], segment_bytes[i]};
+    statement_digest(domain, header, num_header, segs.data(), num_segments, out32);
+}
 
 int tsgpu_sumcheck_prove_product(tsgpu_ctx* ctx, tsgpu_table* const* tables, int d, const tsgpu_fr* claimed_sum,
                                  tsgpu_transcript* transcript, tsgpu_fr* round_polys, tsgpu_fr* final_evaluation,

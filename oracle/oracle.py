@@ -419,6 +419,25 @@ def shout_prove(powers_jac: np.ndarray, max_operations: int, entries_mont: np.nd
 # The reference's Twist / Shout closures return zero (src/twist.rs:181-214, src/shout.rs:157-184).  The product offers, beside the
 # byte-identical prove, the sum-checks those stubs stand for (host/read_check.cpp, host/memory_check.cpp).  Their CPU restatement is the
 # reference's own SumCheck::prove (orc_sumcheck_prove_product: closure form or table form) applied to tables built here with Python integers.
+def statement_digest_elements(domain: bytes, header: Sequence[int], segments: Sequence[bytes]) -> np.ndarray:
+    """The binding digest both constraint sum-checks absorb before their first challenge (host/statement_digest.hpp): a two-level
+    BLAKE2b-256 tree over 2^20-byte chunks, returned as the two field elements (low / high 128 bits) that enter the transcript."""
+    import hashlib
+    CH = 1 << 20
+    root = hashlib.blake2b(digest_size=32)
+    root.update(domain[:16].ljust(16, b"\0"))
+    root.update(len(header).to_bytes(8, "little"))
+    for h in header:
+        root.update(int(h).to_bytes(8, "little"))
+    root.update(len(segments).to_bytes(8, "little"))
+    for seg in segments:
+        root.update(len(seg).to_bytes(8, "little"))
+        for off in range(0, len(seg), CH):
+            root.update(hashlib.blake2b(seg[off:off + CH], digest_size=32).digest())
+    d = root.digest()
+    return fr_from_ints([int.from_bytes(d[:16], "little"), int.from_bytes(d[16:], "little")])
+
+
 def _eq_ints(pt: np.ndarray) -> List[int]:
     return fr_to_ints(eq_table(pt.reshape(-1, 4))) if pt.shape[0] else [1]
 
@@ -447,6 +466,8 @@ def shout_read_check_prove(entries: np.ndarray, idx: np.ndarray, vals: np.ndarra
     K = 1 << max(nent - 1, 0).bit_length(); L = 1 << max(nlook - 1, 0).bit_length()
     l = L.bit_length() - 1
     tr = Transcript()
+    tr.append_field_elements(b"read_check_statement", statement_digest_elements(
+        b"shout_read_check", [nent, nlook], [_u64(entries).tobytes(), _u64(idx).tobytes(), _u64(vals).tobytes()]))
     r = tr.challenge_field_elements(b"read_check_point", l)
     eq = _eq_ints(r)
     vi = fr_to_ints(vals) if nlook else []
@@ -468,6 +489,8 @@ def twist_memory_check_prove(addr: np.ndarray, vals: np.ndarray, isw: np.ndarray
     k, t = K.bit_length() - 1, T.bit_length() - 1
     vi = fr_to_ints(vals) if n else []
     tr = Transcript()
+    tr.append_field_elements(b"memory_check_statement", statement_digest_elements(
+        b"twist_memory_chk", [n, K], [_u64(addr).tobytes(), _u64(vals).tobytes(), np.ascontiguousarray(isw, dtype=np.uint8).tobytes()]))
     r = tr.challenge_field_elements(b"memory_check_point", t)
     eq = _eq_ints(r)
     claim1 = sum(eq[j] * vi[j] for j in range(n) if not isw[j]) % p

@@ -161,3 +161,28 @@ def test_memory_check_config4_shape(ctx, tsgpu, oracle):
     proof = mc.prove_arrays(addr, vals, isw, K, tsgpu.Transcript())
     assert proof.read_check.round_polynomials.shape == (22, 4, 4) and proof.val_evaluation.round_polynomials.shape == (14, 4, 4)
     assert mc.verify_arrays(addr, vals, isw, K, proof, tsgpu.Transcript())
+
+
+def test_memory_check_challenges_depend_on_the_trace(ctx, tsgpu, oracle):
+    """Fiat-Shamir binding (see tests/test_gpu_read_check.py): two read values shifted so that the read claim at a statement-independent
+    point r0 is unchanged - a false trace that a transcript ignoring the statement would accept - are rejected by prover and verifier"""
+    p = oracle.R_MOD
+    K, n = 8, 16
+    addr, vals, isw = _trace(oracle, tsgpu, K, n, seed=77)
+    reads = [j for j in range(n) if not isw[j]]
+    assert len(reads) >= 2
+    a, b = reads[0], reads[-1]
+    r0 = tsgpu.Transcript().challenge_field_elements(b"memory_check_point", 4)
+    eq0 = oracle.fr_to_ints(oracle.eq_table(r0))
+    v = oracle.fr_to_ints(vals)
+    delta = 99
+    v[a] = (v[a] + delta) % p
+    v[b] = (v[b] - delta * eq0[a] * pow(eq0[b], -1, p)) % p
+    forged = oracle.fr_from_ints(v)
+    mc = tsgpu.TwistMemoryCheck(ctx)
+    with pytest.raises(tsgpu.TwistAndShoutError) as e:
+        mc.prove_arrays(addr, forged, isw, K, tsgpu.Transcript())
+    assert e.value.variant == "SumCheck" and e.value.message == "Round 0 consistency check failed"
+    proof = mc.prove_arrays(addr, vals, isw, K, tsgpu.Transcript())
+    assert mc.verify_arrays(addr, vals, isw, K, proof, tsgpu.Transcript())
+    assert not mc.verify_arrays(addr, forged, isw, K, proof, tsgpu.Transcript())

@@ -109,6 +109,40 @@ def test_read_check_benchmark_shape(ctx, tsgpu, oracle):
     rc = tsgpu.ShoutReadCheck(ctx)
     claim, proof, ch = rc.prove_arrays(entries, idx, vals, tsgpu.Transcript())
     assert proof.round_polynomials.shape == (16, 4, 4)
-    tr = tsgpu.Transcript(); r = tr.challenge_field_elements(b"read_check_point", 18)
+    tr = tsgpu.Transcript()
+    tr.append_field_elements(b"read_check_statement", oracle.statement_digest_elements(
+        b"shout_read_check", [T, L], [entries.tobytes(), idx.tobytes(), np.ascontiguousarray(vals).tobytes()]))
+    r = tr.challenge_field_elements(b"read_check_point", 18)
     assert (ctx.mle_evaluate(vals, r) == claim).all()
     assert rc.verify_arrays(entries, idx, vals, proof, tsgpu.Transcript())
+
+
+def test_challenges_depend_on_the_statement(ctx, tsgpu, oracle):
+    """Fiat-Shamir binding: the point r is drawn AFTER the statement digest is absorbed.  Against a statement-independent r0 (what a fresh
+    transcript would hand out) one can shift two returned values so that sum_j eq(r0, j)(v'_j - v_j) = 0: the false statement would share the
+    claim rv~(r0) with the true one and prove / verify.  With the digest in the transcript the false statement is rejected on both sides."""
+    p = oracle.R_MOD
+    entries, idx, vals = _statement(oracle, tsgpu, 32, 16, seed=9)
+    r0 = tsgpu.Transcript().challenge_field_elements(b"read_check_point", 4)            # the point of a transcript that ignores the statement
+    eq0 = oracle.fr_to_ints(oracle.eq_table(r0))
+    v = oracle.fr_to_ints(vals)
+    delta = 12345
+    v[2] = (v[2] + delta) % p
+    v[7] = (v[7] - delta * eq0[2] * pow(eq0[7], -1, p)) % p                             # keeps sum_j eq(r0, j) v_j unchanged
+    forged = oracle.fr_from_ints(v)
+    assert sum(e * a for e, a in zip(eq0, v)) % p == sum(e * a for e, a in zip(eq0, oracle.fr_to_ints(vals))) % p
+    rc = tsgpu.ShoutReadCheck(ctx)
+    with pytest.raises(tsgpu.TwistAndShoutError) as e:
+        rc.prove_arrays(entries, idx, forged, tsgpu.Transcript())
+    assert e.value.variant == "SumCheck" and e.value.message == "Round 0 consistency check failed"
+    claim, proof, _ = rc.prove_arrays(entries, idx, vals, tsgpu.Transcript())
+    assert rc.verify_arrays(entries, idx, vals, proof, tsgpu.Transcript())
+    assert not rc.verify_arrays(entries, idx, forged, proof, tsgpu.Transcript())
+    # the drawn point moves with every part of the statement
+    pts = set()
+    for ent, ix, vv in ((entries, idx, vals), (entries, idx, forged), (entries[::-1].copy(), idx, vals), (entries, idx[::-1].copy(), vals)):
+        tr = tsgpu.Transcript()
+        tr.append_field_elements(b"read_check_statement", oracle.statement_digest_elements(
+            b"shout_read_check", [32, 16], [ent.tobytes(), ix.tobytes(), np.ascontiguousarray(vv).tobytes()]))
+        pts.add(tr.challenge_field_elements(b"read_check_point", 4).tobytes())
+    assert len(pts) == 4

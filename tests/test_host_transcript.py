@@ -94,3 +94,36 @@ def test_less_than_on_field_elements_host(tsgpu, oracle):
                     break
             got = lt.evaluate_at_field_elements(oracle.fr_from_ints([x])[0], oracle.fr_from_ints([y])[0])
             assert oracle.fr_to_ints(got) == [want]
+
+
+def test_statement_digest_matches_hashlib_blake2b_tree(tsgpu, oracle):
+    """host/statement_digest.hpp (BLAKE2b-256, RFC 7693, two-level tree over 2^20-byte chunks) against hashlib: empty, sub-block, block-boundary,
+    multi-chunk and ragged segments; and the RFC's "abc" vector through a one-segment leaf"""
+    import hashlib
+    rng = np.random.default_rng(11)
+
+    def want(domain, header, segs):
+        root = hashlib.blake2b(digest_size=32)
+        root.update(domain[:16].ljust(16, b"\0") + len(header).to_bytes(8, "little") + b"".join(int(h).to_bytes(8, "little") for h in header))
+        root.update(len(segs).to_bytes(8, "little"))
+        for s in segs:
+            root.update(len(s).to_bytes(8, "little"))
+            for off in range(0, len(s), 1 << 20):
+                root.update(hashlib.blake2b(s[off:off + (1 << 20)], digest_size=32).digest())
+        return root.digest()
+
+    cases = [(b"x", [], []), (b"shout_read_check", [3, 4], [b"", b"abc", bytes(127), bytes(128), bytes(129)]),
+             (b"a-domain-longer-than-16", [1 << 63], [rng.bytes((1 << 20) + 5), rng.bytes(1 << 20), rng.bytes(3 * (1 << 20) - 1)])]
+    for domain, header, segs in cases:
+        assert tsgpu.statement_digest(domain, header, segs) == want(domain, header, segs)
+    # the oracle's field-element form of the same digest
+    d = tsgpu.statement_digest(b"shout_read_check", [3, 4], [b"abc"])
+    got = oracle.fr_to_ints(oracle.statement_digest_elements(b"shout_read_check", [3, 4], [b"abc"]))
+    assert got == [int.from_bytes(d[:16], "little"), int.from_bytes(d[16:], "little")]
+    assert hashlib.blake2b(b"abc", digest_size=64).hexdigest().startswith("ba80a53f981c4d0d")          # RFC 7693 appendix A anchors hashlib itself
+
+
+def test_chacha20_u64_matches_oracle_stream(tsgpu, oracle):
+    """tsgpu_chacha20_u64 == the oracle's ChaCha20Rng::next_u64 stream, across several 64-word buffer refills"""
+    for seed in (bytes(32), bytes([2]) * 32, bytes(range(32))):
+        assert (tsgpu.chacha20_u64(seed, 1000) == oracle.chacha_u64(seed, 1000)).all()
