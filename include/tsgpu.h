@@ -251,7 +251,13 @@ size_t tsgpu_transcript_state_len(const tsgpu_transcript* t);
 
 /* SumCheck::new(num_vars, claimed_sum).prove(|v| prod_t mle_t.evaluate(v), transcript)   (sumcheck.rs:56-110)
  * round_polys: num_vars x 4 coefficients (low -> high); challenges / table_finals may be NULL.
- * Returns TSGPU_E_SUMCHECK with "Round {k} consistency check failed" when claimed_sum is wrong. */
+ * Returns TSGPU_E_SUMCHECK with "Round {k} consistency check failed" when claimed_sum is wrong.
+ * Default: the reference's deterministic check - round 0 is summed in full and g(0) + g(1) == claimed_sum is tested before anything is
+ * appended to the transcript (sumcheck.rs:77-84); on that error the tables are unmodified.
+ * Opt-in, tsgpu_set_tuning(ctx, "deferred_claim_check", 1), d = 2 only: round 0 also runs in the claim form (one product per pair less in
+ * the largest round) and the claimed sum is checked against the product of the bound tables at the end.  Same proofs; a wrong claim gives
+ * the same error and the transcript is rolled back to its state at entry, but it is detected only after all rounds ran (except with
+ * probability ~ 2 num_vars / |Fr|) and the tables ARE consumed on that error path. */
 int tsgpu_sumcheck_prove_product(tsgpu_ctx* ctx, tsgpu_table* const* tables, int d, const tsgpu_fr* claimed_sum,
                                  tsgpu_transcript* transcript, tsgpu_fr* round_polys, tsgpu_fr* final_evaluation,
                                  tsgpu_fr* challenges, tsgpu_fr* table_finals);
@@ -316,6 +322,9 @@ int tsgpu_twist_prove_dev(tsgpu_ctx* ctx, const tsgpu_params* params, tsgpu_poly
  * (partial commitments, opening sums, partial opening proofs); every rank returns the same proof, byte-identical to tsgpu_twist_prove. */
 int tsgpu_twist_prove_sharded(tsgpu_ctx* ctx, const tsgpu_params* params, const uint64_t* addresses, const tsgpu_fr* values, size_t num_local,
                               size_t total_operations, tsgpu_proof** out);
+/* same with this rank's zero-padded slices (padded_operations / ranks entries each) already resident in HBM (not consumed) */
+int tsgpu_twist_prove_sharded_dev(tsgpu_ctx* ctx, const tsgpu_params* params, tsgpu_poly* local_addresses, tsgpu_poly* local_values,
+                                  size_t padded_operations, tsgpu_proof** out);
 /* Shout::prove(&LookupTable) (src/shout.rs:97-222): entries = table.entries, lookup_indices[i] = lookups[i].index.
  * TSGPU_E_INVALID_PARAMETERS "Too many lookup operations" beyond max_operations. */
 int tsgpu_shout_prove(tsgpu_ctx* ctx, const tsgpu_params* params, const tsgpu_fr* entries, size_t num_entries,
@@ -418,6 +427,9 @@ void tsgpu_proof_free(tsgpu_proof* p);
  * tsgpu_statement_digest: the 32-byte binding digest the non-parity constraint sum-checks absorb before their first challenge
  * (host/statement_digest.hpp: two-level BLAKE2b-256 tree; domain = at most 16 bytes). */
 void tsgpu_chacha20_u64(const uint8_t* seed32, size_t n, uint64_t* out);
+/* from one ChaCha20Rng::from_seed(seed32): num_fr draws of Fr::rand (ark-ff 0.4.2: four next_u64, top two bits masked, rejection) and then
+ * num_u64 draws of next_u64 - e.g. tau (seed [42; 32], src/utils.rs:81-84) or SURVEY 8(d)'s config-4 inputs (seed [4; 32]) */
+void tsgpu_chacha20_fr_then_u64(const uint8_t* seed32, size_t num_fr, tsgpu_fr* out_fr, size_t num_u64, uint64_t* out_u64);
 void tsgpu_statement_digest(const char* domain, const uint64_t* header, size_t num_header, const void* const* segments,
                             const size_t* segment_bytes, size_t num_segments, uint8_t out32[32]);
 

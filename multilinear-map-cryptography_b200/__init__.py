@@ -8,7 +8,7 @@ The directory name carries a hyphen, so import it with
     binding.py  ctypes binding of libtsgpu.so - no CPU fallback
 """
 from .binding import (Context, Table, SumCheckRounds, SumCheck, SumCheckProof, Transcript, Srs, Poly,  # noqa: F401
-                      KZGCommitment, g1_hash, g1_compress, g1_equal, unique_id, chacha20_u64, statement_digest, TwistAndShoutError, LIB_PATH, lib)
+                      KZGCommitment, g1_hash, g1_compress, g1_equal, unique_id, chacha20_u64, chacha20_fr_then_u64, statement_digest, TwistAndShoutError, LIB_PATH, lib)
 from .api import (setup_params, ProverParams, VerifierParams, MemoryTrace, MemoryOp, Twist, TwistProof,  # noqa: F401,E402
                   LookupTable, LookupOp, Shout, ShoutProof, fe, fe_vec, fe_to_int, HostVerifierParams, kzg_verify, kzg_batch_verify, KZGVectorCommitment,
                   MultilinearExtension, LessThanPolynomial, ShoutReadCheck, TwistMemoryCheck,

@@ -414,6 +414,14 @@ class Twist:
                                                   C.c_size_t(local_addresses.shape[0]), C.c_size_t(total_operations), C.byref(h)))
         return Proof(h)
 
+    def prove_sharded_device(self, local_padded_addresses, local_padded_values, padded_operations: int) -> TwistProof:
+        """prove_sharded from this rank's zero-padded slices already resident in HBM (Poly handles of padded_operations / ranks entries; not consumed)"""
+        ctx = self.prover_params.ctx
+        h = C.c_void_p()
+        ctx.check(lib().tsgpu_twist_prove_sharded_dev(ctx._h, self.prover_params._h, local_padded_addresses._h, local_padded_values._h,
+                                                      C.c_size_t(padded_operations), C.byref(h)))
+        return Proof(h)
+
     @staticmethod
     def shard_range(total_operations: int, rank: int, world: int):
         """[lo, hi) of the operations rank `rank` passes to prove_sharded"""

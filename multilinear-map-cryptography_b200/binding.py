@@ -687,6 +687,14 @@ def chacha20_u64(seed: bytes, n: int) -> np.ndarray:
     return out
 
 
+def chacha20_fr_then_u64(seed: bytes, num_fr: int, num_u64: int = 0):
+    """num_fr draws of Fr::rand then num_u64 draws of next_u64 from one ChaCha20Rng::from_seed(seed); CPU."""
+    assert len(seed) == 32
+    f = np.empty((num_fr, 4), dtype=np.uint64); u = np.empty(num_u64, dtype=np.uint64)
+    lib().tsgpu_chacha20_fr_then_u64(seed, C.c_size_t(num_fr), _p(f), C.c_size_t(num_u64), _p(u))
+    return f, u
+
+
 def statement_digest(domain: bytes, header, segments) -> bytes:
     """the 32-byte binding digest the non-parity constraint sum-checks absorb first (host/statement_digest.hpp); CPU."""
     hdr = np.ascontiguousarray(header, dtype=np.uint64)

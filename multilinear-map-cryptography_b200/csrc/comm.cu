@@ -221,6 +221,7 @@ int tsgpu_sumcheck_prove_product_sharded(tsgpu_ctx* ctx, tsgpu_table* const* tab
     const size_t transcript_mark = tr.state_len();
     auto claim_failed = [&]() -> int {
         tr.truncate(transcript_mark);
+        memset(round_polys, 0, (size_t)num_vars * 4 * sizeof(tsgpu_fr));       // nothing of the aborted run is left in the caller's buffers
         return fail(ctx, TSGPU_E_SUMCHECK, "Round 0 consistency check failed");
     };
     auto absorb = [&](unsigned round, const fr_t e[4], fr_t* r_out) -> int {

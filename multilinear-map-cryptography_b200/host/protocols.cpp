@@ -309,6 +309,16 @@ int tsgpu_twist_prove_sharded(tsgpu_ctx* ctx, const tsgpu_params* params, const 
     tsgpu_poly_free(ctx, pa); tsgpu_poly_free(ctx, pv);
     return rc;
 }
+// same, with this rank's zero-padded slices (m / G entries each) already resident in HBM (not consumed)
+int tsgpu_twist_prove_sharded_dev(tsgpu_ctx* ctx, const tsgpu_params* params, tsgpu_poly* local_addresses, tsgpu_poly* local_values,
+                                  size_t padded_operations, tsgpu_proof** out) {
+    if (!ctx || !params || !out || !local_addresses || !local_values) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    const size_t G = (size_t)tsgpu_comm_size(ctx), m = padded_operations;
+    if (m > params->max_operations) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "Too many operations");
+    if (next_pow2(m) != m || m < G || !tsgpu_srs_can_lagrange(params->srs)) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "sharded proving needs a power-of-two padded length, at least one padded operation per rank and an SRS with its trapdoor");
+    if (tsgpu_poly_len(local_addresses) != m / G || tsgpu_poly_len(local_values) != m / G) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "this rank must pass slices of padded_operations / ranks entries");
+    return prove_two_vectors_sharded(ctx, params, local_addresses, m, local_values, m, "address_commitment", "value_commitment", log2_of(m), out);
+}
 // Shout::prove (shout.rs:97-222) sharded the same way: rank r passes the table entries and the lookup indices that fall into its range of the
 // padded table (length next_power_of_two(total_entries)) resp. of the padded lookup vector (length next_power_of_two(total_lookups)).
 int tsgpu_shout_prove_sharded(tsgpu_ctx* ctx, const tsgpu_params* params, const tsgpu_fr* entries, size_t num_local_entries, size_t total_entries,

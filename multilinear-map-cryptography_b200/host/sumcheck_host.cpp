@@ -40,7 +40,10 @@ int sumcheck_prove_product(tsgpu_ctx* ctx, tsgpu_table* const* tables, int d, co
     if (challenges) challenges->clear();
     fr_t current = claimed_sum;
     tsgpu_fr ev[4];
-    // d = 2: round 0 also runs in the claim form (g(1) = claimed_sum - g(0): a third of its products saved).  The reference's round-0 check
+    // DEFAULT: round 0 is summed in full and g(0) + g(1) == claimed_sum is checked before anything is appended - the reference's deterministic
+    // check (sumcheck.rs:77-84): a wrong claim fails at once, with the transcript untouched (the tables are bound in place only on success paths
+    // after round 0; on this error they are still the caller's unmodified tables).
+    // OPT-IN (tsgpu_set_tuning("deferred_claim_check", 1)), d = 2: round 0 also runs in the claim form (g(1) = claimed_sum - g(0): a third of its products saved).  The reference's round-0 check
     // g(0) + g(1) == claimed_sum (sumcheck.rs:77-84) - the only one that can fail for honest tables - is then paid at the END: a wrong claim off by
     // delta shifts every later running sum by delta * prod_i L_1(r_i) (L_1 = the Lagrange basis polynomial of node 1), so the product of the
     // bound tables differs from the last running sum unless some challenge hits a root of L_1 (probability ~ 2 n / |Fr|, ~2^-247).  On a mismatch
@@ -146,6 +149,11 @@ size_t tsgpu_transcript_state_len(const tsgpu_transcript* t) { return t->tr.stat
 void tsgpu_chacha20_u64(const uint8_t* seed32, size_t n, uint64_t* out) {
     ChaCha20Rng rng(seed32);
     for (size_t i = 0; i < n; ++i) out[i] = rng.next_u64();
+}
+void tsgpu_chacha20_fr_then_u64(const uint8_t* seed32, size_t num_fr, tsgpu_fr* out_fr, size_t num_u64, uint64_t* out_u64) {
+    ChaCha20Rng rng(seed32);
+    for (size_t i = 0; i < num_fr; ++i) { fr_t f = rng.rand_field<fr_t>(); memcpy(out_fr[i].l, f.l, 32); }
+    for (size_t i = 0; i < num_u64; ++i) out_u64[i] = rng.next_u64();
 }
 void tsgpu_statement_digest(const char* domain, const uint64_t* header, size_t num_header, const void* const* segments,
                             const size_t* segment_bytes, size_t num_segments, uint8_t out32[32]) {

@@ -172,34 +172,57 @@ def test_wrong_claimed_sum_is_rejected_in_round_zero(ctx, tsgpu, oracle):
 
 
 @pytest.mark.parametrize("nv", [1, 2, 7, 13])
-def test_deferred_round_zero_check_keeps_the_reference_error_behaviour(ctx, tsgpu, oracle, nv):
-    """d = 2: round 0 runs in the claim form and the claimed sum is checked at the end of the protocol.  A wrong claim must still give
-    Err(SumCheck("Round 0 consistency check failed")) (sumcheck.rs:77-84) and leave the transcript exactly as the reference does (untouched: it
-    fails before the first append); a right claim gives the same proof with the deferred check on and off."""
+def test_round_zero_check_default_and_deferred_forms_behave_like_the_reference(ctx, tsgpu, oracle, nv):
+    """d = 2.  Default: the reference's deterministic round-0 check (sumcheck.rs:77-84) - a wrong claim fails before anything is appended and the
+    tables are untouched.  Opt-in "deferred_claim_check": round 0 in the claim form, the claimed sum checked at the end.  Both must give
+    Err(SumCheck("Round 0 consistency check failed")) for a wrong claim, leave the transcript exactly as the reference does (unchanged), and
+    give the oracle's proof for the right claim."""
     n = 1 << nv
     tables = [oracle.chacha_fr_rand(seed_bytes(90 + t + nv), n) for t in range(2)]
     ai, bi = oracle.fr_to_ints(tables[0]), oracle.fr_to_ints(tables[1])
     claimed = sum(x * y for x, y in zip(ai, bi)) % oracle.R_MOD
     good = oracle.fr_from_ints([claimed])[0]
-    for delta in (1, oracle.R_MOD - 1, 123456789):
-        bad = oracle.fr_from_ints([(claimed + delta) % oracle.R_MOD])[0]
-        tr = tsgpu.Transcript()
-        tr.append_field_element(b"before", tsgpu.fe(7))
-        mark = tr.state_len
-        with pytest.raises(tsgpu.TwistAndShoutError) as e:
-            tsgpu.SumCheck(nv, bad).prove_product(ctx, [ctx.table_upload(t) for t in tables], tr)
-        assert e.value.variant == "SumCheck" and e.value.message == "Round 0 consistency check failed"
-        assert tr.state_len == mark                                   # rolled back: the next challenge is what the reference would draw
-        otr = oracle.Transcript(); otr.append_field_element(b"before", tsgpu.fe(7))
-        assert (tr.challenge_field_element(b"next") == otr.challenge_field_element(b"next")).all()
     ref = oracle.sumcheck_prove_product(tables, good, mode="tables")
-    for flag in (1, 0):
+    for flag in (0, 1):
         ctx.set_tuning("deferred_claim_check", flag)
         try:
+            for delta in (1, oracle.R_MOD - 1, 123456789):
+                bad = oracle.fr_from_ints([(claimed + delta) % oracle.R_MOD])[0]
+                tr = tsgpu.Transcript()
+                tr.append_field_element(b"before", tsgpu.fe(7))
+                mark = tr.state_len
+                dev = [ctx.table_upload(t) for t in tables]
+                with pytest.raises(tsgpu.TwistAndShoutError) as e:
+                    tsgpu.SumCheck(nv, bad).prove_product(ctx, dev, tr)
+                assert e.value.variant == "SumCheck" and e.value.message == "Round 0 consistency check failed"
+                assert tr.state_len == mark                               # the next challenge is what the reference would draw
+                otr = oracle.Transcript(); otr.append_field_element(b"before", tsgpu.fe(7))
+                assert (tr.challenge_field_element(b"next") == otr.challenge_field_element(b"next")).all()
+                if flag == 0:                                             # deterministic form: the caller's tables are still whole
+                    assert dev[0].num_vars == nv and (dev[0].download() == tables[0].reshape(-1, 4)).all() and (dev[1].download() == tables[1].reshape(-1, 4)).all()
             proof = tsgpu.SumCheck(nv, good).prove_product(ctx, [ctx.table_upload(t) for t in tables], tsgpu.Transcript())
         finally:
-            ctx.set_tuning("deferred_claim_check", 1)
+            ctx.set_tuning("deferred_claim_check", 0)
         assert (proof.round_polynomials == ref["round_polynomials"]).all() and (proof.final_evaluation == ref["final_evaluation"]).all()
+
+
+def test_a_thousand_random_wrong_claims_fail_identically_in_both_forms(ctx, tsgpu, oracle):
+    """10^3 random wrong claims on a 2^4-entry product: the deterministic and the deferred form return the same error and leave the same transcript state"""
+    nv = 4
+    tables = [oracle.chacha_fr_rand(seed_bytes(200 + t), 1 << nv) for t in range(2)]
+    claims = oracle.chacha_fr_rand(seed_bytes(203), 1000).reshape(-1, 4)
+    want = tsgpu.Transcript(); want.append_field_element(b"before", tsgpu.fe(1)); want_next = want.challenge_field_element(b"next")
+    try:
+        for flag in (0, 1):
+            ctx.set_tuning("deferred_claim_check", flag)
+            for c in claims:
+                tr = tsgpu.Transcript(); tr.append_field_element(b"before", tsgpu.fe(1))
+                with pytest.raises(tsgpu.TwistAndShoutError) as e:
+                    tsgpu.SumCheck(nv, c).prove_product(ctx, [ctx.table_upload(t) for t in tables], tr)
+                assert e.value.message == "Round 0 consistency check failed"
+                assert (tr.challenge_field_element(b"next") == want_next).all()
+    finally:
+        ctx.set_tuning("deferred_claim_check", 0)
 
 
 def test_reference_integration_x1_times_x2(ctx, tsgpu, oracle):

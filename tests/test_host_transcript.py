@@ -127,3 +127,13 @@ def test_chacha20_u64_matches_oracle_stream(tsgpu, oracle):
     """tsgpu_chacha20_u64 == the oracle's ChaCha20Rng::next_u64 stream, across several 64-word buffer refills"""
     for seed in (bytes(32), bytes([2]) * 32, bytes(range(32))):
         assert (tsgpu.chacha20_u64(seed, 1000) == oracle.chacha_u64(seed, 1000)).all()
+
+
+def test_chacha20_fr_then_u64_matches_oracle(tsgpu, oracle):
+    """Fr::rand draws (incl. the rejection branch: ~1 in 4 candidates is >= r after masking to 254 bits) followed by u64 draws from the same generator"""
+    for seed in (bytes([4]) * 32, bytes([42]) * 32, bytes([5]) * 32):
+        f, u = tsgpu.chacha20_fr_then_u64(seed, 300, 50)
+        of, ou = oracle.chacha_fr_then_u64(seed, 300, 50)
+        assert (f == of).all() and (u == ou).all()
+    tau, _ = oracle.setup_scalars()
+    assert (tsgpu.chacha20_fr_then_u64(bytes([42]) * 32, 1)[0][0] == tau).all()         # src/utils.rs:81-84

@@ -1,0 +1,165 @@
+"""CPU: PUBLISHED known-answer vectors of the third-party primitives the reference leans on, checked against the
+pure-Python restatement (oracle/pyref.py), which the C++ oracle and the product's host code are then compared with on many inputs.
+Sources, all reproduced here from the publications (no network):
+  * SipHash-2-4, Aumasson & Bernstein, "SipHash: a fast short-input PRF", Appendix A: key 00..0f, message 00..0e -> a129ca6149be45e5.
+    It pins the round function / padding / finalisation structure; SipHash-1-3 is the same code with (c, d) = (1, 3).
+  * SipHash-1-3, Rust library/core/tests/hash/sip.rs `test_siphash_1_3`: key 00..0f, messages 00..(i-1), first three vectors.
+  * Rust `DefaultHasher::new().finish()` (SipHash-1-3, keys 0, 0, empty input) = d1fba762150c532c.
+  * ChaCha20: RFC 7539 section 2.3.2 (key 00..1f, counter 1, nonce 00:00:00:09:00:00:00:4a:00:00:00:00) and Appendix A.1 vectors 1 and 2
+    (zero key and nonce, counters 0 and 1).  rand_chacha's ChaCha20Rng is this block function with a 64-bit counter / 64-bit stream id.
+  * BN254 G1: generator (1, 2); 2G from EIP-196 (alt_bn128 addition tests); the curve equation y^2 = x^3 + 3.
+What no publication fixes - ark-ff's Fp::rand masking and rejection, BlockRng's word order for next_u64, ark-serialize's flag bits - is
+restated from the crates' documented behaviour and stays UNPINNED until tests/golden/from_arkworks.json exists (see the last test)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import seed_bytes
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+M64 = (1 << 64) - 1
+
+
+def _siphash(c, d, data, k0, k1):
+    """generic SipHash-c-d, written independently of oracle/pyref.py"""
+    def rotl(v, s):
+        return ((v << s) | (v >> (64 - s))) & M64
+    v = [k0 ^ 0x736F6D6570736575, k1 ^ 0x646F72616E646F6D, k0 ^ 0x6C7967656E657261, k1 ^ 0x7465646279746573]
+
+    def rnd():
+        v[0] = (v[0] + v[1]) & M64; v[1] = rotl(v[1], 13) ^ v[0]; v[0] = rotl(v[0], 32)
+        v[2] = (v[2] + v[3]) & M64; v[3] = rotl(v[3], 16) ^ v[2]
+        v[0] = (v[0] + v[3]) & M64; v[3] = rotl(v[3], 21) ^ v[0]
+        v[2] = (v[2] + v[1]) & M64; v[1] = rotl(v[1], 17) ^ v[2]; v[2] = rotl(v[2], 32)
+    n = len(data)
+    words = [int.from_bytes(data[i:i + 8], "little") for i in range(0, n - n % 8, 8)]
+    words.append(((n & 0xFF) << 56) | int.from_bytes(data[n - n % 8:], "little"))
+    for m in words:
+        v[3] ^= m
+        for _ in range(c):
+            rnd()
+        v[0] ^= m
+    v[2] ^= 0xFF
+    for _ in range(d):
+        rnd()
+    return v[0] ^ v[1] ^ v[2] ^ v[3]
+
+
+K0 = int.from_bytes(bytes(range(8)), "little"); K1 = int.from_bytes(bytes(range(8, 16)), "little")
+
+
+def test_siphash_published_vectors_and_all_implementations(oracle, tsgpu):
+    import pyref
+    assert _siphash(2, 4, bytes(range(15)), K0, K1) == 0xA129CA6149BE45E5                    # SipHash paper, Appendix A
+    rust_1_3 = [0xABAC0158050FC4DC, 0xC9F49BF37D57CA93, 0x82CB9B024DC7D44D]                 # Rust core tests, test_siphash_1_3, rows 0..2
+    for i, want in enumerate(rust_1_3):
+        assert _siphash(1, 3, bytes(range(i)), K0, K1) == want == pyref.siphash13(bytes(range(i)), K0, K1)
+    assert _siphash(1, 3, b"", 0, 0) == 0xD1FBA762150C532C == oracle.siphash13(b"")         # DefaultHasher::new().finish()
+    rng = np.random.default_rng(13)
+    for n in list(range(0, 70)) + [127, 128, 129, 1000, 4097]:
+        d = rng.bytes(n)
+        assert oracle.siphash13(d) == pyref.siphash13(d) == _siphash(1, 3, d, 0, 0)
+    # the product's own SipHash (host/transcript.hpp) is reached through a Transcript: challenge = ChaCha20Rng(seed = hash(len || state) LE x 4)
+    for k in (0, 1, 5):
+        t = tsgpu.Transcript(); o = oracle.Transcript(); p = pyref.Transcript()
+        for j in range(k):
+            x = oracle.fr_from_ints([j * 7 + 1])[0]
+            t.append_field_element(b"label%d" % j, x); o.append_field_element(b"label%d" % j, x); p.append_field_element(b"label%d" % j, j * 7 + 1)
+        c = t.challenge_field_element(b"c")
+        assert (c == o.challenge_field_element(b"c")).all() and oracle.fr_to_ints(c.reshape(1, 4))[0] == p.challenge_field_element(b"c")
+
+
+def test_chacha20_rfc7539_blocks_and_the_rng_word_stream(oracle, tsgpu):
+    import pyref
+    key = [int.from_bytes(bytes(range(4 * i, 4 * i + 4)), "little") for i in range(8)]
+    blk = pyref._chacha_block(key, 1 | (0x09000000 << 32), 0x4A000000)                       # RFC 7539 2.3.2 in the 64 / 64-bit counter / stream layout
+    assert b"".join(w.to_bytes(4, "little") for w in blk).hex() == (
+        "10f1e7e4d13b5915500fdd1fa32071c4c7d1f4c733c068030422aa9ac3d46c4ed2826446079faa0914c2d705d98b02a2b5129cd1de164eb9cbd083e8a2503c4e")
+    a1 = ["76b8e0ada0f13d90405d6ae55386bd28bdd219b8a08ded1aa836efcc8b770dc7da41597c5157488d7724e03fb8d84a376a43b8f41518a11cc387b669b2ee6586",
+          "9f07e7be5551387a98ba977c732d080dcb0f29a048e3656912c6533e32ee7aed29b721769ce64e43d57133b074d839d531ed1f28510afb45ace10a1f4b794d6f"]
+    for ctr, want in enumerate(a1):                                                           # RFC 7539 A.1 test vectors 1 and 2
+        assert b"".join(w.to_bytes(4, "little") for w in pyref._chacha_block([0] * 8, ctr)).hex() == want
+    # ChaCha20Rng::from_seed([0; 32]): the keystream in order, next_u64 = two consecutive words, low word first (rand_core BlockRng)
+    stream = bytes.fromhex(a1[0] + a1[1])
+    want_u64 = [int.from_bytes(stream[8 * i:8 * i + 8], "little") for i in range(16)]
+    assert [int(x) for x in oracle.chacha_u64(bytes(32), 16)] == want_u64 == [int(x) for x in tsgpu.chacha20_u64(bytes(32), 16)]
+    # 300 draws cross the 64-word buffer four times; python, oracle and product agree
+    rng = pyref.ChaCha20Rng(seed_bytes(3))
+    py = [rng.next_u64() for _ in range(300)]
+    assert py == [int(x) for x in oracle.chacha_u64(seed_bytes(3), 300)] == [int(x) for x in tsgpu.chacha20_u64(seed_bytes(3), 300)]
+    # BlockRng::next_u64 at an ODD word index, including the straddle at word 63 -> 0 of the next buffer (unreachable from the reference, which
+    # only ever draws u64s from a fresh generator, but part of the restated behaviour): one next_u32 first, then 40 next_u64
+    rng = pyref.ChaCha20Rng(bytes(32))
+    first = rng.next_u32()
+    ks = b"".join(w.to_bytes(4, "little") for c in range(6) for w in pyref._chacha_block([0] * 8, c))
+    assert first == int.from_bytes(ks[:4], "little")
+    assert [rng.next_u64() for _ in range(40)] == [int.from_bytes(ks[4 + 8 * i:12 + 8 * i], "little") for i in range(40)]
+
+
+def test_bn254_g1_published_points_and_encodings(oracle, tsgpu):
+    p = oracle.P_MOD
+    G = oracle.g1_generator()
+    assert oracle.g1_affine_canonical(G) == [(1, 2)]
+    two_g = (0x030644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD3, 0x15ED738C0E0A7C92E7845F96B2AE9C0A68A6A449E3538FC7FF3EBF7A5A18A2C4)   # EIP-196
+    assert (two_g[1] ** 2 - two_g[0] ** 3 - 3) % p == 0
+    assert oracle.g1_affine_canonical(oracle.g1_add(G, G)) == [two_g] == oracle.g1_affine_canonical(oracle.g1_mul(G, oracle.fr_from_ints([2])[0]))
+    # r G = identity (the group order is the Fr modulus): (r - 1) G = -G
+    neg_g = oracle.g1_mul(G, oracle.fr_from_ints([oracle.R_MOD - 1])[0])
+    assert oracle.g1_affine_canonical(neg_g) == [(1, p - 2)]
+    # ark-serialize compressed G1 (SWFlags): x little-endian; bit 7 of the last byte = "y is the larger of (y, -y)", bit 6 = infinity
+    assert oracle.g1_compress(G).hex() == "01" + "00" * 31 == tsgpu.g1_compress(G).hex()
+    assert oracle.g1_compress(neg_g).hex() == "01" + "00" * 30 + "80" == tsgpu.g1_compress(neg_g).hex()
+    ident = oracle.g1_add(G, neg_g)
+    assert oracle.g1_compress(ident).hex() == "00" * 31 + "40" == tsgpu.g1_compress(ident).hex()
+    x2 = two_g[0].to_bytes(32, "little")
+    flag = 0x80 if two_g[1] > p - two_g[1] else 0
+    assert oracle.g1_compress(oracle.g1_add(G, G)) == x2[:31] + bytes([x2[31] | flag])
+
+
+def test_fp_rand_masking_and_rejection_branch(oracle):
+    """ark-ff 0.4.2 `Fp::rand` (documented behaviour, UNPINNED by any publication): four next_u64 -> the top 2 bits cleared -> accepted as the
+    MONTGOMERY representation iff < r, else the next four words.  Some seed below must exercise a rejection."""
+    import pyref
+    rejected = 0
+    for s in range(1, 9):
+        seed = seed_bytes(s)
+        words = [int(x) for x in oracle.chacha_u64(seed, 64)]
+        got = oracle.limbs_to_ints(oracle.chacha_fr_rand(seed, 4))        # raw limbs = Montgomery form
+        k = 0
+        for i in range(4):
+            while True:
+                cand = (words[k] | (words[k + 1] << 64) | (words[k + 2] << 128) | ((words[k + 3] & (M64 >> 2)) << 192)); k += 4
+                if cand < oracle.R_MOD:
+                    break
+                rejected += 1
+            assert got[i] == cand
+        rng = pyref.ChaCha20Rng(seed)
+        assert [pyref.fr_rand_mont(rng) for _ in range(4)] == got
+    assert rejected > 0
+
+
+def test_vectors_from_real_arkworks_when_present(oracle):
+    """`cargo run --release -- golden` in baseline/arkworks_bench writes tests/golden/from_arkworks.json from REAL arkworks / rand_chacha /
+    Rust std.  When that file exists every vector in it must equal the repository's self-derived tests/golden/appendix_c.json (which
+    tests/test_oracle_golden.py holds the oracle to).  Until someone with a Rust toolchain commits it, byte parity with the reference is
+    'partial': restated and cross-checked, not pinned."""
+    path = os.path.join(HERE, "golden", "from_arkworks.json")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/from_arkworks.json absent: no Rust toolchain in this image - parity with real arkworks stays unpinned")
+    real = json.load(open(path))
+    ours = json.load(open(os.path.join(HERE, "golden", "appendix_c.json")))
+    checked = 0
+    for key, val in real.items():
+        if key == "provenance":
+            continue
+        assert key in ours, key
+        if isinstance(val, dict):
+            for sub, v in val.items():
+                assert ours[key][sub] == v, (key, sub)
+                checked += 1
+        else:
+            assert ours[key] == val, key
+            checked += 1
+    assert checked >= 20

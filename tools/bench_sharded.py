@@ -79,7 +79,7 @@ def run_c2():
     LOGN = int(os.environ.get("C2_LOG", "20"))
     n = 1 << LOGN
     pp, vp = ts.setup_params(ctx, LOGN - 2)
-    addr, vals_u64, isw = bench.synthetic_trace(LOGN, 16, seed=2)          # same trace on every rank
+    addr, vals_u64, isw = bench.trace_random(LOGN, 16, ts.chacha20_u64(bytes([2]) * 32, 3 << LOGN))          # same trace on every rank
     tw = ts.Twist.new(pp)
     lo, hi = tw.shard_range(n, rank, world)
     a_pin = torch.empty(hi - lo, dtype=torch.int64, pin_memory=True); a_pin.numpy().view(np.uint64)[:] = addr[lo:hi]

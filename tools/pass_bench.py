@@ -11,7 +11,7 @@ B = import_module("multilinear-map-cryptography_b200.binding")
 ctx = ts.Context(0)
 pp, vp = ts.setup_params(ctx, 18)
 n = 1 << 20
-addr, vals_u64, isw = bench.synthetic_trace(20, 16, 2)
+addr, vals_u64, isw = bench.trace_random(20, 16, ts.chacha20_u64(bytes([2]) * 32, 3 << 20))
 pa = ctx.poly_from_u64(addr, n); pv = ctx.poly_upload_padded(ts.fe_vec(vals_u64), n)
 lib = B.lib()
 arr = (C.c_void_p * 2)(pa._h, pv._h)

@@ -9,7 +9,7 @@ stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
 ctx = ts.Context(0, stream.cuda_stream)
 pp, vp = ts.setup_params(ctx, 18)
 n = 1 << 20
-addr, vals_u64, isw = bench.synthetic_trace(20, 16, 2)
+addr, vals_u64, isw = bench.trace_random(20, 16, ts.chacha20_u64(bytes([2]) * 32, 3 << 20))
 vals = ts.fe_vec(vals_u64)
 addr_pin = torch.empty(n, dtype=torch.int64, pin_memory=True); addr_pin.numpy().view(np.uint64)[:] = addr
 vals_pin = torch.empty((n, 4), dtype=torch.int64, pin_memory=True); vals_pin.numpy().view(np.uint64)[:] = vals
