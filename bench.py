@@ -432,6 +432,7 @@ def main():
                      "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": int(a_s.nbytes + v_s.nbytes), "d2h_bytes_per_step": int(4 * 16 * 96 + 2 * 32),
                              "note": "bytes per rank; every rank uploads its slice of the trace"},
                      "gpu_launches": int(launches), "ops_per_s": n / (dev_ms * 1e-3),
+                     "exchange": "peer mailboxes over NVLink (single-kernel all-gathers)" if ctx.comm_peer_exchange else "ncclAllGather",
                      "replicas": {"value": rep_ms, "unit": "ms", "scaling": "weak", "what": "one independent proof per GPU from host buffers", "ops_per_s_all_gpus": world * n / (rep_ms * 1e-3)},
                      "roofline": {"kernel": "k_msm_accumulate", "bound": "int32-pipe", "achieved": None, "peak": IMAD_PEAK_TOPS, "unit": "TIMAD/s", "frac": None, "traffic": None,
                                   "note": "per-kernel accounting is reported by the N = 1 line; at N > 1 the step is latency-bound (collectives + fixed per-pass launch chains)"}})
@@ -533,6 +534,16 @@ def bench_c4(ts, dd, ctx, rank, world, timed, max_over_ranks, hbm_peak, hbm_src,
         out[name] = ms
         del clones, it
     ctx.set_tuning("deferred_claim_check", 0)
+    if world > 1:
+        out["exchange"] = "peer mailboxes over NVLink: round sums inside the round kernel, no NCCL call per round" if ctx.comm_peer_exchange else "ncclAllReduce per round"
+        if ctx.comm_peer_exchange:                            # the same proof over the NCCL collectives, for comparison
+            ctx.set_tuning("peer_exchange", 0)
+            clones = [[A.clone(), B.clone()] for _ in range(steps + 2)]
+            it = iter(clones)
+            (out["ms_nccl_allreduce_per_round"],) = max_over_ranks(timed(lambda: prove(next(it)), steps, 2))
+            ctx.set_tuning("peer_exchange", 1)
+            del clones, it
+        out["link_bytes_per_round_per_rank"] = 2 * 32 * (world - 1)    # two field elements (g(0), g(2)) to each peer
     gbs = 128.0 * 2 * N / (out["ms"] * 1e-3) / 1e9
     out["roofline"] = {"kernel": "k_round_eval<2> + k_bind_eval2_claim (whole protocol)", "bound": "hbm", "achieved": gbs, "peak": hbm_peak * world, "unit": "GB/s",
                        "frac": gbs / (hbm_peak * world), "traffic": None, "algorithmic_bytes": 256.0 * N, "peak_source": hbm_src + (f" x {world} GPUs" if world > 1 else ""),

@@ -280,6 +280,9 @@ void tsgpu_fr_from_limb_sums(const uint64_t* sums, size_t n, tsgpu_fr* out);
 int tsgpu_comm_unique_id(uint8_t out[128]);
 int tsgpu_comm_init(tsgpu_ctx* ctx, int nranks, int rank, const uint8_t id[128]);
 int tsgpu_comm_size(const tsgpu_ctx* ctx);
+/* 1 when the ranks exchange over peer-mapped mailboxes (CUDA IPC over NVLink / NVSwitch): the sharded sum-check sums its round values inside the
+ * round kernel and the small all-gathers are one single-block kernel; 0: NCCL collectives (no peer access, or tsgpu_set_tuning("peer_exchange", 0)) */
+int tsgpu_comm_peer_exchange(const tsgpu_ctx* ctx);
 int tsgpu_comm_rank(const tsgpu_ctx* ctx);
 void tsgpu_comm_destroy(tsgpu_ctx* ctx);
 /* all-gather of `bytes` (multiple of 8) per rank, host to host: e.g. per-rank partial MSM results (point-sliced commitment),

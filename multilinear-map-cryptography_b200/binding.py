@@ -147,6 +147,11 @@ class Context:
         return int(lib().tsgpu_comm_size(self._h))
 
     @property
+    def comm_peer_exchange(self) -> bool:
+        """True when the ranks exchange through peer-mapped mailboxes (round sums inside the round kernel) instead of NCCL collectives"""
+        return bool(lib().tsgpu_comm_peer_exchange(self._h))
+
+    @property
     def comm_rank(self) -> int:
         return int(lib().tsgpu_comm_rank(self._h))
 

@@ -173,6 +173,7 @@ int tsgpu_set_tuning(tsgpu_ctx* ctx, const char* key, long value) {
         set_prefetch_min_work(value < 0 || value > 61 ? (size_t)1 << 62 : (size_t)1 << value);
         return TSGPU_OK;
     }
+    if (!strcmp(key, "peer_exchange")) { ctx->peer_exchange = value != 0; return TSGPU_OK; }
     if (!strcmp(key, "deferred_claim_check")) { ctx->deferred_claim_check = value != 0; return TSGPU_OK; }
     if (!strcmp(key, "msm_acc_waves")) { set_msm_acc_waves((int)value); return TSGPU_OK; }
     if (!strcmp(key, "msm_two_level")) { set_msm_two_level(value != 0); return TSGPU_OK; }

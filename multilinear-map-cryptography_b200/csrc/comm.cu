@@ -12,6 +12,7 @@
 // loaded NCCL is the one used.  The host exchanges the 128-byte unique id however it likes (torch.distributed, MPI, a file).
 #include <dlfcn.h>
 #include <nccl.h>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -62,6 +63,14 @@ struct Comm {
     unsigned long long* dev = nullptr;     // 32 limb sums, then gather staging: nranks * 3 field elements
     unsigned long long* host = nullptr;    // pinned mirror
     size_t words = 0;
+    // peer mailboxes (sumcheck.cu): this rank's allocation and every peer's as mapped into this process through CUDA IPC.  With them the round
+    // sums travel inside the round kernel and the small all-gathers are one single-block kernel: no NCCL call on the proving path.
+    bool p2p = false;
+    unsigned char* mbox = nullptr;
+    unsigned char* peer[SC_MAX_PEERS] = {nullptr};
+    unsigned long long* ag_in = nullptr;   // pinned: this rank's all-gather payload
+    unsigned long long* ag_out = nullptr;  // pinned: nranks payloads
+    int* host_err = nullptr;               // pinned: peer time-out flag
 };
 
 int nccl_fail(tsgpu_ctx* ctx, ncclResult_t r, const char* what) {
@@ -80,6 +89,63 @@ __global__ void k_fr_to_limb_sums(const fr_t* in, unsigned n, unsigned long long
 }
 
 Comm* comm_of(tsgpu_ctx* ctx) { return (Comm*)ctx->comm; }
+bool use_p2p(tsgpu_ctx* ctx) { Comm* c = comm_of(ctx); return c && c->p2p && ctx->peer_exchange; }
+
+// Mailboxes: allocate, exchange the CUDA IPC handles over the (already working) NCCL communicator, map every peer's allocation.  Any failure
+// leaves p2p off and the NCCL collectives in use.
+void setup_mailboxes(tsgpu_ctx* ctx, Comm* c) {
+    if (c->nranks < 2 || c->nranks > SC_MAX_PEERS) return;
+    if (const char* env = getenv("TSGPU_NO_PEER_EXCHANGE")) { if (atoi(env)) return; }
+    cudaIpcMemHandle_t mine;
+    const int G = c->nranks;
+    unsigned char* handles_dev = nullptr;
+    std::vector<cudaIpcMemHandle_t> all((size_t)G);
+    bool ok = cudaMalloc((void**)&c->mbox, SC_PEER_MBOX_BYTES) == cudaSuccess && cudaMemset(c->mbox, 0, SC_PEER_MBOX_BYTES) == cudaSuccess &&
+              cudaDeviceSynchronize() == cudaSuccess && cudaIpcGetMemHandle(&mine, c->mbox) == cudaSuccess &&
+              cudaMalloc((void**)&handles_dev, (size_t)(G + 1) * sizeof(mine)) == cudaSuccess;
+    // every rank takes part in the all-gather even if its own set-up failed (a zero handle then tells the peers to stay on NCCL)
+    if (!ok) memset(&mine, 0, sizeof(mine));
+    bool xfer = handles_dev && cudaMemcpyAsync(handles_dev, &mine, sizeof(mine), cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess &&
+                nccl().AllGather(handles_dev, handles_dev + sizeof(mine), sizeof(mine), ncclUint8, c->comm, ctx->stream) == ncclSuccess &&
+                cudaMemcpyAsync(all.data(), handles_dev + sizeof(mine), (size_t)G * sizeof(mine), cudaMemcpyDeviceToHost, ctx->stream) == cudaSuccess &&
+                cudaStreamSynchronize(ctx->stream) == cudaSuccess;
+    if (handles_dev) cudaFree(handles_dev);
+    static const cudaIpcMemHandle_t zero = {};
+    ok = ok && xfer;
+    for (int g = 0; g < G && ok; ++g) ok = memcmp(&all[g], &zero, sizeof(zero)) != 0;
+    for (int g = 0; g < G && ok; ++g) {
+        if (g == c->rank) { c->peer[g] = c->mbox; continue; }
+        void* p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, all[g], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; break; }
+        c->peer[g] = (unsigned char*)p;
+    }
+    ok = ok && cudaMallocHost((void**)&c->ag_in, SC_PEER_AG_DATA) == cudaSuccess && cudaMallocHost((void**)&c->ag_out, SC_PEER_AG_DATA * G) == cudaSuccess &&
+         cudaMallocHost((void**)&c->host_err, sizeof(int)) == cudaSuccess;
+    if (ok) { *c->host_err = 0; ok = sc_peer_configure(c->peer, G, c->rank, c->host_err, ctx->stream) == cudaSuccess; }
+    // all ranks must agree: one more tiny all-reduce (min) of the outcome
+    int flag = ok ? 1 : 0;
+    int* flag_dev = nullptr;
+    if (cudaMalloc((void**)&flag_dev, sizeof(int)) == cudaSuccess) {
+        cudaMemcpyAsync(flag_dev, &flag, sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+        if (nccl().AllReduce(flag_dev, flag_dev, 1, ncclInt32, ncclMin, c->comm, ctx->stream) != ncclSuccess) flag = 0;
+        else { cudaMemcpyAsync(&flag, flag_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream); cudaStreamSynchronize(ctx->stream); }
+        cudaFree(flag_dev);
+    } else flag = 0;
+    cudaGetLastError();
+    c->p2p = flag == 1;
+}
+void release_mailboxes(Comm* c) {
+    for (int g = 0; g < c->nranks && g < SC_MAX_PEERS; ++g)
+        if (c->peer[g] && g != c->rank) cudaIpcCloseMemHandle(c->peer[g]);
+    if (c->mbox) cudaFree(c->mbox);
+    if (c->ag_in) cudaFreeHost(c->ag_in);
+    if (c->ag_out) cudaFreeHost(c->ag_out);
+    if (c->host_err) cudaFreeHost(c->host_err);
+}
+int peer_timeout(tsgpu_ctx* ctx, Comm* c) {
+    if (*c->host_err) { *c->host_err = 0; return fail(ctx, TSGPU_E_PROOF_GENERATION, "peer exchange timed out: a rank of the communicator did not answer"); }
+    return TSGPU_OK;
+}
 
 // exact field sum over the ranks of `n` (<= 4) elements at ctx->dev_out; result to `out` on the host of every rank
 int allreduce_dev_out(tsgpu_ctx* ctx, unsigned n, fr_t* out) {
@@ -138,14 +204,17 @@ int tsgpu_comm_init(tsgpu_ctx* ctx, int nranks, int rank, const uint8_t id[128])
         return fail(ctx, TSGPU_E_PROOF_GENERATION, "communicator buffers");
     }
     ctx->comm = c;
+    if (nranks > 1) setup_mailboxes(ctx, c);
     return TSGPU_OK;
 }
+int tsgpu_comm_peer_exchange(const tsgpu_ctx* ctx) { return ctx && ctx->comm && ((Comm*)ctx->comm)->p2p && ctx->peer_exchange ? 1 : 0; }
 int tsgpu_comm_size(const tsgpu_ctx* ctx) { return ctx && ctx->comm ? ((Comm*)ctx->comm)->nranks : 1; }
 int tsgpu_comm_rank(const tsgpu_ctx* ctx) { return ctx && ctx->comm ? ((Comm*)ctx->comm)->rank : 0; }
 void tsgpu_comm_destroy(tsgpu_ctx* ctx) {
     if (!ctx || !ctx->comm) return;
     Comm* c = (Comm*)ctx->comm;
     cudaStreamSynchronize(ctx->stream);
+    release_mailboxes(c);
     if (c->comm) nccl().CommDestroy(c->comm);
     if (c->dev) cudaFree(c->dev);
     if (c->host) cudaFreeHost(c->host);
@@ -159,6 +228,17 @@ int tsgpu_comm_allgather(tsgpu_ctx* ctx, const void* in, size_t bytes, void* out
     if (!ctx || !in || !out || bytes % 8) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "bad all-gather arguments");
     Comm* c = comm_of(ctx);
     if (!c || c->nranks == 1) { memcpy(out, in, bytes); return TSGPU_OK; }
+    if (use_p2p(ctx) && bytes <= SC_PEER_AG_DATA) {
+        // one single-block kernel: payload from pinned memory into every peer's mailbox, flags, gathered payloads back into pinned memory
+        memcpy(c->ag_in, in, bytes);
+        TSG_CUDA(ctx, launch_peer_allgather(c->ag_in, bytes, c->ag_out, ctx->stream));
+        ctx->launches += 1;
+        TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        int rc = peer_timeout(ctx, c);
+        if (rc) return rc;
+        memcpy(out, c->ag_out, bytes * c->nranks);
+        return TSGPU_OK;
+    }
     const size_t w = bytes / 8;
     TempBuf s, r;
     TSG_CUDA(ctx, s.alloc(bytes, ctx->stream));
@@ -238,13 +318,30 @@ int tsgpu_sumcheck_prove_product_sharded(tsgpu_ctx* ctx, tsgpu_table* const* tab
         return TSGPU_OK;
     };
     int rc;
+    // With peer mailboxes the finishing thread of every round kernel exchanges its sums with the other ranks itself and writes the GLOBAL values to
+    // the pinned mirror: a round is one launch + one stream synchronisation.  Otherwise: kernel -> widen -> ncclAllReduce -> copy (allreduce_dev_out).
+    const bool p2p = use_p2p(ctx) && G > 1;
+    struct PeerScope {          // the switch is stream-ordered: on before the first round kernel, off after the last on every exit path
+        tsgpu_ctx* ctx; bool on;
+        ~PeerScope() { if (on) sc_peer_enable(false, ctx->stream); }
+    } scope{ctx, p2p};
+    if (p2p) TSG_CUDA(ctx, sc_peer_enable(true, ctx->stream));
+    fr_t* round_out = p2p ? ctx->host_out : ctx->dev_out;
+    auto round_values = [&](fr_t* ev) -> int {
+        if (!p2p) return allreduce_dev_out(ctx, 4, ev);
+        TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        int prc = peer_timeout(ctx, c);
+        if (prc) return prc;
+        memcpy(ev, ctx->host_out, 4 * sizeof(fr_t));
+        return TSGPU_OK;
+    };
     // ---- rounds over the local variables
     fr_t ev[4];
     if (n_local) {
         const fr_t zero = fr_t::zero();
-        TSG_CUDA(ctx, launch_round_eval(d, tabs, (size_t)1 << n_local, ctx->partials, ctx->ticket, ctx->dev_out, ctx->sm_count, ctx->stream, deferred ? &zero : nullptr));
+        TSG_CUDA(ctx, launch_round_eval(d, tabs, (size_t)1 << n_local, ctx->partials, ctx->ticket, round_out, ctx->sm_count, ctx->stream, deferred ? &zero : nullptr));
         ctx->launches += 1;
-        if ((rc = allreduce_dev_out(ctx, 4, ev))) return rc;
+        if ((rc = round_values(ev))) return rc;
         if (deferred) {                       // g(1) from the GLOBAL claim after the all-reduce, as in the later rounds
             ev[1] = current - ev[0];
             fr_t dd = ev[2] - ev[1];
@@ -259,9 +356,9 @@ int tsgpu_sumcheck_prove_product_sharded(tsgpu_ctx* ctx, tsgpu_table* const* tab
             // d = 2: the kernel sums g(0) and g(2) only (claim form with claim 0 leaves g(1) slot = -g(0), unused); g(1) follows from
             // the GLOBAL claim after the all-reduce: g(1) = current - g(0), g(3) = g(0) - 3 g(1) + 3 g(2)
             const fr_t zero = fr_t::zero();
-            TSG_CUDA(ctx, launch_bind_eval(d, tabs, n, r, d == 2 ? &zero : nullptr, ctx->partials, ctx->ticket, ctx->dev_out, ctx->sm_count, ctx->stream));
+            TSG_CUDA(ctx, launch_bind_eval(d, tabs, n, r, d == 2 ? &zero : nullptr, ctx->partials, ctx->ticket, round_out, ctx->sm_count, ctx->stream));
             ctx->launches += 1;
-            if ((rc = allreduce_dev_out(ctx, 4, ev))) return rc;
+            if ((rc = round_values(ev))) return rc;
             if (d == 2) {
                 ev[1] = current - ev[0];
                 fr_t dd = ev[2] - ev[1];
@@ -272,6 +369,7 @@ int tsgpu_sumcheck_prove_product_sharded(tsgpu_ctx* ctx, tsgpu_table* const* tab
         }
         for (int t = 0; t < d; ++t) tables[t]->num_vars -= 1;
     }
+    if (p2p) { scope.on = false; TSG_CUDA(ctx, sc_peer_enable(false, ctx->stream)); }
     // ---- one entry per table per rank: gather (rank = high index bits) and finish the last log2 G rounds on every host
     std::vector<fr_t> tail((size_t)G * d);
     {

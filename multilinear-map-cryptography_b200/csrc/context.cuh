@@ -40,6 +40,7 @@ struct tsgpu_ctx {
     bool msm_tables = true;            // SRS handles carry precomputed window tables (tuning "msm_tables", read when an SRS / basis is built)
     bool eval_basis = true;            // Twist/Shout::prove commit through the Lagrange-basis SRS when it exists (tuning "eval_basis")
     bool deferred_claim_check = false; // opt-in (tuning "deferred_claim_check"): SumCheck::prove, d = 2, runs round 0 in the claim form and checks the claimed sum at the end; default = the reference's deterministic round-0 check before anything is appended (sumcheck.rs:77-84)
+    bool peer_exchange = true;         // sharded paths use the peer mailboxes (round sums inside the round kernel, single-kernel all-gathers) when the communicator could map them (tuning "peer_exchange"; 0 = NCCL collectives)
     struct Pending { std::string name; cudaEvent_t a, b; };
     std::vector<Pending> pending;
     std::map<std::string, std::pair<double, uint64_t>> timers;   // name -> (total ms, launches)

@@ -17,11 +17,125 @@
 #include "sumcheck.cuh"
 #include "tma_stream.cuh"
 #include "../host/field64.hpp"
+#include <cstring>
 
 #ifndef TSG_BE_MINB
 #define TSG_BE_MINB 2
 #endif
 namespace tsg {
+
+// ---------------------------------------------------------------- round sums over the ranks, inside the round kernel
+// Sharded SumCheck::prove (comm.cu): every rank sums its slice of the hypercube; the round values are the sums over the ranks.  Instead of
+// a separate widen kernel + ncclAllReduce + copy per round, the FINISHING thread of the round kernel exchanges the block-reduced sums with
+// its peers directly: it stores its NV field elements into slot [parity][rank] of every peer's mailbox (peer-mapped device memory: plain
+// stores that travel over NVLink / NVSwitch), publishes them with a system-scope fence + sequence flag, spins until the G slots of its
+// own mailbox carry the same sequence number, and adds them in rank order (exact modular additions: every rank gets the same bits).  The
+// epilogue then writes the global values to the pinned host mirror as on one GPU.  Two parities: a fast peer may already deliver round
+// k + 1 while this rank still reads round k (it cannot get further ahead: round k + 1 needs this rank's own contribution).
+// State lives in device globals of this translation unit (the kernels are here); comm.cu sets it through sc_peer_*.
+struct PeerState {
+    unsigned char* mbox[SC_MAX_PEERS];   // mailbox of every rank as mapped into THIS process (own rank: the local allocation)
+    int* host_err;                       // pinned: set to 1 when a peer did not answer within the time limit
+    int nranks, rank;
+    unsigned on;                         // exchange enabled for the launches that follow (sharded prove in progress)
+    unsigned seq;                        // exchanges done so far (all ranks run the same sequence of launches)
+};
+__device__ PeerState g_peer;
+constexpr unsigned long long PEER_TIMEOUT_CYCLES = 6000000000ull;   // ~3 s at 2 GHz: a rank that died must not hang the others' GPUs
+
+// 64-bit volatile accesses for everything that crosses the link or is written by a peer (no L1, no wide vector forms on peer mappings)
+__device__ __forceinline__ void peer_store(fr_t* dst, const fr_t& v) {
+    volatile unsigned long long* d = (volatile unsigned long long*)dst;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) d[i] = (unsigned long long)v.l[2 * i] | ((unsigned long long)v.l[2 * i + 1] << 32);
+}
+__device__ __forceinline__ fr_t peer_load(const fr_t* src) {
+    const volatile unsigned long long* s = (const volatile unsigned long long*)src;
+    fr_t r;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const unsigned long long w = s[i]; r.l[2 * i] = (uint32_t)w; r.l[2 * i + 1] = (uint32_t)(w >> 32); }
+    return r;
+}
+
+template <int NV>
+__device__ __noinline__ void peer_sum(fr_t (&v)[NV]) {
+    static_assert(NV * sizeof(fr_t) <= SC_PEER_SLOT_DATA, "slot too small");
+    const int G = g_peer.nranks, me = g_peer.rank;
+    const unsigned seq = g_peer.seq + 1;
+    const size_t par = (size_t)(seq & 1u) * SC_MAX_PEERS * SC_PEER_SLOT;
+    for (int g = 0; g < G; ++g) {
+        fr_t* dst = (fr_t*)(g_peer.mbox[g] + par + (size_t)me * SC_PEER_SLOT);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) peer_store(dst + k, v[k]);
+    }
+    __threadfence_system();
+    for (int g = 0; g < G; ++g)
+        *(volatile unsigned*)(g_peer.mbox[g] + par + (size_t)me * SC_PEER_SLOT + SC_PEER_SLOT_DATA) = seq;
+    const unsigned char* mine = g_peer.mbox[me] + par;
+    const long long t0 = clock64();
+    for (int g = 0; g < G; ++g) {
+        const volatile unsigned* flag = (const volatile unsigned*)(mine + (size_t)g * SC_PEER_SLOT + SC_PEER_SLOT_DATA);
+        while (*flag != seq) {
+            if ((unsigned long long)(clock64() - t0) > PEER_TIMEOUT_CYCLES) { *g_peer.host_err = 1; break; }
+        }
+    }
+    __threadfence_system();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = fr_t::zero();
+    for (int g = 0; g < G; ++g) {
+        const fr_t* src = (const fr_t*)(mine + (size_t)g * SC_PEER_SLOT);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) v[k] = v[k] + peer_load(src + k);
+    }
+    g_peer.seq = seq;
+}
+
+cudaError_t sc_peer_configure(unsigned char* const* mbox, int nranks, int rank, int* host_err, cudaStream_t s) {
+    PeerState st;
+    memset(&st, 0, sizeof(st));
+    for (int g = 0; g < nranks && g < SC_MAX_PEERS; ++g) st.mbox[g] = mbox[g];
+    st.host_err = host_err; st.nranks = nranks; st.rank = rank; st.on = 0; st.seq = 0;
+    cudaError_t e = cudaMemcpyToSymbolAsync(g_peer, &st, sizeof(st), 0, cudaMemcpyHostToDevice, s);
+    return e ? e : cudaStreamSynchronize(s);
+}
+__global__ void k_peer_switch(unsigned on) { g_peer.on = on; }
+cudaError_t sc_peer_enable(bool on, cudaStream_t s) { k_peer_switch<<<1, 1, 0, s>>>(on ? 1u : 0u); return cudaGetLastError(); }
+
+// ---------------------------------------------------------------- small all-gather over the same mailboxes (one block)
+// in: `bytes` (multiple of 8, <= SC_PEER_AG_DATA) of this rank, readable by the device (pinned host memory or HBM); out: nranks * bytes, rank-major
+// (pinned host memory: the host reads it after the stream synchronisation).  Region 2 of the mailbox, own sequence counter.
+__device__ unsigned g_peer_ag_seq;
+__global__ void __launch_bounds__(64) k_peer_allgather(const unsigned long long* in, unsigned words, unsigned long long* out) {
+    const int G = g_peer.nranks, me = g_peer.rank;
+    const unsigned seq = g_peer_ag_seq + 1;
+    const size_t base = (size_t)2 * SC_MAX_PEERS * SC_PEER_SLOT + (size_t)(seq & 1u) * SC_MAX_PEERS * SC_PEER_AG_SLOT;
+    const unsigned t = threadIdx.x;
+    if (t < words) {
+        const unsigned long long w = in[t];
+        for (int g = 0; g < G; ++g) ((unsigned long long*)(g_peer.mbox[g] + base + (size_t)me * SC_PEER_AG_SLOT))[t] = w;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)t < G) {
+        *(volatile unsigned*)(g_peer.mbox[t] + base + (size_t)me * SC_PEER_AG_SLOT + SC_PEER_AG_DATA) = seq;
+        const volatile unsigned* flag = (const volatile unsigned*)(g_peer.mbox[me] + base + (size_t)t * SC_PEER_AG_SLOT + SC_PEER_AG_DATA);
+        const long long t0 = clock64();
+        while (*flag != seq) {
+            if ((unsigned long long)(clock64() - t0) > PEER_TIMEOUT_CYCLES) { *g_peer.host_err = 1; break; }
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (t < words)
+        for (int g = 0; g < G; ++g)
+            out[(size_t)g * words + t] = ((const volatile unsigned long long*)(g_peer.mbox[me] + base + (size_t)g * SC_PEER_AG_SLOT))[t];
+    if (t == 0) g_peer_ag_seq = seq;
+}
+cudaError_t launch_peer_allgather(const void* in, size_t bytes, void* out, cudaStream_t s) {
+    if (bytes % 8 || bytes > SC_PEER_AG_DATA) return cudaErrorInvalidValue;
+    k_peer_allgather<<<1, 64, 0, s>>>((const unsigned long long*)in, (unsigned)(bytes / 8), (unsigned long long*)out);
+    return cudaGetLastError();
+}
 
 // ---------------------------------------------------------------- per-pair evaluation contributions
 template <int D> struct EvalAcc;
@@ -77,6 +191,7 @@ struct EvalAcc2Claim {
 struct EvalClaimEpilogue {
     fr_t* out4; fr_t claim;
     __device__ void operator()(fr_t (&v)[2]) const {
+        if (g_peer.on) peer_sum<2>(v);                 // sharded: v = sums over all ranks; the host derives g(1) from the GLOBAL claim
         fr_t g1 = claim - v[0];
         fr_t d = v[1] - g1;
         out4[0] = v[0]; out4[1] = g1; out4[2] = v[1]; out4[3] = v[0] + d + d + d;
@@ -105,6 +220,7 @@ template <int D>
 struct EvalEpilogue {
     fr_t* out4;
     __device__ void operator()(fr_t (&v)[EvalAcc<D>::NV]) const {
+        if (g_peer.on) peer_sum<EvalAcc<D>::NV>(v);    // sharded: sums over all ranks (extrapolation is linear, so it commutes with the sum)
         fr_t o[4];
         EvalAcc<D>::expand(v, o);
         for (int i = 0; i < 4; ++i) out4[i] = o[i];

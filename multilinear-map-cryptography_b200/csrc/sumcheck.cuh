@@ -28,6 +28,17 @@ constexpr size_t TMA_MIN_WORK = TSG_TMA_MIN_WORK;  // below this the simple grid
 
 struct ScTables { fr_t* t[SC_MAX_TABLES]; };
 
+// peer mailboxes of the sharded sum-check (sumcheck.cu "round sums over the ranks"): per rank one device allocation of SC_PEER_MBOX_BYTES,
+// region 1: 2 parities x SC_MAX_PEERS slots of SC_PEER_SLOT bytes (round sums: up to 4 field elements + flag),
+// region 2: 2 parities x SC_MAX_PEERS slots of SC_PEER_AG_SLOT bytes (small all-gathers: up to SC_PEER_AG_DATA bytes + flag)
+constexpr int SC_MAX_PEERS = 8;
+constexpr size_t SC_PEER_SLOT = 256, SC_PEER_SLOT_DATA = 128;
+constexpr size_t SC_PEER_AG_SLOT = 512, SC_PEER_AG_DATA = 448;
+constexpr size_t SC_PEER_MBOX_BYTES = 2 * SC_MAX_PEERS * (SC_PEER_SLOT + SC_PEER_AG_SLOT);
+cudaError_t sc_peer_configure(unsigned char* const* mbox, int nranks, int rank, int* host_err, cudaStream_t s);
+cudaError_t sc_peer_enable(bool on, cudaStream_t s);     // stream-ordered switch: the round kernels launched after it exchange their sums with the peers
+cudaError_t launch_peer_allgather(const void* in, size_t bytes, void* out, cudaStream_t s);
+
 // number of blocks the evaluation kernels may launch (sizes the partial-sum scratch)
 inline int sc_max_grid(int sm_count) { return sm_count * SC_BLOCKS_PER_SM_BIND; }
 

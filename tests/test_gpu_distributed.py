@@ -79,9 +79,24 @@ def _native_worker(rank, world, port, nv, d, q):
             tot = (tot + p) % O.R_MOD
         claimed = O.fr_from_ints([tot])[0]
         ref = O.sumcheck_prove_product(tables, claimed, mode="tables")
-        proof, chals, finals = ts.SumCheck(nv, claimed).prove_product_sharded(ctx, [ctx.table_upload(t[lo:hi]) for t in full], ts.Transcript(), return_aux=True)
-        ok = (proof.round_polynomials == ref["round_polynomials"]).all() and (proof.final_evaluation == ref["final_evaluation"]).all()
-        ok = ok and (finals == ref["finals"]).all()
+        ok = True
+        # both exchange paths (peer mailboxes: the round sums travel inside the round kernel; NCCL: all-reduce per round), both round-0 forms, and a
+        # wrong claim, which every rank must reject with the reference's error
+        for peer in ((1, 0) if ctx.comm_peer_exchange else (0,)):
+            ctx.set_tuning("peer_exchange", peer)
+            for deferred in (0, 1):
+                ctx.set_tuning("deferred_claim_check", deferred)
+                proof, chals, finals = ts.SumCheck(nv, claimed).prove_product_sharded(ctx, [ctx.table_upload(t[lo:hi]) for t in full], ts.Transcript(), return_aux=True)
+                ok = ok and (proof.round_polynomials == ref["round_polynomials"]).all() and (proof.final_evaluation == ref["final_evaluation"]).all()
+                ok = ok and (finals == ref["finals"]).all() and (chals == ref["challenges"]).all()
+                try:
+                    ts.SumCheck(nv, ts.fe(12345)).prove_product_sharded(ctx, [ctx.table_upload(t[lo:hi]) for t in full], ts.Transcript())
+                    ok = False
+                except ts.TwistAndShoutError as e:
+                    ok = ok and e.variant == "SumCheck" and "Round 0 consistency check failed" in str(e)
+            ctx.set_tuning("deferred_claim_check", 0)
+        ctx.set_tuning("peer_exchange", 1)
+        q.put(("peer_exchange", rank, ctx.comm_peer_exchange))
         # sharded MultilinearExtension::evaluate of table 0
         pt = O.chacha_fr_rand(bytes([90]) * 32, nv).reshape(nv, 4)
         got = ctx.table_upload(full[0][lo:hi]).evaluate_sharded(nv, pt)
@@ -106,7 +121,10 @@ def test_native_sharded_sumcheck_two_gpus_library_nccl(nv, d):
         p.start()
     for p in procs:
         p.join(timeout=300)
-    assert sorted(q.get(timeout=5) for _ in range(2)) == [(0, True), (1, True)]
+    got = [q.get(timeout=5) for _ in range(4)]
+    assert sorted(x for x in got if len(x) == 2) == [(0, True), (1, True)]
+    peers = sorted(x[1:] for x in got if len(x) == 3)
+    assert peers[0][1] == peers[1][1]                       # both ranks agree on the exchange path (NVLink boxes: peer mailboxes)
 
 
 def test_sharded_twist_one_rank_equals_plain_prove(tsgpu):
@@ -171,8 +189,11 @@ def _twist_worker(rank, world, port, q):
             vals = O.chacha_fr_rand(bytes([nops % 251]) * 32, nops).reshape(nops, 4) if wide else ts.fe_vec(rng.integers(0, 1 << 63, size=nops, dtype=np.uint64))
             tw = ts.Twist.new(pp)
             lo, hi = tw.shard_range(nops, rank, world)
+            ctx.set_tuning("peer_exchange", 0)                      # NCCL all-gathers
+            via_nccl = tw.prove_sharded(addr[lo:hi], vals[lo:hi], nops)
+            ctx.set_tuning("peer_exchange", 1)                      # single-kernel all-gathers over the peer mailboxes (when mapped)
             sharded = tw.prove_sharded(addr[lo:hi], vals[lo:hi], nops)
-            ok = ok and tw.verify(sharded, vp)
+            ok = ok and tw.verify(sharded, vp) and sharded.to_bytes() == via_nccl.to_bytes()
             if rank == 0:
                 ok = ok and sharded.to_bytes() == tw.prove_arrays(addr, vals).to_bytes()      # one-GPU proof of the whole trace
             gathered = ctx.comm_allgather(np.frombuffer(sharded.to_bytes()[:64], dtype=np.uint64))
