@@ -176,6 +176,7 @@ int tsgpu_set_tuning(tsgpu_ctx* ctx, const char* key, long value) {
     if (!strcmp(key, "peer_exchange")) { ctx->peer_exchange = value != 0; return TSGPU_OK; }
     if (!strcmp(key, "deferred_claim_check")) { ctx->deferred_claim_check = value != 0; return TSGPU_OK; }
     if (!strcmp(key, "msm_acc_waves")) { set_msm_acc_waves((int)value); return TSGPU_OK; }
+    if (!strcmp(key, "msm_scatter_slice_mb")) { set_msm_scatter_slice(value > 0 ? (size_t)value << 20 : 0); return TSGPU_OK; }
     if (!strcmp(key, "msm_two_level")) { set_msm_two_level(value != 0); return TSGPU_OK; }
     if (!strcmp(key, "kernel_timing")) { ctx->timing = value != 0; return TSGPU_OK; }
     if (!strcmp(key, "msm_tables")) { ctx->msm_tables = value != 0; return TSGPU_OK; }   // 0: per-window bucket sets on the plain SRS points
