@@ -348,6 +348,8 @@ int tsgpu_table_memory_values(tsgpu_ctx* ctx, const uint64_t* addresses, const u
 int tsgpu_table_one_hot_weighted(tsgpu_ctx* ctx, const tsgpu_table* weights, const uint64_t* addresses, const uint8_t* select, int flag, size_t n,
                                  unsigned log_cells, tsgpu_table** out);
 int tsgpu_table_mul(tsgpu_ctx* ctx, const tsgpu_table* a, const tsgpu_table* b, tsgpu_table** out);
+/* table(x, j) <- rows(j) - table(x, j) in place (rows: the cycle variables only; table: cells x cycles) - wv(j) - Val(x, j) of Twist write-checking */
+int tsgpu_table_broadcast_rows_minus(tsgpu_ctx* ctx, const tsgpu_table* rows, tsgpu_table* table);
 int tsgpu_table_lt_point(tsgpu_ctx* ctx, const tsgpu_fr* point, unsigned num_vars, tsgpu_table** out);
 
 /* ---- The lookup-correctness sum-check the reference leaves as a stub (src/shout.rs:157-184: the closure returns zero on every branch
@@ -390,6 +392,18 @@ int tsgpu_twist_memory_check_prove(tsgpu_ctx* ctx, const uint64_t* addresses, co
 int tsgpu_twist_memory_check_verify(tsgpu_ctx* ctx, const uint64_t* addresses, const tsgpu_fr* values, const uint8_t* is_write, size_t num_operations,
                                     size_t memory_size, tsgpu_transcript* transcript, const tsgpu_fr claims[2], const tsgpu_fr* rounds1, size_t num_rounds1,
                                     const tsgpu_fr* final1, const tsgpu_fr* rounds2, size_t num_rounds2, const tsgpu_fr* final2, int* valid);
+/* ---- write-checking, the third sum-check of Twist (with its own Val-evaluation): Inc_j = [write_j] (value_j - Val(address_j, j)) is consistent with
+ * the written values and Val,   sum_j eq(r', j) Inc_j  =  sum_{x, j} ( eq(r', j) [write_j] ra(x, j) ) * ( value_j - Val(x, j) )   (k + t rounds),
+ * ending in a claim Val~(x**, j**) that a second Val-evaluation sum-check (t rounds) proves.  Labels: "memory_write_statement" (digest),
+ * "memory_write_point", "memory_write_claim", "memory_val_claim_2".  Runs on the caller's transcript - normally right after
+ * tsgpu_twist_memory_check_prove on the same one.  claims[2] = {write claim, Val~(x**, j**)}; rounds3 (k + t) x 4, final3; rounds4 t x 4, final4.
+ * A write whose recorded value differs from what the later reads return is caught by read-checking; a wrong Inc / Val pairing by this one. */
+int tsgpu_twist_write_check_prove(tsgpu_ctx* ctx, const uint64_t* addresses, const tsgpu_fr* values, const uint8_t* is_write, size_t num_operations,
+                                  size_t memory_size, tsgpu_transcript* transcript, tsgpu_fr claims[2], tsgpu_fr* rounds3, tsgpu_fr* final3,
+                                  tsgpu_fr* rounds4, tsgpu_fr* final4);
+int tsgpu_twist_write_check_verify(tsgpu_ctx* ctx, const uint64_t* addresses, const tsgpu_fr* values, const uint8_t* is_write, size_t num_operations,
+                                   size_t memory_size, tsgpu_transcript* transcript, const tsgpu_fr claims[2], const tsgpu_fr* rounds3, size_t num_rounds3,
+                                   const tsgpu_fr* final3, const tsgpu_fr* rounds4, size_t num_rounds4, const tsgpu_fr* final4, int* valid);
 /* Twist::verify / Shout::verify (src/twist.rs:255-304, src/shout.rs:225-274): transcript replay, SumCheck::verify and
  * the two KZGCommitment::verify pairing checks (src/commitments.rs:201-228) - all on the CPU, as in the reference. */
 int tsgpu_twist_verify(tsgpu_ctx* ctx, const tsgpu_params* params, const tsgpu_proof* proof, int* valid);

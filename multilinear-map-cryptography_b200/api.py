@@ -568,13 +568,16 @@ class ShoutReadCheck:
 
 
 class TwistMemoryCheck:
-    """The memory-consistency sum-checks the reference leaves as a stub (src/twist.rs:181-214): read-checking over (cell, cycle) and the
-    Val-evaluation sum-check, on one transcript.  NOT part of the reference's proofs (non-parity extension): Twist.prove stays
+    """The memory-consistency sum-checks the reference leaves as a stub (src/twist.rs:181-214): read-checking over (cell, cycle) with its
+    Val-evaluation sum-check, then write-checking (Inc consistent with the written values and Val) with its own, all on one transcript.  NOT part of the reference's proofs (non-parity extension): Twist.prove stays
     byte-identical to the reference; this proves that every Read of a MemoryTrace returns the value last written to its address."""
 
     class Proof:
-        def __init__(self, claims, part1: SumCheckProof, part2: SumCheckProof):
+        def __init__(self, claims, part1: SumCheckProof, part2: SumCheckProof, write_claims=None, part3: Optional[SumCheckProof] = None,
+                     part4: Optional[SumCheckProof] = None):
             self.claims, self.read_check, self.val_evaluation = claims, part1, part2
+            # write-checking (the third sum-check of Twist) and the Val-evaluation of the claim it ends in
+            self.write_claims, self.write_check, self.write_val_evaluation = write_claims, part3, part4
 
     def __init__(self, ctx: Context):
         self.ctx = ctx
@@ -599,7 +602,14 @@ class TwistMemoryCheck:
         r2 = np.zeros((max(t, 1), 4, 4), dtype=np.uint64); f2 = np.zeros(4, dtype=np.uint64)
         self.ctx.check(lib().tsgpu_twist_memory_check_prove(self.ctx._h, _p(addr), _p(vals), _p(isw), C.c_size_t(addr.shape[0]), C.c_size_t(memory_size),
                                                             transcript._h, _p(claims), _p(r1), _p(f1), _p(r2), _p(f2)))
-        return TwistMemoryCheck.Proof(claims, SumCheckProof(r1[:k + t], f1), SumCheckProof(r2[:t], f2))
+        # write-checking on the same transcript (tsgpu_twist_write_check_prove)
+        wclaims = np.zeros((2, 4), dtype=np.uint64)
+        r3 = np.zeros((max(k + t, 1), 4, 4), dtype=np.uint64); f3 = np.zeros(4, dtype=np.uint64)
+        r4 = np.zeros((max(t, 1), 4, 4), dtype=np.uint64); f4 = np.zeros(4, dtype=np.uint64)
+        self.ctx.check(lib().tsgpu_twist_write_check_prove(self.ctx._h, _p(addr), _p(vals), _p(isw), C.c_size_t(addr.shape[0]), C.c_size_t(memory_size),
+                                                           transcript._h, _p(wclaims), _p(r3), _p(f3), _p(r4), _p(f4)))
+        return TwistMemoryCheck.Proof(claims, SumCheckProof(r1[:k + t], f1), SumCheckProof(r2[:t], f2), wclaims, SumCheckProof(r3[:k + t], f3),
+                                      SumCheckProof(r4[:t], f4))
 
     def verify(self, trace: "MemoryTrace", proof: "TwistMemoryCheck.Proof", transcript: Transcript) -> bool:
         addr, vals, isw = trace.arrays()
@@ -617,6 +627,15 @@ class TwistMemoryCheck:
         self.ctx.check(lib().tsgpu_twist_memory_check_verify(self.ctx._h, _p(addr), _p(vals), _p(isw), C.c_size_t(addr.shape[0]), C.c_size_t(memory_size),
                                                              transcript._h, _p(claims), _p(r1), C.c_size_t(r1.shape[0]), _p(f1),
                                                              _p(r2), C.c_size_t(r2.shape[0]), _p(f2), C.byref(ok)))
+        if not ok.value or proof.write_check is None:
+            return bool(ok.value)
+        wclaims = np.ascontiguousarray(proof.write_claims, dtype=np.uint64).reshape(2, 4)
+        r3 = np.ascontiguousarray(proof.write_check.round_polynomials, dtype=np.uint64).reshape(-1, 4, 4)
+        r4 = np.ascontiguousarray(proof.write_val_evaluation.round_polynomials, dtype=np.uint64).reshape(-1, 4, 4)
+        f3 = _fr(proof.write_check.final_evaluation, 1); f4 = _fr(proof.write_val_evaluation.final_evaluation, 1)
+        self.ctx.check(lib().tsgpu_twist_write_check_verify(self.ctx._h, _p(addr), _p(vals), _p(isw), C.c_size_t(addr.shape[0]), C.c_size_t(memory_size),
+                                                            transcript._h, _p(wclaims), _p(r3), C.c_size_t(r3.shape[0]), _p(f3),
+                                                            _p(r4), C.c_size_t(r4.shape[0]), _p(f4), C.byref(ok)))
         return bool(ok.value)
 
 

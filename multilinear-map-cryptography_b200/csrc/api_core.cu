@@ -176,7 +176,6 @@ int tsgpu_set_tuning(tsgpu_ctx* ctx, const char* key, long value) {
     if (!strcmp(key, "peer_exchange")) { ctx->peer_exchange = value != 0; return TSGPU_OK; }
     if (!strcmp(key, "deferred_claim_check")) { ctx->deferred_claim_check = value != 0; return TSGPU_OK; }
     if (!strcmp(key, "msm_acc_waves")) { set_msm_acc_waves((int)value); return TSGPU_OK; }
-    if (!strcmp(key, "msm_scatter_slice_mb")) { set_msm_scatter_slice(value > 0 ? (size_t)value << 20 : 0); return TSGPU_OK; }
     if (!strcmp(key, "msm_two_level")) { set_msm_two_level(value != 0); return TSGPU_OK; }
     if (!strcmp(key, "kernel_timing")) { ctx->timing = value != 0; return TSGPU_OK; }
     if (!strcmp(key, "msm_tables")) { ctx->msm_tables = value != 0; return TSGPU_OK; }   // 0: per-window bucket sets on the plain SRS points
@@ -494,6 +493,14 @@ int tsgpu_table_one_hot_weighted(tsgpu_ctx* ctx, const tsgpu_table* weights, con
     }
     TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *out = o;
+    return TSGPU_OK;
+}
+// table(x, j) <- rows(j) - table(x, j) in place: `rows` has log_cycles variables, `table` log_cells + log_cycles (reference index x + 2^log_cells j)
+int tsgpu_table_broadcast_rows_minus(tsgpu_ctx* ctx, const tsgpu_table* rows, tsgpu_table* table) {
+    if (!ctx || !rows || !table) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    if (rows->num_vars > table->num_vars) return fail(ctx, TSGPU_E_POLYNOMIAL, "Number of variables must match");
+    TSG_CUDA(ctx, launch_broadcast_rows_minus(rows->d, rows->num_vars, table->d, (size_t)1 << table->num_vars, ctx->sm_count, ctx->stream));
+    ctx->launches += 1;
     return TSGPU_OK;
 }
 // elementwise product of two tables of equal size

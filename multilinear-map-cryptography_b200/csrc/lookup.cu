@@ -113,6 +113,14 @@ __global__ void __launch_bounds__(256) k_one_hot_weighted(const fr_t* W, const u
     }
 }
 
+// inout[(x, j)] = rows[j] - inout[(x, j)]: a per-cycle vector broadcast over the cells minus the table (write-checking: wv(j) - Val(x, j)).
+// Position (bitrev_k(x) << t) | bitrev_t(j): the row value of a position is rows[pos & (2^t - 1)] - contiguous, coalesced.
+__global__ void __launch_bounds__(256) k_broadcast_rows_minus(const fr_t* rows, unsigned t, fr_t* inout, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t mask = ((size_t)1 << t) - 1;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) st256(inout + i, ld256_nc(rows + (i & mask)) - ld256_stream(inout + i));
+}
+
 // out = a * b elementwise (full Montgomery products; layout-agnostic)
 __global__ void __launch_bounds__(256) k_table_mul(const fr_t* a, const fr_t* b, fr_t* out, size_t n) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -148,6 +156,10 @@ cudaError_t launch_one_hot_weighted(const fr_t* W, const unsigned long long* add
                                     fr_t* out, int sm_count, cudaStream_t s) {
     if (!n) return cudaSuccess;
     k_one_hot_weighted<<<grid_for(n, 256, (size_t)sm_count * 8), 256, 0, s>>>(W, addr, sel, flag, n, k, t, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_broadcast_rows_minus(const fr_t* rows, unsigned t, fr_t* inout, size_t n, int sm_count, cudaStream_t s) {
+    k_broadcast_rows_minus<<<grid_for(n, 256, (size_t)sm_count * 8), 256, 0, s>>>(rows, t, inout, n);
     return cudaGetLastError();
 }
 cudaError_t launch_table_mul(const fr_t* a, const fr_t* b, fr_t* out, size_t n, int sm_count, cudaStream_t s) {

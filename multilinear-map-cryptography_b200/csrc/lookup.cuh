@@ -20,6 +20,8 @@ cudaError_t launch_val_fill(const unsigned long long* wa, const unsigned long lo
 // out[addr[j] + 2^k j] = W[j] for j < n with sel[j] == flag (pre-zeroed 2^(k + t) table; W: 2^t entries in table order)
 cudaError_t launch_one_hot_weighted(const fr_t* W, const unsigned long long* addr, const unsigned char* sel, unsigned char flag, size_t n, unsigned k, unsigned t,
                                     fr_t* out, int sm_count, cudaStream_t s);
+// inout[(x, j)] = rows[j] - inout[(x, j)] over a 2^(k + t)-entry (cell, cycle) table (n entries), rows: 2^t entries in table order
+cudaError_t launch_broadcast_rows_minus(const fr_t* rows, unsigned t, fr_t* inout, size_t n, int sm_count, cudaStream_t s);
 cudaError_t launch_table_mul(const fr_t* a, const fr_t* b, fr_t* out, size_t n, int sm_count, cudaStream_t s);
 // V[a] = LT~(a, b): the less-than indicator [a < c] (natural integer order) extended multilinearly in c and evaluated at the field point b
 cudaError_t launch_lt_point_table(const fr_t* b_dev, unsigned t, fr_t* out, int sm_count, cudaStream_t s);

@@ -149,11 +149,8 @@ static cudaError_t exclusive_scan_u32(const unsigned* in, unsigned* out, size_t 
 
 // ---------------------------------------------------------------- 3. scatter point indices into bucket order
 // entry = index into the job's base array (+ sign): i for per-window bucket sets, w * point_stride + i into the precomputed tables
-// [b_lo, b_hi): only the entries of these buckets are placed by this launch.  A large MSM is scattered in several passes over bucket ranges whose
-// slices of `sorted` fit the L2 (msm_run): the 4-byte writes of a pass then merge in the cache instead of each costing a DRAM sector
-// read-modify-write; the digits are re-read once per pass, sequentially.
 __global__ void k_msm_scatter(const unsigned* dig, size_t n, unsigned c, unsigned W, const unsigned* offsets, unsigned* cursor, unsigned* sorted,
-                              unsigned set_stride, size_t point_stride, unsigned b_lo, unsigned b_hi) {
+                              unsigned set_stride, size_t point_stride) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const size_t total = (size_t)W * n;
     const unsigned lane = threadIdx.x & 31;
@@ -162,8 +159,7 @@ __global__ void k_msm_scatter(const unsigned* dig, size_t n, unsigned c, unsigne
         unsigned v = t < total ? dig[t] : 0u;
         unsigned d = v & 0x7fffffffu;
         size_t w = t / n, i = t - w * n;
-        unsigned b = d ? (unsigned)(w * set_stride + d - 1) : 0xffffffffu;
-        if (b < b_lo || b >= b_hi) { b = 0xffffffffu; d = 0; }
+        const unsigned b = d ? (unsigned)(w * set_stride + d - 1) : 0xffffffffu;
         const unsigned peers = __match_any_sync(0xffffffffu, b);
         const unsigned leader = __ffs(peers) - 1;
         unsigned base = 0;
@@ -524,8 +520,6 @@ unsigned msm_table_window_bits(size_t n) {
     return lg;
 }
 
-static size_t g_msm_scatter_slice = (size_t)64 << 20;   // bytes of `sorted` one scatter pass may write (0: one pass); B200 L2 = 126 MB
-void set_msm_scatter_slice(size_t bytes) { g_msm_scatter_slice = bytes; }
 static bool g_msm_two_level = false;   // measured on B200: 2^20-op Twist proof reduce 1.30 -> 1.35 ms, 2^24-point MSM 1.83 -> 1.62 ms: no gain where it matters, so opt-in
 void set_msm_two_level(bool on) { g_msm_two_level = on; }
 static int g_msm_acc_waves = 0;      // > 0: grid of k_msm_accumulate = that many resident waves; 0: 16 blocks per SM, scheduled dynamically (measured faster:
@@ -581,7 +575,6 @@ cudaError_t msm_run(const MsmJob* jobs, int K, const MsmLayout& L, unsigned char
     g1_xyzz* partial = (g1_xyzz*)(scratch + L.partial); g1_xyzz* blockres = (g1_xyzz*)(scratch + L.blockres);
     g1_jac* wout = (g1_jac*)(scratch + L.window_out);
     cudaError_t e;
-    unsigned scatter_launches = 0;
     if (ev) cudaEventRecord(ev[0], s);
     // hist and cursor are adjacent-independent regions: clear both
     if ((e = cudaMemsetAsync(hist, 0, L.nbuckets * 4, s))) return e;
@@ -600,20 +593,9 @@ cudaError_t msm_run(const MsmJob* jobs, int K, const MsmLayout& L, unsigned char
         k_msm_digits<<<gridfor(jobs[k].n, 256, cap), 256, 0, s>>>(jobs[k].scalars, jobs[k].n, L.c, L.W, dig + (size_t)k * L.W * L.nmax,
                                                                    hist + k * buckets_per_job, set_stride);
     exclusive_scan_u32(hist, offsets, L.nbuckets, (unsigned*)(scratch + L.scan_tmp), n_items + 1, s);   // n_items[1] = bucket entries (non-zero digits)
-    for (int k = 0; k < K; ++k) {
-        // passes over bucket ranges: the slice of `sorted` one pass writes stays within g_msm_scatter_slice bytes (uniform digits assumed; short
-        // scalars fill few buckets and few entries, where the split costs nothing)
-        const size_t job_bytes = (size_t)L.W * jobs[k].n * 4;
-        unsigned passes = g_msm_scatter_slice ? (unsigned)((job_bytes + g_msm_scatter_slice - 1) / g_msm_scatter_slice) : 1u;
-        if (passes < 1) passes = 1;
-        if (passes > 64) passes = 64;
-        for (unsigned r = 0; r < passes; ++r) {
-            const unsigned b_lo = (unsigned)(buckets_per_job * r / passes), b_hi = (unsigned)(buckets_per_job * (r + 1) / passes);
-            k_msm_scatter<<<gridfor((size_t)L.W * jobs[k].n, 256, cap), 256, 0, s>>>(dig + (size_t)k * L.W * L.nmax, jobs[k].n, L.c, L.W, offsets + k * buckets_per_job,
-                                                                                     cursor + k * buckets_per_job, sorted, set_stride, L.shared ? jobs[k].stride : 0, b_lo, b_hi);
-        }
-        scatter_launches += passes;
-    }
+    for (int k = 0; k < K; ++k)
+        k_msm_scatter<<<gridfor((size_t)L.W * jobs[k].n, 256, cap), 256, 0, s>>>(dig + (size_t)k * L.W * L.nmax, jobs[k].n, L.c, L.W, offsets + k * buckets_per_job,
+                                                                                 cursor + k * buckets_per_job, sorted, set_stride, L.shared ? jobs[k].stride : 0);
     k_msm_item_counts<<<gridfor(L.nbuckets, 256, cap), 256, 0, s>>>(hist, L.nbuckets, items, n_items + 2);
     exclusive_scan_u32(items, item_off, L.nbuckets, (unsigned*)(scratch + L.scan_tmp), n_items, s);
     k_msm_item_fill<<<gridfor(L.nbuckets, 256, cap), 256, 0, s>>>(items, item_off, hist, L.nbuckets, item_bucket, len_hist);
@@ -667,7 +649,7 @@ cudaError_t msm_run(const MsmJob* jobs, int K, const MsmLayout& L, unsigned char
         }
     }
     if (ev) cudaEventRecord(ev[4], s);
-    if (launches) *launches += 16 + (unsigned)K + scatter_launches + (g_msm_two_level && L.span_bits >= 6 ? 2u : 0u);
+    if (launches) *launches += 16 + 2 * (unsigned)K + (g_msm_two_level && L.span_bits >= 6 ? 2u : 0u);
     return cudaGetLastError();
 }
 

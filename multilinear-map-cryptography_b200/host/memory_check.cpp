@@ -9,7 +9,10 @@
 //   0. transcript <- digest(statement) (host/statement_digest.hpp), so that every challenge depends on the whole trace
 //   1. read-checking   sum_j eq(r, j) [read_j] value_j = sum_{x, j} ( eq(r, j) [read_j] ra(x, j) ) * Val(x, j)          k + t rounds
 //   2. Val-evaluation  Val~(x*, j*) = sum_j' ( Inc_j' eq(x*, address_j') ) * LT~(j', j*)                                  t rounds
-//   Both are SumCheck::prove (src/sumcheck.rs:56-110) on the product closures, driven by host/sumcheck_host.cpp on one transcript.
+//   3. write-checking  sum_j eq(r', j) Inc_j = sum_{x, j} ( eq(r', j) [write_j] ra(x, j) ) * ( value_j - Val(x, j) )              k + t rounds
+//   4. Val-evaluation of the Val~ claim that 3 ends in                                                                    t rounds
+//      (tsgpu_twist_write_check_prove / _verify, at the end of this file)
+//   All are SumCheck::prove (src/sumcheck.rs:56-110) on the product closures, driven by host/sumcheck_host.cpp on one transcript.
 //   The verifier has the statement in the clear and recomputes the two closing values from it (device gathers and inner products).
 #include <cstring>
 #include <string>
@@ -54,22 +57,25 @@ int check_statement(tsgpu_ctx* ctx, const uint64_t* addresses, const tsgpu_fr* v
     return TSGPU_OK;
 }
 
+// the statement enters the transcript (two field elements: low / high 128 bits of its digest) before any challenge is drawn
+void absorb_statement(const Statement& st, Transcript& tr, const char* label) {
+    const uint64_t header[2] = {(uint64_t)st.n, (uint64_t)1 << st.k};
+    const StatementSegment segs[3] = {{st.addr, 8 * st.n}, {st.values, 32 * st.n}, {st.is_write, st.n}};
+    uint8_t d[32];
+    statement_digest("twist_memory_chk", header, 2, segs, 3, d);
+    fr_t fe[2];
+    for (int h = 0; h < 2; ++h) {
+        Fr64 x = Fr64::zero();
+        memcpy(x.l, d + 16 * h, 16);
+        x = x * Fr64::r2();
+        memcpy(fe[h].l, x.l, 32);
+    }
+    tr.append_field_elements(label, fe, 2);
+}
+
 // r, eq(r, .) and the read claim sum_j eq(r, j) [read_j] value_j - the opening both sides share
 int open_statement(tsgpu_ctx* ctx, const Statement& st, Transcript& tr, Tables& tabs, tsgpu_table** eq_r, tsgpu_fr* claim) {
-    {   // the statement enters the transcript (two field elements: low / high 128 bits of its digest) before any challenge is drawn
-        const uint64_t header[2] = {(uint64_t)st.n, (uint64_t)1 << st.k};
-        const StatementSegment segs[3] = {{st.addr, 8 * st.n}, {st.values, 32 * st.n}, {st.is_write, st.n}};
-        uint8_t d[32];
-        statement_digest("twist_memory_chk", header, 2, segs, 3, d);
-        fr_t fe[2];
-        for (int h = 0; h < 2; ++h) {
-            Fr64 x = Fr64::zero();
-            memcpy(x.l, d + 16 * h, 16);
-            x = x * Fr64::r2();
-            memcpy(fe[h].l, x.l, 32);
-        }
-        tr.append_field_elements("memory_check_statement", fe, 2);
-    }
+    absorb_statement(st, tr, "memory_check_statement");
     std::vector<fr_t> r = tr.challenge_field_elements("memory_check_point", st.t);
     std::vector<tsgpu_fr> r_abi(st.t ? st.t : 1);
     for (unsigned i = 0; i < st.t; ++i) r_abi[i] = abi_of(r[i]);
@@ -251,6 +257,167 @@ int tsgpu_twist_memory_check_verify(tsgpu_ctx* ctx, const uint64_t* addresses, c
     Fr64 lt = lt_eval(ch2, j_star);
     fr_t lt32; memcpy(lt32.l, lt.l, 32);
     *valid = (fr_of(u_val) * lt32 == p2.final_evaluation) ? 1 : 0;
+    return TSGPU_OK;
+}
+
+// ---- 3. write-checking + 4. its Val-evaluation: the third sum-check of Twist.  Inc_j = [write_j] (value_j - Val(address_j, j)) is what a write adds to
+// its cell; the prover of the paper commits to Inc and proves it consistent with the written values and Val:
+//     sum_j eq(r', j) Inc_j  =  sum_{x, j} ( eq(r', j) [write_j] wa(x, j) ) * ( wv(j) - Val(x, j) )                                   k + t rounds
+// with wa(x, j) = [address_j == x] and wv(j) = value_j broadcast over the cells.  It ends at a new point (x**, j**): the second factor there is
+// value~(j**) - Val~(x**, j**), so the prover sends Val~(x**, j**) and proves it by a second Val-evaluation sum-check (t rounds), exactly as part 2.
+// Runs on the caller's transcript (after tsgpu_twist_memory_check_prove on the same transcript, or alone: the statement digest is absorbed here too).
+// claims[2] = {sum_j eq(r', j) Inc_j, Val~(x**, j**)}; rounds3 (k + t) x 4, final3; rounds4 t x 4, final4.
+namespace {
+// Inc as a table over the cycles (zero for reads and for the padding)
+int inc_table(tsgpu_ctx* ctx, const Statement& st, Tables& tabs, tsgpu_table** out) {
+    std::vector<Fr64> mem((size_t)1 << st.k, Fr64::zero());
+    std::vector<tsgpu_fr> inc(st.n ? st.n : 1);
+    for (size_t j = 0; j < st.n; ++j) {
+        if (st.is_write[j]) {
+            Fr64 v = Fr64::from_raw(st.values[j].l), d = v - mem[st.addr[j]];
+            memcpy(inc[j].l, d.l, 32);
+            mem[st.addr[j]] = v;
+        } else memset(&inc[j], 0, 32);
+    }
+    tsgpu_table** t = tabs.slot();
+    int rc = tsgpu_table_upload(ctx, inc.data(), st.n, st.t, t);
+    if (!rc) *out = *t;
+    return rc;
+}
+int open_write_statement(tsgpu_ctx* ctx, const Statement& st, Transcript& tr, Tables& tabs, tsgpu_table** eq_r, tsgpu_fr* claim) {
+    absorb_statement(st, tr, "memory_write_statement");
+    std::vector<fr_t> r = tr.challenge_field_elements("memory_write_point", st.t);
+    std::vector<tsgpu_fr> r_abi(st.t ? st.t : 1);
+    for (unsigned i = 0; i < st.t; ++i) r_abi[i] = abi_of(r[i]);
+    tsgpu_table** e = tabs.slot();
+    int rc = tsgpu_table_eq(ctx, r_abi.data(), st.t, e);
+    if (rc) return rc;
+    tsgpu_table* inc = nullptr;
+    if ((rc = inc_table(ctx, st, tabs, &inc))) return rc;
+    if ((rc = tsgpu_table_inner_product(ctx, *e, inc, claim))) return rc;
+    tr.append_field_element("memory_write_claim", fr_of(*claim));
+    *eq_r = *e;
+    return TSGPU_OK;
+}
+}  // namespace
+
+int tsgpu_twist_write_check_prove(tsgpu_ctx* ctx, const uint64_t* addresses, const tsgpu_fr* values, const uint8_t* is_write, size_t num_operations,
+                                  size_t memory_size, tsgpu_transcript* transcript, tsgpu_fr claims[2], tsgpu_fr* rounds3, tsgpu_fr* final3,
+                                  tsgpu_fr* rounds4, tsgpu_fr* final4) {
+    if (!ctx || !transcript || !claims || !final3 || !final4) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    Statement st;
+    int rc = check_statement(ctx, addresses, values, is_write, num_operations, memory_size, &st);
+    if (rc) return rc;
+    if ((st.k + st.t && !rounds3) || (st.t && !rounds4)) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    Transcript& tr = *tsgpu_transcript_inner(transcript);
+    Tables tabs(ctx);
+    tsgpu_table* eq_r = nullptr;
+    if ((rc = open_write_statement(ctx, st, tr, tabs, &eq_r, &claims[0]))) return rc;
+    std::string err;
+    // ---- 3. write-checking over (x, j): WA = eq(r', j) [write_j] wa(x, j);  D = wv(j) - Val(x, j)
+    tsgpu_table* pair3[2] = {nullptr, nullptr};
+    tsgpu_table** wv = tabs.slot();
+    rc = tsgpu_table_one_hot_weighted(ctx, eq_r, st.addr, st.is_write, /*flag: writes*/ 1, st.n, st.k, &pair3[0]);
+    if (!rc) rc = tsgpu_table_memory_values(ctx, st.addr, st.is_write, st.values, st.n, st.k, st.t, &pair3[1]);
+    if (!rc) rc = tsgpu_table_upload(ctx, st.values, st.n, st.t, wv);
+    if (!rc) rc = tsgpu_table_broadcast_rows_minus(ctx, *wv, pair3[1]);
+    SumCheckProof p3; std::vector<fr_t> ch3, fin3;
+    if (!rc) {
+        rc = sumcheck_prove_product(ctx, pair3, 2, fr_of(claims[0]), tr, p3, &ch3, &fin3, err);
+        if (rc) fail(ctx, rc, err.c_str());
+    }
+    tsgpu_table_free(ctx, pair3[0]); tsgpu_table_free(ctx, pair3[1]);
+    if (rc) return rc;
+    export_rounds(p3, rounds3, final3);
+    // Val~(x**, j**) = value~(j**) - D~(x**, j**)
+    std::vector<fr_t> x_star(ch3.begin(), ch3.begin() + st.k), j_star(ch3.begin() + st.k, ch3.end());
+    std::vector<tsgpu_fr> j_abi(st.t ? st.t : 1);
+    for (unsigned i = 0; i < st.t; ++i) j_abi[i] = abi_of(j_star[i]);
+    tsgpu_fr wv_at;
+    if ((rc = tsgpu_table_evaluate(ctx, *wv, j_abi.data(), &wv_at))) return rc;
+    const fr_t val_claim = fr_of(wv_at) - fin3[1];
+    claims[1] = abi_of(val_claim);
+    tr.append_field_element("memory_val_claim_2", val_claim);
+    // ---- 4. Val-evaluation at (x**, j**)
+    tsgpu_table* u = nullptr;
+    if ((rc = increments_table(ctx, st, x_star, tabs, &u))) return rc;
+    tsgpu_table* pair4[2] = {u, nullptr};
+    tabs.release(u);
+    rc = tsgpu_table_lt_point(ctx, j_abi.data(), st.t, &pair4[1]);
+    SumCheckProof p4;
+    if (!rc) {
+        rc = sumcheck_prove_product(ctx, pair4, 2, val_claim, tr, p4, nullptr, nullptr, err);
+        if (rc) fail(ctx, rc, err.c_str());
+    }
+    tsgpu_table_free(ctx, pair4[0]); tsgpu_table_free(ctx, pair4[1]);
+    if (rc) return rc;
+    export_rounds(p4, rounds4, final4);
+    return TSGPU_OK;
+}
+
+int tsgpu_twist_write_check_verify(tsgpu_ctx* ctx, const uint64_t* addresses, const tsgpu_fr* values, const uint8_t* is_write, size_t num_operations,
+                                   size_t memory_size, tsgpu_transcript* transcript, const tsgpu_fr claims[2], const tsgpu_fr* rounds3, size_t num_rounds3,
+                                   const tsgpu_fr* final3, const tsgpu_fr* rounds4, size_t num_rounds4, const tsgpu_fr* final4, int* valid) {
+    if (!ctx || !transcript || !claims || !final3 || !final4 || !valid || (!rounds3 && num_rounds3) || (!rounds4 && num_rounds4))
+        return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    Statement st;
+    int rc = check_statement(ctx, addresses, values, is_write, num_operations, memory_size, &st);
+    if (rc) return rc;
+    Transcript& tr = *tsgpu_transcript_inner(transcript);
+    Tables tabs(ctx);
+    tsgpu_table* eq_r = nullptr;
+    tsgpu_fr claim3;
+    if ((rc = open_write_statement(ctx, st, tr, tabs, &eq_r, &claim3))) return rc;
+    *valid = 0;
+    if (fr_of(claim3) != fr_of(claims[0])) return TSGPU_OK;
+    SumCheckProof p3, p4;
+    import_rounds(rounds3, num_rounds3, final3, &p3);
+    import_rounds(rounds4, num_rounds4, final4, &p4);
+    std::vector<fr_t> ch3, ch4;
+    int ok = sumcheck_verify(st.k + st.t, fr_of(claim3), p3, tr, &ch3);
+    if (ok < 0) return fail(ctx, TSGPU_E_SUMCHECK, "Proof has wrong number of rounds");
+    if (!ok) return TSGPU_OK;
+    std::vector<fr_t> x_star(ch3.begin(), ch3.begin() + st.k), j_star(ch3.begin() + st.k, ch3.end());
+    // closing 3: final3 == ( sum_{write j} eq(r', j) eq(j**, j) eq(x**, address_j) ) * ( value~(j**) - Val~(x**, j**) )
+    std::vector<tsgpu_fr> x_abi(st.k ? st.k : 1), j_abi(st.t ? st.t : 1);
+    for (unsigned i = 0; i < st.k; ++i) x_abi[i] = abi_of(x_star[i]);
+    for (unsigned i = 0; i < st.t; ++i) j_abi[i] = abi_of(j_star[i]);
+    tsgpu_table** eqj = tabs.slot();
+    if ((rc = tsgpu_table_eq(ctx, j_abi.data(), st.t, eqj))) return rc;
+    tsgpu_table** eqx = tabs.slot();
+    if ((rc = tsgpu_table_eq(ctx, x_abi.data(), st.k, eqx))) return rc;
+    tsgpu_table** g = tabs.slot();
+    if ((rc = tsgpu_table_gather(ctx, *eqx, st.addr, st.n, st.t, g))) return rc;
+    std::vector<tsgpu_fr> sel(st.n ? st.n : 1);
+    const fr_t one = fr_t::one();
+    for (size_t j = 0; j < st.n; ++j) { if (st.is_write[j]) sel[j] = abi_of(one); else memset(&sel[j], 0, 32); }
+    tsgpu_table** selt = tabs.slot();
+    if ((rc = tsgpu_table_upload(ctx, sel.data(), st.n, st.t, selt))) return rc;
+    tsgpu_table** m1 = tabs.slot();
+    if ((rc = tsgpu_table_mul(ctx, eq_r, *eqj, m1))) return rc;
+    tsgpu_table** m2 = tabs.slot();
+    if ((rc = tsgpu_table_mul(ctx, *g, *selt, m2))) return rc;
+    tsgpu_fr wa;
+    if ((rc = tsgpu_table_inner_product(ctx, *m1, *m2, &wa))) return rc;
+    tsgpu_table** wv = tabs.slot();
+    if ((rc = tsgpu_table_upload(ctx, st.values, st.n, st.t, wv))) return rc;
+    tsgpu_fr wv_at;
+    if ((rc = tsgpu_table_evaluate(ctx, *wv, j_abi.data(), &wv_at))) return rc;
+    if (fr_of(wa) * (fr_of(wv_at) - fr_of(claims[1])) != p3.final_evaluation) return TSGPU_OK;
+    tr.append_field_element("memory_val_claim_2", fr_of(claims[1]));
+    ok = sumcheck_verify(st.t, fr_of(claims[1]), p4, tr, &ch4);
+    if (ok < 0) return fail(ctx, TSGPU_E_SUMCHECK, "Proof has wrong number of rounds");
+    if (!ok) return TSGPU_OK;
+    // closing 4: final4 == U~(j***) * LT~(j***, j**)
+    tsgpu_table* u = nullptr;
+    if ((rc = increments_table(ctx, st, x_star, tabs, &u))) return rc;
+    std::vector<tsgpu_fr> jj_abi(st.t ? st.t : 1);
+    for (unsigned i = 0; i < st.t; ++i) jj_abi[i] = abi_of(ch4[i]);
+    tsgpu_fr u_val;
+    if ((rc = tsgpu_table_evaluate(ctx, u, jj_abi.data(), &u_val))) return rc;
+    Fr64 lt = lt_eval(ch4, j_star);
+    fr_t lt32; memcpy(lt32.l, lt.l, 32);
+    *valid = (fr_of(u_val) * lt32 == p4.final_evaluation) ? 1 : 0;
     return TSGPU_OK;
 }
 

@@ -481,8 +481,9 @@ def shout_read_check_prove(entries: np.ndarray, idx: np.ndarray, vals: np.ndarra
     return claim_fr, sumcheck_prove_product([fr_from_ints(A), fr_from_ints(V)], claim_fr, transcript=tr, mode=mode)
 
 
-def twist_memory_check_prove(addr: np.ndarray, vals: np.ndarray, isw: np.ndarray, K: int, mode: str = "tables"):
-    """Twist read-checking over (cell, cycle) + Val-evaluation on a fresh transcript -> (read claim, Val~(x*, j*), part 1, part 2)"""
+def twist_memory_check_prove(addr: np.ndarray, vals: np.ndarray, isw: np.ndarray, K: int, mode: str = "tables", with_write_check: bool = False):
+    """Twist read-checking over (cell, cycle) + Val-evaluation on a fresh transcript -> (read claim, Val~(x*, j*), part 1, part 2); with_write_check
+    appends (write claim, Val~(x**, j**), part 3, part 4): write-checking and its Val-evaluation on the same transcript"""
     p = R_MOD
     n = addr.shape[0]
     T = 1 << max(n - 1, 0).bit_length()
@@ -517,4 +518,34 @@ def twist_memory_check_prove(addr: np.ndarray, vals: np.ndarray, isw: np.ndarray
     U = [inc[j] * eqx[int(addr[j])] % p if j < n else 0 for j in range(T)]
     V = lt_point_ints(fr_to_ints(j_star) if t else [], t)
     ref2 = sumcheck_prove_product([fr_from_ints(U), fr_from_ints(V)], val_claim, transcript=tr, mode=mode)
-    return claim1_fr, val_claim, ref1, ref2
+    if not with_write_check:
+        return claim1_fr, val_claim, ref1, ref2
+    # ---- write-checking (host/memory_check.cpp, tsgpu_twist_write_check_prove) on the same transcript:
+    #      sum_j eq(r', j) Inc_j = sum_{x, j} ( eq(r', j) [write_j] ra(x, j) ) * ( value_j - Val(x, j) ), then Val-evaluation of the Val~ claim it ends in
+    tr.append_field_elements(b"memory_write_statement", statement_digest_elements(
+        b"twist_memory_chk", [n, K], [_u64(addr).tobytes(), _u64(vals).tobytes(), np.ascontiguousarray(isw, dtype=np.uint8).tobytes()]))
+    rw = tr.challenge_field_elements(b"memory_write_point", t)
+    eqw = _eq_ints(rw)
+    claim3 = sum(eqw[j] * inc[j] for j in range(T)) % p
+    claim3_fr = fr_from_ints([claim3])[0]
+    tr.append_field_element(b"memory_write_claim", claim3_fr)
+    WA = [0] * (K * T)
+    D = [0] * (K * T)
+    for j in range(T):
+        vj = vi[j] if j < n else 0
+        for x in range(K):
+            D[x + K * j] = (vj - VAL[x + K * j]) % p
+        if j < n and isw[j]:
+            WA[int(addr[j]) + K * j] = eqw[j]
+    ref3 = sumcheck_prove_product([fr_from_ints(WA), fr_from_ints(D)], claim3_fr, transcript=tr, mode=mode)
+    ch3 = ref3["challenges"].reshape(-1, 4)
+    x2, j2 = ch3[:k], ch3[k:]
+    wv_at = mle_evaluate(fr_from_ints([vi[j] if j < n else 0 for j in range(T)]), j2, fold=(mode == "tables")).reshape(4) if t else fr_from_ints([vi[0] if n else 0])[0]
+    d_at = mle_evaluate(fr_from_ints(D), ch3, fold=(mode == "tables")).reshape(4)           # second factor at (x**, j**): MultilinearExtension::evaluate
+    val_claim2 = field_binop("fr", "sub", wv_at.reshape(1, 4), d_at.reshape(1, 4))[0]
+    tr.append_field_element(b"memory_val_claim_2", val_claim2)
+    eqx2 = _eq_ints(x2)
+    U2 = [inc[j] * eqx2[int(addr[j])] % p if j < n else 0 for j in range(T)]
+    V2 = lt_point_ints(fr_to_ints(j2) if t else [], t)
+    ref4 = sumcheck_prove_product([fr_from_ints(U2), fr_from_ints(V2)], val_claim2, transcript=tr, mode=mode)
+    return claim1_fr, val_claim, ref1, ref2, claim3_fr, val_claim2, ref3, ref4

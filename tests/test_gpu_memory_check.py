@@ -36,7 +36,7 @@ def _lt_point_ints(oracle, b_ints, t, p):
 
 def _oracle_memory_check(oracle, addr, vals, isw, K, mode):
     """host/memory_check.cpp restated with oracle primitives and Python integers (oracle/oracle.py: twist_memory_check_prove)"""
-    return oracle.twist_memory_check_prove(addr, vals, isw, K, mode)
+    return oracle.twist_memory_check_prove(addr, vals, isw, K, mode, with_write_check=True)
 
 
 @pytest.mark.parametrize("K,n,mode", [(1, 1, "closure"), (2, 2, "closure"), (4, 3, "closure"), (2, 8, "closure"), (8, 6, "closure"),
@@ -45,11 +45,25 @@ def test_memory_check_matches_reference_sumcheck_on_the_real_closures(ctx, tsgpu
     addr, vals, isw = _trace(oracle, tsgpu, K, n, seed=K * 1000 + n, wide=(n % 2 == 0))
     mc = tsgpu.TwistMemoryCheck(ctx)
     proof = mc.prove_arrays(addr, vals, isw, K, tsgpu.Transcript())
-    c1, c2, ref1, ref2 = _oracle_memory_check(oracle, addr, vals, isw, K, mode)
+    c1, c2, ref1, ref2, c3, c4, ref3, ref4 = _oracle_memory_check(oracle, addr, vals, isw, K, mode)
     assert (proof.claims[0] == c1).all() and (proof.claims[1] == c2).all()
     assert (proof.read_check.round_polynomials == ref1["round_polynomials"]).all() and (proof.read_check.final_evaluation == ref1["final_evaluation"]).all()
     assert (proof.val_evaluation.round_polynomials == ref2["round_polynomials"]).all() and (proof.val_evaluation.final_evaluation == ref2["final_evaluation"]).all()
+    # write-checking (third sum-check) and the Val-evaluation of its closing claim
+    assert (proof.write_claims[0] == c3).all() and (proof.write_claims[1] == c4).all()
+    assert (proof.write_check.round_polynomials == ref3["round_polynomials"]).all() and (proof.write_check.final_evaluation == ref3["final_evaluation"]).all()
+    assert (proof.write_val_evaluation.round_polynomials == ref4["round_polynomials"]).all() and (proof.write_val_evaluation.final_evaluation == ref4["final_evaluation"]).all()
     assert mc.verify_arrays(addr, vals, isw, K, proof, tsgpu.Transcript())
+    if n >= 2 and isw.any():
+        # a tampered write-checking part must not verify: claim, a round coefficient, the final evaluation
+        import copy
+        for field in ("write_claims", "write_check", "write_val_evaluation"):
+            bad = copy.deepcopy(proof)
+            if field == "write_claims":
+                bad.write_claims[1] = tsgpu.fe_add(bad.write_claims[1], tsgpu.fe(1))
+            else:
+                getattr(bad, field).final_evaluation[:] = tsgpu.fe_add(getattr(bad, field).final_evaluation, tsgpu.fe(1))
+            assert not mc.verify_arrays(addr, vals, isw, K, bad, tsgpu.Transcript()), field
 
 
 def test_memory_check_reference_demo_trace(ctx, tsgpu, oracle):
