@@ -231,7 +231,7 @@ def main():
     ctx = ts.Context(local, stream.cuda_stream)
     W = max(args.warmup, 3); K = max(args.steps, 1)
     KS = min(K, 5)                                               # side measurements: at most 5 timed steps each
-    for kv in filter(None, os.environ.get("TSGPU_TUNING", "").split(",")):      # A/B switches for experiments, e.g. TSGPU_TUNING=msm_acc_waves=0
+    for kv in filter(None, os.environ.get("TSGPU_TUNING", "").split(",")):      # A/B switches for experiments, e.g. TSGPU_TUNING=eval_basis=0
         key, val = kv.split("=")
         ctx.set_tuning(key, int(val))
     peaks = {}

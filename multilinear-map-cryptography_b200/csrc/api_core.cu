@@ -165,18 +165,12 @@ void tsgpu_timer_reset(tsgpu_ctx* ctx) {
 
 int tsgpu_set_tuning(tsgpu_ctx* ctx, const char* key, long value) {
     if (!key) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null key");
-    if (!strcmp(key, "tma_min_log2")) {   // tables with >= 2^value positions per stream use the TMA-pipelined kernels; < 0 disables
-        set_tma_min_work(value < 0 || value > 62 ? ~(size_t)0 : (size_t)1 << value);
-        return TSGPU_OK;
-    }
     if (!strcmp(key, "prefetch_min_log2")) {   // d = 2 rounds with >= 2^value positions per launch use the warp-private prefetch kernels; < 0 disables
         set_prefetch_min_work(value < 0 || value > 61 ? (size_t)1 << 62 : (size_t)1 << value);
         return TSGPU_OK;
     }
     if (!strcmp(key, "peer_exchange")) { ctx->peer_exchange = value != 0; return TSGPU_OK; }
     if (!strcmp(key, "deferred_claim_check")) { ctx->deferred_claim_check = value != 0; return TSGPU_OK; }
-    if (!strcmp(key, "msm_acc_waves")) { set_msm_acc_waves((int)value); return TSGPU_OK; }
-    if (!strcmp(key, "msm_two_level")) { set_msm_two_level(value != 0); return TSGPU_OK; }
     if (!strcmp(key, "kernel_timing")) { ctx->timing = value != 0; return TSGPU_OK; }
     if (!strcmp(key, "msm_tables")) { ctx->msm_tables = value != 0; return TSGPU_OK; }   // 0: per-window bucket sets on the plain SRS points
     if (!strcmp(key, "eval_basis")) { ctx->eval_basis = value != 0; return TSGPU_OK; }   // 0: Twist/Shout::prove interpolate and commit coefficients

@@ -17,11 +17,6 @@ namespace tsg {
 
 struct FrP {   // BN254 scalar field r
     static constexpr uint32_t INV = 0xefffffffu;   // -r^-1 mod 2^32
-    static constexpr uint32_t INV29 = 0x0fffffffu; // -r^-1 mod 2^29
-    TSG_HD static constexpr uint32_t mod29(int i) {   // r in radix 2^29
-        constexpr uint32_t m[9] = {0x10000001u, 0x1f0fac9fu, 0xe5c2450u, 0x7d090f3u, 0x1585d283u, 0x2db40c0u, 0xa6e141u, 0xe5c2634u, 0x30644eu};
-        return m[i];
-    }
     TSG_HD static constexpr uint32_t mod(int i) {
         constexpr uint32_t m[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
         return m[i];
@@ -37,11 +32,6 @@ struct FrP {   // BN254 scalar field r
 };
 struct FqP {   // BN254 base field p
     static constexpr uint32_t INV = 0xe4866389u;   // -p^-1 mod 2^32
-    static constexpr uint32_t INV29 = 0x04866389u; // -p^-1 mod 2^29
-    TSG_HD static constexpr uint32_t mod29(int i) {   // p in radix 2^29
-        constexpr uint32_t m[9] = {0x187cfd47u, 0x10460b6u, 0x1c72a34fu, 0x2d522d0u, 0x1585d978u, 0x2db40c0u, 0xa6e141u, 0xe5c2634u, 0x30644eu};
-        return m[i];
-    }
     TSG_HD static constexpr uint32_t mod(int i) {
         constexpr uint32_t m[8] = {0xd87cfd47u, 0x3c208c16u, 0x6871ca8du, 0x97816a91u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
         return m[i];
@@ -118,31 +108,6 @@ TSG_HD void redc_step(uint32_t* X, uint32_t* Y) {
     X[7] = ptx::addc(X[7], 0u);
 }
 
-// Same word step with the 8 products formed by plain mul.wide (IMAD.WIDE without a carry predicate: full issue rate on the FMA-heavy
-// pipe) and added with add.cc chains on the ALU pipe.  The carry-chained IMAD.WIDE.U32.X occupies the FMA-heavy pipe twice as long, and
-// that pipe bounds every arithmetic kernel here, so trading some of those for ALU additions balances the two pipes (see TSG_MIX_ROWS).
-template <class P>
-TSG_HD void redc_step_plain(uint32_t* X, uint32_t* Y) {
-    uint32_t m = ptx::mul_lo(Y[0], P::INV);
-    uint32_t t[8], u[8];
-    ptx::mul_wide(t[0], t[1], P::mod(1), m); ptx::mul_wide(t[2], t[3], P::mod(3), m);
-    ptx::mul_wide(t[4], t[5], P::mod(5), m); ptx::mul_wide(t[6], t[7], P::mod(7), m);
-    ptx::mul_wide(u[0], u[1], P::mod(0), m); ptx::mul_wide(u[2], u[3], P::mod(2), m);
-    ptx::mul_wide(u[4], u[5], P::mod(4), m); ptx::mul_wide(u[6], u[7], P::mod(6), m);
-    X[0] = ptx::add_cc(X[0], t[0]);
-#pragma unroll
-    for (int k = 1; k < 7; ++k) X[k] = ptx::addc_cc(X[k], t[k]);
-    X[7] = ptx::addc(X[7], t[7]);
-    Y[0] = ptx::add_cc(Y[0], u[0]);
-#pragma unroll
-    for (int k = 1; k < 8; ++k) Y[k] = ptx::addc_cc(Y[k], u[k]);
-    X[7] = ptx::addc(X[7], 0u);
-}
-
-#ifndef TSG_MIX_ROWS
-#define TSG_MIX_ROWS 0      // number of word steps (0..8) whose reduction rows use plain products + ALU additions
-#endif
-
 // r = a * b * 2^-256 mod p, inputs < p, output < p
 template <class P>
 TSG_HD void mont_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
@@ -155,7 +120,7 @@ TSG_HD void mont_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
             ptx::mul_wide(Y[j], Y[j + 1], a[j], bi);
             ptx::mul_wide(X[j], X[j + 1], a[j + 1], bi);
         }
-        if (0 < TSG_MIX_ROWS) redc_step_plain<P>(X, Y); else redc_step<P>(X, Y);
+        redc_step<P>(X, Y);
     }
 #pragma unroll
     for (int i = 1; i < 8; ++i) {
@@ -180,7 +145,7 @@ TSG_HD void mont_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
         Y[6] = ptx::madc_lo_cc(a[6], bi, Y[6]);
         Y[7] = ptx::madc_hi_cc(a[6], bi, Y[7]);
         X[7] = ptx::addc(X[7], 0u);
-        if (i < TSG_MIX_ROWS) redc_step_plain<P>(X, Y); else redc_step<P>(X, Y);
+        redc_step<P>(X, Y);
     }
     // after step 7: Y = acc[1] (Y[0] == 0), X = acc[0]; result = X + (Y >> 32)
     {
@@ -316,66 +281,6 @@ TSG_HD void mont_reduce(uint32_t* r, const uint32_t* T) {
 }
 
 
-// t[0..16) = a * a: the 28 off-diagonal limb products once (doubled afterwards) + the 8 squares = 36 wide multiply-adds instead of 64.
-// Row i multiplies a_i by a_j, j > i; a product lands on limbs (i + j, i + j + 1), so the j of one parity form a contiguous carry chain that
-// starts at an odd limb (j - i odd: accumulator O) and those of the other parity one that starts at an even limb (accumulator E).  The carry
-// out of a chain goes to the next limb, which at that point holds nothing but earlier carries (rows run in increasing i).
-TSG_HD void sqr_wide(uint32_t* t, const uint32_t* a) {
-    uint32_t E[16], O[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) { E[k] = 0; O[k] = 0; }
-#pragma unroll
-    for (int i = 0; i < 7; ++i) {
-        {   // j = i + 1, i + 3, ...
-            O[2 * i + 1] = ptx::mad_lo_cc(a[i], a[i + 1], O[2 * i + 1]);
-            O[2 * i + 2] = ptx::madc_hi_cc(a[i], a[i + 1], O[2 * i + 2]);
-            int j = i + 3;
-#pragma unroll
-            for (; j <= 7; j += 2) {
-                O[i + j] = ptx::madc_lo_cc(a[i], a[j], O[i + j]);
-                O[i + j + 1] = ptx::madc_hi_cc(a[i], a[j], O[i + j + 1]);
-            }
-            O[i + j] = ptx::addc(O[i + j], 0u);          // i + j <= 15
-        }
-        if (i + 2 <= 7) {   // j = i + 2, i + 4, ...
-            E[2 * i + 2] = ptx::mad_lo_cc(a[i], a[i + 2], E[2 * i + 2]);
-            E[2 * i + 3] = ptx::madc_hi_cc(a[i], a[i + 2], E[2 * i + 3]);
-            int j = i + 4;
-#pragma unroll
-            for (; j <= 7; j += 2) {
-                E[i + j] = ptx::madc_lo_cc(a[i], a[j], E[i + j]);
-                E[i + j + 1] = ptx::madc_hi_cc(a[i], a[j], E[i + j + 1]);
-            }
-            E[i + j] = ptx::addc(E[i + j], 0u);          // i + j <= 14
-        }
-    }
-    // S = E + O (< 2^511), doubled, plus the diagonal
-    uint32_t s[16];
-    s[0] = ptx::add_cc(E[0], O[0]);
-#pragma unroll
-    for (int k = 1; k < 15; ++k) s[k] = ptx::addc_cc(E[k], O[k]);
-    s[15] = ptx::addc(E[15], O[15]);
-#pragma unroll
-    for (int k = 15; k > 0; --k) t[k] = (s[k] << 1) | (s[k - 1] >> 31);
-    t[0] = s[0] << 1;
-    t[0] = ptx::mad_lo_cc(a[0], a[0], t[0]);
-    t[1] = ptx::madc_hi_cc(a[0], a[0], t[1]);
-#pragma unroll
-    for (int i = 1; i < 7; ++i) {
-        t[2 * i] = ptx::madc_lo_cc(a[i], a[i], t[2 * i]);
-        t[2 * i + 1] = ptx::madc_hi_cc(a[i], a[i], t[2 * i + 1]);
-    }
-    t[14] = ptx::madc_lo_cc(a[7], a[7], t[14]);
-    t[15] = ptx::madc_hi(a[7], a[7], t[15]);
-}
-// r = a^2 * 2^-256 mod p: 36 + 72 multiply-adds instead of 136 (a^2 < p^2 < p * 2^256 as mont_reduce requires)
-template <class P>
-TSG_HD void mont_sqr(uint32_t* r, const uint32_t* a) {
-    uint32_t t[16];
-    sqr_wide(t, a);
-    mont_reduce<P>(r, t);
-}
-
 // r = (a b - c d) * 2^-256 mod p with ONE Montgomery reduction: the two 512-bit products are subtracted first (p * 2^256 is added back when the
 // difference is negative, which leaves the residue unchanged), so 2 x 64 + 72 multiply-adds replace the 2 x 136 of two Montgomery products.
 // Inputs < p, output < p: both products are < p^2 < p * 2^256, hence the adjusted difference is in [0, p * 2^256) as mont_reduce requires.
@@ -471,84 +376,6 @@ TSG_HD void mul_ctab(uint32_t* r, const uint32_t* a, const uint32_t (*T)[8]) {
     cond_sub_mod<P>(r);
 }
 
-// ===================================================================================================
-// Radix-2^29 multiplier.  Measured on B200 (tools/ubench2.cu): IMAD.WIDE.U32 issues at full rate
-// (~18.5 T/s) only WITHOUT a carry predicate; the carry-in/out forms (.X, or carry-out) run at half
-// rate.  With nine 29-bit limbs every 29x29 product is < 2^58, so the 18 column sums of a product plus
-// its Montgomery reduction (<= 18 terms each) fit a 64-bit accumulator with no carry handling at all:
-// 81 + 81 plain IMAD.WIDE, carries resolved once by shifts on the ALU pipe.  The reduction strips
-// 8 x 29 + 24 = 256 bits, so values stay in the reference's 2^256 Montgomery domain.
-// ===================================================================================================
-constexpr uint32_t M29 = 0x1fffffffu;
-
-TSG_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, int sh) {   // bits [sh, sh+32) of hi:lo, 0 < sh < 32
-#if defined(__CUDA_ARCH__)
-    return __funnelshift_r(lo, hi, sh);
-#else
-    return (uint32_t)((((uint64_t)hi << 32) | lo) >> sh);
-#endif
-}
-
-// 8 x 32-bit limbs -> 9 x 29-bit limbs
-TSG_HD void to29(uint32_t* o, const uint32_t* x) {
-    o[0] = x[0] & M29;
-#pragma unroll
-    for (int k = 1; k < 8; ++k) {
-        const int bit = 29 * k, w = bit >> 5, sh = bit & 31;   // sh != 0 for k = 1..7
-        o[k] = funnel_r(x[w], x[w + 1], sh) & M29;
-    }
-    o[8] = x[7] >> 8;
-}
-
-// column accumulators t[0..17) += A * B (81 wide MACs, no carries)
-TSG_HD void mac29(unsigned long long* t, const uint32_t* A, const uint32_t* B) {
-#pragma unroll
-    for (int i = 0; i < 9; ++i)
-#pragma unroll
-        for (int j = 0; j < 9; ++j) t[i + j] += (unsigned long long)A[j] * B[i];
-}
-
-// Montgomery-reduce the 17(+1) column sums by 2^256 and repack to 8 x 32-bit limbs; output < p.
-// Requires sum_k t[k] 2^(29k) < p * 2^256 and every t[k] < 2^62.
-template <class P>
-TSG_HD void redc29(uint32_t* r, unsigned long long* t) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        uint32_t m = ((uint32_t)t[i] * P::INV29) & M29;
-#pragma unroll
-        for (int j = 0; j < 9; ++j) t[i + j] += (unsigned long long)m * P::mod29(j);
-        t[i + 1] += t[i] >> 29;
-    }
-    {   // last step removes only 24 bits: 8 * 29 + 24 = 256
-        uint32_t m = ((uint32_t)t[8] * P::INV29) & 0x00ffffffu;
-#pragma unroll
-        for (int j = 0; j < 9; ++j) t[8 + j] += (unsigned long long)m * P::mod29(j);
-    }
-    // carry-normalise limbs 8..17 (value U = sum t[8+k] 2^(29k), divisible by 2^24)
-#pragma unroll
-    for (int k = 8; k < 17; ++k) { t[k + 1] += t[k] >> 29; t[k] &= M29; }
-    // R = U >> 24: 32-bit word w holds bits [32w + 24, 32w + 56) of U
-#pragma unroll
-    for (int w = 0; w < 8; ++w) {
-        const int bit = 32 * w + 24, k = bit / 29, sh = bit % 29;
-        unsigned long long v = (t[8 + k] >> sh) | (t[8 + k + 1] << (29 - sh));
-        if (29 - sh + 29 < 32) v |= t[8 + k + 2] << (58 - sh);
-        r[w] = (uint32_t)v;
-    }
-    cond_sub_mod<P>(r);
-}
-
-template <class P>
-TSG_HD void mont_mul29(uint32_t* r, const uint32_t* a, const uint32_t* b) {
-    uint32_t A[9], B[9];
-    to29(A, a); to29(B, b);
-    unsigned long long t[18];
-#pragma unroll
-    for (int k = 0; k < 18; ++k) t[k] = 0;
-    mac29(t, A, B);
-    redc29<P>(r, t);
-}
-
 }  // namespace limb
 
 // ---------------------------------------------------------------------------------------------------
@@ -565,20 +392,11 @@ struct alignas(16) fp {
     TSG_HD bool operator!=(const fp& b) const { return !(*this == b); }
     TSG_HD fp operator+(const fp& b) const { fp r; limb::add<P>(r.l, l, b.l); return r; }
     TSG_HD fp operator-(const fp& b) const { fp r; limb::sub<P>(r.l, l, b.l); return r; }
-    #if !defined(TSG_MUL_RADIX29)
     TSG_HD fp operator*(const fp& b) const { fp r; limb::mont_mul<P>(r.l, l, b.l); return r; }
-#ifdef TSG_FAST_SQR
-    TSG_HD fp sqr() const { fp r; limb::mont_sqr<P>(r.l, l); return r; }
-#else
+    // a dedicated squaring (28 doubled off-diagonal products + 8 squares) was measured in round 1: no gain on B200 (profiles/r01_kernel_variants.md)
     TSG_HD fp sqr() const { fp r; limb::mont_mul<P>(r.l, l, l); return r; }
-#endif
-    TSG_HD fp sqr_dedicated() const { fp r; limb::mont_sqr<P>(r.l, l); return r; }
     // a * b - c * d with a single reduction (limb::mont_mul_sub)
     TSG_HD static fp mul_sub(const fp& a, const fp& b, const fp& c, const fp& d) { fp r; limb::mont_mul_sub<P>(r.l, a.l, b.l, c.l, d.l); return r; }
-#else
-    TSG_HD fp operator*(const fp& b) const { fp r; limb::mont_mul29<P>(r.l, l, b.l); return r; }
-    TSG_HD fp sqr() const { fp r; limb::mont_mul29<P>(r.l, l, l); return r; }
-#endif
     TSG_HD fp dbl() const { fp r; limb::add<P>(r.l, l, l); return r; }
     TSG_HD fp neg() const { fp z = zero(); fp r; limb::sub<P>(r.l, z.l, l); return r; }
     // Montgomery -> canonical integer limbs
@@ -634,8 +452,8 @@ struct fp_ctab {
 };
 typedef fp_ctab<FrP> fr_ctab;
 
-// Lazy accumulator for sums of products of reduced operands (carry-chain form, 512 bits).  Default
-// (see the measurement note at the radix-2^29 multiplier).
+// Lazy accumulator for sums of products of reduced operands (carry-chain form, 512 bits).  A carry-free radix-2^29 form (81 plain
+// IMAD.WIDE per product) and plain-product reduction rows were built and measured slower in round 1 (ALU-bound; profiles/r01_kernel_variants.md).
 template <class P>
 struct wide_acc32 {
     uint32_t t[16];
@@ -653,66 +471,6 @@ struct wide_acc32 {
     }
 };
 
-// Lazy accumulator in radix 2^29: 18 column sums of 64 bits; a product costs 81 plain IMAD.WIDE and no
-// carry handling; columns are carry-normalised every 6 products (6 * 9 * 2^58 < 2^64).  reduce() folds
-// everything above 2^512 back with 2^512 mod p, then performs one Montgomery reduction.
-template <class P>
-struct wide_acc29 {
-    unsigned long long t[18];
-    int pending;
-    TSG_HD void clear() { for (int i = 0; i < 18; ++i) t[i] = 0; pending = 0; }
-    TSG_HD void carry() {
-#pragma unroll
-        for (int k = 0; k < 17; ++k) { t[k + 1] += t[k] >> 29; t[k] &= limb::M29; }
-        pending = 0;
-    }
-    TSG_HD void add_product29(const uint32_t* A, const uint32_t* B) {
-        limb::mac29(t, A, B);
-        if (++pending == 6) carry();
-    }
-    TSG_HD void add_product(const fp<P>& a, const fp<P>& b) {
-        uint32_t A[9], B[9];
-        limb::to29(A, a.l); limb::to29(B, b.l);
-        add_product29(A, B);
-    }
-    // Montgomery-form value of the accumulated sum (runs once per thread: clarity over speed)
-    TSG_HD fp<P> reduce() {
-        carry();
-        // repack limbs 0..16 (each < 2^29, 493 bits) into sixteen 32-bit words
-        uint32_t W[16];
-#pragma unroll
-        for (int w = 0; w < 16; ++w) {
-            const int bit = 32 * w, k = bit / 29, sh = bit % 29;
-            unsigned long long v = t[k] >> sh;
-            if (k + 1 < 17) v |= t[k + 1] << (29 - sh);
-            if (k + 2 < 17 && 58 - sh < 32) v |= t[k + 2] << (58 - sh);
-            W[w] = (uint32_t)v;
-        }
-        // t[17] sits at bit 493 = 15 * 32 + 13: it overlaps words 15.. and may exceed 2^512
-        unsigned long long top = t[17];
-        unsigned long long lo = top << 13;            // bits 493.. of the sum, low 64
-        unsigned long long hi = top >> 51;            // spill above
-        uint32_t w15 = ptx::add_cc(W[15], (uint32_t)lo);
-        uint32_t h0 = ptx::addc_cc((uint32_t)(lo >> 32), 0u);
-        uint32_t h1 = ptx::addc_cc((uint32_t)hi, 0u);
-        uint32_t h2 = ptx::addc((uint32_t)(hi >> 32), 0u);
-        W[15] = w15;
-        limb::wide_normalize<P>(W);
-        // (h2:h1:h0) * 2^512 == (h2:h1:h0) * (2^512 mod p)
-        fp<P> hv = fp<P>::zero(); hv.l[0] = h0; hv.l[1] = h1; hv.l[2] = h2;
-        fp<P> r2 = fp<P>::r2();
-        uint32_t prod[16];
-        limb::mul_wide(prod, hv.l, r2.l);
-        limb::wide_add(W, prod);
-        limb::wide_normalize<P>(W);
-        fp<P> r; limb::mont_reduce<P>(r.l, W); return r;
-    }
-};
-
-#if defined(TSG_MUL_RADIX29)
-template <class P> using wide_acc = wide_acc29<P>;
-#else
 template <class P> using wide_acc = wide_acc32<P>;
-#endif
 
 }  // namespace tsg

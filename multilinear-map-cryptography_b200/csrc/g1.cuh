@@ -68,11 +68,7 @@ struct alignas(16) g1_xyzz {
         fq_t PP = P.sqr(), PPP = P * PP, Q = X * PP;
         g1_xyzz r;
         r.X = R.sqr() - PPP - Q.dbl();
-#ifndef TSG_NO_FUSED_Y3   // a b - c d with one reduction: 200 instead of 272 multiply-adds (accumulate 4.99 -> 4.81 ms per 2^20-op proof)
-        r.Y = fq_t::mul_sub(R, Q - r.X, Y, PPP);
-#else
-        r.Y = R * (Q - r.X) - Y * PPP;
-#endif
+        r.Y = fq_t::mul_sub(R, Q - r.X, Y, PPP);   // a b - c d with one reduction: 200 instead of 272 multiply-adds (accumulate 4.99 -> 4.81 ms per 2^20-op proof)
         r.ZZ = ZZ * PP; r.ZZZ = ZZZ * PPP;
         return r;
     }
@@ -89,11 +85,7 @@ struct alignas(16) g1_xyzz {
         fq_t PP = P.sqr(), PPP = P * PP, Q = U1 * PP;
         g1_xyzz r;
         r.X = R.sqr() - PPP - Q.dbl();
-#ifndef TSG_NO_FUSED_Y3   // a b - c d with one reduction: 200 instead of 272 multiply-adds (accumulate 4.99 -> 4.81 ms per 2^20-op proof)
         r.Y = fq_t::mul_sub(R, Q - r.X, S1, PPP);
-#else
-        r.Y = R * (Q - r.X) - S1 * PPP;
-#endif
         r.ZZ = ZZ * o.ZZ * PP; r.ZZZ = ZZZ * o.ZZZ * PPP;
         return r;
     }

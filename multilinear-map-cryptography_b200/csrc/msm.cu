@@ -258,13 +258,8 @@ __global__ void __launch_bounds__(256) k_msm_order(const unsigned* hist, const u
 
 // ---------------------------------------------------------------- 3b. bucket accumulation (the hot kernel)
 // Register allocation: without a min-blocks bound ptxas settles on 122 registers (4 blocks of 128 threads per SM: up to 128 registers fit four), which measured best:
-// 96 registers / 5 blocks (small spills) 4.86 ms, 80 / 6 blocks 5.00 ms, 130 / 3 blocks 5.00 ms against 4.81 ms per 2^20-op proof (-DTSG_ACC_MINB=k to try)
-#ifdef TSG_ACC_MINB
-#define TSG_ACC_BOUNDS __launch_bounds__(MSM_ACC_THREADS, TSG_ACC_MINB)
-#else
-#define TSG_ACC_BOUNDS __launch_bounds__(MSM_ACC_THREADS)
-#endif
-__global__ void TSG_ACC_BOUNDS k_msm_accumulate(const MsmBases jobs, unsigned buckets_per_job, const unsigned* sorted, const unsigned* hist, const unsigned* offsets,
+// 96 registers / 5 blocks (small spills) 4.86 ms, 80 / 6 blocks 5.00 ms, 130 / 3 blocks 5.00 ms against 4.81 ms per 2^20-op proof
+__global__ void __launch_bounds__(MSM_ACC_THREADS) k_msm_accumulate(const MsmBases jobs, unsigned buckets_per_job, const unsigned* sorted, const unsigned* hist, const unsigned* offsets,
                                                                   const unsigned* item_off, const unsigned* item_bucket, const unsigned* n_items,
                                                                   const unsigned* order, g1_xyzz* partial) {
     const unsigned M = *n_items;
@@ -375,55 +370,6 @@ __global__ void __launch_bounds__(32) k_msm_bit_finish(const g1_xyzz* parts, uns
     }
 }
 
-// Two-level form of the index-weighted sum  sum_t t R_t  over the T = 2^(h + l) span sums of a bucket set, t = hi 2^l + lo:
-//     sum_t t R_t = 2^l sum_hi hi A_hi + sum_lo lo B_lo,     A_hi = sum_lo R_(hi, lo)  (row sums),  B_lo = sum_hi R_(hi, lo)  (column sums)
-// 2 T additions for the row and column sums instead of the (h + l) T / 2 of a bit decomposition over all T elements; the bit decomposition
-// then runs over the 2^h + 2^l marginal sums only.  The results land in the same slots (slot k < l: bit k of lo, from B; slot k >= l: bit
-// k - l of hi, from A), so the host's Horner tail is unchanged.
-constexpr int MSM_RC_THREADS = 64;
-__global__ void __launch_bounds__(MSM_RC_THREADS) k_msm_rc_sums(const g1_xyzz* R, unsigned T, unsigned l, g1_xyzz* A, g1_xyzz* B) {
-    __shared__ g1_xyzz sh[MSM_RC_THREADS];
-    const unsigned cols = 1u << l, rows = T >> l;
-    const unsigned i = blockIdx.x, w = blockIdx.y;
-    const bool is_row = i < rows;
-    const unsigned idx = is_row ? i : i - rows, len = is_row ? cols : rows, stride = is_row ? 1u : cols;
-    const g1_xyzz* src = R + (size_t)w * T + (is_row ? (size_t)idx * cols : idx);
-    g1_xyzz acc = g1_xyzz::identity();
-    for (unsigned j = threadIdx.x; j < len; j += MSM_RC_THREADS) acc = acc.add(ld_xyzz(src + (size_t)j * stride));
-    sh[threadIdx.x] = acc;
-    __syncthreads();
-    for (unsigned s = MSM_RC_THREADS / 2; s > 0; s >>= 1) {
-        if (threadIdx.x < s) sh[threadIdx.x] = sh[threadIdx.x].add(sh[threadIdx.x + s]);
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) st_xyzz((is_row ? A + (size_t)w * rows : B + (size_t)w * cols) + idx, sh[0]);
-}
-// block (k, w): sum of the marginal sums whose index has the slot's bit set, written as a Jacobian point into slot k of set w
-constexpr int MSM_MBIT_THREADS = 128;
-__global__ void __launch_bounds__(MSM_MBIT_THREADS) k_msm_marginal_bit_sums(const g1_xyzz* A, const g1_xyzz* B, unsigned h, unsigned l, g1_jac* out) {
-    __shared__ g1_xyzz sh[MSM_MBIT_THREADS];
-    const unsigned k = blockIdx.x, w = blockIdx.y, nbits = h + l;
-    const bool from_b = k < l;
-    const unsigned bit = from_b ? k : k - l, len = from_b ? (1u << l) : (1u << h);
-    const g1_xyzz* src = from_b ? B + ((size_t)w << l) : A + ((size_t)w << h);
-    g1_xyzz acc = g1_xyzz::identity();
-    for (unsigned u = threadIdx.x; u < len / 2; u += MSM_MBIT_THREADS) {
-        const unsigned t = ((u >> bit) << (bit + 1)) | (1u << bit) | (u & ((1u << bit) - 1));
-        acc = acc.add(ld_xyzz(src + t));
-    }
-    sh[threadIdx.x] = acc;
-    __syncthreads();
-    for (unsigned s = MSM_MBIT_THREADS / 2; s > 0; s >>= 1) {
-        if (threadIdx.x < s) sh[threadIdx.x] = sh[threadIdx.x].add(sh[threadIdx.x + s]);
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        const size_t slot = (size_t)w * (nbits + 2) + k;
-        g1_jac j = sh[0].to_jacobian();
-        st256(&out[slot].x, j.x); st256(&out[slot].y, j.y); st256(&out[slot].z, j.z);
-    }
-}
-
 // ---------------------------------------------------------------- SRS generation: out[i] = tau^i * G
 // powers of tau: thread handles MSM_POW_SPAN consecutive exponents
 __global__ void k_tau_powers(const fr_t tau, size_t first, size_t n, fr_t* out) {
@@ -520,12 +466,6 @@ unsigned msm_table_window_bits(size_t n) {
     return lg;
 }
 
-static bool g_msm_two_level = false;   // measured on B200: 2^20-op Twist proof reduce 1.30 -> 1.35 ms, 2^24-point MSM 1.83 -> 1.62 ms: no gain where it matters, so opt-in
-void set_msm_two_level(bool on) { g_msm_two_level = on; }
-static int g_msm_acc_waves = 0;      // > 0: grid of k_msm_accumulate = that many resident waves; 0: 16 blocks per SM, scheduled dynamically (measured faster:
-                                     // one persistent wave took 5.60 instead of 4.99 ms per 2^20-op proof - the block scheduler balances the SMs better than the static deal)
-void set_msm_acc_waves(int w) { g_msm_acc_waves = w; }
-
 size_t msm_scratch_bytes(size_t nmax, int K, unsigned c, bool shared, MsmLayout* L, unsigned windows) {
     const unsigned W = windows ? windows : (255 + c - 1) / c;   // windows: only the low digit positions are scanned (scalars known to be short)
     const unsigned sets = (unsigned)K * (shared ? 1u : W);            // bucket sets = windows seen by the reduction
@@ -603,14 +543,8 @@ cudaError_t msm_run(const MsmJob* jobs, int K, const MsmLayout& L, unsigned char
     k_msm_order<<<gridfor(L.max_items, 256 * ORDER_TILE, cap), 256, 0, s>>>(hist, item_off, item_bucket, n_items, len_off, len_cursor, order);
     if (ev) cudaEventRecord(ev[1], s);
     {
-        // one resident wave: the items are sorted by length and dealt round-robin, so every thread of a persistent grid gets the same load, while a grid
-        // of several waves ends with a partly filled one (16 blocks per SM at 5 resident: the last wave ran one block per SM)
-        static int acc_blocks_per_sm = 0;
-        if (!acc_blocks_per_sm) {
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&acc_blocks_per_sm, k_msm_accumulate, MSM_ACC_THREADS, 0) != cudaSuccess || acc_blocks_per_sm < 1) acc_blocks_per_sm = 4;
-        }
-        const size_t acc_cap = (size_t)sm_count * acc_blocks_per_sm * (g_msm_acc_waves > 0 ? g_msm_acc_waves : 1);
-        k_msm_accumulate<<<gridfor(L.max_items, MSM_ACC_THREADS, g_msm_acc_waves > 0 ? acc_cap : (size_t)sm_count * 16), MSM_ACC_THREADS, 0, s>>>(
+        // 16 blocks per SM, scheduled dynamically: measured faster than one persistent resident wave with a static deal (profiles/r01_kernel_variants.md)
+        k_msm_accumulate<<<gridfor(L.max_items, MSM_ACC_THREADS, (size_t)sm_count * 16), MSM_ACC_THREADS, 0, s>>>(
             bases, (unsigned)buckets_per_job, sorted, hist, offsets, item_off, item_bucket, n_items, order, partial);
     }
     if (ev) cudaEventRecord(ev[2], s);
@@ -629,8 +563,7 @@ cudaError_t msm_run(const MsmJob* jobs, int K, const MsmLayout& L, unsigned char
         g1_xyzz* spanR = blockres; g1_xyzz* spanL = blockres + spans; g1_xyzz* bits = (g1_xyzz*)(scratch + L.bits);
         k_msm_span_sums<<<gridfor(spans, 128, (size_t)sm_count * 16), 128, 0, s>>>(partial, items, item_off, nb, L.span, spans, spanR, spanL);
         // two blocks of the bit-sum kernel fit an SM (128 registers x 256 threads): slice every (set, slot) sum so that one wave covers the machine
-        const bool two_level = g_msm_two_level && L.span_bits >= 6;   // index-weighted sum through row / column sums of the span-sum matrix
-        const unsigned slots = two_level ? 2 : L.span_bits + 2, k0 = two_level ? L.span_bits : 0;   // two-level: only the two L-half slots remain here
+        const unsigned slots = L.span_bits + 2, k0 = 0;
         unsigned P = (unsigned)(2 * (size_t)sm_count / (slots * L.sets));
         const unsigned maxP = L.blocks_per_window / (2 * MSM_SUM_THREADS);
         if (P > maxP) P = maxP;
@@ -639,17 +572,9 @@ cudaError_t msm_run(const MsmJob* jobs, int K, const MsmLayout& L, unsigned char
         g1_xyzz* parts = bits;
         k_msm_bit_sums<<<dim3(slots, L.sets, P), MSM_SUM_THREADS, 0, s>>>(spanR, spanL, L.blocks_per_window, L.span_bits, k0, parts);
         k_msm_bit_finish<<<dim3(slots, L.sets), 32, 0, s>>>(parts, P, L.span_bits, k0, wout);
-        if (two_level) {
-            const unsigned l = L.span_bits - L.span_bits / 2, h = L.span_bits / 2;
-            // the marginal sums live behind the slice sums in the same scratch region (msm_scratch_bytes)
-            g1_xyzz* margA = parts + (size_t)L.sets * (L.span_bits + 2) * 32;
-            g1_xyzz* margB = margA + ((size_t)L.sets << h);
-            k_msm_rc_sums<<<dim3((1u << h) + (1u << l), L.sets), MSM_RC_THREADS, 0, s>>>(spanR, L.blocks_per_window, l, margA, margB);
-            k_msm_marginal_bit_sums<<<dim3(L.span_bits, L.sets), MSM_MBIT_THREADS, 0, s>>>(margA, margB, h, l, wout);
-        }
     }
     if (ev) cudaEventRecord(ev[4], s);
-    if (launches) *launches += 16 + 2 * (unsigned)K + (g_msm_two_level && L.span_bits >= 6 ? 2u : 0u);
+    if (launches) *launches += 16 + 2 * (unsigned)K;
     return cudaGetLastError();
 }
 

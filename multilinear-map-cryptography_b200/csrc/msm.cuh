@@ -32,8 +32,6 @@ struct MsmLayout {
 
 unsigned msm_window_bits(size_t n);
 unsigned msm_table_window_bits(size_t n);
-void set_msm_acc_waves(int waves);   // grid of k_msm_accumulate in resident waves (default 1; 0 = fixed 16 blocks per SM)
-void set_msm_two_level(bool on);   // window reduction: index-weighted sum through row / column sums (default) or bit sums over all span sums
 size_t msm_scratch_bytes(size_t nmax, int K, unsigned c, bool shared, MsmLayout* L, unsigned windows = 0);   // windows > 0: scan only that many low digit positions
 // runs every device phase; per bucket set (job-major) span_bits + 2 Jacobian points are left at scratch + L.window_out:
 // S_w = 2^log2(span) * sum_k 2^k P[k] + P[span_bits] + P[span_bits + 1]  (finished on the host: a Horner pass of ~40 group operations)

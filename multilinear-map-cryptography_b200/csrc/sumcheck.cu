@@ -19,9 +19,6 @@
 #include "../host/field64.hpp"
 #include <cstring>
 
-#ifndef TSG_BE_MINB
-#define TSG_BE_MINB 2
-#endif
 namespace tsg {
 
 // ---------------------------------------------------------------- round sums over the ranks, inside the round kernel
@@ -307,7 +304,7 @@ __global__ void __launch_bounds__(SC_THREADS, (D <= 2 ? 2 : 1)) k_bind_eval(ScTa
 
 
 // d = 2 with the claim of the round being evaluated (= g_k(r), known to the host before the launch)
-__global__ void __launch_bounds__(SC_THREADS, TSG_BE_MINB) k_bind_eval2_claim(ScTables tabs, size_t quarter, const fr_ctab r, const fr_t claim, fr_t* partials,
+__global__ void __launch_bounds__(SC_THREADS, 2) k_bind_eval2_claim(ScTables tabs, size_t quarter, const fr_ctab r, const fr_t claim, fr_t* partials,
                                                                    unsigned int* ticket, fr_t* out4) {
     __shared__ fr_t smem[2 * 32];
     EvalAcc2Claim acc; acc.clear();
@@ -329,81 +326,6 @@ __global__ void __launch_bounds__(SC_THREADS, TSG_BE_MINB) k_bind_eval2_claim(Sc
     fr_t v[2];
     acc.finish(v);
     grid_finish_sum<fr_t, 2>(v, partials, ticket, smem, EvalClaimEpilogue{out4, claim});
-}
-
-// ==================================================================================================
-// TMA-pipelined variants for large tables (work a multiple of TMA_THREADS).  Same arithmetic as the
-// simple kernels above; the inputs arrive through the shared-memory ring of tma_stream.cuh.
-// ==================================================================================================
-template <int D>
-__global__ void __launch_bounds__(TMA_THREADS, (D <= 2 ? TMA_MINBLOCKS : 1)) k_round_eval_tma(ScTables tabs, size_t half, fr_t* partials, unsigned int* ticket, fr_t* out4) {
-    extern __shared__ unsigned char smem_raw[];
-    __shared__ fr_t smem[EvalAcc<D>::NV * 32];
-    typedef tma::Pipeline<2 * D, TMA_THREADS, TMA_STAGES> Pipe;
-    Pipe pipe;
-    const fr_t* streams[2 * D];
-#pragma unroll
-    for (int t = 0; t < D; ++t) { streams[2 * t] = tabs.t[t]; streams[2 * t + 1] = tabs.t[t] + half; }
-    pipe.init(smem_raw, streams, half / TMA_THREADS);
-    EvalAcc<D> acc; acc.clear();
-    for (size_t k = 0; k < pipe.my_tiles; ++k) {
-        fr_t e[2 * D];
-        pipe.fetch(k, e);
-        fr_t lo[D], hi[D];
-#pragma unroll
-        for (int t = 0; t < D; ++t) { lo[t] = e[2 * t]; hi[t] = e[2 * t + 1]; }
-        acc.pair(lo, hi);
-    }
-    fr_t v[EvalAcc<D>::NV];
-    acc.finish(v);
-    grid_finish_sum<fr_t, EvalAcc<D>::NV>(v, partials, ticket, smem, EvalEpilogue<D>{out4});
-}
-
-__global__ void __launch_bounds__(TMA_THREADS, 4) k_bind_tma(fr_t* t, size_t half, const fr_ctab r) {
-    extern __shared__ unsigned char smem_raw[];
-    typedef tma::Pipeline<2, TMA_THREADS, TMA_STAGES> Pipe;
-    Pipe pipe;
-    const fr_t* streams[2] = {t, t + half};
-    pipe.init(smem_raw, streams, half / TMA_THREADS);
-    for (size_t k = 0; k < pipe.my_tiles; ++k) {
-        fr_t e[2];
-        pipe.fetch(k, e);
-        st256(t + pipe.tile_of(k) * TMA_THREADS + threadIdx.x, e[0] + r.mul(e[1] - e[0]));
-    }
-}
-
-template <int D>
-__global__ void __launch_bounds__(TMA_THREADS, (D <= 2 ? TMA_MINBLOCKS : 1)) k_bind_eval_tma(ScTables tabs, size_t quarter, const fr_ctab r, fr_t* partials,
-                                                                  unsigned int* ticket, fr_t* out4) {
-    extern __shared__ unsigned char smem_raw[];
-    __shared__ fr_t smem[EvalAcc<D>::NV * 32];
-    typedef tma::Pipeline<4 * D, TMA_THREADS, TMA_STAGES> Pipe;
-    Pipe pipe;
-    const fr_t* streams[4 * D];
-#pragma unroll
-    for (int t = 0; t < D; ++t) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) streams[4 * t + j] = tabs.t[t] + j * quarter;
-    }
-    pipe.init(smem_raw, streams, quarter / TMA_THREADS);
-    EvalAcc<D> acc; acc.clear();
-    for (size_t k = 0; k < pipe.my_tiles; ++k) {
-        fr_t e[4 * D];
-        pipe.fetch(k, e);
-        const size_t p = pipe.tile_of(k) * TMA_THREADS + threadIdx.x;
-        fr_t lo[D], hi[D];
-#pragma unroll
-        for (int t = 0; t < D; ++t) {
-            lo[t] = e[4 * t + 0] + r.mul(e[4 * t + 2] - e[4 * t + 0]);
-            hi[t] = e[4 * t + 1] + r.mul(e[4 * t + 3] - e[4 * t + 1]);
-            st256(tabs.t[t] + p, lo[t]);
-            st256(tabs.t[t] + p + quarter, hi[t]);
-        }
-        acc.pair(lo, hi);
-    }
-    fr_t v[EvalAcc<D>::NV];
-    acc.finish(v);
-    grid_finish_sum<fr_t, EvalAcc<D>::NV>(v, partials, ticket, smem, EvalEpilogue<D>{out4});
 }
 
 // ---------------------------------------------------------------- warp-private prefetch variants
@@ -532,19 +454,9 @@ __global__ void __launch_bounds__(SC_THREADS, 2) k_round_eval2_claim_pf(ScTables
 static size_t g_pf_min_work = (size_t)1 << 21;
 void set_prefetch_min_work(size_t w) { g_pf_min_work = w < 1024 ? 1024 : w; }
 
-// Runtime switch between the simple grid-stride kernels and the TMA-pipelined ones: on B200 the rounds are
-// integer-pipe bound with the carry-chain multiplier and the simple kernels measured 5-10% faster
-// (profiles/r01_kernel_variants.md), so the pipelined path is opt-in (tsgpu_set_tuning "tma_min_log2").
-static size_t g_tma_min_work = ~(size_t)0;
-void set_tma_min_work(size_t w) { g_tma_min_work = w < TMA_THREADS ? TMA_THREADS : w; }
-
 template <class K>
 static cudaError_t enable_smem(K kernel, size_t bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-}
-static inline int tma_grid(size_t tiles, int sm_count, int blocks_per_sm) {
-    size_t cap = (size_t)sm_count * blocks_per_sm;
-    return (int)(tiles < cap ? tiles : cap);
 }
 
 // fr_ctab::make with native 64-bit host arithmetic (the generic one runs ~19 products of the 32-bit limb code with an emulated carry flag,
@@ -584,21 +496,6 @@ cudaError_t launch_round_eval(int d, const ScTables& tabs, size_t n, fr_t* parti
         }
         return cudaGetLastError();
     }
-    if (half >= g_tma_min_work) {
-        size_t tiles = half / TMA_THREADS;
-        int g = tma_grid(tiles, sm_count, TMA_MINBLOCKS);
-        cudaError_t e;
-        switch (d) {
-            case 1: { size_t sm = tma::Pipeline<2, TMA_THREADS, TMA_STAGES>::SMEM_BYTES; if ((e = enable_smem(k_round_eval_tma<1>, sm))) return e;
-                      k_round_eval_tma<1><<<g, TMA_THREADS, sm, s>>>(tabs, half, partials, ticket, out4); break; }
-            case 2: { size_t sm = tma::Pipeline<4, TMA_THREADS, TMA_STAGES>::SMEM_BYTES; if ((e = enable_smem(k_round_eval_tma<2>, sm))) return e;
-                      k_round_eval_tma<2><<<g, TMA_THREADS, sm, s>>>(tabs, half, partials, ticket, out4); break; }
-            case 3: { size_t sm = tma::Pipeline<6, TMA_THREADS, TMA_STAGES>::SMEM_BYTES; if ((e = enable_smem(k_round_eval_tma<3>, sm))) return e;
-                      k_round_eval_tma<3><<<g, TMA_THREADS, sm, s>>>(tabs, half, partials, ticket, out4); break; }
-            default: return cudaErrorInvalidValue;
-        }
-        return cudaGetLastError();
-    }
     if (d == 2 && half >= g_pf_min_work && half % 32 == 0) {
         const size_t sm = (size_t)PF_WARPS * 4 * 1024;
         cudaError_t e = enable_smem(k_round_eval2_pf, sm);
@@ -619,13 +516,6 @@ cudaError_t launch_round_eval(int d, const ScTables& tabs, size_t n, fr_t* parti
 cudaError_t launch_bind(fr_t* t, size_t n, const fr_t& r_elem, int sm_count, cudaStream_t s) {
     const fr_ctab r = make_ctab_host(r_elem);   // T[k] = r 2^(32k+64) mod p: the fold multiplies by this one constant
     size_t half = n / 2;
-    if (half >= g_tma_min_work) {
-        size_t sm = tma::Pipeline<2, TMA_THREADS, TMA_STAGES>::SMEM_BYTES;
-        cudaError_t e = enable_smem(k_bind_tma, sm);
-        if (e) return e;
-        k_bind_tma<<<tma_grid(half / TMA_THREADS, sm_count, 4), TMA_THREADS, sm, s>>>(t, half, r);
-        return cudaGetLastError();
-    }
     int grid = sc_grid(half, sm_count, SC_BLOCKS_PER_SM_BIND);
     k_bind<<<grid, SC_THREADS, 0, s>>>(t, half, r);
     return cudaGetLastError();
@@ -643,7 +533,7 @@ cudaError_t launch_bind_eval(int d, const ScTables& tabs, size_t n, const fr_t& 
                              fr_t* out4, int sm_count, cudaStream_t s) {
     const fr_ctab r = make_ctab_host(r_elem);
     size_t quarter = n / 4;
-    if (claim && d == 2 && quarter < g_tma_min_work) {
+    if (claim && d == 2) {
         if (quarter >= g_pf_min_work && quarter % 32 == 0) {
             const size_t sm = (size_t)PF_WARPS * 8 * 1024;
             cudaError_t e = enable_smem(k_bind_eval2_claim_pf, sm);
@@ -651,22 +541,7 @@ cudaError_t launch_bind_eval(int d, const ScTables& tabs, size_t n, const fr_t& 
             k_bind_eval2_claim_pf<<<sc_grid(quarter, sm_count, 2), SC_THREADS, sm, s>>>(tabs, quarter, r, *claim, partials, ticket, out4);
             return cudaGetLastError();
         }
-        k_bind_eval2_claim<<<sc_grid(quarter, sm_count, TSG_BE_MINB), SC_THREADS, 0, s>>>(tabs, quarter, r, *claim, partials, ticket, out4);
-        return cudaGetLastError();
-    }
-    if (quarter >= g_tma_min_work) {
-        size_t tiles = quarter / TMA_THREADS;
-        int g = tma_grid(tiles, sm_count, TMA_MINBLOCKS);
-        cudaError_t e;
-        switch (d) {
-            case 1: { size_t sm = tma::Pipeline<4, TMA_THREADS, TMA_STAGES>::SMEM_BYTES; if ((e = enable_smem(k_bind_eval_tma<1>, sm))) return e;
-                      k_bind_eval_tma<1><<<g, TMA_THREADS, sm, s>>>(tabs, quarter, r, partials, ticket, out4); break; }
-            case 2: { size_t sm = tma::Pipeline<8, TMA_THREADS, TMA_STAGES>::SMEM_BYTES; if ((e = enable_smem(k_bind_eval_tma<2>, sm))) return e;
-                      k_bind_eval_tma<2><<<g, TMA_THREADS, sm, s>>>(tabs, quarter, r, partials, ticket, out4); break; }
-            case 3: { size_t sm = tma::Pipeline<12, TMA_THREADS, TMA_STAGES>::SMEM_BYTES; if ((e = enable_smem(k_bind_eval_tma<3>, sm))) return e;
-                      k_bind_eval_tma<3><<<tma_grid(tiles, sm_count, 1), TMA_THREADS, sm, s>>>(tabs, quarter, r, partials, ticket, out4); break; }
-            default: return cudaErrorInvalidValue;
-        }
+        k_bind_eval2_claim<<<sc_grid(quarter, sm_count, SC_BLOCKS_PER_SM), SC_THREADS, 0, s>>>(tabs, quarter, r, *claim, partials, ticket, out4);
         return cudaGetLastError();
     }
     int grid = sc_grid(quarter, sm_count, SC_BLOCKS_PER_SM);

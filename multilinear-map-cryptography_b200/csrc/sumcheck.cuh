@@ -9,23 +9,6 @@ constexpr int SC_THREADS = 256;
 constexpr int SC_BLOCKS_PER_SM = 2;        // evaluation kernels: ~100+ registers per thread
 constexpr int SC_BLOCKS_PER_SM_BIND = 4;   // bind-only kernel: light
 constexpr int SC_MAX_TABLES = 3;
-#ifndef TSG_TMA_THREADS
-#define TSG_TMA_THREADS 128
-#endif
-#ifndef TSG_TMA_STAGES
-#define TSG_TMA_STAGES 3
-#endif
-#ifndef TSG_TMA_MINBLOCKS
-#define TSG_TMA_MINBLOCKS 2
-#endif
-#ifndef TSG_TMA_MIN_WORK
-#define TSG_TMA_MIN_WORK (1u << 14)
-#endif
-constexpr int TMA_THREADS = TSG_TMA_THREADS;   // positions per tile of the TMA-pipelined kernels
-constexpr int TMA_STAGES = TSG_TMA_STAGES;
-constexpr int TMA_MINBLOCKS = TSG_TMA_MINBLOCKS;
-constexpr size_t TMA_MIN_WORK = TSG_TMA_MIN_WORK;  // below this the simple grid-stride kernels are used
-
 struct ScTables { fr_t* t[SC_MAX_TABLES]; };
 
 // peer mailboxes of the sharded sum-check (sumcheck.cu "round sums over the ranks"): per rank one device allocation of SC_PEER_MBOX_BYTES,
@@ -42,7 +25,6 @@ cudaError_t launch_peer_allgather(const void* in, size_t bytes, void* out, cudaS
 // number of blocks the evaluation kernels may launch (sizes the partial-sum scratch)
 inline int sc_max_grid(int sm_count) { return sm_count * SC_BLOCKS_PER_SM_BIND; }
 
-void set_tma_min_work(size_t positions);
 void set_prefetch_min_work(size_t positions);   // d = 2 round kernels with a warp-private shared-memory prefetch of the next tile
 // claim (optional, d = 2 only): the value g(0) + g(1) must have; the kernel then sums g(0) and g(2) and derives g(1)
 cudaError_t launch_round_eval(int d, const ScTables& tabs, size_t n, fr_t* partials, unsigned int* ticket, fr_t* out4,

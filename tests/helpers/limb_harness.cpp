@@ -21,9 +21,8 @@ static void binop(int op, const uint32_t* a, const uint32_t* b, size_t n, uint32
             case 6: r = x.inverse(); break;
             case 7: r = x.neg(); break;
             case 8: limb::mont_mul<P>(r.l, x.l, y.l); break;
-            case 9: limb::mont_mul29<P>(r.l, x.l, y.l); break;
-            case 10: r = fp_ctab<P>::make(y).mul(x); break;
-            case 11: r = x.sqr_dedicated(); break;                // 36 + 72 multiply-adds (limb::mont_sqr)   // constant-multiplier table of y applied to x
+            case 10: r = fp_ctab<P>::make(y).mul(x); break;       // constant-multiplier table of y applied to x
+            case 11: r = x.sqr(); break;
             default: r = fp<P>::zero();
         }
         memcpy(out + 8 * i, r.l, 32);
@@ -40,18 +39,6 @@ extern "C" void limb_dot(int field, const uint32_t* a, const uint32_t* b, size_t
         fr_t r = acc.reduce(); memcpy(out, r.l, 32);
     } else {
         wide_acc<FqP> acc; acc.clear();
-        for (size_t i = 0; i < n; ++i) { fq_t x, y; memcpy(x.l, a + 8 * i, 32); memcpy(y.l, b + 8 * i, 32); acc.add_product(x, y); }
-        fq_t r = acc.reduce(); memcpy(out, r.l, 32);
-    }
-}
-// same through the radix-2^29 accumulator
-extern "C" void limb_dot29(int field, const uint32_t* a, const uint32_t* b, size_t n, uint32_t* out) {
-    if (field == 0) {
-        wide_acc29<FrP> acc; acc.clear();
-        for (size_t i = 0; i < n; ++i) { fr_t x, y; memcpy(x.l, a + 8 * i, 32); memcpy(y.l, b + 8 * i, 32); acc.add_product(x, y); }
-        fr_t r = acc.reduce(); memcpy(out, r.l, 32);
-    } else {
-        wide_acc29<FqP> acc; acc.clear();
         for (size_t i = 0; i < n; ++i) { fq_t x, y; memcpy(x.l, a + 8 * i, 32); memcpy(y.l, b + 8 * i, 32); acc.add_product(x, y); }
         fq_t r = acc.reduce(); memcpy(out, r.l, 32);
     }

@@ -93,26 +93,6 @@ def test_large_round_linearity(ctx, oracle):
     assert (finals == ref["finals"]).all()
 
 
-@pytest.mark.parametrize("d", [1, 2, 3])
-@pytest.mark.parametrize("fused", [True, False])
-def test_tma_pipelined_path_matches_oracle(ctx, oracle, d, fused):
-    """2^17 entries with the TMA-pipelined kernels switched on (>= 2^12 positions per stream), the
-    later rounds the simple kernels; every round polynomial and the final table values must match."""
-    nv = 17
-    tables = [oracle.chacha_fr_rand(seed_bytes(40 + 3 * d + t), 1 << nv) for t in range(d)]
-    ctx.set_tuning("tma_min_log2", 12)
-    try:
-        coeffs, chals, finals = drive_rounds(ctx, oracle, tables, fused=fused)
-    finally:
-        ctx.set_tuning("tma_min_log2", -1)
-    zero, one = oracle.fr_from_ints([0, 1])
-    claimed = oracle.field_binop("fr", "add", oracle.horner(coeffs[0], zero), oracle.horner(coeffs[0], one))[0]
-    ref = oracle.sumcheck_prove_product(tables, claimed, mode="tables")
-    assert (coeffs == ref["round_polynomials"]).all()
-    assert (chals == ref["challenges"]).all()
-    assert (finals == ref["finals"]).all()
-
-
 @pytest.mark.parametrize("nv", [12, 17, 18])
 def test_warp_prefetch_path_matches_oracle(ctx, tsgpu, oracle, nv):
     """d = 2 with the warp-private prefetch kernels (cp.async.bulk into one shared-memory slot per warp) switched on for every launch

@@ -46,9 +46,9 @@ def test_add_sub_mul_match_oracle(harness, oracle, field):
     xs, ys = _cases(mod, 4000, 11)
     a = oracle.ints_to_limbs(xs); b = oracle.ints_to_limbs(ys); n = len(xs)
     f = 0 if field == "fr" else 1
-    # op 2: product path the kernels use; op 3: carry-chain wide product + normalise + reduce; op 8: carry-chain product; op 9: radix-2^29 product
+    # op 2: product path the kernels use; op 3: carry-chain wide product + normalise + reduce; op 8: carry-chain product
     # op 10: multiplication through the per-launch constant table (sum-check fold)
-    for op, name in ((0, "add"), (1, "sub"), (2, "mul"), (3, "mul"), (8, "mul"), (9, "mul"), (10, "mul")):
+    for op, name in ((0, "add"), (1, "sub"), (2, "mul"), (3, "mul"), (8, "mul"), (10, "mul")):
         out = np.empty_like(a)
         harness.limb_binop(f, op, _p(a), _p(b), C.c_size_t(n), _p(out))
         assert (out == oracle.field_binop(field, name, a, b)).all(), (field, op)
@@ -86,12 +86,12 @@ def test_lazy_dot_product(harness, oracle, field):
         assert sum(int(w[k]) << (64 * k) for k in range(8)) == xs[i] * ys[i]
     for n in (0, 1, 15, 16, 17, 100, len(xs)):
         o = np.zeros(4, dtype=np.uint64)
-        for fn in (harness.limb_dot, harness.limb_dot29):
+        for fn in (harness.limb_dot,):
             fn(f, _p(a), _p(b), C.c_size_t(n), _p(o))
             assert oracle.limbs_to_ints(o)[0] == sum(x * y for x, y in zip(xs[:n], ys[:n])) * rinv % mod
     big = oracle.ints_to_limbs([mod - 1] * 200)     # worst case for accumulator head-room
     o = np.zeros(4, dtype=np.uint64)
-    for fn in (harness.limb_dot, harness.limb_dot29):
+    for fn in (harness.limb_dot,):
         fn(f, _p(big), _p(big), C.c_size_t(200), _p(o))
         assert oracle.limbs_to_ints(o)[0] == 200 * (mod - 1) ** 2 * rinv % mod
 
@@ -115,8 +115,8 @@ def test_mul_sub_single_reduction_matches_two_products(harness, oracle, field):
 
 
 @pytest.mark.parametrize("field", ["fr", "fq"])
-def test_dedicated_squaring_matches_product(harness, oracle, field):
-    """limb::mont_sqr (28 doubled off-diagonal products + 8 squares, then one reduction) == a * a * R^-1"""
+def test_squaring_matches_product(harness, oracle, field):
+    """fp::sqr == a * a * R^-1 on edge values and all-ones patterns of every length"""
     mod = oracle.R_MOD if field == "fr" else oracle.P_MOD
     xs, _ = _cases(mod, 6000, 21)
     xs += [(1 << 256) % mod, mod - 3, 0xFFFFFFFF, 0xFFFFFFFF << 32, ((1 << 254) - 1) % mod] + [((1 << k) - 1) % mod for k in range(1, 255, 7)]

@@ -14,7 +14,6 @@ torch.cuda.init()
 stream = torch.cuda.Stream()
 torch.cuda.set_stream(stream)
 ctx = ts.Context(0, stream.cuda_stream)
-ctx.set_tuning("tma_min_log2", tma_log)
 pf_log = int(sys.argv[3]) if len(sys.argv) > 3 else -1       # >= 0: d = 2 rounds with at least 2^pf_log positions use the warp-private prefetch kernels
 ctx.set_tuning("prefetch_min_log2", pf_log)
 w = O.chacha_fr_rand(bytes([4]) * 32, nv)
@@ -25,7 +24,7 @@ B = ctx.table_eq(w[::-1].copy())
 ctx.synchronize()
 print("generated 2 tables of 2^%d in %.2fs" % (nv, time.time() - t0), flush=True)
 N = 1 << nv
-res = {"nv": nv, "tma_min_log2": tma_log, "prefetch_min_log2": pf_log}
+res = {"nv": nv, "prefetch_min_log2": pf_log}
 
 def timeit(fn, setup, reps=5):
     best = 1e9
