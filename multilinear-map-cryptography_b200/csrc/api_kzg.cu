@@ -9,6 +9,7 @@
 #include "mle.cuh"
 #include "lagrange.cuh"
 #include <map>
+#include <mutex>
 #include <tuple>
 #include "../host/field64.hpp"
 
@@ -36,6 +37,9 @@ struct tsgpu_srs {
     // per-rank slices of an evaluation basis (sharded proving): nodes first .. first + count - 1 of the m-node domain, with their tables
     struct Slice { g1_affine* pts = nullptr; g1_affine* table = nullptr; unsigned table_c = 0; g1_affine* short_table = nullptr; };
     std::map<std::tuple<size_t, size_t, size_t>, Slice> lagrange_slices;
+    // the lazy caches above are filled through const handles (tsgpu_srs_lagrange_prepare*): one lock per handle serialises the fills, so a
+    // params handle may be shared by proofs running on several host threads (each with its own context / stream)
+    mutable std::mutex cache_mu;
 };
 // a base array the MSM can run on: plain points and, optionally, their window tables
 struct MsmBasis { const g1_affine* pts; size_t n; const g1_affine* table; unsigned table_c; const g1_affine* short_table = nullptr; unsigned short_c = 0, short_windows = 0; };
@@ -533,13 +537,18 @@ int tsgpu_srs_generate_range(tsgpu_ctx* ctx, const tsgpu_fr* tau, size_t first, 
 }
 
 // ------------------------------------------------------------------------------------------- evaluation-basis KZG
-static g1_affine* lagrange_basis(const tsgpu_srs* srs, size_t m) {
+static g1_affine* lagrange_basis_unlocked(const tsgpu_srs* srs, size_t m) {
     auto it = srs->lagrange.find(m);
     return it == srs->lagrange.end() ? nullptr : it->second;
 }
+static g1_affine* lagrange_basis(const tsgpu_srs* srs, size_t m) {
+    std::lock_guard<std::mutex> lock(srs->cache_mu);
+    return lagrange_basis_unlocked(srs, m);
+}
 static MsmBasis lagrange_msm_basis(const tsgpu_srs* srs, size_t m) {
+    std::lock_guard<std::mutex> lock(srs->cache_mu);
     auto it = srs->lagrange_table.find(m);
-    MsmBasis b{lagrange_basis(srs, m), m, it == srs->lagrange_table.end() ? nullptr : it->second.first, it == srs->lagrange_table.end() ? 0u : it->second.second};
+    MsmBasis b{lagrange_basis_unlocked(srs, m), m, it == srs->lagrange_table.end() ? nullptr : it->second.first, it == srs->lagrange_table.end() ? 0u : it->second.second};
     // short scalars (< 2^64): a dedicated table of MSM_SHORT_C-bit windows when the full table's windows are wider, else the low
     // windows of the full table itself
     auto sh = srs->lagrange_short_table.find(m);
@@ -602,7 +611,8 @@ static int build_lagrange_range(tsgpu_ctx* ctx, tsgpu_srs* srs, size_t m, size_t
 int tsgpu_srs_lagrange_prepare(tsgpu_ctx* ctx, const tsgpu_srs* srs_c, size_t m) {
     if (!ctx || !srs_c) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
     tsgpu_srs* srs = const_cast<tsgpu_srs*>(srs_c);
-    if (lagrange_basis(srs, m)) return TSGPU_OK;
+    std::lock_guard<std::mutex> lock(srs->cache_mu);
+    if (lagrange_basis_unlocked(srs, m)) return TSGPU_OK;
     tsgpu_srs::Slice sl;
     int rc = build_lagrange_range(ctx, srs, m, 0, m, &sl);
     if (rc) return rc;
@@ -615,6 +625,7 @@ int tsgpu_srs_lagrange_prepare(tsgpu_ctx* ctx, const tsgpu_srs* srs_c, size_t m)
 int tsgpu_srs_lagrange_prepare_range(tsgpu_ctx* ctx, const tsgpu_srs* srs_c, size_t m, size_t first, size_t count) {
     if (!ctx || !srs_c) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
     tsgpu_srs* srs = const_cast<tsgpu_srs*>(srs_c);
+    std::lock_guard<std::mutex> lock(srs->cache_mu);
     auto key = std::make_tuple(m, first, count);
     if (srs->lagrange_slices.count(key)) return TSGPU_OK;
     tsgpu_srs::Slice sl;
@@ -624,6 +635,7 @@ int tsgpu_srs_lagrange_prepare_range(tsgpu_ctx* ctx, const tsgpu_srs* srs_c, siz
     return TSGPU_OK;
 }
 static MsmBasis lagrange_slice_basis(const tsgpu_srs* srs, size_t m, size_t first, size_t count) {
+    std::lock_guard<std::mutex> lock(srs->cache_mu);
     const tsgpu_srs::Slice& sl = srs->lagrange_slices.at(std::make_tuple(m, first, count));
     MsmBasis b{sl.pts, count, sl.table, sl.table_c};
     if (sl.short_table) { b.short_table = sl.short_table; b.short_c = MSM_SHORT_C; b.short_windows = MSM_SHORT_WINDOWS; }

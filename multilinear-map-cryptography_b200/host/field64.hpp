@@ -126,6 +126,14 @@ struct G1J {
         ax = x * zi2; ay = y * zi2 * zi;
         return true;
     }
+    // coordinates reduced (< p) and Y^2 = X^3 + 3 Z^6 (the identity, Z = 0, passes).  BN254 G1 has cofactor 1: on the curve means in the group.
+    // arkworks' G1Projective cannot hold anything else; bytes that arrive over the C ABI can.
+    bool is_valid() const {
+        if (Fq64::geq_mod(x.l) || Fq64::geq_mod(y.l) || Fq64::geq_mod(z.l)) return false;
+        if (is_identity()) return true;
+        Fq64 z2 = z.sqr(), z6 = z2.sqr() * z2;
+        return y.sqr() == x.sqr() * x + (z6.dbl() + z6);
+    }
     bool equals(const G1J& o) const {
         if (is_identity() || o.is_identity()) return is_identity() && o.is_identity();
         Fq64 a = z.sqr(), b = o.z.sqr();

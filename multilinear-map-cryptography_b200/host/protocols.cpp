@@ -455,6 +455,7 @@ int tsgpu_kzg_verify(const tsgpu_params* params, const tsgpu_g1* commitment, con
                      const tsgpu_g1* proof, int* valid) {
     if (!params || !commitment || !point || !value || !proof || !valid) return TSGPU_E_INVALID_PARAMETERS;
     G1J C, pi; memcpy(&C, commitment, 96); memcpy(&pi, proof, 96);
+    if (!C.is_valid() || !pi.is_valid()) { *valid = 0; return TSGPU_OK; }      // not points of G1: nothing the reference's types could even hold
     *valid = kzg_verify(params->vk, C, Fr64::from_raw(point->l), Fr64::from_raw(value->l), pi) ? 1 : 0;
     return TSGPU_OK;
 }
@@ -481,6 +482,7 @@ int tsgpu_kzg_batch_verify(const tsgpu_params* params, const tsgpu_g1* commitmen
         fr_t g32 = rng.rand_field<fr_t>();
         Fr64 gamma = Fr64::from_raw(g32.l);
         G1J C, pi; memcpy(&C, &commitments[i], 96); memcpy(&pi, &proofs[i], 96);
+        if (!C.is_valid() || !pi.is_valid()) { *valid = 0; return TSGPU_OK; }
         bc = bc.add(C.mul(gamma));
         bv = bv + Fr64::from_raw(values[i].l) * gamma;
         bp = bp.add(pi.mul(gamma));

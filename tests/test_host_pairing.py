@@ -78,3 +78,24 @@ def test_kzg_batch_verify_mirrors_reference_formula(tsgpu, oracle):
 def test_pairing_fast_paths_agree_with_the_plain_ones(tsgpu):
     """split final exponentiation == f^((p^12 - 1) / r), Fq12 inverse / symmetric square / Frobenius^6 == conjugation, Jacobian G2 multiplication"""
     assert tsgpu.lib().tsgpu_pairing_self_check() == 1
+
+
+def test_kzg_verify_rejects_bytes_that_are_not_points_of_g1(tsgpu, oracle):
+    """The C ABI takes raw Jacobian coordinates; arkworks' G1Projective can only ever hold curve points.  An off-curve commitment or proof, or a
+    coordinate that is not reduced mod p, makes verify return false instead of feeding the pairing undefined input."""
+    vp = tsgpu.HostVerifierParams(4)
+    pw = oracle.setup_g1_powers(9, fast=True)
+    poly = oracle.fr_from_ints([1, 2, 3]); z = oracle.fr_from_ints([5])[0]
+    Cm = oracle.kzg_commit(pw, poly)
+    v, q = oracle.kzg_value_quotient(poly, z)
+    pi = oracle.kzg_commit(pw, q)
+    assert tsgpu.kzg_verify(vp, Cm, z, v, pi)
+    off = Cm.copy(); off[0] ^= np.uint64(1)                                   # X changed: Y^2 != X^3 + 3 Z^6
+    assert not tsgpu.kzg_verify(vp, off, z, v, pi) and not tsgpu.kzg_verify(vp, Cm, z, v, off)
+    big = Cm.copy(); big[0:4] = oracle.int_to_limbs((1 << 256) - 1)           # X >= p: not a reduced field element
+    assert not tsgpu.kzg_verify(vp, big, z, v, pi)
+    # another Jacobian representative of the SAME point (X l^2, Y l^3, Z l) still verifies
+    lam = 0x1234567
+    x, y, zz = (oracle.fq_to_ints(Cm[4 * i:4 * i + 4].reshape(1, 4))[0] for i in range(3))
+    rep = np.concatenate([oracle.fq_from_ints([x * lam * lam, y * lam ** 3, zz * lam]).reshape(-1)])
+    assert oracle.g1_equal(rep, Cm) and tsgpu.kzg_verify(vp, rep, z, v, pi)
