@@ -3,6 +3,8 @@
 // "last block finishes" grid reduction used by every kernel that ends in a handful of Fr sums.
 #pragma once
 #include <cuda_runtime.h>
+#include <type_traits>
+#include <utility>
 #include "fp.cuh"
 
 namespace tsg {
@@ -86,6 +88,12 @@ __device__ __forceinline__ void block_reduce_sum(F (&v)[NV], F* smem) {
 // Grid-wide finish: every block deposits NV partial sums; the last block to arrive (atomic ticket)
 // adds them all and writes `out[0..NV)`.  `partials` holds gridDim.x * NV elements, `ticket` is a
 // zero-initialised counter that the finishing block resets for the next launch.
+// An epilogue with a member `warp(F (&v)[NV], F* smem)` is run by the 32 lanes of warp 0 of the finishing block (v valid in lane 0, smem free for its
+// use) instead of by thread 0 alone - the sharded sum-check uses the lanes to talk to all peers at once.
+template <class E, class F, int NV, class = void> struct epilogue_has_warp : std::false_type {};
+template <class E, class F, int NV>
+struct epilogue_has_warp<E, F, NV, std::void_t<decltype(std::declval<const E&>().warp(std::declval<F (&)[NV]>(), (F*)nullptr))>> : std::true_type {};
+
 template <class F, int NV, class Epilogue>
 __device__ __forceinline__ void grid_finish_sum(F (&v)[NV], F* partials, unsigned int* ticket, F* smem, Epilogue epi) {
     __shared__ bool s_last;
@@ -109,7 +117,10 @@ __device__ __forceinline__ void grid_finish_sum(F (&v)[NV], F* partials, unsigne
     }
     __syncthreads();
     block_reduce_sum<F, NV>(acc, smem);
-    if (threadIdx.x == 0) {
+    if constexpr (epilogue_has_warp<Epilogue, F, NV>::value) {
+        if (threadIdx.x < 32) epi.warp(acc, smem);
+        if (threadIdx.x == 0) *ticket = 0;
+    } else if (threadIdx.x == 0) {
         epi(acc);
         *ticket = 0;
     }

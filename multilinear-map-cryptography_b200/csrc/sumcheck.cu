@@ -23,8 +23,8 @@ namespace tsg {
 
 // ---------------------------------------------------------------- round sums over the ranks, inside the round kernel
 // Sharded SumCheck::prove (comm.cu): every rank sums its slice of the hypercube; the round values are the sums over the ranks.  Instead of
-// a separate widen kernel + ncclAllReduce + copy per round, the FINISHING thread of the round kernel exchanges the block-reduced sums with
-// its peers directly: it stores its NV field elements into slot [parity][rank] of every peer's mailbox (peer-mapped device memory: plain
+// a separate widen kernel + ncclAllReduce + copy per round, the first warp of the FINISHING block of the round kernel exchanges the block-reduced
+// sums with its peers directly (lane g serves peer g): it stores its NV field elements into slot [parity][rank] of every peer's mailbox (peer-mapped device memory: plain
 // stores that travel over NVLink / NVSwitch), publishes them with a system-scope fence + sequence flag, spins until the G slots of its
 // own mailbox carry the same sequence number, and adds them in rank order (exact modular additions: every rank gets the same bits).  The
 // epilogue then writes the global values to the pinned host mirror as on one GPU.  Two parities: a fast peer may already deliver round
@@ -54,37 +54,44 @@ __device__ __forceinline__ fr_t peer_load(const fr_t* src) {
     return r;
 }
 
+// run by the 32 lanes of warp 0 of the finishing block: v valid in lane 0 on entry and on exit; lane g serves peer g
 template <int NV>
-__device__ __noinline__ void peer_sum(fr_t (&v)[NV]) {
+__device__ __noinline__ void peer_sum(fr_t (&v)[NV], fr_t* smem) {
     static_assert(NV * sizeof(fr_t) <= SC_PEER_SLOT_DATA, "slot too small");
     const int G = g_peer.nranks, me = g_peer.rank;
+    const int lane = threadIdx.x & 31;
     const unsigned seq = g_peer.seq + 1;
     const size_t par = (size_t)(seq & 1u) * SC_MAX_PEERS * SC_PEER_SLOT;
-    for (int g = 0; g < G; ++g) {
-        fr_t* dst = (fr_t*)(g_peer.mbox[g] + par + (size_t)me * SC_PEER_SLOT);
+    if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < NV; ++k) peer_store(dst + k, v[k]);
+        for (int k = 0; k < NV; ++k) smem[k] = v[k];
     }
-    __threadfence_system();
-    for (int g = 0; g < G; ++g)
-        *(volatile unsigned*)(g_peer.mbox[g] + par + (size_t)me * SC_PEER_SLOT + SC_PEER_SLOT_DATA) = seq;
+    __syncwarp();
     const unsigned char* mine = g_peer.mbox[me] + par;
-    const long long t0 = clock64();
-    for (int g = 0; g < G; ++g) {
-        const volatile unsigned* flag = (const volatile unsigned*)(mine + (size_t)g * SC_PEER_SLOT + SC_PEER_SLOT_DATA);
+    if (lane < G) {
+        unsigned char* slot = g_peer.mbox[lane] + par + (size_t)me * SC_PEER_SLOT;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) peer_store((fr_t*)slot + k, smem[k]);
+        __threadfence_system();
+        *(volatile unsigned*)(slot + SC_PEER_SLOT_DATA) = seq;
+        const volatile unsigned* flag = (const volatile unsigned*)(mine + (size_t)lane * SC_PEER_SLOT + SC_PEER_SLOT_DATA);
+        const long long t0 = clock64();
         while (*flag != seq) {
             if ((unsigned long long)(clock64() - t0) > PEER_TIMEOUT_CYCLES) { *g_peer.host_err = 1; break; }
         }
+        __threadfence_system();
     }
-    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) {
 #pragma unroll
-    for (int k = 0; k < NV; ++k) v[k] = fr_t::zero();
-    for (int g = 0; g < G; ++g) {
-        const fr_t* src = (const fr_t*)(mine + (size_t)g * SC_PEER_SLOT);
+        for (int k = 0; k < NV; ++k) v[k] = fr_t::zero();
+        for (int g = 0; g < G; ++g) {                       // rank order: every rank adds the same values in the same order
+            const fr_t* src = (const fr_t*)(mine + (size_t)g * SC_PEER_SLOT);
 #pragma unroll
-        for (int k = 0; k < NV; ++k) v[k] = v[k] + peer_load(src + k);
+            for (int k = 0; k < NV; ++k) v[k] = v[k] + peer_load(src + k);
+        }
+        g_peer.seq = seq;
     }
-    g_peer.seq = seq;
 }
 
 cudaError_t sc_peer_configure(unsigned char* const* mbox, int nranks, int rank, int* host_err, cudaStream_t s) {
@@ -187,8 +194,11 @@ struct EvalAcc2Claim {
 };
 struct EvalClaimEpilogue {
     fr_t* out4; fr_t claim;
+    __device__ void warp(fr_t (&v)[2], fr_t* smem) const {
+        if (g_peer.on) peer_sum<2>(v, smem);           // sharded: v = sums over all ranks; the host derives g(1) from the GLOBAL claim
+        if ((threadIdx.x & 31) == 0) (*this)(v);
+    }
     __device__ void operator()(fr_t (&v)[2]) const {
-        if (g_peer.on) peer_sum<2>(v);                 // sharded: v = sums over all ranks; the host derives g(1) from the GLOBAL claim
         fr_t g1 = claim - v[0];
         fr_t d = v[1] - g1;
         out4[0] = v[0]; out4[1] = g1; out4[2] = v[1]; out4[3] = v[0] + d + d + d;
@@ -216,8 +226,11 @@ template <> struct EvalAcc<3> {
 template <int D>
 struct EvalEpilogue {
     fr_t* out4;
+    __device__ void warp(fr_t (&v)[EvalAcc<D>::NV], fr_t* smem) const {
+        if (g_peer.on) peer_sum<EvalAcc<D>::NV>(v, smem);   // sharded: sums over all ranks (extrapolation is linear, so it commutes with the sum)
+        if ((threadIdx.x & 31) == 0) (*this)(v);
+    }
     __device__ void operator()(fr_t (&v)[EvalAcc<D>::NV]) const {
-        if (g_peer.on) peer_sum<EvalAcc<D>::NV>(v);    // sharded: sums over all ranks (extrapolation is linear, so it commutes with the sum)
         fr_t o[4];
         EvalAcc<D>::expand(v, o);
         for (int i = 0; i < 4; ++i) out4[i] = o[i];

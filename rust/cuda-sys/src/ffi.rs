@@ -74,6 +74,9 @@ extern "C" {
                              num_lookups: usize, out: *mut *mut Proof) -> c_int;
     pub fn tsgpu_twist_prove_sharded(ctx: *mut Ctx, params: *const Params, addresses: *const u64, values: *const Fr, num_local: usize,
                                      total_operations: usize, out: *mut *mut Proof) -> c_int;
+    pub fn tsgpu_twist_prove_sharded_dev(ctx: *mut Ctx, params: *const Params, local_addresses: *mut Poly, local_values: *mut Poly,
+                                         padded_operations: usize, out: *mut *mut Proof) -> c_int;
+    pub fn tsgpu_comm_peer_exchange(ctx: *const Ctx) -> c_int;     // 1: peer mailboxes over NVLink (round sums inside the round kernel), 0: NCCL collectives
     pub fn tsgpu_shout_prove_sharded(ctx: *mut Ctx, params: *const Params, entries: *const Fr, num_local_entries: usize, total_entries: usize,
                                      lookup_indices: *const u64, num_local_lookups: usize, total_lookups: usize, out: *mut *mut Proof) -> c_int;
     pub fn tsgpu_twist_verify(ctx: *mut Ctx, params: *const Params, proof: *const Proof, valid: *mut c_int) -> c_int;
@@ -103,6 +106,13 @@ extern "C" {
     pub fn tsgpu_twist_memory_check_verify(ctx: *mut Ctx, addresses: *const u64, values: *const Fr, is_write: *const u8, num_operations: usize,
                                            memory_size: usize, transcript: *mut TranscriptH, claims: *const Fr, rounds1: *const Fr, num_rounds1: usize,
                                            final1: *const Fr, rounds2: *const Fr, num_rounds2: usize, final2: *const Fr, valid: *mut c_int) -> c_int;
+    // write-checking (third sum-check of Twist) + the Val-evaluation of the claim it ends in; same transcript, after the memory check
+    pub fn tsgpu_twist_write_check_prove(ctx: *mut Ctx, addresses: *const u64, values: *const Fr, is_write: *const u8, num_operations: usize,
+                                         memory_size: usize, transcript: *mut TranscriptH, claims: *mut Fr, rounds3: *mut Fr, final3: *mut Fr,
+                                         rounds4: *mut Fr, final4: *mut Fr) -> c_int;
+    pub fn tsgpu_twist_write_check_verify(ctx: *mut Ctx, addresses: *const u64, values: *const Fr, is_write: *const u8, num_operations: usize,
+                                          memory_size: usize, transcript: *mut TranscriptH, claims: *const Fr, rounds3: *const Fr, num_rounds3: usize,
+                                          final3: *const Fr, rounds4: *const Fr, num_rounds4: usize, final4: *const Fr, valid: *mut c_int) -> c_int;
 
     // multi-GPU (one process per GPU; the host program carries the 128-byte NCCL id)
     pub fn tsgpu_comm_unique_id(out: *mut u8) -> c_int;

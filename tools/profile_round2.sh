@@ -11,3 +11,6 @@ python tools/ncu_targets.py > gpurun_out/r02_targets.log 2>&1 && timeout 500 ncu
     -k regex:"k_msm_accumulate|k_bind$|k_bind_eval2_claim|k_round_eval|k_msm_span_sums|k_msm_bit_sums|k_msm_scatter|k_msm_digits" -c 10 -f -o gpurun_out/r02_targets \
     python tools/ncu_targets.py > gpurun_out/r02_ncu_targets.log 2>&1
 ls -la gpurun_out | tail -12
+#   4. launch list of the per-rank shape of an 8-way sharded proof (2^17 operations per rank)
+python tools/shape_n8.py 17 3 > gpurun_out/r02_shape_n8.log 2>&1 && timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv \
+    --log-file gpurun_out/r02_launches_shape_n8.csv python tools/shape_n8.py 17 1 > gpurun_out/r02_ncu_shape_n8.log 2>&1
