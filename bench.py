@@ -372,9 +372,9 @@ def main():
         roofline = acc_roofline(dflt, 2 * n)           # the two opening quotients are the full-width scalars of the default path
         roofline["peak_source"] = "tools/ubench.cu on this pool: 18.5 T IMAD.WIDE/s without carry-in (the carry-chained form the multiplier needs issues at half that rate); MEASURED_PEAKS.json has no integer figure"
         roofline["algorithmic_unit"] = "SURVEY 8(d): 16 windows x 11 Fq products x 136 IMAD = 23 936 IMAD per full-width point; `executed` = bucket entries x 1288 multiply-adds"
-        # DRAM bytes per launch from `ncu --set full` of this command (profiles/r01_ncu_accumulate_in_bench.md): commit pass 0.587 + 0.068 GB,
-        # open pass 3.622 + 0.146 GB; mean over the two launches of a proof, like `launch_ms`.  Algorithmic bytes: entries x (64 B point + 4 B entry).
-        roofline["traffic"] = 0.5 * ((0.586715 + 0.067997) + (3.621562 + 0.145975)) * 1e9
+        # DRAM bytes per launch from `ncu --set full` of this command (profiles/r02_ncu_full_summary.md, tools/profile_round2.sh): commit pass 0.493 GB read +
+        # 0.017 GB written, open pass 3.625 + 0.146 GB; mean over the two launches of a proof, like `launch_ms`.  Algorithmic bytes: entries x (64 B point + 4 B entry).
+        roofline["traffic"] = 0.5 * ((0.493 + 0.017) + (3.625 + 0.146)) * 1e9
         roofline["algorithmic_bytes"] = roofline["entries_per_launch"] * 68.0
         line.update({"value": dev_ms, "ms_per_step": dev_ms, "scaling": "weak", "clocks": clocks,
                      "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": int(addr_h.nbytes + vals_h.nbytes), "d2h_bytes_per_step": int(4 * 16 * 96 + 2 * 32),
@@ -455,8 +455,8 @@ def main():
         ctx.set_tuning("kernel_timing", 0)
         gbs = 48.0 * (1 << nv) / (b_ms / b_cnt * 1e-3) / 1e9
         line["roofline_fold"] = {"kernel": "k_bind", "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                                 # DRAM bytes per launch from `ncu --set full` (profiles/r01_ncu_full_summary.md: 0.5369 GB read + 0.2257 GB written at 2^24 entries), scaled to 2^nv
-                                 "traffic": (0.536879 + 0.225681) * 1e9 * (1 << nv) / (1 << 24), "algorithmic_bytes": 48.0 * (1 << nv),
+                                 # DRAM bytes per launch from `ncu --set full` (profiles/r02_ncu_full_summary.md: 0.537 GB read + 0.229 GB written at 2^24 entries), scaled to 2^nv
+                                 "traffic": (0.537 + 0.229) * 1e9 * (1 << nv) / (1 << 24), "algorithmic_bytes": 48.0 * (1 << nv),
                                  "launch_ms": b_ms / b_cnt, "workload": f"one 2^{nv}-entry Fr table (2 GiB), 48 B per output entry", "peak_source": hbm_src}
         del cl, T
 
