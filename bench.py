@@ -534,6 +534,12 @@ def bench_c4(ts, dd, ctx, rank, world, timed, max_over_ranks, hbm_peak, hbm_src,
         out[name] = ms
         del clones, it
     ctx.set_tuning("deferred_claim_check", 0)
+    ctx.set_tuning("sc_tail", 0)                                  # the same proof with one launch + stream synchronisation per round all the way down
+    clones = [[A.clone(), B.clone()] for _ in range(steps + 2)]
+    it = iter(clones)
+    (out["ms_without_persistent_tail"],) = max_over_ranks(timed(lambda: prove(next(it)), steps, 2))
+    ctx.set_tuning("sc_tail", 1)
+    del clones, it
     if world > 1:
         out["exchange"] = "peer mailboxes over NVLink: round sums inside the round kernel, no NCCL call per round" if ctx.comm_peer_exchange else "ncclAllReduce per round"
         if ctx.comm_peer_exchange:                            # the same proof over the NCCL collectives, for comparison

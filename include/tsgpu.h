@@ -64,7 +64,8 @@ uint64_t tsgpu_counter_read(const tsgpu_ctx* ctx, const char* name);
 /* tuning knobs: "prefetch_min_log2" (log2 of the positions per launch from which the d = 2 sum-check rounds use the warp-private TMA prefetch
  * kernels; default 21), "deferred_claim_check" (see tsgpu_sumcheck_prove_product), "peer_exchange" (sharded paths: peer mailboxes over NVLink
  * or NCCL collectives), "eval_basis" (0: Twist / Shout::prove interpolate and commit coefficients), "msm_tables" (0: per-window bucket sets),
- * "kernel_timing" (per-phase CUDA-event timers behind tsgpu_timer_read) */
+ * "sc_tail" (d = 2 claim-form rounds on tables of at most 2^11 entries run in ONE persistent kernel that exchanges round values and challenges with the
+ * host through a mapped mailbox; default 1), "kernel_timing" (per-phase CUDA-event timers behind tsgpu_timer_read) */
 int tsgpu_set_tuning(tsgpu_ctx* ctx, const char* key, long value);
 /* with tuning key "kernel_timing" = 1 the library brackets its main kernels with CUDA events on the context
  * stream; names: "msm_accumulate", "msm_total", "interpolate", "open_scan", "sc_round_eval", "sc_bind_eval", "bind" */

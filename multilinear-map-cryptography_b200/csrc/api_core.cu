@@ -108,6 +108,7 @@ int tsgpu_init(int device, void* stream, tsgpu_ctx** out) {
               cudaMalloc((void**)&ctx->dev_out, 8 * sizeof(fr_t)) == cudaSuccess &&
               cudaMallocHost((void**)&ctx->host_out, 8 * sizeof(fr_t)) == cudaSuccess &&
               cudaMallocHost((void**)&ctx->host_scratch, 64 * sizeof(fr_t)) == cudaSuccess &&
+              cudaHostAlloc((void**)&ctx->tail_box, sizeof(ScTailBox), cudaHostAllocMapped) == cudaSuccess &&
               cudaMemset(ctx->ticket, 0, 64) == cudaSuccess;
     if (!ok) { cudaGetLastError(); tsgpu_destroy(ctx); return TSGPU_E_PROOF_GENERATION; }
     *out = ctx;
@@ -126,6 +127,7 @@ void tsgpu_destroy(tsgpu_ctx* ctx) {
     if (ctx->dev_out) cudaFree(ctx->dev_out);
     if (ctx->host_out) cudaFreeHost(ctx->host_out);
     if (ctx->host_scratch) cudaFreeHost(ctx->host_scratch);
+    if (ctx->tail_box) cudaFreeHost(ctx->tail_box);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -169,6 +171,7 @@ int tsgpu_set_tuning(tsgpu_ctx* ctx, const char* key, long value) {
         set_prefetch_min_work(value < 0 || value > 61 ? (size_t)1 << 62 : (size_t)1 << value);
         return TSGPU_OK;
     }
+    if (!strcmp(key, "sc_tail")) { ctx->sc_tail = value != 0; return TSGPU_OK; }
     if (!strcmp(key, "peer_exchange")) { ctx->peer_exchange = value != 0; return TSGPU_OK; }
     if (!strcmp(key, "deferred_claim_check")) { ctx->deferred_claim_check = value != 0; return TSGPU_OK; }
     if (!strcmp(key, "kernel_timing")) { ctx->timing = value != 0; return TSGPU_OK; }
@@ -642,9 +645,46 @@ static ScTables sc_tabs(const tsgpu_sc* sc) {
     return t;
 }
 
+// ---- persistent tail (sumcheck.cu): entered by tsgpu_sc_bind_eval_claim once the tables fit one CTA's shared memory; every other entry point first
+// makes the resident kernel write the tables back (sc_tail_leave), so callers may mix the calls freely
+static int sc_tail_fail(tsgpu_sc* sc) {
+    sc_tail_post_command(sc->ctx->tail_box, SC_TAIL_ABORT);
+    cudaStreamSynchronize(sc->ctx->stream);
+    sc->tail_active = false;
+    return fail(sc->ctx, TSGPU_E_PROOF_GENERATION, "sum-check tail kernel did not answer");
+}
+static int sc_tail_leave(tsgpu_sc* sc) {
+    if (!sc->tail_active) return TSGPU_OK;
+    sc_tail_post_command(sc->ctx->tail_box, SC_TAIL_FLUSH);
+    sc->tail_active = false;
+    TSG_CUDA(sc->ctx, cudaStreamSynchronize(sc->ctx->stream));
+    return TSGPU_OK;
+}
+// one step of the tail: fold with r, return g(0), g(2) of the next round (or, with no variable left after the fold, the two bound table values)
+static int sc_tail_step(tsgpu_sc* sc, const fr_t& r, fr_t v[2]) {
+    tsgpu_ctx* ctx = sc->ctx;
+    if (!sc->tail_active) {
+        TSG_CUDA(ctx, launch_sc_tail(sc->tables[0]->d, sc->tables[1]->d, (size_t)1 << sc->vars_left, r, ctx->tail_box, ctx->stream));
+        ctx->launches += 1;
+        sc->tail_active = true; sc->tail_seq = 0;
+    } else {
+        sc_tail_post_challenge(ctx->tail_box, r, sc->tail_seq);
+    }
+    sc->tail_seq += 1;
+    if (!sc_tail_wait(ctx->tail_box, sc->tail_seq, ctx->stream, v)) return sc_tail_fail(sc);
+    for (int i = 0; i < sc->d; ++i) sc->tables[i]->num_vars -= 1;
+    sc->vars_left -= 1;
+    if (sc->vars_left == 0) {                     // the kernel has written the bound values to the tables and is leaving
+        sc->tail_active = false;
+        TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return TSGPU_OK;
+}
+
 int tsgpu_sc_round_eval(tsgpu_sc* sc, tsgpu_fr evals[4]) {
     if (!sc || !evals) return TSGPU_E_INVALID_PARAMETERS;
     tsgpu_ctx* ctx = sc->ctx;
+    if (int lrc = sc_tail_leave(sc)) return lrc;
     if (sc->vars_left == 0) return fail(ctx, TSGPU_E_SUMCHECK, "no variables left to evaluate");
     KernelTimer kt(ctx, "sc_round_eval");
     // the finishing block writes the four values straight into the pinned host mirror (unified addressing: no D2H copy to enqueue per round)
@@ -659,6 +699,7 @@ int tsgpu_sc_round_eval_claim(tsgpu_sc* sc, const tsgpu_fr* claim, tsgpu_fr eval
     if (!sc || !evals || !claim) return TSGPU_E_INVALID_PARAMETERS;
     tsgpu_ctx* ctx = sc->ctx;
     if (sc->vars_left == 0) return fail(ctx, TSGPU_E_SUMCHECK, "no variables left to evaluate");
+    if (int lrc = sc_tail_leave(sc)) return lrc;
     KernelTimer kt(ctx, "sc_round_eval");
     const fr_t cl = to_fr(claim);
     TSG_CUDA(ctx, launch_round_eval(sc->d, sc_tabs(sc), (size_t)1 << sc->vars_left, ctx->partials, ctx->ticket, ctx->host_out, ctx->sm_count, ctx->stream,
@@ -671,6 +712,8 @@ int tsgpu_sc_bind(tsgpu_sc* sc, const tsgpu_fr* r) {
     if (!sc || !r) return TSGPU_E_INVALID_PARAMETERS;
     tsgpu_ctx* ctx = sc->ctx;
     if (sc->vars_left == 0) return fail(ctx, TSGPU_E_SUMCHECK, "no variables left to bind");
+    if (sc->tail_active && sc->vars_left == 1) { fr_t fin[2]; return sc_tail_step(sc, to_fr(r), fin); }   // last fold inside the resident kernel
+    if (int lrc = sc_tail_leave(sc)) return lrc;
     for (int i = 0; i < sc->d; ++i) {
         TSG_CUDA(ctx, launch_bind(sc->tables[i]->d, (size_t)1 << sc->vars_left, to_fr(r), ctx->sm_count, ctx->stream));
         ctx->launches += 1;
@@ -684,6 +727,17 @@ static int sc_bind_eval_impl(tsgpu_sc* sc, const tsgpu_fr* r, const tsgpu_fr* cl
     if (!sc || !r || !evals) return TSGPU_E_INVALID_PARAMETERS;
     tsgpu_ctx* ctx = sc->ctx;
     if (sc->vars_left < 2) return fail(ctx, TSGPU_E_SUMCHECK, "bind_eval needs at least two unbound variables");
+    if (claim && sc->d == 2 && ctx->sc_tail && ctx->tail_box && (sc->tail_active || sc->vars_left - 1 <= SC_TAIL_MAX_LOG)) {
+        fr_t v[2];
+        int trc = sc_tail_step(sc, to_fr(r), v);
+        if (trc) return trc;
+        // the four values from g(0), g(2) and the claim, as the per-round kernel's epilogue computes them
+        const fr_t g1 = to_fr(claim) - v[0], dd = v[1] - g1;
+        const fr_t ev[4] = {v[0], g1, v[1], v[0] + dd + dd + dd};
+        memcpy(evals, ev, sizeof(ev));
+        return TSGPU_OK;
+    }
+    if (int lrc = sc_tail_leave(sc)) return lrc;
     KernelTimer kt(ctx, "sc_bind_eval");
     fr_t cl; if (claim) cl = to_fr(claim);
     TSG_CUDA(ctx, launch_bind_eval(sc->d, sc_tabs(sc), (size_t)1 << sc->vars_left, to_fr(r), claim ? &cl : nullptr, ctx->partials, ctx->ticket, ctx->host_out,
@@ -706,11 +760,18 @@ int tsgpu_sc_final(tsgpu_sc* sc, tsgpu_fr* finals) {
     if (!sc || !finals) return TSGPU_E_INVALID_PARAMETERS;
     tsgpu_ctx* ctx = sc->ctx;
     if (sc->vars_left != 0) return fail(ctx, TSGPU_E_SUMCHECK, "variables remain unbound");
+    if (int lrc = sc_tail_leave(sc)) return lrc;
     for (int i = 0; i < sc->d; ++i)
         TSG_CUDA(ctx, cudaMemcpyAsync(ctx->dev_out + i, sc->tables[i]->d, sizeof(fr_t), cudaMemcpyDeviceToDevice, ctx->stream));
     return read_result(ctx, sc->d, finals);
 }
 
-void tsgpu_sc_end(tsgpu_sc* sc) { delete sc; }
+void tsgpu_sc_end(tsgpu_sc* sc) {
+    if (sc && sc->tail_active) {                  // abandoned mid-protocol (an error path of the caller): the resident kernel must not outlive the handle
+        sc_tail_post_command(sc->ctx->tail_box, SC_TAIL_ABORT);
+        cudaStreamSynchronize(sc->ctx->stream);
+    }
+    delete sc;
+}
 
 }  // extern "C"

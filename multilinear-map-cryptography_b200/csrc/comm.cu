@@ -348,10 +348,43 @@ int tsgpu_sumcheck_prove_product_sharded(tsgpu_ctx* ctx, tsgpu_table* const* tab
             ev[3] = ev[0] + dd + dd + dd;
         }
     }
+    // persistent tail (sumcheck.cu): d = 2 rounds on slices that fit one CTA's shared memory run inside ONE resident kernel, which also sums the round values
+    // with the peers; the host feeds it the challenges through the mapped mailbox.  Needs the in-kernel exchange (or a single rank).
+    const bool tail_ok = d == 2 && ctx->sc_tail && ctx->tail_box && (p2p || G == 1);
+    bool tail_active = false; unsigned tail_seq = 0;
+    struct TailGuard {          // an error return must not leave the resident kernel behind
+        tsgpu_ctx* ctx; bool* active;
+        ~TailGuard() { if (*active) { sc_tail_post_command(ctx->tail_box, SC_TAIL_ABORT); cudaStreamSynchronize(ctx->stream); } }
+    } tail_guard{ctx, &tail_active};
+    auto tail_step = [&](const fr_t& r, size_t n, fr_t v[2]) -> int {
+        if (!tail_active) {
+            TSG_CUDA(ctx, launch_sc_tail(tables[0]->d, tables[1]->d, n, r, ctx->tail_box, ctx->stream));
+            ctx->launches += 1;
+            tail_active = true; tail_seq = 0;
+        } else sc_tail_post_challenge(ctx->tail_box, r, tail_seq);
+        tail_seq += 1;
+        if (!sc_tail_wait(ctx->tail_box, tail_seq, ctx->stream, v)) return fail(ctx, TSGPU_E_PROOF_GENERATION, "sum-check tail kernel did not answer");
+        return p2p ? peer_timeout(ctx, c) : TSGPU_OK;
+    };
     for (unsigned round = 0; round < n_local; ++round) {
         fr_t r;
         if ((rc = absorb(round, ev, &r))) return rc;
         const size_t n = (size_t)1 << (n_local - round);
+        if (tail_ok && (tail_active || (n >= 4 && n / 2 <= ((size_t)1 << SC_TAIL_MAX_LOG)))) {
+            fr_t v[2];
+            if ((rc = tail_step(r, n, v))) return rc;
+            if (round + 1 < n_local) {          // v = GLOBAL g(0), g(2) of the next round; g(1) from the global claim
+                ev[0] = v[0]; ev[2] = v[1];
+                ev[1] = current - ev[0];
+                fr_t dd = ev[2] - ev[1];
+                ev[3] = ev[0] + dd + dd + dd;
+            } else {                            // last local fold done: the kernel has written the bound values to the tables and leaves
+                tail_active = false;
+                TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            }
+            for (int t = 0; t < d; ++t) tables[t]->num_vars -= 1;
+            continue;
+        }
         if (round + 1 < n_local) {
             // d = 2: the kernel sums g(0) and g(2) only (claim form with claim 0 leaves g(1) slot = -g(0), unused); g(1) follows from
             // the GLOBAL claim after the all-reduce: g(1) = current - g(0), g(3) = g(0) - 3 g(1) + 3 g(2)

@@ -23,6 +23,8 @@ struct tsgpu_ctx {
     tsg::fr_t* dev_out = nullptr;      // 8 elements
     tsg::fr_t* host_out = nullptr;     // pinned, 8 elements
     tsg::fr_t* host_scratch = nullptr; // pinned, 64 elements (host leg of the batch inversion, lagrange.cu)
+    tsg::ScTailBox* tail_box = nullptr; // pinned + mapped mailbox of the persistent sum-check tail (sumcheck.cu)
+    bool sc_tail = true;               // d = 2 claim-form rounds on tables that fit one CTA's shared memory run in ONE persistent kernel (tuning "sc_tail")
     void* comm = nullptr;              // multi-GPU communicator (comm.cu), optional
     void* interp = nullptr;            // cached interpolation plan (interp.cu)
     // optional per-kernel device timing (CUDA events on `stream`), enabled by tsgpu_set_tuning("kernel_timing", 1)
@@ -57,6 +59,8 @@ struct tsgpu_sc {
     int d = 0;
     unsigned vars_left = 0;
     tsgpu_table* tables[tsg::SC_MAX_TABLES] = {nullptr, nullptr, nullptr};
+    bool tail_active = false;          // the persistent tail kernel is resident and owns the tables
+    unsigned tail_seq = 0;             // results consumed from it so far
 };
 
 namespace tsg {

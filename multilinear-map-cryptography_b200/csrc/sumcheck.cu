@@ -17,6 +17,8 @@
 #include "sumcheck.cuh"
 #include "tma_stream.cuh"
 #include "../host/field64.hpp"
+#include <atomic>
+#include <chrono>
 #include <cstring>
 
 namespace tsg {
@@ -462,6 +464,83 @@ __global__ void __launch_bounds__(SC_THREADS, 2) k_round_eval2_claim_pf(ScTables
     acc.finish(v);
     grid_finish_sum<fr_t, 2>(v, partials, ticket, smem, EvalClaimEpilogue{out4, claim});
 }
+// ---------------------------------------------------------------- persistent tail (d = 2, claim form)
+// One CTA, tables in shared memory.  Per round: g(0) and g(2) over the pairs (p, p + m / 2) -> block reduction -> (sharded: summed with the peers
+// by warp 0, as in the large-table kernels) -> published to the host mailbox; thread 0 then polls the mailbox for the next challenge's constant
+// table, everybody folds in place, and so on until one entry per table is left; those two values go to the mailbox and to A[0], B[0].
+constexpr int SC_TAIL_THREADS = 1024;
+constexpr unsigned long long TAIL_HOST_TIMEOUT_CYCLES = 40000000000ull;   // ~20 s at 2 GHz: the host may be slow between two calls of a round-stepped caller, but a dead host must not pin the GPU
+__global__ void __launch_bounds__(SC_TAIL_THREADS, 1) k_sc_tail2(fr_t* A, fr_t* B, size_t n, const fr_ctab r0, ScTailBox* box) {
+    extern __shared__ __align__(32) unsigned char tail_smem[];
+    __shared__ fr_t red[2 * 32];
+    __shared__ fr_ctab rc;
+    __shared__ unsigned s_state;
+    size_t m = n / 2;
+    fr_t* sa = (fr_t*)tail_smem; fr_t* sb = sa + m;
+    for (size_t p = threadIdx.x; p < m; p += blockDim.x) {          // first fold straight from HBM
+        const fr_t a0 = ld256(A + p), a1 = ld256(A + p + m), b0 = ld256(B + p), b1 = ld256(B + p + m);
+        sa[p] = a0 + r0.mul(a1 - a0); sb[p] = b0 + r0.mul(b1 - b0);
+    }
+    __syncthreads();
+    unsigned seq = 0;
+    while (m >= 2) {
+        const size_t h = m / 2;
+        EvalAcc2Claim acc; acc.clear();
+        for (size_t p = threadIdx.x; p < h; p += blockDim.x) {
+            const fr_t lo[2] = {sa[p], sb[p]}, hi[2] = {sa[p + h], sb[p + h]};
+            acc.pair(lo, hi);
+        }
+        fr_t v[2];
+        acc.finish(v);
+        block_reduce_sum<fr_t, 2>(v, red);
+        if (threadIdx.x < 32) {
+            if (g_peer.on) peer_sum<2>(v, red);
+            if (threadIdx.x == 0) {
+                ++seq;
+                volatile unsigned long long* o = box->out;
+#pragma unroll
+                for (int k = 0; k < 2; ++k)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) o[4 * k + i] = (unsigned long long)v[k].l[2 * i] | ((unsigned long long)v[k].l[2 * i + 1] << 32);
+                __threadfence_system();
+                box->out_seq = seq;
+                const long long t0 = clock64();
+                unsigned st;
+                while ((st = box->in_seq) != seq && st < SC_TAIL_FLUSH) {
+                    if ((unsigned long long)(clock64() - t0) > TAIL_HOST_TIMEOUT_CYCLES) { box->err = 1; st = SC_TAIL_ABORT; break; }
+                }
+                __threadfence_system();
+                s_state = st;
+            }
+        }
+        __syncthreads();
+        if (s_state == SC_TAIL_ABORT) return;
+        if (s_state == SC_TAIL_FLUSH) {                              // hand the tables back as they stand (m entries each)
+            for (size_t p = threadIdx.x; p < m; p += blockDim.x) { st256(A + p, sa[p]); st256(B + p, sb[p]); }
+            return;
+        }
+        if (threadIdx.x < 64) ((uint32_t*)rc.t)[threadIdx.x] = ((volatile uint32_t*)box->ctab)[threadIdx.x];
+        __syncthreads();
+        for (size_t p = threadIdx.x; p < h; p += blockDim.x) {
+            const fr_t a0 = sa[p], a1 = sa[p + h], b0 = sb[p], b1 = sb[p + h];
+            sa[p] = a0 + rc.mul(a1 - a0); sb[p] = b0 + rc.mul(b1 - b0);
+        }
+        __syncthreads();
+        m = h;
+    }
+    if (threadIdx.x == 0) {
+        st256(A, sa[0]); st256(B, sb[0]);
+        volatile unsigned long long* o = box->out;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            o[i] = (unsigned long long)sa[0].l[2 * i] | ((unsigned long long)sa[0].l[2 * i + 1] << 32);
+            o[4 + i] = (unsigned long long)sb[0].l[2 * i] | ((unsigned long long)sb[0].l[2 * i + 1] << 32);
+        }
+        __threadfence_system();
+        box->out_seq = seq + 1;
+    }
+}
+
 // positions per launch from which the prefetch variants run (tuning "prefetch_min_log2").  Measured on B200 (tools/bench_fold.py): +5.7% on the fused
 // kernel and +3% on the evaluation kernel at 2^26 entries, +3-5% down to 2^22, neutral below (the tables then sit in the 126 MB L2).
 static size_t g_pf_min_work = (size_t)1 << 21;
@@ -485,6 +564,42 @@ static fr_ctab make_ctab_host(const fr_t& r_elem) {
         cur = cur * w;
     }
     return c;
+}
+
+// ---------------------------------------------------------------- persistent tail: host side
+cudaError_t launch_sc_tail(fr_t* A, fr_t* B, size_t n, const fr_t& r_elem, ScTailBox* box, cudaStream_t s) {
+    if (n < 4 || (n / 2) > ((size_t)1 << SC_TAIL_MAX_LOG)) return cudaErrorInvalidValue;
+    const size_t sm = n * sizeof(fr_t);                     // two tables of n / 2 entries
+    cudaError_t e = enable_smem(k_sc_tail2, sm);
+    if (e) return e;
+    box->out_seq = 0; box->in_seq = 0; box->err = 0;
+    std::atomic_thread_fence(std::memory_order_seq_cst);
+    k_sc_tail2<<<1, SC_TAIL_THREADS, sm, s>>>(A, B, n, make_ctab_host(r_elem), box);
+    return cudaGetLastError();
+}
+void sc_tail_post_challenge(ScTailBox* box, const fr_t& r_elem, unsigned seq) {
+    const fr_ctab c = make_ctab_host(r_elem);
+    memcpy(box->ctab, c.t, sizeof(c.t));
+    std::atomic_thread_fence(std::memory_order_seq_cst);    // the table is in memory before the sequence number the kernel polls
+    box->in_seq = seq;
+}
+void sc_tail_post_command(ScTailBox* box, unsigned command) {
+    std::atomic_thread_fence(std::memory_order_seq_cst);
+    box->in_seq = command;
+}
+bool sc_tail_wait(ScTailBox* box, unsigned seq, cudaStream_t s, fr_t out[2]) {
+    const auto t0 = std::chrono::steady_clock::now();
+    unsigned spins = 0;
+    while (box->out_seq != seq) {
+        if (box->err) return false;
+        if ((++spins & 0x3fff) == 0) {
+            if (cudaStreamQuery(s) != cudaErrorNotReady) { if (box->out_seq == seq) break; return false; }   // the kernel is gone without publishing: it failed
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(10)) return false;
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_seq_cst);
+    memcpy(out, (const void*)box->out, 2 * sizeof(fr_t));
+    return true;
 }
 
 // ---------------------------------------------------------------- launch helpers

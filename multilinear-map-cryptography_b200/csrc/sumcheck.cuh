@@ -22,6 +22,26 @@ cudaError_t sc_peer_configure(unsigned char* const* mbox, int nranks, int rank, 
 cudaError_t sc_peer_enable(bool on, cudaStream_t s);     // stream-ordered switch: the round kernels launched after it exchange their sums with the peers
 cudaError_t launch_peer_allgather(const void* in, size_t bytes, void* out, cudaStream_t s);
 
+// ---- persistent tail of the d = 2 sum-check (sumcheck.cu "persistent tail"): once the two tables fit one CTA's shared memory (<= SC_TAIL_MAX
+// entries each after the next fold) ONE resident kernel runs all remaining rounds; it hands the round values to the host and takes the next
+// challenge through a mailbox in mapped pinned memory, so a round costs a PCIe round trip instead of a launch + stream synchronisation.
+constexpr unsigned SC_TAIL_MAX_LOG = 11;                 // 2 tables x 2^11 entries x 32 B = 128 KiB of shared memory
+constexpr unsigned SC_TAIL_ABORT = 0xffffffffu;           // leave at once (the tables are abandoned)
+constexpr unsigned SC_TAIL_FLUSH = 0xfffffffeu;           // write the current tables back to HBM and leave (the caller goes on with the per-round kernels)
+struct ScTailBox {                                       // pinned + mapped; 64-byte separated fields
+    volatile unsigned out_seq; unsigned pad0[15];        // GPU -> host: number of results published so far
+    unsigned long long out[16];                          // GPU -> host: g(0), g(2) of the round (raw sums), or the two fully bound table values
+    volatile unsigned in_seq; unsigned pad1[15];         // host -> GPU: number of challenges provided so far (SC_TAIL_ABORT: leave)
+    uint32_t ctab[64];                                   // host -> GPU: constant-multiplier table of the challenge (fr_ctab)
+    volatile unsigned err; unsigned pad2[15];            // GPU -> host: 1 = timed out waiting for the host
+};
+// launches the tail on tables A, B of n entries (n / 2 <= 2^SC_TAIL_MAX_LOG, n >= 4): folds with r, evaluates the next round and publishes it (out_seq = 1)
+cudaError_t launch_sc_tail(fr_t* A, fr_t* B, size_t n, const fr_t& r, ScTailBox* box, cudaStream_t s);
+void sc_tail_post_challenge(ScTailBox* box, const fr_t& r, unsigned seq);            // host: next challenge (seq = 1, 2, ...)
+void sc_tail_post_command(ScTailBox* box, unsigned command);                         // SC_TAIL_ABORT / SC_TAIL_FLUSH
+// host: spin until out_seq == seq (false: time-out, kernel error or GPU-side time-out); values -> out[2]
+bool sc_tail_wait(ScTailBox* box, unsigned seq, cudaStream_t s, fr_t out[2]);
+
 // number of blocks the evaluation kernels may launch (sizes the partial-sum scratch)
 inline int sc_max_grid(int sm_count) { return sm_count * SC_BLOCKS_PER_SM_BIND; }
 

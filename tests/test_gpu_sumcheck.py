@@ -242,3 +242,60 @@ def test_bind_eval_with_claim_returns_the_same_four_values(ctx, oracle, nv):
         ev = full.bind_eval(rs[k:k + 1])
         got = fast.bind_eval(rs[k:k + 1], claim=claim)
         assert (got == ev).all(), (nv, k)
+
+
+def _claim_of(oracle, coeffs, r):
+    """g(r) by Horner on the oracle's field: the claim of the next round"""
+    return oracle.horner(coeffs, r)
+
+
+@pytest.mark.parametrize("nv", [2, 3, 7, 11, 12, 14])
+def test_persistent_tail_rounds_match_oracle_and_the_per_round_kernels(ctx, tsgpu, oracle, nv):
+    """d = 2: once the tables fit one CTA's shared memory (<= 2^11 entries each after the fold) ONE resident kernel runs the remaining rounds and
+    talks to the host through a mapped mailbox (tuning "sc_tail", default on).  Same proof with the tail on and off, equal to the oracle's;
+    and a caller that mixes the claim form with plain bind / round_eval / bind_eval calls (which make the kernel hand the tables back)
+    gets the same values as the per-round kernels."""
+    tables = [oracle.chacha_fr_rand(seed_bytes(120 + t + nv), 1 << nv) for t in range(2)]
+    ai, bi = oracle.fr_to_ints(tables[0]), oracle.fr_to_ints(tables[1])
+    claimed = oracle.fr_from_ints([sum(x * y for x, y in zip(ai, bi)) % oracle.R_MOD])[0]
+    ref = oracle.sumcheck_prove_product(tables, claimed, mode="tables")
+    launches = {}
+    try:
+        for flag in (1, 0):
+            ctx.set_tuning("sc_tail", flag)
+            l0 = ctx.launch_count
+            proof, chals, finals = tsgpu.SumCheck(nv, claimed).prove_product(ctx, [ctx.table_upload(t) for t in tables], tsgpu.Transcript(), return_aux=True)
+            launches[flag] = ctx.launch_count - l0
+            assert (proof.round_polynomials == ref["round_polynomials"]).all() and (proof.final_evaluation == ref["final_evaluation"]).all()
+            assert (chals == ref["challenges"]).all() and (finals == ref["finals"]).all()
+        if nv >= 3:
+            assert launches[1] < launches[0]                     # the tail replaces one launch per round by one launch in all
+        # round-stepped drive mixing the entry points: claim form for two rounds, then a plain bind + round_eval, then bind_eval without a claim
+        ctx.set_tuning("sc_tail", 1)
+        sc = ctx.sumcheck([ctx.table_upload(t) for t in tables])
+        xs = oracle.fr_from_ints([0, 1, 2, 3])
+        ev = sc.round_eval()
+        for rnd in range(nv):
+            coeffs = oracle.lagrange_interpolate(xs, ev)
+            assert (coeffs == ref["round_polynomials"][rnd]).all(), rnd
+            r = ref["challenges"][rnd]
+            if rnd + 1 == nv:
+                sc.bind(r)
+            elif rnd % 3 == 2:
+                sc.bind(r); ev = sc.round_eval()
+            elif rnd % 3 == 1 and rnd > 2:
+                ev = sc.bind_eval(r)
+            else:
+                ev = sc.bind_eval(r, claim=_claim_of(oracle, coeffs, r))
+        assert (sc.final() == ref["finals"]).all()
+        sc.end()
+        # a handle abandoned while the kernel is resident (error path of a caller): end() must release the GPU
+        if nv >= 3:
+            sc = ctx.sumcheck([ctx.table_upload(t) for t in tables])
+            ev = sc.round_eval()
+            coeffs = oracle.lagrange_interpolate(xs, ev)
+            sc.bind_eval(ref["challenges"][0], claim=_claim_of(oracle, coeffs, ref["challenges"][0]))
+            sc.end()
+            assert (ctx.mle_evaluate(tables[0], ref["challenges"]) == oracle.mle_evaluate(tables[0], ref["challenges"], fold=True)).all()   # the stream is free again
+    finally:
+        ctx.set_tuning("sc_tail", 1)
