@@ -132,6 +132,11 @@ int tsgpu_table_bind(tsgpu_ctx* ctx, tsgpu_table* t, const tsgpu_fr* r);
  * The tables are consumed (folded in place). */
 int tsgpu_sc_begin(tsgpu_ctx* ctx, tsgpu_table* const* tables, int d, tsgpu_sc** out);
 unsigned tsgpu_sc_num_vars(const tsgpu_sc* sc);   /* variables still unbound */
+/* on = 1: the caller promises to enqueue nothing else on this context until the rounds of `sc` end (tsgpu_sc_final / tsgpu_sc_end).  The d = 2 claim-form
+ * rounds on tables of at most 2^11 entries then run inside ONE persistent kernel that stays resident between the calls and trades round values for challenges
+ * through a mapped mailbox (a round costs a PCIe round trip instead of a launch + stream synchronisation); any other tsgpu_sc_* call makes it hand the tables
+ * back first.  The library's own SumCheck::prove loops set it; default off: interleaving several handles on one context stays legal. */
+int tsgpu_sc_exclusive(tsgpu_sc* sc, int on);
 /* g(0), g(1), g(2), g(3) of the current round (sumcheck.rs:175-198) */
 int tsgpu_sc_round_eval(tsgpu_sc* sc, tsgpu_fr evals[4]);
 /* the same four values for d = 2 when g(0) + g(1) = claim is vouched for by the caller, who then owes the check of the claim itself (the library's

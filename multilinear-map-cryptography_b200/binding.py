@@ -425,6 +425,10 @@ class SumCheckRounds:
         r = _fr(r, 1)
         self.ctx.check(lib().tsgpu_sc_bind(self._h, _p(r)))
 
+    def exclusive(self, on: bool = True):
+        """promise (on) that nothing else is enqueued on the context until these rounds end: lets the small d = 2 claim-form rounds run in the persistent tail kernel"""
+        self.ctx.check(lib().tsgpu_sc_exclusive(self._h, C.c_int(1 if on else 0)))
+
     def bind_eval(self, r, claim=None) -> np.ndarray:
         """fused bind(r) + evaluation of the next round; with `claim` (= g(r) of the round just bound) g(1) is derived as claim - g(0)"""
         r = _fr(r, 1)

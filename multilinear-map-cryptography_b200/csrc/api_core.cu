@@ -623,6 +623,7 @@ int tsgpu_mle_partial_evaluate(tsgpu_ctx* ctx, const tsgpu_fr* evals, unsigned n
 }
 
 // ------------------------------------------------------------------------------------- sum-check
+static int sc_tail_leave(tsgpu_sc* sc);
 int tsgpu_sc_begin(tsgpu_ctx* ctx, tsgpu_table* const* tables, int d, tsgpu_sc** out) {
     if (!ctx || !tables || !out) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
     if (d < 1 || d > SC_MAX_TABLES) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "sum-check supports products of 1..3 tables");
@@ -639,6 +640,12 @@ int tsgpu_sc_begin(tsgpu_ctx* ctx, tsgpu_table* const* tables, int d, tsgpu_sc**
 }
 
 unsigned tsgpu_sc_num_vars(const tsgpu_sc* sc) { return sc ? sc->vars_left : 0; }
+int tsgpu_sc_exclusive(tsgpu_sc* sc, int on) {
+    if (!sc) return TSGPU_E_INVALID_PARAMETERS;
+    if (!on) { int rc = sc_tail_leave(sc); if (rc) return rc; }
+    sc->exclusive = on != 0;
+    return TSGPU_OK;
+}
 
 static ScTables sc_tabs(const tsgpu_sc* sc) {
     ScTables t; for (int i = 0; i < SC_MAX_TABLES; ++i) t.t[i] = i < sc->d ? sc->tables[i]->d : nullptr;
@@ -727,7 +734,7 @@ static int sc_bind_eval_impl(tsgpu_sc* sc, const tsgpu_fr* r, const tsgpu_fr* cl
     if (!sc || !r || !evals) return TSGPU_E_INVALID_PARAMETERS;
     tsgpu_ctx* ctx = sc->ctx;
     if (sc->vars_left < 2) return fail(ctx, TSGPU_E_SUMCHECK, "bind_eval needs at least two unbound variables");
-    if (claim && sc->d == 2 && ctx->sc_tail && ctx->tail_box && (sc->tail_active || sc->vars_left - 1 <= SC_TAIL_MAX_LOG)) {
+    if (claim && sc->d == 2 && sc->exclusive && ctx->sc_tail && ctx->tail_box && (sc->tail_active || sc->vars_left - 1 <= SC_TAIL_MAX_LOG)) {
         fr_t v[2];
         int trc = sc_tail_step(sc, to_fr(r), v);
         if (trc) return trc;

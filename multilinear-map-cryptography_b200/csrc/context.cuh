@@ -59,6 +59,7 @@ struct tsgpu_sc {
     int d = 0;
     unsigned vars_left = 0;
     tsgpu_table* tables[tsg::SC_MAX_TABLES] = {nullptr, nullptr, nullptr};
+    bool exclusive = false;            // the caller enqueues nothing else on the context until the rounds end (tsgpu_sc_exclusive): the tail kernel may stay resident
     bool tail_active = false;          // the persistent tail kernel is resident and owns the tables
     unsigned tail_seq = 0;             // results consumed from it so far
 };

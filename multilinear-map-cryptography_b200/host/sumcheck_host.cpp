@@ -36,6 +36,7 @@ int sumcheck_prove_product(tsgpu_ctx* ctx, tsgpu_table* const* tables, int d, co
     int rc = tsgpu_sc_begin(ctx, tables, d, &sc);
     if (rc) { err = tsgpu_last_error(ctx); return rc; }
     const unsigned num_vars = tsgpu_sc_num_vars(sc);
+    tsgpu_sc_exclusive(sc, 1);             // this loop owns the context until tsgpu_sc_end: the small rounds may run in the resident tail kernel
     proof.round_polynomials.clear();
     if (challenges) challenges->clear();
     fr_t current = claimed_sum;

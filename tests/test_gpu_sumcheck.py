@@ -273,6 +273,7 @@ def test_persistent_tail_rounds_match_oracle_and_the_per_round_kernels(ctx, tsgp
         # round-stepped drive mixing the entry points: claim form for two rounds, then a plain bind + round_eval, then bind_eval without a claim
         ctx.set_tuning("sc_tail", 1)
         sc = ctx.sumcheck([ctx.table_upload(t) for t in tables])
+        sc.exclusive(True)
         xs = oracle.fr_from_ints([0, 1, 2, 3])
         ev = sc.round_eval()
         for rnd in range(nv):
@@ -292,6 +293,7 @@ def test_persistent_tail_rounds_match_oracle_and_the_per_round_kernels(ctx, tsgp
         # a handle abandoned while the kernel is resident (error path of a caller): end() must release the GPU
         if nv >= 3:
             sc = ctx.sumcheck([ctx.table_upload(t) for t in tables])
+            sc.exclusive(True)
             ev = sc.round_eval()
             coeffs = oracle.lagrange_interpolate(xs, ev)
             sc.bind_eval(ref["challenges"][0], claim=_claim_of(oracle, coeffs, ref["challenges"][0]))
