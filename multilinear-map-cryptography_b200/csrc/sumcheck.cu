@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(SC_THREADS, 2) k_round_eval2_claim_pf(ScTables
 // One CTA, tables in shared memory.  Per round: g(0) and g(2) over the pairs (p, p + m / 2) -> block reduction -> (sharded: summed with the peers
 // by warp 0, as in the large-table kernels) -> published to the host mailbox; thread 0 then polls the mailbox for the next challenge's constant
 // table, everybody folds in place, and so on until one entry per table is left; those two values go to the mailbox and to A[0], B[0].
-constexpr int SC_TAIL_THREADS = 256;    // 255 registers per thread available: the two lazy accumulators stay in registers
+constexpr int SC_TAIL_THREADS = 512;    // 128 registers per thread: the two lazy accumulators stay in registers (122 used)
 constexpr unsigned long long TAIL_HOST_TIMEOUT_CYCLES = 40000000000ull;   // ~20 s at 2 GHz: the host may be slow between two calls of a round-stepped caller, but a dead host must not pin the GPU
 __global__ void __launch_bounds__(SC_TAIL_THREADS, 1) k_sc_tail2(fr_t* A, fr_t* B, size_t n, const fr_ctab r0, ScTailBox* box) {
     extern __shared__ __align__(32) unsigned char tail_smem[];

@@ -43,6 +43,7 @@ extern "C" {
     // sum-check rounds, the transcript stays with the caller (src/sumcheck.rs:56-110,156-207)
     pub fn tsgpu_sc_begin(ctx: *mut Ctx, tables: *const *mut Table, d: c_int, out: *mut *mut Sc) -> c_int;
     pub fn tsgpu_sc_num_vars(sc: *const Sc) -> c_uint;
+    pub fn tsgpu_sc_exclusive(sc: *mut Sc, on: c_int) -> c_int;      // 1: nothing else is enqueued on the context during the rounds (enables the resident tail kernel)
     pub fn tsgpu_sc_round_eval(sc: *mut Sc, evals: *mut Fr) -> c_int;
     pub fn tsgpu_sc_bind(sc: *mut Sc, r: *const Fr) -> c_int;
     pub fn tsgpu_sc_bind_eval(sc: *mut Sc, r: *const Fr, evals: *mut Fr) -> c_int;

@@ -153,6 +153,8 @@ pub fn sumcheck_prove_product(ctx: &Context, sc: &SumCheck, tables: &[Multilinea
     }
     let mut raw_sc = ptr::null_mut();
     if let Err(e) = ctx.check(unsafe { ffi::tsgpu_sc_begin(ctx.raw, handles.as_ptr(), handles.len() as c_int, &mut raw_sc) }) { free_all(&handles); return Err(e); }
+    // this loop enqueues nothing else on the context until tsgpu_sc_end: the small d = 2 rounds may run in the resident tail kernel
+    unsafe { ffi::tsgpu_sc_exclusive(raw_sc, 1); }
     let result = (|| -> Result<SumCheckProof> {
         let xs: Vec<Fr> = (0..4u64).map(Fr::from).collect();
         let mut round_polynomials = Vec::with_capacity(sc.num_vars);
