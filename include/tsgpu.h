@@ -412,6 +412,17 @@ int tsgpu_twist_write_check_prove(tsgpu_ctx* ctx, const uint64_t* addresses, con
 int tsgpu_twist_write_check_verify(tsgpu_ctx* ctx, const uint64_t* addresses, const tsgpu_fr* values, const uint8_t* is_write, size_t num_operations,
                                    size_t memory_size, tsgpu_transcript* transcript, const tsgpu_fr claims[2], const tsgpu_fr* rounds3, size_t num_rounds3,
                                    const tsgpu_fr* final3, const tsgpu_fr* rounds4, size_t num_rounds4, const tsgpu_fr* final4, int* valid);
+/* ---- binding the constraint sum-checks above to the KZG commitments of a Twist / Shout proof.
+ * tsgpu_transcript_bind_proof: appends the two commitment hashes of `proof` under the labels Twist::prove (is_shout = 0: "address_commitment",
+ * "value_commitment", src/twist.rs:157-160) or Shout::prove (1: "table_commitment", "index_commitment", src/shout.rs:129-133) use; called by prover and verifier
+ * on the fresh transcript they then hand to tsgpu_*_check_prove / _verify, it makes every challenge of the sum-checks depend on the commitments.
+ * tsgpu_*_commitments_match: recomputes the two commitments from the clear statement on the device and compares them with the proof's (*match = 1 / 0): what the
+ * verifier runs to know that the commitments it verified openings of commit to the statement the sum-checks are about.  (Non-succinct: the verifier reads the statement.) */
+int tsgpu_transcript_bind_proof(tsgpu_transcript* transcript, const tsgpu_proof* proof, int is_shout);
+int tsgpu_twist_commitments_match(tsgpu_ctx* ctx, const tsgpu_params* params, const tsgpu_proof* proof, const uint64_t* addresses, const tsgpu_fr* values,
+                                  size_t num_operations, int* match);
+int tsgpu_shout_commitments_match(tsgpu_ctx* ctx, const tsgpu_params* params, const tsgpu_proof* proof, const tsgpu_fr* entries, size_t num_entries,
+                                  const uint64_t* lookup_indices, size_t num_lookups, int* match);
 /* Twist::verify / Shout::verify (src/twist.rs:255-304, src/shout.rs:225-274): transcript replay, SumCheck::verify and
  * the two KZGCommitment::verify pairing checks (src/commitments.rs:201-228) - all on the CPU, as in the reference. */
 int tsgpu_twist_verify(tsgpu_ctx* ctx, const tsgpu_params* params, const tsgpu_proof* proof, int* valid);

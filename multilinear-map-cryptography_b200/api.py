@@ -566,6 +566,23 @@ class ShoutReadCheck:
                                                            transcript._h, _p(rp), C.c_size_t(rp.shape[0]), _p(fe), C.byref(ok)))
         return bool(ok.value)
 
+    # ---- binding to the KZG commitments of a Shout proof (tsgpu_transcript_bind_proof / tsgpu_shout_commitments_match)
+    @staticmethod
+    def bind(transcript: Transcript, proof: "ShoutProof") -> Transcript:
+        """absorb the proof's table / index commitment hashes (labels of src/shout.rs:129-133) before the sum-check draws anything; returns the transcript"""
+        rc = lib().tsgpu_transcript_bind_proof(transcript._h, proof._h, C.c_int(1))
+        assert rc == 0, rc
+        return transcript
+
+    def commitments_match(self, params, proof: "ShoutProof", table: LookupTable) -> bool:
+        """do the proof's two commitments commit to THIS table and THESE lookup indices?  (recomputed on the device from the clear statement)"""
+        idx, _ = self._statement(table)
+        entries = _fr(table.entries) if len(table.entries) else np.empty((0, 4), dtype=np.uint64)
+        ok = C.c_int(0)
+        self.ctx.check(lib().tsgpu_shout_commitments_match(self.ctx._h, params._h, proof._h, _p(entries), C.c_size_t(entries.shape[0]), _p(idx),
+                                                           C.c_size_t(idx.shape[0]), C.byref(ok)))
+        return bool(ok.value)
+
 
 class TwistMemoryCheck:
     """The memory-consistency sum-checks the reference leaves as a stub (src/twist.rs:181-214): read-checking over (cell, cycle) with its
@@ -636,6 +653,23 @@ class TwistMemoryCheck:
         self.ctx.check(lib().tsgpu_twist_write_check_verify(self.ctx._h, _p(addr), _p(vals), _p(isw), C.c_size_t(addr.shape[0]), C.c_size_t(memory_size),
                                                             transcript._h, _p(wclaims), _p(r3), C.c_size_t(r3.shape[0]), _p(f3),
                                                             _p(r4), C.c_size_t(r4.shape[0]), _p(f4), C.byref(ok)))
+        return bool(ok.value)
+
+    # ---- binding to the KZG commitments of a Twist proof (tsgpu_transcript_bind_proof / tsgpu_twist_commitments_match)
+    @staticmethod
+    def bind(transcript: Transcript, proof: "TwistProof") -> Transcript:
+        """absorb the proof's address / value commitment hashes (labels of src/twist.rs:157-160) before the sum-checks draw anything; returns the transcript"""
+        rc = lib().tsgpu_transcript_bind_proof(transcript._h, proof._h, C.c_int(0))
+        assert rc == 0, rc
+        return transcript
+
+    def commitments_match(self, params, proof: "TwistProof", trace: "MemoryTrace") -> bool:
+        """do the proof's two commitments commit to THIS trace's addresses and values?  (recomputed on the device from the clear statement)"""
+        addr, vals, _ = trace.arrays()
+        addr = np.ascontiguousarray(addr, dtype=np.uint64).reshape(-1)
+        vals = _fr(vals) if len(vals) else np.empty((0, 4), dtype=np.uint64)
+        ok = C.c_int(0)
+        self.ctx.check(lib().tsgpu_twist_commitments_match(self.ctx._h, params._h, proof._h, _p(addr), _p(vals), C.c_size_t(addr.shape[0]), C.byref(ok)))
         return bool(ok.value)
 
 

@@ -354,6 +354,66 @@ int tsgpu_shout_prove(tsgpu_ctx* ctx, const tsgpu_params* params, const tsgpu_fr
     return rc;
 }
 
+// ------------------------------------------------------------------------------------ binding the constraint sum-checks to the commitments of a proof
+// The non-parity sum-checks (host/read_check.cpp, host/memory_check.cpp) run on a transcript of the caller.  To tie them to the KZG commitments of the
+// byte-identical Twist / Shout proof: (1) the transcript first absorbs the two commitment hashes exactly as Twist::prove / Shout::prove absorb them
+// (tsgpu_transcript_bind_proof), so every challenge of the sum-checks depends on the commitments; (2) the verifier, who holds the statement in the clear,
+// recomputes the two commitments from it on the device (same MSM as the prover) and compares (tsgpu_*_commitments_match): the proof's commitments then
+// provably commit to THIS statement.  The verifier is not succinct - that would take a multilinear opening argument the reference does not have.
+namespace {
+int commitments_of_two_vectors(tsgpu_ctx* ctx, const tsgpu_params* params, tsgpu_poly* pa, tsgpu_poly* pb, tsgpu_g1 out[2]) {
+    const bool eval_basis = ctx->eval_basis && tsgpu_srs_can_lagrange(params->srs) &&
+                            tsgpu_srs_lagrange_prepare(ctx, params->srs, tsgpu_poly_len(pa)) == TSGPU_OK &&
+                            tsgpu_srs_lagrange_prepare(ctx, params->srs, tsgpu_poly_len(pb)) == TSGPU_OK;
+    int rc;
+    if (!eval_basis) {
+        if ((rc = tsgpu_poly_interpolate_iota(ctx, pa))) return rc;
+        if ((rc = tsgpu_poly_interpolate_iota(ctx, pb))) return rc;
+    }
+    const tsgpu_poly* both[2] = {pa, pb};
+    return eval_basis ? tsgpu_kzg_commit_values_batch_dev(ctx, params->srs, both, 2, out) : tsgpu_kzg_commit_batch_dev(ctx, params->srs, both, 2, out);
+}
+int match_result(const tsgpu_proof* proof, const tsgpu_g1 c[2], int* match) {
+    G1J a0, a1, b0, b1;
+    memcpy(&a0, &proof->commitments[0], 96); memcpy(&a1, &proof->commitments[1], 96); memcpy(&b0, &c[0], 96); memcpy(&b1, &c[1], 96);
+    *match = (a0.equals(b0) && a1.equals(b1)) ? 1 : 0;
+    return TSGPU_OK;
+}
+}  // namespace
+int tsgpu_transcript_bind_proof(tsgpu_transcript* transcript, const tsgpu_proof* proof, int is_shout) {
+    if (!transcript || !proof) return TSGPU_E_INVALID_PARAMETERS;
+    Transcript& tr = *tsgpu_transcript_inner(transcript);
+    tsgpu_fr h;
+    tsgpu_g1_hash(&proof->commitments[0], &h); tr.append_field_element(is_shout ? "table_commitment" : "address_commitment", fr_of(h));   // shout.rs:129, twist.rs:157
+    tsgpu_g1_hash(&proof->commitments[1], &h); tr.append_field_element(is_shout ? "index_commitment" : "value_commitment", fr_of(h));
+    return TSGPU_OK;
+}
+int tsgpu_twist_commitments_match(tsgpu_ctx* ctx, const tsgpu_params* params, const tsgpu_proof* proof, const uint64_t* addresses, const tsgpu_fr* values,
+                                  size_t num_operations, int* match) {
+    if (!ctx || !params || !proof || !match || ((!addresses || !values) && num_operations)) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    if (num_operations > params->max_operations) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "Too many operations");
+    const size_t padded = next_pow2(num_operations);
+    tsgpu_poly *pa = nullptr, *pv = nullptr;
+    tsgpu_g1 c[2];
+    int rc = tsgpu_poly_from_u64(ctx, addresses, num_operations, padded, &pa);
+    if (!rc) rc = tsgpu_poly_upload_padded(ctx, values, num_operations, padded, &pv);
+    if (!rc) rc = commitments_of_two_vectors(ctx, params, pa, pv, c);
+    tsgpu_poly_free(ctx, pa); tsgpu_poly_free(ctx, pv);
+    return rc ? rc : match_result(proof, c, match);
+}
+int tsgpu_shout_commitments_match(tsgpu_ctx* ctx, const tsgpu_params* params, const tsgpu_proof* proof, const tsgpu_fr* entries, size_t num_entries,
+                                  const uint64_t* lookup_indices, size_t num_lookups, int* match) {
+    if (!ctx || !params || !proof || !match || (!entries && num_entries) || (!lookup_indices && num_lookups)) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    if (num_lookups > params->max_operations) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "Too many lookup operations");
+    tsgpu_poly *pt = nullptr, *pi = nullptr;
+    tsgpu_g1 c[2];
+    int rc = tsgpu_poly_upload_padded(ctx, entries, num_entries, next_pow2(num_entries), &pt);
+    if (!rc) rc = tsgpu_poly_from_u64(ctx, lookup_indices, num_lookups, next_pow2(num_lookups), &pi);
+    if (!rc) rc = commitments_of_two_vectors(ctx, params, pt, pi, c);
+    tsgpu_poly_free(ctx, pt); tsgpu_poly_free(ctx, pi);
+    return rc ? rc : match_result(proof, c, match);
+}
+
 // ------------------------------------------------------------------------------------ proof accessors
 size_t tsgpu_proof_num_rounds(const tsgpu_proof* p) { return p->round_polynomials.size() / 4; }
 size_t tsgpu_proof_num_openings(const tsgpu_proof* p) { return p->opening_proofs.size(); }

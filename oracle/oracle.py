@@ -459,13 +459,14 @@ def lt_point_ints(b_ints: Sequence[int], t: int) -> List[int]:
     return out
 
 
-def shout_read_check_prove(entries: np.ndarray, idx: np.ndarray, vals: np.ndarray, mode: str = "tables"):
-    """core Shout read-checking rv~(r) = sum_x ra~(x, r) Val~(x) on a fresh transcript -> (claim, sum-check result dict)"""
+def shout_read_check_prove(entries: np.ndarray, idx: np.ndarray, vals: np.ndarray, mode: str = "tables", transcript: Optional["Transcript"] = None):
+    """core Shout read-checking rv~(r) = sum_x ra~(x, r) Val~(x) on a fresh transcript (or the one given: e.g. bound to a proof's commitments)
+    -> (claim, sum-check result dict)"""
     p = R_MOD
     nent, nlook = entries.shape[0], idx.shape[0]
     K = 1 << max(nent - 1, 0).bit_length(); L = 1 << max(nlook - 1, 0).bit_length()
     l = L.bit_length() - 1
-    tr = Transcript()
+    tr = transcript if transcript is not None else Transcript()
     tr.append_field_elements(b"read_check_statement", statement_digest_elements(
         b"shout_read_check", [nent, nlook], [_u64(entries).tobytes(), _u64(idx).tobytes(), _u64(vals).tobytes()]))
     r = tr.challenge_field_elements(b"read_check_point", l)
@@ -481,7 +482,8 @@ def shout_read_check_prove(entries: np.ndarray, idx: np.ndarray, vals: np.ndarra
     return claim_fr, sumcheck_prove_product([fr_from_ints(A), fr_from_ints(V)], claim_fr, transcript=tr, mode=mode)
 
 
-def twist_memory_check_prove(addr: np.ndarray, vals: np.ndarray, isw: np.ndarray, K: int, mode: str = "tables", with_write_check: bool = False):
+def twist_memory_check_prove(addr: np.ndarray, vals: np.ndarray, isw: np.ndarray, K: int, mode: str = "tables", with_write_check: bool = False,
+                             transcript: Optional["Transcript"] = None):
     """Twist read-checking over (cell, cycle) + Val-evaluation on a fresh transcript -> (read claim, Val~(x*, j*), part 1, part 2); with_write_check
     appends (write claim, Val~(x**, j**), part 3, part 4): write-checking and its Val-evaluation on the same transcript"""
     p = R_MOD
@@ -489,7 +491,7 @@ def twist_memory_check_prove(addr: np.ndarray, vals: np.ndarray, isw: np.ndarray
     T = 1 << max(n - 1, 0).bit_length()
     k, t = K.bit_length() - 1, T.bit_length() - 1
     vi = fr_to_ints(vals) if n else []
-    tr = Transcript()
+    tr = transcript if transcript is not None else Transcript()
     tr.append_field_elements(b"memory_check_statement", statement_digest_elements(
         b"twist_memory_chk", [n, K], [_u64(addr).tobytes(), _u64(vals).tobytes(), np.ascontiguousarray(isw, dtype=np.uint8).tobytes()]))
     r = tr.challenge_field_elements(b"memory_check_point", t)

@@ -115,6 +115,13 @@ extern "C" {
                                           memory_size: usize, transcript: *mut TranscriptH, claims: *const Fr, rounds3: *const Fr, num_rounds3: usize,
                                           final3: *const Fr, rounds4: *const Fr, num_rounds4: usize, final4: *const Fr, valid: *mut c_int) -> c_int;
 
+    // binding the constraint sum-checks to the KZG commitments of a Twist (is_shout = 0) / Shout (1) proof
+    pub fn tsgpu_transcript_bind_proof(transcript: *mut TranscriptH, proof: *const Proof, is_shout: c_int) -> c_int;
+    pub fn tsgpu_twist_commitments_match(ctx: *mut Ctx, params: *const Params, proof: *const Proof, addresses: *const u64, values: *const Fr,
+                                         num_operations: usize, matches: *mut c_int) -> c_int;
+    pub fn tsgpu_shout_commitments_match(ctx: *mut Ctx, params: *const Params, proof: *const Proof, entries: *const Fr, num_entries: usize,
+                                         lookup_indices: *const u64, num_lookups: usize, matches: *mut c_int) -> c_int;
+
     // multi-GPU (one process per GPU; the host program carries the 128-byte NCCL id)
     pub fn tsgpu_comm_unique_id(out: *mut u8) -> c_int;
     pub fn tsgpu_comm_init(ctx: *mut Ctx, nranks: c_int, rank: c_int, id: *const u8) -> c_int;

@@ -200,3 +200,46 @@ def test_memory_check_challenges_depend_on_the_trace(ctx, tsgpu, oracle):
     proof = mc.prove_arrays(addr, vals, isw, K, tsgpu.Transcript())
     assert mc.verify_arrays(addr, vals, isw, K, proof, tsgpu.Transcript())
     assert not mc.verify_arrays(addr, forged, isw, K, proof, tsgpu.Transcript())
+
+
+def test_memory_check_bound_to_the_commitments_of_a_twist_proof(ctx, tsgpu, oracle):
+    """src/twist.rs:181-214 ("a production implementation ... tie to the commitments"): the constraint sum-checks run on a transcript that first absorbed the
+    address / value commitment hashes of the byte-identical Twist proof (labels of twist.rs:157-160), and the verifier recomputes both commitments from the
+    clear statement.  The oracle runs the same sum-checks on ITS transcript after appending ITS hashes of ITS commitments."""
+    pp, vp = tsgpu.setup_params(ctx, 6)
+    trace = tsgpu.MemoryTrace.new(16)
+    rng = np.random.default_rng(11)
+    for j in range(50):
+        a = int(rng.integers(0, 16))
+        trace.write(a, tsgpu.fe(int(rng.integers(1, 1 << 62)))) if rng.integers(0, 2) else trace.read(a)
+    tw = tsgpu.Twist.new(pp)
+    proof = tw.prove(trace)
+    assert tw.verify(proof, vp)
+    mc = tsgpu.TwistMemoryCheck(ctx)
+    cproof = mc.prove(trace, mc.bind(tsgpu.Transcript(), proof))
+    assert mc.verify(trace, cproof, mc.bind(tsgpu.Transcript(), proof))
+    assert mc.commitments_match(pp, proof, trace)
+    # oracle: same protocol on the oracle's transcript, hashes of the oracle's own commitments (Jacobian points out of the oracle's proof parser are not needed:
+    # the proof bytes already equal the oracle's - test_gpu_protocols - so the device commitments are the oracle's; the hash is the oracle's g1_hash)
+    addr, vals, isw = trace.arrays()
+    otr = oracle.Transcript()
+    otr.append_field_element(b"address_commitment", oracle.g1_hash(proof.commitments[0]))
+    otr.append_field_element(b"value_commitment", oracle.g1_hash(proof.commitments[1]))
+    c1, c2, ref1, ref2, c3, c4, ref3, ref4 = oracle.twist_memory_check_prove(addr, vals, isw, 16, "tables", with_write_check=True, transcript=otr)
+    assert (cproof.claims[0] == c1).all() and (cproof.read_check.round_polynomials == ref1["round_polynomials"]).all()
+    assert (cproof.write_claims[0] == c3).all() and (cproof.write_val_evaluation.round_polynomials == ref4["round_polynomials"]).all()
+    # unbound, or bound to the proof of ANOTHER trace: every challenge differs, nothing verifies
+    assert not mc.verify(trace, cproof, tsgpu.Transcript())
+    other = tsgpu.MemoryTrace.new(16)
+    for op in trace.operations[:-1]:
+        other.write(op.address, op.value) if op.kind == "W" else other.read(op.address)
+    other.write(3, tsgpu.fe(999))
+    proof2 = tw.prove(other)
+    assert not mc.verify(trace, cproof, mc.bind(tsgpu.Transcript(), proof2))
+    assert not mc.commitments_match(pp, proof2, trace) and mc.commitments_match(pp, proof2, other)
+    # same trace under the coefficient path commits to the same points
+    ctx.set_tuning("eval_basis", 0)
+    try:
+        assert mc.commitments_match(pp, proof, trace) and not mc.commitments_match(pp, proof, other)
+    finally:
+        ctx.set_tuning("eval_basis", 1)

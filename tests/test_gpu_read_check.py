@@ -146,3 +146,33 @@ def test_challenges_depend_on_the_statement(ctx, tsgpu, oracle):
             b"shout_read_check", [32, 16], [ent.tobytes(), ix.tobytes(), np.ascontiguousarray(vv).tobytes()]))
         pts.add(tr.challenge_field_elements(b"read_check_point", 4).tobytes())
     assert len(pts) == 4
+
+
+def test_read_check_bound_to_the_commitments_of_a_shout_proof(ctx, tsgpu, oracle):
+    """src/shout.rs:157-184: the read-checking sum-check on a transcript that first absorbed the table / index commitment hashes of the byte-identical
+    Shout proof (labels of shout.rs:129-133); the verifier recomputes both commitments from the clear statement."""
+    pp, vp = tsgpu.setup_params(ctx, 6)
+    table = tsgpu.LookupTable.new(tsgpu.fe_vec([i * i + 7 for i in range(40)]))
+    rng = np.random.default_rng(3)
+    for i in rng.integers(0, 40, size=33):
+        table.lookup(int(i))
+    sh = tsgpu.Shout.new(pp)
+    proof = sh.prove(table)
+    assert sh.verify(proof, vp)
+    rc = tsgpu.ShoutReadCheck(ctx)
+    claim, cproof, ch = rc.prove(table, rc.bind(tsgpu.Transcript(), proof))
+    assert rc.verify(table, cproof, rc.bind(tsgpu.Transcript(), proof))
+    assert rc.commitments_match(pp, proof, table)
+    idx, vals = rc._statement(table)
+    otr = oracle.Transcript()
+    otr.append_field_element(b"table_commitment", oracle.g1_hash(proof.commitments[0]))
+    otr.append_field_element(b"index_commitment", oracle.g1_hash(proof.commitments[1]))
+    want_claim, ref = oracle.shout_read_check_prove(table.entries, idx, vals, "tables", transcript=otr)
+    assert (claim == want_claim).all() and (cproof.round_polynomials == ref["round_polynomials"]).all() and (ch == ref["challenges"]).all()
+    assert not rc.verify(table, cproof, tsgpu.Transcript())                       # unbound transcript: other challenges
+    other = tsgpu.LookupTable.new(tsgpu.fe_vec([i * i + 7 for i in range(39)] + [5]))
+    for l in table.lookups:
+        other.lookup(l.index)
+    proof2 = sh.prove(other)
+    assert not rc.verify(table, cproof, rc.bind(tsgpu.Transcript(), proof2))
+    assert not rc.commitments_match(pp, proof2, table) and rc.commitments_match(pp, proof2, other)
