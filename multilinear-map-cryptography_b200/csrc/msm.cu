@@ -303,6 +303,86 @@ __global__ void __launch_bounds__(128) k_msm_merge_chunks(g1_xyzz* partial, cons
     }
 }
 
+// ---------------------------------------------------------------- lane-cooperative XYZZ addition (the latency-bound tree levels of the reduction)
+// A lone thread needs ~14 dependent field products (~3500 instructions, 10-20 us when its warp has the scheduler to itself) for one XYZZ + XYZZ
+// addition; tree levels run few of them, so their cost is that latency.  Here the four lanes of a QUAD (lanes 4q .. 4q + 3 of a warp) share one
+// addition of add-2008-s: four product steps with one product per lane, operands exchanged through QUAD_SLOTS field elements of shared memory:
+//   step 1   U1 = X1 ZZ2 | U2 = X2 ZZ1 | S1 = Y1 ZZZ2 | S2 = Y2 ZZZ1          (then every lane: P = U2 - U1, R = S2 - S1)
+//   step 2   PP = P^2    | ZZ1 ZZ2     | R^2          | ZZZ1 ZZZ2
+//   step 3   Q = U1 PP   | PPP = P PP  | ZZ3 = ZZ1 ZZ2 PP | (PPP)
+//   step 4   X3 = R^2 - PPP - 2Q, Y3 = R (Q - X3) - S1 PPP | ZZZ3 = ZZZ1 ZZZ2 PPP      (one fused a b - c d on every lane: no divergence)
+// i.e. ~4.5 products deep instead of ~13.5.  Same bits as g1_xyzz::add.  All 32 lanes of a warp must call it (quads with active = false only keep the
+// warp converged: their pointers must still be readable); dst may alias A or B; the caller orders successive tree levels (__syncthreads / __syncwarp).
+constexpr int QUAD_SLOTS = 12;
+__device__ __noinline__ void xyzz_add_alone(g1_xyzz* dst, const g1_xyzz* A, const g1_xyzz* B) {
+    const g1_xyzz a = *A, b = *B;
+    *dst = a.add(b);
+}
+__device__ __forceinline__ fq_t fq_sel(bool c, const fq_t& a, const fq_t& b) {
+    fq_t r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.l[i] = c ? a.l[i] : b.l[i];
+    return r;
+}
+__device__ __forceinline__ void quad_add(g1_xyzz* dst, const g1_xyzz* A, const g1_xyzz* B, fq_t* scr, bool active) {
+    const unsigned r = threadIdx.x & 3;
+    const fq_t* fa = reinterpret_cast<const fq_t*>(A);   // fields in order X, Y, ZZ, ZZZ
+    const fq_t* fb = reinterpret_cast<const fq_t*>(B);
+    fq_t* fd = reinterpret_cast<fq_t*>(dst);
+    const bool idA = fa[2].is_zero(), idB = fb[2].is_zero();
+    {   // step 1
+        const fq_t* s0 = (r & 1) ? fb : fa; const fq_t* s1 = (r & 1) ? fa : fb;
+        const fq_t a = s0[r >> 1], b = s1[2 + (r >> 1)];
+        scr[r] = a * b;
+    }
+    __syncwarp();
+    const fq_t P = scr[1] - scr[0], R = scr[3] - scr[2];
+    const bool same_x = P.is_zero();
+    {   // step 2
+        const fq_t ma = fa[2 + (r >> 1)], mb = fb[2 + (r >> 1)];
+        const fq_t a = fq_sel(r == 0, P, fq_sel(r == 2, R, ma)), b = fq_sel(r == 0, P, fq_sel(r == 2, R, mb));
+        scr[4 + r] = a * b;   // 4: PP, 5: ZZ1 ZZ2, 6: R^2, 7: ZZZ1 ZZZ2
+    }
+    __syncwarp();
+    {   // step 3
+        const fq_t PP = scr[4];
+        const fq_t a = fq_sel(r == 0, scr[0], fq_sel(r == 2, scr[5], P));
+        scr[8 + r] = a * PP;   // 8: Q, 9: PPP, 10: ZZ3, 11: PPP again
+    }
+    __syncwarp();
+    {   // step 4
+        const fq_t Q = scr[8], PPP = scr[9];
+        const fq_t X3 = scr[6] - PPP - Q.dbl();
+        const fq_t a = fq_sel(r == 0, R, scr[7]), b = fq_sel(r == 0, Q - X3, PPP), c = fq_sel(r == 0, scr[2], fq_t::zero());
+        const fq_t res = fq_t::mul_sub(a, b, c, PPP);
+        if (active) {
+            if (idB) { if (dst != A) fd[r] = fa[r]; }
+            else if (idA) fd[r] = fb[r];
+            else if (same_x) { if (r == 0) xyzz_add_alone(dst, A, B); }   // doubling / inverse points: the lone-thread formulas
+            else if (r == 0) { fd[0] = X3; fd[1] = res; }
+            else if (r == 1) fd[3] = res;
+            else if (r == 2) fd[2] = scr[10];
+        }
+    }
+    __syncwarp();
+}
+// tree sum of sh[0 .. n) (n a power of two) into sh[0] by the quads of a block; scr_all: QUAD_SLOTS elements per quad.  Block-wide: every thread calls.
+__device__ __forceinline__ void quad_tree_sum(g1_xyzz* sh, unsigned n, fq_t* scr_all) {
+    const unsigned q = threadIdx.x >> 2, quads = blockDim.x >> 2;
+    fq_t* scr = scr_all + (size_t)q * QUAD_SLOTS;
+    for (unsigned s = n >> 1; s > 0; s >>= 1) {
+        for (unsigned base = 0; base < s; base += quads) {
+            if (base + ((threadIdx.x >> 5) << 3) < s) {   // warp-uniform: some quad of this warp has a pair
+                const unsigned pair = base + q;
+                const bool act = pair < s;
+                const unsigned i = act ? pair : 0;
+                quad_add(sh + i, sh + i, sh + i + s, scr, act);
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------- 4. window reduction  S_w = sum_b (b + 1) * B_{w,b}
 // Three short launches with a shallow dependency chain (a lone XYZZ addition has ~6 us latency, so depth is what costs):
 //   a. span sums: thread per span of S consecutive buckets: R = sum B, L = sum_j (j + 1) B_{lo + j}   (2 S additions deep)
@@ -325,9 +405,11 @@ __global__ void __launch_bounds__(128) k_msm_span_sums(const g1_xyzz* partial, c
         st_xyzz(R + t, running); st_xyzz(L + t, acc);
     }
 }
-__global__ void __launch_bounds__(MSM_SUM_THREADS) k_msm_bit_sums(const g1_xyzz* R, const g1_xyzz* L, unsigned T, unsigned nbits, unsigned k0, g1_xyzz* parts) {
+__global__ void __launch_bounds__(MSM_SUM_THREADS) k_msm_bit_sums(const g1_xyzz* R, const g1_xyzz* L, unsigned T, unsigned nbits, unsigned k0, g1_xyzz* parts, int quad) {
     // block (k, w, p): slice p of gridDim.z of the elements that bit k selects (k == nbits: all L's) of bucket set w
-    __shared__ g1_xyzz sh[MSM_SUM_THREADS];
+    extern __shared__ __align__(16) unsigned char bit_sums_smem[];
+    g1_xyzz* sh = reinterpret_cast<g1_xyzz*>(bit_sums_smem);                       // MSM_SUM_THREADS points, then the quads' exchange slots
+    fq_t* scr = reinterpret_cast<fq_t*>(sh + MSM_SUM_THREADS);
     // slots k < nbits: the R's whose span index has bit k set; slots nbits and nbits + 1: the two halves of the L's (so that every
     // block sums the same number of elements, T / 2 / P)
     const unsigned k = blockIdx.x + k0, w = blockIdx.y, p = blockIdx.z, P = gridDim.z;   // k0: first slot of this launch
@@ -345,21 +427,41 @@ __global__ void __launch_bounds__(MSM_SUM_THREADS) k_msm_bit_sums(const g1_xyzz*
     }
     sh[threadIdx.x] = acc;
     __syncthreads();
-    for (unsigned s = blockDim.x / 2; s > 0; s >>= 1) {
-        if (threadIdx.x < s) sh[threadIdx.x] = sh[threadIdx.x].add(sh[threadIdx.x + s]);
-        __syncthreads();
+    if (quad) {
+        quad_tree_sum(sh, blockDim.x, scr);
+    } else {
+        for (unsigned s = blockDim.x / 2; s > 0; s >>= 1) {
+            if (threadIdx.x < s) sh[threadIdx.x] = sh[threadIdx.x].add(sh[threadIdx.x + s]);
+            __syncthreads();
+        }
     }
     if (threadIdx.x == 0) st_xyzz(parts + ((size_t)w * (nbits + 2) + k) * P + p, sh[0]);
 }
 // block (k, w): adds the P <= 32 slice sums of (set w, bit k) and writes the sum as a Jacobian point.  The weights 2^(k + log2 S) and the
 // final additions are a Horner evaluation over span_bits + 1 points per set: ~40 group operations, done by the host in microseconds
 // (on the device they would be a chain of ~20 dependent doublings, ~0.1 ms of pure latency)
-__global__ void __launch_bounds__(32) k_msm_bit_finish(const g1_xyzz* parts, unsigned P, unsigned nbits, unsigned k0, g1_jac* out) {
+__global__ void __launch_bounds__(MSM_FIN_THREADS) k_msm_bit_finish(const g1_xyzz* parts, unsigned P, unsigned nbits, unsigned k0, g1_jac* out, int quad) {
     __shared__ g1_xyzz sh[32];
+    __shared__ fq_t scr[(MSM_FIN_THREADS / 4) * QUAD_SLOTS];
     const unsigned k = blockIdx.x + k0, w = blockIdx.y;
     const size_t slot = (size_t)w * (nbits + 2) + k;
-    sh[threadIdx.x] = threadIdx.x < P ? ld_xyzz(parts + slot * P + threadIdx.x) : g1_xyzz::identity();
-    __syncwarp();
+    if (threadIdx.x < 32) sh[threadIdx.x] = threadIdx.x < P ? ld_xyzz(parts + slot * P + threadIdx.x) : g1_xyzz::identity();
+    __syncthreads();
+    if (quad) {
+        unsigned n = 1; while (n < P) n <<= 1;
+        quad_tree_sum(sh, n, scr);
+        // (X ZZ^2, Y ZZZ^2, ZZZ): lanes 0 and 1 take one coordinate each (same instructions, other operands)
+        if (threadIdx.x < 2) {
+            const fq_t* f = reinterpret_cast<const fq_t*>(&sh[0]);
+            const bool id = f[2].is_zero();
+            const fq_t z = f[2 + threadIdx.x], c = f[threadIdx.x];
+            const fq_t v = id ? fq_t::one() : c * z.sqr();
+            st256(threadIdx.x ? &out[slot].y : &out[slot].x, v);
+            if (threadIdx.x == 0) st256(&out[slot].z, id ? fq_t::zero() : f[3]);
+        }
+        return;
+    }
+    if (threadIdx.x >= 32) return;
     for (unsigned s = 16; s > 0; s >>= 1) {
         if (threadIdx.x < s && threadIdx.x + s < P) sh[threadIdx.x] = sh[threadIdx.x].add(sh[threadIdx.x + s]);
         __syncwarp();
@@ -442,6 +544,8 @@ __global__ void k_affine_to_jac(const g1_affine* in, size_t n, g1_jac* out) {
 }
 
 // ---------------------------------------------------------------- launchers
+static int g_msm_quad_tree = 1;   // tree levels of the window reduction by lane quads (tuning "msm_quad_tree"; 0 = one thread per addition)
+void msm_set_quad_tree(int on) { g_msm_quad_tree = on ? 1 : 0; }
 static inline int gridfor(size_t work, int threads, size_t cap) {
     size_t g = (work + threads - 1) / threads;
     if (g < 1) g = 1;
@@ -475,7 +579,10 @@ size_t msm_scratch_bytes(size_t nmax, int K, unsigned c, bool shared, MsmLayout*
     // span of the window reduction: long spans when there are many buckets (throughput-bound), short ones when the dependency
     // chain of 2 x span additions would dominate (aim at >= 32768 span threads)
     unsigned span = MSM_RED_SPAN;
-    while (span > 2 && nbuckets / span < 65536) span >>= 1;
+    size_t min_spans = MSM_RED_MIN_SPANS;
+    if (const char* env = getenv("TSGPU_RED_SPAN")) { int v = atoi(env); if (v >= 2 && v <= 64 && !(v & (v - 1))) span = (unsigned)v; }          // experiments
+    if (const char* env = getenv("TSGPU_RED_MIN_SPANS")) { long v = atol(env); if (v >= 1) min_spans = (size_t)v; }
+    while (span > 2 && nbuckets / span < min_spans) span >>= 1;
     if (span > nb) span = (unsigned)nb;
     unsigned nbits = 0; while (((size_t)span << nbits) < nb) ++nbits;   // spans per bucket set = 2^nbits
     size_t off = 0;
@@ -570,8 +677,11 @@ cudaError_t msm_run(const MsmJob* jobs, int K, const MsmLayout& L, unsigned char
         if (P > 32) P = 32;
         if (P < 1) P = 1;
         g1_xyzz* parts = bits;
-        k_msm_bit_sums<<<dim3(slots, L.sets, P), MSM_SUM_THREADS, 0, s>>>(spanR, spanL, L.blocks_per_window, L.span_bits, k0, parts);
-        k_msm_bit_finish<<<dim3(slots, L.sets), 32, 0, s>>>(parts, P, L.span_bits, k0, wout);
+        const size_t sum_smem = MSM_SUM_THREADS * sizeof(g1_xyzz) + (MSM_SUM_THREADS / 4) * QUAD_SLOTS * sizeof(fq_t);
+        static bool smem_set = false;
+        if (!smem_set) { if ((e = cudaFuncSetAttribute(k_msm_bit_sums, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sum_smem))) return e; smem_set = true; }
+        k_msm_bit_sums<<<dim3(slots, L.sets, P), MSM_SUM_THREADS, sum_smem, s>>>(spanR, spanL, L.blocks_per_window, L.span_bits, k0, parts, g_msm_quad_tree);
+        k_msm_bit_finish<<<dim3(slots, L.sets), MSM_FIN_THREADS, 0, s>>>(parts, P, L.span_bits, k0, wout, g_msm_quad_tree);
     }
     if (ev) cudaEventRecord(ev[4], s);
     if (launches) *launches += 16 + 2 * (unsigned)K;

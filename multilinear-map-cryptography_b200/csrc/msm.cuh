@@ -7,9 +7,12 @@ namespace tsg {
 
 constexpr unsigned MSM_CHUNK = 64;        // max entries one work item adds into its accumulator (bounds the serial chain of one thread)
 constexpr int MSM_ACC_THREADS = 128;
-constexpr unsigned MSM_RED_SPAN = 8;      // most buckets per thread in the window reduction (2 x span additions deep; the bit-decomposed tail costs
+constexpr unsigned MSM_RED_SPAN = 32;     // most buckets per thread in the window reduction (2 x span additions deep; the bit-decomposed tail costs
                                           // log2(buckets / span) / 2 additions per span); small bucket sets use shorter spans to keep the chain short
+constexpr size_t MSM_RED_MIN_SPANS = 32768; // ... i.e. halve the span while fewer span threads than this would run (measured with the quad tree, round 2: 8 / 65536 -> 32 / 32768
+                                          // takes the reduction of the open pass of a 2^20-op proof from 0.80 to 0.70 ms, of the commit pass from 0.25 to 0.19 ms)
 constexpr int MSM_SUM_THREADS = 256;
+constexpr int MSM_FIN_THREADS = 64;       // k_msm_bit_finish: 16 lane quads add the <= 32 slice sums of one (set, slot)
 constexpr size_t MSM_POW_SPAN = 64;       // consecutive tau powers per thread
 constexpr size_t MSM_INV_SPAN = 32;       // points per batch inversion
 
@@ -30,6 +33,7 @@ struct MsmLayout {
     size_t dig, sorted, hist, offsets, cursor, items, item_off, item_bucket, n_items, order, len_hist, scan_tmp, partial, blockres, bits, window_out;
 };
 
+void msm_set_quad_tree(int on);
 unsigned msm_window_bits(size_t n);
 unsigned msm_table_window_bits(size_t n);
 size_t msm_scratch_bytes(size_t nmax, int K, unsigned c, bool shared, MsmLayout* L, unsigned windows = 0);   // windows > 0: scan only that many low digit positions

@@ -24,5 +24,11 @@ def run(name, fn, reps=5):
     r = {k: round(ctx.timer_read(k)[0] / reps, 3) for k in ("msm_total", "msm_sort", "msm_accumulate", "msm_merge", "msm_reduce", "open_bary")}
     ctx.set_tuning("kernel_timing", 0)
     print(name, json.dumps(r), flush=True)
-run("commit pass", lambda: ctx.check(lib.tsgpu_kzg_commit_values_batch_dev(ctx._h, pp.srs._h, arr, C.c_size_t(2), B._p(outs))))
-run("open pass  ", lambda: ctx.check(lib.tsgpu_kzg_open_values_batch_dev(ctx._h, pp.srs._h, arr, C.c_size_t(2), B._p(z), B._p(vals), B._p(outs))))
+import hashlib
+for quad in ([int(a) for a in sys.argv[1:]] or [1]):
+  ctx.set_tuning("msm_quad_tree", quad)
+  print("msm_quad_tree =", quad)
+  run("commit pass", lambda: ctx.check(lib.tsgpu_kzg_commit_values_batch_dev(ctx._h, pp.srs._h, arr, C.c_size_t(2), B._p(outs))))
+  h1 = hashlib.sha256(outs.tobytes()).hexdigest()[:16]
+  run("open pass  ", lambda: ctx.check(lib.tsgpu_kzg_open_values_batch_dev(ctx._h, pp.srs._h, arr, C.c_size_t(2), B._p(z), B._p(vals), B._p(outs))))
+  print("result hashes", h1, hashlib.sha256(outs.tobytes() + vals.tobytes()).hexdigest()[:16])
