@@ -1,0 +1,3 @@
+python -m pytest tests -x -q -m gpu 2>&1 | tail -5
+python bench.py --no-cpu-baseline > gpurun_out/r2e_bench_n1.json 2> gpurun_out/r2e_bench_n1.err; echo bench rc=$?
+tail -c 600 gpurun_out/r2e_bench_n1.err
