@@ -175,6 +175,13 @@ int tsgpu_poly_clone(tsgpu_ctx* ctx, const tsgpu_poly* p, tsgpu_poly** out);
  * (src/twist.rs:115-148, src/shout.rs:105-118) */
 int tsgpu_poly_from_u64(tsgpu_ctx* ctx, const uint64_t* v, size_t n, size_t padded, tsgpu_poly** out);
 int tsgpu_poly_upload_padded(tsgpu_ctx* ctx, const tsgpu_fr* vals, size_t n, size_t padded, tsgpu_poly** out);
+/* same vector, but the host -> device copy runs on a side stream of the context and the call returns without waiting: work enqueued on the context
+ * afterwards overlaps the transfer (tsgpu_twist_prove commits the address vector while the 32 n bytes of values travel).  No other entry point waits for
+ * the copy by itself: tsgpu_poly_wait orders the context's stream behind it (a no-op for vectors that are not in flight); tsgpu_poly_free may be called at
+ * any time.  `vals` must stay valid until then; pinned memory is what makes the copy asynchronous. */
+int tsgpu_poly_upload_padded_async(tsgpu_ctx* ctx, const tsgpu_fr* vals, size_t n, size_t padded, tsgpu_poly** out);
+int tsgpu_poly_wait(tsgpu_ctx* ctx, tsgpu_poly* p);
+int tsgpu_poly_in_flight(const tsgpu_poly* p);
 
 /* ---- vector_to_polynomial: poly_utils::lagrange_interpolate over x_i = i  (src/twist.rs:307-315,
  * src/shout.rs:277-285, src/polynomials.rs:301-352) --------------------------------------------------------

@@ -128,6 +128,7 @@ void tsgpu_destroy(tsgpu_ctx* ctx) {
     if (ctx->host_out) cudaFreeHost(ctx->host_out);
     if (ctx->host_scratch) cudaFreeHost(ctx->host_scratch);
     if (ctx->tail_box) cudaFreeHost(ctx->tail_box);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -176,6 +177,7 @@ int tsgpu_set_tuning(tsgpu_ctx* ctx, const char* key, long value) {
     if (!strcmp(key, "deferred_claim_check")) { ctx->deferred_claim_check = value != 0; return TSGPU_OK; }
     if (!strcmp(key, "kernel_timing")) { ctx->timing = value != 0; return TSGPU_OK; }
     if (!strcmp(key, "msm_quad_tree")) { tsg::msm_set_quad_tree(value != 0); return TSGPU_OK; }   // 0: tree levels of the window reduction with one thread per addition (process-wide)
+    if (!strcmp(key, "h2d_overlap")) { ctx->h2d_overlap = value != 0; return TSGPU_OK; }
     if (!strcmp(key, "msm_tables")) { ctx->msm_tables = value != 0; return TSGPU_OK; }   // 0: per-window bucket sets on the plain SRS points
     if (!strcmp(key, "eval_basis")) { ctx->eval_basis = value != 0; return TSGPU_OK; }   // 0: Twist/Shout::prove interpolate and commit coefficients
     return fail(ctx, TSGPU_E_INVALID_PARAMETERS, std::string("unknown tuning key ") + key);

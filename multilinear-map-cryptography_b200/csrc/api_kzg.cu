@@ -46,6 +46,7 @@ struct MsmBasis { const g1_affine* pts; size_t n; const g1_affine* table; unsign
 struct tsgpu_poly {
     fr_t* d = nullptr;        // n coefficients, low -> high, natural order
     size_t n = 0;
+    cudaEvent_t ready = nullptr;   // set while a side-stream upload is in flight (tsgpu_poly_upload_padded_async): tsgpu_poly_wait orders the context's stream behind it
 };
 
 static_assert(sizeof(g1_affine) == 64 && sizeof(g1_jac) == 96 && sizeof(g1_xyzz) == 128, "point layouts");
@@ -295,6 +296,7 @@ int tsgpu_poly_clone(tsgpu_ctx* ctx, const tsgpu_poly* p, tsgpu_poly** out) {
 }
 void tsgpu_poly_free(tsgpu_ctx* ctx, tsgpu_poly* p) {
     if (!p) return;
+    if (p->ready) { if (ctx) cudaStreamWaitEvent(ctx->stream, p->ready, 0); else cudaEventSynchronize(p->ready); cudaEventDestroy(p->ready); }
     if (p->d) cudaFreeAsync(p->d, ctx ? ctx->stream : nullptr);
     delete p;
 }
@@ -333,6 +335,38 @@ int tsgpu_poly_upload_padded(tsgpu_ctx* ctx, const tsgpu_fr* vals, size_t n, siz
     *out = p;
     return TSGPU_OK;
 }
+
+// same vector, but the host -> device copy runs on the context's side stream and the call returns without waiting for it: whatever is enqueued
+// on the context afterwards overlaps the transfer.  Nothing in the library waits for the copy by itself - call tsgpu_poly_wait before the first use.
+int tsgpu_poly_upload_padded_async(tsgpu_ctx* ctx, const tsgpu_fr* vals, size_t n, size_t padded, tsgpu_poly** out) {
+    if (!ctx || !out || (!vals && n) || padded < n) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "bad argument");
+    if (!ctx->copy_stream) TSG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    tsgpu_poly* p = new (std::nothrow) tsgpu_poly;
+    if (!p) return fail(ctx, TSGPU_E_PROOF_GENERATION, "out of host memory");
+    p->n = padded;
+    cudaError_t e = cudaMallocAsync((void**)&p->d, (padded ? padded : 1) * sizeof(fr_t), ctx->stream);
+    if (e != cudaSuccess) { delete p; return cuda_fail(ctx, e, "cudaMallocAsync(poly)"); }
+    cudaEvent_t allocated = nullptr;
+    e = cudaEventCreateWithFlags(&allocated, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ready, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(allocated, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, allocated, 0);     // the side stream may touch the block once the allocation is ordered
+    if (e == cudaSuccess && padded > n) e = cudaMemsetAsync(p->d + n, 0, (padded - n) * sizeof(fr_t), ctx->copy_stream);
+    if (e == cudaSuccess && n) e = cudaMemcpyAsync(p->d, vals, n * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->copy_stream);
+    if (e == cudaSuccess) e = cudaEventRecord(p->ready, ctx->copy_stream);
+    if (allocated) cudaEventDestroy(allocated);
+    if (e != cudaSuccess) { tsgpu_poly_free(ctx, p); return cuda_fail(ctx, e, "side-stream upload"); }
+    *out = p;
+    return TSGPU_OK;
+}
+int tsgpu_poly_wait(tsgpu_ctx* ctx, tsgpu_poly* p) {
+    if (!ctx || !p) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");
+    if (!p->ready) return TSGPU_OK;
+    TSG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, p->ready, 0));
+    cudaEventDestroy(p->ready); p->ready = nullptr;
+    return TSGPU_OK;
+}
+int tsgpu_poly_in_flight(const tsgpu_poly* p) { return p && p->ready ? 1 : 0; }
 
 // ------------------------------------------------------------------------------------------- interpolation
 static int log2_exact(size_t n) { int l = 0; while (((size_t)1 << l) < n) ++l; return ((size_t)1 << l) == n ? l : -1; }

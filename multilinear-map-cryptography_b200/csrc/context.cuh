@@ -14,6 +14,8 @@ struct tsgpu_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t copy_stream = nullptr;   // side stream of tsgpu_poly_upload_padded_async (created on first use)
+    bool h2d_overlap = true;              // Twist::prove from host buffers: the value vector travels while the address vector is committed (tuning "h2d_overlap")
     int sm_count = 0;
     std::string err;
     uint64_t launches = 0;

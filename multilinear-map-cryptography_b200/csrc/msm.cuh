@@ -5,7 +5,10 @@
 
 namespace tsg {
 
-constexpr unsigned MSM_CHUNK = 64;        // max entries one work item adds into its accumulator (bounds the serial chain of one thread)
+#ifndef TSG_MSM_CHUNK
+#define TSG_MSM_CHUNK 64
+#endif
+constexpr unsigned MSM_CHUNK = TSG_MSM_CHUNK;       // max entries one work item adds into its accumulator (bounds the serial chain of one thread)
 constexpr int MSM_ACC_THREADS = 128;
 constexpr unsigned MSM_RED_SPAN = 32;     // most buckets per thread in the window reduction (2 x span additions deep; the bit-decomposed tail costs
                                           // log2(buckets / span) / 2 additions per span); small bucket sets use shorter spans to keep the chain short

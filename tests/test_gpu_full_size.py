@@ -46,6 +46,37 @@ def test_twist_2p20_ops_verifies_and_both_paths_agree(ctx, tsgpu, params18):
     assert not twist.verify(proof, vp)
 
 
+def test_twist_2p20_overlapped_upload_gives_the_same_bytes(ctx, tsgpu, params18):
+    """Twist::prove from host buffers commits the address vector while the values travel on a side stream (h2d_overlap, traces of >= 24 MiB of values):
+    same bytes as with the plain upload + one batched commit pass; a vector may be freed while its copy is in flight."""
+    import ctypes as C
+    bd = importlib.import_module(PKG + ".binding")
+    pp, vp = params18
+    for n in (1 << 20, (1 << 20) - 12345):
+        addr, vals_u64, isw = _trace(n, 1 << 16, 21)
+        vals = tsgpu.fe_vec(vals_u64)
+        twist = tsgpu.Twist.new(pp)
+        a = twist.prove_arrays(addr, vals, isw).to_bytes()
+        try:
+            ctx.set_tuning("h2d_overlap", 0)
+            b = twist.prove_arrays(addr, vals, isw).to_bytes()
+        finally:
+            ctx.set_tuning("h2d_overlap", 1)
+        assert a == b
+    h = C.c_void_p()
+    ctx.check(tsgpu.lib().tsgpu_poly_upload_padded_async(ctx._h, bd._p(vals), C.c_size_t(n), C.c_size_t(1 << 20), C.byref(h)))
+    assert tsgpu.lib().tsgpu_poly_in_flight(h) == 1
+    tsgpu.lib().tsgpu_poly_free(ctx._h, h)                      # freed while the copy may still run: the free is ordered behind it
+    h = C.c_void_p()
+    ctx.check(tsgpu.lib().tsgpu_poly_upload_padded_async(ctx._h, bd._p(vals), C.c_size_t(n), C.c_size_t(1 << 20), C.byref(h)))
+    ctx.check(tsgpu.lib().tsgpu_poly_wait(ctx._h, h))
+    assert tsgpu.lib().tsgpu_poly_in_flight(h) == 0
+    out = np.empty((1 << 20, 4), dtype=np.uint64)
+    ctx.check(tsgpu.lib().tsgpu_poly_download(ctx._h, h, bd._p(out)))
+    assert (out[:n] == vals).all() and not out[n:].any()
+    tsgpu.lib().tsgpu_poly_free(ctx._h, h)
+
+
 def test_twist_2p20_full_width_values_and_ragged_length(ctx, tsgpu, oracle, params18):
     """field-sized memory values (the short-scalar tables must be bypassed) and a length that is not a power of two (zero padding)"""
     pp, vp = params18
