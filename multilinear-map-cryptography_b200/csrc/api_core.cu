@@ -108,6 +108,7 @@ int tsgpu_init(int device, void* stream, tsgpu_ctx** out) {
               cudaMalloc((void**)&ctx->dev_out, 8 * sizeof(fr_t)) == cudaSuccess &&
               cudaMallocHost((void**)&ctx->host_out, 8 * sizeof(fr_t)) == cudaSuccess &&
               cudaMallocHost((void**)&ctx->host_scratch, 64 * sizeof(fr_t)) == cudaSuccess &&
+              cudaMallocHost((void**)&ctx->host_msm, tsgpu_ctx::HOST_MSM_BYTES) == cudaSuccess &&
               cudaHostAlloc((void**)&ctx->tail_box, sizeof(ScTailBox), cudaHostAllocMapped) == cudaSuccess &&
               cudaMemset(ctx->ticket, 0, 64) == cudaSuccess;
     if (!ok) { cudaGetLastError(); tsgpu_destroy(ctx); return TSGPU_E_PROOF_GENERATION; }
@@ -127,6 +128,7 @@ void tsgpu_destroy(tsgpu_ctx* ctx) {
     if (ctx->dev_out) cudaFree(ctx->dev_out);
     if (ctx->host_out) cudaFreeHost(ctx->host_out);
     if (ctx->host_scratch) cudaFreeHost(ctx->host_scratch);
+    if (ctx->host_msm) cudaFreeHost(ctx->host_msm);
     if (ctx->tail_box) cudaFreeHost(ctx->tail_box);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -143,6 +145,7 @@ uint64_t tsgpu_counter_read(const tsgpu_ctx* ctx, const char* name) {
     if (!strcmp(name, "msm_calls")) return ctx->msm_calls;
     if (!strcmp(name, "msm_points")) return ctx->msm_points;
     if (!strcmp(name, "msm_entries")) return ctx->msm_entries;
+    if (!strcmp(name, "msm_slot_overflows")) return ctx->msm_slot_overflows;
     return 0;
 }
 int tsgpu_synchronize(tsgpu_ctx* ctx) {
@@ -177,6 +180,7 @@ int tsgpu_set_tuning(tsgpu_ctx* ctx, const char* key, long value) {
     if (!strcmp(key, "deferred_claim_check")) { ctx->deferred_claim_check = value != 0; return TSGPU_OK; }
     if (!strcmp(key, "kernel_timing")) { ctx->timing = value != 0; return TSGPU_OK; }
     if (!strcmp(key, "msm_quad_tree")) { tsg::msm_set_quad_tree(value != 0); return TSGPU_OK; }   // 0: tree levels of the window reduction with one thread per addition (process-wide)
+    if (!strcmp(key, "msm_slotted")) { ctx->msm_slotted = value != 0; return TSGPU_OK; }
     if (!strcmp(key, "h2d_overlap")) { ctx->h2d_overlap = value != 0; return TSGPU_OK; }
     if (!strcmp(key, "msm_tables")) { ctx->msm_tables = value != 0; return TSGPU_OK; }   // 0: per-window bucket sets on the plain SRS points
     if (!strcmp(key, "eval_basis")) { ctx->eval_basis = value != 0; return TSGPU_OK; }   // 0: Twist/Shout::prove interpolate and commit coefficients

@@ -46,6 +46,7 @@ struct MsmBasis { const g1_affine* pts; size_t n; const g1_affine* table; unsign
 struct tsgpu_poly {
     fr_t* d = nullptr;        // n coefficients, low -> high, natural order
     size_t n = 0;
+    bool short64 = false;          // every entry is known to fit 64 bits (built by tsgpu_poly_from_u64 and not modified since): the commit pass skips its probe
     cudaEvent_t ready = nullptr;   // set while a side-stream upload is in flight (tsgpu_poly_upload_padded_async): tsgpu_poly_wait orders the context's stream behind it
 };
 
@@ -68,7 +69,8 @@ G1J combine_windows(const g1_jac* win, unsigned W, unsigned c) {
 // K independent device MSMs in one pass (bases and scalars resident); results to the host as Jacobian points.
 // Mode: precomputed tables (one shared bucket set per job) when every job has a table of the same window width and uses at
 // least a quarter of it; otherwise per-window bucket sets on the plain points.
-int msm_device_batch(tsgpu_ctx* ctx, int K, const MsmBasis* basis, const fr_t* const* scalars, const size_t* n, tsgpu_g1* out, bool maybe_short = false) {
+int msm_device_batch(tsgpu_ctx* ctx, int K, const MsmBasis* basis, const fr_t* const* scalars, const size_t* n, tsgpu_g1* out, bool maybe_short = false,
+                     bool known_short = false) {
     size_t nmax = 0;
     for (int k = 0; k < K; ++k) nmax = n[k] > nmax ? n[k] : nmax;
     if (nmax == 0) { G1J id = G1J::identity(); for (int k = 0; k < K; ++k) memcpy(&out[k], &id, 96); return TSGPU_OK; }
@@ -80,7 +82,7 @@ int msm_device_batch(tsgpu_ctx* ctx, int K, const MsmBasis* basis, const fr_t* c
     if (maybe_short && shared) {
         use_short = true;
         for (int k = 0; k < K; ++k) use_short = use_short && basis[k].short_table && basis[k].short_c == basis[0].short_c;
-        if (use_short) {
+        if (use_short && !known_short) {
             unsigned* flag = (unsigned*)(ctx->dev_out + 7);   // last result slot doubles as the probe flag
             TSG_CUDA(ctx, cudaMemsetAsync(flag, 0, 4, ctx->stream));
             for (int k = 0; k < K; ++k) TSG_CUDA(ctx, launch_scalar_probe(scalars[k], n[k], flag, ctx->sm_count, ctx->stream));
@@ -93,35 +95,51 @@ int msm_device_batch(tsgpu_ctx* ctx, int K, const MsmBasis* basis, const fr_t* c
     }
     const unsigned c = use_short ? basis[0].short_c : shared ? basis[0].table_c : msm_window_bits(nmax);
     MsmLayout L;
-    size_t bytes = msm_scratch_bytes(nmax, K, c, shared, &L, use_short ? basis[0].short_windows : 0);
-    cudaError_t aerr;
-    unsigned char* scratch_p = (unsigned char*)arena_get(ctx, tsgpu_ctx::ARENA_MSM, bytes, &aerr);
-    if (!scratch_p) return cuda_fail(ctx, aerr, "cudaMalloc(msm scratch)");
-    MsmJob jobs[MSM_MAX_BATCH];
-    for (int k = 0; k < K; ++k) jobs[k] = MsmJob{use_short ? basis[k].short_table : shared ? basis[k].table : basis[k].pts, basis[k].n, scalars[k], n[k]};
-    unsigned launches = 0;
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    if (ctx->timing) for (auto& x : ev) cudaEventCreate(&x);
-    {
-        KernelTimer kt(ctx, "msm_total");
-        TSG_CUDA(ctx, msm_run(jobs, K, L, scratch_p, ctx->sm_count, ctx->stream, &launches, ctx->timing ? ev : nullptr));
-    }
-    if (ctx->timing) {
-        // four phases share five events (timers_collect destroys each event once)
-        static const char* names[4] = {"msm_sort", "msm_accumulate", "msm_merge", "msm_reduce"};
-        for (int k = 0; k < 4; ++k) ctx->pending.push_back({names[k], ev[k], ev[k + 1]});
+    std::vector<g1_jac> raw;
+    unsigned counts[4] = {0, 0, 0, 0};   // work items, bucket entries, largest chunk count, slotted-sort overflow flag
+    unsigned char* scratch_p = nullptr;
+    // full-width scalars over window tables go through the slotted sort first; a bucket overflowing its slots (skewed scalars) reruns the pass through the counting sort
+    for (int attempt = (shared && !use_short && ctx->msm_slotted) ? 0 : 1; attempt < 2; ++attempt) {
+        size_t bytes = msm_scratch_bytes(nmax, K, c, shared, &L, use_short ? basis[0].short_windows : 0, attempt == 0);
+        cudaError_t aerr;
+        scratch_p = (unsigned char*)arena_get(ctx, tsgpu_ctx::ARENA_MSM, bytes, &aerr);
+        if (!scratch_p) return cuda_fail(ctx, aerr, "cudaMalloc(msm scratch)");
+        MsmJob jobs[MSM_MAX_BATCH];
+        for (int k = 0; k < K; ++k) jobs[k] = MsmJob{use_short ? basis[k].short_table : shared ? basis[k].table : basis[k].pts, basis[k].n, scalars[k], n[k]};
+        unsigned launches = 0;
+        cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+        if (ctx->timing) for (auto& x : ev) cudaEventCreate(&x);
+        {
+            KernelTimer kt(ctx, "msm_total");
+            TSG_CUDA(ctx, msm_run(jobs, K, L, scratch_p, ctx->sm_count, ctx->stream, &launches, ctx->timing ? ev : nullptr));
+        }
+        if (ctx->timing) {
+            // four phases share five events (timers_collect destroys each event once)
+            static const char* names[4] = {"msm_sort", "msm_accumulate", "msm_merge", "msm_reduce"};
+            for (int k = 0; k < 4; ++k) ctx->pending.push_back({names[k], ev[k], ev[k + 1]});
+        }
+        ctx->launches += launches;
+        raw.resize((size_t)L.sets * (L.span_bits + 2));
+        const size_t raw_bytes = raw.size() * sizeof(g1_jac);
+        if (raw_bytes + sizeof(counts) <= tsgpu_ctx::HOST_MSM_BYTES) {        // through the pinned staging block: two plain DMA transfers
+            TSG_CUDA(ctx, cudaMemcpyAsync(ctx->host_msm, scratch_p + L.window_out, raw_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+            TSG_CUDA(ctx, cudaMemcpyAsync(ctx->host_msm + raw_bytes, scratch_p + L.n_items, sizeof(counts), cudaMemcpyDeviceToHost, ctx->stream));
+            TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            memcpy(raw.data(), ctx->host_msm, raw_bytes); memcpy(counts, ctx->host_msm + raw_bytes, sizeof(counts));
+        } else {
+            TSG_CUDA(ctx, cudaMemcpyAsync(raw.data(), scratch_p + L.window_out, raw_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+            TSG_CUDA(ctx, cudaMemcpyAsync(counts, scratch_p + L.n_items, sizeof(counts), cudaMemcpyDeviceToHost, ctx->stream));
+            TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+        timers_collect(ctx);
+        if (!(L.cap_log2 && counts[3])) break;
+        ctx->msm_slot_overflows += 1;
     }
     for (int k = 0; k < K; ++k) ctx->msm_points += n[k];
-    ctx->launches += launches;
     const unsigned per_set = L.span_bits + 2;
-    std::vector<g1_jac> raw((size_t)L.sets * per_set), win(L.sets);
-    unsigned counts[2] = {0, 0};   // work items, bucket entries
-    TSG_CUDA(ctx, cudaMemcpyAsync(raw.data(), scratch_p + L.window_out, raw.size() * sizeof(g1_jac), cudaMemcpyDeviceToHost, ctx->stream));
-    TSG_CUDA(ctx, cudaMemcpyAsync(counts, scratch_p + L.n_items, sizeof(counts), cudaMemcpyDeviceToHost, ctx->stream));
-    TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<g1_jac> win(L.sets);
     ctx->msm_entries += counts[1];
     ctx->msm_calls += 1;
-    timers_collect(ctx);
     // bucket-set sums: S = span * sum_k 2^k P[k] + P[span_bits] + P[span_bits + 1]  (Horner over the index-bit sums, then the span-local part)
     unsigned logS = 0; while ((1u << logS) < L.span) ++logS;
     for (unsigned w = 0; w < L.sets; ++w) {
@@ -291,6 +309,7 @@ int tsgpu_poly_clone(tsgpu_ctx* ctx, const tsgpu_poly* p, tsgpu_poly** out) {
     cudaError_t e = cudaMallocAsync((void**)&c->d, (p->n ? p->n : 1) * sizeof(fr_t), ctx->stream);
     if (e != cudaSuccess) { delete c; return cuda_fail(ctx, e, "cudaMallocAsync(poly)"); }
     if (p->n) TSG_CUDA(ctx, cudaMemcpyAsync(c->d, p->d, p->n * sizeof(fr_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    c->short64 = p->short64;
     *out = c;
     return TSGPU_OK;
 }
@@ -318,6 +337,7 @@ int tsgpu_poly_from_u64(tsgpu_ctx* ctx, const uint64_t* v, size_t n, size_t padd
         ctx->launches += 1;
     }
     TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    p->short64 = true;
     *out = p;
     return TSGPU_OK;
 }
@@ -386,6 +406,7 @@ int tsgpu_poly_interpolate_iota(tsgpu_ctx* ctx, tsgpu_poly* p) {
     if (l < 0) return fail(ctx, TSGPU_E_POLYNOMIAL, "interpolation length must be a power of two (Twist/Shout pad first)");
     if (l > 27) return fail(ctx, TSGPU_E_POLYNOMIAL, "interpolation size exceeds the 2^28 two-adicity of Fr");
     KernelTimer kt(ctx, "interpolate");
+    p->short64 = false;   // coefficients are field-sized
     TSG_CUDA(ctx, interp_run(ctx, p->d, (unsigned)l, p->d));
     return TSGPU_OK;
 }
@@ -768,7 +789,9 @@ int tsgpu_kzg_commit_values_batch_dev(tsgpu_ctx* ctx, const tsgpu_srs* srs, cons
             basis[i] = lagrange_msm_basis(srs, n[i]);
         }
     }
-    return msm_device_batch(ctx, (int)count, basis, sc, n, outs, /*maybe_short=*/true);
+    bool known_short = count > 0;
+    for (size_t i = 0; i < count; ++i) known_short = known_short && values[i]->short64;
+    return msm_device_batch(ctx, (int)count, basis, sc, n, outs, /*maybe_short=*/true, known_short);
 }
 int tsgpu_kzg_commit_values_dev(tsgpu_ctx* ctx, const tsgpu_srs* srs, const tsgpu_poly* values, tsgpu_g1* out) {
     if (!values || !out) return fail(ctx, TSGPU_E_INVALID_PARAMETERS, "null argument");

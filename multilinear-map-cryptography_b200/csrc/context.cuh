@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <nvtx3/nvToolsExt.h>
+#include <chrono>
 #include <cstdint>
 #include <map>
 #include <string>
@@ -25,6 +26,8 @@ struct tsgpu_ctx {
     tsg::fr_t* dev_out = nullptr;      // 8 elements
     tsg::fr_t* host_out = nullptr;     // pinned, 8 elements
     tsg::fr_t* host_scratch = nullptr; // pinned, 64 elements (host leg of the batch inversion, lagrange.cu)
+    unsigned char* host_msm = nullptr; // pinned, HOST_MSM_BYTES: window sums + counters of an MSM pass land here (a pageable target costs a staged copy per transfer)
+    static constexpr size_t HOST_MSM_BYTES = 64 << 10;
     tsg::ScTailBox* tail_box = nullptr; // pinned + mapped mailbox of the persistent sum-check tail (sumcheck.cu)
     bool sc_tail = true;               // d = 2 claim-form rounds on tables that fit one CTA's shared memory run in ONE persistent kernel (tuning "sc_tail")
     void* comm = nullptr;              // multi-GPU communicator (comm.cu), optional
@@ -40,6 +43,8 @@ struct tsgpu_ctx {
     uint64_t msm_points = 0;           // points processed by MSMs (for points/s reporting)
     uint64_t msm_entries = 0;          // bucket entries (non-zero signed digits) = mixed additions of k_msm_accumulate
     uint64_t msm_calls = 0;
+    uint64_t msm_slot_overflows = 0;   // passes that overflowed the slotted sort and were rerun through the counting sort
+    bool msm_slotted = true;           // full-width scalars over window tables are sorted in one pass into fixed slots per bucket (tuning "msm_slotted")
     bool timing = false;
     bool msm_tables = true;            // SRS handles carry precomputed window tables (tuning "msm_tables", read when an SRS / basis is built)
     bool eval_basis = true;            // Twist/Shout::prove commit through the Lagrange-basis SRS when it exists (tuning "eval_basis")
@@ -108,6 +113,16 @@ struct KernelTimer {
         if (!a) return;
         cudaEventRecord(b, ctx->stream);
         ctx->pending.push_back({name, a, b});
+    }
+};
+// host wall clock of a phase of a proving path (includes the device work the phase waits for), folded into ctx->timers under `name` when timing is enabled
+struct WallTimer {
+    tsgpu_ctx* ctx; const char* name; std::chrono::steady_clock::time_point t0;
+    WallTimer(tsgpu_ctx* c, const char* n) : ctx(c), name(n), t0(std::chrono::steady_clock::now()) {}
+    ~WallTimer() {
+        if (!ctx || !ctx->timing) return;
+        auto& t = ctx->timers[name];
+        t.first += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); t.second += 1;
     }
 };
 void timers_collect(tsgpu_ctx* ctx);   // after a stream synchronisation: fold finished event pairs into ctx->timers

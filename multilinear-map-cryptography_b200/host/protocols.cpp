@@ -57,7 +57,7 @@ int prove_two_vectors(tsgpu_ctx* ctx, const tsgpu_params* params, tsgpu_poly* pa
                       tsgpu_srs_lagrange_prepare(ctx, params->srs, tsgpu_poly_len(pa)) == TSGPU_OK &&
                       tsgpu_srs_lagrange_prepare(ctx, params->srs, tsgpu_poly_len(pb)) == TSGPU_OK;
     if (!eval_basis) {
-        if ((rc = tsgpu_poly_wait(ctx, pb))) return rc;
+        if ((rc = tsgpu_poly_wait(ctx, pa)) || (rc = tsgpu_poly_wait(ctx, pb))) return rc;
         if ((rc = tsgpu_poly_interpolate_iota(ctx, pa))) return rc;            // vector_to_polynomial
         if ((rc = tsgpu_poly_interpolate_iota(ctx, pb))) return rc;
     }
@@ -65,18 +65,25 @@ int prove_two_vectors(tsgpu_ctx* ctx, const tsgpu_params* params, tsgpu_poly* pa
     if (!pr) return fail(ctx, TSGPU_E_PROOF_GENERATION, "out of host memory");
     memset(&pr->opening_point, 0, 32);
     const tsgpu_poly* both[2] = {pa, pb};
-    if (eval_basis && tsgpu_poly_in_flight(pb)) {
-        // pb is still travelling on the side stream (tsgpu_twist_prove from host buffers): commit pa alone while it does, then pb.  Two passes instead
-        // of one batched pass cost ~0.25 ms of device time at 2^20 operations and hide ~0.45 ms of the 0.6 ms transfer.
-        rc = tsgpu_kzg_commit_values_batch_dev(ctx, params->srs, &both[0], 1, &pr->commitments[0]);
-        if (!rc) rc = tsgpu_poly_wait(ctx, pb);
-        if (!rc) rc = tsgpu_kzg_commit_values_batch_dev(ctx, params->srs, &both[1], 1, &pr->commitments[1]);
+    {
+    WallTimer wt(ctx, "wall_commit");
+    if (eval_basis && (tsgpu_poly_in_flight(pa) || tsgpu_poly_in_flight(pb))) {
+        // one vector is still travelling on the side stream (tsgpu_twist_prove / tsgpu_shout_prove from host buffers): commit the resident one alone while it
+        // does, then the other.  Two passes instead of one batched pass cost ~0.25 ms of device time at 2^20 operations and hide most of the 0.6 ms transfer.
+        const int first = tsgpu_poly_in_flight(pa) ? 1 : 0, second = 1 - first;
+        tsgpu_poly* late = second ? pb : pa;
+        rc = tsgpu_kzg_commit_values_batch_dev(ctx, params->srs, &both[first], 1, &pr->commitments[first]);
+        if (!rc) rc = tsgpu_poly_wait(ctx, late);
+        if (!rc) rc = tsgpu_kzg_commit_values_batch_dev(ctx, params->srs, &both[second], 1, &pr->commitments[second]);
     } else {
-        rc = tsgpu_poly_wait(ctx, pb);
+        rc = tsgpu_poly_wait(ctx, pa);
+        if (!rc) rc = tsgpu_poly_wait(ctx, pb);
         if (!rc) rc = eval_basis ? tsgpu_kzg_commit_values_batch_dev(ctx, params->srs, both, 2, pr->commitments)     // both commitments in one MSM pass
                                  : tsgpu_kzg_commit_batch_dev(ctx, params->srs, both, 2, pr->commitments);
     }
+    }
     if (rc) { delete pr; return rc; }
+    WallTimer* wtr = new WallTimer(ctx, "wall_transcript");
     Transcript tr(params->fiat_shamir_seed);
     tsgpu_fr h;
     tsgpu_g1_hash(&pr->commitments[0], &h); tr.append_field_element(label_a, fr_of(h));
@@ -92,7 +99,9 @@ int prove_two_vectors(tsgpu_ctx* ctx, const tsgpu_params* params, tsgpu_poly* pa
     }
     pr->final_evaluation = abi_of(fr_t::zero());
     std::vector<fr_t> ch = tr.challenge_field_elements("opening_challenges", rounds);   // twist.rs:219
+    delete wtr;
     if (!ch.empty()) {                                                                  // twist.rs:226-243
+        WallTimer wt(ctx, "wall_open");
         tsgpu_fr z = abi_of(ch[0]);
         pr->opening_point = z;
         if (eval_basis) {
@@ -246,13 +255,17 @@ int prove_two_vectors_sharded(tsgpu_ctx* ctx, const tsgpu_params* params, tsgpu_
     };
     int rc;
     tsgpu_g1 part[2];
-    if (same) rc = tsgpu_kzg_commit_values_slice_batch_dev(ctx, params->srs, ma, first[0], both, 2, part);
-    else {
-        rc = tsgpu_kzg_commit_values_slice_batch_dev(ctx, params->srs, m[0], first[0], &both[0], 1, &part[0]);
-        if (!rc) rc = tsgpu_kzg_commit_values_slice_batch_dev(ctx, params->srs, m[1], first[1], &both[1], 1, &part[1]);
+    {
+        WallTimer wt(ctx, "wall_commit");
+        if (same) rc = tsgpu_kzg_commit_values_slice_batch_dev(ctx, params->srs, ma, first[0], both, 2, part);
+        else {
+            rc = tsgpu_kzg_commit_values_slice_batch_dev(ctx, params->srs, m[0], first[0], &both[0], 1, &part[0]);
+            if (!rc) rc = tsgpu_kzg_commit_values_slice_batch_dev(ctx, params->srs, m[1], first[1], &both[1], 1, &part[1]);
+        }
     }
-    if (!rc) rc = sum_over_ranks(part, pr->commitments);
+    if (!rc) { WallTimer wt(ctx, "wall_exchange"); rc = sum_over_ranks(part, pr->commitments); }
     if (!rc) {
+        WallTimer* wtr = new WallTimer(ctx, "wall_transcript");
         Transcript tr(params->fiat_shamir_seed);
         tsgpu_fr h;
         tsgpu_g1_hash(&pr->commitments[0], &h); tr.append_field_element(label_a, fr_of(h));
@@ -265,17 +278,19 @@ int prove_two_vectors_sharded(tsgpu_ctx* ctx, const tsgpu_params* params, tsgpu_
         }
         pr->final_evaluation = abi_of(fr_t::zero());
         std::vector<fr_t> ch = tr.challenge_field_elements("opening_challenges", rounds);
+        delete wtr;
         if (!ch.empty()) {
             tsgpu_fr z = abi_of(ch[0]);
             pr->opening_point = z;
             tsgpu_fr vs[2]; tsgpu_g1 pis[2];
             if (same) {
                 tsgpu_fr mine[3];                               // product of this rank's (z - j), partial sums of the two vectors
-                rc = tsgpu_kzg_open_values_slice_partial(ctx, ma, first[0], both, 2, &z, mine);
+                { WallTimer wt(ctx, "wall_open_partial"); rc = tsgpu_kzg_open_values_slice_partial(ctx, ma, first[0], both, 2, &z, mine); }
                 std::vector<tsgpu_fr> all(3 * G);
-                if (!rc) rc = tsgpu_comm_allgather(ctx, mine, sizeof(mine), all.data());
+                if (!rc) { WallTimer wt(ctx, "wall_exchange"); rc = tsgpu_comm_allgather(ctx, mine, sizeof(mine), all.data()); }
                 if (!rc) {
                     combine(all, 3, 2, vs);
+                    WallTimer wt(ctx, "wall_open_finish");
                     rc = tsgpu_kzg_open_values_slice_finish(ctx, params->srs, ma, first[0], both, 2, vs, part);
                 }
             } else {
@@ -290,7 +305,7 @@ int prove_two_vectors_sharded(tsgpu_ctx* ctx, const tsgpu_params* params, tsgpu_
                     }
                 }
             }
-            if (!rc) rc = sum_over_ranks(part, pis);
+            if (!rc) { WallTimer wt(ctx, "wall_exchange"); rc = sum_over_ranks(part, pis); }
             if (!rc) for (int i = 0; i < 2; ++i) { pr->opening_proofs.push_back(pis[i]); pr->final_evaluations.push_back(vs[i]); }
         }
     }
@@ -361,8 +376,10 @@ int tsgpu_shout_prove(tsgpu_ctx* ctx, const tsgpu_params* params, const tsgpu_fr
     const size_t table_size = next_pow2(num_entries);                       // shout.rs:105
     const size_t lookups_size = next_pow2(num_lookups);                     // shout.rs:116
     tsgpu_poly *pt = nullptr, *pi = nullptr;
-    int rc = tsgpu_poly_upload_padded(ctx, entries, num_entries, table_size, &pt);
-    if (!rc) rc = tsgpu_poly_from_u64(ctx, lookup_indices, num_lookups, lookups_size, &pi);
+    // (committing the index vector while the table travels on the side stream, as tsgpu_twist_prove does with its values, was measured on C3 - 2^20 entries, 2^22
+    //  lookups - and did not pay: 19.14 against 18.95 ms; the two commit passes of different lengths batch too well)
+    int rc = tsgpu_poly_from_u64(ctx, lookup_indices, num_lookups, lookups_size, &pi);
+    if (!rc) rc = tsgpu_poly_upload_padded(ctx, entries, num_entries, table_size, &pt);
     if (!rc) rc = prove_two_vectors(ctx, params, pt, pi, "table_commitment", "index_commitment", log2_of(lookups_size), out);
     tsgpu_poly_free(ctx, pt); tsgpu_poly_free(ctx, pi);
     return rc;

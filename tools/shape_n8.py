@@ -26,4 +26,4 @@ ctx.synchronize(); t0 = time.perf_counter()
 for _ in range(reps):
     tw.prove_sharded(addr, vals, n)
 ctx.synchronize(); dt = (time.perf_counter() - t0) / reps
-print({"log_ops": log_n, "ms_per_proof_wall": dt * 1e3, **{k: ctx.timer_read(k)[0] / reps for k in ("msm_total", "msm_sort", "msm_accumulate", "msm_merge", "msm_reduce", "open_bary")}})
+print({"log_ops": log_n, "ms_per_proof_wall": dt * 1e3, **{k: ctx.timer_read(k)[0] / reps for k in ("msm_total", "msm_sort", "msm_accumulate", "msm_merge", "msm_reduce", "open_bary", "wall_commit", "wall_exchange", "wall_transcript", "wall_open_partial", "wall_open_finish")}})
