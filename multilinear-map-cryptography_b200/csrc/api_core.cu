@@ -145,7 +145,6 @@ uint64_t tsgpu_counter_read(const tsgpu_ctx* ctx, const char* name) {
     if (!strcmp(name, "msm_calls")) return ctx->msm_calls;
     if (!strcmp(name, "msm_points")) return ctx->msm_points;
     if (!strcmp(name, "msm_entries")) return ctx->msm_entries;
-    if (!strcmp(name, "msm_slot_overflows")) return ctx->msm_slot_overflows;
     return 0;
 }
 int tsgpu_synchronize(tsgpu_ctx* ctx) {
@@ -180,7 +179,6 @@ int tsgpu_set_tuning(tsgpu_ctx* ctx, const char* key, long value) {
     if (!strcmp(key, "deferred_claim_check")) { ctx->deferred_claim_check = value != 0; return TSGPU_OK; }
     if (!strcmp(key, "kernel_timing")) { ctx->timing = value != 0; return TSGPU_OK; }
     if (!strcmp(key, "msm_quad_tree")) { tsg::msm_set_quad_tree(value != 0); return TSGPU_OK; }   // 0: tree levels of the window reduction with one thread per addition (process-wide)
-    if (!strcmp(key, "msm_slotted")) { ctx->msm_slotted = value != 0; return TSGPU_OK; }
     if (!strcmp(key, "h2d_overlap")) { ctx->h2d_overlap = value != 0; return TSGPU_OK; }
     if (!strcmp(key, "msm_tables")) { ctx->msm_tables = value != 0; return TSGPU_OK; }   // 0: per-window bucket sets on the plain SRS points
     if (!strcmp(key, "eval_basis")) { ctx->eval_basis = value != 0; return TSGPU_OK; }   // 0: Twist/Shout::prove interpolate and commit coefficients

@@ -96,11 +96,10 @@ int msm_device_batch(tsgpu_ctx* ctx, int K, const MsmBasis* basis, const fr_t* c
     const unsigned c = use_short ? basis[0].short_c : shared ? basis[0].table_c : msm_window_bits(nmax);
     MsmLayout L;
     std::vector<g1_jac> raw;
-    unsigned counts[4] = {0, 0, 0, 0};   // work items, bucket entries, largest chunk count, slotted-sort overflow flag
+    unsigned counts[2] = {0, 0};   // work items, bucket entries
     unsigned char* scratch_p = nullptr;
-    // full-width scalars over window tables go through the slotted sort first; a bucket overflowing its slots (skewed scalars) reruns the pass through the counting sort
-    for (int attempt = (shared && !use_short && ctx->msm_slotted) ? 0 : 1; attempt < 2; ++attempt) {
-        size_t bytes = msm_scratch_bytes(nmax, K, c, shared, &L, use_short ? basis[0].short_windows : 0, attempt == 0);
+    {
+        size_t bytes = msm_scratch_bytes(nmax, K, c, shared, &L, use_short ? basis[0].short_windows : 0);
         cudaError_t aerr;
         scratch_p = (unsigned char*)arena_get(ctx, tsgpu_ctx::ARENA_MSM, bytes, &aerr);
         if (!scratch_p) return cuda_fail(ctx, aerr, "cudaMalloc(msm scratch)");
@@ -132,8 +131,6 @@ int msm_device_batch(tsgpu_ctx* ctx, int K, const MsmBasis* basis, const fr_t* c
             TSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         }
         timers_collect(ctx);
-        if (!(L.cap_log2 && counts[3])) break;
-        ctx->msm_slot_overflows += 1;
     }
     for (int k = 0; k < K; ++k) ctx->msm_points += n[k];
     const unsigned per_set = L.span_bits + 2;

@@ -43,8 +43,6 @@ struct tsgpu_ctx {
     uint64_t msm_points = 0;           // points processed by MSMs (for points/s reporting)
     uint64_t msm_entries = 0;          // bucket entries (non-zero signed digits) = mixed additions of k_msm_accumulate
     uint64_t msm_calls = 0;
-    uint64_t msm_slot_overflows = 0;   // passes that overflowed the slotted sort and were rerun through the counting sort
-    bool msm_slotted = true;           // full-width scalars over window tables are sorted in one pass into fixed slots per bucket (tuning "msm_slotted")
     bool timing = false;
     bool msm_tables = true;            // SRS handles carry precomputed window tables (tuning "msm_tables", read when an SRS / basis is built)
     bool eval_basis = true;            // Twist/Shout::prove commit through the Lagrange-basis SRS when it exists (tuning "eval_basis")

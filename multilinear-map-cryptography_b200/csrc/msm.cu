@@ -12,7 +12,6 @@
 // Integer-pipe bound: ~ n * W * 10 Fq products; memory traffic is the 64-byte gathers of step 3.
 #include <cstdio>
 #include <cstdlib>
-#include <cmath>
 #include <cooperative_groups.h>
 #include "fr_device.cuh"
 #include "g1.cuh"
@@ -58,51 +57,6 @@ __global__ void k_msm_digits(const fr_t* scalars, size_t n, unsigned c, unsigned
             if (d && (unsigned)(__ffs(peers) - 1) == (threadIdx.x & 31)) atomicAdd(&hist[key], (unsigned)__popc(peers));
         }
     }
-}
-
-// ---------------------------------------------------------------- 1s. slotted sort: ONE pass, a fixed number of entry slots per bucket
-// Table mode with full-width scalars (the opening quotients): every bucket holds a Poisson-distributed ~26 entries, so bucket b simply owns the
-// 2^cap_log2 slots behind b << cap_log2 and an entry costs ONE atomic (its position) + ONE 4-byte store - instead of the counting sort's histogram
-// atomic, digit round trip, 1 M-counter scan, cursor atomic, offset read and store.  count[] is the histogram the later phases read; a bucket that
-// runs over its slots raises *overflow and the host reruns the pass through the counting sort (skewed scalars; never seen for random ones).
-__global__ void __launch_bounds__(256) k_msm_slot_scatter(const fr_t* scalars, size_t n, unsigned c, unsigned W, unsigned* count, unsigned* slots, unsigned cap_log2,
-                                                          size_t point_stride, unsigned* overflow) {
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    const unsigned nb = 1u << (c - 1), cap = 1u << cap_log2;
-    bool over = false;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const fr_t s = ld256_nc(scalars + i).from_mont();
-        unsigned carry = 0;
-#pragma unroll 4
-        for (unsigned w = 0; w < W; ++w) {
-            const unsigned bit = w * c, limb = bit >> 5, off = bit & 31;
-            unsigned long long two = limb < 8 ? s.l[limb] : 0u;
-            if (limb + 1 < 8) two |= (unsigned long long)s.l[limb + 1] << 32;
-            unsigned d = (unsigned)((two >> off) & ((1u << c) - 1)) + carry;
-            unsigned sign = 0;
-            if (d > nb) { d = (1u << c) - d; sign = 1; carry = 1; } else carry = 0;
-            if (d) {
-                const unsigned pos = atomicAdd(&count[d - 1], 1u);
-                if (pos < cap) slots[((size_t)(d - 1) << cap_log2) + pos] = (unsigned)(w * point_stride + i) | (sign << 31);
-                else over = true;
-            }
-        }
-    }
-    if (over) *overflow = 1u;
-}
-// offsets[b] = b << cap_log2 (what the exclusive scan produces in the counting sort); *entries += sum of the histogram
-// (an overflowed bucket is clamped to its slots: the pass then finishes safely with a wrong sum that the host discards)
-__global__ void __launch_bounds__(256) k_msm_slot_offsets(unsigned* count, size_t nbuckets, unsigned cap_log2, unsigned* offsets, unsigned* entries) {
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    unsigned sum = 0;
-    for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < nbuckets; b += stride) {
-        offsets[b] = (unsigned)(b << cap_log2);
-        unsigned k = count[b];
-        if (k > (1u << cap_log2)) { k = 1u << cap_log2; count[b] = k; }
-        sum += k;
-    }
-    sum = __reduce_add_sync(0xffffffffu, sum);
-    if ((threadIdx.x & 31) == 0 && sum) atomicAdd(entries, sum);
 }
 
 // *flag != 0 afterwards iff some scalar (canonical form) does not fit 64 bits
@@ -618,20 +572,7 @@ unsigned msm_table_window_bits(size_t n) {
     return lg;
 }
 
-// slots per bucket of the slotted sort for n points per job (0: not applicable - use the counting sort).  lambda = the largest expected bucket load: the mean
-// W n / 2^(c-1), plus what the top digit position piles onto the low buckets when it covers only `top` < c - 1 bits of the 254-bit scalars (n / (0.75 * 2^top)).
-unsigned msm_slot_cap_log2(size_t n, unsigned c, unsigned W) {
-    const double nb = (double)((size_t)1 << (c - 1));
-    double lambda = (double)W * (double)n / nb;
-    const int top = 254 - (int)(W - 1) * (int)c;
-    if (top < 1) return 0;
-    if (top < (int)c - 1) lambda += (double)n / (0.75 * (double)((size_t)1 << top));
-    double need = lambda + 7.0 * sqrt(lambda) + 8.0;
-    unsigned lg = 5; while ((double)(1u << lg) < need && lg < 12) ++lg;
-    return lg <= 8 ? lg : 0;   // beyond 256 slots the slot array is too sparse (4-byte stores into distinct DRAM sectors): measured slower than the counting sort (C3: 2^22 points, 1024 slots)
-}
-
-size_t msm_scratch_bytes(size_t nmax, int K, unsigned c, bool shared, MsmLayout* L, unsigned windows, bool slotted) {
+size_t msm_scratch_bytes(size_t nmax, int K, unsigned c, bool shared, MsmLayout* L, unsigned windows) {
     const unsigned W = windows ? windows : (255 + c - 1) / c;   // windows: only the low digit positions are scanned (scalars known to be short)
     const unsigned sets = (unsigned)K * (shared ? 1u : W);            // bucket sets = windows seen by the reduction
     const size_t nb = (size_t)1 << (c - 1), nbuckets = sets * nb;
@@ -650,10 +591,8 @@ size_t msm_scratch_bytes(size_t nmax, int K, unsigned c, bool shared, MsmLayout*
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
     L->c = c; L->W = W; L->K = (unsigned)K; L->sets = sets; L->shared = shared; L->nmax = nmax;
     L->nbuckets = nbuckets; L->max_items = max_items; L->blocks_per_window = (unsigned)(nb / span); L->span = span; L->span_bits = nbits;
-    L->cap_log2 = slotted && shared && !windows ? msm_slot_cap_log2(nmax, c, W) : 0;
-    if (L->cap_log2 && ((nbuckets << L->cap_log2) >> 32)) L->cap_log2 = 0;       // slot offsets are 32 bits
-    L->dig = take(L->cap_log2 ? 0 : entries * 4);
-    L->sorted = take(L->cap_log2 ? (nbuckets << L->cap_log2) * 4 : entries * 4);
+    L->dig = take(entries * 4);
+    L->sorted = take(entries * 4);
     L->hist = take(nbuckets * 4);
     L->offsets = take(nbuckets * 4);
     L->cursor = take(nbuckets * 4);
@@ -699,13 +638,6 @@ cudaError_t msm_run(const MsmJob* jobs, int K, const MsmLayout& L, unsigned char
     const size_t buckets_per_job = (size_t)(L.sets / L.K) * nb;
     MsmBases bases;
     for (int k = 0; k < MSM_MAX_BATCH; ++k) bases.p[k] = k < K ? jobs[k].bases : nullptr;
-    if (L.cap_log2) {
-        // slotted sort (table mode, full-width scalars): one pass; n_items[3] = overflow flag, n_items[1] = bucket entries
-        for (int k = 0; k < K; ++k)
-            k_msm_slot_scatter<<<gridfor(jobs[k].n, 256, cap), 256, 0, s>>>(jobs[k].scalars, jobs[k].n, L.c, L.W, hist + k * buckets_per_job,
-                                                                            sorted + ((size_t)k * buckets_per_job << L.cap_log2), L.cap_log2, jobs[k].stride, n_items + 3);
-        k_msm_slot_offsets<<<gridfor(L.nbuckets, 256, cap), 256, 0, s>>>(hist, L.nbuckets, L.cap_log2, offsets, n_items + 1);
-    } else {
     for (int k = 0; k < K; ++k)
         k_msm_digits<<<gridfor(jobs[k].n, 256, cap), 256, 0, s>>>(jobs[k].scalars, jobs[k].n, L.c, L.W, dig + (size_t)k * L.W * L.nmax,
                                                                    hist + k * buckets_per_job, set_stride);
@@ -713,7 +645,6 @@ cudaError_t msm_run(const MsmJob* jobs, int K, const MsmLayout& L, unsigned char
     for (int k = 0; k < K; ++k)
         k_msm_scatter<<<gridfor((size_t)L.W * jobs[k].n, 256, cap), 256, 0, s>>>(dig + (size_t)k * L.W * L.nmax, jobs[k].n, L.c, L.W, offsets + k * buckets_per_job,
                                                                                  cursor + k * buckets_per_job, sorted, set_stride, L.shared ? jobs[k].stride : 0);
-    }
     k_msm_item_counts<<<gridfor(L.nbuckets, 256, cap), 256, 0, s>>>(hist, L.nbuckets, items, n_items + 2);
     exclusive_scan_u32(items, item_off, L.nbuckets, (unsigned*)(scratch + L.scan_tmp), n_items, s);
     k_msm_item_fill<<<gridfor(L.nbuckets, 256, cap), 256, 0, s>>>(items, item_off, hist, L.nbuckets, item_bucket, len_hist);
@@ -755,7 +686,7 @@ cudaError_t msm_run(const MsmJob* jobs, int K, const MsmLayout& L, unsigned char
         k_msm_bit_finish<<<dim3(slots, L.sets), MSM_FIN_THREADS, 0, s>>>(parts, P, L.span_bits, k0, wout, g_msm_quad_tree);
     }
     if (ev) cudaEventRecord(ev[4], s);
-    if (launches) *launches += L.cap_log2 ? 13 + (unsigned)K : 16 + 2 * (unsigned)K;
+    if (launches) *launches += 16 + 2 * (unsigned)K;
     return cudaGetLastError();
 }
 

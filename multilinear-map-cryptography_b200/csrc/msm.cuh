@@ -30,7 +30,6 @@ struct MsmJob {
 struct MsmBases { const g1_affine* p[MSM_MAX_BATCH]; };
 
 struct MsmLayout {
-    unsigned cap_log2;                                           // > 0: slotted sort - bucket b owns the 2^cap_log2 entry slots behind b << cap_log2 (no counting sort)
     unsigned c, W, K, sets, blocks_per_window, span, span_bits;   // sets = bucket sets = K * (shared ? 1 : W); blocks_per_window = spans per set = 2^span_bits
     bool shared;                                                 // all W digit positions of a job feed one bucket set (needs the precomputed tables)
     size_t nmax, nbuckets, max_items;
@@ -40,7 +39,7 @@ struct MsmLayout {
 void msm_set_quad_tree(int on);
 unsigned msm_window_bits(size_t n);
 unsigned msm_table_window_bits(size_t n);
-size_t msm_scratch_bytes(size_t nmax, int K, unsigned c, bool shared, MsmLayout* L, unsigned windows = 0, bool slotted = false);   // windows > 0: scan only that many low digit positions
+size_t msm_scratch_bytes(size_t nmax, int K, unsigned c, bool shared, MsmLayout* L, unsigned windows = 0);   // windows > 0: scan only that many low digit positions
 // runs every device phase; per bucket set (job-major) span_bits + 2 Jacobian points are left at scratch + L.window_out:
 // S_w = 2^log2(span) * sum_k 2^k P[k] + P[span_bits] + P[span_bits + 1]  (finished on the host: a Horner pass of ~40 group operations)
 cudaError_t msm_run(const MsmJob* jobs, int K, const MsmLayout& L, unsigned char* scratch, int sm_count,

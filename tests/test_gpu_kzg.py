@@ -66,31 +66,6 @@ def test_commit_edge_scalars(ctx, tsgpu, oracle, srs_small):
     assert tsgpu.g1_compress(z).hex() == "00" * 31 + "40" and oracle.fr_to_ints(tsgpu.g1_hash(z)) == [0]
 
 
-def test_one_pass_sort_overflow_reruns_through_the_counting_sort(ctx, tsgpu, oracle):
-    """Full-width scalars over window tables are sorted in ONE pass into fixed slots per bucket (k_msm_slot_scatter; here 2^13 points, 13-bit windows, 256 slots).
-    Random scalars stay there; equal scalars put all 8192 entries of a window into one bucket, overflow the slots, and the pass is rerun through the
-    counting sort - same group element either way, and as with the one-pass sort switched off."""
-    tau, _ = oracle.setup_scalars()
-    n = 1 << 13
-    srs = ctx.srs_generate(tau, n + 1)
-    aff = oracle.g1_batch_to_affine(oracle.setup_g1_powers(n, fast=True))
-    rnd = oracle.chacha_fr_rand(seed_bytes(77), n).reshape(n, 4)
-    over0 = ctx.counter("msm_slot_overflows")
-    got = tsgpu.KZGCommitment.commit(srs, rnd)
-    assert oracle.g1_compress(got) == oracle.g1_compress(oracle.msm_pippenger(aff, rnd))
-    assert ctx.counter("msm_slot_overflows") == over0
-    try:
-        ctx.set_tuning("msm_slotted", 0)
-        assert oracle.g1_compress(tsgpu.KZGCommitment.commit(srs, rnd)) == oracle.g1_compress(got)
-    finally:
-        ctx.set_tuning("msm_slotted", 1)
-    for k, v in enumerate((oracle.R_MOD - 1, 0x1234567890abcdef1234567890abcdef1234567890abcdef1234567890ab % oracle.R_MOD)):
-        poly = oracle.fr_from_ints([v] * n)
-        got = tsgpu.KZGCommitment.commit(srs, poly)
-        assert oracle.g1_compress(got) == oracle.g1_compress(oracle.msm_pippenger(aff, poly))
-        assert ctx.counter("msm_slot_overflows") == over0 + k + 1
-
-
 def test_commit_too_long_is_commitment_error(ctx, tsgpu, oracle, srs_small):
     srs, _ = srs_small
     poly = oracle.fr_from_ints([1] * (len(srs) + 1))
