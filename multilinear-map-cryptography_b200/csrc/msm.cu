@@ -15,6 +15,7 @@
 #include <cooperative_groups.h>
 #include "fr_device.cuh"
 #include "g1.cuh"
+#include <algorithm>
 #include "msm.cuh"
 
 namespace tsg {
@@ -170,18 +171,18 @@ __global__ void k_msm_scatter(const unsigned* dig, size_t n, unsigned c, unsigne
 }
 
 // ---------------------------------------------------------------- work items: slices of at most MSM_CHUNK entries
-__global__ void k_msm_item_counts(const unsigned* hist, size_t nbuckets, unsigned* items, unsigned* max_chunks) {
+__global__ void k_msm_item_counts(const unsigned* hist, size_t nbuckets, unsigned chunk, unsigned* items, unsigned* max_chunks) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     unsigned mx = 0;
     for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < nbuckets; b += stride) {
-        unsigned k = (hist[b] + MSM_CHUNK - 1) / MSM_CHUNK;
+        unsigned k = (hist[b] + chunk - 1) / chunk;
         items[b] = k;
         mx = k > mx ? k : mx;
     }
     mx = __reduce_max_sync(0xffffffffu, mx);
     if ((threadIdx.x & 31) == 0 && mx > 1) atomicMax(max_chunks, mx);
 }
-__global__ void __launch_bounds__(256) k_msm_item_fill(const unsigned* items, const unsigned* item_off, const unsigned* hist, size_t nbuckets,
+__global__ void __launch_bounds__(256) k_msm_item_fill(const unsigned* items, const unsigned* item_off, const unsigned* hist, size_t nbuckets, unsigned chunk,
                                                        unsigned* item_bucket, unsigned* len_hist) {
     // len_hist[MSM_CHUNK - len] counts work items by length (longest first), privatised in shared memory
     __shared__ unsigned sh[MSM_CHUNK + 1];
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__(256) k_msm_item_fill(const unsigned* items, co
         if (k <= 8) {
             for (unsigned j = 0; j < k; ++j) {
                 item_bucket[o + j] = (unsigned)b;
-                unsigned len = cnt - j * MSM_CHUNK; if (len > MSM_CHUNK) len = MSM_CHUNK;
+                unsigned len = cnt - j * chunk; if (len > chunk) len = chunk;
                 atomicAdd(&sh[MSM_CHUNK - len], 1u);
             }
         }
@@ -208,7 +209,7 @@ __global__ void __launch_bounds__(256) k_msm_item_fill(const unsigned* items, co
             const unsigned bb = (unsigned)(b0 + (threadIdx.x & ~31u) + src);
             for (unsigned j = lane; j < kb; j += 32) {
                 item_bucket[ob + j] = bb;
-                unsigned len = cb - j * MSM_CHUNK; if (len > MSM_CHUNK) len = MSM_CHUNK;
+                unsigned len = cb - j * chunk; if (len > chunk) len = chunk;
                 atomicAdd(&sh[MSM_CHUNK - len], 1u);
             }
         }
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_msm_len_scan(const unsigned* l
 // order[] = work items sorted by decreasing length, so that the 32 lanes of a warp of k_msm_accumulate run the
 // same number of additions (bucket loads are Poisson distributed: unsorted, a warp waits for its fullest bucket)
 constexpr int ORDER_TILE = 4;   // items per thread per tile
-__global__ void __launch_bounds__(256) k_msm_order(const unsigned* hist, const unsigned* item_off, const unsigned* item_bucket, const unsigned* n_items,
+__global__ void __launch_bounds__(256) k_msm_order(const unsigned* hist, const unsigned* item_off, const unsigned* item_bucket, const unsigned* n_items, unsigned chunk,
                                                    const unsigned* len_off, unsigned* len_cursor, unsigned* order) {
     __shared__ unsigned sh_cnt[MSM_CHUNK + 1], sh_base[MSM_CHUNK + 1];
     const unsigned M = *n_items;
@@ -242,7 +243,7 @@ __global__ void __launch_bounds__(256) k_msm_order(const unsigned* hist, const u
             key[q] = 0xffffffffu;
             if (it < M) {
                 unsigned b = item_bucket[it];
-                unsigned len = hist[b] - (it - item_off[b]) * MSM_CHUNK; if (len > MSM_CHUNK) len = MSM_CHUNK;
+                unsigned len = hist[b] - (it - item_off[b]) * chunk; if (len > chunk) len = chunk;
                 key[q] = MSM_CHUNK - len;
                 rank[q] = atomicAdd(&sh_cnt[key[q]], 1u);
             }
@@ -260,7 +261,7 @@ __global__ void __launch_bounds__(256) k_msm_order(const unsigned* hist, const u
 // Register allocation: without a min-blocks bound ptxas settles on 122 registers (4 blocks of 128 threads per SM: up to 128 registers fit four), which measured best:
 // 96 registers / 5 blocks (small spills) 4.86 ms, 80 / 6 blocks 5.00 ms, 130 / 3 blocks 5.00 ms against 4.81 ms per 2^20-op proof
 __global__ void __launch_bounds__(MSM_ACC_THREADS) k_msm_accumulate(const MsmBases jobs, unsigned buckets_per_job, const unsigned* sorted, const unsigned* hist, const unsigned* offsets,
-                                                                  const unsigned* item_off, const unsigned* item_bucket, const unsigned* n_items,
+                                                                  const unsigned* item_off, const unsigned* item_bucket, const unsigned* n_items, unsigned chunk,
                                                                   const unsigned* order, g1_xyzz* partial) {
     const unsigned M = *n_items;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -269,7 +270,7 @@ __global__ void __launch_bounds__(MSM_ACC_THREADS) k_msm_accumulate(const MsmBas
         unsigned b = item_bucket[it];
         unsigned k = it - item_off[b];
         unsigned cnt = hist[b], base = offsets[b];
-        unsigned lo = k * MSM_CHUNK, hi = lo + MSM_CHUNK < cnt ? lo + MSM_CHUNK : cnt;
+        unsigned lo = k * chunk, hi = lo + chunk < cnt ? lo + chunk : cnt;
         const g1_affine* bases = jobs.p[b / buckets_per_job];
         g1_xyzz acc = g1_xyzz::identity();
         for (unsigned p = lo; p < hi; ++p) {
@@ -281,13 +282,30 @@ __global__ void __launch_bounds__(MSM_ACC_THREADS) k_msm_accumulate(const MsmBas
     }
 }
 
+// ---------------------------------------------------------------- 3c'. buckets split into a few chunks: one thread per bucket adds its chunks into the first one
+// (the common case: Poisson tails, the piled-up top window, the short chunks of small passes - a chain of 1-2 additions on every split bucket at once;
+// the cooperative tree below, a full pass + grid barrier per level, stays for buckets with many chunks: equal scalars, carries of small scalars)
+__global__ void __launch_bounds__(128) k_msm_merge_serial(g1_xyzz* partial, const unsigned* items, const unsigned* item_off, size_t nbuckets, const unsigned* n_items) {
+    const unsigned max_chunks = n_items[2];
+    if (max_chunks <= 1 || max_chunks > MSM_SERIAL_MERGE) return;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < nbuckets; b += stride) {
+        const unsigned k = items[b];
+        if (k < 2) continue;
+        g1_xyzz* pb = partial + item_off[b];
+        g1_xyzz acc = ld_xyzz(pb);
+        for (unsigned q = 1; q < k; ++q) acc = acc.add(ld_xyzz(pb + q));
+        st_xyzz(pb, acc);
+    }
+}
+
 // ---------------------------------------------------------------- 3c. buckets split into several chunks: pairwise tree over their partial sums
 // round with stride s: chunk q of a bucket (q a multiple of 2s) absorbs chunk q + s; after ceil(log2 k) rounds chunk 0 holds the bucket sum.
 // One cooperative launch runs every round (grid.sync between rounds) and returns at once when no bucket was split.
 __global__ void __launch_bounds__(128) k_msm_merge_chunks(g1_xyzz* partial, const unsigned* items, const unsigned* item_off, const unsigned* item_bucket,
                                                           const unsigned* n_items) {
     const unsigned max_chunks = n_items[2];    // largest chunk count of any bucket (0 when none exceeds one chunk)
-    if (max_chunks <= 1) return;
+    if (max_chunks <= MSM_SERIAL_MERGE) return;   // few chunks per bucket: k_msm_merge_serial has added them
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     const unsigned M = n_items[0];
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -577,7 +595,13 @@ size_t msm_scratch_bytes(size_t nmax, int K, unsigned c, bool shared, MsmLayout*
     const unsigned sets = (unsigned)K * (shared ? 1u : W);            // bucket sets = windows seen by the reduction
     const size_t nb = (size_t)1 << (c - 1), nbuckets = sets * nb;
     const size_t entries = (size_t)K * W * nmax;
-    const size_t max_items = nbuckets + entries / MSM_CHUNK + 1;
+    // Work-item length.  Many buckets (>= MSM_ITEMS_TARGET): one item per bucket is parallelism enough, long chunks keep the merges rare.  Few buckets (the per-rank shapes of a
+    // sharded proof: 2^16 buckets per set): shorter chunks, so that the accumulation has ~3 waves of items to balance (2^17 ops per rank: 0.89 -> 0.68 ms) - as long as a bucket
+    // still splits into <= ~3 chunks, which k_msm_merge_serial adds with one thread per bucket
+    unsigned chunk = MSM_CHUNK;
+    if (const char* env = getenv("TSGPU_MSM_CHUNK")) { int v = atoi(env); if (v >= 1 && v <= (int)MSM_CHUNK) chunk = (unsigned)v; }   // experiments
+    else while (chunk > 16 && std::max(nbuckets, entries / chunk) + nbuckets / 2 < MSM_ITEMS_TARGET && entries / nbuckets < (size_t)chunk) chunk >>= 1;
+    const size_t max_items = nbuckets + entries / chunk + 1;
     // span of the window reduction: long spans when there are many buckets (throughput-bound), short ones when the dependency
     // chain of 2 x span additions would dominate (aim at >= 32768 span threads)
     unsigned span = MSM_RED_SPAN;
@@ -589,7 +613,7 @@ size_t msm_scratch_bytes(size_t nmax, int K, unsigned c, bool shared, MsmLayout*
     unsigned nbits = 0; while (((size_t)span << nbits) < nb) ++nbits;   // spans per bucket set = 2^nbits
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
-    L->c = c; L->W = W; L->K = (unsigned)K; L->sets = sets; L->shared = shared; L->nmax = nmax;
+    L->c = c; L->W = W; L->K = (unsigned)K; L->sets = sets; L->shared = shared; L->nmax = nmax; L->chunk = chunk;
     L->nbuckets = nbuckets; L->max_items = max_items; L->blocks_per_window = (unsigned)(nb / span); L->span = span; L->span_bits = nbits;
     L->dig = take(entries * 4);
     L->sorted = take(entries * 4);
@@ -645,16 +669,16 @@ cudaError_t msm_run(const MsmJob* jobs, int K, const MsmLayout& L, unsigned char
     for (int k = 0; k < K; ++k)
         k_msm_scatter<<<gridfor((size_t)L.W * jobs[k].n, 256, cap), 256, 0, s>>>(dig + (size_t)k * L.W * L.nmax, jobs[k].n, L.c, L.W, offsets + k * buckets_per_job,
                                                                                  cursor + k * buckets_per_job, sorted, set_stride, L.shared ? jobs[k].stride : 0);
-    k_msm_item_counts<<<gridfor(L.nbuckets, 256, cap), 256, 0, s>>>(hist, L.nbuckets, items, n_items + 2);
+    k_msm_item_counts<<<gridfor(L.nbuckets, 256, cap), 256, 0, s>>>(hist, L.nbuckets, L.chunk, items, n_items + 2);
     exclusive_scan_u32(items, item_off, L.nbuckets, (unsigned*)(scratch + L.scan_tmp), n_items, s);
-    k_msm_item_fill<<<gridfor(L.nbuckets, 256, cap), 256, 0, s>>>(items, item_off, hist, L.nbuckets, item_bucket, len_hist);
+    k_msm_item_fill<<<gridfor(L.nbuckets, 256, cap), 256, 0, s>>>(items, item_off, hist, L.nbuckets, L.chunk, item_bucket, len_hist);
     k_msm_len_scan<<<1, SCAN_THREADS, 0, s>>>(len_hist, len_off);
-    k_msm_order<<<gridfor(L.max_items, 256 * ORDER_TILE, cap), 256, 0, s>>>(hist, item_off, item_bucket, n_items, len_off, len_cursor, order);
+    k_msm_order<<<gridfor(L.max_items, 256 * ORDER_TILE, cap), 256, 0, s>>>(hist, item_off, item_bucket, n_items, L.chunk, len_off, len_cursor, order);
     if (ev) cudaEventRecord(ev[1], s);
     {
         // 16 blocks per SM, scheduled dynamically: measured faster than one persistent resident wave with a static deal (profiles/r01_kernel_variants.md)
         k_msm_accumulate<<<gridfor(L.max_items, MSM_ACC_THREADS, (size_t)sm_count * 16), MSM_ACC_THREADS, 0, s>>>(
-            bases, (unsigned)buckets_per_job, sorted, hist, offsets, item_off, item_bucket, n_items, order, partial);
+            bases, (unsigned)buckets_per_job, sorted, hist, offsets, item_off, item_bucket, n_items, L.chunk, order, partial);
     }
     if (ev) cudaEventRecord(ev[2], s);
     {
@@ -663,6 +687,7 @@ cudaError_t msm_run(const MsmJob* jobs, int K, const MsmLayout& L, unsigned char
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&coop_blocks_per_sm, k_msm_merge_chunks, 128, 0) != cudaSuccess || coop_blocks_per_sm < 1) coop_blocks_per_sm = 1;
             if (coop_blocks_per_sm > 4) coop_blocks_per_sm = 4;
         }
+        k_msm_merge_serial<<<gridfor(L.nbuckets, 128, (size_t)sm_count * 16), 128, 0, s>>>(partial, items, item_off, L.nbuckets, n_items);
         void* args[] = {(void*)&partial, (void*)&items, (void*)&item_off, (void*)&item_bucket, (void*)&n_items};
         if ((e = cudaLaunchCooperativeKernel((const void*)k_msm_merge_chunks, dim3(sm_count * coop_blocks_per_sm), dim3(128), args, 0, s))) return e;
     }
@@ -686,7 +711,7 @@ cudaError_t msm_run(const MsmJob* jobs, int K, const MsmLayout& L, unsigned char
         k_msm_bit_finish<<<dim3(slots, L.sets), MSM_FIN_THREADS, 0, s>>>(parts, P, L.span_bits, k0, wout, g_msm_quad_tree);
     }
     if (ev) cudaEventRecord(ev[4], s);
-    if (launches) *launches += 16 + 2 * (unsigned)K;
+    if (launches) *launches += 17 + 2 * (unsigned)K;
     return cudaGetLastError();
 }
 

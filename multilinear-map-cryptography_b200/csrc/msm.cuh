@@ -9,6 +9,8 @@ namespace tsg {
 #define TSG_MSM_CHUNK 64
 #endif
 constexpr unsigned MSM_CHUNK = TSG_MSM_CHUNK;       // max entries one work item adds into its accumulator (bounds the serial chain of one thread)
+constexpr unsigned MSM_SERIAL_MERGE = 6;  // passes whose buckets split into at most this many chunks merge them with one thread per bucket (k_msm_merge_serial); beyond it k_msm_merge_chunks runs its tree
+constexpr size_t MSM_ITEMS_TARGET = 240000; // ~3 resident waves of accumulation threads (148 SMs x 512): below it a pass shortens its chunks (msm_scratch_bytes)
 constexpr int MSM_ACC_THREADS = 128;
 constexpr unsigned MSM_RED_SPAN = 32;     // most buckets per thread in the window reduction (2 x span additions deep; the bit-decomposed tail costs
                                           // log2(buckets / span) / 2 additions per span); small bucket sets use shorter spans to keep the chain short
@@ -30,7 +32,7 @@ struct MsmJob {
 struct MsmBases { const g1_affine* p[MSM_MAX_BATCH]; };
 
 struct MsmLayout {
-    unsigned c, W, K, sets, blocks_per_window, span, span_bits;   // sets = bucket sets = K * (shared ? 1 : W); blocks_per_window = spans per set = 2^span_bits
+    unsigned c, W, K, sets, blocks_per_window, span, span_bits, chunk;   // chunk: entries per work item (<= MSM_CHUNK)   // sets = bucket sets = K * (shared ? 1 : W); blocks_per_window = spans per set = 2^span_bits
     bool shared;                                                 // all W digit positions of a job feed one bucket set (needs the precomputed tables)
     size_t nmax, nbuckets, max_items;
     size_t dig, sorted, hist, offsets, cursor, items, item_off, item_bucket, n_items, order, len_hist, scan_tmp, partial, blockres, bits, window_out;
