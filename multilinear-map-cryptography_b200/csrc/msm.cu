@@ -617,15 +617,16 @@ size_t msm_scratch_bytes(size_t nmax, int K, unsigned c, bool shared, MsmLayout*
     L->nbuckets = nbuckets; L->max_items = max_items; L->blocks_per_window = (unsigned)(nb / span); L->span = span; L->span_bits = nbits;
     L->dig = take(entries * 4);
     L->sorted = take(entries * 4);
-    L->hist = take(nbuckets * 4);
-    L->offsets = take(nbuckets * 4);
+    L->hist = take(nbuckets * 4);                  // hist .. len_hist are contiguous: msm_run clears them with one memset
     L->cursor = take(nbuckets * 4);
+    L->n_items = take(256);
+    L->len_hist = take(3 * (MSM_CHUNK + 1) * 4);   // length histogram, offsets, cursors
+    L->zero_bytes = off - L->hist;
+    L->offsets = take(nbuckets * 4);
     L->items = take(nbuckets * 4);
     L->item_off = take(nbuckets * 4);
     L->item_bucket = take(max_items * 4);
-    L->n_items = take(256);
     L->order = take(max_items * 4);
-    L->len_hist = take(3 * (MSM_CHUNK + 1) * 4);   // length histogram, offsets, cursors
     L->scan_tmp = take((nbuckets / 1024 + 64) * 4);
     L->partial = take(max_items * sizeof(g1_xyzz));
     L->blockres = take((size_t)2 * sets * L->blocks_per_window * sizeof(g1_xyzz));   // span sums R, then L
@@ -649,13 +650,10 @@ cudaError_t msm_run(const MsmJob* jobs, int K, const MsmLayout& L, unsigned char
     g1_jac* wout = (g1_jac*)(scratch + L.window_out);
     cudaError_t e;
     if (ev) cudaEventRecord(ev[0], s);
-    // hist and cursor are adjacent-independent regions: clear both
-    if ((e = cudaMemsetAsync(hist, 0, L.nbuckets * 4, s))) return e;
-    if ((e = cudaMemsetAsync(cursor, 0, L.nbuckets * 4, s))) return e;
+    // bucket histogram, scatter cursors, counters and the length histogram lie side by side: one clear
+    if ((e = cudaMemsetAsync(hist, 0, L.zero_bytes, s))) return e;
     unsigned* order = (unsigned*)(scratch + L.order);
     unsigned* len_hist = (unsigned*)(scratch + L.len_hist); unsigned* len_off = len_hist + (MSM_CHUNK + 1); unsigned* len_cursor = len_off + (MSM_CHUNK + 1);
-    if ((e = cudaMemsetAsync(len_hist, 0, 3 * (MSM_CHUNK + 1) * 4, s))) return e;
-    if ((e = cudaMemsetAsync(n_items, 0, 256, s))) return e;
     const size_t cap = (size_t)sm_count * 8;
     const unsigned nb = 1u << (L.c - 1);
     const unsigned set_stride = L.shared ? 0u : nb;
@@ -711,7 +709,7 @@ cudaError_t msm_run(const MsmJob* jobs, int K, const MsmLayout& L, unsigned char
         k_msm_bit_finish<<<dim3(slots, L.sets), MSM_FIN_THREADS, 0, s>>>(parts, P, L.span_bits, k0, wout, g_msm_quad_tree);
     }
     if (ev) cudaEventRecord(ev[4], s);
-    if (launches) *launches += 17 + 2 * (unsigned)K;
+    if (launches) *launches += 17 + 2 * (unsigned)K;   // kernels only (the clear is a memset)
     return cudaGetLastError();
 }
 

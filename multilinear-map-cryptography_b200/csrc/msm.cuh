@@ -36,6 +36,7 @@ struct MsmLayout {
     bool shared;                                                 // all W digit positions of a job feed one bucket set (needs the precomputed tables)
     size_t nmax, nbuckets, max_items;
     size_t dig, sorted, hist, offsets, cursor, items, item_off, item_bucket, n_items, order, len_hist, scan_tmp, partial, blockres, bits, window_out;
+    size_t zero_bytes;   // hist, cursor, n_items, len_hist: one contiguous block cleared at the start of a pass
 };
 
 void msm_set_quad_tree(int on);
