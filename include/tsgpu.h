@@ -445,6 +445,10 @@ int tsgpu_kzg_batch_verify(const tsgpu_params* params, const tsgpu_g1* commitmen
 /* pairing self-test hooks: prod_i e(a_i G1, b_i G2) == 1 ?;  G2 generator on the twist and of order r */
 int tsgpu_pairing_product_of_generators_is_one(const tsgpu_fr* a, const tsgpu_fr* b, size_t n);
 int tsgpu_g2_generator_checks(void);
+/* prod_i e(P_i, Q_i) == 1 for arbitrary points in canonical coordinates (4 little-endian 64-bit limbs per Fq element): g1 = n x (x, y), g2 = n x (x.c0, x.c1, y.c0, y.c1), all-zero = identity;
+ * -1 when a coordinate is not reduced or a point is off its curve.  The pairing is the one behind KZGCommitment::verify (src/commitments.rs:211-226: Bn254::pairing); this hook lets the
+ * published alt_bn128 pairing-check vectors (EIP-197) run against it. */
+int tsgpu_pairing_check_points(const uint64_t* g1, const uint64_t* g2, size_t n);
 int tsgpu_pairing_self_check(void);   /* split final exponentiation == plain power, Fq12 inverse / square / Frobenius, Jacobian G2 multiplication: 1 when all agree */
 
 size_t tsgpu_proof_num_rounds(const tsgpu_proof* p);

@@ -593,6 +593,33 @@ int tsgpu_pairing_product_of_generators_is_one(const tsgpu_fr* a, const tsgpu_fr
     }
     return pairing_product_is_one(P, Q) ? 1 : 0;
 }
+// prod_i e(P_i, Q_i) == 1 ? for ARBITRARY points given by their canonical coordinates (four little-endian 64-bit limbs each): g1 = n x (x, y), (0, 0) = the identity;
+// g2 = n x (x.c0, x.c1, y.c0, y.c1) over Fq2 = Fq[u] / (u^2 + 1), all zero = the identity.  -1: a coordinate is not reduced or a point is not on its curve; else 1 / 0.
+// Lets published pairing-check vectors (EIP-197 / alt_bn128 precompile tests) run against this pairing (tests/test_published_kats.py).
+int tsgpu_pairing_check_points(const uint64_t* g1, const uint64_t* g2, size_t n) {
+    if ((!g1 || !g2) && n) return -1;
+    std::vector<G1J> P; std::vector<G2A> Q;
+    for (size_t i = 0; i < n; ++i) {
+        const uint64_t* a = g1 + 8 * i; const uint64_t* b = g2 + 16 * i;
+        for (int k = 0; k < 2; ++k) if (Fq64::geq_mod(a + 4 * k)) return -1;
+        for (int k = 0; k < 4; ++k) if (Fq64::geq_mod(b + 4 * k)) return -1;
+        uint64_t any1 = 0, any2 = 0;
+        for (int k = 0; k < 8; ++k) any1 |= a[k];
+        for (int k = 0; k < 16; ++k) any2 |= b[k];
+        G1J p = G1J::identity();
+        if (any1) { p.x = Fq64::from_raw(a) * Fq64::r2(); p.y = Fq64::from_raw(a + 4) * Fq64::r2(); p.z = Fq64::one(); }
+        if (!p.is_valid()) return -1;
+        G2A q = G2A::infinity();
+        if (any2) {
+            q.x = Fq2{Fq64::from_raw(b) * Fq64::r2(), Fq64::from_raw(b + 4) * Fq64::r2()};
+            q.y = Fq2{Fq64::from_raw(b + 8) * Fq64::r2(), Fq64::from_raw(b + 12) * Fq64::r2()};
+            q.inf = false;
+        }
+        if (!q.on_curve()) return -1;
+        P.push_back(p); Q.push_back(q);
+    }
+    return pairing_product_is_one(P, Q) ? 1 : 0;
+}
 // self-check of the faster pairing pieces: the split final exponentiation equals the plain power by (p^12 - 1) / r, the Fq12 inverse and
 // the symmetric square agree with the product, the Jacobian G2 scalar multiplication equals repeated affine additions
 int tsgpu_pairing_self_check(void) {

@@ -163,3 +163,39 @@ def test_vectors_from_real_arkworks_when_present(oracle):
             assert ours[key] == val, key
             checked += 1
     assert checked >= 20
+
+
+def test_bn254_pairing_check_vector_from_the_alt_bn128_precompile_tests(tsgpu):
+    """EIP-197 pairing check e(P1, Q1) e(P2, Q2) == 1 on points this repository did not produce: the 384-byte input of go-ethereum's `bn256Pairing` precompile test
+    "jeff1" (expected output 1; the second G2 point is the standard generator).  Encoding there: big-endian 32-byte words, G1 = (x, y), G2 = (x.im, x.re, y.im, y.re).
+    The product must be one as published, stop being one when a point is negated or swapped for another valid point, and off-curve / unreduced input must be refused.
+    (A product check is invariant under powers of the pairing, so this pins bilinearity on foreign points, not the GT element itself.)"""
+    import ctypes as C
+    words = """1c76476f4def4bb94541d57ebba1193381ffa7aa76ada664dd31c16024c43f59 3034dd2920f673e204fee2811c678745fc819b55d3e9d294e45c9b03a76aef41
+               209dd15ebff5d46c4bd888e51a93cf99a7329636c63514396b4a452003a35bf7 04bf11ca01483bfa8b34b43561848d28905960114c8ac04049af4b6315a41678
+               2bb8324af6cfc93537a2ad1a445cfd0ca2a71acd7ac41fadbf933c2a51be344d 120a2a4cf30c1bf9845f20c6fe39e07ea2cce61f0c9bb048165fe5e4de877550
+               111e129f1cf1097710d41c4ac70fcdfa5ba2023c6ff1cbeac322de49d1b6df7c 2032c61a830e3c17286de9462bf242fca2883585b93870a73853face6a6bf411
+               198e9393920d483a7260bfb731fb5d25f1aa493335a9e71297e485b7aef312c2 1800deef121f1e76426a00665e5c4479674322d4f75edadd46debd5cd992f6ed
+               090689d0585ff075ec9e99ad690c3395bc4b313370b38ef355acdadcd122975b 12c85ea5db8c6deb4aab71808dcb408fe3d1e7690c43d37b4ce6cc0166fa7daa""".split()
+    w = [int(x, 16) for x in words]
+    P_MOD = 21888242871839275222246405745257275088696311157297823662689037894645226208583
+
+    def limbs(vals):
+        return np.array([(v >> (64 * k)) & 0xFFFFFFFFFFFFFFFF for v in vals for k in range(4)], dtype=np.uint64)
+
+    def check(g1_pts, g2_pts):
+        g1 = limbs([c for pt in g1_pts for c in pt]); g2 = limbs([c for pt in g2_pts for c in pt])
+        return tsgpu.lib().tsgpu_pairing_check_points(g1.ctypes.data_as(C.c_void_p), g2.ctypes.data_as(C.c_void_p), C.c_size_t(len(g1_pts)))
+
+    p1, p2 = (w[0], w[1]), (w[6], w[7])
+    q1, q2 = (w[3], w[2], w[5], w[4]), (w[9], w[8], w[11], w[10])          # (re, im) order of the hook
+    assert check([p1, p2], [q1, q2]) == 1
+    assert check([p2, p1], [q2, q1]) == 1
+    assert check([p1], [q1]) == 0 and check([p2], [q2]) == 0              # each factor alone is not one
+    assert check([(p1[0], P_MOD - p1[1]), p2], [q1, q2]) == 0             # -P1
+    assert check([p1, p2], [q2, q2]) == 0                                  # another valid G2 point
+    assert check([p1, p1], [q1, (q1[0], q1[1], P_MOD - q1[2], (P_MOD - q1[3]) % P_MOD)]) == 1    # e(P, Q) e(P, -Q) = 1
+    assert check([(0, 0), p2], [q1, (0, 0, 0, 0)]) == 1                   # identities contribute one
+    assert check([(p1[0], p1[1] + 1), p2], [q1, q2]) == -1                # off the curve
+    assert check([(p1[0] + P_MOD, p1[1]), p2], [q1, q2]) == -1            # not reduced
+    assert check([p1, p2], [(q1[0] + 1, q1[1], q1[2], q1[3]), q2]) == -1  # G2 point off the twist
