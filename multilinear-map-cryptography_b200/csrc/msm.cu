@@ -171,13 +171,15 @@ __global__ void k_msm_scatter(const unsigned* dig, size_t n, unsigned c, unsigne
 }
 
 // ---------------------------------------------------------------- work items: slices of at most MSM_CHUNK entries
-__global__ void k_msm_item_counts(const unsigned* hist, size_t nbuckets, unsigned chunk, unsigned* items, unsigned* max_chunks) {
+// max_chunks[0] = largest chunk count of a bucket, max_chunks[1] = number of buckets with more than MSM_SERIAL_MERGE chunks, listed in heavy[] (any order)
+__global__ void k_msm_item_counts(const unsigned* hist, size_t nbuckets, unsigned chunk, unsigned* items, unsigned* max_chunks, unsigned* heavy) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     unsigned mx = 0;
     for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < nbuckets; b += stride) {
         unsigned k = (hist[b] + chunk - 1) / chunk;
         items[b] = k;
         mx = k > mx ? k : mx;
+        if (k > MSM_SERIAL_MERGE) heavy[atomicAdd(max_chunks + 1, 1u)] = (unsigned)b;
     }
     mx = __reduce_max_sync(0xffffffffu, mx);
     if ((threadIdx.x & 31) == 0 && mx > 1) atomicMax(max_chunks, mx);
@@ -287,11 +289,11 @@ __global__ void __launch_bounds__(MSM_ACC_THREADS) k_msm_accumulate(const MsmBas
 // the cooperative tree below, a full pass + grid barrier per level, stays for buckets with many chunks: equal scalars, carries of small scalars)
 __global__ void __launch_bounds__(128) k_msm_merge_serial(g1_xyzz* partial, const unsigned* items, const unsigned* item_off, size_t nbuckets, const unsigned* n_items) {
     const unsigned max_chunks = n_items[2];
-    if (max_chunks <= 1 || max_chunks > MSM_SERIAL_MERGE) return;
+    if (max_chunks <= 1 || max_chunks > MSM_BLOCK_MERGE) return;   // beyond MSM_BLOCK_MERGE the cooperative tree merges every bucket
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < nbuckets; b += stride) {
         const unsigned k = items[b];
-        if (k < 2) continue;
+        if (k < 2 || k > MSM_SERIAL_MERGE) continue;               // heavier buckets: k_msm_merge_heavy
         g1_xyzz* pb = partial + item_off[b];
         g1_xyzz acc = ld_xyzz(pb);
         for (unsigned q = 1; q < k; ++q) acc = acc.add(ld_xyzz(pb + q));
@@ -305,7 +307,7 @@ __global__ void __launch_bounds__(128) k_msm_merge_serial(g1_xyzz* partial, cons
 __global__ void __launch_bounds__(128) k_msm_merge_chunks(g1_xyzz* partial, const unsigned* items, const unsigned* item_off, const unsigned* item_bucket,
                                                           const unsigned* n_items) {
     const unsigned max_chunks = n_items[2];    // largest chunk count of any bucket (0 when none exceeds one chunk)
-    if (max_chunks <= MSM_SERIAL_MERGE) return;   // few chunks per bucket: k_msm_merge_serial has added them
+    if (max_chunks <= MSM_BLOCK_MERGE) return;   // k_msm_merge_serial / k_msm_merge_heavy have merged every split bucket
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     const unsigned M = n_items[0];
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -397,6 +399,30 @@ __device__ __forceinline__ void quad_tree_sum(g1_xyzz* sh, unsigned n, fq_t* scr
                 quad_add(sh + i, sh + i, sh + i + s, scr, act);
             }
         }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------- 3c''. buckets split into MANY chunks (but at most MSM_BLOCK_MERGE): one BLOCK per listed bucket
+// The piled-up top window of a large MSM (2^24 points, c = 22: 2^24 entries on 2^11 buckets = 128 chunks each) and short scalars with a narrow top window land here.
+// Every thread adds a strided share of the bucket's partial sums, the 128 results meet in a lane-quad tree in shared memory.  The cooperative tree, which scans ALL work
+// items once per level (7 levels x 5 M items at 2^24 points: 1.9 ms), is left for the degenerate passes (equal scalars: one bucket with thousands of chunks).
+constexpr int MSM_HEAVY_THREADS = 128;
+__global__ void __launch_bounds__(MSM_HEAVY_THREADS) k_msm_merge_heavy(g1_xyzz* partial, const unsigned* items, const unsigned* item_off, const unsigned* heavy, const unsigned* n_items) {
+    const unsigned max_chunks = n_items[2], n_heavy = n_items[3];
+    if (max_chunks <= MSM_SERIAL_MERGE || max_chunks > MSM_BLOCK_MERGE) return;
+    __shared__ g1_xyzz sh[MSM_HEAVY_THREADS];
+    __shared__ fq_t scr[(MSM_HEAVY_THREADS / 4) * QUAD_SLOTS];
+    for (unsigned h = blockIdx.x; h < n_heavy; h += gridDim.x) {
+        const unsigned b = heavy[h], k = items[b];
+        g1_xyzz* pb = partial + item_off[b];
+        g1_xyzz acc = g1_xyzz::identity();
+        for (unsigned i = threadIdx.x; i < k; i += MSM_HEAVY_THREADS) acc = acc.add(ld_xyzz(pb + i));
+        sh[threadIdx.x] = acc;
+        __syncthreads();
+        unsigned m = 1; while (m < k && m < (unsigned)MSM_HEAVY_THREADS) m <<= 1;   // block-uniform: the tree spans the slots that hold a sum
+        quad_tree_sum(sh, m, scr);   // ends on a block barrier
+        if (threadIdx.x == 0) st_xyzz(pb, sh[0]);
         __syncthreads();
     }
 }
@@ -623,6 +649,7 @@ size_t msm_scratch_bytes(size_t nmax, int K, unsigned c, bool shared, MsmLayout*
     L->len_hist = take(3 * (MSM_CHUNK + 1) * 4);   // length histogram, offsets, cursors
     L->zero_bytes = off - L->hist;
     L->offsets = take(nbuckets * 4);
+    L->heavy = take(nbuckets * 4);                 // buckets with more than MSM_SERIAL_MERGE chunks (k_msm_item_counts)
     L->items = take(nbuckets * 4);
     L->item_off = take(nbuckets * 4);
     L->item_bucket = take(max_items * 4);
@@ -667,7 +694,7 @@ cudaError_t msm_run(const MsmJob* jobs, int K, const MsmLayout& L, unsigned char
     for (int k = 0; k < K; ++k)
         k_msm_scatter<<<gridfor((size_t)L.W * jobs[k].n, 256, cap), 256, 0, s>>>(dig + (size_t)k * L.W * L.nmax, jobs[k].n, L.c, L.W, offsets + k * buckets_per_job,
                                                                                  cursor + k * buckets_per_job, sorted, set_stride, L.shared ? jobs[k].stride : 0);
-    k_msm_item_counts<<<gridfor(L.nbuckets, 256, cap), 256, 0, s>>>(hist, L.nbuckets, L.chunk, items, n_items + 2);
+    k_msm_item_counts<<<gridfor(L.nbuckets, 256, cap), 256, 0, s>>>(hist, L.nbuckets, L.chunk, items, n_items + 2, (unsigned*)(scratch + L.heavy));
     exclusive_scan_u32(items, item_off, L.nbuckets, (unsigned*)(scratch + L.scan_tmp), n_items, s);
     k_msm_item_fill<<<gridfor(L.nbuckets, 256, cap), 256, 0, s>>>(items, item_off, hist, L.nbuckets, L.chunk, item_bucket, len_hist);
     k_msm_len_scan<<<1, SCAN_THREADS, 0, s>>>(len_hist, len_off);
@@ -686,6 +713,7 @@ cudaError_t msm_run(const MsmJob* jobs, int K, const MsmLayout& L, unsigned char
             if (coop_blocks_per_sm > 4) coop_blocks_per_sm = 4;
         }
         k_msm_merge_serial<<<gridfor(L.nbuckets, 128, (size_t)sm_count * 16), 128, 0, s>>>(partial, items, item_off, L.nbuckets, n_items);
+        k_msm_merge_heavy<<<sm_count * 4, MSM_HEAVY_THREADS, 0, s>>>(partial, items, item_off, (const unsigned*)(scratch + L.heavy), n_items);
         void* args[] = {(void*)&partial, (void*)&items, (void*)&item_off, (void*)&item_bucket, (void*)&n_items};
         if ((e = cudaLaunchCooperativeKernel((const void*)k_msm_merge_chunks, dim3(sm_count * coop_blocks_per_sm), dim3(128), args, 0, s))) return e;
     }
@@ -709,7 +737,7 @@ cudaError_t msm_run(const MsmJob* jobs, int K, const MsmLayout& L, unsigned char
         k_msm_bit_finish<<<dim3(slots, L.sets), MSM_FIN_THREADS, 0, s>>>(parts, P, L.span_bits, k0, wout, g_msm_quad_tree);
     }
     if (ev) cudaEventRecord(ev[4], s);
-    if (launches) *launches += 17 + 2 * (unsigned)K;   // kernels only (the clear is a memset)
+    if (launches) *launches += 18 + 2 * (unsigned)K;   // kernels only (the clear is a memset)
     return cudaGetLastError();
 }
 

@@ -8,8 +8,10 @@ namespace tsg {
 #ifndef TSG_MSM_CHUNK
 #define TSG_MSM_CHUNK 64
 #endif
-constexpr unsigned MSM_CHUNK = TSG_MSM_CHUNK;       // max entries one work item adds into its accumulator (bounds the serial chain of one thread)
-constexpr unsigned MSM_SERIAL_MERGE = 6;  // passes whose buckets split into at most this many chunks merge them with one thread per bucket (k_msm_merge_serial); beyond it k_msm_merge_chunks runs its tree
+constexpr unsigned MSM_CHUNK = TSG_MSM_CHUNK;       // LARGEST number of entries one work item adds into its accumulator (bounds the serial chain of one thread; sizes the length histogram);
+                                                    // the length a pass uses (16, 32 or 64) is chosen in msm_scratch_bytes
+constexpr unsigned MSM_SERIAL_MERGE = 16;  // passes whose buckets split into at most this many chunks merge them with one thread per bucket (k_msm_merge_serial)
+constexpr unsigned MSM_BLOCK_MERGE = 2048; // ... up to this many chunks one block per bucket (k_msm_merge_heavy)
 constexpr size_t MSM_ITEMS_TARGET = 240000; // ~3 resident waves of accumulation threads (148 SMs x 512): below it a pass shortens its chunks (msm_scratch_bytes)
 constexpr int MSM_ACC_THREADS = 128;
 constexpr unsigned MSM_RED_SPAN = 32;     // most buckets per thread in the window reduction (2 x span additions deep; the bit-decomposed tail costs
@@ -36,6 +38,7 @@ struct MsmLayout {
     bool shared;                                                 // all W digit positions of a job feed one bucket set (needs the precomputed tables)
     size_t nmax, nbuckets, max_items;
     size_t dig, sorted, hist, offsets, cursor, items, item_off, item_bucket, n_items, order, len_hist, scan_tmp, partial, blockres, bits, window_out;
+    size_t heavy;        // list of the buckets k_msm_merge_heavy handles
     size_t zero_bytes;   // hist, cursor, n_items, len_hist: one contiguous block cleared at the start of a pass
 };
 

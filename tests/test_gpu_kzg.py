@@ -160,13 +160,15 @@ def test_commit_edge_scalars_table_mode(ctx, tsgpu, oracle, srs_small):
 @pytest.mark.parametrize("chunk", [1, 2, 5, 16, 64])
 def test_commit_every_chunk_length_and_merge_path(ctx, tsgpu, oracle, srs_small, chunk, monkeypatch):
     """work-item length (entries one accumulation thread adds; chosen per pass from the bucket count, csrc/msm.cu msm_scratch_bytes) forced through TSGPU_MSM_CHUNK:
-    buckets split into up to MSM_SERIAL_MERGE chunks are merged by one thread per bucket (k_msm_merge_serial), more by the cooperative tree (k_msm_merge_chunks);
+    buckets split into up to MSM_SERIAL_MERGE chunks are merged by one thread per bucket (k_msm_merge_serial), up to MSM_BLOCK_MERGE by one block per bucket
+    (k_msm_merge_heavy), more by the cooperative tree (k_msm_merge_chunks);
     every combination returns the oracle's group element - uniform scalars, seven distinct scalars (heavy buckets) and short scalars"""
     monkeypatch.setenv("TSGPU_MSM_CHUNK", str(chunk))
     srs, ref = srs_small
     n = 4096
     aff = oracle.g1_batch_to_affine(ref[:n])
-    cases = [oracle.chacha_fr_rand(seed_bytes(77), n).reshape(n, 4), oracle.fr_from_ints([i % 7 for i in range(n)]), oracle.fr_from_ints([(i * 2654435761) % (1 << 40) for i in range(n)])]
+    cases = [oracle.chacha_fr_rand(seed_bytes(77), n).reshape(n, 4), oracle.fr_from_ints([i % 7 for i in range(n)]), oracle.fr_from_ints([(i * 2654435761) % (1 << 40) for i in range(n)]),
+             oracle.fr_from_ints([123456789] * n)]   # one bucket per window holds every point: 4096 one-entry chunks run the cooperative tree, 2048 and fewer the block-per-bucket merge
     for poly in cases:
         got = tsgpu.KZGCommitment.commit(srs, poly)
         assert tsgpu.g1_compress(got) == oracle.g1_compress(oracle.msm_pippenger(aff, poly))
