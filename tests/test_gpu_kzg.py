@@ -40,6 +40,18 @@ def test_srs_upload_roundtrip(ctx, oracle, srs_small):
     assert oracle.g1_compress(srs.download()) == oracle.g1_compress(pts)
 
 
+def test_msm_reproduces_the_published_alt_bn128_product(ctx, tsgpu, oracle):
+    """EIP-196 scalar-multiplication vector "chfast1" (tests/test_published_kats.py) through the device MSM: an SRS made of copies of the published point,
+    scalars that sum to the published scalar -> the published product"""
+    from test_published_kats import CHFAST1_POINT, CHFAST1_SCALAR, CHFAST1_PRODUCT
+    P = np.concatenate([oracle.fq_from_ints([CHFAST1_POINT[0]]).reshape(-1), oracle.fq_from_ints([CHFAST1_POINT[1]]).reshape(-1), oracle.fq_from_ints([1]).reshape(-1)])
+    for n in (1, 3, 700):
+        srs = ctx.srs_upload(np.stack([P] * n))
+        ks = [CHFAST1_SCALAR] if n == 1 else [CHFAST1_SCALAR - sum(range(2, n + 1))] + list(range(2, n + 1))
+        got = tsgpu.KZGCommitment.commit(srs, oracle.fr_from_ints(ks))
+        assert oracle.g1_affine_canonical(got) == [CHFAST1_PRODUCT]
+
+
 @pytest.mark.parametrize("n", [0, 1, 2, 3, 31, 32, 100, 1024])
 def test_commit_matches_reference_serial_sum(ctx, tsgpu, oracle, srs_small, n):
     """vs the verbatim commitments.rs:173-177 sum of double-and-add products"""

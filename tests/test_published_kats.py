@@ -118,6 +118,26 @@ def test_bn254_g1_published_points_and_encodings(oracle, tsgpu):
     assert oracle.g1_compress(oracle.g1_add(G, G)) == x2[:31] + bytes([x2[31] | flag])
 
 
+# EIP-196 scalar multiplication on a point that is not the generator: go-ethereum's `bn256ScalarMul` precompile test "chfast1" (input point, 64-bit scalar, expected product)
+CHFAST1_POINT = (0x2bd3e6d0f3b142924f5ca7b49ce5b9d54c4703d7ae5648e61d02268b1a0a9fb7, 0x21611ce0a6af85915e2f1d70300909ce2e49dfad4a4619c8390cae66cefdb204)
+CHFAST1_SCALAR = 0x11138ce750fa15c2
+CHFAST1_PRODUCT = (0x070a8d6a982153cae4be29d434e8faef8a47b274a053f5a4ee2a6c9c13c31e5c, 0x031b8ce914eba3a9ffb989f9cdd5b0f01943074bf4f0f315690ec3cec6981afc)
+
+
+def test_bn254_g1_published_scalar_multiplication(oracle):
+    """the published alt_bn128 product k P (EIP-196 test "chfast1") from the pure-Python restatement and from the C++ oracle's Jacobian double-and-add:
+    pins the G1 group law and `point * scalar` (commitments.rs:173-177, utils.rs:94-102) on a foreign point"""
+    import pyref
+    assert pyref.g1_is_on_curve(CHFAST1_POINT) and pyref.g1_is_on_curve(CHFAST1_PRODUCT)
+    assert pyref.g1_mul(CHFAST1_POINT, CHFAST1_SCALAR) == CHFAST1_PRODUCT
+    P = np.concatenate([oracle.fq_from_ints([CHFAST1_POINT[0]]).reshape(-1), oracle.fq_from_ints([CHFAST1_POINT[1]]).reshape(-1), oracle.fq_from_ints([1]).reshape(-1)])
+    got = oracle.g1_mul(P, oracle.fr_from_ints([CHFAST1_SCALAR])[0])
+    assert oracle.g1_affine_canonical(got) == [CHFAST1_PRODUCT]
+    # and through the CPU Pippenger the GPU MSM is compared with: sum over three copies with scalars k - 5, 2, 3
+    aff = oracle.g1_batch_to_affine(np.stack([P, P, P]))
+    assert oracle.g1_affine_canonical(oracle.msm_pippenger(aff, oracle.fr_from_ints([CHFAST1_SCALAR - 5, 2, 3]))) == [CHFAST1_PRODUCT]
+
+
 def test_fp_rand_masking_and_rejection_branch(oracle):
     """ark-ff 0.4.2 `Fp::rand` (documented behaviour, UNPINNED by any publication): four next_u64 -> the top 2 bits cleared -> accepted as the
     MONTGOMERY representation iff < r, else the next four words.  Some seed below must exercise a rejection."""
