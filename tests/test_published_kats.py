@@ -133,6 +133,14 @@ def test_bn254_g1_published_scalar_multiplication(oracle):
     P = np.concatenate([oracle.fq_from_ints([CHFAST1_POINT[0]]).reshape(-1), oracle.fq_from_ints([CHFAST1_POINT[1]]).reshape(-1), oracle.fq_from_ints([1]).reshape(-1)])
     got = oracle.g1_mul(P, oracle.fr_from_ints([CHFAST1_SCALAR])[0])
     assert oracle.g1_affine_canonical(got) == [CHFAST1_PRODUCT]
+    # EIP-196 point addition on two foreign points (go-ethereum's `bn256Add` test "chfast1")
+    A = (0x18b18acfb4c2c30276db5411368e7185b311dd124691610c5d3b74034e093dc9, 0x063c909c4720840cb5134cb9f59fa749755796819658d32efc0d288198f37266)
+    B = (0x07c2b7f58a84bd6145f00c9c2bc0bb1a187f20ff2c92963a88019e7c6a014eed, 0x06614e20c147e940f2d70da3f74c9a17df361706a4485c742bd6788478fa17d7)
+    C = (0x2243525c5efd4b9c3d3c45ac0ca3fe4dd85e830a4ce6b65fa1eeaee202839703, 0x301d1d33be6da8e509df21cc35964723180eed7532537db9ae5e7d48f195c915)
+    assert pyref.g1_add(A, B) == C == pyref.g1_add(B, A)
+    jac = lambda Q: np.concatenate([oracle.fq_from_ints([Q[0]]).reshape(-1), oracle.fq_from_ints([Q[1]]).reshape(-1), oracle.fq_from_ints([1]).reshape(-1)])
+    assert oracle.g1_affine_canonical(oracle.g1_add(jac(A), jac(B))) == [C]
+    assert oracle.g1_affine_canonical(oracle.msm_pippenger(oracle.g1_batch_to_affine(np.stack([jac(A), jac(B)])), oracle.fr_from_ints([1, 1]))) == [C]
     # and through the CPU Pippenger the GPU MSM is compared with: sum over three copies with scalars k - 5, 2, 3
     aff = oracle.g1_batch_to_affine(np.stack([P, P, P]))
     assert oracle.g1_affine_canonical(oracle.msm_pippenger(aff, oracle.fr_from_ints([CHFAST1_SCALAR - 5, 2, 3]))) == [CHFAST1_PRODUCT]
