@@ -71,11 +71,34 @@ struct F64 {
         return r;
     }
     F64 sqr() const { return *this * *this; }
-    F64 inverse() const {   // Fermat; 0 -> 0
+    F64 inverse_fermat() const {   // a^(p - 2); 0 -> 0.  Kept as the cross-check of inverse() (tsgpu_pairing_self_check)
         uint64_t e[4] = {modl(0) - 2, modl(1), modl(2), modl(3)};
         F64 acc = one();
         for (int i = 255; i >= 0; --i) { acc = acc.sqr(); if ((e[i >> 6] >> (i & 63)) & 1) acc = acc * *this; }
         return acc;
+    }
+    // Binary extended Euclid on the Montgomery representative x = a R (as an integer below p): y = x^-1 mod p, then a^-1 R = y R^2 - two products by R^2.
+    // ~4x faster than the Fermat power (a few hundred 256-bit shifts / subtractions instead of ~380 products); the host inverts on every commitment hash, every
+    // barycentric opening and at every step of the pairing's affine G2 arithmetic.  0 -> 0.
+    F64 inverse() const {
+        if (is_zero()) return *this;
+        uint64_t u[4], v[4], b[4] = {1, 0, 0, 0}, c[4] = {0, 0, 0, 0};
+        memcpy(u, l, 32);
+        for (int i = 0; i < 4; ++i) v[i] = modl(i);
+        auto is_one = [](const uint64_t* a) { return a[0] == 1 && (a[1] | a[2] | a[3]) == 0; };
+        auto shr1 = [](uint64_t* a) { a[0] = (a[0] >> 1) | (a[1] << 63); a[1] = (a[1] >> 1) | (a[2] << 63); a[2] = (a[2] >> 1) | (a[3] << 63); a[3] >>= 1; };
+        auto add_p = [](uint64_t* a) { u128_t cy = 0; for (int i = 0; i < 4; ++i) { cy += (u128_t)a[i] + modl(i); a[i] = (uint64_t)cy; cy >>= 64; } };   // a < p: a + p < 2^255
+        auto sub = [](uint64_t* a, const uint64_t* o) { u128_t br = 0; for (int i = 0; i < 4; ++i) { u128_t d = (u128_t)a[i] - o[i] - br; a[i] = (uint64_t)d; br = (d >> 64) & 1; } return (bool)br; };
+        auto geq = [](const uint64_t* a, const uint64_t* o) { for (int i = 3; i >= 0; --i) { if (a[i] > o[i]) return true; if (a[i] < o[i]) return false; } return true; };
+        // invariants: b x == u, c x == v (mod p); u, v > 0; b, c in [0, p)
+        while (!is_one(u) && !is_one(v)) {
+            while (!(u[0] & 1)) { shr1(u); if (b[0] & 1) add_p(b); shr1(b); }
+            while (!(v[0] & 1)) { shr1(v); if (c[0] & 1) add_p(c); shr1(c); }
+            if (geq(u, v)) { sub(u, v); if (sub(b, c)) add_p(b); }
+            else { sub(v, u); if (sub(c, b)) add_p(c); }
+        }
+        F64 y; memcpy(y.l, is_one(u) ? b : c, 32);
+        return (y * r2()) * r2();
     }
     F64 from_mont() const { F64 o = zero(); o.l[0] = 1; return *this * o; }
 };

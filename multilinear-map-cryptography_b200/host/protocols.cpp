@@ -629,6 +629,19 @@ int tsgpu_pairing_self_check(void) {
     G2A Q = G2A::generator();
     Fq12 f = miller_loop(ax, ay, false, Q);
     if (!(final_exponentiation(f) == final_exponentiation_plain(f))) return 0;
+    {   // the Euclidean field inverse against the Fermat power, both fields: small, large, structured and pseudo-random elements
+        Fq64 xq = Fq64::from_u64(3); Fr64 xr = Fr64::from_u64(5);
+        for (int i = 0; i < 200; ++i) {
+            if (!(xq.inverse() == xq.inverse_fermat()) || !(xq * xq.inverse() == Fq64::one())) return 0;
+            if (!(xr.inverse() == xr.inverse_fermat()) || !(xr * xr.inverse() == Fr64::one())) return 0;
+            xq = xq * xq + Fq64::from_u64(0x9e3779b97f4a7c15ull + i); xr = xr * xr + Fr64::from_u64(0xc2b2ae3d27d4eb4full + i);
+        }
+        const Fq64 eq[] = {Fq64::one(), Fq64::zero() - Fq64::one(), Fq64::from_u64(2), Fq64::from_raw(Fq64::one().l).dbl(), Fq64::r2(), Fq64::from_u64(1).inverse_fermat()};
+        for (const Fq64& e : eq) if (!(e.inverse() == e.inverse_fermat())) return 0;
+        const Fr64 er[] = {Fr64::one(), Fr64::zero() - Fr64::one(), Fr64::from_u64(2), Fr64::r2()};
+        for (const Fr64& e : er) if (!(e.inverse() == e.inverse_fermat())) return 0;
+        if (!Fq64::zero().inverse().is_zero() || !Fr64::zero().inverse().is_zero()) return 0;
+    }
     if (!(f * f.inverse()).is_one()) return 0;
     if (!(f.sqr() == f * f)) return 0;
     if (!(f.frobenius().frobenius().frobenius().frobenius().frobenius().frobenius() == f.conj6())) return 0;   // (f^p)^..6 times = f^(p^6)
