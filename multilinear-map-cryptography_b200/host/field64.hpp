@@ -81,9 +81,10 @@ struct F64 {
     // ~4x faster than the Fermat power (a few hundred 256-bit shifts / subtractions instead of ~380 products); the host inverts on every commitment hash, every
     // barycentric opening and at every step of the pairing's affine G2 arithmetic.  0 -> 0.
     F64 inverse() const {
-        if (is_zero()) return *this;
         uint64_t u[4], v[4], b[4] = {1, 0, 0, 0}, c[4] = {0, 0, 0, 0};
         memcpy(u, l, 32);
+        while (geq_mod(u)) sub_mod(u);   // limbs that arrive over the C ABI need not be reduced (2^256 < 6 p: a few subtractions); a multiple of p has no inverse and would never terminate below
+        if ((u[0] | u[1] | u[2] | u[3]) == 0) return zero();
         for (int i = 0; i < 4; ++i) v[i] = modl(i);
         auto is_one = [](const uint64_t* a) { return a[0] == 1 && (a[1] | a[2] | a[3]) == 0; };
         auto shr1 = [](uint64_t* a) { a[0] = (a[0] >> 1) | (a[1] << 63); a[1] = (a[1] >> 1) | (a[2] << 63); a[2] = (a[2] >> 1) | (a[3] << 63); a[3] >>= 1; };

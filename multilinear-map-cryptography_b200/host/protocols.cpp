@@ -641,6 +641,13 @@ int tsgpu_pairing_self_check(void) {
         const Fr64 er[] = {Fr64::one(), Fr64::zero() - Fr64::one(), Fr64::from_u64(2), Fr64::r2()};
         for (const Fr64& e : er) if (!(e.inverse() == e.inverse_fermat())) return 0;
         if (!Fq64::zero().inverse().is_zero() || !Fr64::zero().inverse().is_zero()) return 0;
+        {   // unreduced limbs (possible only for bytes handed in over the C ABI): p itself -> 0, p + 2 -> the inverse of 2
+            Fq64 m; for (int i = 0; i < 4; ++i) m.l[i] = Fq64::modl(i);
+            if (!m.inverse().is_zero()) return 0;
+            Fq64 m2 = m; m2.l[0] += 2;
+            Fq64 two; two.l[0] = 2; two.l[1] = two.l[2] = two.l[3] = 0;
+            if (!(m2.inverse() == two.inverse())) return 0;
+        }
     }
     if (!(f * f.inverse()).is_one()) return 0;
     if (!(f.sqr() == f * f)) return 0;
