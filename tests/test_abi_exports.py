@@ -85,3 +85,30 @@ def test_both_arms_generate_the_same_trace(tsgpu, oracle):
         if b & 1:
             mem[a % 65536] = c
         assert vals[j] == mem.get(a % 65536, 0)
+
+
+def _prototypes(text, pattern):
+    """name -> number of parameters, from C prototypes or Rust `pub fn` declarations (comments stripped by the caller)"""
+    out = {}
+    for m in re.finditer(pattern, text, flags=re.S):
+        name, args = m.group(1), m.group(2).strip()
+        out[name] = 0 if args in ("", "void") else args.count(",") + 1
+    return out
+
+
+def test_rust_extern_block_agrees_with_the_header():
+    """rust/cuda-sys/src/ffi.rs (never compiled here: no Rust toolchain) must not drift from include/tsgpu.h: every function it declares exists in the header with
+    the same number of parameters, and the entry points of the proving path are all declared (KZG verify stays on arkworks in the Rust wrapper: two pairings on the CPU either way)"""
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "tsgpu.h")).read(), flags=re.S)
+    c = _prototypes(hdr, r"\b(tsgpu_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;")
+    rs = open(os.path.join(ROOT, "rust", "cuda-sys", "src", "ffi.rs")).read()
+    rs = re.sub(r"//[^\n]*", "", rs)
+    r = _prototypes(rs, r"pub fn (tsgpu_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*(?:->[^;]*)?;")
+    assert len(r) > 70
+    unknown = sorted(set(r) - set(c))
+    assert not unknown, f"declared in ffi.rs but not in tsgpu.h: {unknown}"
+    arity = {n: (r[n], c[n]) for n in r if r[n] != c[n]}
+    assert not arity, f"parameter counts differ (ffi.rs, tsgpu.h): {arity}"
+    for n in ("tsgpu_init", "tsgpu_setup_params", "tsgpu_twist_prove", "tsgpu_shout_prove", "tsgpu_twist_verify", "tsgpu_shout_verify", "tsgpu_kzg_commit", "tsgpu_kzg_open",
+              "tsgpu_mle_evaluate", "tsgpu_mle_partial_evaluate", "tsgpu_sc_begin", "tsgpu_sc_round_eval", "tsgpu_sc_bind", "tsgpu_sc_bind_eval_claim", "tsgpu_sc_final"):
+        assert n in r, n
